@@ -1,0 +1,164 @@
+// conv.cu - C-ABI entry points of the convolution layer: operand preparation, dispatch between the
+// tcgen05 implicit-GEMM kernels (conv_tc.cu) and the generic SIMT kernels (conv_simt.cu), and the
+// fused optimizer.  Reference: src/cuda/cuda_conv_layer.cu:319-562, src/cuda/cuda_main.cu:433-475.
+#include "common.cuh"
+
+namespace cb200 {
+extern const char* g_last_conv_impl;
+extern int g_force_simt;
+int conv_forward_simt(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t);
+int conv_dgrad_simt(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, const cb200_activ*, const void*, cudaStream_t);
+int conv_wgrad_simt(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
+int conv_colsum(int dtype, const void* dy, float* out, long long P, int c, cudaStream_t st);
+// tcgen05 path (conv_tc.cu); *_supported() says whether the geometry is taken
+bool conv_tc_fwd_supported(const cb200_conv_desc*);
+bool conv_tc_dgrad_supported(const cb200_conv_desc*);
+bool conv_tc_wgrad_supported(const cb200_conv_desc*);
+int conv_forward_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t);
+int conv_dgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, const cb200_activ*, const void*, cudaStream_t);
+int conv_wgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
+
+// master [out_c][taps*in_c + 1] (column = c*taps + tap, bias last) -> compute operands.
+// One thread per master element; the same mapping is used by the optimizer below.
+template <typename T>
+__device__ __forceinline__ void scatter_weight(float wv, int f, int col, int taps, int in_c, int in_cp, int out_cp,
+                                               T* __restrict__ w_fwd, T* __restrict__ w_bwd, float* __restrict__ bias_w) {
+	if (col == taps * in_c) { bias_w[f] = wv; return; }
+	const int c = col / taps, tap = col - c * taps;
+	w_fwd[((size_t)f * taps + tap) * in_cp + c] = from_f32<T>(wv);
+	w_bwd[((size_t)c * taps + (taps - 1 - tap)) * out_cp + f] = from_f32<T>(wv);
+}
+
+template <typename T>
+__global__ void conv_prepare_kernel(const float* __restrict__ master, T* __restrict__ w_fwd, T* __restrict__ w_bwd,
+                                    float* __restrict__ bias_w, int out_c, int taps, int in_c, int in_cp, int out_cp,
+                                    size_t ms_f, size_t ms_c) {
+	// master element (filter f, column col) lives at f*ms_f + col*ms_c:
+	//   conv  layout [out_c][kref]      -> ms_f = kref, ms_c = 1
+	//   dense layout [in_size][n + 1]   -> ms_f = 1,    ms_c = n + 1   (src/dense_layer.c:253-268)
+	const int kref = taps * in_c + 1;
+	const size_t total = (size_t)out_c * kref;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int f = (int)(i / kref), col = (int)(i - (size_t)f * kref);
+		scatter_weight<T>(master[f * ms_f + col * ms_c], f, col, taps, in_c, in_cp, out_cp, w_fwd, w_bwd, bias_w);
+	}
+}
+
+// moment = (lr/B)*g + mom*moment ; moment += lr*wd*w*S ; w -= moment/S   (cuda_conv_layer.cu:551-560,
+// cuda_main.cu:455-467), then the refreshed 16-bit operands are written in the same pass.
+template <typename T>
+__global__ void conv_update_kernel(float* __restrict__ master, float* __restrict__ moment,
+                                   const float* __restrict__ grad, const float* __restrict__ grad_b,
+                                   const float* __restrict__ hyper, float bias_value, int is_pivot,
+                                   T* __restrict__ w_fwd, T* __restrict__ w_bwd, float* __restrict__ bias_w,
+                                   int out_c, int taps, int in_c, int in_cp, int out_cp, size_t ms_f, size_t ms_c) {
+	const int kref = taps * in_c + 1;
+	const size_t total = (size_t)out_c * kref;
+	const float alpha = hyper[0], mom = hyper[1], wdlr = hyper[2], S = hyper[3];
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int f = (int)(i / kref), col = (int)(i - (size_t)f * kref);
+		const size_t mi = f * ms_f + col * ms_c;
+		float wv = master[mi];
+		if (i < total - (size_t)is_pivot) {
+			float g;
+			if (col == kref - 1) g = bias_value * grad_b[f];
+			else { const int c = col / taps, tap = col - c * taps; g = grad[((size_t)f * taps + tap) * in_cp + c]; }
+			float m = alpha * g + mom * moment[mi];
+			m += wdlr * wv * S;
+			wv -= m / S;
+			moment[mi] = m;
+			master[mi] = wv;
+		}
+		scatter_weight<T>(wv, f, col, taps, in_c, in_cp, out_cp, w_fwd, w_bwd, bias_w);
+	}
+}
+
+static int check_desc(const cb200_conv_desc* d) {
+	CB_ARG(d != nullptr);
+	CB_ARG(d->batch > 0 && d->in_c > 0 && d->out_c > 0 && d->in_h > 0 && d->in_w > 0 && d->out_h > 0 && d->out_w > 0);
+	CB_ARG(d->f_h > 0 && d->f_w > 0 && d->stride_h > 0 && d->stride_w > 0 && d->pad_h >= 0 && d->pad_w >= 0);
+	CB_ARG(d->out_h == (d->in_h + 2 * d->pad_h - d->f_h) / d->stride_h + 1);
+	CB_ARG(d->out_w == (d->in_w + 2 * d->pad_w - d->f_w) / d->stride_w + 1);
+	CB_ARG(d->length >= 0 && d->length <= d->batch);
+	return CB200_OK;
+}
+}  // namespace cb200
+using namespace cb200;
+
+extern "C" {
+
+size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * d->f_h * d->f_w * round8(d->in_c); }
+size_t cb200_conv_wbwd_elems(const cb200_conv_desc* d) { return (size_t)d->in_c * d->f_h * d->f_w * round8(d->out_c); }
+size_t cb200_conv_grad_elems(const cb200_conv_desc* d) { return cb200_conv_wfwd_elems(d); }
+size_t cb200_conv_master_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * ((size_t)d->f_h * d->f_w * d->in_c + 1); }
+
+static int prepare_weights_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, size_t ms_f, size_t ms_c, void* s) {
+	CB_REQUIRE_DEVICE();
+	int rc = check_desc(d); if (rc) return rc;
+	cudaStream_t st = as_stream(s);
+	// pad lanes of the operands must be zero: clear, then scatter
+	CB_CUDA(cudaMemsetAsync(w->w_fwd, 0, cb200_conv_wfwd_elems(d) * cb200_dtype_size(d->dtype), st));
+	CB_CUDA(cudaMemsetAsync(w->w_bwd, 0, cb200_conv_wbwd_elems(d) * cb200_dtype_size(d->dtype), st));
+	const int taps = d->f_h * d->f_w;
+	long long total = (long long)cb200_conv_master_elems(d);
+	CB_DISPATCH_DTYPE(d->dtype, T, (conv_prepare_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+		w->master, (T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_conv_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, void* s) {
+	return prepare_weights_impl(d, w, (size_t)d->f_h * d->f_w * d->in_c + 1, 1, s);
+}
+int cb200_dense_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, void* s) {
+	return prepare_weights_impl(d, w, 1, (size_t)d->out_c + 1, s);
+}
+
+int cb200_conv_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y, void* s) {
+	CB_REQUIRE_DEVICE();
+	int rc = check_desc(d); if (rc) return rc;
+	if (!g_force_simt && conv_tc_fwd_supported(d)) { g_last_conv_impl = "tcgen05"; return conv_forward_tc(d, w, x, y, as_stream(s)); }
+	g_last_conv_impl = "simt";
+	return conv_forward_simt(d, w, x, y, as_stream(s));
+}
+
+int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* dy, void* dx,
+                             const cb200_activ* prev_activ, const void* prev_out, void* s) {
+	CB_REQUIRE_DEVICE();
+	int rc = check_desc(d); if (rc) return rc;
+	if (!g_force_simt && conv_tc_dgrad_supported(d)) { g_last_conv_impl = "tcgen05"; return conv_dgrad_tc(d, w, dy, dx, prev_activ, prev_out, as_stream(s)); }
+	g_last_conv_impl = "simt";
+	return conv_dgrad_simt(d, w, dy, dx, prev_activ, prev_out, as_stream(s));
+}
+
+int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, void* s) {
+	CB_REQUIRE_DEVICE();
+	int rc = check_desc(d); if (rc) return rc;
+	cudaStream_t st = as_stream(s);
+	long long P = (long long)d->batch * d->out_h * d->out_w;
+	rc = conv_colsum(d->dtype, dy, w->grad_b, P, d->out_c, st);
+	if (rc) return rc;
+	if (!g_force_simt && conv_tc_wgrad_supported(d)) { g_last_conv_impl = "tcgen05"; return conv_wgrad_tc(d, w, x, dy, st); }
+	g_last_conv_impl = "simt";
+	return conv_wgrad_simt(d, w, x, dy, st);
+}
+
+static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, int is_pivot,
+                       size_t ms_f, size_t ms_c, void* s) {
+	CB_REQUIRE_DEVICE();
+	int rc = check_desc(d); if (rc) return rc;
+	const int taps = d->f_h * d->f_w;
+	long long total = (long long)cb200_conv_master_elems(d);
+	CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
+		w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, is_pivot,
+		(T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_conv_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, int is_pivot, void* s) {
+	return update_impl(d, w, hyper, is_pivot, (size_t)d->f_h * d->f_w * d->in_c + 1, 1, s);
+}
+int cb200_dense_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, void* s) {
+	return update_impl(d, w, hyper, 0, 1, (size_t)d->out_c + 1, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,561 @@
+// conv_tc.cu - implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces the reference's "im2col scatter kernel + cublasGemmEx" pipeline for the three GEMMs of a
+// conv layer (src/cuda/cuda_conv_layer.cu:379-397 forward, :505-527 data gradient, :551-557 weight
+// gradient).  Nothing is unrolled to memory: the GEMM A operand is fetched tap by tap straight from
+// the channels-last activation with 4-D TMA boxes (c, x, y, image); out-of-bound box elements are
+// zero-filled by the TMA unit, which IS the convolution's zero padding.
+//
+//   forward / data-gradient kernel (conv_igemm_kernel)
+//     D[128 pixels][BN out-channels] += A[pixels][64 ch of tap t] * W[out-ch][tap t][64 ch]^T
+//     M tile  = a TWxTHxTN rectangle of output pixels (TW*TH*TN = 128) -> one TMA box per tap
+//     K loop  = taps x channel blocks, multi-stage smem ring, mbarrier full/empty pipeline
+//     MMA     = tcgen05.mma kind::f16, K-major A and B (128B/64B swizzle), FP32 accumulator in TMEM,
+//               double-buffered so the epilogue of tile i overlaps the main loop of tile i+1
+//     epilogue= tcgen05.ld -> bias + activation (+ previous layer's derivative for dgrad) -> cast -> store
+//     The data gradient is the same kernel run on dy with the rotated/transposed weights (w_bwd)
+//     and padding f-1-p.
+//   weight-gradient kernel (conv_wgrad_kernel)
+//     G[128 out-ch][BN in-ch] (one tap) += dy[pixels][out-ch]^T * x[shifted pixels][in-ch]
+//     both operands are MN-major (the contraction index, pixels, is the slow one in memory),
+//     split over pixel ranges across CTAs, FP32 atomics into the raw-gradient buffer.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp w may only touch TMEM lanes 32*(w%4)..+31).
+#include <cuda.h>
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cb200 {
+
+using namespace ptx;
+
+// ---------------------------------------------------------------- host: tensor-map encoding
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+	if (g_encode) return CB200_OK;
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+	if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+		set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+		return CB200_ERR_CUDA;
+	}
+	g_encode = (EncodeTiledFn)fn;
+	return CB200_OK;
+}
+
+// rank-4 map over act[n][y][x][c] (c fastest).  box = (bc, bw, bh, bn)
+static int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n,
+                        int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw) {
+	int rc = load_encode(); if (rc) return rc;
+	const cuuint64_t es = 2;
+	cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+	cuuint64_t strides[3] = {(cuuint64_t)cp * es, (cuuint64_t)w * cp * es, (cuuint64_t)h * w * cp * es};
+	cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+	cuuint32_t estr[4] = {1, 1, 1, 1};
+	CUresult r = g_encode(m, dtype == CB200_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+	                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+	                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act %dx%dx%dx%d box %dx%dx%dx%d) failed: %d", cp, w, h, n, bc, bw, bh, bn, (int)r); return CB200_ERR_CUDA; }
+	return CB200_OK;
+}
+// rank-3 map over w[row][tap][c] (c fastest). box = (bc, 1, brow)
+static int make_w_map(CUtensorMap* m, const void* base, int dtype, int cp, int taps, int rows, int bc, int brow, CUtensorMapSwizzle sw) {
+	int rc = load_encode(); if (rc) return rc;
+	const cuuint64_t es = 2;
+	cuuint64_t dims[3] = {(cuuint64_t)cp, (cuuint64_t)taps, (cuuint64_t)rows};
+	cuuint64_t strides[2] = {(cuuint64_t)cp * es, (cuuint64_t)taps * cp * es};
+	cuuint32_t box[3] = {(cuuint32_t)bc, 1, (cuuint32_t)brow};
+	cuuint32_t estr[3] = {1, 1, 1};
+	CUresult r = g_encode(m, dtype == CB200_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+	                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+	                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%dx%d box %dx1x%d) failed: %d", cp, taps, rows, bc, brow, (int)r); return CB200_ERR_CUDA; }
+	return CB200_OK;
+}
+
+// choose the TWxTHxTN pixel rectangle (product = npix, all powers of two) that wastes the least work
+static void choose_rect(int W, int H, int N, int npix, int& tw, int& th, int& tn) {
+	double best = 1e30;
+	tw = npix; th = 1; tn = 1;
+	for (int a = 1; a <= npix; a <<= 1)
+		for (int b = 1; a * b <= npix; b <<= 1) {
+			int c = npix / (a * b);
+			if (a > 256 || b > 256 || c > 256) continue;
+			double cover = (double)ceil_div(W, a) * a * (double)ceil_div(H, b) * b * (double)ceil_div(N, c) * c;
+			double cost = cover / ((double)W * H * N) - 1e-6 * a;   // tie-break: prefer wide rows
+			if (cost < best) { best = cost; tw = a; th = b; tn = c; }
+		}
+}
+
+// ================================================================ forward / dgrad kernel
+struct IgemmParams {
+	// pixel space of the OUTPUT of this GEMM (== input pixel space shifted by the taps; stride 1)
+	int W, H, N;
+	int tw, th, tn;              // M-tile rectangle
+	int tiles_w, tiles_h, tiles_n, tiles_m, tiles_nn, num_tiles;
+	int f_h, f_w, off_h, off_w;  // taps and the (negative) padding offset of tap (0,0)
+	int kc_blocks;               // channel blocks of BK per tap
+	int n_real, n_pad;           // real / padded output channels
+	int mode;                    // 0 = forward epilogue, 1 = dgrad epilogue
+	int length;
+	float bias_value;
+	const float* bias_w;
+	void* out;
+	const void* prev_out;
+	cb200_activ activ;           // forward: this layer; dgrad: the previous layer
+	uint32_t idesc;
+};
+
+template <int BN, int BK>
+struct IgemmCfg {
+	static constexpr int A_BYTES = 128 * BK * 2;
+	static constexpr int B_BYTES = BN * BK * 2;
+	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+	static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+	static constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);   // 128B / 64B / 32B swizzle
+	static constexpr uint32_t SBO = 8 * BK * 2;                                 // 8 rows of one swizzle atom
+};
+
+template <typename T, int BN, int BK>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
+	using Cfg = IgemmCfg<BN, BK>;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+	// barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the tmem address slot
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_a);
+		prefetch_tensormap(&tmap_b);
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+		fence_barrier_init();
+	}
+	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	const int taps = p.f_h * p.f_w;
+	const int k_iters = taps * p.kc_blocks;
+
+	if (warp == 0) {
+		// ===================== TMA producer =====================
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+				const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+				const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+				for (int tap = 0; tap < taps; tap++) {
+					const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
+					for (int cb = 0; cb < p.kc_blocks; cb++) {
+						mbar_wait(empty_bar(stage), phase ^ 1u);
+						const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+						mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+						tma_load_4d(sa, &tmap_a, full_bar(stage), cb * BK, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
+						tma_load_3d(sb, &tmap_b, full_bar(stage), cb * BK, tap, nt * BN);
+						if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===================== MMA issuer =====================
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			int acc = 0; uint32_t acc_phase = 0;
+			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+				for (int k = 0; k < k_iters; k++) {
+					mbar_wait(full_bar(stage), phase);
+					tc_fence_after();
+					const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+					for (int kk = 0; kk < BK / 16; kk++) {
+						const uint64_t da = make_smem_desc(sa + kk * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+						const uint64_t db = make_smem_desc(sb + kk * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+						mma_f16_ss(d_tmem, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
+					}
+					mma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+				}
+				mma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
+				if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+			}
+		}
+	} else {
+		// ===================== epilogue warps =====================
+		const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+		const int row = quad * 32 + lane;                // row of the 128-pixel tile
+		int acc = 0; uint32_t acc_phase = 0;
+		T* out = reinterpret_cast<T*>(p.out);
+		const T* prev = reinterpret_cast<const T*>(p.prev_out);
+		const bool mask_tail = activ_masks_tail(p.activ);
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+			const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+			const int px = twi * p.tw + (row % p.tw);
+			const int py = thi * p.th + (row / p.tw) % p.th;
+			const int pn = tni * p.tn + row / (p.tw * p.th);
+			const bool row_ok = px < p.W && py < p.H && pn < p.N;
+			const size_t pix = ((size_t)pn * p.H + py) * p.W + px;
+			const bool dead = mask_tail && pn >= p.length;
+
+			mbar_wait(tfull_bar(acc), acc_phase);
+			tc_fence_after();
+			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+			for (int c0 = 0; c0 < BN; c0 += 32) {
+				uint32_t r[32];
+				if (BN - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
+				else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
+#pragma unroll
+					for (int j = 0; j < 16; j++) { r[j] = h[j]; r[16 + j] = 0; } }
+				tmem_ld_wait();
+				const int col0 = nt * BN + c0;
+				if (row_ok) {
+#pragma unroll
+					for (int v = 0; v < 4; v++) {
+						const int col = col0 + v * 8;
+						if (col >= p.n_pad || c0 + v * 8 >= BN) continue;
+						float o[8];
+						if (p.mode == 0) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const int ch = col + j;
+								float z = __uint_as_float(r[v * 8 + j]);
+								o[j] = (ch < p.n_real && !dead) ? activ_forward(p.activ, z + p.bias_value * __ldg(p.bias_w + ch)) : 0.0f;
+							}
+						} else {
+							float pv[8];
+							const bool hook = prev != nullptr && p.activ.type != CB200_LINEAR;
+							if (hook) load8<T>(prev + pix * p.n_pad + col, pv);
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const int ch = col + j;
+								float z = __uint_as_float(r[v * 8 + j]);
+								if (hook) z = activ_deriv_mul(p.activ, z, pv[j]);
+								o[j] = (ch < p.n_real && !dead) ? z : 0.0f;
+							}
+						}
+						store8<T>(out + pix * p.n_pad + col, o);
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(tempty_bar(acc));
+			if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+		}
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+template <typename T, int BN, int BK>
+static int launch_igemm(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, cudaStream_t st) {
+	using Cfg = IgemmCfg<BN, BK>;
+	static bool configured = false;
+	auto kern = conv_igemm_kernel<T, BN, BK>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+	kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+template <typename T>
+static int dispatch_igemm(int bn, int bk, const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, cudaStream_t st) {
+#define CASE(BN_, BK_) if (bn == BN_ && bk == BK_) return launch_igemm<T, BN_, BK_>(ma, mb, p, st)
+	CASE(256, 64); CASE(128, 64); CASE(64, 64); CASE(32, 64); CASE(16, 64);
+	CASE(256, 32); CASE(128, 32); CASE(64, 32); CASE(32, 32); CASE(16, 32);
+	CASE(256, 16); CASE(128, 16); CASE(64, 16); CASE(32, 16); CASE(16, 16);
+#undef CASE
+	set_error("conv_tc: no kernel instance for BN=%d BK=%d", bn, bk);
+	return CB200_ERR_UNSUPPORTED;
+}
+
+static int pick_bk(int cp) { return cp % 64 == 0 ? 64 : (cp % 32 == 0 ? 32 : (cp % 16 == 0 ? 16 : 0)); }
+static int pick_bn(int n_pad) { return n_pad > 128 ? 256 : n_pad > 64 ? 128 : n_pad > 32 ? 64 : n_pad > 16 ? 32 : 16; }
+static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B; }
+
+static bool tc_common_ok(const cb200_conv_desc* d) {
+	if (d->dtype != CB200_FP16 && d->dtype != CB200_BF16) return false;
+	if (d->stride_h != 1 || d->stride_w != 1) return false;
+	if (d->pad_h > d->f_h - 1 || d->pad_w > d->f_w - 1) return false;
+	return true;
+}
+bool conv_tc_fwd_supported(const cb200_conv_desc* d) { return tc_common_ok(d) && pick_bk(round8(d->in_c)) != 0; }
+bool conv_tc_dgrad_supported(const cb200_conv_desc* d) { return tc_common_ok(d) && pick_bk(round8(d->out_c)) != 0 && round8(d->in_c) >= 16; }
+
+// GEMM over: input tensor `src` with cin_p channels on an (in_h, in_w) grid, weights wmat[rows=n_real][taps][cin_p],
+// output pixel grid (out_h, out_w), tap (0,0) reads input pixel (oy + off_h, ox + off_w).
+static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, int batch,
+                     const void* wmat, int n_real, int f_h, int f_w, int off_h, int off_w,
+                     int out_h, int out_w, IgemmParams p, cudaStream_t st) {
+	const int bk = pick_bk(cin_p);
+	const int n_pad = round8(n_real);
+	const int bn = pick_bn(n_pad);
+	int tw, th, tn;
+	choose_rect(out_w, out_h, batch, 128, tw, th, tn);
+	CUtensorMap ma, mb;
+	int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, tw, th, tn, swizzle_for(bk));
+	if (rc) return rc;
+	rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, bn, swizzle_for(bk));
+	if (rc) return rc;
+	p.W = out_w; p.H = out_h; p.N = batch;
+	p.tw = tw; p.th = th; p.tn = tn;
+	p.tiles_w = ceil_div(out_w, tw); p.tiles_h = ceil_div(out_h, th); p.tiles_n = ceil_div(batch, tn);
+	p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+	p.tiles_nn = ceil_div(n_pad, bn);
+	p.num_tiles = p.tiles_m * p.tiles_nn;
+	p.f_h = f_h; p.f_w = f_w; p.off_h = off_h; p.off_w = off_w;
+	p.kc_blocks = ceil_div(cin_p, bk);
+	p.n_real = n_real; p.n_pad = n_pad;
+	p.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
+	if (dtype == CB200_FP16) return dispatch_igemm<__half>(bn, bk, ma, mb, p, st);
+	return dispatch_igemm<__nv_bfloat16>(bn, bk, ma, mb, p, st);
+}
+
+int conv_forward_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y, cudaStream_t st) {
+	IgemmParams p;
+	memset(&p, 0, sizeof(p));
+	p.mode = 0; p.length = d->length; p.bias_value = d->bias_value; p.bias_w = w->bias_w;
+	p.out = y; p.prev_out = nullptr; p.activ = d->activ;
+	return run_igemm(d->dtype, x, round8(d->in_c), d->in_h, d->in_w, d->batch, w->w_fwd, d->out_c,
+	                 d->f_h, d->f_w, -d->pad_h, -d->pad_w, d->out_h, d->out_w, p, st);
+}
+
+int conv_dgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* dy, void* dx,
+                  const cb200_activ* prev_activ, const void* prev_out, cudaStream_t st) {
+	IgemmParams p;
+	memset(&p, 0, sizeof(p));
+	p.mode = 1; p.length = d->length; p.bias_value = 0.0f; p.bias_w = nullptr;
+	p.out = dx; p.prev_out = prev_out;
+	p.activ.type = CB200_LINEAR;
+	if (prev_activ && prev_out) p.activ = *prev_activ;
+	// full correlation of dy with the rotated filters: padding f-1-p
+	return run_igemm(d->dtype, dy, round8(d->out_c), d->out_h, d->out_w, d->batch, w->w_bwd, d->in_c,
+	                 d->f_h, d->f_w, -(d->f_h - 1 - d->pad_h), -(d->f_w - 1 - d->pad_w), d->in_h, d->in_w, p, st);
+}
+
+// ================================================================ weight-gradient kernel
+struct WgradParams {
+	int W, H, N;                 // OUTPUT pixel grid of the layer (dy) ; x is read at pixel + tap offset
+	int tw, th, tn;              // pixel rectangle of one K step (64 pixels)
+	int tiles_w, tiles_h, tiles_n, pix_tiles;
+	int f_h, f_w, off_h, off_w;
+	int f_tiles, c_tiles, splits, tiles_per_split;
+	int out_c, in_cp;
+	float* grad;                 // [out_c][taps][in_cp]
+	uint32_t idesc;
+};
+
+// BNC input channels per CTA, fetched as slabs of SLAB_C channels (64 -> 128B swizzle, 32 -> 64B, 16 -> 32B)
+template <int BNC, int SLAB_C>
+struct WgradCfg {
+	static constexpr int KPIX = 64;                                 // pixels per pipeline stage
+	static constexpr int A_SLAB_BYTES = KPIX * 128;                 // dy: 2 slabs of [64 pix][64 ch]
+	static constexpr int A_BYTES = 2 * A_SLAB_BYTES;
+	static constexpr int B_SLABS = BNC / SLAB_C;
+	static constexpr int B_ROW_BYTES = SLAB_C * 2;
+	static constexpr int B_SLAB_BYTES = KPIX * B_ROW_BYTES;
+	static constexpr int B_BYTES = B_SLABS * B_SLAB_BYTES;
+	static constexpr uint32_t B_LAYOUT = SLAB_C == 64 ? 2u : (SLAB_C == 32 ? 4u : 6u);
+	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+	static constexpr int TMEM_COLS = BNC <= 32 ? 32 : BNC <= 64 ? 64 : BNC <= 128 ? 128 : 256;
+};
+
+// grid.x = f_tiles * c_tiles * taps, grid.y = splits
+template <int BNC, int SLAB_C>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
+	using Cfg = WgradCfg<BNC, SLAB_C>;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+	const uint32_t done_bar = bar_base + 8u * (2 * Cfg::STAGES);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_dy);
+		prefetch_tensormap(&tmap_x);
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		mbar_init(done_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	const int taps = p.f_h * p.f_w;
+	int job = blockIdx.x;
+	const int tap = job % taps; job /= taps;
+	const int ct = job % p.c_tiles;
+	const int ft = job / p.c_tiles;
+	const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
+	const int t_begin = blockIdx.y * p.tiles_per_split;
+	int t_end = t_begin + p.tiles_per_split;
+	if (t_end > p.pix_tiles) t_end = p.pix_tiles;
+	const int n_steps = t_end - t_begin;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			for (int t = t_begin; t < t_end; t++) {
+				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
+				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+				mbar_wait(empty_bar(stage), phase ^ 1u);
+				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+				mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+				tma_load_4d(sa, &tmap_dy, full_bar(stage), ft * 128, w0, h0, n0);
+				tma_load_4d(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), ft * 128 + 64, w0, h0, n0);
+#pragma unroll
+				for (int sl = 0; sl < Cfg::B_SLABS; sl++)
+					tma_load_4d(sb + sl * Cfg::B_SLAB_BYTES, &tmap_x, full_bar(stage), ct * BNC + sl * SLAB_C, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
+				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+			}
+		}
+	} else if (warp == 1) {
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			for (int k = 0; k < n_steps; k++) {
+				mbar_wait(full_bar(stage), phase);
+				tc_fence_after();
+				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+				for (int kk = 0; kk < Cfg::KPIX / 16; kk++) {
+					// MN-major: 8 pixel rows per K group -> SBO; channel slabs -> LBO; 16 pixel rows per MMA
+					const uint64_t da = make_smem_desc(sa + kk * 2048, Cfg::A_SLAB_BYTES, 1024, 2);
+					const uint64_t db = make_smem_desc(sb + kk * 16 * Cfg::B_ROW_BYTES, Cfg::B_SLAB_BYTES, 8 * Cfg::B_ROW_BYTES, Cfg::B_LAYOUT);
+					mma_f16_ss(tmem_base, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
+				}
+				mma_commit(empty_bar(stage));
+				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+			}
+			mma_commit(done_bar);
+		}
+	} else if (n_steps > 0) {
+		const int quad = warp & 3;
+		const int f = ft * 128 + quad * 32 + lane;
+		mbar_wait(done_bar, 0);
+		tc_fence_after();
+		const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+		for (int c0 = 0; c0 < BNC; c0 += 32) {
+			uint32_t r[32];
+			tmem_ld_32x32(t_row + c0, r);
+			tmem_ld_wait();
+			if (f < p.out_c) {
+				float* dst = p.grad + ((size_t)f * taps + tap) * p.in_cp + ct * BNC + c0;
+#pragma unroll
+				for (int j = 0; j < 32; j++)
+					if (ct * BNC + c0 + j < p.in_cp) atomicAdd(dst + j, __uint_as_float(r[j]));
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+bool conv_tc_wgrad_supported(const cb200_conv_desc* d) {
+	if (!tc_common_ok(d)) return false;
+	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
+	return out_cp >= 64 && (in_cp >= 64 || in_cp == 32 || in_cp == 16);
+}
+
+template <int BNC, int SLAB_C>
+static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& p, dim3 grid, cudaStream_t st) {
+	using Cfg = WgradCfg<BNC, SLAB_C>;
+	static bool configured = false;
+	auto kern = conv_wgrad_kernel<BNC, SLAB_C>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(mdy, mx, p);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int conv_wgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
+	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
+	const int slab_c = in_cp >= 64 ? 64 : in_cp;
+	const int bnc = in_cp < 64 ? in_cp : (in_cp > 128 ? 256 : (in_cp > 64 ? 128 : 64));
+	WgradParams p;
+	memset(&p, 0, sizeof(p));
+	choose_rect(d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn);
+	CUtensorMap mdy, mx;
+	int rc = make_act_map(&mdy, dy, d->dtype, out_cp, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B);
+	if (rc) return rc;
+	rc = make_act_map(&mx, x, d->dtype, in_cp, d->in_w, d->in_h, d->batch, slab_c, p.tw, p.th, p.tn, swizzle_for(slab_c));
+	if (rc) return rc;
+	p.W = d->out_w; p.H = d->out_h; p.N = d->batch;
+	p.tiles_w = ceil_div(p.W, p.tw); p.tiles_h = ceil_div(p.H, p.th); p.tiles_n = ceil_div(p.N, p.tn);
+	p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+	p.f_h = d->f_h; p.f_w = d->f_w; p.off_h = -d->pad_h; p.off_w = -d->pad_w;
+	p.f_tiles = ceil_div(out_cp, 128); p.c_tiles = ceil_div(in_cp, bnc);
+	const int jobs = p.f_tiles * p.c_tiles * d->f_h * d->f_w;
+	int splits = ceil_div(g_num_sms * 2, jobs);
+	const int max_splits = ceil_div(p.pix_tiles, 8);
+	if (splits > max_splits) splits = max_splits;
+	if (splits < 1) splits = 1;
+	p.tiles_per_split = ceil_div(p.pix_tiles, splits);
+	splits = ceil_div(p.pix_tiles, p.tiles_per_split);
+	p.splits = splits;
+	p.out_c = d->out_c; p.in_cp = in_cp;
+	p.grad = w->grad;
+	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, bnc, 1, 1);
+	if (cudaMemsetAsync(w->grad, 0, sizeof(float) * (size_t)d->out_c * d->f_h * d->f_w * in_cp, st) != cudaSuccess) {
+		set_error("wgrad memset failed"); return CB200_ERR_CUDA;
+	}
+	dim3 grid((unsigned)jobs, (unsigned)splits);
+	if (bnc == 256) return launch_wgrad<256, 64>(mdy, mx, p, grid, st);
+	if (bnc == 128) return launch_wgrad<128, 64>(mdy, mx, p, grid, st);
+	if (bnc == 64) return launch_wgrad<64, 64>(mdy, mx, p, grid, st);
+	if (bnc == 32) return launch_wgrad<32, 32>(mdy, mx, p, grid, st);
+	return launch_wgrad<16, 16>(mdy, mx, p, grid, st);
+}
+
+}  // namespace cb200

@@ -1,0 +1,117 @@
+// output.cu - output-layer passes: softmax, error signal (delta) and loss monitor.
+// Reference kernels: softmax_activation_kernel (src/cuda/cuda_activ_functions.cu:280-381),
+// quadratic_* / cross_entropy_* (:114-194, :384-470) and their CPU twins in src/activ_functions.c.
+// The target batch keeps the reference layout [B][c*h*w] (per sample: channel-major, then pixel).
+#include "common.cuh"
+
+namespace cb200 {
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	v = is_max ? warp_max(v) : warp_sum(v);
+	if (lane == 0) red[wid] = v;
+	__syncthreads();
+	float r = threadIdx.x < nw ? red[threadIdx.x] : (is_max ? -INFINITY : 0.0f);
+	if (wid == 0) {
+		r = is_max ? warp_max(r) : warp_sum(r);
+		if (lane == 0) red[0] = r;
+	}
+	__syncthreads();
+	r = red[0];
+	__syncthreads();
+	return r;
+}
+
+// one block per sample; softmax over all c*hw real values of the sample (upstream semantics for the
+// conv layout: a single softmax per sample across filters AND positions)
+template <typename T>
+__global__ void softmax_kernel(T* __restrict__ y, int length, int c, int cp, int hw) {
+	__shared__ float red[32];
+	const int b = blockIdx.x;
+	T* row = y + (size_t)b * hw * cp;
+	const int n = hw * cp;
+	if (b >= length) {
+		for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = from_f32<T>(0.0f);
+		return;
+	}
+	float vmax = -INFINITY;
+	for (int i = threadIdx.x; i < n; i += blockDim.x)
+		if (i % cp < c) vmax = fmaxf(vmax, to_f32<T>(row[i]));
+	vmax = block_reduce(vmax, red, true);
+	float sum = 0.0f;
+	for (int i = threadIdx.x; i < n; i += blockDim.x)
+		if (i % cp < c) sum += expf(to_f32<T>(row[i]) - vmax);
+	sum = block_reduce(sum, red, false);
+	for (int i = threadIdx.x; i < n; i += blockDim.x)
+		row[i] = (i % cp < c) ? from_f32<T>(expf(to_f32<T>(row[i]) - vmax) / sum) : from_f32<T>(0.0f);
+}
+
+template <typename T>
+__global__ void output_delta_kernel(T* __restrict__ delta, const T* __restrict__ y, const T* __restrict__ target,
+                                    int batch, int length, int c, int cp, int hw, float scale) {
+	const size_t total = (size_t)batch * hw * cp;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int ch = (int)(i % cp);
+		const size_t pix = i / cp;
+		const int p = (int)(pix % hw);
+		const int b = (int)(pix / hw);
+		float v = 0.0f;
+		if (ch < c && b < length) v = (to_f32<T>(y[i]) - to_f32<T>(target[((size_t)b * c + ch) * hw + p])) * scale;
+		delta[i] = from_f32<T>(v);
+	}
+}
+
+// loss[b] = sum over the sample's outputs; one block per sample
+template <typename T>
+__global__ void output_loss_kernel(float* __restrict__ loss, const T* __restrict__ y, const T* __restrict__ target,
+                                   int length, int c, int cp, int hw, int kind) {
+	__shared__ float red[32];
+	const int b = blockIdx.x;
+	float s = 0.0f;
+	if (b < length) {
+		const int n = hw * cp;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) {
+			const int ch = i % cp, p = i / cp;
+			if (ch >= c) continue;
+			const float o = to_f32<T>(y[(size_t)b * n + i]);
+			const float t = to_f32<T>(target[((size_t)b * c + ch) * hw + p]);
+			if (kind == 0) s += 0.5f * (o - t) * (o - t);
+			else s += -t * logf(o > 0.000001f ? o : 0.000001f);
+		}
+	}
+	s = block_reduce(s, red, false);
+	if (threadIdx.x == 0) loss[b] = s;
+}
+}  // namespace cb200
+using namespace cb200;
+
+extern "C" {
+
+int cb200_softmax(void* y, int dtype, int batch, int length, int c, int h, int w, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_ARG(batch > 0 && c > 0);
+	CB_DISPATCH_DTYPE(dtype, T, (softmax_kernel<T><<<batch, 256, 0, as_stream(s)>>>((T*)y, length, c, round8(c), h * w)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_output_delta(void* delta, const void* y, const void* target, int dtype, int batch, int length,
+                       int c, int h, int w, float scale, void* s) {
+	CB_REQUIRE_DEVICE();
+	long long total = (long long)batch * h * w * round8(c);
+	CB_DISPATCH_DTYPE(dtype, T, (output_delta_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
+		(T*)delta, (const T*)y, (const T*)target, batch, length, c, round8(c), h * w, scale)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_output_loss(float* loss, const void* y, const void* target, int dtype, int batch, int length,
+                      int c, int h, int w, int kind, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_DISPATCH_DTYPE(dtype, T, (output_loss_kernel<T><<<batch, 256, 0, as_stream(s)>>>(
+		loss, (const T*)y, (const T*)target, length, c, round8(c), h * w, kind)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// pool.cu - max / average pooling, forward and backward, on channels-last tensors.
+// One thread handles 8 consecutive channels of one pixel (128-bit accesses for 16-bit types),
+// so a warp always touches one contiguous span of memory.
+// Reference: src/cuda/cuda_pool_layer.cu:31-277 (kernels), :429-547 (layer functions);
+// CPU twin src/naiv/naiv_pool_layer.c:30-318.
+#include "common.cuh"
+
+namespace cb200 {
+
+struct PoolGeom {
+	int batch, length, c, cp, in_h, in_w, out_h, out_w, p_h, p_w, s_h, s_w, pad_h, pad_w, type;
+	cb200_activ activ;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ map, PoolGeom g) {
+	const int cv = g.cp >> 3;
+	const long long total = (long long)g.batch * g.out_h * g.out_w * cv;
+	const bool mask_tail = activ_masks_tail(g.activ);
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int v = (int)(i % cv);
+		long long r = i / cv;
+		const int ox = (int)(r % g.out_w); r /= g.out_w;
+		const int oy = (int)(r % g.out_h);
+		const int b = (int)(r / g.out_h);
+		float best[8];
+		int arg[8];
+		int count = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) { best[j] = 0.0f; arg[j] = 255; }
+		// window scan order y then x (z,y,x upstream), first strict maximum wins
+		for (int py = 0; py < g.p_h; py++) {
+			const int iy = oy * g.s_h + py - g.pad_h;
+			if (iy < 0 || iy >= g.in_h) continue;
+			for (int px = 0; px < g.p_w; px++) {
+				const int ix = ox * g.s_w + px - g.pad_w;
+				if (ix < 0 || ix >= g.in_w) continue;
+				float val[8];
+				load8<T>(x + (((long long)b * g.in_h + iy) * g.in_w + ix) * g.cp + v * 8, val);
+				if (g.type == CB200_POOL_MAX) {
+					const int loc = py * g.p_w + px;
+					if (count == 0) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) { best[j] = val[j]; arg[j] = loc; }
+					} else {
+#pragma unroll
+						for (int j = 0; j < 8; j++) if (val[j] > best[j]) { best[j] = val[j]; arg[j] = loc; }
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < 8; j++) best[j] += val[j];
+				}
+				count++;
+			}
+		}
+		if (g.type == CB200_POOL_AVG) {
+			const float inv = 1.0f / (float)count;   // count == 0 gives inf/nan exactly like upstream's r_avg/sum_elem
+#pragma unroll
+			for (int j = 0; j < 8; j++) best[j] *= inv;
+		}
+		const bool dead = mask_tail && b >= g.length;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const bool real = (v * 8 + j) < g.c;
+			best[j] = (real && !dead) ? activ_forward(g.activ, best[j]) : 0.0f;
+			if (!real) arg[j] = 255;
+		}
+		const long long o = (((long long)b * g.out_h + oy) * g.out_w + ox) * g.cp + v * 8;
+		store8<T>(y + o, best);
+		if (map != nullptr && g.type == CB200_POOL_MAX) {
+			uint2 packed;
+			packed.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+			packed.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
+			*reinterpret_cast<uint2*>(map + o) = packed;
+		}
+	}
+}
+
+// gather form of the backward pass: each input pixel sums the deltas of the windows that selected it
+// (deltah_max_pool_cont / deltah_avg_pool_cont upstream), then the previous layer's deriv hook.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ map, T* __restrict__ dx,
+                const T* __restrict__ prev_out, cb200_activ prev_activ, PoolGeom g) {
+	const int cv = g.cp >> 3;
+	const long long total = (long long)g.batch * g.in_h * g.in_w * cv;
+	const bool hook = prev_out != nullptr && prev_activ.type != CB200_LINEAR;
+	const bool mask_tail = hook && activ_masks_tail(prev_activ);
+	const float inv_vol = 1.0f / (float)(g.p_h * g.p_w);
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int v = (int)(i % cv);
+		long long r = i / cv;
+		const int ix = (int)(r % g.in_w); r /= g.in_w;
+		const int iy = (int)(r % g.in_h);
+		const int b = (int)(r / g.in_h);
+		float acc[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+		const int py_pos = iy + g.pad_h, px_pos = ix + g.pad_w;
+		for (int oy = py_pos / g.s_h; oy >= 0 && py_pos - oy * g.s_h < g.p_h; oy--) {
+			if (oy >= g.out_h) continue;
+			const int fy = py_pos - oy * g.s_h;
+			for (int ox = px_pos / g.s_w; ox >= 0 && px_pos - ox * g.s_w < g.p_w; ox--) {
+				if (ox >= g.out_w) continue;
+				const int fx = px_pos - ox * g.s_w;
+				const long long o = (((long long)b * g.out_h + oy) * g.out_w + ox) * g.cp + v * 8;
+				float d[8];
+				load8<T>(dy + o, d);
+				if (g.type == CB200_POOL_MAX) {
+					const uint2 packed = *reinterpret_cast<const uint2*>(map + o);
+					const int loc = fy * g.p_w + fx;
+#pragma unroll
+					for (int j = 0; j < 8; j++) {
+						const uint32_t m = ((j < 4 ? packed.x : packed.y) >> (8 * (j & 3))) & 0xffu;
+						if ((int)m == loc) acc[j] += d[j];
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < 8; j++) acc[j] += d[j] * inv_vol;
+				}
+			}
+		}
+		const long long o_in = (((long long)b * g.in_h + iy) * g.in_w + ix) * g.cp + v * 8;
+		if (hook) {
+			float pv[8];
+			load8<T>(prev_out + o_in, pv);
+			const bool dead = mask_tail && b >= g.length;
+#pragma unroll
+			for (int j = 0; j < 8; j++) acc[j] = dead ? 0.0f : activ_deriv_mul(prev_activ, acc[j], pv[j]);
+		}
+		store8<T>(dx + o_in, acc);
+	}
+}
+
+static int fill_geom(const cb200_pool_desc* d, PoolGeom& g) {
+	CB_ARG(d != nullptr && d->batch > 0 && d->c > 0);
+	CB_ARG(d->p_h > 0 && d->p_w > 0 && d->stride_h > 0 && d->stride_w > 0);
+	CB_ARG(d->p_h * d->p_w < 255);
+	g.batch = d->batch; g.length = d->length; g.c = d->c; g.cp = round8(d->c);
+	g.in_h = d->in_h; g.in_w = d->in_w; g.out_h = d->out_h; g.out_w = d->out_w;
+	g.p_h = d->p_h; g.p_w = d->p_w; g.s_h = d->stride_h; g.s_w = d->stride_w; g.pad_h = d->pad_h; g.pad_w = d->pad_w;
+	g.type = d->pool_type; g.activ = d->activ;
+	return CB200_OK;
+}
+}  // namespace cb200
+using namespace cb200;
+
+extern "C" {
+
+int cb200_pool_forward(const cb200_pool_desc* d, const void* x, void* y, uint8_t* map, void* s) {
+	CB_REQUIRE_DEVICE();
+	PoolGeom g;
+	int rc = fill_geom(d, g); if (rc) return rc;
+	long long total = (long long)g.batch * g.out_h * g.out_w * (g.cp >> 3);
+	CB_DISPATCH_DTYPE(d->dtype, T, (pool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, (T*)y, map, g)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_pool_backward(const cb200_pool_desc* d, const void* dy, const uint8_t* map, void* dx,
+                        const cb200_activ* prev_activ, const void* prev_out, void* s) {
+	CB_REQUIRE_DEVICE();
+	PoolGeom g;
+	int rc = fill_geom(d, g); if (rc) return rc;
+	CB_ARG(d->pool_type != CB200_POOL_MAX || map != nullptr);
+	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
+	if (prev_activ) pa = *prev_activ;
+	long long total = (long long)g.batch * g.in_h * g.in_w * (g.cp >> 3);
+	CB_DISPATCH_DTYPE(d->dtype, T, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)dy, map, (T*)dx, (const T*)prev_out, pa, g)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// runtime.cu - device bring-up, memory/stream/event/graph plumbing and layout import/export
+// of the B200-native CIANNA core.  Replaces src/cuda/cuda_main.cu of the reference
+// (init_cuda :922-1067, typed alloc/copy helpers :108-379, event timers :533-588).
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace cb200 {
+bool g_have_device = false;
+cudaStream_t g_stream = nullptr;
+int g_num_sms = 148;
+long long g_launches = 0;
+static char g_error[1024] = "no error";
+const char* g_last_conv_impl = "none";
+int g_force_simt = 0;
+
+void set_error(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, ap);
+	va_end(ap);
+}
+}  // namespace cb200
+using namespace cb200;
+
+extern "C" {
+
+const char* cb200_last_error(void) { return g_error; }
+const char* cb200_version(void) { return "cianna_b200 0.1 (sm_100a)"; }
+const char* cb200_last_conv_impl(void) { return g_last_conv_impl; }
+void cb200_force_simt(int on) { g_force_simt = on; }
+long long cb200_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+int cb200_round_channels(int c) { return round8(c); }
+size_t cb200_dtype_size(int dtype) { return dtype == CB200_FP32 ? 4 : 2; }
+
+int cb200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int cb200_init(int device) {
+	int n = cb200_device_count();
+	if (n <= 0) { set_error("cb200_init: no CUDA device visible; this core has no CPU fallback"); return CB200_ERR_NO_DEVICE; }
+	if (device >= 0) CB_CUDA(cudaSetDevice(device));
+	int dev = 0;
+	CB_CUDA(cudaGetDevice(&dev));
+	cudaDeviceProp prop;
+	CB_CUDA(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major != 10) {
+		set_error("cb200_init: device %d is sm_%d%d; this library only carries sm_100a code", dev, prop.major, prop.minor);
+		return CB200_ERR_UNSUPPORTED;
+	}
+	g_num_sms = prop.multiProcessorCount;
+	if (!g_stream) CB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+	g_have_device = true;
+	return CB200_OK;
+}
+
+// ---------------------------------------------------------------- memory
+int cb200_malloc(void** p, size_t bytes) {
+	CB_REQUIRE_DEVICE();
+	if (bytes == 0) bytes = 16;
+	CB_CUDA(cudaMalloc(p, bytes));
+	CB_CUDA(cudaMemsetAsync(*p, 0, bytes, g_stream));
+	return CB200_OK;
+}
+int cb200_free(void* p) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaFree(p)); return CB200_OK; }
+int cb200_host_alloc(void** p, size_t bytes) {
+	CB_REQUIRE_DEVICE();
+	CB_CUDA(cudaMallocHost(p, bytes ? bytes : 16));
+	memset(*p, 0, bytes);
+	return CB200_OK;
+}
+int cb200_host_free(void* p) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaFreeHost(p)); return CB200_OK; }
+int cb200_memset(void* p, int byte, size_t bytes, void* s) {
+	CB_REQUIRE_DEVICE(); CB_CUDA(cudaMemsetAsync(p, byte, bytes, as_stream(s))); return CB200_OK;
+}
+int cb200_h2d(void* d, const void* h, size_t bytes, void* s) {
+	CB_REQUIRE_DEVICE(); CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, as_stream(s))); return CB200_OK;
+}
+int cb200_d2h(void* h, const void* d, size_t bytes, void* s) {
+	CB_REQUIRE_DEVICE(); CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, as_stream(s))); return CB200_OK;
+}
+int cb200_d2d(void* d, const void* s_, size_t bytes, void* s) {
+	CB_REQUIRE_DEVICE(); CB_CUDA(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, as_stream(s))); return CB200_OK;
+}
+int cb200_stream_create(void** s) {
+	CB_REQUIRE_DEVICE(); cudaStream_t st; CB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = st; return CB200_OK;
+}
+int cb200_stream_destroy(void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamDestroy((cudaStream_t)s)); return CB200_OK; }
+int cb200_stream_sync(void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamSynchronize(as_stream(s))); return CB200_OK; }
+int cb200_device_sync(void) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaDeviceSynchronize()); return CB200_OK; }
+int cb200_stream_wait(void* s, void* on) {
+	CB_REQUIRE_DEVICE();
+	cudaEvent_t ev;
+	CB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	CB_CUDA(cudaEventRecord(ev, as_stream(on)));
+	CB_CUDA(cudaStreamWaitEvent(as_stream(s), ev, 0));
+	CB_CUDA(cudaEventDestroy(ev));
+	return CB200_OK;
+}
+int cb200_event_create(void** ev) { CB_REQUIRE_DEVICE(); cudaEvent_t e; CB_CUDA(cudaEventCreate(&e)); *ev = e; return CB200_OK; }
+int cb200_event_destroy(void* ev) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return CB200_OK; }
+int cb200_event_record(void* ev, void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventRecord((cudaEvent_t)ev, as_stream(s))); return CB200_OK; }
+int cb200_event_elapsed_ms(void* a, void* b, float* ms) {
+	CB_REQUIRE_DEVICE();
+	CB_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+	CB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+	return CB200_OK;
+}
+int cb200_graph_begin(void* s) {
+	CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamBeginCapture(as_stream(s), cudaStreamCaptureModeThreadLocal)); return CB200_OK;
+}
+int cb200_graph_end(void* s, void** exec) {
+	CB_REQUIRE_DEVICE();
+	cudaGraph_t g;
+	CB_CUDA(cudaStreamEndCapture(as_stream(s), &g));
+	cudaGraphExec_t ge;
+	CB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+	CB_CUDA(cudaGraphDestroy(g));
+	*exec = ge;
+	return CB200_OK;
+}
+int cb200_graph_launch(void* exec, void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, as_stream(s))); g_launches++; return CB200_OK; }
+int cb200_graph_destroy(void* exec) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)exec)); return CB200_OK; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- casts
+template <typename T>
+__global__ void cast_from_f32_kernel(T* __restrict__ dst, const float* __restrict__ src, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		dst[i] = from_f32<T>(src[i]);
+}
+template <typename T>
+__global__ void cast_to_f32_kernel(float* __restrict__ dst, const T* __restrict__ src, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		dst[i] = to_f32<T>(src[i]);
+}
+
+// ---------------------------------------------------------------- layout conversions
+// dataset row [C*H*W + 1] (channel-major planes, bias slot last) -> act[b][y][x][Cp]
+template <typename T>
+__global__ void import_input_kernel(T* __restrict__ dst, const T* __restrict__ src, int batch, int c, int hw, int cp) {
+	size_t total = (size_t)batch * hw * cp;
+	size_t row = (size_t)c * hw + 1;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		int ch = (int)(i % cp);
+		size_t pix = i / cp;
+		int p = (int)(pix % hw);
+		size_t b = pix / hw;
+		dst[i] = ch < c ? src[b * row + (size_t)ch * hw + p] : from_f32<T>(0.0f);
+	}
+}
+// reference activation layout [C][B][HW] (FP32) -> internal
+template <typename T>
+__global__ void import_cbhw_kernel(T* __restrict__ dst, const float* __restrict__ src, int batch, int c, int hw, int cp) {
+	size_t total = (size_t)batch * hw * cp;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		int ch = (int)(i % cp);
+		size_t pix = i / cp;
+		int p = (int)(pix % hw);
+		size_t b = pix / hw;
+		dst[i] = ch < c ? from_f32<T>(src[((size_t)ch * batch + b) * hw + p]) : from_f32<T>(0.0f);
+	}
+}
+template <typename T>
+__global__ void export_cbhw_kernel(float* __restrict__ dst, const T* __restrict__ src, int batch, int c, int hw, int cp) {
+	size_t total = (size_t)c * batch * hw;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		int p = (int)(i % hw);
+		size_t r = i / hw;
+		int b = (int)(r % batch);
+		int ch = (int)(r / batch);
+		dst[i] = to_f32<T>(src[((size_t)b * hw + p) * cp + ch]);
+	}
+}
+__global__ void export_pool_map_kernel(int32_t* __restrict__ dst, const uint8_t* __restrict__ src, int batch, int c, int hw, int cp) {
+	size_t total = (size_t)c * batch * hw;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		int p = (int)(i % hw);
+		size_t r = i / hw;
+		int b = (int)(r % batch);
+		int ch = (int)(r / batch);
+		uint8_t v = src[((size_t)b * hw + p) * cp + ch];
+		dst[i] = v == 255 ? -1 : (int32_t)v;
+	}
+}
+template <typename T>
+__global__ void export_dense_kernel(float* __restrict__ dst, const T* __restrict__ src, int batch, int n, int cp, float bias_node) {
+	size_t total = (size_t)batch * (n + 1);
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		int j = (int)(i % (n + 1));
+		size_t b = i / (n + 1);
+		dst[i] = j < n ? to_f32<T>(src[b * cp + j]) : bias_node;
+	}
+}
+
+extern "C" {
+
+int cb200_cast_from_f32(void* dst, int dtype, const float* src, size_t n, void* s) {
+	CB_REQUIRE_DEVICE();
+	if (n == 0) return CB200_OK;
+	CB_DISPATCH_DTYPE(dtype, T, (cast_from_f32_kernel<T><<<grid_for((long long)n, 256), 256, 0, as_stream(s)>>>((T*)dst, src, n)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_cast_to_f32(float* dst, const void* src, int dtype, size_t n, void* s) {
+	CB_REQUIRE_DEVICE();
+	if (n == 0) return CB200_OK;
+	CB_DISPATCH_DTYPE(dtype, T, (cast_to_f32_kernel<T><<<grid_for((long long)n, 256), 256, 0, as_stream(s)>>>(dst, (const T*)src, n)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+// round-toward-zero host conversion (the reference converts datasets on the host with
+// __float2half_rz / __float2bfloat16_rz, src/cuda/cuda_main.cu:790,813)
+static inline uint16_t f32_to_bf16_rz(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }
+static inline uint16_t f32_to_f16_rz(float f) {
+	uint32_t u; memcpy(&u, &f, 4);
+	uint32_t sign = (u >> 16) & 0x8000u;
+	int32_t exp = (int32_t)((u >> 23) & 0xff) - 127 + 15;
+	uint32_t man = u & 0x7fffffu;
+	if (((u >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));  // inf / nan
+	if (exp >= 31) return (uint16_t)(sign | 0x7bffu);                                       // RZ: clamp to max finite
+	if (exp <= 0) {
+		if (exp < -10) return (uint16_t)sign;
+		man |= 0x800000u;
+		return (uint16_t)(sign | (man >> (14 - exp)));                                      // subnormal, truncated
+	}
+	return (uint16_t)(sign | ((uint32_t)exp << 10) | (man >> 13));
+}
+int cb200_host_cast_from_f32(void* dst, int dtype, const float* src, size_t n) {
+	if (dtype == CB200_FP32) { memcpy(dst, src, n * 4); return CB200_OK; }
+	uint16_t* o = (uint16_t*)dst;
+	if (dtype == CB200_FP16) for (size_t i = 0; i < n; i++) o[i] = f32_to_f16_rz(src[i]);
+	else if (dtype == CB200_BF16) for (size_t i = 0; i < n; i++) o[i] = f32_to_bf16_rz(src[i]);
+	else { set_error("cb200_host_cast_from_f32: unknown dtype %d", dtype); return CB200_ERR_ARG; }
+	return CB200_OK;
+}
+
+int cb200_import_input(void* dst, const void* src, int dtype, int batch, int c, int h, int w, void* s) {
+	CB_REQUIRE_DEVICE();
+	int cp = round8(c);
+	long long total = (long long)batch * h * w * cp;
+	CB_DISPATCH_DTYPE(dtype, T, (import_input_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((T*)dst, (const T*)src, batch, c, h * w, cp)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_import_cbhw(void* dst, int dtype, const float* src, int batch, int c, int h, int w, void* s) {
+	CB_REQUIRE_DEVICE();
+	int cp = round8(c);
+	long long total = (long long)batch * h * w * cp;
+	CB_DISPATCH_DTYPE(dtype, T, (import_cbhw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((T*)dst, src, batch, c, h * w, cp)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_export_cbhw(float* dst, const void* src, int dtype, int batch, int c, int h, int w, void* s) {
+	CB_REQUIRE_DEVICE();
+	int cp = round8(c);
+	long long total = (long long)batch * h * w * c;
+	CB_DISPATCH_DTYPE(dtype, T, (export_cbhw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(dst, (const T*)src, batch, c, h * w, cp)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_export_pool_map(int32_t* dst, const uint8_t* src, int batch, int c, int h, int w, void* s) {
+	CB_REQUIRE_DEVICE();
+	int cp = round8(c);
+	long long total = (long long)batch * h * w * c;
+	export_pool_map_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(dst, src, batch, c, h * w, cp);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+int cb200_export_dense(float* dst, const void* src, int dtype, int batch, int n, float bias_node, void* s) {
+	CB_REQUIRE_DEVICE();
+	int cp = round8(n);
+	long long total = (long long)batch * (n + 1);
+	CB_DISPATCH_DTYPE(dtype, T, (export_dense_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(dst, (const T*)src, batch, n, cp, bias_node)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+/*
+ * cianna.h - host-side C library of the B200-native CIANNA core (libcianna_host.so).
+ *
+ * Mirrors the operator interface of the reference's host layer for the hot path
+ * (names, argument order/meaning and exit-on-error behaviour of src/prototypes.h:36-110:
+ * init_network, create_dataset, conv_create, pool_create, norm_create, dense_create,
+ * train_network, forward_testset, compute_error, save_network, load_network, set_frozen_layers),
+ * so that upstream call sites (src/python_module.c, src/main.c) and the parity tests read the same
+ * on both sides.  The implementation is new: every layer object drives the C-ABI of
+ * include/cianna_b200.h; there is exactly one compute method, "C_CUDA", and no CPU fallback.
+ *
+ * Object model differences with upstream (internal only): activations live on the device in the
+ * core's channels-last layout, layer->output / layer->delta_o are device pointers in that layout;
+ * use cb_layer_export_* to read them back in the reference's [C][B][H*W] / [B][n+1] layouts.
+ */
+#ifndef CIANNA_HOST_H
+#define CIANNA_HOST_H
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <stddef.h>
+#include "cianna_b200.h"
+
+#ifndef MAX_LAYERS_NB
+#define MAX_LAYERS_NB 200
+#endif
+#ifndef MAX_NETWORKS_NB
+#define MAX_NETWORKS_NB 10
+#endif
+
+/* same vocabulary / numeric values as upstream src/structs.h:32-43,69-70 (they appear in save files
+ * and in the Python-level strings) */
+enum layer_type_enum { CONV, POOL, DENSE, NORM, LRN };
+enum activation_functions_enum { RELU, LOGISTIC, SOFTMAX, YOLO, LINEAR };
+enum inference_modes_enum { AVG_MODEL, MC_MODEL };
+enum batch_param_enum { OFF, SGD, FULL };
+enum compute_method_enum { C_NAIV, C_BLAS, C_CUDA };
+enum memory_localization_enum { NO_LOC, HOST, DEVICE };
+enum pool_types_enum { MAX_pool, AVG_pool };
+enum TC_comp_mode { FP32C_FP32A, TF32C_FP32A, FP16C_FP32A, FP16C_FP16A, BF16C_FP32A };
+
+typedef struct network network;
+typedef struct layer layer;
+
+typedef struct Dataset {
+	int size;              /* number of samples */
+	int nb_batch;
+	int localization;      /* NO_LOC / HOST / DEVICE */
+	void **input;          /* [nb_batch] pinned host batches, compute dtype, [batch_size][input_dim+1] (bias slot last) */
+	void **target;         /* [nb_batch] pinned host batches, compute dtype, [batch_size][output_dim] */
+	void **input_device;   /* device-resident copies when dynamic_load == 0 */
+	void **target_device;
+} Dataset;
+
+struct layer {
+	int type;
+	int activation_type;
+	int index;
+	network *c_network;
+	layer *previous;
+	void *param;
+	void *output;          /* device, internal layout [B][h][w][Cp] */
+	void *delta_o;         /* device, same shape (NULL when inference_only) */
+	int out_c, out_h, out_w;
+	int frozen;
+	float bias_value;
+	float dropout_rate;
+	cb200_activ activ;
+	void (*forward)(layer *current);
+	void (*backprop)(layer *current);
+	int nb_params;
+	float time_fwd, time_back;
+};
+
+typedef struct conv_param {
+	int f_size[3], stride[3], padding[3], int_padding[3];
+	int nb_filters, nb_area[3], prev_size[3], prev_depth;
+	int flat_f_size;
+	cb200_conv_desc desc;
+	cb200_conv_weights w;
+	size_t grad_offset;    /* position of [grad | grad_b] in the network's gradient arena */
+	size_t grad_len;
+} conv_param;
+
+typedef struct pool_param {
+	int p_size[3], stride[3], padding[3], nb_area[3], prev_size[3];
+	int nb_maps, prev_depth, pool_type, global;
+	cb200_pool_desc desc;
+	uint8_t *pool_map;     /* device */
+} pool_param;
+
+typedef struct norm_param {
+	int group_size, set_off, nb_group, n_dim, dim_offset;
+	cb200_norm_desc desc;
+	float *gamma, *beta, *gamma_update, *beta_update;   /* device, FP32 [nb_group] */
+	float *mean, *var, *d_gamma, *d_beta;               /* device, FP32 [batch][nb_group] */
+	float *gsum;                                        /* device, FP32 [2][nb_group] inside the gradient arena */
+	void *workspace;
+	size_t grad_offset;
+} norm_param;
+
+typedef struct dense_param {
+	int in_size;           /* inputs incl. the bias node */
+	int nb_neurons;
+	int prev_c, prev_h, prev_w;
+	cb200_conv_desc desc;  /* a dense layer runs as a convolution whose filter covers the whole input map */
+	cb200_conv_weights w;
+	size_t grad_offset, grad_len;
+} dense_param;
+
+struct network {
+	layer *net_layers[MAX_LAYERS_NB];
+	int id;
+	int compute_method;
+	int inference_only;
+	int nb_layers;
+	float input_bias;
+	float learning_rate, momentum, decay, weight_decay;
+	Dataset train, test, valid;
+	Dataset train_buf, test_buf, valid_buf;
+	int in_dims[4];
+	size_t input_dim;
+	int output_dim;
+	int out_size;
+	int batch_size;
+	int batch_param;
+	int iter;
+	int is_inference;
+	int inference_drop_mode;
+	int no_error;
+	int perf_eval;
+	long long int total_nb_param;
+	long long int memory_footprint;
+	int adv_size;
+	int length;
+	float TC_scale_factor;
+	int dynamic_load;
+	int use_cuda_TC;       /* enum TC_comp_mode */
+	int dtype;             /* cb200_dtype derived from use_cuda_TC */
+
+	/* device-side state of one step */
+	void *input_raw;       /* current batch in dataset layout (device) */
+	void *input;           /* current batch in internal layout (device) */
+	void *target;          /* current target batch (device, compute dtype) */
+	float *loss_dev;       /* FP32 [batch_size] per-sample loss */
+	float *loss_host;      /* pinned */
+	float *hyper_dev;      /* CB200_HYPER_LEN floats */
+	float *grad_arena;     /* all raw gradients, contiguous (all-reduced in data-parallel runs) */
+	size_t grad_arena_len;
+	int training_ready;
+	int dp_world;          /* data-parallel world size (1 = single GPU) */
+	float last_batch_loss;
+	double last_epoch_loss;
+	float last_items_per_s;
+};
+
+extern network *networks[MAX_NETWORKS_NB];
+extern int nb_networks;
+extern int is_init;
+
+/* ---- upstream-compatible API (src/prototypes.h) ---- */
+void init_network(int network_number, int u_input_dim[4], int u_output_dim, float in_bias, int u_batch_size,
+	const char *compute_method_string, int u_dynamic_load, const char *cuda_TC_string, int inference_only, int no_logo, int adv_size);
+Dataset create_dataset(network *net, int nb_elem);
+void free_dataset(Dataset *data);
+int nb_area_comp(int size, int f_size, int padding, int int_padding, int stride);
+int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int *stride, int *padding,
+	int *int_padding, int *in_shape, const char *activation, float *bias, float drop_rate,
+	const char *init_fct, float init_scaling, FILE *f_load, int f_bin);
+int pool_create(network *net, layer *previous, int *pool_size, int *stride, int *padding,
+	const char *char_pool_type, const char *activation, int global, float drop_rate);
+int norm_create(network *net, layer *previous, const char *norm_type, const char *activation, int group_size, int set_off, FILE *f_load, int f_bin);
+int dense_create(network *net, layer *previous, int nb_neurons, const char *activation, float *bias,
+	float drop_rate, int strict_size, const char *init_fct, float init_scaling, FILE *f_load, int f_bin);
+void conv_save(FILE *f, layer *current, int f_bin);
+void conv_load(network *net, FILE *f, int f_bin);
+void pool_save(FILE *f, layer *current, int f_bin);
+void pool_load(network *net, FILE *f, int f_bin);
+void norm_save(FILE *f, layer *current, int f_bin);
+void norm_load(network *net, FILE *f, int f_bin);
+void dense_save(FILE *f, layer *current, int f_bin);
+void dense_load(network *net, FILE *f, int f_bin);
+void save_network(network *net, const char *filename, int f_bin);
+void load_network(network *net, const char *filename, int epoch, int nb_layers, int f_bin);
+void set_frozen_layers(network *net, int *tab, int dim);
+void train_network(network *net, int nb_epochs, int control_interv, float u_begin_learning_rate, float u_end_learning_rate, float u_momentum,
+	float u_decay, float u_weight_decay, int show_confmat, int save_net, int save_bin, int shuffle_gpu, int shuffle_every, float c_TC_scale_factor, int silent);
+void forward_testset(network *net, int saving, int repeat, int drop_mode, int silent);
+void compute_error(network *net, Dataset data, int saving, int confusion_matrix, int repeat, int silent);
+void perf_eval_display(network *net);
+
+/* activation helpers (src/activ_functions.c:260-374, 580-610) */
+void load_activ_param(layer *current, const char *activ);
+void set_activ_defaults(layer *current, const char *activ);
+void print_string_activ_param(layer *current, char *activ);
+void print_activ_param(FILE *f, layer *current, int f_bin);
+/* initialisers (src/initializers.c) */
+void init_weights(float *tab, int dim_in, int dim_out, const char *init_fct, float init_scaling);
+
+/* ---- additions of this implementation ---- */
+/* copy one sample (FP32) into a dataset batch slot, converting to the compute dtype like upstream's
+ * Dataset.cont_copy (src/cuda/cuda_main.cu:355-371) */
+void dataset_set_sample(network *net, Dataset *data, int index, const float *input, const float *target);
+void dataset_upload(network *net, Dataset *data);   /* dynamic_load == 0: make device-resident copies */
+/* data-parallel set-up: call on every rank after init_network, before training */
+void cb_dp_unique_id(void *id128);
+void cb_dp_init(network *net, const void *id128, int rank, int world);
+/* one mini-batch from explicit host arrays (FP32, dataset layout [B][input_dim+1] and [B][output_dim]) */
+void cb_load_batch(network *net, const float *input, const float *target);
+void cb_load_batch_typed(network *net, const void *input_typed, const void *target_typed);
+void cb_forward(network *net, int length, int is_inference);
+void cb_backward(network *net, float lr, float momentum, float weight_decay);   /* delta + backprop + update */
+float cb_batch_loss(network *net);                                               /* sum over samples / length */
+void cb_train_step(network *net, float lr, float momentum, float weight_decay); /* forward + backward on the loaded batch */
+void cb_sync(void);
+/* read-back in the reference's layouts; dst sized by the caller */
+void cb_layer_export_output(network *net, int l, float *dst);
+void cb_layer_export_delta(network *net, int l, float *dst);
+void cb_layer_export_pool_map(network *net, int l, int *dst);
+size_t cb_layer_weight_count(network *net, int l);
+void cb_layer_get_weights(network *net, int l, float *dst);   /* conv/dense: FP32 master (reference layout); norm: gamma then beta */
+void cb_layer_set_weights(network *net, int l, const float *src);
+void cb_layer_get_moment(network *net, int l, float *dst);
+void cb_layer_get_norm_stats(network *net, int l, float *mean, float *var, float *d_gamma, float *d_beta);
+void cb_layer_shape(network *net, int l, int *out4);         /* c, h, w, type */
+const char *cb_layer_conv_impl(network *net, int l);          /* which kernel family ran last ("tcgen05"/"simt") */
+
+#define CB_CHECK(call) do { int rc__ = (call); if (rc__ != 0) { \
+	printf("\nERROR: %s failed (%d): %s\n", #call, rc__, cb200_last_error()); exit(EXIT_FAILURE); } } while (0)
+
+#endif

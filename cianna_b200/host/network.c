@@ -1,0 +1,714 @@
+/*
+ * network.c - network object, datasets, the mini-batch training / inference loops and checkpoint I/O.
+ *
+ * Same call surface and semantics as upstream src/auxil.c (init_network :52-297, create_dataset :299-363,
+ * save/load_network :468-611, compute_error :1100-1659, train_network :1662-1972, forward_testset :1975-2039);
+ * different mechanics: no per-layer device synchronisation, loss reduced on the device (one float per
+ * sample comes back instead of the whole per-element loss tensor), raw gradients kept in one arena that is
+ * all-reduced across GPUs (NCCL) before a fused optimizer pass.
+ */
+#include <math.h>
+#include <string.h>
+#include <time.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include "cianna.h"
+
+network *networks[MAX_NETWORKS_NB];
+int nb_networks = 0;
+int is_init = 0;
+
+static double now_s(void)
+{
+	struct timeval tv;
+	gettimeofday(&tv, NULL);
+	return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+/* ------------------------------------------------------------------ init */
+void init_network(int network_number, int u_input_dim[4], int u_output_dim, float in_bias, int u_batch_size,
+	const char *compute_method_string, int u_dynamic_load, const char *cuda_TC_string, int inference_only, int no_logo, int adv_size)
+{
+	network *net;
+	const char *mode_name = "FP32C_FP32A";
+	int mode = FP32C_FP32A;
+
+	if (!is_init && !no_logo)
+		printf("############################################################\n"
+		       "CIANNA B200-native core (%s), API of CIANNA V-1.0.0.0\n"
+		       "############################################################\n\n", cb200_version());
+	if (network_number < 0 || network_number >= MAX_NETWORKS_NB) { printf("ERROR: network id out of range\n"); exit(EXIT_FAILURE); }
+	if (strcmp(compute_method_string, "C_CUDA") != 0) {
+		printf("ERROR: compute method %s is not available: this build only carries the CUDA (sm_100a) back-end and has no CPU fallback.\n", compute_method_string);
+		exit(EXIT_FAILURE);
+	}
+	if (strcmp(cuda_TC_string, "off") == 0 || strcmp(cuda_TC_string, "FP32C_FP32A") == 0) { mode = FP32C_FP32A; mode_name = "FP32C_FP32A"; }
+	else if (strcmp(cuda_TC_string, "on") == 0 || strcmp(cuda_TC_string, "FP16C_FP32A") == 0) { mode = FP16C_FP32A; mode_name = "FP16C_FP32A"; }
+	else if (strcmp(cuda_TC_string, "BF16C_FP32A") == 0) { mode = BF16C_FP32A; mode_name = "BF16C_FP32A"; }
+	else if (strcmp(cuda_TC_string, "TF32C_FP32A") == 0 || strcmp(cuda_TC_string, "FP16C_FP16A") == 0) {
+		printf("ERROR: mixed precision mode %s is not provided by the B200 core (available: FP32C_FP32A, FP16C_FP32A, BF16C_FP32A).\n", cuda_TC_string);
+		exit(EXIT_FAILURE);
+	} else { printf("ERROR: unknown mixed_precision string %s\n", cuda_TC_string); exit(EXIT_FAILURE); }
+
+	net = (network *)calloc(1, sizeof(network));
+	networks[network_number] = net;
+	net->id = network_number;
+	net->compute_method = C_CUDA;
+	net->dynamic_load = u_dynamic_load;
+	net->use_cuda_TC = mode;
+	net->dtype = mode == FP32C_FP32A ? CB200_FP32 : (mode == FP16C_FP32A ? CB200_FP16 : CB200_BF16);
+	srand((unsigned)time(NULL));
+	CB_CHECK(cb200_init(-1));
+	if (network_number >= nb_networks) nb_networks = network_number + 1;
+	is_init = 1;
+
+	net->in_dims[0] = u_input_dim[0]; net->in_dims[1] = u_input_dim[1];
+	net->in_dims[2] = u_input_dim[2]; net->in_dims[3] = u_input_dim[3];
+	net->input_dim = ((size_t)u_input_dim[0]) * u_input_dim[1] * u_input_dim[2] * u_input_dim[3];
+	net->output_dim = u_output_dim;
+	net->input_bias = in_bias;
+	if (u_batch_size > 1) { net->batch_size = u_batch_size; net->batch_param = OFF; }
+	else if (u_batch_size == 1) { net->batch_size = 1; net->batch_param = SGD; printf(" Automatically switch to SGD scheme (batch_size = 1)\n"); }
+	else { net->batch_size = 16; net->batch_param = FULL; printf(" Undefined batch size -> automatic value is 16\n"); }
+	net->inference_only = inference_only;
+	net->inference_drop_mode = AVG_MODEL;
+	net->perf_eval = 1;
+	net->adv_size = adv_size <= 0 ? 30 : adv_size;
+	net->TC_scale_factor = 1.0f;
+	net->dp_world = 1;
+	net->length = net->batch_size;
+	net->train_buf.localization = NO_LOC; net->test_buf.localization = NO_LOC; net->valid_buf.localization = NO_LOC;
+
+	{
+		size_t es = cb200_dtype_size(net->dtype);
+		CB_CHECK(cb200_malloc(&net->input_raw, (size_t)net->batch_size * (net->input_dim + 1) * es));
+		CB_CHECK(cb200_malloc(&net->input, (size_t)net->batch_size * net->in_dims[0] * net->in_dims[1] * cb200_round_channels(net->in_dims[3]) * es));
+		CB_CHECK(cb200_malloc(&net->target, (size_t)net->batch_size * (net->output_dim > 0 ? net->output_dim : 1) * es));
+		CB_CHECK(cb200_malloc((void **)&net->loss_dev, (size_t)net->batch_size * sizeof(float)));
+		CB_CHECK(cb200_host_alloc((void **)&net->loss_host, (size_t)net->batch_size * sizeof(float)));
+		CB_CHECK(cb200_malloc((void **)&net->hyper_dev, CB200_HYPER_LEN * sizeof(float)));
+	}
+	printf("Network (id: %d) initialized with : \nInput dimensions: %dx%dx%dx%d \nOutput dimension: %d \nBatch size: %d \n"
+	       "Using CUDA (%s) compute method \nInference only: %d\n\n",
+		net->id, net->in_dims[0], net->in_dims[1], net->in_dims[2], net->in_dims[3], net->output_dim, net->batch_size, mode_name, inference_only);
+	if (net->dynamic_load) printf("Dynamic load ENABLED\n\n");
+}
+
+/* ------------------------------------------------------------------ datasets */
+Dataset create_dataset(network *net, int nb_elem)
+{
+	Dataset data;
+	int i, j;
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t in_elems = (size_t)net->batch_size * (net->input_dim + 1);
+	size_t out_elems = (size_t)net->batch_size * net->output_dim;
+	float bias = net->input_bias;
+	unsigned char bias_typed[4];
+
+	memset(&data, 0, sizeof(data));
+	data.size = nb_elem;
+	data.nb_batch = (nb_elem - 1) / net->batch_size + 1;
+	data.localization = HOST;
+	data.input = (void **)calloc(data.nb_batch, sizeof(void *));
+	data.target = (void **)calloc(data.nb_batch, sizeof(void *));
+	cb200_host_cast_from_f32(bias_typed, net->dtype, &bias, 1);
+	for (i = 0; i < data.nb_batch; i++) {
+		CB_CHECK(cb200_host_alloc(&data.input[i], in_elems * es));
+		CB_CHECK(cb200_host_alloc(&data.target[i], (out_elems ? out_elems : 1) * es));
+		for (j = 0; j < net->batch_size; j++)
+			memcpy((char *)data.input[i] + ((size_t)j * (net->input_dim + 1) + net->input_dim) * es, bias_typed, es);
+	}
+	return data;
+}
+
+void free_dataset(Dataset *data)
+{
+	int i;
+	if (data->input == NULL) return;
+	for (i = 0; i < data->nb_batch; i++) {
+		cb200_host_free(data->input[i]);
+		cb200_host_free(data->target[i]);
+		if (data->input_device) { cb200_free(data->input_device[i]); cb200_free(data->target_device[i]); }
+	}
+	free(data->input); free(data->target);
+	free(data->input_device); free(data->target_device);
+	memset(data, 0, sizeof(*data));
+}
+
+void dataset_set_sample(network *net, Dataset *data, int index, const float *input, const float *target)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	int b = index / net->batch_size, j = index % net->batch_size;
+	if (index < 0 || index >= data->size) { printf("ERROR: dataset_set_sample index out of range\n"); exit(EXIT_FAILURE); }
+	if (input != NULL)
+		cb200_host_cast_from_f32((char *)data->input[b] + (size_t)j * (net->input_dim + 1) * es, net->dtype, input, net->input_dim);
+	if (target != NULL)
+		cb200_host_cast_from_f32((char *)data->target[b] + (size_t)j * net->output_dim * es, net->dtype, target, net->output_dim);
+}
+
+void dataset_upload(network *net, Dataset *data)
+{
+	int i;
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t in_bytes = (size_t)net->batch_size * (net->input_dim + 1) * es;
+	size_t out_bytes = (size_t)net->batch_size * net->output_dim * es;
+	if (data->input_device != NULL) return;
+	data->input_device = (void **)calloc(data->nb_batch, sizeof(void *));
+	data->target_device = (void **)calloc(data->nb_batch, sizeof(void *));
+	for (i = 0; i < data->nb_batch; i++) {
+		CB_CHECK(cb200_malloc(&data->input_device[i], in_bytes));
+		CB_CHECK(cb200_malloc(&data->target_device[i], out_bytes ? out_bytes : 16));
+		CB_CHECK(cb200_h2d(data->input_device[i], data->input[i], in_bytes, NULL));
+		CB_CHECK(cb200_h2d(data->target_device[i], data->target[i], out_bytes, NULL));
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+	data->localization = DEVICE;
+}
+
+/* ------------------------------------------------------------------ training preparation */
+static void prepare_training(network *net)
+{
+	int k;
+	size_t total = 0;
+	if (net->training_ready) return;
+	if (net->inference_only) { printf("\nERROR: network was created in inference only mode, it cannot be trained.\n"); exit(EXIT_FAILURE); }
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->type == CONV) {
+			conv_param *p = (conv_param *)l->param;
+			p->grad_offset = total;
+			p->grad_len = cb200_conv_grad_elems(&p->desc) + p->desc.out_c;
+			total += (p->grad_len + 63) & ~(size_t)63;
+		} else if (l->type == DENSE) {
+			dense_param *p = (dense_param *)l->param;
+			p->grad_offset = total;
+			p->grad_len = cb200_conv_grad_elems(&p->desc) + p->desc.out_c;
+			total += (p->grad_len + 63) & ~(size_t)63;
+		}
+	}
+	/* the (tiny) norm gradients sit together at the end: one all-reduce for all of them */
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->type == NORM) {
+			norm_param *p = (norm_param *)l->param;
+			p->grad_offset = total;
+			total += 2 * (size_t)p->nb_group;
+		}
+	}
+	net->grad_arena_len = total;
+	CB_CHECK(cb200_malloc((void **)&net->grad_arena, (total ? total : 1) * sizeof(float)));
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->type == CONV) {
+			conv_param *p = (conv_param *)l->param;
+			p->w.grad = net->grad_arena + p->grad_offset;
+			p->w.grad_b = p->w.grad + cb200_conv_grad_elems(&p->desc);
+		} else if (l->type == DENSE) {
+			dense_param *p = (dense_param *)l->param;
+			p->w.grad = net->grad_arena + p->grad_offset;
+			p->w.grad_b = p->w.grad + cb200_conv_grad_elems(&p->desc);
+		} else if (l->type == NORM) {
+			norm_param *p = (norm_param *)l->param;
+			p->gsum = net->grad_arena + p->grad_offset;
+		}
+	}
+	net->training_ready = 1;
+}
+
+static void last_layer_dims(network *net, int *c, int *h, int *w)
+{
+	layer *last = net->net_layers[net->nb_layers - 1];
+	*c = last->out_c; *h = last->out_h; *w = last->out_w;
+}
+
+static void set_hyper(network *net, float lr, float momentum, float weight_decay)
+{
+	float h[CB200_HYPER_LEN];
+	memset(h, 0, sizeof(h));
+	net->learning_rate = lr; net->momentum = momentum; net->weight_decay = weight_decay;
+	h[0] = lr / (float)(net->batch_size * net->dp_world);
+	h[1] = momentum;
+	h[2] = lr * weight_decay;
+	h[3] = net->TC_scale_factor;
+	h[4] = lr;
+	CB_CHECK(cb200_h2d(net->hyper_dev, h, sizeof(h), NULL));
+}
+
+/* ------------------------------------------------------------------ one mini-batch */
+void cb_load_batch_typed(network *net, const void *input_typed, const void *target_typed)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	CB_CHECK(cb200_h2d(net->input_raw, input_typed, (size_t)net->batch_size * (net->input_dim + 1) * es, NULL));
+	if (target_typed != NULL && net->output_dim > 0)
+		CB_CHECK(cb200_h2d(net->target, target_typed, (size_t)net->batch_size * net->output_dim * es, NULL));
+}
+
+void cb_load_batch(network *net, const float *input, const float *target)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t n_in = (size_t)net->batch_size * (net->input_dim + 1), n_out = (size_t)net->batch_size * net->output_dim;
+	void *ti = malloc(n_in * es), *tt = malloc((n_out ? n_out : 1) * es);
+	cb200_host_cast_from_f32(ti, net->dtype, input, n_in);
+	if (target != NULL) cb200_host_cast_from_f32(tt, net->dtype, target, n_out);
+	cb_load_batch_typed(net, ti, target != NULL ? tt : NULL);
+	CB_CHECK(cb200_stream_sync(NULL));
+	free(ti); free(tt);
+}
+
+static void use_device_batch(network *net, const void *input_dev)
+{
+	/* dataset layout -> channels-last */
+	CB_CHECK(cb200_import_input(net->input, input_dev, net->dtype, net->batch_size, net->in_dims[3], net->in_dims[1], net->in_dims[0], NULL));
+}
+
+void cb_forward(network *net, int length, int is_inference)
+{
+	int k;
+	net->length = length;
+	net->is_inference = is_inference;
+	use_device_batch(net, net->input_raw);
+	for (k = 0; k < net->nb_layers; k++)
+		net->net_layers[k]->forward(net->net_layers[k]);
+}
+
+static void output_deriv_error(network *net, const void *target_dev)
+{
+	layer *last = net->net_layers[net->nb_layers - 1];
+	/* quadratic (LIN / RELU / LOGI outputs) and cross-entropy (SMAX) share delta = (o - t) * S upstream */
+	CB_CHECK(cb200_output_delta(last->delta_o, last->output, target_dev, net->dtype, net->batch_size, net->length,
+		last->out_c, last->out_h, last->out_w, net->TC_scale_factor, NULL));
+	if (last->activation_type == RELU || last->activation_type == LOGISTIC) {
+		printf("\nERROR: RELU / LOGI output layers are not supported by the B200 core yet (use LIN or SMAX).\n");
+		exit(EXIT_FAILURE);
+	}
+}
+
+static void output_error(network *net, const void *target_dev)
+{
+	layer *last = net->net_layers[net->nb_layers - 1];
+	CB_CHECK(cb200_output_loss(net->loss_dev, last->output, target_dev, net->dtype, net->batch_size, net->length,
+		last->out_c, last->out_h, last->out_w, last->activation_type == SOFTMAX ? 1 : 0, NULL));
+}
+
+static void apply_updates(network *net)
+{
+	int k, any_norm = 0;
+	size_t norm_begin = 0, norm_len = 0;
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->type == NORM && !l->frozen) {
+			norm_param *p = (norm_param *)l->param;
+			if (!any_norm) { norm_begin = p->grad_offset; any_norm = 1; }
+			norm_len = p->grad_offset + 2 * (size_t)p->nb_group - norm_begin;
+		}
+	}
+	if (net->dp_world > 1) {
+		if (any_norm) CB_CHECK(cb200_dp_allreduce(net->grad_arena + norm_begin, norm_len, NULL));
+		CB_CHECK(cb200_dp_join(NULL));
+	}
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->frozen) continue;
+		if (l->type == CONV) {
+			conv_param *p = (conv_param *)l->param;
+			CB_CHECK(cb200_conv_update(&p->desc, &p->w, net->hyper_dev, 0, NULL));
+		} else if (l->type == DENSE) {
+			dense_param *p = (dense_param *)l->param;
+			CB_CHECK(cb200_dense_update(&p->desc, &p->w, net->hyper_dev, NULL));
+		} else if (l->type == NORM) {
+			norm_param *p = (norm_param *)l->param;
+			CB_CHECK(cb200_norm_update(&p->desc, p->gamma, p->beta, p->gamma_update, p->beta_update, p->gsum, net->hyper_dev, NULL));
+		}
+	}
+}
+
+static void backward_pass(network *net, const void *target_dev)
+{
+	int k;
+	output_deriv_error(net, target_dev);
+	for (k = net->nb_layers - 1; k >= 0; k--)
+		net->net_layers[k]->backprop(net->net_layers[k]);
+	apply_updates(net);
+}
+
+void cb_backward(network *net, float lr, float momentum, float weight_decay)
+{
+	prepare_training(net);
+	set_hyper(net, lr, momentum, weight_decay);
+	backward_pass(net, net->target);
+}
+
+float cb_batch_loss(network *net)
+{
+	int k;
+	double s = 0.0;
+	output_error(net, net->target);
+	CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+	for (k = 0; k < net->length; k++) s += net->loss_host[k];
+	return net->length > 0 ? (float)(s / net->length) : 0.0f;
+}
+
+void cb_train_step(network *net, float lr, float momentum, float weight_decay)
+{
+	cb_forward(net, net->batch_size, 0);
+	cb_backward(net, lr, momentum, weight_decay);
+}
+
+void cb_sync(void) { CB_CHECK(cb200_device_sync()); }
+
+void cb_dp_unique_id(void *id128) { CB_CHECK(cb200_dp_unique_id(id128)); }
+void cb_dp_init(network *net, const void *id128, int rank, int world)
+{
+	CB_CHECK(cb200_dp_init(id128, rank, world));
+	net->dp_world = world;
+}
+
+/* ------------------------------------------------------------------ training loop */
+static void progress(network *net, int done, int total, double loss, double ips)
+{
+	int i, size = net->adv_size, filled = (int)((double)done / total * size);
+	printf("\r[");
+	for (i = 0; i < size; i++) printf(i < filled ? "#" : "-");
+	printf("] %d/%d  Loss: %.5g  it/s: %.1f ", done, total, loss, ips);
+	fflush(stdout);
+}
+
+void train_network(network *net, int nb_iter, int control_interv, float u_begin_learning_rate, float u_end_learning_rate, float u_momentum,
+	float u_decay, float u_weight_decay, int show_confmat, int save_every, int save_bin, int shuffle_gpu, int shuffle_every, float c_TC_scale_factor, int silent)
+{
+	int i, j, k;
+	char name[200];
+	(void)shuffle_gpu;
+
+	if (net->inference_only) {
+		printf("\n Network was loaded in inference only mode. \n Re-init network with inference only set to false to re-eanble training capability.\n");
+		return;
+	}
+	if (net->train.input == NULL) { printf("\nERROR: no TRAIN dataset defined\n"); exit(EXIT_FAILURE); }
+	/* loss scaling is only honoured by the FP16 mode (src/cuda/cuda_main.cu:63-76) */
+	net->TC_scale_factor = net->use_cuda_TC == FP16C_FP32A ? c_TC_scale_factor : 1.0f;
+	net->momentum = u_momentum; net->decay = u_decay; net->weight_decay = u_weight_decay;
+	{
+		layer *last = net->net_layers[net->nb_layers - 1];
+		net->out_size = last->type == DENSE ? last->out_c + 1 : last->out_c * last->out_h * last->out_w;
+		if (last->type == DENSE && net->out_size != net->output_dim + 1) { printf("\nERROR: last layer size does not match the expected output dimensions.\n"); exit(EXIT_FAILURE); }
+	}
+	prepare_training(net);
+	if (!net->dynamic_load) dataset_upload(net, &net->train);
+	if (net->iter == 0) remove("error.txt");
+
+	for (i = 0; i < nb_iter; i++) {
+		double total_error = 0.0, t_epoch = now_s();
+		float lr = u_end_learning_rate + (u_begin_learning_rate - u_end_learning_rate) * expf(-net->decay * net->iter);
+		if (silent < 1) printf("\n");
+		net->iter++;
+		if (shuffle_every > 0 && (net->iter + 1) % shuffle_every == 0 && net->batch_param != SGD && silent < 1)
+			printf(" (note) dataset shuffling is left to the caller in this build\n");
+		set_hyper(net, lr, net->momentum, net->weight_decay);
+		net->is_inference = 0;
+		for (j = 0; j < net->train.nb_batch; j++) {
+			double t_batch = now_s(), batch_error = 0.0;
+			const void *tgt;
+			net->length = (j == net->train.nb_batch - 1 && net->train.size % net->batch_size > 0) ? net->train.size % net->batch_size : net->batch_size;
+			if (net->dynamic_load) {
+				cb_load_batch_typed(net, net->train.input[j], net->train.target[j]);
+				use_device_batch(net, net->input_raw);
+				tgt = net->target;
+			} else {
+				use_device_batch(net, net->train.input_device[j]);
+				tgt = net->train.target_device[j];
+			}
+			for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
+			/* the loss monitor reads the forward output, so it can be queued before the backward sweep */
+			output_error(net, tgt);
+			CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
+			backward_pass(net, tgt);
+			CB_CHECK(cb200_stream_sync(NULL));
+			for (k = 0; k < net->length; k++) { batch_error += net->loss_host[k]; total_error += net->loss_host[k]; }
+			batch_error /= net->length;
+			if (isnan(batch_error)) { printf("\nERROR: Network divergence detected (Nan)!\n\n"); exit(EXIT_FAILURE); }
+			net->last_batch_loss = (float)batch_error;
+			if (silent < 1) progress(net, j + 1, net->train.nb_batch, batch_error, net->batch_size / (now_s() - t_batch));
+		}
+		net->last_items_per_s = (float)(net->train.size / (now_s() - t_epoch));
+		net->last_epoch_loss = total_error / net->train.size;
+		if (control_interv > 0 && net->iter % control_interv == 0) {
+			if (silent < 1) {
+				printf("\n%*s", 14, " ");
+				printf("Average Training perf: %0.2f it/s |", net->last_items_per_s);
+				printf(" Mean Loss: %.5g |", net->last_epoch_loss);
+				printf(" Learning rate: %.5g | Momentum: %.5g | Weight decay: %.5g\n", lr, net->momentum, net->weight_decay);
+			}
+			if (net->valid.input != NULL) {
+				net->is_inference = 1; net->no_error = 0;
+				compute_error(net, net->valid, 0, show_confmat, 1, silent);
+			}
+		}
+		if (save_every > 0 && net->iter % save_every == 0) {
+			sprintf(name, "net_save/net%d_s%04d.dat", net->id, net->iter);
+			printf("Saving network for iteration: %d (mode: %d)\n", net->iter, save_bin);
+			save_network(net, name, save_bin);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ inference */
+void compute_error(network *net, Dataset data, int saving, int confusion_matrix, int repeat, int silent)
+{
+	int j, k;
+	double total_error = 0.0, t0 = now_s();
+	int c, h, w;
+	size_t out_elems;
+	float *out_dev = NULL, *out_host = NULL;
+	FILE *f_save = NULL;
+	char name[200];
+	struct stat st;
+	layer *last = net->net_layers[net->nb_layers - 1];
+	(void)confusion_matrix; (void)repeat;
+
+	last_layer_dims(net, &c, &h, &w);
+	out_elems = last->type == DENSE ? (size_t)net->batch_size * (c + 1) : (size_t)net->batch_size * c * h * w;
+	if (saving > 0) {
+		if (stat("fwd_res", &st) == -1) mkdir("fwd_res", 0700);
+		sprintf(name, "fwd_res/net%d_%04d.dat", net->id, net->iter);
+		f_save = fopen(name, saving == 1 ? "w+" : "wb+");
+		if (f_save == NULL) { printf("ERROR: cannot open %s\n", name); exit(EXIT_FAILURE); }
+		CB_CHECK(cb200_malloc((void **)&out_dev, out_elems * sizeof(float)));
+		CB_CHECK(cb200_host_alloc((void **)&out_host, out_elems * sizeof(float)));
+	}
+	if (!net->dynamic_load) dataset_upload(net, &data);
+	net->is_inference = 1;
+	for (j = 0; j < data.nb_batch; j++) {
+		const void *tgt;
+		net->length = (j == data.nb_batch - 1 && data.size % net->batch_size > 0) ? data.size % net->batch_size : net->batch_size;
+		if (net->dynamic_load) {
+			cb_load_batch_typed(net, data.input[j], data.target[j]);
+			use_device_batch(net, net->input_raw);
+			tgt = net->target;
+		} else {
+			use_device_batch(net, data.input_device[j]);
+			tgt = data.target_device[j];
+		}
+		for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
+		if (!net->no_error) {
+			output_error(net, tgt);
+			CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
+		}
+		if (saving > 0) {
+			if (last->type == DENSE) CB_CHECK(cb200_export_dense(out_dev, last->output, net->dtype, net->batch_size, c, 0.0f, NULL));
+			else CB_CHECK(cb200_export_cbhw(out_dev, last->output, net->dtype, net->batch_size, c, h, w, NULL));
+			CB_CHECK(cb200_d2h(out_host, out_dev, out_elems * sizeof(float), NULL));
+		}
+		CB_CHECK(cb200_stream_sync(NULL));
+		if (!net->no_error) for (k = 0; k < net->length; k++) total_error += net->loss_host[k];
+		if (saving > 0) {
+			/* one line / record per sample, sample-major like upstream's fwd_res files (src/auxil.c:1346-1400) */
+			int b, o, per = last->type == DENSE ? c : c * h * w;
+			for (b = 0; b < net->length; b++) {
+				for (o = 0; o < per; o++) {
+					float v = last->type == DENSE ? out_host[(size_t)b * (c + 1) + o]
+						: out_host[((size_t)(o / (h * w)) * net->batch_size + b) * (h * w) + o % (h * w)];
+					if (saving == 1) fprintf(f_save, "%g ", v); else fwrite(&v, sizeof(float), 1, f_save);
+				}
+				if (saving == 1) fprintf(f_save, "\n");
+			}
+		}
+	}
+	net->last_items_per_s = (float)(data.size / (now_s() - t0));
+	net->last_epoch_loss = data.size > 0 ? total_error / data.size : 0.0;
+	if (silent < 1) {
+		printf("\n%*s", 14, " ");
+		printf("Average forward perf: %0.2f it/s |", net->last_items_per_s);
+		if (!net->no_error) printf(" Cumulated error: \t %g", net->last_epoch_loss);
+		printf("\n");
+	}
+	if (f_save != NULL) { fclose(f_save); cb200_free(out_dev); cb200_host_free(out_host); }
+}
+
+void forward_testset(network *net, int saving, int repeat, int drop_mode, int silent)
+{
+	if (net->test.input == NULL) { printf("\nERROR: no TEST dataset defined\n"); exit(EXIT_FAILURE); }
+	net->inference_drop_mode = drop_mode;
+	net->is_inference = 1;
+	compute_error(net, net->test, saving, 0, repeat, silent);
+}
+
+/* ------------------------------------------------------------------ checkpoint I/O */
+void save_network(network *net, const char *filename, int f_bin)
+{
+	int i;
+	FILE *f;
+	struct stat st;
+	if (stat("net_save", &st) == -1) mkdir("net_save", 0700);
+	f = fopen(filename, f_bin ? "wb+" : "w+");
+	if (f == NULL) { printf("ERROR : cannot save %s file\n", filename); exit(EXIT_FAILURE); }
+	if (f_bin) fwrite(net->in_dims, sizeof(int), 4, f);
+	else fprintf(f, "%dx%dx%dx%d\n", net->in_dims[0], net->in_dims[1], net->in_dims[2], net->in_dims[3]);
+	for (i = 0; i < net->nb_layers; i++) {
+		switch (net->net_layers[i]->type) {
+		case CONV: conv_save(f, net->net_layers[i], f_bin); break;
+		case POOL: pool_save(f, net->net_layers[i], f_bin); break;
+		case NORM: norm_save(f, net->net_layers[i], f_bin); break;
+		case DENSE: dense_save(f, net->net_layers[i], f_bin); break;
+		default: printf("ERROR: layer type cannot be saved\n"); exit(EXIT_FAILURE);
+		}
+	}
+	fclose(f);
+}
+
+void load_network(network *net, const char *filename, int iter, int nb_layers, int f_bin)
+{
+	FILE *f;
+	int temp_dim[4], layer_count = 0;
+	char layer_type = 'A';
+	net->iter = iter;
+	net->nb_layers = 0;
+	f = fopen(filename, f_bin ? "rb+" : "r+");
+	if (f == NULL) { printf(" ERROR: cannot load/find %s file\n", filename); exit(EXIT_FAILURE); }
+	if (f_bin) fread(temp_dim, sizeof(int), 4, f);
+	else fscanf(f, "%dx%dx%dx%d\n", &temp_dim[0], &temp_dim[1], &temp_dim[2], &temp_dim[3]);
+	if (net->in_dims[0] != temp_dim[0] || net->in_dims[1] != temp_dim[1] || net->in_dims[2] != temp_dim[2] || net->in_dims[3] != temp_dim[3]) {
+		printf(" WARNING: change in image format !\nLoaded network was trained with : W = %d, H = %d, D = %d, C = %d\n", temp_dim[0], temp_dim[1], temp_dim[2], temp_dim[3]);
+		if (net->in_dims[3] != temp_dim[3]) { printf(" ERROR: wrong number of input channel !\n"); exit(EXIT_FAILURE); }
+	}
+	do {
+		if (f_bin) { if (fread(&layer_type, sizeof(char), 1, f) != 1) break; }
+		else { if (fscanf(f, "%c", &layer_type) == EOF) break; }
+		switch (layer_type) {
+		case 'C': conv_load(net, f, f_bin); break;
+		case 'P': pool_load(net, f, f_bin); break;
+		case 'N': norm_load(net, f, f_bin); break;
+		case 'D': dense_load(net, f, f_bin); break;
+		case 'L': printf("ERROR: LRN layers cannot be loaded by the B200 core yet.\n"); exit(EXIT_FAILURE); break;
+		case ' ':
+		case '\n': layer_count--; break;
+		default: printf("ERROR: Layer type not recognized when loading the save model, likely file format error!\n"); exit(EXIT_FAILURE);
+		}
+		layer_count++;
+	} while (nb_layers <= 0 || layer_count < nb_layers);
+	fclose(f);
+}
+
+void set_frozen_layers(network *net, int *tab, int dim)
+{
+	int i;
+	for (i = 0; i < dim; i++) net->net_layers[tab[i]]->frozen = 1;
+}
+
+void perf_eval_display(network *net)
+{
+	printf("\n  Per-layer timing is collected with ncu / CUDA events on demand in this build (no per-layer device sync in the loop);\n"
+	       "  last epoch: %.2f it/s\n", net->last_items_per_s);
+}
+
+/* ------------------------------------------------------------------ read-back helpers (tests, parity) */
+static void export_act(network *net, layer *l, const void *src, float *dst)
+{
+	float *tmp = NULL;
+	size_t n = l->type == DENSE ? (size_t)net->batch_size * (l->out_c + 1) : (size_t)net->batch_size * l->out_c * l->out_h * l->out_w;
+	CB_CHECK(cb200_malloc((void **)&tmp, n * sizeof(float)));
+	if (l->type == DENSE) CB_CHECK(cb200_export_dense(tmp, src, net->dtype, net->batch_size, l->out_c, 0.0f, NULL));
+	else CB_CHECK(cb200_export_cbhw(tmp, src, net->dtype, net->batch_size, l->out_c, l->out_h, l->out_w, NULL));
+	CB_CHECK(cb200_d2h(dst, tmp, n * sizeof(float), NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+	cb200_free(tmp);
+}
+
+void cb_layer_export_output(network *net, int l, float *dst) { export_act(net, net->net_layers[l], net->net_layers[l]->output, dst); }
+void cb_layer_export_delta(network *net, int l, float *dst) { export_act(net, net->net_layers[l], net->net_layers[l]->delta_o, dst); }
+
+void cb_layer_export_pool_map(network *net, int l, int *dst)
+{
+	layer *cur = net->net_layers[l];
+	pool_param *p = (pool_param *)cur->param;
+	int32_t *tmp = NULL;
+	size_t n = (size_t)net->batch_size * cur->out_c * cur->out_h * cur->out_w;
+	if (cur->type != POOL || p->pool_map == NULL) { printf("ERROR: layer %d has no pool map\n", l); exit(EXIT_FAILURE); }
+	CB_CHECK(cb200_malloc((void **)&tmp, n * sizeof(int32_t)));
+	CB_CHECK(cb200_export_pool_map(tmp, p->pool_map, net->batch_size, cur->out_c, cur->out_h, cur->out_w, NULL));
+	CB_CHECK(cb200_d2h(dst, tmp, n * sizeof(int32_t), NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+	cb200_free(tmp);
+}
+
+void cb_layer_shape(network *net, int l, int *out4)
+{
+	layer *cur = net->net_layers[l];
+	out4[0] = cur->out_c; out4[1] = cur->out_h; out4[2] = cur->out_w; out4[3] = cur->type;
+}
+
+size_t cb_layer_weight_count(network *net, int l)
+{
+	layer *cur = net->net_layers[l];
+	if (cur->type == CONV) return cb200_conv_master_elems(&((conv_param *)cur->param)->desc);
+	if (cur->type == DENSE) { dense_param *p = (dense_param *)cur->param; return (size_t)p->in_size * (p->nb_neurons + 1); }
+	if (cur->type == NORM) return 2 * (size_t)((norm_param *)cur->param)->nb_group;
+	return 0;
+}
+
+extern void dense_get_weights(layer *cur, float *dst, int moment);
+extern void dense_set_weights(layer *cur, const float *src);
+
+void cb_layer_get_weights(network *net, int l, float *dst)
+{
+	layer *cur = net->net_layers[l];
+	if (cur->type == CONV) {
+		conv_param *p = (conv_param *)cur->param;
+		CB_CHECK(cb200_d2h(dst, p->w.master, cb200_conv_master_elems(&p->desc) * sizeof(float), NULL));
+	} else if (cur->type == NORM) {
+		norm_param *p = (norm_param *)cur->param;
+		CB_CHECK(cb200_d2h(dst, p->gamma, p->nb_group * sizeof(float), NULL));
+		CB_CHECK(cb200_d2h(dst + p->nb_group, p->beta, p->nb_group * sizeof(float), NULL));
+	} else if (cur->type == DENSE) {
+		dense_get_weights(cur, dst, 0);
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+}
+
+void cb_layer_get_moment(network *net, int l, float *dst)
+{
+	layer *cur = net->net_layers[l];
+	if (cur->type == CONV) {
+		conv_param *p = (conv_param *)cur->param;
+		CB_CHECK(cb200_d2h(dst, p->w.moment, cb200_conv_master_elems(&p->desc) * sizeof(float), NULL));
+	} else if (cur->type == NORM) {
+		norm_param *p = (norm_param *)cur->param;
+		CB_CHECK(cb200_d2h(dst, p->gamma_update, p->nb_group * sizeof(float), NULL));
+		CB_CHECK(cb200_d2h(dst + p->nb_group, p->beta_update, p->nb_group * sizeof(float), NULL));
+	} else if (cur->type == DENSE) {
+		dense_get_weights(cur, dst, 1);
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+}
+
+void cb_layer_set_weights(network *net, int l, const float *src)
+{
+	layer *cur = net->net_layers[l];
+	if (cur->type == CONV) {
+		conv_param *p = (conv_param *)cur->param;
+		CB_CHECK(cb200_h2d(p->w.master, src, cb200_conv_master_elems(&p->desc) * sizeof(float), NULL));
+		CB_CHECK(cb200_stream_sync(NULL));
+		CB_CHECK(cb200_conv_prepare_weights(&p->desc, &p->w, NULL));
+	} else if (cur->type == NORM) {
+		norm_param *p = (norm_param *)cur->param;
+		CB_CHECK(cb200_h2d(p->gamma, src, p->nb_group * sizeof(float), NULL));
+		CB_CHECK(cb200_h2d(p->beta, src + p->nb_group, p->nb_group * sizeof(float), NULL));
+	} else if (cur->type == DENSE) {
+		dense_set_weights(cur, src);
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+}
+
+void cb_layer_get_norm_stats(network *net, int l, float *mean, float *var, float *d_gamma, float *d_beta)
+{
+	layer *cur = net->net_layers[l];
+	norm_param *p = (norm_param *)cur->param;
+	size_t n = (size_t)p->nb_group * net->batch_size * sizeof(float);
+	if (cur->type != NORM) { printf("ERROR: layer %d is not a norm layer\n", l); exit(EXIT_FAILURE); }
+	if (mean) CB_CHECK(cb200_d2h(mean, p->mean, n, NULL));
+	if (var) CB_CHECK(cb200_d2h(var, p->var, n, NULL));
+	if (d_gamma && p->d_gamma) CB_CHECK(cb200_d2h(d_gamma, p->d_gamma, n, NULL));
+	if (d_beta && p->d_beta) CB_CHECK(cb200_d2h(d_beta, p->d_beta, n, NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+}

@@ -1,0 +1,308 @@
+/*
+ * cianna_b200.h - C-ABI of the B200-native compute core (libcianna_b200.so).
+ *
+ * This is the drop-in boundary for CIANNA's C_CUDA back-end: every entry point below
+ * replaces one (group of) function(s) the reference binds through its per-layer
+ * `forward`/`backprop` function pointers and `cuda_*` helpers.  Signatures carry only
+ * plain pointers, sizes and POD descriptors (no C++/torch types) so that host code in
+ * C (cianna_b200/host, or a patched upstream src/*.c) can call it.
+ *
+ * Reference interface replaced (paths relative to the upstream tree):
+ *   src/prototypes.h:217-295            the `cuda_*` extern "C" surface
+ *   src/structs.h:88-262                the per-precision kernel function tables
+ *   src/cuda/cuda_{conv,pool,norm,lrn,dense}_layer.cu, cuda_activ_functions.cu, cuda_main.cu
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on failure (cb200_last_error() gives
+ *     the text).  Nothing here falls back to the CPU: without a CUDA device every compute
+ *     entry point fails with CB200_ERR_NO_DEVICE.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the core's default compute stream).
+ *   - Device tensors use the core's INTERNAL layout: channels-last
+ *         act[b][y][x][c],  c in [0, Cp),  Cp = cb200_round_channels(C) (multiple of 8),
+ *     pad channels are kept at zero.  The reference's layouts ([C][B][H*W] activations,
+ *     [B][C*H*W+1] dataset rows, [N][K+pad] filters) only exist at the boundary and are
+ *     converted by the cb200_import_* / cb200_export_* entry points.
+ *   - dtype is the storage/compute type of activations and deltas; accumulation is always
+ *     FP32 (reference modes FP32C_FP32A, FP16C_FP32A, BF16C_FP32A, src/structs.h:70).
+ */
+#ifndef CIANNA_B200_H
+#define CIANNA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ enums */
+typedef enum { CB200_FP32 = 0, CB200_FP16 = 1, CB200_BF16 = 2 } cb200_dtype;
+/* same order as the reference's activation_functions_enum (src/structs.h:33) */
+typedef enum { CB200_RELU = 0, CB200_LOGISTIC = 1, CB200_SOFTMAX = 2, CB200_YOLO = 3, CB200_LINEAR = 4 } cb200_activ_type;
+typedef enum { CB200_POOL_MAX = 0, CB200_POOL_AVG = 1 } cb200_pool_type;
+
+enum {
+	CB200_OK = 0,
+	CB200_ERR_NO_DEVICE = 1,
+	CB200_ERR_CUDA = 2,
+	CB200_ERR_UNSUPPORTED = 3,
+	CB200_ERR_ARG = 4,
+	CB200_ERR_NCCL = 5
+};
+
+/* Activation applied in a producing kernel's epilogue (forward) or as the
+ * "previous->deriv_activation" hook of a backward kernel.
+ * Replaces: ReLU/logistic/linear kernels + wrappers, src/cuda/cuda_activ_functions.cu:37-111,203-270. */
+typedef struct {
+	int   type;        /* cb200_activ_type (SOFTMAX / YOLO are separate passes) */
+	float leak;        /* RELU leaking factor (default 0.05) */
+	float saturation;  /* RELU / LOGISTIC saturation (800 / 6) */
+	float beta;        /* LOGISTIC beta */
+} cb200_activ;
+
+/* ------------------------------------------------------------------ runtime */
+/* Replaces init_cuda (src/cuda/cuda_main.cu:922-1067). device < 0: keep current device. */
+int  cb200_init(int device);
+int  cb200_device_count(void);
+const char* cb200_last_error(void);
+const char* cb200_version(void);
+/* which implementation the last conv/dense call dispatched to: "tcgen05" or "simt" */
+const char* cb200_last_conv_impl(void);
+/* force the generic SIMT kernels (parity cross-checks of the tcgen05 path); 0 = auto */
+void cb200_force_simt(int on);
+/* number of kernels launched by this library since the last reset */
+long long cb200_launch_count(int reset);
+
+int  cb200_round_channels(int c);
+size_t cb200_dtype_size(int dtype);
+
+/* memory: replaces cuda_create_table*, cuda_free_table, cuda_put/get_table*, cuda_set_mem_value
+ * (src/cuda/cuda_main.cu:108-379) */
+int  cb200_malloc(void** dev_ptr, size_t bytes);          /* zero-initialised */
+int  cb200_free(void* dev_ptr);
+int  cb200_host_alloc(void** host_ptr, size_t bytes);     /* pinned host memory */
+int  cb200_host_free(void* host_ptr);
+int  cb200_memset(void* dev_ptr, int byte, size_t bytes, void* stream);
+int  cb200_h2d(void* dev_dst, const void* host_src, size_t bytes, void* stream);
+int  cb200_d2h(void* host_dst, const void* dev_src, size_t bytes, void* stream);
+int  cb200_d2d(void* dev_dst, const void* dev_src, size_t bytes, void* stream);
+int  cb200_stream_create(void** stream);
+int  cb200_stream_destroy(void* stream);
+int  cb200_stream_sync(void* stream);                     /* NULL: default compute stream */
+int  cb200_device_sync(void);
+/* make `stream` wait for everything enqueued so far on `on_stream` */
+int  cb200_stream_wait(void* stream, void* on_stream);
+/* events (replace cuda_perf_eval_*, src/cuda/cuda_main.cu:533-588, without forcing a sync per layer) */
+int  cb200_event_create(void** ev);
+int  cb200_event_destroy(void* ev);
+int  cb200_event_record(void* ev, void* stream);
+int  cb200_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);  /* synchronises on ev_stop */
+/* CUDA graph capture of a whole step on `stream` */
+int  cb200_graph_begin(void* stream);
+int  cb200_graph_end(void* stream, void** graph_exec);
+int  cb200_graph_launch(void* graph_exec, void* stream);
+int  cb200_graph_destroy(void* graph_exec);
+
+/* typed conversion helpers: FP32 host/device arrays <-> dtype arrays on device.
+ * Replaces cuda_convert_table / cuda_get_table_to_FP32 (src/cuda/cuda_main.cu:153-300). */
+int  cb200_cast_from_f32(void* dev_dst, int dtype, const float* dev_src, size_t n, void* stream);
+int  cb200_cast_to_f32(float* dev_dst, const void* dev_src, int dtype, size_t n, void* stream);
+/* host-side conversion with round-toward-zero, as the reference's dataset conversion does
+ * (src/cuda/cuda_main.cu:790,813) */
+int  cb200_host_cast_from_f32(void* host_dst, int dtype, const float* host_src, size_t n);
+
+/* ------------------------------------------------------------------ layout import / export */
+/* Dataset rows -> internal.  src: device array [batch][C*H*W + 1] in `dtype` (reference dataset
+ * layout incl. the trailing bias slot, src/auxil.c:320-329) ; dst: act[batch][H][W][Cp].
+ * Replaces the first-layer branch of im2col (src/cuda/cuda_conv_layer.cu:36-103, bias_in=1). */
+int  cb200_import_input(void* dst, const void* src, int dtype, int batch, int c, int h, int w, void* stream);
+/* Reference activation layout [C][B][H*W] (FP32, device) <-> internal (dtype). */
+int  cb200_import_cbhw(void* dst, int dtype, const float* src, int batch, int c, int h, int w, void* stream);
+int  cb200_export_cbhw(float* dst, const void* src, int dtype, int batch, int c, int h, int w, void* stream);
+/* pool argmax map: internal uint8 [B][Ho][Wo][Cp] -> reference int32 [C][B][Ho*Wo] */
+int  cb200_export_pool_map(int32_t* dst, const uint8_t* src, int batch, int c, int h, int w, void* stream);
+/* dense layout [B][n+1] (reference, FP32, bias node last) <-> internal [B][1][1][Cp(n)] */
+int  cb200_export_dense(float* dst, const void* src, int dtype, int batch, int n, float bias_node, void* stream);
+
+/* ------------------------------------------------------------------ convolution */
+/* Geometry of one conv layer (2-D; depth = 1). Replaces conv_param (src/structs.h:392-415). */
+typedef struct {
+	int dtype;
+	int batch;            /* net->batch_size */
+	int length;           /* net->length: samples >= length are forced to zero by non-linear activations */
+	int in_c, in_h, in_w;
+	int out_c, out_h, out_w;
+	int f_h, f_w;
+	int stride_h, stride_w;
+	int pad_h, pad_w;
+	float bias_value;     /* constant input of the bias column (layer->bias_value) */
+	cb200_activ activ;    /* this layer's activation (fused in the forward epilogue) */
+} cb200_conv_desc;
+
+/* Compute-side weights of one conv (or dense) layer, all device pointers owned by the caller:
+ *   master : FP32 [out_c][k_ref] in the REFERENCE layout (k_ref = f_h*f_w*in_c + 1, column order
+ *            c-major / tap-minor, bias column last; src/cuda/cuda_conv_layer.cu:91-94); this is
+ *            what save/load files hold (src/conv_layer.c:491-526)
+ *   moment : FP32 [out_c][k_ref] momentum buffer ("update", src/structs.h:413)
+ *   w_fwd  : dtype [out_c][f_h*f_w][in_cp]   K-major operand of the forward implicit GEMM
+ *   w_bwd  : dtype [in_c][f_h*f_w][out_cp]   180-degree rotated + transposed operand of the
+ *            data-gradient GEMM (replaces cuda_rotate_filter_matrix, cuda_conv_layer.cu:106-128)
+ *   bias_w : FP32 [out_c] = master[f][k_ref-1]
+ *   grad   : FP32 [out_c][f_h*f_w][in_cp] raw weight gradient sum_m col*delta (all-reduced in DP)
+ *   grad_b : FP32 [out_c] raw bias-column gradient sum_m delta
+ */
+typedef struct {
+	float* master;
+	float* moment;
+	void*  w_fwd;
+	void*  w_bwd;
+	float* bias_w;
+	float* grad;
+	float* grad_b;
+} cb200_conv_weights;
+
+size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d);
+size_t cb200_conv_wbwd_elems(const cb200_conv_desc* d);
+size_t cb200_conv_grad_elems(const cb200_conv_desc* d);
+size_t cb200_conv_master_elems(const cb200_conv_desc* d);
+
+/* (re)build w_fwd / w_bwd / bias_w from master. Replaces cuda_master_weight_copy
+ * (src/cuda/cuda_main.cu:433-452) + the per-step filter rotation. */
+int cb200_conv_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, void* stream);
+
+/* y = act( conv(x, W) + bias_value*W[:,bias] ).  Replaces cuda_forward_conv_layer
+ * (src/cuda/cuda_conv_layer.cu:319-423: cast + im2col + cublasGemmEx + activation). */
+int cb200_conv_forward(const cb200_conv_desc* d, const cb200_conv_weights* w,
+                       const void* x, void* y, void* stream);
+
+/* dx = fullconv(dy, rot(W)) * act'(prev).  `prev_activ`/`prev_out` describe the PREVIOUS layer's
+ * activation and activated output (NULL prev_out or LINEAR: no hook).  Replaces the error-propagation
+ * half of cuda_backward_conv_layer (cuda_conv_layer.cu:456-541). */
+int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights* w,
+                             const void* dy, void* dx,
+                             const cb200_activ* prev_activ, const void* prev_out, void* stream);
+
+/* grad = sum over batch/pixels of im2col(x)^T * dy (raw, no lr), grad_b = sum dy.
+ * Replaces the cublasGemmEx at cuda_conv_layer.cu:551-557 (optimizer split out so that the raw
+ * gradient can be all-reduced across GPUs before momentum is applied). */
+int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weights* w,
+                                const void* x, const void* dy, void* stream);
+
+/* Optimizer hyper-parameters live in a small device buffer so that a captured CUDA graph can be
+ * replayed with a new learning rate: hyper[0]=lr/batch_total, [1]=momentum, [2]=lr*weight_decay,
+ * [3]=TC_scale_factor, [4]=lr (plain). */
+#define CB200_HYPER_LEN 8
+/* moment = hyper0*grad + mom*moment ; moment += wd_lr*master*S ; master -= moment/S ; then refresh
+ * w_fwd / w_bwd / bias_w.  Replaces the alpha/beta of the wgrad GEMM + cuda_update_weights
+ * (cuda_conv_layer.cu:551-560, cuda_main.cu:455-475) + next step's cuda_master_weight_copy. */
+int cb200_conv_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper,
+                      int is_pivot, void* stream);
+
+/* ------------------------------------------------------------------ dense */
+/* A dense layer runs through the convolution entry points above with a descriptor whose filter covers
+ * the whole input map (f_h = in_h, f_w = in_w, no padding, 1x1 output): the reference's flatten order
+ * flat[b][c*A + a] (cuda_flat_dense, src/cuda/cuda_dense_layer.cu:33-54) is exactly the conv column order
+ * c*taps + tap, so no flatten / reroll pass exists.  Only the FP32 master layout differs: upstream keeps
+ * W[in_size][n + 1] (input-major, pivot column last; src/dense_layer.c:253-268).  These two variants of
+ * prepare / update read that layout; `master`/`moment` then hold in_size*(n+1) floats and the pivot
+ * column is never touched (upstream: is_pivot, cuda_dense_layer.cu:489-495).
+ * Replaces cuda_forward/backward_dense_layer's three cublasGemmEx calls (cuda_dense_layer.cu:370,420,489). */
+int cb200_dense_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, void* stream);
+int cb200_dense_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, void* stream);
+
+/* ------------------------------------------------------------------ pooling */
+typedef struct {
+	int dtype;
+	int batch;
+	int c, in_h, in_w, out_h, out_w;
+	int p_h, p_w, stride_h, stride_w, pad_h, pad_w;
+	int pool_type;        /* cb200_pool_type */
+	int length;
+	cb200_activ activ;    /* layer activation applied to the pooled output (LINEAR / RELU / LOGISTIC) */
+} cb200_pool_desc;
+
+/* Replaces cuda_forward_pool_layer (src/cuda/cuda_pool_layer.cu:429-492). map: uint8 [B][Ho][Wo][Cp],
+ * local window index y*p_w+x of the first strict maximum, 255 when the window is empty (reference: -1). */
+int cb200_pool_forward(const cb200_pool_desc* d, const void* x, void* y, uint8_t* map, void* stream);
+/* Replaces cuda_backward_pool_layer (cuda_pool_layer.cu:495-547) incl. the previous->deriv_activation hook. */
+int cb200_pool_backward(const cb200_pool_desc* d, const void* dy, const uint8_t* map, void* dx,
+                        const cb200_activ* prev_activ, const void* prev_out, void* stream);
+
+/* ------------------------------------------------------------------ group normalisation */
+typedef struct {
+	int dtype;
+	int batch, length;
+	int c, h, w;
+	int group_size, nb_group, set_off;
+	float eps;            /* 1e-3 upstream */
+} cb200_norm_desc;
+
+/* mean/var: FP32 [batch][nb_group]; gamma/beta: FP32 [nb_group] (device).
+ * Replaces cuda_forward_norm_layer (src/cuda/cuda_norm_layer.cu:361-397). */
+size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial sums, caller-owned */
+int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y,
+                       const float* gamma, const float* beta, float* mean, float* var,
+                       void* workspace, void* stream);
+/* d_gamma/d_beta: FP32 [batch][nb_group] per-sample sums (as upstream); dx includes the
+ * previous->deriv_activation hook (prev_out == x of this layer).
+ * Replaces cuda_backward_norm_layer's device half (cuda_norm_layer.cu:399-432). */
+int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy, void* dx,
+                        const float* gamma, const float* mean, const float* var,
+                        float* d_gamma, float* d_beta,
+                        const cb200_activ* prev_activ, void* workspace, void* stream);
+/* gamma_upd = mom*gamma_upd + lr*sum_b(d_gamma)/batch_total ; gamma -= gamma_upd/S (same for beta).
+ * gsum: FP32 [2][nb_group] batch-summed (d_gamma, d_beta) (the buffer that is all-reduced in DP).
+ * Replaces the host loop + 4 blocking memcpys of cuda_norm_layer.cu:434-457. */
+int cb200_norm_reduce_grads(const cb200_norm_desc* d, const float* d_gamma, const float* d_beta,
+                            float* gsum, void* stream);
+int cb200_norm_update(const cb200_norm_desc* d, float* gamma, float* beta, float* gamma_upd, float* beta_upd,
+                      const float* gsum, const float* hyper, void* stream);
+
+/* ------------------------------------------------------------------ local response normalisation */
+typedef struct {
+	int dtype;
+	int batch, length;
+	int c, h, w;
+	int range;
+	float k, alpha, beta;
+} cb200_lrn_desc;
+/* Replaces cuda_forward/backward_lrn_layer (src/cuda/cuda_lrn_layer.cu:35-101,172-215). */
+int cb200_lrn_forward(const cb200_lrn_desc* d, const void* x, void* y, float* local_scale, void* stream);
+int cb200_lrn_backward(const cb200_lrn_desc* d, const void* x, const void* y, const void* dy, void* dx,
+                       const float* local_scale, const cb200_activ* prev_activ, const void* prev_out, void* stream);
+
+/* ------------------------------------------------------------------ output layer: softmax / losses */
+/* All three take the last layer's tensor in internal layout [B][h][w][Cp] and the target batch in the
+ * reference's target layout [B][c*h*w] (per sample c-major, src/cuda/cuda_activ_functions.cu:114-194),
+ * stored in `dtype` like upstream (src/cuda/cuda_main.cu:398). */
+/* in-place softmax over the c*h*w values of each sample (zero for b >= length).
+ * Replaces softmax_activation_kernel (cuda_activ_functions.cu:280-381). */
+int cb200_softmax(void* y, int dtype, int batch, int length, int c, int h, int w, void* stream);
+/* delta = (y - t) * scale (quadratic and cross-entropy share it upstream), zero for b >= length.
+ * Replaces quadratic/cross_entropy_deriv_output_error (cuda_activ_functions.cu:114-155,384-425). */
+int cb200_output_delta(void* delta, const void* y, const void* target, int dtype,
+                       int batch, int length, int c, int h, int w, float scale, void* stream);
+/* per-sample loss summed over the sample's outputs -> loss[batch] (FP32), kind 0: 0.5*(y-t)^2,
+ * kind 1: -t*log(max(y,1e-6)).  Replaces *_output_error kernels + the host-side summation of the
+ * whole per-element tensor (cuda_activ_functions.cu:157-194,427-470; src/auxil.c:1851-1917). */
+int cb200_output_loss(float* loss, const void* y, const void* target, int dtype,
+                      int batch, int length, int c, int h, int w, int kind, void* stream);
+
+/* ------------------------------------------------------------------ data parallel (NCCL) */
+/* One process per GPU.  Rank 0 creates the id (128 bytes) and ships it to the others through any
+ * side channel (torch.distributed store, MPI, a file); then every rank calls cb200_dp_init.
+ * The reference has no multi-GPU path (src/cuda/cuda_main.cu:1066). */
+int cb200_dp_unique_id(void* id128);
+int cb200_dp_init(const void* id128, int rank, int world);
+int cb200_dp_world(void);
+/* in-place sum all-reduce of an FP32 device buffer on the core's communication stream, ordered
+ * after everything enqueued so far on `after_stream`; cb200_dp_join makes `stream` wait for all
+ * all-reduces issued so far.  No-ops when world == 1. */
+int cb200_dp_allreduce(float* buf, size_t n, void* after_stream);
+int cb200_dp_join(void* stream);
+int cb200_dp_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIANNA_B200_H */
