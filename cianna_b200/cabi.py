@@ -1,0 +1,285 @@
+"""ctypes view of the C-ABI (include/cianna_b200.h): structure mirrors + a tiny device-buffer helper.
+
+Used by the parity tests and bench.py to call the kernels exactly the way a C host would, with host
+buffers in and out.  No torch types cross this boundary.
+"""
+import ctypes
+
+import numpy as np
+
+from . import CIANNA
+
+FP32, FP16, BF16 = 0, 1, 2
+RELU, LOGISTIC, SOFTMAX, YOLO, LINEAR = 0, 1, 2, 3, 4
+POOL_MAX, POOL_AVG = 0, 1
+
+
+class Activ(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int), ("leak", ctypes.c_float), ("saturation", ctypes.c_float), ("beta", ctypes.c_float)]
+
+
+def activ(kind=LINEAR, leak=0.05, saturation=800.0, beta=1.0):
+    if kind == LINEAR:
+        return Activ(LINEAR, 0.0, 0.0, 0.0)
+    if kind == LOGISTIC:
+        return Activ(LOGISTIC, 0.0, 6.0 if saturation == 800.0 else saturation, beta)
+    return Activ(kind, leak, saturation, 0.0)
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int),
+                ("in_c", ctypes.c_int), ("in_h", ctypes.c_int), ("in_w", ctypes.c_int),
+                ("out_c", ctypes.c_int), ("out_h", ctypes.c_int), ("out_w", ctypes.c_int),
+                ("f_h", ctypes.c_int), ("f_w", ctypes.c_int), ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int),
+                ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int), ("bias_value", ctypes.c_float), ("activ", Activ)]
+
+
+class ConvWeights(ctypes.Structure):
+    _fields_ = [("master", ctypes.c_void_p), ("moment", ctypes.c_void_p), ("w_fwd", ctypes.c_void_p), ("w_bwd", ctypes.c_void_p),
+                ("bias_w", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("grad_b", ctypes.c_void_p)]
+
+
+class PoolDesc(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("c", ctypes.c_int), ("in_h", ctypes.c_int), ("in_w", ctypes.c_int),
+                ("out_h", ctypes.c_int), ("out_w", ctypes.c_int), ("p_h", ctypes.c_int), ("p_w", ctypes.c_int),
+                ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int), ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int),
+                ("pool_type", ctypes.c_int), ("length", ctypes.c_int), ("activ", Activ)]
+
+
+class NormDesc(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int), ("c", ctypes.c_int), ("h", ctypes.c_int),
+                ("w", ctypes.c_int), ("group_size", ctypes.c_int), ("nb_group", ctypes.c_int), ("set_off", ctypes.c_int), ("eps", ctypes.c_float)]
+
+
+def lib():
+    L = CIANNA.core()
+    if not getattr(L, "_cabi_ready", False):
+        L.cb200_conv_wfwd_elems.restype = ctypes.c_size_t
+        L.cb200_conv_wbwd_elems.restype = ctypes.c_size_t
+        L.cb200_conv_grad_elems.restype = ctypes.c_size_t
+        L.cb200_conv_master_elems.restype = ctypes.c_size_t
+        L.cb200_norm_workspace_bytes.restype = ctypes.c_size_t
+        L.cb200_dtype_size.restype = ctypes.c_size_t
+        L.cb200_malloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+        L.cb200_free.argtypes = [ctypes.c_void_p]
+        L.cb200_h2d.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.cb200_d2h.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.cb200_memset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        L.cb200_stream_sync.argtypes = [ctypes.c_void_p]
+        L.cb200_cast_from_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.cb200_cast_to_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        L.cb200_import_cbhw.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+        L.cb200_export_cbhw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+        L.cb200_conv_prepare_weights.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.cb200_conv_forward.argtypes = [ctypes.c_void_p] * 5
+        L.cb200_conv_backward_data.argtypes = [ctypes.c_void_p] * 7
+        L.cb200_conv_backward_weights.argtypes = [ctypes.c_void_p] * 5
+        L.cb200_conv_update.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.cb200_event_create.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        L.cb200_event_record.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.cb200_event_elapsed_ms.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        L.cb200_host_cast_from_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+        L._cabi_ready = True
+    return L
+
+
+def init_device(device=0):
+    check(lib().cb200_init(int(device)))
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("cb200 call failed (%d): %s" % (rc, lib().cb200_last_error().decode()))
+
+
+class DevBuf:
+    """a device allocation owned through the C-ABI"""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = ctypes.c_void_p()
+        check(lib().cb200_malloc(ctypes.byref(self.ptr), self.nbytes))
+
+    @classmethod
+    def from_numpy(cls, a):
+        a = np.ascontiguousarray(a)
+        b = cls(a.nbytes)
+        check(lib().cb200_h2d(b.ptr, a.ctypes.data, a.nbytes, None))
+        check(lib().cb200_stream_sync(None))
+        return b
+
+    def to_numpy(self, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(lib().cb200_d2h(out.ctypes.data, self.ptr, out.nbytes, None))
+        check(lib().cb200_stream_sync(None))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().cb200_free(self.ptr)
+            self.ptr = ctypes.c_void_p()
+
+
+def round8(c):
+    return (c + 7) & ~7
+
+
+def upload_act(x_cbhw, dtype, batch, c, h, w):
+    """reference-layout FP32 [C][B][H*W] host array -> device tensor in the core's layout / dtype"""
+    L = lib()
+    src = DevBuf.from_numpy(np.ascontiguousarray(x_cbhw, dtype=np.float32))
+    dst = DevBuf(batch * h * w * round8(c) * L.cb200_dtype_size(dtype))
+    check(L.cb200_import_cbhw(dst.ptr, dtype, src.ptr, batch, c, h, w, None))
+    check(L.cb200_stream_sync(None))
+    src.free()
+    return dst
+
+
+def download_act(buf, dtype, batch, c, h, w):
+    L = lib()
+    tmp = DevBuf(c * batch * h * w * 4)
+    check(L.cb200_export_cbhw(tmp.ptr, buf.ptr, dtype, batch, c, h, w, None))
+    out = tmp.to_numpy(np.float32, (c, batch, h * w))
+    tmp.free()
+    return out
+
+
+class ConvLayer:
+    """one conv layer driven through the C-ABI only (weights in the reference layout [N][k*k*C+1])"""
+
+    def __init__(self, dtype, batch, in_c, in_h, in_w, out_c, f, stride=1, pad=0, bias_value=0.1, act=None, length=None):
+        L = lib()
+        out_h = (in_h + 2 * pad - f) // stride + 1
+        out_w = (in_w + 2 * pad - f) // stride + 1
+        self.d = ConvDesc(dtype, batch, batch if length is None else length, in_c, in_h, in_w, out_c, out_h, out_w,
+                          f, f, stride, stride, pad, pad, bias_value, act if act is not None else activ(LINEAR))
+        self.dtype = dtype
+        es = L.cb200_dtype_size(dtype)
+        dp = ctypes.byref(self.d)
+        self.bufs = dict(
+            master=DevBuf(L.cb200_conv_master_elems(dp) * 4), moment=DevBuf(L.cb200_conv_master_elems(dp) * 4),
+            w_fwd=DevBuf(L.cb200_conv_wfwd_elems(dp) * es), w_bwd=DevBuf(L.cb200_conv_wbwd_elems(dp) * es),
+            bias_w=DevBuf(out_c * 4), grad=DevBuf(L.cb200_conv_grad_elems(dp) * 4), grad_b=DevBuf(out_c * 4))
+        self.w = ConvWeights(*[self.bufs[k].ptr for k in ("master", "moment", "w_fwd", "w_bwd", "bias_w", "grad", "grad_b")])
+        self.y = DevBuf(batch * out_h * out_w * round8(out_c) * es)
+        self.dx = DevBuf(batch * in_h * in_w * round8(in_c) * es)
+
+    def set_weights(self, w_ref):
+        L = lib()
+        a = np.ascontiguousarray(w_ref, dtype=np.float32)
+        check(L.cb200_h2d(self.bufs["master"].ptr, a.ctypes.data, a.nbytes, None))
+        check(L.cb200_stream_sync(None))
+        check(L.cb200_conv_prepare_weights(ctypes.byref(self.d), ctypes.byref(self.w), None))
+
+    def forward(self, x_buf):
+        check(lib().cb200_conv_forward(ctypes.byref(self.d), ctypes.byref(self.w), x_buf.ptr, self.y.ptr, None))
+        return self.y
+
+    def backward_data(self, dy_buf, prev_act=None, prev_out=None):
+        pa = ctypes.byref(prev_act) if prev_act is not None else None
+        po = prev_out.ptr if prev_out is not None else None
+        check(lib().cb200_conv_backward_data(ctypes.byref(self.d), ctypes.byref(self.w), dy_buf.ptr, self.dx.ptr, pa, po, None))
+        return self.dx
+
+    def backward_weights(self, x_buf, dy_buf):
+        check(lib().cb200_conv_backward_weights(ctypes.byref(self.d), ctypes.byref(self.w), x_buf.ptr, dy_buf.ptr, None))
+
+    def grad_ref_layout(self):
+        """raw gradient re-ordered to the reference filter layout [N][k*k*C + 1] (bias column = bias_value * sum dy)"""
+        d = self.d
+        taps, cp = d.f_h * d.f_w, round8(d.in_c)
+        g = self.bufs["grad"].to_numpy(np.float32, (d.out_c, taps, cp))[:, :, : d.in_c]
+        gb = self.bufs["grad_b"].to_numpy(np.float32, (d.out_c,))
+        out = np.empty((d.out_c, taps * d.in_c + 1), dtype=np.float32)
+        out[:, :-1] = g.transpose(0, 2, 1).reshape(d.out_c, d.in_c * taps)
+        out[:, -1] = gb * d.bias_value
+        return out
+
+    def free(self):
+        for b in self.bufs.values():
+            b.free()
+        self.y.free()
+        self.dx.free()
+
+
+def _ensure_pool_norm_sigs():
+    L = lib()
+    if getattr(L, "_pn_ready", False):
+        return L
+    L.cb200_pool_forward.argtypes = [ctypes.c_void_p] * 5
+    L.cb200_pool_backward.argtypes = [ctypes.c_void_p] * 7
+    L.cb200_export_pool_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    L.cb200_norm_forward.argtypes = [ctypes.c_void_p] * 9
+    L.cb200_norm_backward.argtypes = [ctypes.c_void_p] * 12
+    L._pn_ready = True
+    return L
+
+
+class PoolLayer:
+    def __init__(self, dtype, batch, c, in_h, in_w, p, stride=None, pad=0, ptype=POOL_MAX, act=None, length=None):
+        L = _ensure_pool_norm_sigs()
+        stride = p if stride is None else stride
+        out_h = (in_h + 2 * pad - p) // stride + 1
+        out_w = (in_w + 2 * pad - p) // stride + 1
+        self.d = PoolDesc(dtype, batch, c, in_h, in_w, out_h, out_w, p, p, stride, stride, pad, pad, ptype,
+                          batch if length is None else length, act if act is not None else activ(LINEAR))
+        es = L.cb200_dtype_size(dtype)
+        self.y = DevBuf(batch * out_h * out_w * round8(c) * es)
+        self.map = DevBuf(batch * out_h * out_w * round8(c))
+        self.dx = DevBuf(batch * in_h * in_w * round8(c) * es)
+
+    def forward(self, x_buf):
+        check(lib().cb200_pool_forward(ctypes.byref(self.d), x_buf.ptr, self.y.ptr, self.map.ptr, None))
+        return self.y
+
+    def map_ref_layout(self):
+        d = self.d
+        tmp = DevBuf(d.c * d.batch * d.out_h * d.out_w * 4)
+        check(lib().cb200_export_pool_map(tmp.ptr, self.map.ptr, d.batch, d.c, d.out_h, d.out_w, None))
+        out = tmp.to_numpy(np.int32, (d.c, d.batch, d.out_h * d.out_w))
+        tmp.free()
+        return out
+
+    def backward(self, dy_buf, prev_act=None, prev_out=None):
+        pa = ctypes.byref(prev_act) if prev_act is not None else None
+        po = prev_out.ptr if prev_out is not None else None
+        check(lib().cb200_pool_backward(ctypes.byref(self.d), dy_buf.ptr, self.map.ptr, self.dx.ptr, pa, po, None))
+        return self.dx
+
+
+class NormLayer:
+    def __init__(self, dtype, batch, c, h, w, group_size, set_off=0, length=None):
+        L = _ensure_pool_norm_sigs()
+        nb_group = (c + group_size - 1) // group_size
+        self.d = NormDesc(dtype, batch, batch if length is None else length, c, h, w, group_size, nb_group, set_off, 0.001)
+        es = L.cb200_dtype_size(dtype)
+        n = batch * h * w * round8(c) * es
+        self.y, self.dx = DevBuf(n), DevBuf(n)
+        self.gamma = DevBuf.from_numpy(np.ones(nb_group, np.float32))
+        self.beta = DevBuf.from_numpy(np.zeros(nb_group, np.float32))
+        self.mean, self.var = DevBuf(batch * nb_group * 4), DevBuf(batch * nb_group * 4)
+        self.d_gamma, self.d_beta = DevBuf(batch * nb_group * 4), DevBuf(batch * nb_group * 4)
+        self.ws = DevBuf(L.cb200_norm_workspace_bytes(ctypes.byref(self.d)))
+        self.nb_group = nb_group
+
+    def set_params(self, gamma, beta):
+        self.gamma.free(); self.beta.free()
+        self.gamma = DevBuf.from_numpy(np.ascontiguousarray(gamma, np.float32))
+        self.beta = DevBuf.from_numpy(np.ascontiguousarray(beta, np.float32))
+
+    def forward(self, x_buf):
+        check(lib().cb200_norm_forward(ctypes.byref(self.d), x_buf.ptr, self.y.ptr, self.gamma.ptr, self.beta.ptr,
+                                       self.mean.ptr, self.var.ptr, self.ws.ptr, None))
+        return self.y
+
+    def backward(self, x_buf, dy_buf, prev_act=None):
+        pa = ctypes.byref(prev_act) if prev_act is not None else None
+        check(lib().cb200_norm_backward(ctypes.byref(self.d), x_buf.ptr, dy_buf.ptr, self.dx.ptr, self.gamma.ptr, self.mean.ptr,
+                                        self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa, self.ws.ptr, None))
+        return self.dx
+
+    def stats(self):
+        shp = (self.d.batch, self.nb_group)
+        return (self.mean.to_numpy(np.float32, shp), self.var.to_numpy(np.float32, shp),
+                self.d_gamma.to_numpy(np.float32, shp), self.d_beta.to_numpy(np.float32, shp))

@@ -225,6 +225,21 @@ void cb_layer_get_norm_stats(network *net, int l, float *mean, float *var, float
 void cb_layer_shape(network *net, int l, int *out4);         /* c, h, w, type */
 const char *cb_layer_conv_impl(network *net, int l);          /* which kernel family ran last ("tcgen05"/"simt") */
 
+/* accessors for language bindings */
+network *cb_get_network(int id);
+int cb_net_nb_layers(network *net);
+int cb_nb_networks(void);
+layer *cb_net_layer(network *net, int idx);
+int cb_net_batch_size(network *net);
+float cb_net_last_items_per_s(network *net);
+double cb_net_last_epoch_loss(network *net);
+void cb_net_set_no_error(network *net, int v);
+Dataset *cb_net_dataset(network *net, const char *name);
+void cb_set_dataset(network *net, const char *name, int size, const float *input, const float *target);
+void cb_swap_data_buffers(network *net, const char *name);
+void cb_net_in_dims(network *net, int *out4);
+void cb_set_TC_scale_factor(network *net, float v);
+
 #define CB_CHECK(call) do { int rc__ = (call); if (rc__ != 0) { \
 	printf("\nERROR: %s failed (%d): %s\n", #call, rc__, cb200_last_error()); exit(EXIT_FAILURE); } } while (0)
 

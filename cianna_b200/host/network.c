@@ -712,3 +712,52 @@ void cb_layer_get_norm_stats(network *net, int l, float *mean, float *var, float
 	if (d_beta && p->d_beta) CB_CHECK(cb200_d2h(d_beta, p->d_beta, n, NULL));
 	CB_CHECK(cb200_stream_sync(NULL));
 }
+
+/* ------------------------------------------------------------------ accessors for the language bindings */
+network *cb_get_network(int id) { return (id >= 0 && id < MAX_NETWORKS_NB) ? networks[id] : NULL; }
+int cb_net_nb_layers(network *net) { return net->nb_layers; }
+int cb_nb_networks(void) { return nb_networks; }
+layer *cb_net_layer(network *net, int idx) { return (idx >= 0 && idx < net->nb_layers) ? net->net_layers[idx] : NULL; }
+int cb_net_batch_size(network *net) { return net->batch_size; }
+float cb_net_last_items_per_s(network *net) { return net->last_items_per_s; }
+double cb_net_last_epoch_loss(network *net) { return net->last_epoch_loss; }
+void cb_net_set_no_error(network *net, int v) { net->no_error = v; }
+
+Dataset *cb_net_dataset(network *net, const char *name)
+{
+	if (strcmp(name, "TRAIN") == 0) return &net->train;
+	if (strcmp(name, "VALID") == 0) return &net->valid;
+	if (strcmp(name, "TEST") == 0) return &net->test;
+	if (strcmp(name, "TRAIN_buf") == 0) return &net->train_buf;
+	if (strcmp(name, "VALID_buf") == 0) return &net->valid_buf;
+	if (strcmp(name, "TEST_buf") == 0) return &net->test_buf;
+	printf("ERROR: unknown dataset name %s\n", name);
+	exit(EXIT_FAILURE);
+}
+
+/* (re)create the named dataset and fill it from row-major FP32 arrays [size][input_dim] / [size][output_dim] */
+void cb_set_dataset(network *net, const char *name, int size, const float *input, const float *target)
+{
+	Dataset *d = cb_net_dataset(net, name);
+	int i;
+	if (d->input != NULL) free_dataset(d);
+	*d = create_dataset(net, size);
+	if (input != NULL || target != NULL)
+		for (i = 0; i < size; i++)
+			dataset_set_sample(net, d, i, input ? input + (size_t)i * net->input_dim : NULL, target ? target + (size_t)i * net->output_dim : NULL);
+	if (!net->dynamic_load) dataset_upload(net, d);
+}
+
+/* upstream swap_data_buffers (src/python_module.c:222-283): exchange a dataset with its "_buf" twin */
+void cb_swap_data_buffers(network *net, const char *name)
+{
+	Dataset tmp, *a, *b;
+	char buf_name[32];
+	snprintf(buf_name, sizeof(buf_name), "%s_buf", name);
+	a = cb_net_dataset(net, name);
+	b = cb_net_dataset(net, buf_name);
+	tmp = *a; *a = *b; *b = tmp;
+}
+void cb_net_in_dims(network *net, int *out4) { int i; for (i = 0; i < 4; i++) out4[i] = net->in_dims[i]; }
+/* loss scaling is only honoured by the FP16 mode (upstream cuda_set_TC_scale_factor, src/cuda/cuda_main.cu:63-76) */
+void cb_set_TC_scale_factor(network *net, float v) { net->TC_scale_factor = net->use_cuda_TC == FP16C_FP32A ? v : 1.0f; }

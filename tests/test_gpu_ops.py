@@ -1,0 +1,207 @@
+"""GPU parity, operator level: every kernel family is called through the C-ABI (include/cianna_b200.h) with
+host buffers and checked against the oracle (oracle/cianna_oracle.py, pinned by tests/test_oracle.py).
+
+Tolerances (BASELINE.json north_star): bit-exact for the implicit-GEMM address mapping (integer-valued
+tensors) and pool argmax; 1e-5 relative for FP32 activations / gradients; 2e-2 for mixed precision.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cianna_oracle as co
+from tests.common import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-5
+TOL_MIXED = 2e-2
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from cianna_b200 import cabi as m
+    m.init_device(0)
+    return m
+
+
+def _int_tensor(rng, shape, p_zero=0.5):
+    v = rng.choice(np.array([-1.0, 0.0, 1.0], np.float32), size=shape, p=[(1 - p_zero) / 2, p_zero, (1 - p_zero) / 2])
+    return v.astype(np.float32)
+
+
+# geometry: (batch, in_c, size, out_c, f, pad)
+TC_SHAPES = [
+    (8, 32, 14, 64, 3, 1),     # BK=32 (64B swizzle), BN=64
+    (3, 64, 13, 48, 3, 1),     # odd image size / batch, partial tiles in every dimension
+    (8, 64, 14, 256, 3, 1),    # BN=256
+    (4, 128, 28, 128, 1, 0),   # 1x1, two channel blocks
+    (16, 16, 7, 16, 3, 1),     # BK=16 (32B swizzle), BN=16
+    (2, 256, 14, 1000, 1, 0),  # the Darknet19 head: N=1000 -> four 256-wide tiles, last one partial
+    (5, 64, 10, 32, 5, 2),     # 5x5 filter
+    (128, 64, 1, 40, 1, 0),    # dense-like: 1x1 map, tile spans 128 images
+]
+
+
+@pytest.mark.parametrize("dtype_name", ["FP16", "BF16"])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
+    """integer-valued inputs / weights: every product and partial sum is exactly representable, so the
+    tensor-core implicit GEMM must reproduce the reference im2col + GEMM bit for bit (forward, data
+    gradient and weight gradient)."""
+    B, C, S, N, f, pad = shape
+    dtype = cabi.FP16 if dtype_name == "FP16" else cabi.BF16
+    rng = np.random.default_rng(hash(shape) % 2**31)
+    x = _int_tensor(rng, (C, B, S * S), 0.6)
+    w = _int_tensor(rng, (N, f * f * C + 1), 0.7)
+    w[:, -1] = rng.integers(-2, 3, N)
+    layer = cabi.ConvLayer(dtype, B, C, S, S, N, f, 1, pad, bias_value=1.0)
+    layer.set_weights(w)
+    xb = cabi.upload_act(x, dtype, B, C, S, S)
+    So = S + 2 * pad - f + 1
+    y = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+    assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
+    ref, col = co.conv_forward(x, w, False, B, C, S, S, f, 1, pad, 1.0)
+    assert np.abs(ref).max() < 256, "test values must stay exactly representable in bf16"
+    assert np.array_equal(y, ref)
+
+    dy = _int_tensor(rng, (N, B, So * So), 0.8)
+    dyb = cabi.upload_act(dy, dtype, B, N, So, So)
+    dx = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
+    assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
+    ref_dx = co.conv_backward_data(dy, w, B, C, S, S, f, 1, pad)
+    assert np.abs(ref_dx).max() < 256
+    assert np.array_equal(dx, ref_dx)
+
+    layer.backward_weights(xb, dyb)
+    got = layer.grad_ref_layout()
+    ref_g = co.conv_weight_grad(col, dy).astype(np.float32)
+    assert np.array_equal(got, ref_g), cabi.lib().cb200_last_conv_impl()
+    layer.free(); xb.free(); dyb.free()
+
+
+@pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
+@pytest.mark.parametrize("shape", [(4, 3, 16, 8, 3, 1, 1), (2, 8, 9, 12, 3, 0, 2), (3, 5, 12, 7, 5, 2, 1), (2, 16, 8, 16, 2, 0, 2)])
+def test_conv_simt_matches_oracle(cabi, shape, dtype_name):
+    """generic kernels (FP32 mode, strides, tiny channel counts) against the oracle on random data"""
+    B, C, S, N, f, pad, stride = shape
+    dtype = getattr(cabi, dtype_name)
+    tol = TOL_FP32 if dtype_name == "FP32" else TOL_MIXED
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((C, B, S * S)).astype(np.float32)
+    w = (rng.standard_normal((N, f * f * C + 1)) * 0.2).astype(np.float32)
+    cabi.lib().cb200_force_simt(1)
+    try:
+        layer = cabi.ConvLayer(dtype, B, C, S, S, N, f, stride, pad, bias_value=0.1, act=cabi.activ(cabi.RELU))
+        layer.set_weights(w)
+        xb = cabi.upload_act(x, dtype, B, C, S, S)
+        So = (S + 2 * pad - f) // stride + 1
+        y = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+        pre, col = co.conv_forward(x, w, False, B, C, S, S, f, stride, pad, 0.1)
+        ref = co.relu_forward(pre, B)
+        assert rel_err(y, ref) < tol
+        dy = rng.standard_normal((N, B, So * So)).astype(np.float32)
+        dyb = cabi.upload_act(dy, dtype, B, N, So, So)
+        dx = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
+        assert rel_err(dx, co.conv_backward_data(dy, w, B, C, S, S, f, stride, pad)) < tol
+        layer.backward_weights(xb, dyb)
+        assert rel_err(layer.grad_ref_layout(), co.conv_weight_grad(col, dy)) < tol
+    finally:
+        cabi.lib().cb200_force_simt(0)
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 14, 128, 3, 1), (4, 32, 28, 64, 3, 1), (6, 128, 7, 64, 1, 0)])
+def test_conv_tcgen05_vs_simt_random(cabi, shape):
+    """same 16-bit operands through both kernel families: only the FP32 summation order may differ"""
+    B, C, S, N, f, pad = shape
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((C, B, S * S)).astype(np.float32)
+    w = (rng.standard_normal((N, f * f * C + 1)) * 0.1).astype(np.float32)
+    outs = []
+    for force in (0, 1):
+        cabi.lib().cb200_force_simt(force)
+        layer = cabi.ConvLayer(cabi.FP16, B, C, S, S, N, f, 1, pad, bias_value=0.1, act=cabi.activ(cabi.RELU))
+        layer.set_weights(w)
+        xb = cabi.upload_act(x, cabi.FP16, B, C, S, S)
+        So = S + 2 * pad - f + 1
+        y = cabi.download_act(layer.forward(xb), cabi.FP16, B, N, So, So)
+        dy = rng.standard_normal((N, B, So * So)).astype(np.float32) if force == 0 else dy
+        dyb = cabi.upload_act(dy, cabi.FP16, B, N, So, So)
+        dx = cabi.download_act(layer.backward_data(dyb, cabi.activ(cabi.RELU), xb), cabi.FP16, B, C, S, S)
+        layer.backward_weights(xb, dyb)
+        outs.append((y, dx, layer.grad_ref_layout(), cabi.lib().cb200_last_conv_impl()))
+    cabi.lib().cb200_force_simt(0)
+    assert outs[0][3] == b"tcgen05" and outs[1][3] == b"simt"
+    assert rel_err(outs[0][0], outs[1][0]) < 2e-3
+    assert rel_err(outs[0][1], outs[1][1]) < 2e-3
+    assert rel_err(outs[0][2], outs[1][2]) < 1e-4
+
+
+def test_pool_argmax_bit_exact_vs_golden(cabi):
+    """max-pool on the reference's own input tensor: values and argmax map must be identical"""
+    g = load_golden("mini_darknet_blas")
+    x = g["out_1"]                      # GN output feeding the first max pool
+    C, B, A = x.shape
+    S = int(round(A ** 0.5))
+    pool = cabi.PoolLayer(cabi.FP32, B, C, S, S, 2)
+    xb = cabi.upload_act(x, cabi.FP32, B, C, S, S)
+    y = cabi.download_act(pool.forward(xb), cabi.FP32, B, C, S // 2, S // 2)
+    assert np.array_equal(y, g["out_2"])
+    assert np.array_equal(pool.map_ref_layout(), g["map_2"])
+
+
+@pytest.mark.parametrize("cfg", [(2, 2, 0, "MAX"), (3, 2, 1, "MAX"), (3, 1, 1, "MAX"), (2, 2, 0, "AVG"), (3, 2, 1, "AVG")])
+def test_pool_forward_backward_vs_oracle(cabi, cfg):
+    """window / stride / padding variants incl. ties (quantised values) - first maximum must win"""
+    p, s, pad, kind = cfg
+    B, C, S = 3, 10, 9
+    rng = np.random.default_rng(5)
+    x = np.round(rng.standard_normal((C, B, S * S)) * 2).astype(np.float32) / 2      # many exact ties
+    pool = cabi.PoolLayer(cabi.FP32, B, C, S, S, p, s, pad, cabi.POOL_MAX if kind == "MAX" else cabi.POOL_AVG)
+    xb = cabi.upload_act(x, cabi.FP32, B, C, S, S)
+    So = (S + 2 * pad - p) // s + 1
+    y = cabi.download_act(pool.forward(xb), cabi.FP32, B, C, So, So)
+    ref_y, ref_m = co.pool_forward(x, B, C, S, S, p, s, pad, kind)
+    if kind == "MAX":
+        assert np.array_equal(y, ref_y)
+        assert np.array_equal(pool.map_ref_layout(), ref_m)
+    else:
+        assert rel_err(y, ref_y) < TOL_FP32
+    dy = rng.standard_normal((C, B, So * So)).astype(np.float32)
+    dyb = cabi.upload_act(dy, cabi.FP32, B, C, So, So)
+    dx = cabi.download_act(pool.backward(dyb), cabi.FP32, B, C, S, S)
+    assert rel_err(dx, co.pool_backward(dy, ref_m, B, C, S, S, p, s, pad, kind)) < TOL_FP32
+
+
+@pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
+@pytest.mark.parametrize("cfg", [(4, 32, 12, 4, 0, 4), (3, 16, 7, 8, 1, 2), (2, 64, 40, 16, 0, 2), (2, 8, 5, 8, 0, 2)])
+def test_group_norm_vs_oracle(cabi, cfg, dtype_name):
+    B, C, S, gs, set_off, length = cfg
+    dtype = getattr(cabi, dtype_name)
+    tol = TOL_FP32 if dtype_name == "FP32" else TOL_MIXED
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((C, B, S * S)) * 1.5 + 0.7).astype(np.float32)
+    if dtype_name != "FP32":   # make the input exactly representable so both sides see the same tensor
+        x = x.astype(np.float16).astype(np.float32) if dtype_name == "FP16" else (x.view(np.uint32) & 0xFFFF0000).view(np.float32)
+    G = C // gs
+    gamma = (1 + 0.3 * rng.standard_normal(G)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(G)).astype(np.float32)
+    nl = cabi.NormLayer(dtype, B, C, S, S, gs, set_off, length)
+    nl.set_params(gamma, beta)
+    xb = cabi.upload_act(x, dtype, B, C, S, S)
+    y = cabi.download_act(nl.forward(xb), dtype, B, C, S, S)
+    ref_y, mean, var = co.group_norm_forward(x, gamma, beta, gs, set_off, length)
+    assert rel_err(y, ref_y) < tol
+    m, v, _, _ = nl.stats()
+    assert rel_err(m, mean) < TOL_FP32 * 5 and rel_err(v, var) < TOL_FP32 * 5
+    dy = rng.standard_normal((C, B, S * S)).astype(np.float32)
+    dy[:, length:, :] = 0
+    if dtype_name != "FP32":
+        dy = dy.astype(np.float16).astype(np.float32) if dtype_name == "FP16" else (dy.view(np.uint32) & 0xFFFF0000).view(np.float32)
+    dyb = cabi.upload_act(dy, dtype, B, C, S, S)
+    dx = cabi.download_act(nl.backward(xb, dyb), dtype, B, C, S, S)
+    ref_dx, dgam, dbet = co.group_norm_backward(x, dy, gamma, mean, var, gs, set_off, length)
+    assert rel_err(dx, ref_dx) < tol
+    _, _, dg, db = nl.stats()
+    assert rel_err(dg, dgam) < 1e-4 and rel_err(db, dbet) < 1e-4
