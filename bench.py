@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Darknet19 448 px FP16C_FP32A training images/s (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU implementation
+
+One "step" = one mini-batch of the full training hot path (layout import, forward, loss, backward, gradient
+exchange, optimizer) over synthetic ImageNet-shaped data with random-init weights.
+
+  value  whole-job images/s with the batches already resident in HBM (dynamic_load = 0 semantics), timed with CUDA
+         events on the compute stream over exactly K steps, max over ranks
+  e2e    the same metric through the reference-facing API (cnn.train: per step a host->device copy of the batch from
+         pinned host memory and a device->host read of the per-sample loss), host buffers in, loss out
+  roofline  dominant kernel family (tcgen05 implicit-GEMM conv): algorithmic FLOPs / CUDA-event time of its launches
+         inside the timed region, against the measured dense bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline  the compiled reference (oracle/_ref, OpenBLAS back-end) on the host cores, bounded sample
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "darknet19_448_train_images_per_sec"
+UNIT = "images/s"
+TRAIN_GFLOP_PER_IMG = 66.71     # algorithmic 2*M*N*K incl. bias column, fwd + dgrad + wgrad
+HYPER = dict(learning_rate=0.003, momentum=0.9, weight_decay=0.0002)   # examples/ImageNET/imagenet_train.py:101-103 upstream
+
+
+def darknet19_spec(batch, size=448, classes=1000):
+    from cianna_b200 import configs
+    return configs.darknet19(batch, size, classes)
+
+
+def synth_batches(nb_batch, batch, size, classes, seed):
+    """inputs (U[0,255) - 100)/155 like examples/ImageNET/aux_fct.py:122 upstream, one-hot targets"""
+    rng = np.random.default_rng(seed)
+    n = nb_batch * batch
+    x = ((rng.random((n, size * size * 3), dtype=np.float32) * 255.0 - 100.0) / 155.0).astype(np.float32)
+    t = np.zeros((n, classes), dtype=np.float32)
+    t[np.arange(n), rng.integers(0, classes, n)] = 1.0
+    return x, t
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1398.3), d.get("hbm_gbs", 6547.5), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """the UNMODIFIED reference (oracle/_ref/omp: src/*.c + OpenBLAS back-end) through its own Python API on the host cores"""
+    if rank != 0:
+        return
+    from oracle import ref_driver as rd, ref_loader
+    if not ref_loader.available("omp"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/omp/CIANNA.so is not built (needs /root/reference at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    b = 2 if (args.steps + args.warmup) <= 24 else 1
+    spec = darknet19_spec(b, args.size, 1000)
+    cnn, _ = ref_loader.load("omp")
+    with rd._Quiet():
+        rd.build_network(cnn, spec, "C_BLAS", "off", network=0)
+    kw = dict(nb_iter=1, control_interv=1000, shuffle_every=0, silent=1, network=0, confmat=0, save_every=0, **HYPER)
+
+    def run(nb, seed):
+        x, t = synth_batches(nb, b, args.size, 1000, seed)
+        with rd._Quiet():
+            cnn.create_dataset("TRAIN", nb * b, x, t, network=0, silent=1)
+            t0 = time.perf_counter()
+            cnn.train(**kw)
+            return time.perf_counter() - t0
+
+    if args.warmup > 0:
+        run(args.warmup, 1)
+    dt = run(args.steps, 2)
+    val = args.steps * b / dt
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": "Darknet19 ImageNet classifier 448px training (reference CPU back-end C_BLAS, FP32)", "batch_per_step": b,
+                       "image_size": args.size, "classes": 1000},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "%d training steps of %d images, reference built from /root/reference/src with OpenBLAS + OpenMP" % (args.steps, b)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(size):
+    """bounded CPU sample for the main line (rank 0, N = 1): 2 steps of 2 images with the compiled reference"""
+    from oracle import ref_driver as rd, ref_loader
+    if not ref_loader.available("omp"):
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref/omp not built"}
+    code = r"""
+import sys, os, time, json
+sys.path.insert(0, %r)
+import bench
+from oracle import ref_driver as rd, ref_loader
+cnn, _ = ref_loader.load("omp")
+spec = bench.darknet19_spec(2, %d, 1000)
+with rd._Quiet():
+    rd.build_network(cnn, spec, "C_BLAS", "off", network=0)
+x, t = bench.synth_batches(2, 2, %d, 1000, 3)
+with rd._Quiet():
+    cnn.create_dataset("TRAIN", 4, x, t, network=0, silent=1)
+    t0 = time.perf_counter()
+    cnn.train(nb_iter=1, control_interv=1000, shuffle_every=0, silent=1, network=0, confmat=0, save_every=0, **bench.HYPER)
+    dt = time.perf_counter() - t0
+sys.stderr.write("CPUBASE " + json.dumps({"dt": dt}) + "\n")
+""" % (ROOT, size, size)
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OPENBLAS_NUM_THREADS=str(cores))
+    try:
+        r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=600)
+        for ln in r.stderr.splitlines():
+            if ln.startswith("CPUBASE "):
+                dt = json.loads(ln[8:])["dt"]
+                return {"value": 4.0 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": "1 epoch of 2 steps x 2 images (Darknet19-448, FP32, C_BLAS + OpenMP), %.1f s" % dt}
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "failed: " + r.stderr[-200:]}
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "timed out after 600 s"}
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, local_rank, world):
+    from cianna_b200 import CIANNA as cnn
+    from cianna_b200 import cabi
+    from cianna_b200 import utils
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = cabi.lib()
+    cabi.check(L.cb200_init(local_rank))
+    H = cnn.host()
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    H.cb_train_steps.argtypes = [vp, ci, cf, cf, cf, ci, ci]
+    H.cb_forward_steps.argtypes = [vp, ci, ci, ci]
+    L.cb200_profile_collect.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+
+    B = args.batch
+    spec = darknet19_spec(B, args.size, 1000)
+    quiet = utils.Quiet()
+    with quiet:
+        utils.build_network(cnn, spec, "C_CUDA", args.precision, network=0, dynamic_load=1)
+    net = cnn._net(0)
+    if world > 1:
+        import torch
+        idbuf = (ctypes.c_char * 128)()
+        if rank == 0:
+            H.cb_dp_unique_id(idbuf)
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+        H.cb_dp_init(net, idbuf, rank, world)
+    cnn.set_TC_scale_factor(256.0, network=0)     # examples/ImageNET/imagenet_train.py upstream: TC_scale_factor=256
+
+    nb = min(args.steps, args.host_batches)
+    x, t = synth_batches(nb, B, args.size, 1000, seed=100 + rank)
+    with quiet:
+        cnn.create_dataset("TRAIN", nb * B, x, t, network=0, silent=1)
+        cnn.create_dataset("TEST", min(nb, 2) * B, x[: min(nb, 2) * B], t[: min(nb, 2) * B], network=0, silent=1)
+    del x, t
+    lr, mom, wd = HYPER["learning_rate"], HYPER["momentum"], HYPER["weight_decay"]
+
+    def barrier():
+        cabi.check(L.cb200_device_sync())
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn):
+        ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
+        cabi.check(L.cb200_event_create(ctypes.byref(ev0)))
+        cabi.check(L.cb200_event_create(ctypes.byref(ev1)))
+        barrier()
+        cabi.check(L.cb200_event_record(ev0, None))
+        fn()
+        cabi.check(L.cb200_event_record(ev1, None))
+        ms = ctypes.c_float()
+        cabi.check(L.cb200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+        barrier()
+        v = float(ms.value)
+        if dist is not None:
+            import torch
+            tt = torch.tensor([v], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            v = float(tt.item())
+        return v
+
+    # ---- device-resident steps (value) with per-family event timing of the conv kernels
+    H.cb_train_steps(net, args.warmup, lr, mom, wd, 1, 0)
+    barrier()
+    L.cb200_profile_reset()
+    L.cb200_profile_enable(1)
+    L.cb200_launch_count(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res = timed(lambda: H.cb_train_steps(net, args.steps, lr, mom, wd, 1, 0))
+    clocks = sampler.stop()
+    launches = int(L.cb200_launch_count(0))
+    L.cb200_profile_enable(0)
+    fam = {}
+    for f, name in ((0, "conv_fwd_tcgen05"), (1, "conv_dgrad_tcgen05"), (2, "conv_wgrad_tcgen05"), (3, "conv_fwd_simt"), (4, "conv_dgrad_simt"),
+                    (5, "conv_wgrad_simt"), (6, "pool"), (7, "group_norm")):
+        ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        cabi.check(L.cb200_profile_collect(f, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n)))
+        fam[name] = {"ms": ms.value, "work": work.value, "launches": int(n.value)}
+    L.cb200_profile_reset()
+    loss_after = cnn.host().cb_net_last_epoch_loss(net)
+
+    # ---- end to end through the reference-facing API: cnn.train over host-resident batches (dynamic_load = 1)
+    def e2e_run():
+        full, rem = divmod(args.steps, nb)
+        with quiet:
+            if full:
+                cnn.train(nb_iter=full, control_interv=10 ** 6, shuffle_every=0, silent=1, network=0, TC_scale_factor=256.0, **HYPER)
+        if rem:
+            H.cb_train_steps(net, rem, lr, mom, wd, 0, 1)
+    H.cb_train_steps(net, min(args.warmup, 2), lr, mom, wd, 0, 1)
+    ms_e2e = timed(e2e_run)
+
+    # ---- inference (forward only), device resident and end to end
+    H.cb_forward_steps(net, 2, 1, 0)
+    ms_inf = timed(lambda: H.cb_forward_steps(net, args.steps, 1, 0))
+    ms_inf_e2e = timed(lambda: H.cb_forward_steps(net, args.steps, 0, 1))
+
+    if rank != 0:
+        return
+    imgs = args.steps * B * world
+    value = imgs / (ms_res / 1000.0)
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    conv_tc = {k: v for k, v in fam.items() if k.endswith("tcgen05") and v["launches"] > 0}
+    if conv_tc:
+        dom = max(conv_tc, key=lambda k: conv_tc[k]["ms"])
+        ach = conv_tc[dom]["work"] / (conv_tc[dom]["ms"] / 1000.0) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches": conv_tc[dom]["launches"], "avg_launch_ms": conv_tc[dom]["ms"] / conv_tc[dom]["launches"],
+                "share_of_step": conv_tc[dom]["ms"] / ms_res}
+    else:
+        dom = max(fam, key=lambda k: fam[k]["ms"])
+        ach = fam[dom]["work"] / max(fam[dom]["ms"], 1e-9) * 1e3 / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src}
+    families = {}
+    for k, v in fam.items():
+        if v["launches"] == 0:
+            continue
+        rate = v["work"] / (v["ms"] / 1000.0)
+        families[k] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                       ("tflops" if k.startswith("conv") else "gbs"): rate / (1e12 if k.startswith("conv") else 1e9)}
+    es = 2 if args.precision != "off" else 4
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"off": "f32", "FP16C_FP32A": "f16", "BF16C_FP32A": "bf16"}[args.precision], "data": "synthetic",
+            "config": {"workload": "Darknet19 ImageNet classifier 448px %s training, synthetic data" % args.precision, "batch_per_gpu": B,
+                       "global_batch": B * world, "image_size": args.size, "classes": 1000, "parallelism": "dp%d" % world,
+                       "l2_policy": "inputs larger than L2 (activations %.1f GB per step)" % (36.5e6 * 2 * B / 1e9),
+                       "train_gflop_per_image": TRAIN_GFLOP_PER_IMG},
+            "e2e": {"value": imgs / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": B * ((args.size * args.size * 3 + 1) + 1000) * es,
+                    "d2h_bytes_per_step": B * 4, "api": "cianna_b200.CIANNA.train (dynamic_load=1)"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_families": families,
+            "effective_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
+            "inference": {"value": imgs / (ms_inf / 1000.0), "unit": UNIT, "e2e": imgs / (ms_inf_e2e / 1000.0)},
+            "last_epoch_loss": loss_after}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(args.size)
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "skipped (reported at N=1 only)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=448)
+    ap.add_argument("--precision", default="FP16C_FP32A", choices=["off", "FP16C_FP32A", "BF16C_FP32A"])
+    ap.add_argument("--host-batches", type=int, default=4, help="distinct synthetic batches kept in pinned host memory")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,12 @@ extern cudaStream_t g_stream;       // default compute stream of the core
 extern int g_num_sms;
 extern long long g_launches;
 
+// opt-in per-kernel-family timing (runtime.cu). Families: see cb200_profile_collect in the header.
+void prof_begin(int family, double work, cudaStream_t st);
+void prof_end(cudaStream_t st);
+enum { PROF_CONV_FWD_TC = 0, PROF_CONV_DGRAD_TC = 1, PROF_CONV_WGRAD_TC = 2, PROF_CONV_FWD_SIMT = 3, PROF_CONV_DGRAD_SIMT = 4,
+       PROF_CONV_WGRAD_SIMT = 5, PROF_POOL = 6, PROF_NORM = 7, PROF_OPTIM = 8, PROF_OTHER = 9 };
+
 inline cudaStream_t as_stream(void* s) { return s ? (cudaStream_t)s : g_stream; }
 
 #define CB_REQUIRE_DEVICE()                                                               \

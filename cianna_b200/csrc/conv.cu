@@ -116,18 +116,27 @@ int cb200_dense_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weigh
 int cb200_conv_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y, void* s) {
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d); if (rc) return rc;
-	if (!g_force_simt && conv_tc_fwd_supported(d)) { g_last_conv_impl = "tcgen05"; return conv_forward_tc(d, w, x, y, as_stream(s)); }
-	g_last_conv_impl = "simt";
-	return conv_forward_simt(d, w, x, y, as_stream(s));
+	// algorithmic FLOPs: 2*M*N*K with K including the bias column, excluding any channel padding
+	const double flops = 2.0 * d->batch * d->out_h * d->out_w * (double)d->out_c * ((double)d->f_h * d->f_w * d->in_c + 1);
+	const bool tc = !g_force_simt && conv_tc_fwd_supported(d);
+	g_last_conv_impl = tc ? "tcgen05" : "simt";
+	prof_begin(tc ? PROF_CONV_FWD_TC : PROF_CONV_FWD_SIMT, flops, as_stream(s));
+	rc = tc ? conv_forward_tc(d, w, x, y, as_stream(s)) : conv_forward_simt(d, w, x, y, as_stream(s));
+	prof_end(as_stream(s));
+	return rc;
 }
 
 int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* dy, void* dx,
                              const cb200_activ* prev_activ, const void* prev_out, void* s) {
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d); if (rc) return rc;
-	if (!g_force_simt && conv_tc_dgrad_supported(d)) { g_last_conv_impl = "tcgen05"; return conv_dgrad_tc(d, w, dy, dx, prev_activ, prev_out, as_stream(s)); }
-	g_last_conv_impl = "simt";
-	return conv_dgrad_simt(d, w, dy, dx, prev_activ, prev_out, as_stream(s));
+	const double flops = 2.0 * d->batch * d->in_h * d->in_w * (double)d->in_c * ((double)d->f_h * d->f_w * d->out_c);
+	const bool tc = !g_force_simt && conv_tc_dgrad_supported(d);
+	g_last_conv_impl = tc ? "tcgen05" : "simt";
+	prof_begin(tc ? PROF_CONV_DGRAD_TC : PROF_CONV_DGRAD_SIMT, flops, as_stream(s));
+	rc = tc ? conv_dgrad_tc(d, w, dy, dx, prev_activ, prev_out, as_stream(s)) : conv_dgrad_simt(d, w, dy, dx, prev_activ, prev_out, as_stream(s));
+	prof_end(as_stream(s));
+	return rc;
 }
 
 int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, void* s) {
@@ -137,9 +146,13 @@ int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weigh
 	long long P = (long long)d->batch * d->out_h * d->out_w;
 	rc = conv_colsum(d->dtype, dy, w->grad_b, P, d->out_c, st);
 	if (rc) return rc;
-	if (!g_force_simt && conv_tc_wgrad_supported(d)) { g_last_conv_impl = "tcgen05"; return conv_wgrad_tc(d, w, x, dy, st); }
-	g_last_conv_impl = "simt";
-	return conv_wgrad_simt(d, w, x, dy, st);
+	const double flops = 2.0 * P * (double)d->out_c * ((double)d->f_h * d->f_w * d->in_c + 1);
+	const bool tc = !g_force_simt && conv_tc_wgrad_supported(d);
+	g_last_conv_impl = tc ? "tcgen05" : "simt";
+	prof_begin(tc ? PROF_CONV_WGRAD_TC : PROF_CONV_WGRAD_SIMT, flops, st);
+	rc = tc ? conv_wgrad_tc(d, w, x, dy, st) : conv_wgrad_simt(d, w, x, dy, st);
+	prof_end(st);
+	return rc;
 }
 
 static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, int is_pivot,

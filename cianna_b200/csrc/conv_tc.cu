@@ -304,7 +304,8 @@ static int dispatch_igemm(int bn, int bk, const CUtensorMap& ma, const CUtensorM
 	return CB200_ERR_UNSUPPORTED;
 }
 
-static int pick_bk(int cp) { return cp % 64 == 0 ? 64 : (cp % 32 == 0 ? 32 : (cp % 16 == 0 ? 16 : 0)); }
+// channel block of the K loop: the last block of a tap may run past the tensor (TMA zero-fills it)
+static int pick_bk(int cp) { return cp >= 64 ? 64 : (cp >= 32 ? 32 : (cp >= 16 ? 16 : 0)); }
 static int pick_bn(int n_pad) { return n_pad > 128 ? 256 : n_pad > 64 ? 128 : n_pad > 32 ? 64 : n_pad > 16 ? 32 : 16; }
 static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B; }
 

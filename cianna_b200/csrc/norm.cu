@@ -233,6 +233,8 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	CB_ARG(workspace != nullptr);
 	cudaStream_t st = as_stream(s);
 	double* ws = (double*)workspace;
+	// algorithmic bytes: read x (stats) + read x + write y = 3 passes over the real elements
+	prof_begin(PROF_NORM, 3.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
 	dim3 grid((unsigned)ceil_div(g.hw, NORM_PIX_PER_BLOCK), (unsigned)g.batch);
 	size_t smem = sizeof(double) * 2 * g.nb_group;
@@ -243,6 +245,7 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	long long total = (long long)g.batch * g.hw * (g.cp >> 3);
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_apply_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, gamma, beta, mean, var, g)));
 	CB_LAUNCH_CHECK();
+	prof_end(st);
 	return CB200_OK;
 }
 
@@ -257,6 +260,8 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	double* ws = (double*)workspace;
 	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
 	if (prev_activ) pa = *prev_activ;
+	// algorithmic bytes: (dy, x) for the reductions + (dy, x) + write dx = 5 passes
+	prof_begin(PROF_NORM, 5.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
 	dim3 grid((unsigned)ceil_div(g.hw, NORM_PIX_PER_BLOCK), (unsigned)g.batch);
 	size_t smem = sizeof(double) * 2 * g.nb_group;
@@ -268,6 +273,7 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_apply_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
 		(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, g)));
 	CB_LAUNCH_CHECK();
+	prof_end(st);
 	return CB200_OK;
 }
 

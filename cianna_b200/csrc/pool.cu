@@ -153,8 +153,12 @@ int cb200_pool_forward(const cb200_pool_desc* d, const void* x, void* y, uint8_t
 	PoolGeom g;
 	int rc = fill_geom(d, g); if (rc) return rc;
 	long long total = (long long)g.batch * g.out_h * g.out_w * (g.cp >> 3);
+	const double es = (double)cb200_dtype_size(d->dtype);
+	// algorithmic bytes: read the input once, write output + 1-byte argmax
+	prof_begin(PROF_POOL, (double)g.batch * g.c * ((double)g.in_h * g.in_w * es + (double)g.out_h * g.out_w * (es + 1)), as_stream(s));
 	CB_DISPATCH_DTYPE(d->dtype, T, (pool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, (T*)y, map, g)));
 	CB_LAUNCH_CHECK();
+	prof_end(as_stream(s));
 	return CB200_OK;
 }
 
@@ -167,8 +171,11 @@ int cb200_pool_backward(const cb200_pool_desc* d, const void* dy, const uint8_t*
 	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
 	if (prev_activ) pa = *prev_activ;
 	long long total = (long long)g.batch * g.in_h * g.in_w * (g.cp >> 3);
+	const double es = (double)cb200_dtype_size(d->dtype);
+	prof_begin(PROF_POOL, (double)g.batch * g.c * ((double)g.in_h * g.in_w * es + (double)g.out_h * g.out_w * (es + 1)), as_stream(s));
 	CB_DISPATCH_DTYPE(d->dtype, T, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)dy, map, (T*)dx, (const T*)prev_out, pa, g)));
 	CB_LAUNCH_CHECK();
+	prof_end(as_stream(s));
 	return CB200_OK;
 }
 

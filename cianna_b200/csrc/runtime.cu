@@ -13,6 +13,28 @@ static char g_error[1024] = "no error";
 const char* g_last_conv_impl = "none";
 int g_force_simt = 0;
 
+// ---- opt-in per-kernel-family timing (CUDA event pairs on the launching stream, harvested lazily:
+// replaces the always-on per-layer cudaEventSynchronize of upstream's perf_eval, src/auxil.c:698-766)
+struct ProfRec { cudaEvent_t a, b; int family; double work; };
+static const int PROF_MAX = 16384;
+static ProfRec* g_prof = nullptr;
+static int g_prof_n = 0;
+int g_prof_on = 0;
+
+void prof_begin(int family, double work, cudaStream_t st) {
+	if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+	if (!g_prof) g_prof = (ProfRec*)calloc(PROF_MAX, sizeof(ProfRec));
+	ProfRec& r = g_prof[g_prof_n];
+	if (!r.a) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
+	r.family = family; r.work = work;
+	cudaEventRecord(r.a, st);
+}
+void prof_end(cudaStream_t st) {
+	if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+	cudaEventRecord(g_prof[g_prof_n].b, st);
+	g_prof_n++;
+}
+
 void set_error(const char* fmt, ...) {
 	va_list ap;
 	va_start(ap, fmt);
@@ -29,6 +51,22 @@ const char* cb200_version(void) { return "cianna_b200 0.1 (sm_100a)"; }
 const char* cb200_last_conv_impl(void) { return g_last_conv_impl; }
 void cb200_force_simt(int on) { g_force_simt = on; }
 long long cb200_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+void cb200_profile_enable(int on) { g_prof_on = on; }
+int cb200_profile_collect(int family, double* ms, double* work, long long* launches) {
+	CB_REQUIRE_DEVICE();
+	CB_CUDA(cudaDeviceSynchronize());
+	double t = 0.0, w = 0.0; long long n = 0;
+	for (int i = 0; i < g_prof_n; i++) {
+		if (g_prof[i].family != family) continue;
+		float e = 0.0f;
+		if (cudaEventElapsedTime(&e, g_prof[i].a, g_prof[i].b) == cudaSuccess) { t += e; w += g_prof[i].work; n++; }
+	}
+	if (ms) *ms = t;
+	if (work) *work = w;
+	if (launches) *launches = n;
+	return CB200_OK;
+}
+void cb200_profile_reset(void) { g_prof_n = 0; }
 int cb200_round_channels(int c) { return round8(c); }
 size_t cb200_dtype_size(int dtype) { return dtype == CB200_FP32 ? 4 : 2; }
 
@@ -51,6 +89,9 @@ int cb200_init(int device) {
 		return CB200_ERR_UNSUPPORTED;
 	}
 	g_num_sms = prop.multiProcessorCount;
+	// debugging aid: CB200_FORCE_SIMT=1 routes every conv through the generic kernels (see cb200_force_simt)
+	const char* fs = getenv("CB200_FORCE_SIMT");
+	if (fs && fs[0] == '1') g_force_simt = 1;
 	if (!g_stream) CB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
 	g_have_device = true;
 	return CB200_OK;

@@ -152,6 +152,7 @@ struct network {
 	float last_batch_loss;
 	double last_epoch_loss;
 	float last_items_per_s;
+	void *out_host;        /* pinned staging of the last layer's output (inference read-back) */
 };
 
 extern network *networks[MAX_NETWORKS_NB];
@@ -239,6 +240,8 @@ void cb_set_dataset(network *net, const char *name, int size, const float *input
 void cb_swap_data_buffers(network *net, const char *name);
 void cb_net_in_dims(network *net, int *out4);
 void cb_set_TC_scale_factor(network *net, float v);
+void cb_train_steps(network *net, int nsteps, float lr, float momentum, float weight_decay, int resident, int sync_each_step);
+void cb_forward_steps(network *net, int nsteps, int resident, int sync_each_step);
 
 #define CB_CHECK(call) do { int rc__ = (call); if (rc__ != 0) { \
 	printf("\nERROR: %s failed (%d): %s\n", #call, rc__, cb200_last_error()); exit(EXIT_FAILURE); } } while (0)

@@ -365,6 +365,71 @@ void cb_dp_init(network *net, const void *id128, int rank, int world)
 }
 
 /* ------------------------------------------------------------------ training loop */
+/* One mini-batch of the training loop (body of upstream's batch loop, src/auxil.c:1797-1917): host->device copy of
+ * the batch when it is not device-resident, layout import, forward sweep, loss monitor (per-sample sums, async
+ * device->host), backward sweep, gradient exchange and optimizer.  Everything is enqueued; the caller decides
+ * when to synchronise. */
+static void train_one_batch(network *net, Dataset *data, int j, int resident)
+{
+	int k;
+	const void *tgt;
+	net->is_inference = 0;
+	net->length = (j == data->nb_batch - 1 && data->size % net->batch_size > 0) ? data->size % net->batch_size : net->batch_size;
+	if (!resident) {
+		cb_load_batch_typed(net, data->input[j], data->target[j]);
+		use_device_batch(net, net->input_raw);
+		tgt = net->target;
+	} else {
+		use_device_batch(net, data->input_device[j]);
+		tgt = data->target_device[j];
+	}
+	for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
+	/* the loss monitor reads the forward output, so it can be queued before the backward sweep */
+	output_error(net, tgt);
+	CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
+	backward_pass(net, tgt);
+}
+
+/* exactly `nsteps` training steps cycling over the TRAIN dataset's batches with the current hyper-parameters
+ * (benchmark / profiling entry: the same per-batch work as train_network, without the printing) */
+void cb_train_steps(network *net, int nsteps, float lr, float momentum, float weight_decay, int resident, int sync_each_step)
+{
+	int s;
+	if (net->train.input == NULL) { printf("\nERROR: no TRAIN dataset defined\n"); exit(EXIT_FAILURE); }
+	prepare_training(net);
+	if (resident) dataset_upload(net, &net->train);
+	set_hyper(net, lr, momentum, weight_decay);
+	for (s = 0; s < nsteps; s++) {
+		train_one_batch(net, &net->train, s % net->train.nb_batch, resident);
+		if (sync_each_step) CB_CHECK(cb200_stream_sync(NULL));
+	}
+}
+
+/* `nsteps` forward-only passes over the TEST dataset's batches (inference throughput) */
+void cb_forward_steps(network *net, int nsteps, int resident, int sync_each_step)
+{
+	int s, k;
+	Dataset *data = &net->test;
+	if (data->input == NULL) { printf("\nERROR: no TEST dataset defined\n"); exit(EXIT_FAILURE); }
+	if (resident) dataset_upload(net, data);
+	net->is_inference = 1;
+	net->length = net->batch_size;
+	for (s = 0; s < nsteps; s++) {
+		int j = s % data->nb_batch;
+		if (!resident) { cb_load_batch_typed(net, data->input[j], NULL); use_device_batch(net, net->input_raw); }
+		else use_device_batch(net, data->input_device[j]);
+		for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
+		if (!resident) {
+			/* device->host read of the step's result: the class scores of the batch */
+			layer *last = net->net_layers[net->nb_layers - 1];
+			size_t bytes = (size_t)net->batch_size * last->out_h * last->out_w * cb200_round_channels(last->out_c) * cb200_dtype_size(net->dtype);
+			if (net->out_host == NULL) CB_CHECK(cb200_host_alloc(&net->out_host, bytes));
+			CB_CHECK(cb200_d2h(net->out_host, last->output, bytes, NULL));
+		}
+		if (sync_each_step) CB_CHECK(cb200_stream_sync(NULL));
+	}
+}
+
 static void progress(network *net, int done, int total, double loss, double ips)
 {
 	int i, size = net->adv_size, filled = (int)((double)done / total * size);
@@ -409,21 +474,7 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		net->is_inference = 0;
 		for (j = 0; j < net->train.nb_batch; j++) {
 			double t_batch = now_s(), batch_error = 0.0;
-			const void *tgt;
-			net->length = (j == net->train.nb_batch - 1 && net->train.size % net->batch_size > 0) ? net->train.size % net->batch_size : net->batch_size;
-			if (net->dynamic_load) {
-				cb_load_batch_typed(net, net->train.input[j], net->train.target[j]);
-				use_device_batch(net, net->input_raw);
-				tgt = net->target;
-			} else {
-				use_device_batch(net, net->train.input_device[j]);
-				tgt = net->train.target_device[j];
-			}
-			for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
-			/* the loss monitor reads the forward output, so it can be queued before the backward sweep */
-			output_error(net, tgt);
-			CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
-			backward_pass(net, tgt);
+			train_one_batch(net, &net->train, j, !net->dynamic_load);
 			CB_CHECK(cb200_stream_sync(NULL));
 			for (k = 0; k < net->length; k++) { batch_error += net->loss_host[k]; total_error += net->loss_host[k]; }
 			batch_error /= net->length;

@@ -73,6 +73,14 @@ void cb200_force_simt(int on);
 /* number of kernels launched by this library since the last reset */
 long long cb200_launch_count(int reset);
 
+/* opt-in timing of kernel families with CUDA event pairs recorded on the launching stream (no per-layer sync:
+ * replaces the always-on cuda_perf_eval_* of src/cuda/cuda_main.cu:533-588).  family: 0/1/2 = tcgen05 conv
+ * forward / data-grad / weight-grad, 3/4/5 = same on the SIMT kernels, 6 = pooling, 7 = group-norm.
+ * `work` accumulates the algorithmic FLOPs (conv) or bytes (pool / norm) of the timed launches. */
+void cb200_profile_enable(int on);
+void cb200_profile_reset(void);
+int  cb200_profile_collect(int family, double* ms, double* work, long long* launches);
+
 int  cb200_round_channels(int c);
 size_t cb200_dtype_size(int dtype);
 

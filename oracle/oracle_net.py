@@ -114,11 +114,15 @@ class OracleNet:
         return pre
 
     def _deriv(self, L, delta):
-        """previous->deriv_activation applied to the delta that reaches layer L's output"""
+        """previous->deriv_activation applied to the delta that reaches layer L's output.
+        L["deriv_value"] (optional) replaces the activated output the derivative is evaluated on: the mixed-precision
+        parity tests put the product's own 16-bit activations there (and the product's argmax in L["map"]) so that both
+        sides take the same DISCRETE decisions (leaky-ReLU slope, max-pool winner) and only the arithmetic is compared."""
         if L["act"] == "RELU":
+            value = L.get("deriv_value", L["output"])
             if L["kind"] == "dense":
-                return co.relu_deriv_dense(delta, L["output"], self.length)
-            return co.relu_deriv(delta, L["output"], self.length)
+                return co.relu_deriv_dense(delta, value, self.length)
+            return co.relu_deriv(delta, value, self.length)
         return delta
 
     def backward(self, target, lr, momentum=0.0, weight_decay=0.0):

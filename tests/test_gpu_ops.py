@@ -151,27 +151,30 @@ def test_pool_argmax_bit_exact_vs_golden(cabi):
     assert np.array_equal(pool.map_ref_layout(), g["map_2"])
 
 
+@pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
 @pytest.mark.parametrize("cfg", [(2, 2, 0, "MAX"), (3, 2, 1, "MAX"), (3, 1, 1, "MAX"), (2, 2, 0, "AVG"), (3, 2, 1, "AVG")])
-def test_pool_forward_backward_vs_oracle(cabi, cfg):
-    """window / stride / padding variants incl. ties (quantised values) - first maximum must win"""
+def test_pool_forward_backward_vs_oracle(cabi, cfg, dtype_name):
+    """window / stride / padding variants incl. ties (values quantised to halves, exactly representable in every
+    dtype) - first maximum must win, argmax bit-exact in all three storage types"""
     p, s, pad, kind = cfg
     B, C, S = 3, 10, 9
+    DT = getattr(cabi, dtype_name)
     rng = np.random.default_rng(5)
     x = np.round(rng.standard_normal((C, B, S * S)) * 2).astype(np.float32) / 2      # many exact ties
-    pool = cabi.PoolLayer(cabi.FP32, B, C, S, S, p, s, pad, cabi.POOL_MAX if kind == "MAX" else cabi.POOL_AVG)
-    xb = cabi.upload_act(x, cabi.FP32, B, C, S, S)
+    pool = cabi.PoolLayer(DT, B, C, S, S, p, s, pad, cabi.POOL_MAX if kind == "MAX" else cabi.POOL_AVG)
+    xb = cabi.upload_act(x, DT, B, C, S, S)
     So = (S + 2 * pad - p) // s + 1
-    y = cabi.download_act(pool.forward(xb), cabi.FP32, B, C, So, So)
+    y = cabi.download_act(pool.forward(xb), DT, B, C, So, So)
     ref_y, ref_m = co.pool_forward(x, B, C, S, S, p, s, pad, kind)
     if kind == "MAX":
         assert np.array_equal(y, ref_y)
         assert np.array_equal(pool.map_ref_layout(), ref_m)
     else:
-        assert rel_err(y, ref_y) < TOL_FP32
-    dy = rng.standard_normal((C, B, So * So)).astype(np.float32)
-    dyb = cabi.upload_act(dy, cabi.FP32, B, C, So, So)
-    dx = cabi.download_act(pool.backward(dyb), cabi.FP32, B, C, S, S)
-    assert rel_err(dx, co.pool_backward(dy, ref_m, B, C, S, S, p, s, pad, kind)) < TOL_FP32
+        assert rel_err(y, ref_y) < (TOL_FP32 if dtype_name == "FP32" else TOL_MIXED)
+    dy = (np.round(rng.standard_normal((C, B, So * So)) * 8) / 8).astype(np.float32)
+    dyb = cabi.upload_act(dy, DT, B, C, So, So)
+    dx = cabi.download_act(pool.backward(dyb), DT, B, C, S, S)
+    assert rel_err(dx, co.pool_backward(dy, ref_m, B, C, S, S, p, s, pad, kind)) < (TOL_FP32 if dtype_name == "FP32" else TOL_MIXED)
 
 
 @pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
