@@ -31,7 +31,8 @@ class ConvDesc(ctypes.Structure):
                 ("in_c", ctypes.c_int), ("in_h", ctypes.c_int), ("in_w", ctypes.c_int),
                 ("out_c", ctypes.c_int), ("out_h", ctypes.c_int), ("out_w", ctypes.c_int),
                 ("f_h", ctypes.c_int), ("f_w", ctypes.c_int), ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int),
-                ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int), ("bias_value", ctypes.c_float), ("activ", Activ)]
+                ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int), ("bias_value", ctypes.c_float), ("activ", Activ),
+                ("input_is_patches", ctypes.c_int)]
 
 
 class ConvWeights(ctypes.Structure):
@@ -153,7 +154,7 @@ class ConvLayer:
         out_h = (in_h + 2 * pad - f) // stride + 1
         out_w = (in_w + 2 * pad - f) // stride + 1
         self.d = ConvDesc(dtype, batch, batch if length is None else length, in_c, in_h, in_w, out_c, out_h, out_w,
-                          f, f, stride, stride, pad, pad, bias_value, act if act is not None else activ(LINEAR))
+                          f, f, stride, stride, pad, pad, bias_value, act if act is not None else activ(LINEAR), 0)
         self.dtype = dtype
         es = L.cb200_dtype_size(dtype)
         dp = ctypes.byref(self.d)

@@ -73,6 +73,44 @@ __global__ void conv_update_kernel(float* __restrict__ master, float* __restrict
 	}
 }
 
+// ---- first layer run on patch rows (cb200_import_input_patches): a 1x1 GEMM over kp columns, bias inside the GEMM
+static cb200_conv_desc effective_desc(const cb200_conv_desc* d) {
+	cb200_conv_desc e = *d;
+	if (d->input_is_patches) {
+		e.in_c = cb200_patch_width(d->in_c, d->f_h, d->f_w);
+		e.in_h = d->out_h; e.in_w = d->out_w;
+		e.f_h = 1; e.f_w = 1; e.stride_h = 1; e.stride_w = 1; e.pad_h = 0; e.pad_w = 0;
+		e.bias_value = 0.0f;
+		e.input_is_patches = 0;
+	}
+	return e;
+}
+template <typename T>
+__global__ void patch_prepare_kernel(const float* __restrict__ master, T* __restrict__ w_fwd, float* __restrict__ bias_w, int out_c, int kref, int kp) {
+	const size_t total = (size_t)out_c * kp;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int f = (int)(i / kp), col = (int)(i - (size_t)f * kp);
+		w_fwd[i] = from_f32<T>(col < kref ? master[(size_t)f * kref + col] : 0.0f);
+		if (col == 0) bias_w[f] = 0.0f;
+	}
+}
+template <typename T>
+__global__ void patch_update_kernel(float* __restrict__ master, float* __restrict__ moment, const float* __restrict__ grad,
+                                    const float* __restrict__ hyper, T* __restrict__ w_fwd, int out_c, int kref, int kp) {
+	const size_t total = (size_t)out_c * kref;
+	const float alpha = hyper[0], mom = hyper[1], wdlr = hyper[2], S = hyper[3];
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int f = (int)(i / kref), col = (int)(i - (size_t)f * kref);
+		float wv = master[i];
+		float m = alpha * grad[(size_t)f * kp + col] + mom * moment[i];   // the bias column's gradient comes out of the GEMM itself
+		m += wdlr * wv * S;
+		wv -= m / S;
+		moment[i] = m;
+		master[i] = wv;
+		w_fwd[(size_t)f * kp + col] = from_f32<T>(wv);
+	}
+}
+
 static int check_desc(const cb200_conv_desc* d) {
 	CB_ARG(d != nullptr);
 	CB_ARG(d->batch > 0 && d->in_c > 0 && d->out_c > 0 && d->in_h > 0 && d->in_w > 0 && d->out_h > 0 && d->out_w > 0);
@@ -87,7 +125,10 @@ using namespace cb200;
 
 extern "C" {
 
-size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * d->f_h * d->f_w * round8(d->in_c); }
+size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d) {
+	if (d->input_is_patches) return (size_t)d->out_c * cb200_patch_width(d->in_c, d->f_h, d->f_w);
+	return (size_t)d->out_c * d->f_h * d->f_w * round8(d->in_c);
+}
 size_t cb200_conv_wbwd_elems(const cb200_conv_desc* d) { return (size_t)d->in_c * d->f_h * d->f_w * round8(d->out_c); }
 size_t cb200_conv_grad_elems(const cb200_conv_desc* d) { return cb200_conv_wfwd_elems(d); }
 size_t cb200_conv_master_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * ((size_t)d->f_h * d->f_w * d->in_c + 1); }
@@ -96,6 +137,13 @@ static int prepare_weights_impl(const cb200_conv_desc* d, const cb200_conv_weigh
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d); if (rc) return rc;
 	cudaStream_t st = as_stream(s);
+	if (d->input_is_patches) {
+		const int kref = d->f_h * d->f_w * d->in_c + 1, kp = cb200_patch_width(d->in_c, d->f_h, d->f_w);
+		CB_DISPATCH_DTYPE(d->dtype, T, (patch_prepare_kernel<T><<<grid_for((long long)d->out_c * kp, 256), 256, 0, st>>>(
+			w->master, (T*)w->w_fwd, w->bias_w, d->out_c, kref, kp)));
+		CB_LAUNCH_CHECK();
+		return CB200_OK;
+	}
 	// pad lanes of the operands must be zero: clear, then scatter
 	CB_CUDA(cudaMemsetAsync(w->w_fwd, 0, cb200_conv_wfwd_elems(d) * cb200_dtype_size(d->dtype), st));
 	CB_CUDA(cudaMemsetAsync(w->w_bwd, 0, cb200_conv_wbwd_elems(d) * cb200_dtype_size(d->dtype), st));
@@ -113,11 +161,13 @@ int cb200_dense_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weigh
 	return prepare_weights_impl(d, w, 1, (size_t)d->out_c + 1, s);
 }
 
-int cb200_conv_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y, void* s) {
+int cb200_conv_forward(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, void* y, void* s) {
 	CB_REQUIRE_DEVICE();
-	int rc = check_desc(d); if (rc) return rc;
+	int rc = check_desc(d_in); if (rc) return rc;
+	const cb200_conv_desc eff = effective_desc(d_in);
+	const cb200_conv_desc* d = &eff;
 	// algorithmic FLOPs: 2*M*N*K with K including the bias column, excluding any channel padding
-	const double flops = 2.0 * d->batch * d->out_h * d->out_w * (double)d->out_c * ((double)d->f_h * d->f_w * d->in_c + 1);
+	const double flops = 2.0 * d_in->batch * d_in->out_h * d_in->out_w * (double)d_in->out_c * ((double)d_in->f_h * d_in->f_w * d_in->in_c + 1);
 	const bool tc = !g_force_simt && conv_tc_fwd_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_FWD_TC : PROF_CONV_FWD_SIMT, flops, as_stream(s));
@@ -130,6 +180,7 @@ int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights*
                              const cb200_activ* prev_activ, const void* prev_out, void* s) {
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d); if (rc) return rc;
+	if (d->input_is_patches) { set_error("cb200_conv_backward_data: a patch-input (first) layer has no data gradient"); return CB200_ERR_UNSUPPORTED; }
 	const double flops = 2.0 * d->batch * d->in_h * d->in_w * (double)d->in_c * ((double)d->f_h * d->f_w * d->out_c);
 	const bool tc = !g_force_simt && conv_tc_dgrad_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
@@ -139,14 +190,18 @@ int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights*
 	return rc;
 }
 
-int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, void* s) {
+int cb200_conv_backward_weights(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, const void* dy, void* s) {
 	CB_REQUIRE_DEVICE();
-	int rc = check_desc(d); if (rc) return rc;
+	int rc = check_desc(d_in); if (rc) return rc;
+	const cb200_conv_desc eff = effective_desc(d_in);
+	const cb200_conv_desc* d = &eff;
 	cudaStream_t st = as_stream(s);
 	long long P = (long long)d->batch * d->out_h * d->out_w;
-	rc = conv_colsum(d->dtype, dy, w->grad_b, P, d->out_c, st);
-	if (rc) return rc;
-	const double flops = 2.0 * P * (double)d->out_c * ((double)d->f_h * d->f_w * d->in_c + 1);
+	if (!d_in->input_is_patches) {      // (patch rows carry the bias input as a column: its gradient comes out of the GEMM)
+		rc = conv_colsum(d->dtype, dy, w->grad_b, P, d->out_c, st);
+		if (rc) return rc;
+	}
+	const double flops = 2.0 * P * (double)d_in->out_c * ((double)d_in->f_h * d_in->f_w * d_in->in_c + 1);
 	const bool tc = !g_force_simt && conv_tc_wgrad_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_WGRAD_TC : PROF_CONV_WGRAD_SIMT, flops, st);
@@ -159,6 +214,13 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
                        size_t ms_f, size_t ms_c, void* s) {
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d); if (rc) return rc;
+	if (d->input_is_patches) {
+		const int kref = d->f_h * d->f_w * d->in_c + 1, kp = cb200_patch_width(d->in_c, d->f_h, d->f_w);
+		CB_DISPATCH_DTYPE(d->dtype, T, (patch_update_kernel<T><<<grid_for((long long)d->out_c * kref, 256), 256, 0, as_stream(s)>>>(
+			w->master, w->moment, w->grad, hyper, (T*)w->w_fwd, d->out_c, kref, kp)));
+		CB_LAUNCH_CHECK();
+		return CB200_OK;
+	}
 	const int taps = d->f_h * d->f_w;
 	long long total = (long long)cb200_conv_master_elems(d);
 	CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(

@@ -20,8 +20,9 @@
 //     both operands are MN-major (the contraction index, pixels, is the slow one in memory),
 //     split over pixel ranges across CTAs, FP32 atomics into the raw-gradient buffer.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (warp w may only touch TMEM lanes 32*(w%4)..+31).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then the epilogue warps
+// (forward/dgrad kernel: 8 = two per TMEM lane quadrant, a warp may only touch lanes 32*(warp%4)..+31;
+// weight-gradient kernel: 4).
 #include <cuda.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -119,14 +120,14 @@ struct IgemmCfg {
 	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
 	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias rows*/;
 	static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 	static constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);   // 128B / 64B / 32B swizzle
 	static constexpr uint32_t SBO = 8 * BK * 2;                                 // 8 rows of one swizzle atom
 };
 
 template <typename T, int BN, int BK>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
 	using Cfg = IgemmCfg<BN, BK>;
 	extern __shared__ uint8_t smem_raw[];
@@ -138,6 +139,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
 	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
 	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+	const uint32_t bias_smem = bar_base + 256u;          // 2 x 256 floats, one row per accumulator stage
 	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,7 +148,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		prefetch_tensormap(&tmap_a);
 		prefetch_tensormap(&tmap_b);
 		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-		for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+		for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
 		fence_barrier_init();
 	}
 	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -206,28 +208,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 			}
 		}
 	} else {
-		// ===================== epilogue warps =====================
+		// ===================== epilogue warps (8: two per TMEM lane quadrant, alternating 32-column chunks) ==========
+		const int ew = warp - 2;                         // 0..7
 		const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+		const int half = ew >> 2;                        // which of the two warps of the quadrant
+		const int etid = threadIdx.x - 64;               // 0..255
 		const int row = quad * 32 + lane;                // row of the 128-pixel tile
 		int acc = 0; uint32_t acc_phase = 0;
-		T* out = reinterpret_cast<T*>(p.out);
-		const T* prev = reinterpret_cast<const T*>(p.prev_out);
-		const bool mask_tail = activ_masks_tail(p.activ);
+		T* __restrict__ out = reinterpret_cast<T*>(p.out);
+		const T* __restrict__ prev = reinterpret_cast<const T*>(p.prev_out);
+		// everything the inner loop needs, in registers (the parameter block lives in constant memory)
+		const int act = p.activ.type, mode = p.mode, n_real = p.n_real, n_pad = p.n_pad, length = p.length;
+		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta, bias_value = p.bias_value;
+		const float* __restrict__ bias_w = p.bias_w;
+		const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
+		const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
+		float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
 		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-			const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
-			const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
-			const int px = twi * p.tw + (row % p.tw);
-			const int py = thi * p.th + (row / p.tw) % p.th;
-			const int pn = tni * p.tn + row / (p.tw * p.th);
-			const bool row_ok = px < p.W && py < p.H && pn < p.N;
-			const size_t pix = ((size_t)pn * p.H + py) * p.W + px;
-			const bool dead = mask_tail && pn >= p.length;
+			const int mt = tile % tiles_m, nt = tile / tiles_m;
+			const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
+			const int px = twi * tw + (row % tw);
+			const int py = thi * th + (row / tw) % th;
+			const int pn = tni * tn + row / (tw * th);
+			const bool row_ok = px < PW && py < PH && pn < PN;
+			const size_t pix = ((size_t)pn * PH + py) * PW + px;
+			const bool dead = mask_tail && pn >= length;
+			// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory
+			float* bs = bias_s + acc * 256;
+			if (mode == 0)
+				for (int c = etid; c < BN; c += 256) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
+			asm volatile("bar.sync 1, 256;" ::: "memory");
 
 			mbar_wait(tfull_bar(acc), acc_phase);
 			tc_fence_after();
 			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-			for (int c0 = 0; c0 < BN; c0 += 32) {
+			for (int c0 = half * 32; c0 < BN; c0 += 64) {
 				uint32_t r[32];
 				if (BN - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
 				else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
@@ -235,34 +252,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 					for (int j = 0; j < 16; j++) { r[j] = h[j]; r[16 + j] = 0; } }
 				tmem_ld_wait();
 				const int col0 = nt * BN + c0;
-				if (row_ok) {
 #pragma unroll
-					for (int v = 0; v < 4; v++) {
-						const int col = col0 + v * 8;
-						if (col >= p.n_pad || c0 + v * 8 >= BN) continue;
-						float o[8];
-						if (p.mode == 0) {
+				for (int v = 0; v < 4; v++) {
+					const int col = col0 + v * 8;
+					if (!row_ok || col >= n_pad || c0 + v * 8 >= BN) continue;
+					float o[8];
+#pragma unroll
+					for (int j = 0; j < 8; j++) o[j] = __uint_as_float(r[v * 8 + j]);
+					if (dead) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) o[j] = 0.0f;
+					} else if (mode == 0) {
+						const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
+						o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+						if (act == CB200_RELU) {
 #pragma unroll
 							for (int j = 0; j < 8; j++) {
-								const int ch = col + j;
-								float z = __uint_as_float(r[v * 8 + j]);
-								o[j] = (ch < p.n_real && !dead) ? activ_forward(p.activ, z + p.bias_value * __ldg(p.bias_w + ch)) : 0.0f;
+								const float z = o[j];
+								const float hi = sat + (z - sat) * leak;
+								o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
 							}
-						} else {
-							float pv[8];
-							const bool hook = prev != nullptr && p.activ.type != CB200_LINEAR;
-							if (hook) load8<T>(prev + pix * p.n_pad + col, pv);
+						} else if (act == CB200_LOGISTIC) {
 #pragma unroll
-							for (int j = 0; j < 8; j++) {
-								const int ch = col + j;
-								float z = __uint_as_float(r[v * 8 + j]);
-								if (hook) z = activ_deriv_mul(p.activ, z, pv[j]);
-								o[j] = (ch < p.n_real && !dead) ? z : 0.0f;
+							for (int j = 0; j < 8; j++) o[j] = 1.0f / (1.0f + expf(fminf(-beta * o[j], sat)));
+						}
+						if (col + 8 > n_real) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+						}
+					} else {
+						if (hook) {
+							float pv[8];
+							load8<T>(prev + pix * n_pad + col, pv);
+							if (act == CB200_RELU) {
+#pragma unroll
+								for (int j = 0; j < 8; j++) o[j] = (pv[j] <= 0.0f || pv[j] > sat) ? o[j] * leak : o[j];
+							} else {
+#pragma unroll
+								for (int j = 0; j < 8; j++) o[j] = o[j] * beta * pv[j] * (1.0f - pv[j]);
 							}
 						}
-						store8<T>(out + pix * p.n_pad + col, o);
+						if (col + 8 > n_real) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+						}
 					}
+					store8<T>(out + pix * n_pad + col, o);
 				}
+				__syncwarp();        // reconverge before the next warp-collective tcgen05.ld
 			}
 			tc_fence_before();
 			__syncwarp();
@@ -288,7 +325,7 @@ static int launch_igemm(const CUtensorMap& ma, const CUtensorMap& mb, const Igem
 		configured = true;
 	}
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-	kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+	kern<<<grid, 320, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }
@@ -501,7 +538,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 bool conv_tc_wgrad_supported(const cb200_conv_desc* d) {
 	if (!tc_common_ok(d)) return false;
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
-	return out_cp >= 64 && (in_cp >= 64 || in_cp == 32 || in_cp == 16);
+	// (a 64-channel dy slab on a tensor with fewer channels relies on TMA zero-filling the missing ones)
+	return out_cp >= 16 && (in_cp >= 64 || in_cp == 32 || in_cp == 16);
 }
 
 template <int BNC, int SLAB_C>

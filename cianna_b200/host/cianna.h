@@ -153,6 +153,7 @@ struct network {
 	double last_epoch_loss;
 	float last_items_per_s;
 	void *out_host;        /* pinned staging of the last layer's output (inference read-back) */
+	const cb200_conv_desc *patch_desc;   /* first conv layer when it consumes patch rows (few input channels), else NULL */
 };
 
 extern network *networks[MAX_NETWORKS_NB];

@@ -150,6 +150,15 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	p->desc.bias_value = current->bias_value;
 	p->desc.activ = current->activ;
 	if (current->activation_type == SOFTMAX) p->desc.activ.type = CB200_LINEAR;   /* softmax is a separate pass */
+	/* first layer on an input with very few channels (RGB / grey): the layout import unrolls the receptive fields into
+	 * patch rows so that the layer runs on the tensor-core GEMM kernels (include/cianna_b200.h, cb200_import_input_patches) */
+	p->desc.input_is_patches = (previous == NULL && cb200_round_channels(pc) < 16) ? 1 : 0;
+	if (p->desc.input_is_patches) {
+		size_t bytes = (size_t)net->batch_size * current->out_h * current->out_w * cb200_patch_width(pc, f_size[1], f_size[0]) * cb200_dtype_size(net->dtype);
+		CB_CHECK(cb200_free(net->input));
+		net->input = dev_alloc(bytes);
+		net->patch_desc = &p->desc;
+	}
 
 	conv_alloc_weights(net, &p->desc, &p->w);
 	current->output = dev_alloc(act_bytes(net, current->out_c, current->out_h, current->out_w));

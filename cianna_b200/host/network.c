@@ -257,8 +257,13 @@ void cb_load_batch(network *net, const float *input, const float *target)
 
 static void use_device_batch(network *net, const void *input_dev)
 {
-	/* dataset layout -> channels-last */
-	CB_CHECK(cb200_import_input(net->input, input_dev, net->dtype, net->batch_size, net->in_dims[3], net->in_dims[1], net->in_dims[0], NULL));
+	/* dataset layout -> channels-last (or -> first-layer patch rows) */
+	if (net->patch_desc != NULL) {
+		const cb200_conv_desc *d = net->patch_desc;
+		CB_CHECK(cb200_import_input_patches(net->input, input_dev, net->dtype, net->batch_size, d->in_c, d->in_h, d->in_w,
+			d->f_h, d->f_w, d->stride_h, d->stride_w, d->pad_h, d->pad_w, d->out_h, d->out_w, d->bias_value, NULL));
+	} else
+		CB_CHECK(cb200_import_input(net->input, input_dev, net->dtype, net->batch_size, net->in_dims[3], net->in_dims[1], net->in_dims[0], NULL));
 }
 
 void cb_forward(network *net, int length, int is_inference)

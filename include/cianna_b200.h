@@ -124,6 +124,17 @@ int  cb200_host_cast_from_f32(void* host_dst, int dtype, const float* host_src, 
  * layout incl. the trailing bias slot, src/auxil.c:320-329) ; dst: act[batch][H][W][Cp].
  * Replaces the first-layer branch of im2col (src/cuda/cuda_conv_layer.cu:36-103, bias_in=1). */
 int  cb200_import_input(void* dst, const void* src, int dtype, int batch, int c, int h, int w, void* stream);
+/* First-layer variant for inputs with very few channels (RGB / grey images): writes, for every OUTPUT pixel of the
+ * first convolution, its receptive field as one row [c*f_h*f_w values in the reference's column order c*taps + tap |
+ * bias_value | zero pad] of cb200_patch_width(c, f_h, f_w) elements: dst[batch][out_h][out_w][patch_width].
+ * This is the one place where the reference's explicit unrolling (im2col_kernel with bias_in = 1,
+ * src/cuda/cuda_conv_layer.cu:36-103) is kept, fused into the layout import: with 3 input channels the unrolled row
+ * (28 values) is no larger than the layer's own output row, so the layer is HBM-bound either way, and it lets the first
+ * layer use the same tensor-core GEMM kernels as every other layer. */
+int  cb200_patch_width(int c, int f_h, int f_w);
+int  cb200_import_input_patches(void* dst, const void* src, int dtype, int batch, int c, int h, int w,
+                                int f_h, int f_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                                int out_h, int out_w, float bias_value, void* stream);
 /* Reference activation layout [C][B][H*W] (FP32, device) <-> internal (dtype). */
 int  cb200_import_cbhw(void* dst, int dtype, const float* src, int batch, int c, int h, int w, void* stream);
 int  cb200_export_cbhw(float* dst, const void* src, int dtype, int batch, int c, int h, int w, void* stream);
@@ -145,6 +156,9 @@ typedef struct {
 	int pad_h, pad_w;
 	float bias_value;     /* constant input of the bias column (layer->bias_value) */
 	cb200_activ activ;    /* this layer's activation (fused in the forward epilogue) */
+	int input_is_patches; /* 1: `x` is the patch tensor made by cb200_import_input_patches (first layer with few
+	                         input channels); the layer then runs as a 1x1 GEMM over cb200_patch_width() columns
+	                         whose last real column is the bias input, w_fwd/grad are [out_c][patch_width] */
 } cb200_conv_desc;
 
 /* Compute-side weights of one conv (or dense) layer, all device pointers owned by the caller:

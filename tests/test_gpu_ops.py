@@ -41,6 +41,8 @@ TC_SHAPES = [
     (2, 256, 14, 1000, 1, 0),  # the Darknet19 head: N=1000 -> four 256-wide tiles, last one partial
     (5, 64, 10, 32, 5, 2),     # 5x5 filter
     (128, 64, 1, 40, 1, 0),    # dense-like: 1x1 map, tile spans 128 images
+    (4, 32, 12, 32, 1, 0),     # 32 -> 32 channels: the shape of a first layer run on patch rows (weight-gradient slab wider than the tensor)
+    (2, 16, 9, 24, 3, 1),      # 16-channel operands everywhere
 ]
 
 
@@ -76,9 +78,49 @@ def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
 
     layer.backward_weights(xb, dyb)
     got = layer.grad_ref_layout()
+    assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
     ref_g = co.conv_weight_grad(col, dy).astype(np.float32)
-    assert np.array_equal(got, ref_g), cabi.lib().cb200_last_conv_impl()
+    assert np.array_equal(got, ref_g)
     layer.free(); xb.free(); dyb.free()
+
+
+@pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
+@pytest.mark.parametrize("cfg", [(4, 3, 16, 32, 3, 1, 1), (3, 1, 12, 8, 5, 2, 1), (2, 3, 9, 16, 3, 0, 2)])
+def test_first_layer_patch_rows(cabi, cfg, dtype_name):
+    """first layer on few input channels: the layout import unrolls receptive fields (reference column order, bias
+    input as a column) and the layer runs as a 1x1 GEMM; forward, weight gradient and SGD update against the oracle"""
+    import ctypes
+    B, C, S, N, f, pad, stride = cfg
+    dtype = getattr(cabi, dtype_name)
+    tol = TOL_FP32 if dtype_name == "FP32" else TOL_MIXED
+    L = cabi.lib()
+    L.cb200_patch_width.restype = ctypes.c_int
+    L.cb200_import_input_patches.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 13 + [ctypes.c_float, ctypes.c_void_p]
+    rng = np.random.default_rng(9)
+    x = np.empty((B, C * S * S + 1), np.float32)
+    x[:, :-1] = rng.integers(-3, 4, (B, C * S * S)) / 4.0          # exactly representable in every dtype
+    x[:, -1] = 0.5
+    w = (rng.integers(-4, 5, (N, f * f * C + 1)) / 8.0).astype(np.float32)
+    layer = cabi.ConvLayer(dtype, B, C, S, S, N, f, stride, pad, bias_value=0.5, act=cabi.activ(cabi.RELU))
+    layer.d.input_is_patches = 1
+    layer.set_weights(w)
+    So = (S + 2 * pad - f) // stride + 1
+    kp = L.cb200_patch_width(C, f, f)
+    es = L.cb200_dtype_size(dtype)
+    xt = np.empty(x.size, np.uint16 if es == 2 else np.float32)
+    cabi.check(L.cb200_host_cast_from_f32(xt.ctypes.data, dtype, x.ctypes.data, x.size))
+    src = cabi.DevBuf.from_numpy(xt)
+    patches = cabi.DevBuf(B * So * So * kp * es)
+    cabi.check(L.cb200_import_input_patches(patches.ptr, src.ptr, dtype, B, C, S, S, f, f, stride, stride, pad, pad, So, So, 0.5, None))
+    y = cabi.download_act(layer.forward(patches), dtype, B, N, So, So)
+    pre, col = co.conv_forward(x, w, True, B, C, S, S, f, stride, pad, 0.5)
+    assert rel_err(y, co.relu_forward(pre, B)) < tol
+    dy = (rng.integers(-4, 5, (N, B, So * So)) / 4.0).astype(np.float32)
+    dyb = cabi.upload_act(dy, dtype, B, N, So, So)
+    layer.backward_weights(patches, dyb)
+    g = layer.bufs["grad"].to_numpy(np.float32, (N, kp))[:, : f * f * C + 1]
+    assert rel_err(g, co.conv_weight_grad(col, dy)) < tol
+    assert np.array_equal(layer.bufs["grad"].to_numpy(np.float32, (N, kp))[:, f * f * C + 1:], np.zeros((N, kp - f * f * C - 1), np.float32))
 
 
 @pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
