@@ -119,6 +119,30 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* __restrict_
 	*reinterpret_cast<uint4*>(p) = r;
 }
 
+// raw (unconverted) 8-channel packet: lets a thread issue several independent 128-bit loads before it
+// starts converting, which is what keeps enough bytes in flight per SM for HBM3e (Little's law)
+template <typename T> struct Raw8 { uint4 a; };
+template <> struct Raw8<float> { float4 a, b; };
+template <typename T> __device__ __forceinline__ Raw8<T> load_raw8(const T* __restrict__ p) {
+	Raw8<T> r; r.a = __ldg(reinterpret_cast<const uint4*>(p)); return r;
+}
+template <> __device__ __forceinline__ Raw8<float> load_raw8<float>(const float* __restrict__ p) {
+	Raw8<float> r; r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1); return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&o)[8]) {
+	o[0] = r.a.x; o[1] = r.a.y; o[2] = r.a.z; o[3] = r.a.w; o[4] = r.b.x; o[5] = r.b.y; o[6] = r.b.z; o[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__half>& r, float (&o)[8]) {
+	const __half2* h = reinterpret_cast<const __half2*>(&r.a);
+#pragma unroll
+	for (int i = 0; i < 4; i++) { float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&o)[8]) {
+	const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.a);
+#pragma unroll
+	for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+
 // ---------------------------------------------------------------- activations
 // Forward: reference ReLU_activation_kernel / logistic_activation_kernel
 // (src/cuda/cuda_activ_functions.cu:37-70, 203-235); LINEAR is the identity.

@@ -12,12 +12,23 @@
 namespace cb200 {
 
 struct NormGeom {
-	int batch, length, c, cp, hw, group_size, nb_group, set_off;
+	int batch, length, c, cp, hw, group_size, nb_group, set_off, ppb;
 	float eps;
 };
 
 constexpr int NORM_THREADS = 256;
-constexpr int NORM_PIX_PER_BLOCK = 1024;
+// pixels handled by one block: sized on the host so that every launch has several waves of blocks
+// (deep layers have few pixels per sample) while a thread still streams a few 128-bit packets
+static int norm_pix_per_block(int hw, int batch, int cv) {
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	long long want_blocks = (long long)g_num_sms * 8;
+	long long ppb = ((long long)hw * batch + want_blocks - 1) / want_blocks;
+	const int min_ppb = lanes_p * 4;
+	if (ppb < min_ppb) ppb = min_ppb;
+	if (ppb > 1024) ppb = 1024;
+	return (int)ppb;
+}
 
 // Accumulate, for every channel vector owned by the thread, sum(a) and sum(a*b) over the block's
 // pixel range; b == a gives (sum x, sum x^2), b == x with a == delta gives (sum d, sum d*x).
@@ -25,56 +36,88 @@ constexpr int NORM_PIX_PER_BLOCK = 1024;
 template <typename T, bool TWO_INPUTS>
 __global__ void __launch_bounds__(NORM_THREADS)
 norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double* __restrict__ ws, NormGeom g) {
-	extern __shared__ double sm_acc[];   // [nb_group][2]
+	extern __shared__ float sm_acc[];    // [nb_group][2] block-level partial sums
 	const int cv = g.cp >> 3;
 	const int b = blockIdx.y;
-	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x) sm_acc[i] = 0.0;
+	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x) sm_acc[i] = 0.0f;
 	__syncthreads();
 
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
-	const int p0 = blockIdx.x * NORM_PIX_PER_BLOCK;
-	int p1 = p0 + NORM_PIX_PER_BLOCK;
+	const int p0 = blockIdx.x * g.ppb;
+	int p1 = p0 + g.ppb;
 	if (p1 > g.hw) p1 = g.hw;
 
-	if (lane_p < lanes_p) {
+	{
+		// (threads beyond lanes_c * lanes_p keep zero sums: every lane must reach the shuffles below)
+		const bool active = lane_p < lanes_p;
 		for (int v = lane_c; v < cv; v += lanes_c) {
 			float s0[8], s1[8];
 #pragma unroll
 			for (int j = 0; j < 8; j++) { s0[j] = 0.0f; s1[j] = 0.0f; }
-			for (int p = p0 + lane_p; p < p1; p += lanes_p) {
-				const long long o = ((long long)b * g.hw + p) * g.cp + v * 8;
-				float av[8], bv[8];
-				load8<T>(a_in + o, av);
-				if (TWO_INPUTS) load8<T>(b_in + o, bv);
+			constexpr int U = TWO_INPUTS ? 2 : 4;        // independent 128-bit loads in flight per thread: 4
+			for (int p = p0 + lane_p; active && p < p1; p += lanes_p * U) {
+				Raw8<T> ra[U], rb[U];
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					const int pp = p + u * lanes_p;
+					if (pp < p1) {
+						const long long o = ((long long)b * g.hw + pp) * g.cp + v * 8;
+						ra[u] = load_raw8<T>(a_in + o);
+						if (TWO_INPUTS) rb[u] = load_raw8<T>(b_in + o);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					if (p + u * lanes_p < p1) {
+						float av[8], bv[8];
+						unpack8(ra[u], av);
+						if (TWO_INPUTS) unpack8(rb[u], bv);
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							s0[j] += av[j];
+							s1[j] += av[j] * (TWO_INPUTS ? bv[j] : av[j]);
+						}
+					}
+				}
+			}
+			// lanes of a warp that own the same channel vector (lanes_c < 32, a power of two) are summed by shuffles
+			// first, so that only lanes_c lanes per warp touch the shared accumulators
+			bool writer = true;
+			if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
 #pragma unroll
 				for (int j = 0; j < 8; j++) {
-					s0[j] += av[j];
-					s1[j] += av[j] * (TWO_INPUTS ? bv[j] : av[j]);
+					for (int off = lanes_c; off < 32; off <<= 1) {
+						s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], off);
+						s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+					}
 				}
+				writer = (threadIdx.x & 31) < lanes_c;
 			}
 			// fold the 8 channels into their groups (a vector spans one group when group_size % 8 == 0)
-			int cur = -1;
-			double g0 = 0.0, g1 = 0.0;
+			if (writer) {
+				int cur = -1;
+				float g0 = 0.0f, g1 = 0.0f;
 #pragma unroll
-			for (int j = 0; j < 8; j++) {
-				const int ch = v * 8 + j;
-				if (ch >= g.c) break;
-				const int grp = ch / g.group_size;
-				if (grp != cur) {
-					if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
-					cur = grp; g0 = 0.0; g1 = 0.0;
+				for (int j = 0; j < 8; j++) {
+					const int ch = v * 8 + j;
+					if (ch >= g.c) break;
+					const int grp = ch / g.group_size;
+					if (grp != cur) {
+						if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
+						cur = grp; g0 = 0.0f; g1 = 0.0f;
+					}
+					g0 += s0[j];
+					g1 += s1[j];
 				}
-				g0 += (double)s0[j];
-				g1 += (double)s1[j];
+				if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
 			}
-			if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
 		}
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x)
-		atomicAdd(&ws[(size_t)b * g.nb_group * 2 + i], sm_acc[i]);
+		atomicAdd(&ws[(size_t)b * g.nb_group * 2 + i], (double)sm_acc[i]);
 }
 
 // mean = S1/n ; var = S2/n - mean^2  (biased variance, as upstream)
@@ -99,89 +142,120 @@ __global__ void norm_finalize_bwd_kernel(const double* __restrict__ ws, const fl
 	d_gamma[i] = (float)((sdx - (double)mean[i] * sd) / sqrt((double)var[i] + (double)g.eps));
 }
 
+// Apply kernels: same thread -> (channel vector, pixel lane) mapping as the statistics kernel, one sample per
+// blockIdx.y.  A thread keeps ONE channel vector, so the per-channel affine constants are computed once outside
+// the pixel loop and the loop body is: 128-bit load(s), 8 FMAs, 128-bit store - no integer division, several loads in flight.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NORM_THREADS)
 norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ mean, const float* __restrict__ var, NormGeom g) {
 	const int cv = g.cp >> 3;
-	const long long total = (long long)g.batch * g.hw * cv;
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		const int v = (int)(i % cv);
-		const long long pix = i / cv;
-		const int b = (int)(pix / g.hw);
-		float xv[8], out[8];
-		load8<T>(x + pix * g.cp + v * 8, xv);
-		if (b >= g.length) {
+	const int b = blockIdx.y;
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	if (lane_p >= lanes_p) return;
+	const int p0 = blockIdx.x * g.ppb;
+	int p1 = p0 + g.ppb;
+	if (p1 > g.hw) p1 = g.hw;
+	const bool dead = b >= g.length;
+	constexpr int U = 4;
+	for (int v = lane_c; v < cv; v += lanes_c) {
+		float sc[8], sh[8];
 #pragma unroll
-			for (int j = 0; j < 8; j++) out[j] = 0.0f;
-		} else {
-			int cur = -1;
-			float sc = 1.0f, sh = 0.0f;
-#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				const int ch = v * 8 + j;
-				if (ch >= g.c) { out[j] = 0.0f; continue; }
+		for (int j = 0; j < 8; j++) {
+			const int ch = v * 8 + j;
+			sc[j] = 0.0f; sh[j] = 0.0f;
+			if (ch < g.c && !dead) {
 				const int grp = ch / g.group_size;
-				if (grp != cur) {
-					cur = grp;
-					if (grp < g.nb_group - g.set_off) {
-						const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
-						sc = gamma[grp] * rstd;
-						sh = beta[grp] - mean[b * g.nb_group + grp] * sc;
-					} else { sc = 1.0f; sh = 0.0f; }
-				}
-				out[j] = xv[j] * sc + sh;
+				if (grp < g.nb_group - g.set_off) {
+					const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
+					sc[j] = gamma[grp] * rstd;
+					sh[j] = beta[grp] - mean[b * g.nb_group + grp] * sc[j];
+				} else sc[j] = 1.0f;
 			}
 		}
-		store8<T>(y + pix * g.cp + v * 8, out);
+		const long long base = (long long)b * g.hw * g.cp + v * 8;
+		for (int p = p0 + lane_p; p < p1; p += lanes_p * U) {
+			Raw8<T> raw[U];
+#pragma unroll
+			for (int u = 0; u < U; u++) { const int pp = p + u * lanes_p; if (pp < p1) raw[u] = load_raw8<T>(x + base + (long long)pp * g.cp); }
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const int pp = p + u * lanes_p;
+				if (pp >= p1) continue;
+				float xv[8], out[8];
+				unpack8(raw[u], xv);
+#pragma unroll
+				for (int j = 0; j < 8; j++) out[j] = xv[j] * sc[j] + sh[j];
+				store8<T>(y + base + (long long)pp * g.cp, out);
+			}
+		}
 	}
 }
 
 // dx = gamma*rstd/n * (n*d - d_beta - xhat*d_gamma), then the previous layer's deriv hook on x
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NORM_THREADS)
 norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
                       const float* __restrict__ mean, const float* __restrict__ var,
                       const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
                       cb200_activ prev_activ, NormGeom g) {
 	const int cv = g.cp >> 3;
-	const long long total = (long long)g.batch * g.hw * cv;
+	const int b = blockIdx.y;
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	if (lane_p >= lanes_p) return;
+	const int p0 = blockIdx.x * g.ppb;
+	int p1 = p0 + g.ppb;
+	if (p1 > g.hw) p1 = g.hw;
+	const bool dead = b >= g.length;
 	const float n = (float)(g.group_size * g.hw);
 	const float inv_n = 1.0f / n;
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		const int v = (int)(i % cv);
-		const long long pix = i / cv;
-		const int b = (int)(pix / g.hw);
-		float out[8];
-		if (b >= g.length) {
+	constexpr int U = 2;
+	for (int v = lane_c; v < cv; v += lanes_c) {
+		// per-channel constants of this thread's vector: mode 0 = zero, 1 = pass-through (set_off groups), 2 = normalised
+		float mu[8], rstd[8], k0[8], dg[8], db[8];
+		int mode[8];
 #pragma unroll
-			for (int j = 0; j < 8; j++) out[j] = 0.0f;
-		} else {
-			float xv[8], dv[8];
-			load8<T>(x + pix * g.cp + v * 8, xv);
-			load8<T>(dy + pix * g.cp + v * 8, dv);
-			int cur = -1;
-			bool active = false;
-			float mu = 0.0f, rstd = 0.0f, gm = 0.0f, dg = 0.0f, db = 0.0f;
-#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				const int ch = v * 8 + j;
-				if (ch >= g.c) { out[j] = 0.0f; continue; }
+		for (int j = 0; j < 8; j++) {
+			const int ch = v * 8 + j;
+			mode[j] = 0; mu[j] = 0.0f; rstd[j] = 0.0f; k0[j] = 0.0f; dg[j] = 0.0f; db[j] = 0.0f;
+			if (ch < g.c && !dead) {
 				const int grp = ch / g.group_size;
-				if (grp != cur) {
-					cur = grp;
-					active = grp < g.nb_group - g.set_off;
-					if (active) {
-						const int s = b * g.nb_group + grp;
-						mu = mean[s]; rstd = 1.0f / sqrtf(var[s] + g.eps); gm = gamma[grp]; dg = d_gamma[s]; db = d_beta[s];
-					}
-				}
-				float r = dv[j];
-				if (active) r = inv_n * gm * rstd * (n * dv[j] - db - (xv[j] - mu) * rstd * dg);
-				out[j] = activ_deriv_mul(prev_activ, r, xv[j]);
+				if (grp < g.nb_group - g.set_off) {
+					const int s = b * g.nb_group + grp;
+					mode[j] = 2; mu[j] = mean[s]; rstd[j] = 1.0f / sqrtf(var[s] + g.eps);
+					k0[j] = inv_n * gamma[grp] * rstd[j]; dg[j] = d_gamma[s]; db[j] = d_beta[s];
+				} else mode[j] = 1;
 			}
 		}
-		store8<T>(dx + pix * g.cp + v * 8, out);
+		const long long base = (long long)b * g.hw * g.cp + v * 8;
+		for (int p = p0 + lane_p; p < p1; p += lanes_p * U) {
+			Raw8<T> rx[U], rd[U];
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const int pp = p + u * lanes_p;
+				if (pp < p1) { rx[u] = load_raw8<T>(x + base + (long long)pp * g.cp); rd[u] = load_raw8<T>(dy + base + (long long)pp * g.cp); }
+			}
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const int pp = p + u * lanes_p;
+				if (pp >= p1) continue;
+				float xv[8], dv[8], out[8];
+				unpack8(rx[u], xv);
+				unpack8(rd[u], dv);
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					float r = 0.0f;
+					if (mode[j] == 2) r = k0[j] * (n * dv[j] - db[j] - (xv[j] - mu[j]) * rstd[j] * dg[j]);
+					else if (mode[j] == 1) r = dv[j];
+					out[j] = mode[j] == 0 ? 0.0f : activ_deriv_mul(prev_activ, r, xv[j]);
+				}
+				store8<T>(dx + base + (long long)pp * g.cp, out);
+			}
+		}
 	}
 }
 
@@ -216,6 +290,7 @@ static int fill_geom(const cb200_norm_desc* d, NormGeom& g) {
 	CB_ARG(d->nb_group * d->group_size >= d->c);
 	g.batch = d->batch; g.length = d->length; g.c = d->c; g.cp = round8(d->c); g.hw = d->h * d->w;
 	g.group_size = d->group_size; g.nb_group = d->nb_group; g.set_off = d->set_off; g.eps = d->eps;
+	g.ppb = norm_pix_per_block(g.hw, g.batch, g.cp >> 3);
 	return CB200_OK;
 }
 }  // namespace cb200
@@ -236,14 +311,13 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	// algorithmic bytes: read x (stats) + read x + write y = 3 passes over the real elements
 	prof_begin(PROF_NORM, 3.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
-	dim3 grid((unsigned)ceil_div(g.hw, NORM_PIX_PER_BLOCK), (unsigned)g.batch);
-	size_t smem = sizeof(double) * 2 * g.nb_group;
+	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
+	size_t smem = sizeof(float) * 2 * g.nb_group;
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, smem, st>>>((const T*)x, nullptr, ws, g)));
 	CB_LAUNCH_CHECK();
 	norm_finalize_fwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, g);
 	CB_LAUNCH_CHECK();
-	long long total = (long long)g.batch * g.hw * (g.cp >> 3);
-	CB_DISPATCH_DTYPE(d->dtype, T, (norm_apply_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, gamma, beta, mean, var, g)));
+	CB_DISPATCH_DTYPE(d->dtype, T, (norm_apply_kernel<T><<<grid, NORM_THREADS, 0, st>>>((const T*)x, (T*)y, gamma, beta, mean, var, g)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);
 	return CB200_OK;
@@ -263,14 +337,13 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	// algorithmic bytes: (dy, x) for the reductions + (dy, x) + write dx = 5 passes
 	prof_begin(PROF_NORM, 5.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
-	dim3 grid((unsigned)ceil_div(g.hw, NORM_PIX_PER_BLOCK), (unsigned)g.batch);
-	size_t smem = sizeof(double) * 2 * g.nb_group;
+	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
+	size_t smem = sizeof(float) * 2 * g.nb_group;
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, true><<<grid, NORM_THREADS, smem, st>>>((const T*)dy, (const T*)x, ws, g)));
 	CB_LAUNCH_CHECK();
 	norm_finalize_bwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, d_gamma, d_beta, g);
 	CB_LAUNCH_CHECK();
-	long long total = (long long)g.batch * g.hw * (g.cp >> 3);
-	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_apply_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_apply_kernel<T><<<grid, NORM_THREADS, 0, st>>>(
 		(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, g)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);

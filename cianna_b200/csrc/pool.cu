@@ -15,15 +15,15 @@ struct PoolGeom {
 template <typename T>
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ map, PoolGeom g) {
-	const int cv = g.cp >> 3;
-	const long long total = (long long)g.batch * g.out_h * g.out_w * cv;
+	// grid: (x: output columns x channel vectors, y: output row, z: sample) - 32-bit index math only
+	const unsigned cv = (unsigned)g.cp >> 3;
 	const bool mask_tail = activ_masks_tail(g.activ);
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		const int v = (int)(i % cv);
-		long long r = i / cv;
-		const int ox = (int)(r % g.out_w); r /= g.out_w;
-		const int oy = (int)(r % g.out_h);
-		const int b = (int)(r / g.out_h);
+	const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx < (unsigned)g.out_w * cv) {
+		const int v = (int)(idx % cv);
+		const int ox = (int)(idx / cv);
+		const int oy = blockIdx.y;
+		const int b = blockIdx.z;
 		float best[8];
 		int arg[8];
 		int count = 0;
@@ -83,17 +83,16 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ map, T* __restrict__ dx,
                 const T* __restrict__ prev_out, cb200_activ prev_activ, PoolGeom g) {
-	const int cv = g.cp >> 3;
-	const long long total = (long long)g.batch * g.in_h * g.in_w * cv;
+	const unsigned cv = (unsigned)g.cp >> 3;
 	const bool hook = prev_out != nullptr && prev_activ.type != CB200_LINEAR;
 	const bool mask_tail = hook && activ_masks_tail(prev_activ);
 	const float inv_vol = 1.0f / (float)(g.p_h * g.p_w);
-	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		const int v = (int)(i % cv);
-		long long r = i / cv;
-		const int ix = (int)(r % g.in_w); r /= g.in_w;
-		const int iy = (int)(r % g.in_h);
-		const int b = (int)(r / g.in_h);
+	const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx < (unsigned)g.in_w * cv) {
+		const int v = (int)(idx % cv);
+		const int ix = (int)(idx / cv);
+		const int iy = blockIdx.y;
+		const int b = blockIdx.z;
 		float acc[8];
 #pragma unroll
 		for (int j = 0; j < 8; j++) acc[j] = 0.0f;
@@ -133,6 +132,114 @@ pool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ map, T* __
 	}
 }
 
+// fast path of the backward pass for non-overlapping windows (stride == size, no padding: every pooling layer of the
+// BASELINE configs): an input pixel belongs to exactly one window, four pixels are kept in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_bwd_disjoint_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ map, T* __restrict__ dx,
+                         const T* __restrict__ prev_out, cb200_activ prev_activ, PoolGeom g) {
+	const unsigned cv = (unsigned)g.cp >> 3;
+	const bool hook = prev_out != nullptr && prev_activ.type != CB200_LINEAR;
+	const bool mask_tail = hook && activ_masks_tail(prev_activ);
+	const float inv_vol = 1.0f / (float)(g.p_h * g.p_w);
+	const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (unsigned)g.in_w * cv) return;
+	const int v = (int)(idx % cv);
+	const int ix = (int)(idx / cv);
+	const int iy = blockIdx.y, b = blockIdx.z;
+	const int oy = iy / g.p_h, ox = ix / g.p_w;
+	const int loc = (iy - oy * g.p_h) * g.p_w + (ix - ox * g.p_w);
+	const long long o_in = (((long long)b * g.in_h + iy) * g.in_w + ix) * g.cp + v * 8;
+	float acc[8];
+#pragma unroll
+	for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+	Raw8<T> rp;
+	if (hook) rp = load_raw8<T>(prev_out + o_in);
+	if (oy < g.out_h && ox < g.out_w) {
+		const long long o = (((long long)b * g.out_h + oy) * g.out_w + ox) * g.cp + v * 8;
+		const Raw8<T> rd = load_raw8<T>(dy + o);
+		float d[8];
+		if (g.type == CB200_POOL_MAX) {
+			const uint2 rm = __ldg(reinterpret_cast<const uint2*>(map + o));
+			unpack8(rd, d);
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const uint32_t m = ((j < 4 ? rm.x : rm.y) >> (8 * (j & 3))) & 0xffu;
+				if ((int)m == loc) acc[j] = d[j];
+			}
+		} else {
+			unpack8(rd, d);
+#pragma unroll
+			for (int j = 0; j < 8; j++) acc[j] = d[j] * inv_vol;
+		}
+	}
+	if (hook) {
+		float pv[8];
+		unpack8(rp, pv);
+		const bool dead = mask_tail && b >= g.length;
+#pragma unroll
+		for (int j = 0; j < 8; j++) acc[j] = dead ? 0.0f : activ_deriv_mul(prev_activ, acc[j], pv[j]);
+	}
+	store8<T>(dx + o_in, acc);
+}
+
+// global average pooling (window == whole map): one block per sample, threads = channel vectors x pixel lanes,
+// shared-memory reduction over the pixel lanes.  (Darknet19 head: 14x14x1000 -> 1000 per image.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_global_avg_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
+	extern __shared__ float red[];                 // [lanes_p][lanes_c * 8]
+	const int cv = g.cp >> 3, hw = g.in_h * g.in_w;
+	const int b = blockIdx.x;
+	const int lanes_c = cv < 256 ? cv : 256;
+	const int lanes_p = 256 / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	const bool mask_tail = activ_masks_tail(g.activ);
+	const bool dead = mask_tail && b >= g.length;
+	constexpr int U = 4;
+	for (int v0 = 0; v0 < cv; v0 += lanes_c) {
+		const int v = v0 + lane_c;
+		float acc[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+		if (lane_p < lanes_p && v < cv) {
+			const T* base = x + (long long)b * hw * g.cp + v * 8;
+			for (int p = lane_p; p < hw; p += lanes_p * U) {
+				Raw8<T> raw[U];
+#pragma unroll
+				for (int u = 0; u < U; u++) { const int pp = p + u * lanes_p; if (pp < hw) raw[u] = load_raw8<T>(base + (long long)pp * g.cp); }
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					if (p + u * lanes_p < hw) {
+						float t[8];
+						unpack8(raw[u], t);
+#pragma unroll
+						for (int j = 0; j < 8; j++) acc[j] += t[j];
+					}
+				}
+			}
+		}
+		if (lane_p < lanes_p) {
+#pragma unroll
+			for (int j = 0; j < 8; j++) red[(lane_p * lanes_c + lane_c) * 8 + j] = acc[j];
+		}
+		__syncthreads();
+		if (lane_p == 0 && v < cv) {
+			float out[8];
+			const float inv = 1.0f / (float)hw;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				float t = 0.0f;
+				for (int q = 0; q < lanes_p; q++) t += red[(q * lanes_c + lane_c) * 8 + j];
+				const bool real = (v * 8 + j) < g.c;
+				out[j] = (real && !dead) ? activ_forward(g.activ, t * inv) : 0.0f;
+			}
+			store8<T>(y + (long long)b * g.cp + v * 8, out);
+		}
+		__syncthreads();
+	}
+}
+
 static int fill_geom(const cb200_pool_desc* d, PoolGeom& g) {
 	CB_ARG(d != nullptr && d->batch > 0 && d->c > 0);
 	CB_ARG(d->p_h > 0 && d->p_w > 0 && d->stride_h > 0 && d->stride_w > 0);
@@ -152,11 +259,17 @@ int cb200_pool_forward(const cb200_pool_desc* d, const void* x, void* y, uint8_t
 	CB_REQUIRE_DEVICE();
 	PoolGeom g;
 	int rc = fill_geom(d, g); if (rc) return rc;
-	long long total = (long long)g.batch * g.out_h * g.out_w * (g.cp >> 3);
+	dim3 grid((unsigned)ceil_div(g.out_w * (g.cp >> 3), 256), (unsigned)g.out_h, (unsigned)g.batch);
 	const double es = (double)cb200_dtype_size(d->dtype);
 	// algorithmic bytes: read the input once, write output + 1-byte argmax
 	prof_begin(PROF_POOL, (double)g.batch * g.c * ((double)g.in_h * g.in_w * es + (double)g.out_h * g.out_w * (es + 1)), as_stream(s));
-	CB_DISPATCH_DTYPE(d->dtype, T, (pool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, (T*)y, map, g)));
+	const bool global_avg = g.type == CB200_POOL_AVG && g.out_h == 1 && g.out_w == 1 && g.p_h == g.in_h && g.p_w == g.in_w &&
+	                        g.pad_h == 0 && g.pad_w == 0 && g.in_h * g.in_w >= 16;
+	if (global_avg) {
+		CB_DISPATCH_DTYPE(d->dtype, T, (pool_global_avg_kernel<T><<<g.batch, 256, 256 * 8 * sizeof(float), as_stream(s)>>>((const T*)x, (T*)y, g)));
+	} else {
+		CB_DISPATCH_DTYPE(d->dtype, T, (pool_fwd_kernel<T><<<grid, 256, 0, as_stream(s)>>>((const T*)x, (T*)y, map, g)));
+	}
 	CB_LAUNCH_CHECK();
 	prof_end(as_stream(s));
 	return CB200_OK;
@@ -170,10 +283,15 @@ int cb200_pool_backward(const cb200_pool_desc* d, const void* dy, const uint8_t*
 	CB_ARG(d->pool_type != CB200_POOL_MAX || map != nullptr);
 	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
 	if (prev_activ) pa = *prev_activ;
-	long long total = (long long)g.batch * g.in_h * g.in_w * (g.cp >> 3);
+	dim3 grid((unsigned)ceil_div(g.in_w * (g.cp >> 3), 256), (unsigned)g.in_h, (unsigned)g.batch);
 	const double es = (double)cb200_dtype_size(d->dtype);
 	prof_begin(PROF_POOL, (double)g.batch * g.c * ((double)g.in_h * g.in_w * es + (double)g.out_h * g.out_w * (es + 1)), as_stream(s));
-	CB_DISPATCH_DTYPE(d->dtype, T, (pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)dy, map, (T*)dx, (const T*)prev_out, pa, g)));
+	const bool disjoint = g.s_h == g.p_h && g.s_w == g.p_w && g.pad_h == 0 && g.pad_w == 0;
+	if (disjoint) {
+		CB_DISPATCH_DTYPE(d->dtype, T, (pool_bwd_disjoint_kernel<T><<<grid, 256, 0, as_stream(s)>>>((const T*)dy, map, (T*)dx, (const T*)prev_out, pa, g)));
+	} else {
+		CB_DISPATCH_DTYPE(d->dtype, T, (pool_bwd_kernel<T><<<grid, 256, 0, as_stream(s)>>>((const T*)dy, map, (T*)dx, (const T*)prev_out, pa, g)));
+	}
 	CB_LAUNCH_CHECK();
 	prof_end(as_stream(s));
 	return CB200_OK;

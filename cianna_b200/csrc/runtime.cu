@@ -194,34 +194,41 @@ __global__ void import_input_kernel(T* __restrict__ dst, const T* __restrict__ s
 	}
 }
 // dataset rows -> first-layer patch rows (see cb200_import_input_patches in the header)
+// grid: (x: output columns x 8-column packets, y: output row, z: sample); the column -> (channel, ky, kx) decode
+// is a small table in shared memory so that the inner loop has no integer division
 template <typename T>
-__global__ void import_patches_kernel(T* __restrict__ dst, const T* __restrict__ src, int batch, int c, int h, int w,
-                                      int f_h, int f_w, int s_h, int s_w, int p_h, int p_w, int out_h, int out_w, int kp, float bias_value) {
+__global__ void __launch_bounds__(256)
+import_patches_kernel(T* __restrict__ dst, const T* __restrict__ src, int c, int h, int w,
+                      int f_h, int f_w, int s_h, int s_w, int p_h, int p_w, int out_h, int out_w, int kp, float bias_value) {
+	__shared__ int tab[256];      // kp <= 256: (channel plane offset / ky / kx) packed, -1 = bias, -2 = zero pad
 	const int taps = f_h * f_w, kreal = c * taps;
-	const int kv = kp >> 3;
-	const size_t total = (size_t)batch * out_h * out_w * kv;
-	const size_t row = (size_t)c * h * w + 1;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-		const int v = (int)(i % kv);
-		size_t r = i / kv;
-		const int ox = (int)(r % out_w); r /= out_w;
-		const int oy = (int)(r % out_h);
-		const size_t b = r / out_h;
-		float o[8];
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const int col = v * 8 + j;
-			float val = 0.0f;
-			if (col < kreal) {
-				const int ch = col / taps, tap = col - ch * taps;
-				const int ky = tap / f_w, kx = tap - ky * f_w;
-				const int iy = oy * s_h - p_h + ky, ix = ox * s_w - p_w + kx;
-				if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = to_f32<T>(src[b * row + ((size_t)ch * h + iy) * w + ix]);
-			} else if (col == kreal) val = bias_value;
-			o[j] = val;
-		}
-		store8<T>(dst + i * 8, o);
+	for (int col = threadIdx.x; col < kp; col += blockDim.x) {
+		int code = -2;
+		if (col < kreal) { const int ch = col / taps, tap = col - ch * taps; const int ky = tap / f_w, kx = tap - ky * f_w; code = (ch << 16) | (ky << 8) | kx; }
+		else if (col == kreal) code = -1;
+		tab[col] = code;
 	}
+	__syncthreads();
+	const unsigned kv = (unsigned)kp >> 3;
+	const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (unsigned)out_w * kv) return;
+	const int v = (int)(idx % kv), ox = (int)(idx / kv);
+	const int oy = blockIdx.y;
+	const size_t b = blockIdx.z;
+	const T* img = src + b * ((size_t)c * h * w + 1);
+	float o[8];
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int code = tab[v * 8 + j];
+		float val = 0.0f;
+		if (code >= 0) {
+			const int ch = code >> 16, ky = (code >> 8) & 0xff, kx = code & 0xff;
+			const int iy = oy * s_h - p_h + ky, ix = ox * s_w - p_w + kx;
+			if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = to_f32<T>(img[((size_t)ch * h + iy) * w + ix]);
+		} else if (code == -1) val = bias_value;
+		o[j] = val;
+	}
+	store8<T>(dst + (((b * out_h + oy) * out_w + ox) * (size_t)kp) + v * 8, o);
 }
 
 // reference activation layout [C][B][HW] (FP32) -> internal
@@ -324,9 +331,10 @@ int cb200_import_input_patches(void* dst, const void* src, int dtype, int batch,
                                int stride_h, int stride_w, int pad_h, int pad_w, int out_h, int out_w, float bias_value, void* s) {
 	CB_REQUIRE_DEVICE();
 	const int kp = cb200_patch_width(c, f_h, f_w);
-	long long total = (long long)batch * out_h * out_w * (kp >> 3);
-	CB_DISPATCH_DTYPE(dtype, T, (import_patches_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
-		(T*)dst, (const T*)src, batch, c, h, w, f_h, f_w, stride_h, stride_w, pad_h, pad_w, out_h, out_w, kp, bias_value)));
+	CB_ARG(kp <= 256 && f_h < 256 && f_w < 256);
+	dim3 grid((unsigned)ceil_div(out_w * (kp >> 3), 256), (unsigned)out_h, (unsigned)batch);
+	CB_DISPATCH_DTYPE(dtype, T, (import_patches_kernel<T><<<grid, 256, 0, as_stream(s)>>>(
+		(T*)dst, (const T*)src, c, h, w, f_h, f_w, stride_h, stride_w, pad_h, pad_w, out_h, out_w, kp, bias_value)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }
