@@ -213,22 +213,27 @@ norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __re
 	const bool dead = b >= g.length;
 	const float n = (float)(g.group_size * g.hw);
 	const float inv_n = 1.0f / n;
+	const int act = prev_activ.type;
+	const float leak = prev_activ.leak, sat = prev_activ.saturation, abeta = prev_activ.beta;
 	constexpr int U = 2;
 	for (int v = lane_c; v < cv; v += lanes_c) {
-		// per-channel constants of this thread's vector: mode 0 = zero, 1 = pass-through (set_off groups), 2 = normalised
-		float mu[8], rstd[8], k0[8], dg[8], db[8];
-		int mode[8];
+		// dx = k0*(n*d - d_beta - (x - mu)*rstd*d_gamma) rewritten per channel as ca*d + cx*x + cc (three constants);
+		// pass-through groups (set_off): ca = 1; dead samples / pad channels: all zero
+		float ca[8], cx[8], cc[8];
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
 			const int ch = v * 8 + j;
-			mode[j] = 0; mu[j] = 0.0f; rstd[j] = 0.0f; k0[j] = 0.0f; dg[j] = 0.0f; db[j] = 0.0f;
+			ca[j] = 0.0f; cx[j] = 0.0f; cc[j] = 0.0f;
 			if (ch < g.c && !dead) {
 				const int grp = ch / g.group_size;
 				if (grp < g.nb_group - g.set_off) {
 					const int s = b * g.nb_group + grp;
-					mode[j] = 2; mu[j] = mean[s]; rstd[j] = 1.0f / sqrtf(var[s] + g.eps);
-					k0[j] = inv_n * gamma[grp] * rstd[j]; dg[j] = d_gamma[s]; db[j] = d_beta[s];
-				} else mode[j] = 1;
+					const float rstd = 1.0f / sqrtf(var[s] + g.eps);
+					const float k0 = inv_n * gamma[grp] * rstd;
+					ca[j] = k0 * n;
+					cx[j] = -k0 * rstd * d_gamma[s];
+					cc[j] = k0 * (mean[s] * rstd * d_gamma[s] - d_beta[s]);
+				} else ca[j] = 1.0f;
 			}
 		}
 		const long long base = (long long)b * g.hw * g.cp + v * 8;
@@ -247,11 +252,13 @@ norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __re
 				unpack8(rx[u], xv);
 				unpack8(rd[u], dv);
 #pragma unroll
-				for (int j = 0; j < 8; j++) {
-					float r = 0.0f;
-					if (mode[j] == 2) r = k0[j] * (n * dv[j] - db[j] - (xv[j] - mu[j]) * rstd[j] * dg[j]);
-					else if (mode[j] == 1) r = dv[j];
-					out[j] = mode[j] == 0 ? 0.0f : activ_deriv_mul(prev_activ, r, xv[j]);
+				for (int j = 0; j < 8; j++) out[j] = fmaf(ca[j], dv[j], fmaf(cx[j], xv[j], cc[j]));
+				if (act == CB200_RELU) {
+#pragma unroll
+					for (int j = 0; j < 8; j++) out[j] = (xv[j] <= 0.0f || xv[j] > sat) ? out[j] * leak : out[j];
+				} else if (act == CB200_LOGISTIC) {
+#pragma unroll
+					for (int j = 0; j < 8; j++) out[j] = out[j] * abeta * xv[j] * (1.0f - xv[j]);
 				}
 				store8<T>(dx + base + (long long)pp * g.cp, out);
 			}
