@@ -121,7 +121,9 @@ struct IgemmCfg {
 	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
 	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
 	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias rows*/;
-	static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;                      // accumulator ring in TMEM (512 columns)
+	static constexpr int ACC_COLS = ACC_STAGES * BN;
+	static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
 	static constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);   // 128B / 64B / 32B swizzle
 	static constexpr uint32_t SBO = 8 * BK * 2;                                 // 8 rows of one swizzle atom
 };
@@ -137,8 +139,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
-	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
-	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 8);
 	const uint32_t bias_smem = bar_base + 256u;          // 2 x 256 floats, one row per accumulator stage
 	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -148,7 +150,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		prefetch_tensormap(&tmap_a);
 		prefetch_tensormap(&tmap_b);
 		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-		for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
 		fence_barrier_init();
 	}
 	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -204,17 +206,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 				}
 				mma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
-				if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
 			}
 		}
 	} else {
-		// ===================== epilogue warps (8: two per TMEM lane quadrant, alternating 32-column chunks) ==========
+		// ===================== epilogue warps: two groups of four (one warp per TMEM lane quadrant) =====================
+		// group g drains the accumulators of the CTA's tiles g, g+2, g+4, ... so two tiles are in their epilogue at any
+		// time while the MMA warp runs up to ACC_STAGES tiles ahead
 		const int ew = warp - 2;                         // 0..7
 		const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-		const int half = ew >> 2;                        // which of the two warps of the quadrant
-		const int etid = threadIdx.x - 64;               // 0..255
+		const int grp = ew >> 2;                         // epilogue group
+		const int gtid = (ew & 3) * 32 + lane;           // 0..127 inside the group
 		const int row = quad * 32 + lane;                // row of the 128-pixel tile
-		int acc = 0; uint32_t acc_phase = 0;
 		T* __restrict__ out = reinterpret_cast<T*>(p.out);
 		const T* __restrict__ prev = reinterpret_cast<const T*>(p.prev_out);
 		// everything the inner loop needs, in registers (the parameter block lives in constant memory)
@@ -224,8 +227,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
 		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 		const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
-		float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+		float* bs = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw))) + grp * 256;
+		int it = 0;
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+			if ((it & 1) != grp) continue;
+			const int acc = it % Cfg::ACC_STAGES;
+			const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
 			const int mt = tile % tiles_m, nt = tile / tiles_m;
 			const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
 			const int px = twi * tw + (row % tw);
@@ -234,17 +241,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 			const bool row_ok = px < PW && py < PH && pn < PN;
 			const size_t pix = ((size_t)pn * PH + py) * PW + px;
 			const bool dead = mask_tail && pn >= length;
-			// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory
-			float* bs = bias_s + acc * 256;
+			// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
+			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
 			if (mode == 0)
-				for (int c = etid; c < BN; c += 256) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
-			asm volatile("bar.sync 1, 256;" ::: "memory");
+				for (int c = gtid; c < BN; c += 128) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
+			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 
 			mbar_wait(tfull_bar(acc), acc_phase);
 			tc_fence_after();
 			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-			for (int c0 = half * 32; c0 < BN; c0 += 64) {
+			for (int c0 = 0; c0 < BN; c0 += 32) {
 				uint32_t r[32];
 				if (BN - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
 				else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
@@ -304,7 +311,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(tempty_bar(acc));
-			if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
 		}
 	}
 
