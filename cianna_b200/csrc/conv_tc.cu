@@ -413,69 +413,76 @@ int conv_dgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const v
 }
 
 // ================================================================ weight-gradient kernel
+// One CTA owns MF blocks of 128 output channels x up to TGMAX filter taps x BNC input channels: per 64-pixel K step it
+// fetches the dy slabs once and one shifted x tile per tap, and issues MF * taps accumulating MMAs into separate TMEM
+// column ranges.  Sharing dy across taps (and x across the MF output blocks) is what keeps the L2 -> SM traffic of the
+// early, HBM-bound layers near one pass over dy instead of one pass per tap.
 struct WgradParams {
 	int W, H, N;                 // OUTPUT pixel grid of the layer (dy) ; x is read at pixel + tap offset
 	int tw, th, tn;              // pixel rectangle of one K step (64 pixels)
 	int tiles_w, tiles_h, tiles_n, pix_tiles;
 	int f_h, f_w, off_h, off_w;
-	int f_tiles, c_tiles, splits, tiles_per_split;
+	int f_groups, c_tiles, tap_groups, tg;   // job grid; tg = taps per group (<= TGMAX)
+	int splits, tiles_per_split, stages;
 	int out_c, in_cp;
 	float* grad;                 // [out_c][taps][in_cp]
-	uint32_t idesc;
+	uint32_t idesc, tmem_cols;
 };
 
-// BNC input channels per CTA, fetched as slabs of SLAB_C channels (64 -> 128B swizzle, 32 -> 64B, 16 -> 32B)
 template <int BNC, int SLAB_C>
 struct WgradCfg {
 	static constexpr int KPIX = 64;                                 // pixels per pipeline stage
-	static constexpr int A_SLAB_BYTES = KPIX * 128;                 // dy: 2 slabs of [64 pix][64 ch]
-	static constexpr int A_BYTES = 2 * A_SLAB_BYTES;
+	static constexpr int A_SLAB_BYTES = KPIX * 128;                 // dy: slabs of [64 pix][64 ch]
+	static constexpr int A_BYTES = 2 * A_SLAB_BYTES;                // one block of 128 output channels
 	static constexpr int B_SLABS = BNC / SLAB_C;
 	static constexpr int B_ROW_BYTES = SLAB_C * 2;
 	static constexpr int B_SLAB_BYTES = KPIX * B_ROW_BYTES;
-	static constexpr int B_BYTES = B_SLABS * B_SLAB_BYTES;
+	static constexpr int B_BYTES = B_SLABS * B_SLAB_BYTES;          // one tap
 	static constexpr uint32_t B_LAYOUT = SLAB_C == 64 ? 2u : (SLAB_C == 32 ? 4u : 6u);
-	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
-	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-	static constexpr int TMEM_COLS = BNC <= 32 ? 32 : BNC <= 64 ? 64 : BNC <= 128 ? 128 : 256;
+	static constexpr int SMEM_DATA = 196 * 1024;
+	static constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256;
 };
 
-// grid.x = f_tiles * c_tiles * taps, grid.y = splits
-template <int BNC, int SLAB_C>
+// grid.x = f_groups * c_tiles * tap_groups, grid.y = splits
+template <int BNC, int SLAB_C, int MF, int TGMAX>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
 	using Cfg = WgradCfg<BNC, SLAB_C>;
+	constexpr int MAX_STAGES = 8;
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-	const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+	const uint32_t bar_base = smem_base + Cfg::SMEM_DATA;
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
-	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-	const uint32_t done_bar = bar_base + 8u * (2 * Cfg::STAGES);
-	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+	auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+	const uint32_t done_bar = bar_base + 8u * (2 * MAX_STAGES);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
 	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	const int taps = p.f_h * p.f_w;
+	int job = blockIdx.x;
+	const int tgi = job % p.tap_groups; job /= p.tap_groups;
+	const int ct = job % p.c_tiles;
+	const int fg = job / p.c_tiles;
+	const int tap0 = tgi * p.tg;
+	const int ntap = min(p.tg, taps - tap0);                          // taps of this CTA (>= 1)
+	const uint32_t stage_bytes = (uint32_t)(MF * Cfg::A_BYTES + p.tg * Cfg::B_BYTES);
+	const uint32_t tx_bytes = (uint32_t)(MF * Cfg::A_BYTES + ntap * Cfg::B_BYTES);
+	const int stages = p.stages;
 
 	if (threadIdx.x == 0) {
 		prefetch_tensormap(&tmap_dy);
 		prefetch_tensormap(&tmap_x);
-		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
 		mbar_init(done_bar, 1);
 		fence_barrier_init();
 	}
-	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot_ptr;
 
-	const int taps = p.f_h * p.f_w;
-	int job = blockIdx.x;
-	const int tap = job % taps; job /= taps;
-	const int ct = job % p.c_tiles;
-	const int ft = job / p.c_tiles;
-	const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
 	const int t_begin = blockIdx.y * p.tiles_per_split;
 	int t_end = t_begin + p.tiles_per_split;
 	if (t_end > p.pix_tiles) t_end = p.pix_tiles;
@@ -488,14 +495,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
 				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
 				mbar_wait(empty_bar(stage), phase ^ 1u);
-				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-				mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-				tma_load_4d(sa, &tmap_dy, full_bar(stage), ft * 128, w0, h0, n0);
-				tma_load_4d(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), ft * 128 + 64, w0, h0, n0);
+				const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + MF * Cfg::A_BYTES;
+				mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
 #pragma unroll
-				for (int sl = 0; sl < Cfg::B_SLABS; sl++)
-					tma_load_4d(sb + sl * Cfg::B_SLAB_BYTES, &tmap_x, full_bar(stage), ct * BNC + sl * SLAB_C, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
-				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+				for (int mf = 0; mf < MF; mf++) {
+					const int ch0 = (fg * MF + mf) * 128;
+					tma_load_4d(sa + mf * Cfg::A_BYTES, &tmap_dy, full_bar(stage), ch0, w0, h0, n0);
+					tma_load_4d(sa + mf * Cfg::A_BYTES + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), ch0 + 64, w0, h0, n0);
+				}
+				for (int ti = 0; ti < ntap; ti++) {
+					const int tap = tap0 + ti;
+					const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
+#pragma unroll
+					for (int sl = 0; sl < Cfg::B_SLABS; sl++)
+						tma_load_4d(sb + ti * Cfg::B_BYTES + sl * Cfg::B_SLAB_BYTES, &tmap_x, full_bar(stage),
+						            ct * BNC + sl * SLAB_C, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
+				}
+				if (++stage == stages) { stage = 0; phase ^= 1u; }
 			}
 		}
 	} else if (warp == 1) {
@@ -504,41 +520,60 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 			for (int k = 0; k < n_steps; k++) {
 				mbar_wait(full_bar(stage), phase);
 				tc_fence_after();
-				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+				const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + MF * Cfg::A_BYTES;
 #pragma unroll
-				for (int kk = 0; kk < Cfg::KPIX / 16; kk++) {
-					// MN-major: 8 pixel rows per K group -> SBO; channel slabs -> LBO; 16 pixel rows per MMA
-					const uint64_t da = make_smem_desc(sa + kk * 2048, Cfg::A_SLAB_BYTES, 1024, 2);
-					const uint64_t db = make_smem_desc(sb + kk * 16 * Cfg::B_ROW_BYTES, Cfg::B_SLAB_BYTES, 8 * Cfg::B_ROW_BYTES, Cfg::B_LAYOUT);
-					mma_f16_ss(tmem_base, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
+				for (int mf = 0; mf < MF; mf++) {
+					for (int ti = 0; ti < ntap; ti++) {
+						const uint32_t d_tmem = tmem_base + (uint32_t)((mf * p.tg + ti) * BNC);
+#pragma unroll
+						for (int kk = 0; kk < Cfg::KPIX / 16; kk++) {
+							// MN-major: 8 pixel rows per K group -> SBO; channel slabs -> LBO; 16 pixel rows per MMA
+							const uint64_t da = make_smem_desc(sa + mf * Cfg::A_BYTES + kk * 2048, Cfg::A_SLAB_BYTES, 1024, 2);
+							const uint64_t db = make_smem_desc(sb + ti * Cfg::B_BYTES + kk * 16 * Cfg::B_ROW_BYTES, Cfg::B_SLAB_BYTES,
+							                                   8 * Cfg::B_ROW_BYTES, Cfg::B_LAYOUT);
+							mma_f16_ss(d_tmem, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
+						}
+					}
 				}
 				mma_commit(empty_bar(stage));
-				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+				if (++stage == stages) { stage = 0; phase ^= 1u; }
 			}
 			mma_commit(done_bar);
 		}
 	} else if (n_steps > 0) {
 		const int quad = warp & 3;
-		const int f = ft * 128 + quad * 32 + lane;
 		mbar_wait(done_bar, 0);
 		tc_fence_after();
-		const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+		for (int mf = 0; mf < MF; mf++) {
+			const int f = (fg * MF + mf) * 128 + quad * 32 + lane;
+			for (int ti = 0; ti < ntap; ti++) {
+				const int tap = tap0 + ti;
+				const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((mf * p.tg + ti) * BNC);
 #pragma unroll 1
-		for (int c0 = 0; c0 < BNC; c0 += 32) {
-			uint32_t r[32];
-			tmem_ld_32x32(t_row + c0, r);
-			tmem_ld_wait();
-			if (f < p.out_c) {
-				float* dst = p.grad + ((size_t)f * taps + tap) * p.in_cp + ct * BNC + c0;
+				for (int c0 = 0; c0 < BNC; c0 += 32) {
+					uint32_t r[32];
+					if (BNC - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
+					else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
 #pragma unroll
-				for (int j = 0; j < 32; j++)
-					if (ct * BNC + c0 + j < p.in_cp) atomicAdd(dst + j, __uint_as_float(r[j]));
+						for (int j = 0; j < 16; j++) { r[j] = h[j]; r[16 + j] = 0; } }
+					tmem_ld_wait();
+					if (f < p.out_c) {
+						float* dst = p.grad + ((size_t)f * taps + tap) * p.in_cp + ct * BNC + c0;
+#pragma unroll
+						for (int j = 0; j < 32; j += 4) {
+							if (c0 + j < BNC && ct * BNC + c0 + j < p.in_cp)      // in_cp is a multiple of 8: whole quads are in or out
+								asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+								             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+						}
+					}
+					__syncwarp();
+				}
 			}
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 bool conv_tc_wgrad_supported(const cb200_conv_desc* d) {
@@ -548,11 +583,11 @@ bool conv_tc_wgrad_supported(const cb200_conv_desc* d) {
 	return out_cp >= 16 && (in_cp >= 64 || in_cp == 32 || in_cp == 16);
 }
 
-template <int BNC, int SLAB_C>
+template <int BNC, int SLAB_C, int MF, int TGMAX>
 static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& p, dim3 grid, cudaStream_t st) {
 	using Cfg = WgradCfg<BNC, SLAB_C>;
 	static bool configured = false;
-	auto kern = conv_wgrad_kernel<BNC, SLAB_C>;
+	auto kern = conv_wgrad_kernel<BNC, SLAB_C, MF, TGMAX>;
 	if (!configured) {
 		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
 			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
@@ -566,8 +601,17 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
 
 int conv_wgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
+	const int taps = d->f_h * d->f_w;
 	const int slab_c = in_cp >= 64 ? 64 : in_cp;
 	const int bnc = in_cp < 64 ? in_cp : (in_cp > 128 ? 256 : (in_cp > 64 ? 128 : 64));
+	// blocks of 128 output channels per CTA and taps per CTA, bounded by the 512 TMEM columns
+	const int mf = (out_cp > 128 && bnc >= 128) ? 2 : 1;
+	int tg_cap = 512 / (mf * bnc);
+	if (bnc == 256 && mf == 1) tg_cap = 2;
+	if (bnc == 128 && mf == 1) tg_cap = 3;
+	if (bnc == 64) tg_cap = 5;
+	if (bnc <= 32) tg_cap = 9;
+	const int tg = taps < tg_cap ? taps : tg_cap;
 	WgradParams p;
 	memset(&p, 0, sizeof(p));
 	choose_rect(d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn);
@@ -580,8 +624,14 @@ int conv_wgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const v
 	p.tiles_w = ceil_div(p.W, p.tw); p.tiles_h = ceil_div(p.H, p.th); p.tiles_n = ceil_div(p.N, p.tn);
 	p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 	p.f_h = d->f_h; p.f_w = d->f_w; p.off_h = -d->pad_h; p.off_w = -d->pad_w;
-	p.f_tiles = ceil_div(out_cp, 128); p.c_tiles = ceil_div(in_cp, bnc);
-	const int jobs = p.f_tiles * p.c_tiles * d->f_h * d->f_w;
+	p.f_groups = ceil_div(out_cp, 128 * mf); p.c_tiles = ceil_div(in_cp, bnc);
+	p.tg = tg; p.tap_groups = ceil_div(taps, tg);
+	const int stage_bytes = mf * 16384 + tg * 64 * bnc * 2;
+	p.stages = (196 * 1024) / stage_bytes;
+	if (p.stages > 8) p.stages = 8;
+	const int acc_cols = mf * tg * bnc;
+	p.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+	const int jobs = p.f_groups * p.c_tiles * p.tap_groups;
 	int splits = ceil_div(g_num_sms * 2, jobs);
 	const int max_splits = ceil_div(p.pix_tiles, 8);
 	if (splits > max_splits) splits = max_splits;
@@ -592,15 +642,18 @@ int conv_wgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const v
 	p.out_c = d->out_c; p.in_cp = in_cp;
 	p.grad = w->grad;
 	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, bnc, 1, 1);
-	if (cudaMemsetAsync(w->grad, 0, sizeof(float) * (size_t)d->out_c * d->f_h * d->f_w * in_cp, st) != cudaSuccess) {
+	if (p.stages < 2 || acc_cols > 512) { set_error("conv_wgrad_tc: bad tiling (stages %d, tmem %d)", p.stages, acc_cols); return CB200_ERR_UNSUPPORTED; }
+	if (cudaMemsetAsync(w->grad, 0, sizeof(float) * (size_t)d->out_c * taps * in_cp, st) != cudaSuccess) {
 		set_error("wgrad memset failed"); return CB200_ERR_CUDA;
 	}
 	dim3 grid((unsigned)jobs, (unsigned)splits);
-	if (bnc == 256) return launch_wgrad<256, 64>(mdy, mx, p, grid, st);
-	if (bnc == 128) return launch_wgrad<128, 64>(mdy, mx, p, grid, st);
-	if (bnc == 64) return launch_wgrad<64, 64>(mdy, mx, p, grid, st);
-	if (bnc == 32) return launch_wgrad<32, 32>(mdy, mx, p, grid, st);
-	return launch_wgrad<16, 16>(mdy, mx, p, grid, st);
+	if (bnc == 256 && mf == 2) return launch_wgrad<256, 64, 2, 1>(mdy, mx, p, grid, st);
+	if (bnc == 256) return launch_wgrad<256, 64, 1, 2>(mdy, mx, p, grid, st);
+	if (bnc == 128 && mf == 2) return launch_wgrad<128, 64, 2, 2>(mdy, mx, p, grid, st);
+	if (bnc == 128) return launch_wgrad<128, 64, 1, 3>(mdy, mx, p, grid, st);
+	if (bnc == 64) return launch_wgrad<64, 64, 1, 5>(mdy, mx, p, grid, st);
+	if (bnc == 32) return launch_wgrad<32, 32, 1, 9>(mdy, mx, p, grid, st);
+	return launch_wgrad<16, 16, 1, 9>(mdy, mx, p, grid, st);
 }
 
 }  // namespace cb200
