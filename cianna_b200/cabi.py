@@ -212,7 +212,7 @@ def _ensure_pool_norm_sigs():
     L.cb200_pool_backward.argtypes = [ctypes.c_void_p] * 7
     L.cb200_export_pool_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
     L.cb200_norm_forward.argtypes = [ctypes.c_void_p] * 9
-    L.cb200_norm_backward.argtypes = [ctypes.c_void_p] * 12
+    L.cb200_norm_backward.argtypes = [ctypes.c_void_p] * 13
     L._pn_ready = True
     return L
 
@@ -262,6 +262,7 @@ class NormLayer:
         self.mean, self.var = DevBuf(batch * nb_group * 4), DevBuf(batch * nb_group * 4)
         self.d_gamma, self.d_beta = DevBuf(batch * nb_group * 4), DevBuf(batch * nb_group * 4)
         self.ws = DevBuf(L.cb200_norm_workspace_bytes(ctypes.byref(self.d)))
+        self.colsum = DevBuf(c * 4)
         self.nb_group = nb_group
 
     def set_params(self, gamma, beta):
@@ -277,7 +278,7 @@ class NormLayer:
     def backward(self, x_buf, dy_buf, prev_act=None):
         pa = ctypes.byref(prev_act) if prev_act is not None else None
         check(lib().cb200_norm_backward(ctypes.byref(self.d), x_buf.ptr, dy_buf.ptr, self.dx.ptr, self.gamma.ptr, self.mean.ptr,
-                                        self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa, self.ws.ptr, None))
+                                        self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa, self.colsum.ptr, self.ws.ptr, None))
         return self.dx
 
     def stats(self):

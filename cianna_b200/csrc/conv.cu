@@ -191,13 +191,18 @@ int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights*
 }
 
 int cb200_conv_backward_weights(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, const void* dy, void* s) {
+	return cb200_conv_backward_weights_ex(d_in, w, x, dy, 0, s);
+}
+
+int cb200_conv_backward_weights_ex(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, const void* dy,
+                                   int have_grad_b, void* s) {
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d_in); if (rc) return rc;
 	const cb200_conv_desc eff = effective_desc(d_in);
 	const cb200_conv_desc* d = &eff;
 	cudaStream_t st = as_stream(s);
 	long long P = (long long)d->batch * d->out_h * d->out_w;
-	if (!d_in->input_is_patches) {      // (patch rows carry the bias input as a column: its gradient comes out of the GEMM)
+	if (!d_in->input_is_patches && !have_grad_b) {      // (patch rows carry the bias input as a column: its gradient comes out of the GEMM)
 		rc = conv_colsum(d->dtype, dy, w->grad_b, P, d->out_c, st);
 		if (rc) return rc;
 	}

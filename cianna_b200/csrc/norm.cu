@@ -200,13 +200,18 @@ __global__ void __launch_bounds__(NORM_THREADS)
 norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
                       const float* __restrict__ mean, const float* __restrict__ var,
                       const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                      cb200_activ prev_activ, NormGeom g) {
+                      cb200_activ prev_activ, float* __restrict__ colsum, NormGeom g) {
+	extern __shared__ float cs_acc[];          // [cp] per-block column sums of dx (only when colsum != nullptr)
 	const int cv = g.cp >> 3;
 	const int b = blockIdx.y;
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
-	if (lane_p >= lanes_p) return;
+	if (colsum != nullptr) {
+		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
+		__syncthreads();
+	}
+	const bool active_thread = lane_p < lanes_p;
 	const int p0 = blockIdx.x * g.ppb;
 	int p1 = p0 + g.ppb;
 	if (p1 > g.hw) p1 = g.hw;
@@ -237,7 +242,10 @@ norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __re
 			}
 		}
 		const long long base = (long long)b * g.hw * g.cp + v * 8;
-		for (int p = p0 + lane_p; p < p1; p += lanes_p * U) {
+		float csum[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) csum[j] = 0.0f;
+		for (int p = p0 + lane_p; active_thread && p < p1; p += lanes_p * U) {
 			Raw8<T> rx[U], rd[U];
 #pragma unroll
 			for (int u = 0; u < U; u++) {
@@ -261,8 +269,28 @@ norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __re
 					for (int j = 0; j < 8; j++) out[j] = out[j] * abeta * xv[j] * (1.0f - xv[j]);
 				}
 				store8<T>(dx + base + (long long)pp * g.cp, out);
+#pragma unroll
+				for (int j = 0; j < 8; j++) csum[j] += out[j];
 			}
 		}
+		if (colsum != nullptr) {
+			// column sums of the delta just produced = raw bias-column gradient of the preceding convolution
+			bool writer = active_thread;
+			if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+					for (int off = lanes_c; off < 32; off <<= 1) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], off);
+				writer = (threadIdx.x & 31) < lanes_c;
+			}
+			if (writer) {
+#pragma unroll
+				for (int j = 0; j < 8; j++) atomicAdd(&cs_acc[v * 8 + j], csum[j]);
+			}
+		}
+	}
+	if (colsum != nullptr) {
+		__syncthreads();
+		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
 	}
 }
 
@@ -332,7 +360,7 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 
 int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy, void* dx, const float* gamma,
                         const float* mean, const float* var, float* d_gamma, float* d_beta,
-                        const cb200_activ* prev_activ, void* workspace, void* s) {
+                        const cb200_activ* prev_activ, float* dx_colsum, void* workspace, void* s) {
 	CB_REQUIRE_DEVICE();
 	NormGeom g;
 	int rc = fill_geom(d, g); if (rc) return rc;
@@ -350,8 +378,9 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	CB_LAUNCH_CHECK();
 	norm_finalize_bwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, d_gamma, d_beta, g);
 	CB_LAUNCH_CHECK();
-	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_apply_kernel<T><<<grid, NORM_THREADS, 0, st>>>(
-		(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, g)));
+	if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
+	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_apply_kernel<T><<<grid, NORM_THREADS, dx_colsum ? sizeof(float) * g.cp : 0, st>>>(
+		(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, g)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);
 	return CB200_OK;

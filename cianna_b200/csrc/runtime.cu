@@ -194,28 +194,42 @@ __global__ void import_input_kernel(T* __restrict__ dst, const T* __restrict__ s
 	}
 }
 // dataset rows -> first-layer patch rows (see cb200_import_input_patches in the header)
-// grid: (x: output columns x 8-column packets, y: output row, z: sample); the column -> (channel, ky, kx) decode
-// is a small table in shared memory so that the inner loop has no integer division
+// grid: (x: tiles of output columns, y: output row, z: sample).  A block first stages the f_h input row segments of
+// every channel that its output columns need in shared memory (coalesced reads of the planar dataset row), then each
+// thread assembles one 8-column packet of a patch row from shared memory; the column -> (channel, ky, kx) decode is a
+// small table, so there is no integer division and no scattered global load in the inner loop.
 template <typename T>
 __global__ void __launch_bounds__(256)
 import_patches_kernel(T* __restrict__ dst, const T* __restrict__ src, int c, int h, int w,
-                      int f_h, int f_w, int s_h, int s_w, int p_h, int p_w, int out_h, int out_w, int kp, float bias_value) {
-	__shared__ int tab[256];      // kp <= 256: (channel plane offset / ky / kx) packed, -1 = bias, -2 = zero pad
+                      int f_h, int f_w, int s_h, int s_w, int p_h, int p_w, int out_h, int out_w, int kp, float bias_value,
+                      int tile_x, int seg_w) {
+	extern __shared__ unsigned char smem_u8[];
+	int* tab = reinterpret_cast<int*>(smem_u8);                 // [kp]: (channel << 16 | ky << 8 | kx), -1 = bias, -2 = zero pad
+	T* seg = reinterpret_cast<T*>(smem_u8 + 1024);              // [c][f_h][seg_w]
 	const int taps = f_h * f_w, kreal = c * taps;
+	const int oy = blockIdx.y;
+	const size_t b = blockIdx.z;
+	const int ox0 = blockIdx.x * tile_x;
+	const int ix0 = ox0 * s_w - p_w;                            // first input column of the segment
 	for (int col = threadIdx.x; col < kp; col += blockDim.x) {
 		int code = -2;
 		if (col < kreal) { const int ch = col / taps, tap = col - ch * taps; const int ky = tap / f_w, kx = tap - ky * f_w; code = (ch << 16) | (ky << 8) | kx; }
 		else if (col == kreal) code = -1;
 		tab[col] = code;
 	}
-	__syncthreads();
-	const unsigned kv = (unsigned)kp >> 3;
-	const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= (unsigned)out_w * kv) return;
-	const int v = (int)(idx % kv), ox = (int)(idx / kv);
-	const int oy = blockIdx.y;
-	const size_t b = blockIdx.z;
 	const T* img = src + b * ((size_t)c * h * w + 1);
+	const int rows = c * f_h;
+	for (int i = threadIdx.x; i < rows * seg_w; i += blockDim.x) {
+		const int r = i / seg_w, xx = i - r * seg_w;
+		const int ch = r / f_h, ky = r - ch * f_h;
+		const int iy = oy * s_h - p_h + ky, ix = ix0 + xx;
+		seg[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? img[((size_t)ch * h + iy) * w + ix] : from_f32<T>(0.0f);
+	}
+	__syncthreads();
+	const int kv = kp >> 3;
+	const int v = threadIdx.x % kv, lx = threadIdx.x / kv;
+	const int ox = ox0 + lx;
+	if (lx >= tile_x || ox >= out_w) return;
 	float o[8];
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
@@ -223,8 +237,7 @@ import_patches_kernel(T* __restrict__ dst, const T* __restrict__ src, int c, int
 		float val = 0.0f;
 		if (code >= 0) {
 			const int ch = code >> 16, ky = (code >> 8) & 0xff, kx = code & 0xff;
-			const int iy = oy * s_h - p_h + ky, ix = ox * s_w - p_w + kx;
-			if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = to_f32<T>(img[((size_t)ch * h + iy) * w + ix]);
+			val = to_f32<T>(seg[(ch * f_h + ky) * seg_w + lx * s_w + kx]);
 		} else if (code == -1) val = bias_value;
 		o[j] = val;
 	}
@@ -332,9 +345,13 @@ int cb200_import_input_patches(void* dst, const void* src, int dtype, int batch,
 	CB_REQUIRE_DEVICE();
 	const int kp = cb200_patch_width(c, f_h, f_w);
 	CB_ARG(kp <= 256 && f_h < 256 && f_w < 256);
-	dim3 grid((unsigned)ceil_div(out_w * (kp >> 3), 256), (unsigned)out_h, (unsigned)batch);
-	CB_DISPATCH_DTYPE(dtype, T, (import_patches_kernel<T><<<grid, 256, 0, as_stream(s)>>>(
-		(T*)dst, (const T*)src, c, h, w, f_h, f_w, stride_h, stride_w, pad_h, pad_w, out_h, out_w, kp, bias_value)));
+	const int tile_x = 256 / (kp >> 3);
+	const int seg_w = (tile_x - 1) * stride_w + f_w;
+	const size_t smem = 1024 + (size_t)c * f_h * seg_w * cb200_dtype_size(dtype);
+	CB_ARG(smem <= 48 * 1024);
+	dim3 grid((unsigned)ceil_div(out_w, tile_x), (unsigned)out_h, (unsigned)batch);
+	CB_DISPATCH_DTYPE(dtype, T, (import_patches_kernel<T><<<grid, 256, smem, as_stream(s)>>>(
+		(T*)dst, (const T*)src, c, h, w, f_h, f_w, stride_h, stride_w, pad_h, pad_w, out_h, out_w, kp, bias_value, tile_x, seg_w)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }

@@ -78,6 +78,7 @@ typedef struct conv_param {
 	int flat_f_size;
 	cb200_conv_desc desc;
 	cb200_conv_weights w;
+	int bias_grad_from_next;   /* the following norm layer's backward pass also produces this layer's grad_b */
 	size_t grad_offset;    /* position of [grad | grad_b] in the network's gradient arena */
 	size_t grad_len;
 } conv_param;
@@ -153,6 +154,11 @@ struct network {
 	double last_epoch_loss;
 	float last_items_per_s;
 	void *out_host;        /* pinned staging of the last layer's output (inference read-back) */
+	/* double-buffered host->device staging of dynamic_load batches on a copy stream (overlaps the previous step) */
+	void *copy_stream;
+	void *stage_in[2], *stage_tg[2];
+	const void *staged_src[2];   /* host batch currently (being) copied into each slot */
+	int stage_slot;
 	const cb200_conv_desc *patch_desc;   /* first conv layer when it consumes patch rows (few input channels), else NULL */
 };
 

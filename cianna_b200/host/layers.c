@@ -78,7 +78,7 @@ static void backward_conv_layer(layer *current)
 		CB_CHECK(cb200_conv_backward_data(&p->desc, &p->w, current->delta_o, current->previous->delta_o,
 			&current->previous->activ, current->previous->output, NULL));
 	if (!current->frozen) {
-		CB_CHECK(cb200_conv_backward_weights(&p->desc, &p->w, layer_input(current), current->delta_o, NULL));
+		CB_CHECK(cb200_conv_backward_weights_ex(&p->desc, &p->w, layer_input(current), current->delta_o, p->bias_grad_from_next, NULL));
 		if (net->dp_world > 1) CB_CHECK(cb200_dp_allreduce(p->w.grad, p->grad_len, NULL));
 	}
 }
@@ -422,8 +422,17 @@ static void backward_norm_layer(layer *current)
 	network *net = current->c_network;
 	norm_param *p = (norm_param *)current->param;
 	p->desc.length = net->length;
-	CB_CHECK(cb200_norm_backward(&p->desc, current->previous->output, current->delta_o, current->previous->delta_o,
-		p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &current->previous->activ, p->workspace, NULL));
+	{
+		/* the delta written for a preceding convolution is also column-summed: that is its bias-column gradient */
+		layer *prev = current->previous;
+		float *colsum = NULL;
+		if (prev->type == CONV && !prev->frozen) {
+			conv_param *cp = (conv_param *)prev->param;
+			if (cp->bias_grad_from_next) colsum = cp->w.grad_b;
+		}
+		CB_CHECK(cb200_norm_backward(&p->desc, prev->output, current->delta_o, prev->delta_o,
+			p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, NULL));
+	}
 	if (!current->frozen)
 		CB_CHECK(cb200_norm_reduce_grads(&p->desc, p->d_gamma, p->d_beta, p->gsum, NULL));
 }
@@ -444,6 +453,8 @@ int norm_create(network *net, layer *previous, const char *norm_type, const char
 	if (previous->type == NORM || previous->type == LRN) { printf("\nERROR: stacking two normalization layers is not allowed.\n"); exit(EXIT_FAILURE); }
 
 	p = (norm_param *)calloc(1, sizeof(norm_param));
+	if (previous->type == CONV && !((conv_param *)previous->param)->desc.input_is_patches)
+		((conv_param *)previous->param)->bias_grad_from_next = 1;
 	p->group_size = group_size; p->set_off = set_off;
 	p->n_dim = previous->out_c; p->dim_offset = previous->out_h * previous->out_w;
 	p->nb_group = p->n_dim % group_size == 0 ? p->n_dim / group_size : p->n_dim / group_size + 1;

@@ -370,20 +370,69 @@ void cb_dp_init(network *net, const void *id128, int rank, int world)
 }
 
 /* ------------------------------------------------------------------ training loop */
+/* ---- dynamic_load staging: batch j+1 travels host -> device on a copy stream while step j computes.
+ * Replaces the blocking cudaMemcpy per batch of upstream (src/auxil.c:1811-1819). */
+static void stage_init(network *net)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	int s;
+	if (net->copy_stream != NULL) return;
+	CB_CHECK(cb200_stream_create(&net->copy_stream));
+	for (s = 0; s < 2; s++) {
+		CB_CHECK(cb200_malloc(&net->stage_in[s], (size_t)net->batch_size * (net->input_dim + 1) * es));
+		CB_CHECK(cb200_malloc(&net->stage_tg[s], (size_t)net->batch_size * (net->output_dim > 0 ? net->output_dim : 1) * es));
+		net->staged_src[s] = NULL;
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+}
+
+static void stage_issue(network *net, int slot, const void *in_host, const void *tg_host)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	CB_CHECK(cb200_h2d(net->stage_in[slot], in_host, (size_t)net->batch_size * (net->input_dim + 1) * es, net->copy_stream));
+	if (tg_host != NULL && net->output_dim > 0)
+		CB_CHECK(cb200_h2d(net->stage_tg[slot], tg_host, (size_t)net->batch_size * net->output_dim * es, net->copy_stream));
+	net->staged_src[slot] = in_host;
+}
+
+static void stage_invalidate(network *net) { net->staged_src[0] = NULL; net->staged_src[1] = NULL; }
+
+/* returns the slot holding batch (in_host, tg_host), copying it now if it was not prefetched, then starts the copy of
+ * the next batch into the other slot; on return the compute stream is ordered after the current batch's copy */
+static int stage_acquire(network *net, const void *in_host, const void *tg_host, const void *next_in, const void *next_tg)
+{
+	int slot;
+	stage_init(net);
+	slot = net->stage_slot;
+	if (net->staged_src[slot] != in_host) {
+		/* not prefetched (first step, or the caller jumped): the slot may still be read by earlier compute work */
+		CB_CHECK(cb200_stream_wait(net->copy_stream, NULL));
+		stage_issue(net, slot, in_host, tg_host);
+	}
+	CB_CHECK(cb200_stream_wait(NULL, net->copy_stream));        /* compute waits for this batch */
+	if (next_in != NULL) {
+		CB_CHECK(cb200_stream_wait(net->copy_stream, NULL));    /* the other slot's last reader (previous step) is queued */
+		stage_issue(net, slot ^ 1, next_in, next_tg);
+	}
+	net->stage_slot = slot ^ 1;
+	return slot;
+}
+
 /* One mini-batch of the training loop (body of upstream's batch loop, src/auxil.c:1797-1917): host->device copy of
  * the batch when it is not device-resident, layout import, forward sweep, loss monitor (per-sample sums, async
  * device->host), backward sweep, gradient exchange and optimizer.  Everything is enqueued; the caller decides
  * when to synchronise. */
-static void train_one_batch(network *net, Dataset *data, int j, int resident)
+static void train_one_batch(network *net, Dataset *data, int j, int resident, int j_next)
 {
 	int k;
 	const void *tgt;
 	net->is_inference = 0;
 	net->length = (j == data->nb_batch - 1 && data->size % net->batch_size > 0) ? data->size % net->batch_size : net->batch_size;
 	if (!resident) {
-		cb_load_batch_typed(net, data->input[j], data->target[j]);
-		use_device_batch(net, net->input_raw);
-		tgt = net->target;
+		int slot = stage_acquire(net, data->input[j], data->target[j],
+			j_next >= 0 ? data->input[j_next] : NULL, j_next >= 0 ? data->target[j_next] : NULL);
+		use_device_batch(net, net->stage_in[slot]);
+		tgt = net->stage_tg[slot];
 	} else {
 		use_device_batch(net, data->input_device[j]);
 		tgt = data->target_device[j];
@@ -403,9 +452,10 @@ void cb_train_steps(network *net, int nsteps, float lr, float momentum, float we
 	if (net->train.input == NULL) { printf("\nERROR: no TRAIN dataset defined\n"); exit(EXIT_FAILURE); }
 	prepare_training(net);
 	if (resident) dataset_upload(net, &net->train);
+	stage_invalidate(net);      /* host batches may have been rewritten since the last call */
 	set_hyper(net, lr, momentum, weight_decay);
 	for (s = 0; s < nsteps; s++) {
-		train_one_batch(net, &net->train, s % net->train.nb_batch, resident);
+		train_one_batch(net, &net->train, s % net->train.nb_batch, resident, s + 1 < nsteps ? (s + 1) % net->train.nb_batch : -1);
 		if (sync_each_step) CB_CHECK(cb200_stream_sync(NULL));
 	}
 }
@@ -417,12 +467,15 @@ void cb_forward_steps(network *net, int nsteps, int resident, int sync_each_step
 	Dataset *data = &net->test;
 	if (data->input == NULL) { printf("\nERROR: no TEST dataset defined\n"); exit(EXIT_FAILURE); }
 	if (resident) dataset_upload(net, data);
+	stage_invalidate(net);
 	net->is_inference = 1;
 	net->length = net->batch_size;
 	for (s = 0; s < nsteps; s++) {
 		int j = s % data->nb_batch;
-		if (!resident) { cb_load_batch_typed(net, data->input[j], NULL); use_device_batch(net, net->input_raw); }
-		else use_device_batch(net, data->input_device[j]);
+		if (!resident) {
+			int slot = stage_acquire(net, data->input[j], NULL, s + 1 < nsteps ? data->input[(s + 1) % data->nb_batch] : NULL, NULL);
+			use_device_batch(net, net->stage_in[slot]);
+		} else use_device_batch(net, data->input_device[j]);
 		for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
 		if (!resident) {
 			/* device->host read of the step's result: the class scores of the batch */
@@ -476,10 +529,11 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		if (shuffle_every > 0 && (net->iter + 1) % shuffle_every == 0 && net->batch_param != SGD && silent < 1)
 			printf(" (note) dataset shuffling is left to the caller in this build\n");
 		set_hyper(net, lr, net->momentum, net->weight_decay);
+		stage_invalidate(net);
 		net->is_inference = 0;
 		for (j = 0; j < net->train.nb_batch; j++) {
 			double t_batch = now_s(), batch_error = 0.0;
-			train_one_batch(net, &net->train, j, !net->dynamic_load);
+			train_one_batch(net, &net->train, j, !net->dynamic_load, j + 1 < net->train.nb_batch ? j + 1 : -1);
 			CB_CHECK(cb200_stream_sync(NULL));
 			for (k = 0; k < net->length; k++) { batch_error += net->loss_host[k]; total_error += net->loss_host[k]; }
 			batch_error /= net->length;

@@ -209,6 +209,9 @@ int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights*
  * gradient can be all-reduced across GPUs before momentum is applied). */
 int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weights* w,
                                 const void* x, const void* dy, void* stream);
+/* same, when grad_b was already produced by the kernel that wrote dy (cb200_norm_backward's dx_colsum) */
+int cb200_conv_backward_weights_ex(const cb200_conv_desc* d, const cb200_conv_weights* w,
+                                   const void* x, const void* dy, int have_grad_b, void* stream);
 
 /* Optimizer hyper-parameters live in a small device buffer so that a captured CUDA graph can be
  * replayed with a new learning rate: hyper[0]=lr/batch_total, [1]=momentum, [2]=lr*weight_decay,
@@ -271,7 +274,10 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y,
 int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy, void* dx,
                         const float* gamma, const float* mean, const float* var,
                         float* d_gamma, float* d_beta,
-                        const cb200_activ* prev_activ, void* workspace, void* stream);
+                        const cb200_activ* prev_activ, float* dx_colsum, void* workspace, void* stream);
+/* dx_colsum (optional, FP32 [c]): receives sum over batch and pixels of dx per channel - the raw bias-column gradient
+ * (grad_b) of the convolution that feeds this norm layer, produced for free while dx is written; the caller then uses
+ * cb200_conv_backward_weights_ex(..., have_grad_b = 1) for that convolution. */
 /* gamma_upd = mom*gamma_upd + lr*sum_b(d_gamma)/batch_total ; gamma -= gamma_upd/S (same for beta).
  * gsum: FP32 [2][nb_group] batch-summed (d_gamma, d_beta) (the buffer that is all-reduced in DP).
  * Replaces the host loop + 4 blocking memcpys of cuda_norm_layer.cu:434-457. */

@@ -172,7 +172,15 @@ def test_training_steps_match_live_reference(cnn, mode):
         ref.backward(t, 0.05, 0.9, 0.0005)
         cnn.backward_batch(0.05, 0.9, 0.0005)
         if mode == "off":     # (mixed precision deltas: see the conditioned-oracle comparison above)
-            e_d = rel_err(cnn.layer_delta(0) / S, ref.delta(0))
+            # elements whose pre-activation is within rounding of zero may take the other leaky-ReLU slope (x1 vs x0.05):
+            # they are counted and excluded, everything else must match
+            r0, m0 = ref.output(0), cnn.layer_output(0)
+            big = np.abs(r0) > 1e-5 * np.abs(r0).max()
+            assert np.all((r0 > 0)[big] == (m0 > 0)[big])
+            sure = big
+            REPORT["live/%s" % mode]["relu_near_zero_step%d" % step] = int((~big).sum())
+            assert (~big).mean() < 1e-3
+            e_d = rel_err(np.where(sure, cnn.layer_delta(0) / S, 0), np.where(sure, ref.delta(0), 0))
             REPORT["live/%s" % mode]["delta0_step%d" % step] = e_d
             assert e_d < 5 * tol, (step, e_d)
     for i, k in enumerate(kinds):

@@ -250,3 +250,6 @@ def test_group_norm_vs_oracle(cabi, cfg, dtype_name):
     assert rel_err(dx, ref_dx) < tol
     _, _, dg, db = nl.stats()
     assert rel_err(dg, dgam) < 1e-4 and rel_err(db, dbet) < 1e-4
+    # fused by-product: per-channel sums of dx (bias-column gradient of the convolution in front of the norm layer)
+    cs = nl.colsum.to_numpy(np.float32, (C,))
+    assert rel_err(cs, ref_dx.astype(np.float64).sum(axis=(1, 2))) < (1e-4 if dtype_name == "FP32" else TOL_MIXED)
