@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
 
 
 def cpu_baseline_sample(size):
-    """bounded CPU sample for the main line (rank 0, N = 1): 2 steps of 2 images with the compiled reference"""
+    """bounded CPU sample for the main line (rank 0, N = 1): 4 training steps of 4 images with the compiled reference"""
     from oracle import ref_driver as rd, ref_loader
     if not ref_loader.available("omp"):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref/omp not built"}
@@ -156,12 +156,12 @@ sys.path.insert(0, %r)
 import bench
 from oracle import ref_driver as rd, ref_loader
 cnn, _ = ref_loader.load("omp")
-spec = bench.darknet19_spec(2, %d, 1000)
+spec = bench.darknet19_spec(4, %d, 1000)
 with rd._Quiet():
     rd.build_network(cnn, spec, "C_BLAS", "off", network=0)
-x, t = bench.synth_batches(2, 2, %d, 1000, 3)
+x, t = bench.synth_batches(4, 4, %d, 1000, 3)
 with rd._Quiet():
-    cnn.create_dataset("TRAIN", 4, x, t, network=0, silent=1)
+    cnn.create_dataset("TRAIN", 16, x, t, network=0, silent=1)
     t0 = time.perf_counter()
     cnn.train(nb_iter=1, control_interv=1000, shuffle_every=0, silent=1, network=0, confmat=0, save_every=0, **bench.HYPER)
     dt = time.perf_counter() - t0
@@ -174,8 +174,8 @@ sys.stderr.write("CPUBASE " + json.dumps({"dt": dt}) + "\n")
         for ln in r.stderr.splitlines():
             if ln.startswith("CPUBASE "):
                 dt = json.loads(ln[8:])["dt"]
-                return {"value": 4.0 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-                        "sample": "1 epoch of 2 steps x 2 images (Darknet19-448, FP32, C_BLAS + OpenMP), %.1f s" % dt}
+                return {"value": 16.0 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": "1 epoch of 4 training steps x 4 images (Darknet19-448, FP32, reference C_BLAS + OpenMP back-end), %.1f s" % dt}
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "failed: " + r.stderr[-200:]}
     except subprocess.TimeoutExpired:
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "timed out after 600 s"}
@@ -290,18 +290,36 @@ def run_ours(args, rank, local_rank, world):
     ms_inf = timed(lambda: H.cb_forward_steps(net, args.steps, 1, 0))
     ms_inf_e2e = timed(lambda: H.cb_forward_steps(net, args.steps, 0, 1))
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     imgs = args.steps * B * world
     value = imgs / (ms_res / 1000.0)
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    conv_tc = {k: v for k, v in fam.items() if k.endswith("tcgen05") and v["launches"] > 0}
-    if conv_tc:
-        dom = max(conv_tc, key=lambda k: conv_tc[k]["ms"])
-        ach = conv_tc[dom]["work"] / (conv_tc[dom]["ms"] / 1000.0) / 1e12
-        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                "peak_source": peak_src, "launches": conv_tc[dom]["launches"], "avg_launch_ms": conv_tc[dom]["ms"] / conv_tc[dom]["launches"],
-                "share_of_step": conv_tc[dom]["ms"] / ms_res}
+    # forward and data gradient are launches of the SAME kernel (conv_igemm_kernel); the weight gradient is its own kernel
+    kern = {}
+    for name, members in (("conv_igemm_kernel", ("conv_fwd_tcgen05", "conv_dgrad_tcgen05")), ("conv_wgrad_kernel", ("conv_wgrad_tcgen05",))):
+        agg = {"ms": sum(fam[m]["ms"] for m in members), "work": sum(fam[m]["work"] for m in members), "launches": sum(fam[m]["launches"] for m in members)}
+        if agg["launches"] > 0:
+            kern[name] = agg
+    if kern:
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        ach = kern[dom]["work"] / (kern[dom]["ms"] / 1000.0) / 1e12
+        traffic, ncu_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_conv_metrics_summary.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            key = {"conv_igemm_kernel": "igemm", "conv_wgrad_kernel": "wgrad"}[dom]
+            if tj.get("batch", 128) == B and args.size == 448 and key in tj:
+                traffic = tj[key]["avg_dram_bytes_per_launch"]
+                ncu_note = {"source": "profiles/r1_conv_metrics_b128.csv (ncu, dram__bytes_read.sum + dram__bytes_write.sum, mean over the kernel's launches of one step)",
+                            "tensor_pipe_pct_time_weighted": tj[key]["tensor_pipe_pct_time_weighted"]}
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "peak_source": peak_src, "launches": kern[dom]["launches"], "avg_launch_ms": kern[dom]["ms"] / kern[dom]["launches"],
+                "algorithmic_flops_per_launch": kern[dom]["work"] / kern[dom]["launches"],
+                "share_of_step": kern[dom]["ms"] / ms_res, "ncu": ncu_note}
     else:
         dom = max(fam, key=lambda k: fam[k]["ms"])
         ach = fam[dom]["work"] / max(fam[dom]["ms"], 1e-9) * 1e3 / 1e12
