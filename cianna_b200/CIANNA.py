@@ -13,8 +13,8 @@ libcianna_b200.so (CUDA core, C-ABI of include/cianna_b200.h).  Usage is unchang
     cnn.train(nb_iter=1, learning_rate=0.003, momentum=0.9, ...)
 
 There is no CPU path: comp_meth must be "C_CUDA" and a missing CUDA extension / device is an error.
-Methods that belong to parts of upstream outside this round's scope (yolo parameters, lrn,
-print_arch_tex) raise NotImplementedError rather than silently doing nothing.
+Methods that belong to parts of upstream outside this round's scope (lrn, print_arch_tex) raise
+NotImplementedError rather than silently doing nothing.
 """
 import ctypes
 import math
@@ -260,11 +260,92 @@ def set_frozen_layers(froz_array, network=None):
     L.set_frozen_layers(_net(network), arr, int(a.size))
 
 
-def _yolo_na(*args, **kwargs):
-    raise NotImplementedError("YOLO output-layer configuration is not built yet in the B200 core (SURVEY.md 8a21-25)")
+# ---- YOLO output layer configuration (src/python_module.c:583-884): the five small helpers only build arrays whose
+# "unset" entries carry the markers set_yolo_params looks for
+def set_IoU_limits(good_IoU_lim=-2.0, low_IoU_best_box_assoc=-2.0, min_prob_IoU_lim=-2.0, min_obj_IoU_lim=-2.0,
+                   min_class_IoU_lim=-2.0, min_param_IoU_lim=-2.0, diff_IoU_lim=-2.0, diff_obj_lim=-2.0):
+    return np.array([good_IoU_lim, low_IoU_best_box_assoc, min_prob_IoU_lim, min_obj_IoU_lim, min_class_IoU_lim,
+                     min_param_IoU_lim, diff_IoU_lim, diff_obj_lim], dtype=np.float32)
 
 
-set_IoU_limits = set_fit_parts = set_error_scales = set_sm_single = set_slopes_and_maxes = set_yolo_params = _yolo_na
+def set_fit_parts(position=-2, size=-2, probability=-2, objectness=-2, classes=-2, parameters=-2):
+    return np.array([position, size, probability, objectness, classes, parameters], dtype=np.int32)
+
+
+def set_error_scales(position=-1.0, size=-1.0, probability=-1.0, objectness=-1.0, classes=-1.0, parameters=-1.0):
+    return np.array([position, size, probability, objectness, classes, parameters], dtype=np.float32)
+
+
+def set_sm_single(slope=-1.0, fmin=-100000.0, fmax=100000.0):
+    return np.array([slope, fmax, fmin], dtype=np.float32)
+
+
+def set_slopes_and_maxes(position=None, size=None, probability=None, objectness=None, classes=None, parameters=None):
+    out = np.empty((6, 3), dtype=np.float32)
+    for i, v in enumerate((position, size, probability, objectness, classes, parameters)):
+        out[i] = (-1.0, 100000.0, -100000.0) if v is None else np.asarray(v, dtype=np.float32).ravel()[:3]
+    return out
+
+
+def _fptr(a, n=None):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+    if n is not None and a.size != n:
+        raise SystemExit("ERROR: YOLO parameter array has %d elements, expected %d" % (a.size, n))
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def set_yolo_params(nb_box=0, nb_class=0, nb_param=0, max_nb_obj_per_image=0, prior_size=None, prior_noobj_prob=None,
+                    error_scales=None, slopes_and_maxes=None, param_ind_scales=None, IoU_limits=None, fit_parts=None,
+                    IoU_type="empty", prior_dist_type="empty", strict_box_size=0, fit_dim=0, rand_startup=-1,
+                    rand_prob_best_box_assoc=0.0, rand_prob=0.0, min_prior_forced_scaling=0.0, class_softmax=0, diff_flag=0,
+                    network=0, error_type="empty", no_override=0, raw_output=0):
+    """Same keywords and defaults as upstream (src/python_module.c:764-884); returns the number of filters the YOLO
+    layer must have. prior_size is [dims][nb_box] like upstream."""
+    L = _load()
+    net = _net(network)
+    keep = []
+    c_prior = None
+    if prior_size is not None:
+        ps = np.asarray(prior_size, dtype=np.float32)
+        if ps.ndim != 2 or ps.shape[1] != nb_box:
+            raise SystemExit("ERROR: The prior_size array must have nb_box elements!")
+        if fit_dim <= 0:
+            fit_dim = ps.shape[0]
+        elif fit_dim > ps.shape[0]:
+            raise SystemExit("ERROR: fit_dim parameter cannot be larger than the number of dimensions of prior_size!")
+        flat = np.zeros((nb_box, 3), dtype=np.float32)
+        flat[:, :fit_dim] = ps[:fit_dim].T
+        keep.append(flat)
+        c_prior = flat.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    a_noobj, c_noobj = _fptr(prior_noobj_prob, nb_box)
+    a_scales, c_scales = _fptr(error_scales, 6)
+    a_pis, c_pis = _fptr(param_ind_scales, nb_param)
+    a_lim, c_lim = _fptr(IoU_limits, 8)
+    c_sm = None
+    if slopes_and_maxes is not None:
+        sm = np.ascontiguousarray(slopes_and_maxes, dtype=np.float32).reshape(6, 3)
+        rows = (ctypes.POINTER(ctypes.c_float) * 6)(*[sm[i].ctypes.data_as(ctypes.POINTER(ctypes.c_float)) for i in range(6)])
+        keep += [sm, rows]
+        c_sm = rows
+    c_fit = None
+    if fit_parts is not None:
+        fp = np.ascontiguousarray(fit_parts, dtype=np.int32).ravel()
+        keep.append(fp)
+        c_fit = fp.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    L.set_yolo_params.restype = ctypes.c_int
+    L.set_yolo_params.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                  ctypes.c_char_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.POINTER(ctypes.c_float)),
+                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    return L.set_yolo_params(net, int(nb_box), int(nb_class), int(nb_param), int(max_nb_obj_per_image), _s(IoU_type),
+                             _s(prior_dist_type), c_prior, c_noobj, int(fit_dim), int(strict_box_size), int(rand_startup),
+                             float(rand_prob_best_box_assoc), float(rand_prob), float(min_prior_forced_scaling), c_scales, c_sm,
+                             c_pis, c_lim, c_fit, int(class_softmax), int(diff_flag), _s(error_type), int(no_override),
+                             int(raw_output))
 
 
 def perf_eval(network=None):
@@ -396,6 +477,57 @@ def set_TC_scale_factor(value, network=None):
     L = _load()
     L.cb_set_TC_scale_factor.argtypes = [ctypes.c_void_p, ctypes.c_float]
     L.cb_set_TC_scale_factor(_net(network), float(value))
+
+
+# ---- YOLO read-backs (parity tests): association state, loss split, decoded boxes
+def _yolo_geom(network):
+    L = _load()
+    net = _net(network)
+    last = L.cb_net_nb_layers(net) - 1
+    c, h, w, _ = layer_shape(last, network)
+    return L, net, L.cb_net_batch_size(net), c, h * w
+
+
+def yolo_set_seed(seed, network=None):
+    L = _load()
+    L.cb_yolo_set_seed.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong]
+    L.cb_yolo_set_seed(_net(network), int(seed))
+
+
+def set_iter(iteration, train_size=0, network=None):
+    """epoch counter of the network (drives the YOLO random start-up phase: iter * train.size <= rand_startup);
+    train_size stands in for the TRAIN dataset's size when batches are fed with load_batch"""
+    L = _load()
+    L.cb_net_set_iter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.cb_net_set_iter(_net(network), int(iteration), int(train_size))
+
+
+def yolo_box_state(nb_box, network=None):
+    """[B][cells][nb_box] int32 after backward_batch: 0 background, 1 good-but-not-best, 2 associated to a target"""
+    L, net, b, c, cells = _yolo_geom(network)
+    a = np.zeros((b, cells, nb_box), dtype=np.int32)
+    L.cb_yolo_box_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.cb_yolo_box_state(net, a.ctypes.data)
+    return a
+
+
+def yolo_loss_parts(nb_box, network=None):
+    """after batch_loss: (parts[6] averaged over the batch, monitor [B][cells][nb_box][2] = objectness, IoU or -1)"""
+    L, net, b, c, cells = _yolo_geom(network)
+    parts = np.zeros(6, dtype=np.float32)
+    mon = np.zeros((b, cells, nb_box, 2), dtype=np.float32)
+    L.cb_yolo_loss_parts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.cb_yolo_loss_parts(net, parts.ctypes.data, mon.ctypes.data)
+    return parts, mon
+
+
+def yolo_boxes(network=None):
+    """decoded forward output, reference layout [C][B][cells]: box corners in pixels, then prob / obj / classes / params"""
+    L, net, b, c, cells = _yolo_geom(network)
+    a = np.zeros((c, b, cells), dtype=np.float32)
+    L.cb_yolo_export_boxes.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.cb_yolo_export_boxes(net, a.ctypes.data)
+    return a
 
 
 def last_conv_impl():

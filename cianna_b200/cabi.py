@@ -285,3 +285,128 @@ class NormLayer:
         shp = (self.d.batch, self.nb_group)
         return (self.mean.to_numpy(np.float32, shp), self.var.to_numpy(np.float32, shp),
                 self.d_gamma.to_numpy(np.float32, shp), self.d_beta.to_numpy(np.float32, shp))
+
+
+class YoloDesc(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int), ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
+                ("nb_box", ctypes.c_int), ("nb_class", ctypes.c_int), ("nb_param", ctypes.c_int), ("max_nb_obj", ctypes.c_int),
+                ("target_stride", ctypes.c_int), ("fit_dim", ctypes.c_int), ("IoU_type", ctypes.c_int), ("prior_dist_type", ctypes.c_int),
+                ("error_type", ctypes.c_int), ("class_softmax", ctypes.c_int), ("diff_flag", ctypes.c_int),
+                ("strict_box_size_association", ctypes.c_int), ("rand_startup", ctypes.c_int),
+                ("rand_prob_best_box_assoc", ctypes.c_float), ("rand_prob", ctypes.c_float), ("min_prior_forced_scaling", ctypes.c_float),
+                ("cell_size", ctypes.c_int * 3), ("scale_tab", ctypes.c_float * 6), ("slopes_and_maxes", ctypes.c_float * 18),
+                ("IoU_limits", ctypes.c_float * 8), ("fit_parts", ctypes.c_int * 6),
+                ("prior_size", ctypes.c_void_p), ("noobj_prob_prior", ctypes.c_void_p), ("param_ind_scale", ctypes.c_void_p)]
+
+
+IOU_TYPES = {"IoU": 0, "GIoU": 1, "DIoU": 2, "DIoU2": 3}
+DIST_TYPES = {"IoU": 0, "IOU": 0, "SIZE": 1, "OFFSET": 2}
+_IOU_LIMITS = {0: (0.5, 0.1, 0.0, 0.0, 0.2, 0.2, 0.5, 0.3), 1: (0.4, -0.5, -1.0, -1.0, -0.3, -0.3, 0.4, 0.2),
+               2: (0.3, -0.6, -1.0, -1.0, -0.5, -0.5, 0.3, 0.1), 3: (0.3, -0.5, -1.0, -1.0, -0.4, -0.4, 0.3, 0.1)}
+
+
+class YoloHead:
+    """YOLO output head driven through the C-ABI only. `y` takes the keywords of set_yolo_params (prior_size [dims][nb_box]);
+    the defaults applied here are upstream's (src/activ_functions.c:1129-1380)."""
+
+    def __init__(self, dtype, batch, grid_h, grid_w, in_w, in_h, y, length=None):
+        L = lib()
+        L.cb200_yolo_workspace_bytes.restype = ctypes.c_size_t
+        L.cb200_yolo_activation.argtypes = [ctypes.c_void_p] * 3
+        L.cb200_yolo_delta.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_float, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_ulonglong] + [ctypes.c_void_p] * 3
+        L.cb200_yolo_loss.argtypes = [ctypes.c_void_p] * 8
+        L.cb200_yolo_export_boxes.argtypes = [ctypes.c_void_p] * 4
+        nb_box, nc, npar = y["nb_box"], y.get("nb_class", 0), y.get("nb_param", 0)
+        diff = y.get("diff_flag", 0)
+        d = YoloDesc()
+        d.dtype, d.batch, d.length = dtype, batch, batch if length is None else length
+        d.grid_h, d.grid_w = grid_h, grid_w
+        d.nb_box, d.nb_class, d.nb_param, d.max_nb_obj = nb_box, nc, npar, y["max_nb_obj_per_image"]
+        d.target_stride = 1 + d.max_nb_obj * (7 + npar + diff)
+        ps = np.asarray(y["prior_size"], dtype=np.float32)
+        d.fit_dim = y.get("fit_dim", 0) or ps.shape[0]
+        d.IoU_type = IOU_TYPES.get(y.get("IoU_type", "empty"), 1)
+        d.prior_dist_type = DIST_TYPES.get(y.get("prior_dist_type", "empty"), 1)
+        d.error_type = 0 if y.get("error_type", "empty") == "complete" else 1
+        d.class_softmax, d.diff_flag = y.get("class_softmax", 0), diff
+        d.strict_box_size_association = y.get("strict_box_size", 0)
+        rs = y.get("rand_startup", -1)
+        d.rand_startup = 64000 if rs < 0 else rs
+        d.rand_prob_best_box_assoc = max(0.0, y.get("rand_prob_best_box_assoc", 0.0))
+        d.rand_prob = max(0.0, y.get("rand_prob", 0.0))
+        d.min_prior_forced_scaling = max(0.0, y.get("min_prior_forced_scaling", 0.0))
+        d.cell_size[0], d.cell_size[1], d.cell_size[2] = in_w // grid_w, in_h // grid_h, 1
+        scales = [2.0, 2.0, 1.0, 2.0, 1.0, 1.0]
+        for i, v in enumerate(y.get("error_scales", [-1.0] * 6)):
+            if v > 0.0:
+                scales[i] = float(v)
+        sm = np.array([[1, 6, -6], [1, 1.6, -1.6], [1, 6, -6], [1, 6, -6], [1, 6, -6], [1, 1.2, -0.2]], dtype=np.float32)
+        if "slopes_and_maxes" in y:
+            u = np.asarray(y["slopes_and_maxes"], dtype=np.float32).reshape(6, 3)
+            sm[:, 0] = np.where(u[:, 0] > 0.0, u[:, 0], sm[:, 0])
+            sm[:, 1] = np.where(u[:, 1] < 100000.0, u[:, 1], sm[:, 1])
+            sm[:, 2] = np.where(u[:, 2] > -100000.0, u[:, 2], sm[:, 2])
+        lim = list(_IOU_LIMITS[d.IoU_type])
+        for i, v in enumerate(y.get("IoU_limits", [-2.0] * 8)):
+            if v > -1.99:
+                lim[i] = float(v)
+        fit = [1, 1, 1, 1, 1 if nc > 0 else -1, 1 if npar > 0 else -1]
+        for i, v in enumerate(y.get("fit_parts", [-2] * 6)):
+            if v > -2:
+                fit[i] = int(v)
+        for i in range(6):
+            d.scale_tab[i] = scales[i]
+            d.fit_parts[i] = fit[i]
+        for i in range(18):
+            d.slopes_and_maxes[i] = float(sm.ravel()[i])
+        for i in range(8):
+            d.IoU_limits[i] = lim[i]
+        prior = np.zeros((nb_box, 3), dtype=np.float32)
+        prior[:, : d.fit_dim] = ps[: d.fit_dim].T
+        prior = np.maximum(prior, 1.0)
+        noobj = np.asarray(y.get("prior_noobj_prob", [0.2] * nb_box), dtype=np.float32)
+        pis = np.asarray(y.get("param_ind_scales", [1.0] * max(npar, 1)), dtype=np.float32)
+        self.tables = [DevBuf.from_numpy(prior), DevBuf.from_numpy(noobj), DevBuf.from_numpy(pis)]
+        d.prior_size, d.noobj_prob_prior, d.param_ind_scale = [t.ptr.value for t in self.tables]
+        self.d, self.dtype = d, dtype
+        self.C = nb_box * (8 + nc + npar)
+        self.cells = grid_h * grid_w
+        self.ws = DevBuf(L.cb200_yolo_workspace_bytes(ctypes.byref(d)))
+        es = L.cb200_dtype_size(dtype)
+        self.delta = DevBuf(batch * self.cells * round8(self.C) * es)
+        self.state = DevBuf(batch * self.cells * nb_box * 4)
+        self.loss_buf = DevBuf(batch * 4)
+        self.parts = DevBuf(batch * 6 * 4)
+        self.monitor = DevBuf(batch * self.cells * nb_box * 2 * 4)
+
+    def upload_targets(self, t):
+        """FP32 rows [B][target_stride] -> device buffer in the head's dtype (round toward zero like the dataset path)"""
+        L = lib()
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        host = np.empty(t.size * L.cb200_dtype_size(self.dtype), dtype=np.uint8)
+        L.cb200_host_cast_from_f32(host.ctypes.data, self.dtype, t.ctypes.data, t.size)
+        return DevBuf.from_numpy(host)
+
+    def activation(self, y_buf):
+        check(lib().cb200_yolo_activation(ctypes.byref(self.d), y_buf.ptr, None))
+
+    def deriv_error(self, y_buf, t_buf, tc_scale=1.0, nb_im_iter=10**9, seed=1, step=0):
+        d = self.d
+        check(lib().cb200_yolo_delta(ctypes.byref(d), self.delta.ptr, y_buf.ptr, t_buf.ptr, tc_scale, nb_im_iter, seed, step,
+                                     self.state.ptr, self.ws.ptr, None))
+        return (download_act(self.delta, self.dtype, d.batch, self.C, d.grid_h, d.grid_w),
+                self.state.to_numpy(np.int32, (d.batch, self.cells, d.nb_box)))
+
+    def loss(self, y_buf, t_buf):
+        d = self.d
+        check(lib().cb200_yolo_loss(ctypes.byref(d), self.loss_buf.ptr, self.parts.ptr, self.monitor.ptr, y_buf.ptr, t_buf.ptr, self.ws.ptr, None))
+        return (self.loss_buf.to_numpy(np.float32, (d.batch,)), self.parts.to_numpy(np.float32, (d.batch, 6)),
+                self.monitor.to_numpy(np.float32, (d.batch, self.cells, d.nb_box, 2)))
+
+    def boxes(self, y_buf):
+        d = self.d
+        tmp = DevBuf(self.C * d.batch * self.cells * 4)
+        check(lib().cb200_yolo_export_boxes(ctypes.byref(d), tmp.ptr, y_buf.ptr, None))
+        out = tmp.to_numpy(np.float32, (self.C, d.batch, self.cells))
+        tmp.free()
+        return out

@@ -41,6 +41,7 @@ enum TC_comp_mode { FP32C_FP32A, TF32C_FP32A, FP16C_FP32A, FP16C_FP16A, BF16C_FP
 
 typedef struct network network;
 typedef struct layer layer;
+typedef struct yolo_param yolo_param;
 
 typedef struct Dataset {
 	int size;              /* number of samples */
@@ -66,6 +67,7 @@ struct layer {
 	float bias_value;
 	float dropout_rate;
 	cb200_activ activ;
+	void *activ_param;     /* yolo_param of a YOLO output layer (own copy, device tables attached), else NULL */
 	void (*forward)(layer *current);
 	void (*backprop)(layer *current);
 	int nb_params;
@@ -108,6 +110,33 @@ typedef struct dense_param {
 	cb200_conv_weights w;
 	size_t grad_offset, grad_len;
 } dense_param;
+
+/* YOLO output-layer set-up, same fields and defaults as upstream's yolo_param (src/structs.h:527-575); the
+ * association scratch tables of upstream are replaced by one device workspace (include/cianna_b200.h) */
+struct yolo_param {
+	int no_override, raw_output;
+	int nb_box, nb_class, nb_param, max_nb_obj_per_image, fit_dim;
+	int IoU_type, prior_dist_type;
+	float *prior_size;            /* host [nb_box][3] */
+	float *noobj_prob_prior;      /* host [nb_box] */
+	int class_softmax, diff_flag, error_type;
+	int strict_box_size_association, rand_startup;
+	float rand_prob_best_box_assoc, rand_prob, min_prior_forced_scaling;
+	float scale_tab[6];
+	float slopes_and_maxes_tab[6][3];
+	float *param_ind_scale;       /* host [nb_param] */
+	float IoU_limits[8];
+	int fit_parts[6];
+	int cell_size[3];
+	/* device side (filled by set_yolo_activ on the layer's copy) */
+	cb200_yolo_desc desc;
+	float *dev_tables;            /* prior_size | noobj_prob_prior | param_ind_scale */
+	float *workspace;
+	float *parts_dev, *parts_host;       /* [batch][6] loss split */
+	float *monitor_dev, *monitor_host;   /* [batch][cells][nb_box][2] */
+	int *box_state_dev;                  /* [batch][cells][nb_box] lock state written by the association pass */
+	unsigned long long seed, step;
+};
 
 struct network {
 	layer *net_layers[MAX_LAYERS_NB];
@@ -160,6 +189,7 @@ struct network {
 	const void *staged_src[2];   /* host batch currently (being) copied into each slot */
 	int stage_slot;
 	const cb200_conv_desc *patch_desc;   /* first conv layer when it consumes patch rows (few input channels), else NULL */
+	yolo_param *y_param;   /* network-level YOLO set-up (set_yolo_params), copied into the YOLO layer at creation */
 };
 
 extern network *networks[MAX_NETWORKS_NB];
@@ -202,6 +232,13 @@ void load_activ_param(layer *current, const char *activ);
 void set_activ_defaults(layer *current, const char *activ);
 void print_string_activ_param(layer *current, char *activ);
 void print_activ_param(FILE *f, layer *current, int f_bin);
+/* YOLO output layer (src/activ_functions.c:970-1477) */
+int set_yolo_params(network *net, size_t nb_box, int nb_class, int nb_param, int max_nb_obj_per_image, const char *IoU_type_char,
+	const char *prior_dist_type_char, float *prior_size, float *yolo_noobj_prob_prior, int fit_dim,
+	int strict_box_size, int rand_startup, float rand_prob_best_box_assoc, float rand_prob, float min_prior_forced_scaling, float *scale_tab,
+	float **slopes_and_maxes_tab, float *param_ind_scale, float *IoU_limits, int *fit_parts, int class_softmax,
+	int diff_flag, const char *error_type, int no_override, int raw_output);
+void set_yolo_activ(layer *current);
 /* initialisers (src/initializers.c) */
 void init_weights(float *tab, int dim_in, int dim_out, const char *init_fct, float init_scaling);
 
@@ -249,6 +286,13 @@ void cb_net_in_dims(network *net, int *out4);
 void cb_set_TC_scale_factor(network *net, float v);
 void cb_train_steps(network *net, int nsteps, float lr, float momentum, float weight_decay, int resident, int sync_each_step);
 void cb_forward_steps(network *net, int nsteps, int resident, int sync_each_step);
+/* YOLO read-backs for bindings / parity tests: box_state int32 [B][cells][nb_box] of the last cb_backward,
+ * loss split [6] and monitor [B][cells][nb_box][2] of the last cb_batch_loss, decoded boxes [C][B][cells] */
+void cb_yolo_set_seed(network *net, unsigned long long seed);
+void cb_yolo_box_state(network *net, int *dst);
+void cb_yolo_loss_parts(network *net, float *parts6, float *monitor);
+void cb_yolo_export_boxes(network *net, float *dst);
+void cb_net_set_iter(network *net, int iter, int train_size);
 
 #define CB_CHECK(call) do { int rc__ = (call); if (rc__ != 0) { \
 	printf("\nERROR: %s failed (%d): %s\n", #call, rc__, cb200_last_error()); exit(EXIT_FAILURE); } } while (0)

@@ -67,6 +67,11 @@ static void forward_conv_layer(layer *current)
 	CB_CHECK(cb200_conv_forward(&p->desc, &p->w, layer_input(current), current->output, NULL));
 	if (current->activation_type == SOFTMAX)
 		CB_CHECK(cb200_softmax(current->output, net->dtype, net->batch_size, net->length, current->out_c, current->out_h, current->out_w, NULL));
+	else if (current->activation_type == YOLO) {
+		yolo_param *y = (yolo_param *)current->activ_param;
+		y->desc.length = net->length;
+		CB_CHECK(cb200_yolo_activation(&y->desc, current->output, NULL));
+	}
 }
 
 static void backward_conv_layer(layer *current)
@@ -139,7 +144,7 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	set_activ_defaults(current, activation);
 	if (bias != NULL) current->bias_value = *bias;
 	if (previous == NULL) current->bias_value = net->input_bias;
-	if (current->activation_type == YOLO) { printf("\nERROR: YOLO output layers are not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
+	if (current->activation_type == YOLO) set_yolo_activ(current);   /* checks nb_filters against the YOLO set-up */
 
 	p->desc.dtype = net->dtype; p->desc.batch = net->batch_size; p->desc.length = net->batch_size;
 	p->desc.in_c = pc; p->desc.in_h = ph; p->desc.in_w = pw;
@@ -149,7 +154,8 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	p->desc.pad_h = padding[1]; p->desc.pad_w = padding[0];
 	p->desc.bias_value = current->bias_value;
 	p->desc.activ = current->activ;
-	if (current->activation_type == SOFTMAX) p->desc.activ.type = CB200_LINEAR;   /* softmax is a separate pass */
+	if (current->activation_type == SOFTMAX || current->activation_type == YOLO)
+		p->desc.activ.type = CB200_LINEAR;   /* softmax / the YOLO head are separate passes on the linear output */
 	/* first layer on an input with very few channels (RGB / grey): the layout import unrolls the receptive fields into
 	 * patch rows so that the layer runs on the tensor-core GEMM kernels (include/cianna_b200.h, cb200_import_input_patches) */
 	p->desc.input_is_patches = (previous == NULL && cb200_round_channels(pc) < 16) ? 1 : 0;
@@ -219,6 +225,19 @@ void conv_save(FILE *f, layer *current, int f_bin)
 		fwrite(&current->dropout_rate, sizeof(float), 1, f);
 		fwrite(&current->bias_value, sizeof(float), 1, f);
 		print_activ_param(f, current, f_bin);
+		if (current->activation_type == YOLO) {
+			/* YOLO set-up block of the save format (src/conv_layer.c:442-456): priors dimension-major */
+			yolo_param *y = current->c_network->y_param;
+			int a, b;
+			fwrite(&y->nb_box, sizeof(int), 1, f);
+			fwrite(&y->nb_class, sizeof(int), 1, f);
+			fwrite(&y->nb_param, sizeof(int), 1, f);
+			fwrite(&y->fit_dim, sizeof(int), 1, f);
+			fwrite(&y->class_softmax, sizeof(int), 1, f);
+			for (a = 0; a < 3; a++)
+				for (b = 0; b < y->nb_box; b++) fwrite(y->prior_size + b * 3 + a, sizeof(float), 1, f);
+			for (a = 0; a < 6; a++) fwrite(y->slopes_and_maxes_tab[a], sizeof(float), 3, f);
+		}
 	} else {
 		fprintf(f, "C");
 		fprintf(f, "%df%dx%dx%d.%dx%dx%ds%dx%dx%dp%dx%dx%dip%dx%dx%dx%didim%fd%fb", p->nb_filters,
@@ -227,6 +246,17 @@ void conv_save(FILE *f, layer *current, int f_bin)
 			p->prev_size[0], p->prev_size[1], p->prev_size[2], p->prev_depth, current->dropout_rate, current->bias_value);
 		print_activ_param(f, current, f_bin);
 		fprintf(f, "\n");
+		if (current->activation_type == YOLO) {
+			yolo_param *y = current->c_network->y_param;
+			int a, b;
+			fprintf(f, "%d %d %d %d %d\n", y->nb_box, y->nb_class, y->nb_param, y->fit_dim, y->class_softmax);
+			for (a = 0; a < 3; a++) {
+				for (b = 0; b < y->nb_box; b++) fprintf(f, "%g ", y->prior_size[b * 3 + a]);
+				fprintf(f, "\n");
+			}
+			for (a = 0; a < 6; a++)
+				fprintf(f, "%g %g %g \n", y->slopes_and_maxes_tab[a][0], y->slopes_and_maxes_tab[a][1], y->slopes_and_maxes_tab[a][2]);
+		}
 	}
 	CB_CHECK(cb200_d2h(host_w, p->w.master, nw * sizeof(float), NULL));
 	CB_CHECK(cb200_stream_sync(NULL));
@@ -266,7 +296,44 @@ void conv_load(network *net, FILE *f, int f_bin)
 			&padding[0], &padding[1], &padding[2], &int_padding[0], &int_padding[1], &int_padding[2],
 			&input_shape[0], &input_shape[1], &input_shape[2], &input_shape[3], &dropout_rate, &bias, activ_type);
 	}
-	if (strncmp(activ_type, "YOLO", 4) == 0) { printf("\nERROR: YOLO layers cannot be loaded by the B200 core yet.\n"); exit(EXIT_FAILURE); }
+	if (strncmp(activ_type, "YOLO", 4) == 0) {
+		/* YOLO set-up block (src/conv_layer.c:571-650): the saved geometry of the head replaces the one given to
+		 * set_yolo_params unless no_override was requested */
+		int head[5], a, b;
+		float *prior, sm[6][3];
+		if (f_bin) fread(head, sizeof(int), 5, f);
+		else fscanf(f, "%d %d %d %d %d\n", &head[0], &head[1], &head[2], &head[3], &head[4]);
+		if (head[0] <= 0 || head[0] > CB200_YOLO_MAX_BOX) { printf("\nERROR: corrupted YOLO block in save file (nb_box = %d)\n", head[0]); exit(EXIT_FAILURE); }
+		prior = (float *)calloc(3 * head[0], sizeof(float));
+		for (a = 0; a < 3; a++)
+			for (b = 0; b < head[0]; b++) {
+				if (f_bin) fread(prior + b * 3 + a, sizeof(float), 1, f);
+				else fscanf(f, "%f", prior + b * 3 + a);
+			}
+		for (a = 0; a < 6; a++) {
+			if (f_bin) fread(sm[a], sizeof(float), 3, f);
+			else fscanf(f, "%f %f %f", &sm[a][0], &sm[a][1], &sm[a][2]);
+		}
+		if (net->y_param->no_override != 1) {
+			yolo_param *y = net->y_param;
+			y->nb_box = head[0]; y->nb_class = head[1]; y->nb_param = head[2]; y->fit_dim = head[3]; y->class_softmax = head[4];
+			free(y->prior_size);
+			y->prior_size = prior;
+			memcpy(y->slopes_and_maxes_tab, sm, sizeof(sm));
+			printf(" WARNING: Overriding the following YOLO parameters from save file:\n");
+			printf(" Nboxes = %d, Nclasses = %d, Nparams = %d\n", y->nb_box, y->nb_class, y->nb_param);
+			printf(" Classification type: %s\n", y->class_softmax ? "softmax-CrossEntropy" : "sigmoid-MSE");
+			printf(" Nb dim fitted : %d\n\n", y->fit_dim);
+			for (a = 0; a < 3; a++) {
+				printf(" %c priors = [", "WHD"[a]);
+				for (b = 0; b < y->nb_box; b++) printf("%4.4f ", y->prior_size[b * 3 + a]);
+				printf("]\n");
+			}
+			printf("\n Activation slopes and limits: \n   = ");
+			for (a = 0; a < 6; a++) printf("[%6.2f %6.2f %6.2f]\n     ", sm[a][0], sm[a][1], sm[a][2]);
+			printf("\n");
+		} else free(prior);
+	}
 	previous = net->nb_layers <= 0 ? NULL : net->net_layers[net->nb_layers - 1];
 	conv_create(net, previous, f_size, nb_filters, stride, padding, int_padding, input_shape, activ_type, &bias, dropout_rate, NULL, 0.0f, f, f_bin);
 }

@@ -78,6 +78,9 @@ void init_network(int network_number, int u_input_dim[4], int u_output_dim, floa
 	net->dp_world = 1;
 	net->length = net->batch_size;
 	net->train_buf.localization = NO_LOC; net->test_buf.localization = NO_LOC; net->valid_buf.localization = NO_LOC;
+	/* empty YOLO set-up (src/auxil.c:261-295); set_yolo_params fills it before the YOLO layer is created */
+	net->y_param = (yolo_param *)calloc(1, sizeof(yolo_param));
+	net->y_param->min_prior_forced_scaling = -1.0f;
 
 	{
 		size_t es = cb200_dtype_size(net->dtype);
@@ -279,6 +282,14 @@ void cb_forward(network *net, int length, int is_inference)
 static void output_deriv_error(network *net, const void *target_dev)
 {
 	layer *last = net->net_layers[net->nb_layers - 1];
+	if (last->activation_type == YOLO) {
+		/* target association + error signal in one pass (src/cuda/cuda_activ_functions.cu:2369-2381) */
+		yolo_param *y = (yolo_param *)last->activ_param;
+		y->desc.length = net->length;
+		CB_CHECK(cb200_yolo_delta(&y->desc, last->delta_o, last->output, target_dev, net->TC_scale_factor,
+			(long long)net->iter * net->train.size, y->seed, y->step++, y->box_state_dev, y->workspace, NULL));
+		return;
+	}
 	/* quadratic (LIN / RELU / LOGI outputs) and cross-entropy (SMAX) share delta = (o - t) * S upstream */
 	CB_CHECK(cb200_output_delta(last->delta_o, last->output, target_dev, net->dtype, net->batch_size, net->length,
 		last->out_c, last->out_h, last->out_w, net->TC_scale_factor, NULL));
@@ -291,6 +302,12 @@ static void output_deriv_error(network *net, const void *target_dev)
 static void output_error(network *net, const void *target_dev)
 {
 	layer *last = net->net_layers[net->nb_layers - 1];
+	if (last->activation_type == YOLO) {
+		yolo_param *y = (yolo_param *)last->activ_param;
+		y->desc.length = net->length;
+		CB_CHECK(cb200_yolo_loss(&y->desc, net->loss_dev, y->parts_dev, y->monitor_dev, last->output, target_dev, y->workspace, NULL));
+		return;
+	}
 	CB_CHECK(cb200_output_loss(net->loss_dev, last->output, target_dev, net->dtype, net->batch_size, net->length,
 		last->out_c, last->out_h, last->out_w, last->activation_type == SOFTMAX ? 1 : 0, NULL));
 }
@@ -575,6 +592,9 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 	char name[200];
 	struct stat st;
 	layer *last = net->net_layers[net->nb_layers - 1];
+	yolo_param *yolo = last->activation_type == YOLO ? (yolo_param *)last->activ_param : NULL;
+	double part_err[6] = {0, 0, 0, 0, 0, 0}, sum_IoU = 0.0, sum_obj = 0.0;
+	long nb_IoU = 0, nb_good_IoU = 0;
 	(void)confusion_matrix; (void)repeat;
 
 	last_layer_dims(net, &c, &h, &w);
@@ -604,14 +624,31 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		if (!net->no_error) {
 			output_error(net, tgt);
 			CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
+			if (yolo != NULL) {
+				CB_CHECK(cb200_d2h(yolo->parts_host, yolo->parts_dev, (size_t)net->batch_size * 6 * sizeof(float), NULL));
+				CB_CHECK(cb200_d2h(yolo->monitor_host, yolo->monitor_dev, (size_t)net->batch_size * h * w * yolo->nb_box * 2 * sizeof(float), NULL));
+			}
 		}
 		if (saving > 0) {
-			if (last->type == DENSE) CB_CHECK(cb200_export_dense(out_dev, last->output, net->dtype, net->batch_size, c, 0.0f, NULL));
+			if (yolo != NULL && net->y_param->raw_output == 0) CB_CHECK(cb200_yolo_export_boxes(&yolo->desc, out_dev, last->output, NULL));
+			else if (last->type == DENSE) CB_CHECK(cb200_export_dense(out_dev, last->output, net->dtype, net->batch_size, c, 0.0f, NULL));
 			else CB_CHECK(cb200_export_cbhw(out_dev, last->output, net->dtype, net->batch_size, c, h, w, NULL));
 			CB_CHECK(cb200_d2h(out_host, out_dev, out_elems * sizeof(float), NULL));
 		}
 		CB_CHECK(cb200_stream_sync(NULL));
 		if (!net->no_error) for (k = 0; k < net->length; k++) total_error += net->loss_host[k];
+		if (!net->no_error && yolo != NULL) {
+			/* loss split and association statistics of the batch (src/auxil.c:1429-1486) */
+			size_t m, nm = (size_t)net->batch_size * h * w * yolo->nb_box;
+			for (k = 0; k < net->length * 6; k++) part_err[k % 6] += yolo->parts_host[k];
+			for (m = 0; m < nm; m++)
+				if (yolo->monitor_host[2 * m] > -0.98f) {
+					nb_IoU++;
+					sum_obj += yolo->monitor_host[2 * m];
+					sum_IoU += yolo->monitor_host[2 * m + 1];
+					if (yolo->monitor_host[2 * m + 1] >= net->y_param->IoU_limits[0]) nb_good_IoU++;
+				}
+		}
 		if (saving > 0) {
 			/* one line / record per sample, sample-major like upstream's fwd_res files (src/auxil.c:1346-1400) */
 			int b, o, per = last->type == DENSE ? c : c * h * w;
@@ -631,7 +668,23 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		printf("\n%*s", 14, " ");
 		printf("Average forward perf: %0.2f it/s |", net->last_items_per_s);
 		if (!net->no_error) printf(" Cumulated error: \t %g", net->last_epoch_loss);
+		if (!net->no_error && yolo != NULL && data.size > 0)
+			printf("\nLoss dist. ||Pos: %.5f |Size: %.5f |Prob: %.5f |Obj: %.5f |Class: %.5f |Param: %.5f ||M IoU = %.4f |M Obj = %0.4f |P Good = %0.4f",
+				part_err[0] / data.size, part_err[1] / data.size, part_err[2] / data.size, part_err[3] / data.size, part_err[4] / data.size,
+				part_err[5] / data.size, sum_IoU / nb_IoU, sum_obj / nb_IoU, (float)nb_good_IoU / (float)nb_IoU);
 		printf("\n");
+	}
+	if (net->no_error == 0 && silent != 1) {
+		/* learning-curve file, same columns as upstream (src/auxil.c:1528-1547) */
+		FILE *f_err = fopen("error.txt", "a");
+		if (f_err != NULL) {
+			fprintf(f_err, "%d %g", net->iter, net->last_epoch_loss);
+			if (yolo != NULL && data.size > 0)
+				fprintf(f_err, " %g %g %g %g %g %g", part_err[0] / data.size, part_err[1] / data.size, part_err[2] / data.size,
+					part_err[3] / data.size, part_err[4] / data.size, part_err[5] / data.size);
+			fprintf(f_err, "\n");
+			fclose(f_err);
+		}
 	}
 	if (f_save != NULL) { fclose(f_save); cb200_free(out_dev); cb200_host_free(out_host); }
 }
@@ -867,6 +920,51 @@ void cb_swap_data_buffers(network *net, const char *name)
 	a = cb_net_dataset(net, name);
 	b = cb_net_dataset(net, buf_name);
 	tmp = *a; *a = *b; *b = tmp;
+}
+/* ---- YOLO read-backs (bindings, parity tests) */
+static yolo_param *yolo_of(network *net)
+{
+	layer *last = net->net_layers[net->nb_layers - 1];
+	if (last->activation_type != YOLO) { printf("ERROR: the last layer is not a YOLO layer\n"); exit(EXIT_FAILURE); }
+	return (yolo_param *)last->activ_param;
+}
+void cb_yolo_set_seed(network *net, unsigned long long seed) { yolo_param *y = yolo_of(net); y->seed = seed; y->step = 0; }
+void cb_yolo_box_state(network *net, int *dst)
+{
+	yolo_param *y = yolo_of(net);
+	CB_CHECK(cb200_d2h(dst, y->box_state_dev, (size_t)net->batch_size * y->desc.grid_h * y->desc.grid_w * y->nb_box * sizeof(int), NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+}
+/* split of the last cb_batch_loss: parts6 = sums over the batch's samples / length, monitor = raw [B][cells][nb_box][2] */
+void cb_yolo_loss_parts(network *net, float *parts6, float *monitor)
+{
+	yolo_param *y = yolo_of(net);
+	int k;
+	CB_CHECK(cb200_d2h(y->parts_host, y->parts_dev, (size_t)net->batch_size * 6 * sizeof(float), NULL));
+	if (monitor != NULL)
+		CB_CHECK(cb200_d2h(monitor, y->monitor_dev, (size_t)net->batch_size * y->desc.grid_h * y->desc.grid_w * y->nb_box * 2 * sizeof(float), NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+	for (k = 0; k < 6; k++) parts6[k] = 0.0f;
+	for (k = 0; k < net->length * 6; k++) parts6[k % 6] += y->parts_host[k] / net->length;
+}
+void cb_yolo_export_boxes(network *net, float *dst)
+{
+	yolo_param *y = yolo_of(net);
+	layer *last = net->net_layers[net->nb_layers - 1];
+	size_t n = (size_t)net->batch_size * last->out_c * last->out_h * last->out_w;
+	float *tmp = NULL;
+	CB_CHECK(cb200_malloc((void **)&tmp, n * sizeof(float)));
+	CB_CHECK(cb200_yolo_export_boxes(&y->desc, tmp, last->output, NULL));
+	CB_CHECK(cb200_d2h(dst, tmp, n * sizeof(float), NULL));
+	CB_CHECK(cb200_stream_sync(NULL));
+	cb200_free(tmp);
+}
+/* epoch counter (and, when no TRAIN dataset is loaded, the dataset size) seen by the YOLO association pass:
+ * it leaves its random start-up phase once iter * train.size > rand_startup (src/activ_functions.c:3006-3015) */
+void cb_net_set_iter(network *net, int iter, int train_size)
+{
+	net->iter = iter;
+	if (train_size > 0 && net->train.input == NULL) net->train.size = train_size;
 }
 void cb_net_in_dims(network *net, int *out4) { int i; for (i = 0; i < 4; i++) out4[i] = net->in_dims[i]; }
 /* loss scaling is only honoured by the FP16 mode (upstream cuda_set_TC_scale_factor, src/cuda/cuda_main.cu:63-76) */

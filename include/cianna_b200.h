@@ -316,6 +316,63 @@ int cb200_output_delta(void* delta, const void* y, const void* target, int dtype
 int cb200_output_loss(float* loss, const void* y, const void* target, int dtype,
                       int batch, int length, int c, int h, int w, int kind, void* stream);
 
+/* ------------------------------------------------------------------ YOLO output layer */
+/* Detection head of the reference (src/activ_functions.c:970-1477 for the parameters,
+ * src/cuda/cuda_activ_functions.cu:477-597 activation, :700-1406 association + error signal,
+ * :1409-2075 loss monitor).  The last conv layer carries nb_box*(8+nb_class+nb_param) filters; per box:
+ * [x y z | w h d | prob | objectness | classes.. | params..].  Tensors are in internal layout
+ * [B][gh][gw][Cp]; the target batch keeps the reference layout, one row per image,
+ * [n_obj, (class, x0, y0, z0, x1, y1, z1, params.., (difficult))...] of target_stride values, stored
+ * in `dtype` like upstream.  All tables below are plain values; the three pointers are DEVICE arrays. */
+enum { CB200_IOU = 0, CB200_GIOU = 1, CB200_DIOU = 2, CB200_DIOU2 = 3 };           /* src/structs.h:40 */
+enum { CB200_DIST_IOU = 0, CB200_DIST_SIZE = 1, CB200_DIST_OFFSET = 2 };            /* src/structs.h:41 */
+enum { CB200_ERR_COMPLETE = 0, CB200_ERR_NATURAL = 1 };                             /* src/structs.h:42 */
+#define CB200_YOLO_MAX_BOX 32
+typedef struct {
+	int dtype;
+	int batch, length;
+	int grid_h, grid_w;                   /* nb_area[1], nb_area[0] of the last conv layer */
+	int nb_box, nb_class, nb_param;
+	int max_nb_obj;                       /* max_nb_obj_per_image */
+	int target_stride;                    /* values per image in the target batch: 1+max_nb_obj*(7+nb_param+diff_flag) */
+	int fit_dim;
+	int IoU_type, prior_dist_type, error_type;
+	int class_softmax, diff_flag;
+	int strict_box_size_association;
+	int rand_startup;
+	float rand_prob_best_box_assoc, rand_prob, min_prior_forced_scaling;
+	int cell_size[3];                     /* in_dims[i] / nb_area[i] (third = depth, 1 grid cell) */
+	float scale_tab[6];                   /* pos, size, prob, obj, class, param */
+	float slopes_and_maxes[18];           /* [6][slope, max, min] */
+	float IoU_limits[8];
+	int fit_parts[6];
+	const float* prior_size;              /* device [nb_box][3], already clamped to >= 1 */
+	const float* noobj_prob_prior;        /* device [nb_box] */
+	const float* param_ind_scale;         /* device [nb_param] (may be NULL when nb_param == 0) */
+} cb200_yolo_desc;
+/* FP32 scratch shared by the two association passes: [batch][max_nb_obj][nb_box + 1] */
+size_t cb200_yolo_workspace_bytes(const cb200_yolo_desc* d);
+/* in place on the linear output of the last convolution.  Replaces YOLO_activation_kernel (:477-597). */
+int cb200_yolo_activation(const cb200_yolo_desc* d, void* y, void* stream);
+/* target association + error signal delta (already multiplied by the activation derivative and by
+ * tc_scale; zero for b >= length and for pad channels).  nb_im_iter = iter * train.size drives the
+ * random start-up phase; seed/step select the draw of the counter-based generator used by the random
+ * association branches (upstream: curand states seeded with time(NULL)).  box_state (optional, device
+ * int32 [B][gh*gw][nb_box]) receives upstream's box_locked values: 0 background, 1 good-but-not-best,
+ * 2 associated.  Replaces YOLO_deriv_error_kernel (:700-1406). */
+int cb200_yolo_delta(const cb200_yolo_desc* d, void* delta, const void* y, const void* target,
+                     float tc_scale, long long nb_im_iter, unsigned long long seed, unsigned long long step,
+                     int* box_state, float* workspace, void* stream);
+/* loss monitor: loss[b] = sum of the image's per-element YOLO errors; parts (optional) FP32 [batch][6] =
+ * the same sum split into position/size/probability/objectness/class/param; monitor (optional) FP32
+ * [B][gh*gw][nb_box][2] = (objectness, IoU) of each associated box, -1 elsewhere (upstream IoU_monitor).
+ * Replaces YOLO_error_kernel (:1409-2075) + the host-side sums of src/auxil.c:1429-1486. */
+int cb200_yolo_loss(const cb200_yolo_desc* d, float* loss, float* parts, float* monitor, const void* y,
+                    const void* target, float* workspace, void* stream);
+/* decoded boxes for a forward pass written in the reference's [C][B][gh*gw] FP32 layout
+ * (x0,y0,z0,x1,y1,z1 in pixels, then prob, objectness, classes, params), src/auxil.c:1304-1344. */
+int cb200_yolo_export_boxes(const cb200_yolo_desc* d, float* dst, const void* y, void* stream);
+
 /* ------------------------------------------------------------------ data parallel (NCCL) */
 /* One process per GPU.  Rank 0 creates the id (128 bytes) and ships it to the others through any
  * side channel (torch.distributed store, MPI, a file); then every rank calls cb200_dp_init.

@@ -37,6 +37,17 @@ def build_network(cnn, spec, comp_meth, mixed_precision="off", network=None, dyn
     cnn.init(in_dim=i_ar(spec["in_dim"]), in_nb_ch=spec["in_ch"], out_dim=spec["out_dim"], bias=spec.get("bias", 0.1),
              b_size=spec["batch"], comp_meth=comp_meth, dynamic_load=dynamic_load, mixed_precision=mixed_precision,
              inference_only=inference_only, no_logo=1, **kw)
+    if "yolo" in spec:
+        # YOLO head set-up goes between init and the layers on both sides (upstream ex. scripts do the same)
+        y = dict(spec["yolo"])
+        if "prior_size" in y:
+            y["prior_size"] = np.ascontiguousarray(y["prior_size"], dtype=np.float32)
+        for key in ("prior_noobj_prob", "error_scales", "slopes_and_maxes", "param_ind_scales", "IoU_limits"):
+            if key in y:
+                y[key] = np.ascontiguousarray(y[key], dtype=np.float32)
+        if "fit_parts" in y:
+            y["fit_parts"] = np.ascontiguousarray(y["fit_parts"], dtype=np.int32)
+        cnn.set_yolo_params(network=0 if network is None else network, **y)
     for kind, a in spec["layers"]:
         a = dict(a)
         for key in ("f_size", "stride", "padding", "int_padding", "p_size"):
@@ -169,6 +180,72 @@ class RefNet:
         err = np.zeros(self.B * out_size, dtype=np.float32)
         self.lib.probe_loss(0, t.ctypes.data_as(ctypes.c_void_p), err.ctypes.data_as(ctypes.c_void_p), out_size)
         return err.reshape(shape)
+
+
+    # ---- YOLO output layer
+    def set_iter(self, it, train_size):
+        self.lib.probe_set_iter(0, int(it), int(train_size))
+
+    def _yolo_array(self, what, shape, dtype):
+        self.lib.probe_yolo_ptr.restype = ctypes.c_void_p
+        p = self.lib.probe_yolo_ptr(0, what)
+        ct = ctypes.c_float if dtype == np.float32 else ctypes.c_int
+        return np.frombuffer((ct * int(np.prod(shape))).from_address(p), dtype=dtype).reshape(shape).copy()
+
+    def yolo_monitor(self, nb_box):
+        """[B][cells][nb_box][2] (objectness, IoU) of the associated boxes after loss(), -1 elsewhere"""
+        cells = self.out_shape(self.n_layers - 1)[2]
+        return self._yolo_array(0, (self.B, cells, nb_box, 2), np.float32)
+
+    def yolo_box_state(self, nb_box):
+        """[B][cells][nb_box] upstream box_locked after the last association pass"""
+        cells = self.out_shape(self.n_layers - 1)[2]
+        return self._yolo_array(1, (self.B, cells, nb_box), np.int32)
+
+    def set_last_output(self, x):
+        l = self.n_layers - 1
+        self._array(l, 0, self.out_shape(l))[...] = x
+
+    def last_activation(self, length=None):
+        self.lib.probe_last_activation(0, self.B if length is None else int(length))
+
+    def last_deriv_error(self, targets, length=None):
+        t = np.ascontiguousarray(targets, dtype=np.float32)
+        self._keep.append(t)
+        self.lib.probe_last_deriv_error.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        self.lib.probe_last_deriv_error(0, t.ctypes.data_as(ctypes.c_void_p), self.B if length is None else int(length))
+
+
+def make_yolo_targets(spec, seed, n_obj=None, fill=0.0):
+    """seeded target rows [B][1 + max_nb_obj*(7+nb_param+diff_flag)]: boxes inside the image whose sizes scatter around the
+    priors, classes in 1..nb_class, params in [0,1), difficult flags in 0..3 when enabled"""
+    rng = np.random.default_rng(seed)
+    y = spec["yolo"]
+    B = spec["batch"]
+    W, H = spec["in_dim"]
+    nb_param, diff = y.get("nb_param", 0), y.get("diff_flag", 0)
+    per = 7 + nb_param + diff
+    max_obj = y["max_nb_obj_per_image"]
+    prior = np.asarray(y["prior_size"], dtype=np.float32)       # [dims][nb_box]
+    t = np.full((B, 1 + max_obj * per), fill, dtype=np.float32)
+    for b in range(B):
+        n = int(rng.integers(0, max_obj + 1)) if n_obj is None else int(n_obj)
+        t[b, 0] = n
+        for j in range(n):
+            k = int(rng.integers(0, prior.shape[1]))
+            w = float(prior[0, k]) * float(np.exp(rng.normal(0, 0.35)))
+            h = float(prior[1, k]) * float(np.exp(rng.normal(0, 0.35)))
+            w, h = min(w, W - 1.0), min(h, H - 1.0)
+            cx = float(rng.uniform(w / 2, W - w / 2))
+            cy = float(rng.uniform(h / 2, H - h / 2))
+            row = t[b, 1 + j * per: 1 + (j + 1) * per]
+            row[0] = rng.integers(1, max(1, y.get("nb_class", 0)) + 1)
+            row[1:7] = (cx - w / 2, cy - h / 2, 0.0, cx + w / 2, cy + h / 2, 1.0)
+            if nb_param:
+                row[7:7 + nb_param] = rng.random(nb_param)
+            if diff:
+                row[7 + nb_param] = rng.integers(0, 4)
+    return t
 
 
 def make_inputs(spec, seed, scale=1.0):

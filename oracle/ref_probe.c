@@ -149,3 +149,43 @@ void probe_reset(void)
 	/* forget all networks so that a test can build a fresh one with id 0 (nothing is freed upstream either) */
 	nb_networks = 0;
 }
+
+/* -------- YOLO output layer (src/activ_functions.c:970-2985) ------------ */
+/* the association pass looks at iter * train.size to leave its random start-up phase */
+void probe_set_iter(int net_id, int iter, int train_size)
+{
+	networks[net_id]->iter = iter;
+	networks[net_id]->train.size = train_size;
+}
+
+/* what: 0 IoU_monitor [B*cells][nb_box][2], 1 box_locked (int) [B*cells][nb_box], 2 prior_size [nb_box][3],
+ * 3 cell_size (int) [3] - arrays of the last layer's own yolo_param copy */
+void* probe_yolo_ptr(int net_id, int what)
+{
+	network *net = networks[net_id];
+	yolo_param *a = (yolo_param*) net->net_layers[net->nb_layers-1]->activ_param;
+	if(a == NULL) return NULL;
+	if(what == 0) return a->IoU_monitor;
+	if(what == 1) return a->box_locked;
+	if(what == 2) return a->prior_size;
+	if(what == 3) return a->cell_size;
+	return NULL;
+}
+
+/* kernel-level driving of the output layer: the caller writes raw values into the last layer's output buffer
+ * (probe_ptr what=0), then runs only its activation / only its error signal */
+void probe_last_activation(int net_id, int length)
+{
+	network *net = networks[net_id];
+	layer *last = net->net_layers[net->nb_layers-1];
+	net->length = length;
+	last->activation(last);
+}
+
+void probe_last_deriv_error(int net_id, float *target, int length)
+{
+	network *net = networks[net_id];
+	net->target = target;
+	net->length = length;
+	output_deriv_error(net->net_layers[net->nb_layers-1]);
+}

@@ -1,0 +1,307 @@
+"""GPU parity of the YOLO output head.
+
+Kernel level (through the C-ABI: cb200_yolo_activation / _delta / _loss / _export_boxes):
+  * against tests/golden/yolo_*.npz - raw head values and target rows run through the compiled reference
+    (tests/golden/make_golden_yolo.py) for six set-ups covering the four overlap measures, the three prior distances,
+    strict association, low-IoU re-association, difficult flags, class-only images, softmax classes, user tables;
+  * against the restatement oracle/yolo_oracle.py (pinned to the same fixtures) on fresh seeds, and for BF16 storage;
+  * against the compiled reference itself, live, when oracle/_ref is on the box.
+Network level (cianna_b200.CIANNA public API): a small detector trained for three steps next to the reference, and the
+binary checkpoint (which carries the YOLO block) exchanged both ways.
+
+Bar: the box <-> target association (upstream's box_locked states, and which boxes the IoU monitor reports) is integer
+work and must be IDENTICAL whenever both sides read the same values; floating point: 1e-5 of the tensor's max in FP32,
+2e-2 with FP16 / BF16 storage (measured: ~1e-3 / ~8e-3, the rounding of the stored delta).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_driver as rd
+from oracle import yolo_oracle as yo
+from tests import netdefs
+from tests.common import GOLDEN_DIR, ref_available, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DT = {"off": 0, "FP16C_FP32A": 1, "BF16C_FP32A": 2}
+TOL = {"off": 1e-5, "FP16C_FP32A": 2e-2, "BF16C_FP32A": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from cianna_b200 import cabi as m
+    m.init_device(0)
+    return m
+
+
+@pytest.fixture(scope="module")
+def cnn():
+    from cianna_b200 import CIANNA as m
+    return m
+
+
+def rz(a, mode):
+    """FP32 -> storage type, round toward zero (the dataset cast) -> FP32"""
+    a = np.asarray(a, dtype=np.float32)
+    if mode == "off":
+        return a
+    if mode == "FP16C_FP32A":
+        h = a.astype(np.float16)
+        over = np.abs(h.astype(np.float32)) > np.abs(a)
+        return np.where(over, np.nextafter(h, np.float16(0)), h).astype(np.float32)
+    return (a.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def rn(a, mode):
+    """FP32 -> storage type, round to nearest even -> FP32 (what a kernel's store does)"""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if mode == "off":
+        return a
+    if mode == "FP16C_FP32A":
+        return a.astype(np.float16).astype(np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def _head(cabi, spec, mode, length=None):
+    st = spec["layers"][0][1]["stride"]
+    gw, gh = spec["in_dim"][0] // st[0], spec["in_dim"][1] // st[1]
+    return cabi.YoloHead(DT[mode], spec["batch"], gh, gw, spec["in_dim"][0], spec["in_dim"][1], spec["yolo"], length=length), (gw, gh)
+
+
+def _sums(e, per, nb_class, nb_param):
+    """per-element loss [C][B][cells] -> (loss[B], parts[B][6])"""
+    C, B, _ = e.shape
+    col = np.arange(C) % per
+    part = np.where(col < 3, 0, np.where(col < 6, 1, np.where(col == 6, 2, np.where(col == 7, 3, np.where(col < 8 + nb_class, 4, 5)))))
+    parts = np.zeros((B, 6), dtype=np.float64)
+    for p in range(6):
+        parts[:, p] = e[part == p].sum(axis=(0, 2), dtype=np.float64)
+    return parts.sum(axis=1), parts
+
+
+def _check_head(cabi, spec, mode, x, t, a_ref, delta_ref, state_ref, loss_ref, mon_ref, tc_scale=1.0):
+    """a_ref .. mon_ref: what the reference side makes of (x, t); for 16-bit modes they were computed from rn(a_ref) / rz(t)"""
+    head, (gw, gh) = _head(cabi, spec, mode)
+    B, C = spec["batch"], head.C
+    s = yo.YoloSetup(spec["yolo"], spec["in_dim"], (gw, gh))
+    # activation, in place on the raw values
+    ybuf = cabi.upload_act(x, DT[mode], B, C, gh, gw)
+    head.activation(ybuf)
+    a = cabi.download_act(ybuf, DT[mode], B, C, gh, gw)
+    assert rel_err(a, a_ref) < {"off": 2e-6, "FP16C_FP32A": 2e-3, "BF16C_FP32A": 1.2e-2}[mode]   # input and output rounding
+    ybuf.free()
+    # association + error signal on the reference's activated values, so that both sides read the same numbers
+    ybuf = cabi.upload_act(rn(a_ref, mode), DT[mode], B, C, gh, gw)
+    tbuf = head.upload_targets(t)
+    delta, state = head.deriv_error(ybuf, tbuf, tc_scale=tc_scale)
+    assert np.array_equal(state, state_ref), "box <-> target association differs (%d boxes)" % int((state != state_ref).sum())
+    assert rel_err(delta / tc_scale, delta_ref) < TOL[mode]
+    # loss monitor
+    loss, parts, mon = head.loss(ybuf, tbuf)
+    assert np.array_equal(mon[..., 0] > -0.98, mon_ref[..., 0] > -0.98), "IoU monitor reports other boxes"
+    assert rel_err(mon, mon_ref) < (1e-5 if mode == "off" else 1e-3)
+    want_loss, want_parts = _sums(loss_ref, s.per, s.nb_class, s.nb_param)
+    assert rel_err(loss, want_loss) < 1e-5
+    assert rel_err(parts, want_parts) < 1e-5
+    ybuf.free(); tbuf.free()
+    return float(rel_err(delta / tc_scale, delta_ref))
+
+
+@pytest.mark.parametrize("mode", ["off", "FP16C_FP32A"])
+@pytest.mark.parametrize("name", netdefs.YOLO_HEAD_CASES)
+def test_yolo_head_matches_golden(cabi, name, mode):
+    spec = netdefs.yolo_head(name)
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "yolo_%s.npz" % name)))
+    sfx = "" if mode == "off" else "_h"
+    _check_head(cabi, spec, mode, g["x"], g["t"], g["a"], g["delta" + sfx], g["state" + sfx], g["loss" + sfx], g["monitor" + sfx])
+
+
+@pytest.mark.parametrize("mode", ["off", "FP16C_FP32A", "BF16C_FP32A"])
+@pytest.mark.parametrize("name", netdefs.YOLO_HEAD_CASES)
+def test_yolo_head_matches_oracle_fresh_seeds(cabi, name, mode):
+    """new values, a partial batch, loss scaling; reference side = the restatement pinned by tests/test_oracle.py"""
+    spec = netdefs.yolo_head(name, batch=5)
+    st = spec["layers"][0][1]["stride"]
+    grid = (spec["in_dim"][0] // st[0], spec["in_dim"][1] // st[1])
+    s = yo.YoloSetup(spec["yolo"], spec["in_dim"], grid)
+    C = s.nb_box * s.per
+    for seed in (21, 22):
+        rng = np.random.default_rng(seed)
+        x = (1.5 * rng.standard_normal((C, 5, grid[0] * grid[1]))).astype(np.float32)
+        t = rd.make_yolo_targets(spec, seed + 100)
+        a = yo.activation(s, x)
+        ar, tr = rn(a, mode), rz(t, mode)
+        d, state = yo.run(s, ar, tr, "delta")
+        e, mon = yo.run(s, ar, tr, "loss")
+        _check_head(cabi, spec, mode, x, t, a, d, state, e, mon, tc_scale=16.0 if mode == "FP16C_FP32A" else 1.0)
+
+
+def test_yolo_partial_batch_and_boxes(cabi):
+    """length < batch: the trailing images get a zero error signal, no loss, an empty monitor; decoded boxes follow
+    the forward-save formula of upstream (src/auxil.c:1304-1344)"""
+    spec = netdefs.yolo_head("giou_default", batch=4)
+    head, (gw, gh) = _head(cabi, spec, "off", length=3)
+    s = yo.YoloSetup(spec["yolo"], spec["in_dim"], (gw, gh))
+    rng = np.random.default_rng(5)
+    x = (1.5 * rng.standard_normal((head.C, 4, gw * gh))).astype(np.float32)
+    t = rd.make_yolo_targets(spec, 6, n_obj=4)
+    a = yo.activation(s, x)
+    ybuf = cabi.upload_act(a, 0, 4, head.C, gh, gw)
+    tbuf = head.upload_targets(t)
+    delta, state = head.deriv_error(ybuf, tbuf)
+    loss, parts, mon = head.loss(ybuf, tbuf)
+    d_ref, st_ref = yo.run(s, a, t, "delta")
+    assert np.array_equal(state[:3], st_ref[:3]) and rel_err(delta[:, :3], d_ref[:, :3]) < 1e-5
+    assert not delta[:, 3].any() and not state[3].any() and loss[3] == 0.0 and np.all(mon[3] == -1.0)
+    boxes = head.boxes(ybuf)
+    cell = np.arange(gw * gh)
+    gx, gy = (cell % gw).astype(np.float32), (cell // gw).astype(np.float32)
+    for k in range(s.nb_box):
+        o = k * s.per
+        cx = (a[o] + gx) * s.cell[0]
+        cy = (a[o + 1] + gy) * s.cell[1]
+        hw, hh = 0.5 * s.prior[k, 0] * np.exp(a[o + 3]), 0.5 * s.prior[k, 1] * np.exp(a[o + 4])
+        assert rel_err(boxes[o], cx - hw) < 1e-5 and rel_err(boxes[o + 3], cx + hw) < 1e-5
+        assert rel_err(boxes[o + 1], cy - hh) < 1e-5 and rel_err(boxes[o + 4], cy + hh) < 1e-5
+        assert np.array_equal(boxes[o + 6: o + s.per], a[o + 6: o + s.per])
+
+
+def test_yolo_random_association_is_seeded_and_valid(cabi):
+    """start-up phase (nb_im_iter <= rand_startup): every owned target takes a random free box. The draw is reproducible
+    for a given (seed, step), changes with the step, never gives one box to two targets, and trains as many boxes as the
+    deterministic pass does in cells that are not over-subscribed."""
+    spec = netdefs.yolo_head("giou_default", batch=4)
+    spec["yolo"] = dict(spec["yolo"], rand_startup=1000)
+    head, (gw, gh) = _head(cabi, spec, "off")
+    s = yo.YoloSetup(spec["yolo"], spec["in_dim"], (gw, gh))
+    rng = np.random.default_rng(9)
+    a = yo.activation(s, (1.5 * rng.standard_normal((head.C, 4, gw * gh))).astype(np.float32))
+    t = rd.make_yolo_targets(spec, 10, n_obj=5)
+    ybuf, tbuf = cabi.upload_act(a, 0, 4, head.C, gh, gw), head.upload_targets(t)
+    d1, s1 = head.deriv_error(ybuf, tbuf, nb_im_iter=10, seed=77, step=3)
+    d2, s2 = head.deriv_error(ybuf, tbuf, nb_im_iter=10, seed=77, step=3)
+    d3, s3 = head.deriv_error(ybuf, tbuf, nb_im_iter=10, seed=77, step=4)
+    _, s_det = head.deriv_error(ybuf, tbuf, nb_im_iter=10**9)
+    assert np.array_equal(s1, s2) and np.array_equal(d1, d2)
+    assert not np.array_equal(s1, s3)
+    # a cell never trains more boxes than it owns targets, and (nearly) every target finds a box
+    per = s.tlen
+    owned = np.zeros((4, gw * gh), dtype=np.int64)
+    for b in range(4):
+        for j in range(int(t[b, 0])):
+            row = t[b, 1 + j * per: 1 + (j + 1) * per]
+            owned[b, int((row[5] + row[2]) * 0.5 / s.cell[1]) * gw + int((row[4] + row[1]) * 0.5 / s.cell[0])] += 1
+    for st in (s1, s3, s_det):
+        assert np.all((st == 2).sum(axis=2) <= owned)
+        assert (st == 2).sum() >= 0.8 * owned.sum()
+
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not present on this box")
+@pytest.mark.parametrize("name", netdefs.YOLO_HEAD_CASES)
+def test_yolo_head_matches_live_reference(cabi, name):
+    spec = netdefs.yolo_head(name)
+    ref = rd.RefNet(spec, "C_BLAS")
+    ref.set_iter(1, spec["batch"])
+    last = ref.n_layers - 1
+    nb_box = spec["yolo"]["nb_box"]
+    rng = np.random.default_rng(31)
+    x = (1.5 * rng.standard_normal(ref.out_shape(last))).astype(np.float32)
+    t = rd.make_yolo_targets(spec, 32)
+    ref.set_last_output(x)
+    ref.last_activation()
+    a = ref.output(last)
+    ref.last_deriv_error(t)
+    delta, state = ref.delta(last), ref.yolo_box_state(nb_box)
+    ref.set_last_output(a)
+    loss = ref.loss(t)
+    _check_head(cabi, spec, "off", x, t, a, delta, state, loss, ref.yolo_monitor(nb_box))
+
+
+def _build(cnn, spec, mode):
+    with rd._Quiet():
+        rd.build_network(cnn, spec, "C_CUDA", mode, network=0)
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not present on this box")
+@pytest.mark.parametrize("mode", ["off", "FP16C_FP32A"])
+def test_yolo_network_training_matches_live_reference(cnn, mode):
+    """the whole detector through the public API: three SGD steps with momentum and weight decay next to the reference"""
+    spec = netdefs.yolo_net()
+    kinds = [k for k, _ in spec["layers"]]
+    nb_box = spec["yolo"]["nb_box"]
+    ref = rd.RefNet(spec, "C_BLAS")
+    ref.set_iter(1, spec["batch"])
+    _build(cnn, spec, mode)
+    cnn.set_iter(1, train_size=spec["batch"], network=0)
+    S = 32.0 if mode == "FP16C_FP32A" else 1.0
+    cnn.set_TC_scale_factor(S, network=0)
+    for i, k in enumerate(kinds):
+        if k == "conv":
+            cnn.set_layer_weights(i, ref.weights_view(i))
+    last = len(kinds) - 1
+    tol = TOL[mode] * 3
+    for step in range(3):
+        x, _ = rd.make_inputs(spec, 200 + step)
+        t = rd.make_yolo_targets(spec, 300 + step)
+        if mode != "off":
+            t = rz(t, mode)      # both sides see the target values the 16-bit dataset holds
+        ref.forward(x)
+        cnn.load_batch(x, t)
+        cnn.forward_batch()
+        assert rel_err(cnn.layer_output(last), ref.output(last)) < tol, step
+        want = float(ref.loss(t).sum() / spec["batch"])
+        assert abs(cnn.batch_loss() - want) < tol * max(want, 1.0), step
+        ref.backward(t, 0.02, 0.9, 0.0005)
+        cnn.backward_batch(0.02, 0.9, 0.0005)
+        state, state_ref = cnn.yolo_box_state(nb_box), ref.yolo_box_state(nb_box)
+        if mode == "off":
+            assert np.array_equal(state, state_ref), step
+            assert rel_err(cnn.layer_delta(last) / S, ref.delta(last)) < tol, step
+        else:
+            # 16-bit activations may move an overlap across a threshold: count, do not hide
+            assert (state != state_ref).mean() < 0.02, step
+    for i, k in enumerate(kinds):
+        if k == "conv":
+            e = rel_err(cnn.layer_weights(i), ref.weights_view(i))
+            assert e < tol, (i, e)
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not present on this box")
+def test_yolo_checkpoint_is_interchangeable(cnn, tmp_path, monkeypatch):
+    """binary save with the YOLO block (src/conv_layer.c:442-456, :571-650): product -> reference -> product"""
+    monkeypatch.chdir(tmp_path)
+    spec = netdefs.yolo_net()
+    kinds = [k for k, _ in spec["layers"]]
+    _build(cnn, spec, "off")
+    x, _ = rd.make_inputs(spec, 1)
+    t = rd.make_yolo_targets(spec, 2)
+    cnn.load_batch(x, t)
+    cnn.forward_batch()
+    last = len(kinds) - 1
+    out_mine = cnn.layer_output(last)
+    with rd._Quiet():
+        cnn.save("mine.dat", network=0, bin=1)
+    ref_cnn, lib = rd.ref_loader.load("serial")
+    lib.probe_reset()
+    y = dict(spec["yolo"])
+    y["prior_size"] = np.ascontiguousarray(y["prior_size"], dtype=np.float32)
+    with rd._Quiet():
+        ref_cnn.init(in_dim=rd.i_ar(spec["in_dim"]), in_nb_ch=3, out_dim=spec["out_dim"], bias=0.1, b_size=spec["batch"],
+                     comp_meth="C_BLAS", no_logo=1, network=0)
+        ref_cnn.set_yolo_params(network=0, **y)
+        ref_cnn.load("mine.dat", 0, network=0, bin=1)
+        ref_cnn.save("theirs.dat", network=0, bin=1)
+    assert os.path.getsize("mine.dat") == os.path.getsize("theirs.dat")
+    with rd._Quiet():
+        cnn.init(in_dim=rd.i_ar(spec["in_dim"]), in_nb_ch=3, out_dim=spec["out_dim"], bias=0.1, b_size=spec["batch"],
+                 comp_meth="C_CUDA", no_logo=1, network=0)
+        cnn.set_yolo_params(network=0, **y)
+        cnn.load("theirs.dat", 0, network=0, bin=1)
+    cnn.load_batch(x, t)
+    cnn.forward_batch()
+    assert np.array_equal(cnn.layer_output(last), out_mine)

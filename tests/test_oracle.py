@@ -79,3 +79,86 @@ def test_golden_fixture_integrity():
     assert int(g["length"][0]) == 3
     assert np.all(g["out_0"][:, 3:, :] == 0)          # RELU conv output of the padded sample
     assert np.all(g["delta_%d" % 11][:, 3:, :] == 0)
+
+
+# ---- YOLO output head: the restatement (oracle/yolo_oracle.py) against fixtures made by the compiled reference
+from oracle import yolo_oracle as yo  # noqa: E402
+from tests import netdefs  # noqa: E402
+
+
+def _yolo_case(name):
+    spec = netdefs.yolo_head(name)
+    g = dict(np.load("%s/golden/yolo_%s.npz" % (__file__.rsplit("/", 1)[0], name)))
+    grid = (spec["in_dim"][0] // spec["layers"][0][1]["stride"][0], spec["in_dim"][1] // spec["layers"][0][1]["stride"][1])
+    return spec, g, yo.YoloSetup(spec["yolo"], spec["in_dim"], grid)
+
+
+@pytest.mark.parametrize("name", netdefs.YOLO_HEAD_CASES)
+def test_yolo_oracle_matches_golden(name):
+    spec, g, s = _yolo_case(name)
+    assert rel_err(yo.activation(s, g["x"]), g["a"]) < 1e-6
+    for sfx in ("", "_h"):
+        a = g["a"] if sfx == "" else g["a"].astype(np.float16).astype(np.float32)
+        t = g["t"] if sfx == "" else _rz16(g["t"])
+        d, st = yo.run(s, a, t, "delta")
+        assert np.array_equal(st, g["state" + sfx]), "box association differs"
+        assert rel_err(d, g["delta" + sfx]) < 1e-6
+        e, mon = yo.run(s, a, t, "loss")
+        assert np.array_equal(mon[..., 0] > -0.98, g["monitor" + sfx][..., 0] > -0.98)
+        assert rel_err(e, g["loss" + sfx]) < 1e-6
+        assert rel_err(mon, g["monitor" + sfx]) < 1e-6
+
+
+def _rz16(a):
+    a = np.asarray(a, dtype=np.float32)
+    h = a.astype(np.float16)
+    over = np.abs(h.astype(np.float32)) > np.abs(a)
+    return np.where(over, np.nextafter(h, np.float16(0)), h).astype(np.float32)
+
+
+def test_yolo_fixtures_exercise_every_association_branch():
+    """the fixtures are only worth something if they reach the branches: associated / good-but-not-best / background boxes,
+    strict prior sets, low-IoU re-association, difficult targets that are skipped, a class-only image, crowded cells"""
+    seen = {}
+    for name in netdefs.YOLO_HEAD_CASES:
+        spec, g, s = _yolo_case(name)
+        st = g["state"]
+        seen[name] = [int((st == v).sum()) for v in (0, 1, 2)]
+        assert seen[name][0] > 0 and seen[name][2] > 0, (name, seen[name])
+    assert sum(v[1] for v in seen.values()) > 5
+    spec, g, s = _yolo_case("giou_default")
+    assert g["t"][0, 0] == -1.0
+    spec, g, s = _yolo_case("single_box")
+    assert (g["state"] == 2).sum() < g["t"][:, 0].sum()          # more targets than boxes somewhere
+    spec, g, s = _yolo_case("diou2_difficult")
+    per = 7 + 1 + 1
+    nobj = g["t"][:, 0].astype(int)
+    flags = np.concatenate([g["t"][b, 1: 1 + nobj[b] * per].reshape(-1, per)[:, -1] for b in range(len(nobj))])
+    assert (flags > 0).any() and (g["state"] == 2).sum() < nobj.sum()
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not present on this box")
+@pytest.mark.parametrize("name", ["giou_default", "iou_strict", "custom_tables"])
+def test_yolo_oracle_matches_live_reference(name):
+    """fresh seeds against the compiled reference, incl. its end-to-end forward of the raw values"""
+    from oracle import ref_driver as rd
+    spec, _, s = _yolo_case(name)
+    ref = rd.RefNet(spec, "C_BLAS")
+    ref.set_iter(1, spec["batch"])
+    last = ref.n_layers - 1
+    for seed in (7, 8):
+        rng = np.random.default_rng(seed)
+        x = (1.5 * rng.standard_normal(ref.out_shape(last))).astype(np.float32)
+        t = rd.make_yolo_targets(spec, seed + 50)
+        ref.set_last_output(x)
+        ref.last_activation()
+        a = ref.output(last)
+        assert rel_err(yo.activation(s, x), a) < 1e-6
+        ref.last_deriv_error(t)
+        d, st = yo.run(s, a, t, "delta")
+        assert np.array_equal(st, ref.yolo_box_state(s.nb_box))
+        assert rel_err(d, ref.delta(last)) < 1e-6
+        ref.set_last_output(a)
+        e, mon = yo.run(s, a, t, "loss")
+        assert rel_err(e, ref.loss(t)) < 1e-6
+        assert rel_err(mon, ref.yolo_monitor(s.nb_box)) < 1e-6
