@@ -284,6 +284,7 @@ def test_yolo_checkpoint_is_interchangeable(cnn, tmp_path, monkeypatch):
     cnn.forward_batch()
     last = len(kinds) - 1
     out_mine = cnn.layer_output(last)
+    w_mine = {i: cnn.layer_weights(i) for i, k in enumerate(kinds) if k in ("conv", "norm")}
     with rd._Quiet():
         cnn.save("mine.dat", network=0, bin=1)
     ref_cnn, lib = rd.ref_loader.load("serial")
@@ -304,4 +305,7 @@ def test_yolo_checkpoint_is_interchangeable(cnn, tmp_path, monkeypatch):
         cnn.load("theirs.dat", 0, network=0, bin=1)
     cnn.load_batch(x, t)
     cnn.forward_batch()
-    assert np.array_equal(cnn.layer_output(last), out_mine)
+    for i, w in w_mine.items():
+        assert np.array_equal(cnn.layer_weights(i), w), i
+    # (group-norm statistics are accumulated with atomics: the forward pass is reproducible to rounding, not bitwise)
+    assert rel_err(cnn.layer_output(last), out_mine) < 1e-6
