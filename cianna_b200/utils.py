@@ -16,6 +16,8 @@ def build_network(cnn, spec, comp_meth="C_CUDA", mixed_precision="off", network=
     cnn.init(in_dim=i_ar(spec["in_dim"]), in_nb_ch=spec["in_ch"], out_dim=spec["out_dim"], bias=spec.get("bias", 0.1),
              b_size=spec["batch"], comp_meth=comp_meth, dynamic_load=dynamic_load, mixed_precision=mixed_precision,
              inference_only=inference_only, no_logo=1, **kw)
+    if "yolo" in spec:    # YOLO head set-up: between init and the layers, as in upstream's detection scripts
+        cnn.set_yolo_params(network=0 if network is None else network, **spec["yolo"])
     for kind, a in spec["layers"]:
         a = dict(a)
         for key in ("f_size", "stride", "padding", "int_padding", "p_size"):
