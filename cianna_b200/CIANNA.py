@@ -530,6 +530,11 @@ def yolo_boxes(network=None):
     return a
 
 
+def set_fusion(on):
+    """group-norm + 2x2 max-pool fusion for the layers created from now on (default on)"""
+    _load().cb_set_fusion(int(on))
+
+
 def last_conv_impl():
     return core().cb200_last_conv_impl().decode()
 

@@ -281,6 +281,23 @@ class NormLayer:
                                         self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa, self.colsum.ptr, self.ws.ptr, None))
         return self.dx
 
+    def forward_pool(self, x_buf, pool):
+        """fused group-norm + 2x2 max-pool: writes pool.y / pool.map only"""
+        L = lib()
+        L.cb200_norm_pool_forward.argtypes = [ctypes.c_void_p] * 11
+        check(L.cb200_norm_pool_forward(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, pool.y.ptr, pool.map.ptr, self.gamma.ptr,
+                                        self.beta.ptr, self.mean.ptr, self.var.ptr, self.ws.ptr, None))
+        return pool.y
+
+    def backward_pool(self, x_buf, dpool_buf, pool, prev_act=None):
+        L = lib()
+        L.cb200_norm_pool_backward.argtypes = [ctypes.c_void_p] * 15
+        pa = ctypes.byref(prev_act) if prev_act is not None else None
+        check(L.cb200_norm_pool_backward(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, dpool_buf.ptr, pool.map.ptr, self.dx.ptr,
+                                         self.gamma.ptr, self.mean.ptr, self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa,
+                                         self.colsum.ptr, self.ws.ptr, None))
+        return self.dx
+
     def stats(self):
         shp = (self.d.batch, self.nb_group)
         return (self.mean.to_numpy(np.float32, shp), self.var.to_numpy(np.float32, shp),

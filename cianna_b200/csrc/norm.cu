@@ -30,6 +30,41 @@ static int norm_pix_per_block(int hw, int batch, int cv) {
 	return (int)ppb;
 }
 
+// Per-thread sums of one channel vector -> the block's per-group accumulators in shared memory.
+// Lanes of a warp that own the same channel vector (lanes_c < 32, a power of two) are summed by shuffles first, so
+// that only lanes_c lanes per warp touch the shared accumulators; then the 8 channels are folded into their groups
+// (a vector spans one group when group_size % 8 == 0).  Every lane of the warp must call this.
+__device__ __forceinline__ void fold_into_groups(float (&s0)[8], float (&s1)[8], int v, int lanes_c, const NormGeom& g, float* sm_acc) {
+	bool writer = true;
+	if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			for (int off = lanes_c; off < 32; off <<= 1) {
+				s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], off);
+				s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+			}
+		}
+		writer = (threadIdx.x & 31) < lanes_c;
+	}
+	if (writer) {
+		int cur = -1;
+		float g0 = 0.0f, g1 = 0.0f;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const int ch = v * 8 + j;
+			if (ch >= g.c) break;
+			const int grp = ch / g.group_size;
+			if (grp != cur) {
+				if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
+				cur = grp; g0 = 0.0f; g1 = 0.0f;
+			}
+			g0 += s0[j];
+			g1 += s1[j];
+		}
+		if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
+	}
+}
+
 // Accumulate, for every channel vector owned by the thread, sum(a) and sum(a*b) over the block's
 // pixel range; b == a gives (sum x, sum x^2), b == x with a == delta gives (sum d, sum d*x).
 // ws layout: double [batch][nb_group][2].
@@ -82,37 +117,7 @@ norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double
 					}
 				}
 			}
-			// lanes of a warp that own the same channel vector (lanes_c < 32, a power of two) are summed by shuffles
-			// first, so that only lanes_c lanes per warp touch the shared accumulators
-			bool writer = true;
-			if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
-#pragma unroll
-				for (int j = 0; j < 8; j++) {
-					for (int off = lanes_c; off < 32; off <<= 1) {
-						s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], off);
-						s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-					}
-				}
-				writer = (threadIdx.x & 31) < lanes_c;
-			}
-			// fold the 8 channels into their groups (a vector spans one group when group_size % 8 == 0)
-			if (writer) {
-				int cur = -1;
-				float g0 = 0.0f, g1 = 0.0f;
-#pragma unroll
-				for (int j = 0; j < 8; j++) {
-					const int ch = v * 8 + j;
-					if (ch >= g.c) break;
-					const int grp = ch / g.group_size;
-					if (grp != cur) {
-						if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
-						cur = grp; g0 = 0.0f; g1 = 0.0f;
-					}
-					g0 += s0[j];
-					g1 += s1[j];
-				}
-				if (cur >= 0 && cur < g.nb_group) { atomicAdd(&sm_acc[cur * 2], g0); atomicAdd(&sm_acc[cur * 2 + 1], g1); }
-			}
+			fold_into_groups(s0, s1, v, lanes_c, g, sm_acc);
 		}
 	}
 	__syncthreads();
@@ -187,7 +192,7 @@ norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
 				float xv[8], out[8];
 				unpack8(raw[u], xv);
 #pragma unroll
-				for (int j = 0; j < 8; j++) out[j] = xv[j] * sc[j] + sh[j];
+				for (int j = 0; j < 8; j++) out[j] = fmaf(xv[j], sc[j], sh[j]);
 				store8<T>(y + base + (long long)pp * g.cp, out);
 			}
 		}
@@ -294,15 +299,17 @@ norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __re
 	}
 }
 
-// gsum[0][g] = sum_b d_gamma[b][g], gsum[1][g] = sum_b d_beta[b][g]
+// gsum[0][g] = sum_b d_gamma[b][g], gsum[1][g] = sum_b d_beta[b][g]; one warp per group, lanes over the batch
 __global__ void norm_reduce_grads_kernel(const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
                                          float* __restrict__ gsum, int batch, int nb_group) {
-	const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+	const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (grp >= nb_group) return;
 	double sg = 0.0, sb = 0.0;
-	for (int b = 0; b < batch; b++) { sg += d_gamma[b * nb_group + grp]; sb += d_beta[b * nb_group + grp]; }
-	gsum[grp] = (float)sg;
-	gsum[nb_group + grp] = (float)sb;
+	for (int b = lane; b < batch; b += 32) { sg += d_gamma[b * nb_group + grp]; sb += d_beta[b * nb_group + grp]; }
+	sg = warp_sum(sg);
+	sb = warp_sum(sb);
+	if (lane == 0) { gsum[grp] = (float)sg; gsum[nb_group + grp] = (float)sb; }
 }
 
 // upd = mom*upd + lr*(sum/B) ; param -= upd/S     (hyper[0] = lr/B_total, hyper[3] = S)
@@ -318,6 +325,240 @@ __global__ void norm_update_kernel(float* __restrict__ gamma, float* __restrict_
 	beta_upd[grp] = bu;
 	gamma[grp] -= gu / S;
 	beta[grp] -= bu / S;
+}
+
+// ---------------------------------------------------------------- group-norm + 2x2 max-pool, fused
+// Geometry of the pooled side; the norm geometry `n` describes the input-sized tensor (n.hw = in_h * in_w).
+struct FusedGeom {
+	NormGeom n;
+	int in_w, out_w, out_hw, ppb_out;
+};
+
+template <typename T> __device__ __forceinline__ float round_to_storage(float v) { return to_f32<T>(from_f32<T>(v)); }
+template <> __device__ __forceinline__ float round_to_storage<float>(float v) { return v; }
+
+__device__ __forceinline__ uint32_t map_byte(const uint2& m, int j) { return ((j < 4 ? m.x : m.y) >> (8 * (j & 3))) & 0xffu; }
+
+// per-channel affine constants of the forward apply (zero for pad channels and samples beyond `length`)
+__device__ __forceinline__ void fwd_constants(const NormGeom& g, int b, int v, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              const float* __restrict__ mean, const float* __restrict__ var, float (&sc)[8], float (&sh)[8]) {
+	const bool dead = b >= g.length;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int ch = v * 8 + j;
+		sc[j] = 0.0f; sh[j] = 0.0f;
+		if (ch < g.c && !dead) {
+			const int grp = ch / g.group_size;
+			if (grp < g.nb_group - g.set_off) {
+				const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
+				sc[j] = gamma[grp] * rstd;
+				sh[j] = beta[grp] - mean[b * g.nb_group + grp] * sc[j];
+			} else sc[j] = 1.0f;
+		}
+	}
+}
+
+// y = x*sc + sh rounded to the storage type (what the unfused apply would have stored), then the first strict maximum
+// of the window in scan order (0,0) (0,1) (1,0) (1,1); only the pooled value and its window index are written
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ map, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var, FusedGeom f) {
+	const NormGeom& g = f.n;
+	const int cv = g.cp >> 3;
+	const int b = blockIdx.y;
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	if (lane_p >= lanes_p) return;
+	const int q0 = blockIdx.x * f.ppb_out;
+	int q1 = q0 + f.ppb_out;
+	if (q1 > f.out_hw) q1 = f.out_hw;
+	const long long row = (long long)f.in_w * g.cp;
+	for (int v = lane_c; v < cv; v += lanes_c) {
+		float sc[8], sh[8];
+		fwd_constants(g, b, v, gamma, beta, mean, var, sc, sh);
+		const T* xb = x + (long long)b * g.hw * g.cp + v * 8;
+		const long long ob = (long long)b * f.out_hw * g.cp + v * 8;
+		for (int q = q0 + lane_p; q < q1; q += lanes_p) {
+			const int oy = q / f.out_w, ox = q - oy * f.out_w;
+			const T* p = xb + (long long)(2 * oy) * row + (long long)(2 * ox) * g.cp;
+			const Raw8<T> r0 = load_raw8<T>(p), r1 = load_raw8<T>(p + g.cp), r2 = load_raw8<T>(p + row), r3 = load_raw8<T>(p + row + g.cp);
+			float a0[8], a1[8], a2[8], a3[8], best[8];
+			unpack8(r0, a0); unpack8(r1, a1); unpack8(r2, a2); unpack8(r3, a3);
+			uint32_t arg[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				best[j] = round_to_storage<T>(fmaf(a0[j], sc[j], sh[j]));
+				arg[j] = 0;
+				float t = round_to_storage<T>(fmaf(a1[j], sc[j], sh[j]));
+				if (t > best[j]) { best[j] = t; arg[j] = 1; }
+				t = round_to_storage<T>(fmaf(a2[j], sc[j], sh[j]));
+				if (t > best[j]) { best[j] = t; arg[j] = 2; }
+				t = round_to_storage<T>(fmaf(a3[j], sc[j], sh[j]));
+				if (t > best[j]) { best[j] = t; arg[j] = 3; }
+				if (v * 8 + j >= g.c) { best[j] = 0.0f; arg[j] = 255; }
+			}
+			const long long o = ob + (long long)q * g.cp;
+			store8<T>(pooled + o, best);
+			uint2 packed;
+			packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+			packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+			if (map != nullptr) *reinterpret_cast<uint2*>(map + o) = packed;
+		}
+	}
+}
+
+// backward reductions: the delta of the normalised tensor is the pooled delta at the selected window position and
+// zero elsewhere, so sum(d) and sum(d*x) run over the pooled pixels, reading x at the position the map names
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, double* __restrict__ ws, FusedGeom f) {
+	extern __shared__ float sm_acc[];
+	const NormGeom& g = f.n;
+	const int cv = g.cp >> 3;
+	const int b = blockIdx.y;
+	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x) sm_acc[i] = 0.0f;
+	__syncthreads();
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	const bool active = lane_p < lanes_p;
+	const int q0 = blockIdx.x * f.ppb_out;
+	int q1 = q0 + f.ppb_out;
+	if (q1 > f.out_hw) q1 = f.out_hw;
+	const long long row = (long long)f.in_w * g.cp;
+	for (int v = lane_c; v < cv; v += lanes_c) {
+		float s0[8], s1[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) { s0[j] = 0.0f; s1[j] = 0.0f; }
+		const T* xb = x + (long long)b * g.hw * g.cp + v * 8;
+		const long long ob = (long long)b * f.out_hw * g.cp + v * 8;
+		for (int q = q0 + lane_p; active && q < q1; q += lanes_p) {
+			const int oy = q / f.out_w, ox = q - oy * f.out_w;
+			const T* p = xb + (long long)(2 * oy) * row + (long long)(2 * ox) * g.cp;
+			const long long o = ob + (long long)q * g.cp;
+			const Raw8<T> rd = load_raw8<T>(dp + o);
+			const uint2 rm = __ldg(reinterpret_cast<const uint2*>(map + o));
+			const Raw8<T> r0 = load_raw8<T>(p), r1 = load_raw8<T>(p + g.cp), r2 = load_raw8<T>(p + row), r3 = load_raw8<T>(p + row + g.cp);
+			float d[8], a0[8], a1[8], a2[8], a3[8];
+			unpack8(rd, d); unpack8(r0, a0); unpack8(r1, a1); unpack8(r2, a2); unpack8(r3, a3);
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const uint32_t m = map_byte(rm, j);
+				const float xs = m == 0 ? a0[j] : (m == 1 ? a1[j] : (m == 2 ? a2[j] : a3[j]));
+				if (m < 4) { s0[j] += d[j]; s1[j] += d[j] * xs; }
+			}
+		}
+		fold_into_groups(s0, s1, v, lanes_c, g, sm_acc);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x)
+		atomicAdd(&ws[(size_t)b * g.nb_group * 2 + i], (double)sm_acc[i]);
+}
+
+// dx of the four input pixels of each window: ca*d + cx*x + cc with d = pooled delta at the selected position, else 0;
+// then the previous layer's derivative hook and the column sums, exactly like norm_bwd_apply_kernel
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, T* __restrict__ dx,
+                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ var,
+                           const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
+                           cb200_activ prev_activ, float* __restrict__ colsum, FusedGeom f) {
+	extern __shared__ float cs_acc[];
+	const NormGeom& g = f.n;
+	const int cv = g.cp >> 3;
+	const int b = blockIdx.y;
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	if (colsum != nullptr) {
+		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
+		__syncthreads();
+	}
+	const bool active_thread = lane_p < lanes_p;
+	const int q0 = blockIdx.x * f.ppb_out;
+	int q1 = q0 + f.ppb_out;
+	if (q1 > f.out_hw) q1 = f.out_hw;
+	const bool dead = b >= g.length;
+	const float n = (float)(g.group_size * g.hw);
+	const float inv_n = 1.0f / n;
+	const int act = prev_activ.type;
+	const float leak = prev_activ.leak, sat = prev_activ.saturation, abeta = prev_activ.beta;
+	const long long row = (long long)f.in_w * g.cp;
+	for (int v = lane_c; v < cv; v += lanes_c) {
+		float ca[8], cx[8], cc[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const int ch = v * 8 + j;
+			ca[j] = 0.0f; cx[j] = 0.0f; cc[j] = 0.0f;
+			if (ch < g.c && !dead) {
+				const int grp = ch / g.group_size;
+				if (grp < g.nb_group - g.set_off) {
+					const int s = b * g.nb_group + grp;
+					const float rstd = 1.0f / sqrtf(var[s] + g.eps);
+					const float k0 = inv_n * gamma[grp] * rstd;
+					ca[j] = k0 * n;
+					cx[j] = -k0 * rstd * d_gamma[s];
+					cc[j] = k0 * (mean[s] * rstd * d_gamma[s] - d_beta[s]);
+				} else ca[j] = 1.0f;
+			}
+		}
+		const long long xb = (long long)b * g.hw * g.cp + v * 8;
+		const long long ob = (long long)b * f.out_hw * g.cp + v * 8;
+		float csum[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) csum[j] = 0.0f;
+		for (int q = q0 + lane_p; active_thread && q < q1; q += lanes_p) {
+			const int oy = q / f.out_w, ox = q - oy * f.out_w;
+			const long long pi = xb + (long long)(2 * oy) * row + (long long)(2 * ox) * g.cp;
+			const long long o = ob + (long long)q * g.cp;
+			const Raw8<T> rd = load_raw8<T>(dp + o);
+			const uint2 rm = __ldg(reinterpret_cast<const uint2*>(map + o));
+			Raw8<T> rx[4];
+			rx[0] = load_raw8<T>(x + pi); rx[1] = load_raw8<T>(x + pi + g.cp);
+			rx[2] = load_raw8<T>(x + pi + row); rx[3] = load_raw8<T>(x + pi + row + g.cp);
+			float d[8];
+			unpack8(rd, d);
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				float xv[8], out[8];
+				unpack8(rx[k], xv);
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					const float dv = map_byte(rm, j) == (uint32_t)k ? d[j] : 0.0f;
+					out[j] = fmaf(ca[j], dv, fmaf(cx[j], xv[j], cc[j]));
+				}
+				if (act == CB200_RELU) {
+#pragma unroll
+					for (int j = 0; j < 8; j++) out[j] = (xv[j] <= 0.0f || xv[j] > sat) ? out[j] * leak : out[j];
+				} else if (act == CB200_LOGISTIC) {
+#pragma unroll
+					for (int j = 0; j < 8; j++) out[j] = out[j] * abeta * xv[j] * (1.0f - xv[j]);
+				}
+				store8<T>(dx + pi + (k >> 1) * row + (k & 1) * g.cp, out);
+#pragma unroll
+				for (int j = 0; j < 8; j++) csum[j] += out[j];
+			}
+		}
+		if (colsum != nullptr) {
+			bool writer = active_thread;
+			if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+					for (int off = lanes_c; off < 32; off <<= 1) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], off);
+				writer = (threadIdx.x & 31) < lanes_c;
+			}
+			if (writer) {
+#pragma unroll
+				for (int j = 0; j < 8; j++) atomicAdd(&cs_acc[v * 8 + j], csum[j]);
+			}
+		}
+	}
+	if (colsum != nullptr) {
+		__syncthreads();
+		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
+	}
 }
 
 static int fill_geom(const cb200_norm_desc* d, NormGeom& g) {
@@ -386,9 +627,80 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	return CB200_OK;
 }
 
+int cb200_norm_pool_fusable(const cb200_norm_desc* nd, const cb200_pool_desc* pd) {
+	if (nd == nullptr || pd == nullptr) return 0;
+	return pd->pool_type == CB200_POOL_MAX && pd->p_h == 2 && pd->p_w == 2 && pd->stride_h == 2 && pd->stride_w == 2 &&
+	       pd->pad_h == 0 && pd->pad_w == 0 && pd->activ.type == CB200_LINEAR && nd->c == pd->c && nd->h == pd->in_h &&
+	       nd->w == pd->in_w && (pd->in_h & 1) == 0 && (pd->in_w & 1) == 0 && pd->out_h * 2 == pd->in_h &&
+	       pd->out_w * 2 == pd->in_w && nd->dtype == pd->dtype && nd->batch == pd->batch;
+}
+
+static int fill_fused(const cb200_norm_desc* nd, const cb200_pool_desc* pd, FusedGeom& f) {
+	int rc = fill_geom(nd, f.n); if (rc) return rc;
+	if (!cb200_norm_pool_fusable(nd, pd)) { set_error("cb200_norm_pool_*: this norm / pool pair cannot be fused (see cb200_norm_pool_fusable)"); return CB200_ERR_ARG; }
+	f.in_w = pd->in_w; f.out_w = pd->out_w; f.out_hw = pd->out_h * pd->out_w;
+	f.ppb_out = norm_pix_per_block(f.out_hw, f.n.batch, f.n.cp >> 3);
+	return CB200_OK;
+}
+
+int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, void* pooled, uint8_t* pool_map,
+                            const float* gamma, const float* beta, float* mean, float* var, void* workspace, void* s) {
+	CB_REQUIRE_DEVICE();
+	FusedGeom f;
+	int rc = fill_fused(nd, pd, f); if (rc) return rc;
+	CB_ARG(workspace != nullptr);
+	const NormGeom& g = f.n;
+	cudaStream_t st = as_stream(s);
+	double* ws = (double*)workspace;
+	const double es = (double)cb200_dtype_size(nd->dtype), E = (double)g.batch * g.hw * g.c;
+	// algorithmic bytes: read x (statistics) + read x + write pooled values and their 1-byte window index
+	prof_begin(PROF_NORM, 2.0 * E * es + 0.25 * E * (es + 1.0), st);
+	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
+	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
+	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>((const T*)x, nullptr, ws, g)));
+	CB_LAUNCH_CHECK();
+	norm_finalize_fwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, g);
+	CB_LAUNCH_CHECK();
+	dim3 grid_o((unsigned)ceil_div(f.out_hw, f.ppb_out), (unsigned)g.batch);
+	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_fwd_kernel<T><<<grid_o, NORM_THREADS, 0, st>>>((const T*)x, (T*)pooled, pool_map, gamma, beta, mean, var, f)));
+	CB_LAUNCH_CHECK();
+	prof_end(st);
+	return CB200_OK;
+}
+
+int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, const void* d_pooled,
+                             const uint8_t* pool_map, void* dx, const float* gamma, const float* mean, const float* var,
+                             float* d_gamma, float* d_beta, const cb200_activ* prev_activ, float* dx_colsum, void* workspace, void* s) {
+	CB_REQUIRE_DEVICE();
+	FusedGeom f;
+	int rc = fill_fused(nd, pd, f); if (rc) return rc;
+	CB_ARG(workspace != nullptr && pool_map != nullptr);
+	const NormGeom& g = f.n;
+	cudaStream_t st = as_stream(s);
+	double* ws = (double*)workspace;
+	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
+	if (prev_activ) pa = *prev_activ;
+	const double es = (double)cb200_dtype_size(nd->dtype), E = (double)g.batch * g.hw * g.c;
+	// algorithmic bytes: x for the reductions, x again + dx for the apply, the pooled delta and its map twice
+	prof_begin(PROF_NORM, 3.0 * E * es + 0.5 * E * (es + 1.0), st);
+	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
+	dim3 grid_o((unsigned)ceil_div(f.out_hw, f.ppb_out), (unsigned)g.batch);
+	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_stats_kernel<T><<<grid_o, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
+		(const T*)x, (const T*)d_pooled, pool_map, ws, f)));
+	CB_LAUNCH_CHECK();
+	norm_finalize_bwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, d_gamma, d_beta, g);
+	CB_LAUNCH_CHECK();
+	if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
+	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_apply_kernel<T><<<grid_o, NORM_THREADS, dx_colsum ? sizeof(float) * g.cp : 0, st>>>(
+		(const T*)x, (const T*)d_pooled, pool_map, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, f)));
+	CB_LAUNCH_CHECK();
+	prof_end(st);
+	return CB200_OK;
+}
+
 int cb200_norm_reduce_grads(const cb200_norm_desc* d, const float* d_gamma, const float* d_beta, float* gsum, void* s) {
 	CB_REQUIRE_DEVICE();
-	norm_reduce_grads_kernel<<<ceil_div(d->nb_group, 128), 128, 0, as_stream(s)>>>(d_gamma, d_beta, gsum, d->batch, d->nb_group);
+	norm_reduce_grads_kernel<<<ceil_div(d->nb_group * 32, 128), 128, 0, as_stream(s)>>>(d_gamma, d_beta, gsum, d->batch, d->nb_group);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }

@@ -90,6 +90,7 @@ typedef struct pool_param {
 	int nb_maps, prev_depth, pool_type, global;
 	cb200_pool_desc desc;
 	uint8_t *pool_map;     /* device */
+	int fused_norm;        /* the preceding group-norm layer is evaluated inside this layer's kernels (see norm_param) */
 } pool_param;
 
 typedef struct norm_param {
@@ -100,6 +101,9 @@ typedef struct norm_param {
 	float *gsum;                                        /* device, FP32 [2][nb_group] inside the gradient arena */
 	void *workspace;
 	size_t grad_offset;
+	/* set when the next layer is a 2x2 max-pool: the pair runs as cb200_norm_pool_forward / _backward, this layer's
+	 * full-resolution output and delta are never materialised (layer->output == layer->delta_o == NULL) */
+	layer *fused_pool;
 } norm_param;
 
 typedef struct dense_param {
@@ -293,6 +297,8 @@ void cb_yolo_box_state(network *net, int *dst);
 void cb_yolo_loss_parts(network *net, float *parts6, float *monitor);
 void cb_yolo_export_boxes(network *net, float *dst);
 void cb_net_set_iter(network *net, int iter, int train_size);
+/* group-norm + max-pool fusion for the layers created from now on (default on; CB200_NO_FUSION=1 in the environment turns it off) */
+void cb_set_fusion(int on);
 
 #define CB_CHECK(call) do { int rc__ = (call); if (rc__ != 0) { \
 	printf("\nERROR: %s failed (%d): %s\n", #call, rc__, cb200_last_error()); exit(EXIT_FAILURE); } } while (0)

@@ -45,9 +45,34 @@ int nb_area_comp(int size, int f_size, int padding, int int_padding, int stride)
 	return (size + (size - 1) * int_padding + padding * 2 - f_size) / stride + 1;
 }
 
+/* ---- group-norm + max-pool fusion ---- */
+static int fusion_enabled = -1;
+void cb_set_fusion(int on) { fusion_enabled = on ? 1 : 0; }
+static int fusion_on(void)
+{
+	if (fusion_enabled < 0) {
+		const char *e = getenv("CB200_NO_FUSION");
+		fusion_enabled = (e != NULL && e[0] != '\0' && e[0] != '0') ? 0 : 1;
+	}
+	return fusion_enabled;
+}
+
+/* a fused norm layer keeps no full-resolution output / delta; anything else that wants to read them un-fuses it */
+static void unfuse_norm(layer *norm)
+{
+	network *net = norm->c_network;
+	norm_param *np = (norm_param *)norm->param;
+	if (np->fused_pool == NULL) return;
+	((pool_param *)np->fused_pool->param)->fused_norm = 0;
+	np->fused_pool = NULL;
+	norm->output = dev_alloc(act_bytes(net, norm->out_c, norm->out_h, norm->out_w));
+	if (!net->inference_only) norm->delta_o = dev_alloc(act_bytes(net, norm->out_c, norm->out_h, norm->out_w));
+}
+
 static layer *new_layer(network *net, int type, layer *previous)
 {
 	layer *current = (layer *)calloc(1, sizeof(layer));
+	if (previous != NULL && previous->type == NORM) unfuse_norm(previous);
 	if (net->nb_layers >= MAX_LAYERS_NB) { printf("\nERROR: too many layers (MAX_LAYERS_NB=%d)\n", MAX_LAYERS_NB); exit(EXIT_FAILURE); }
 	current->index = net->nb_layers;
 	net->net_layers[net->nb_layers++] = current;
@@ -345,7 +370,14 @@ static void forward_pool_layer(layer *current)
 	pool_param *p = (pool_param *)current->param;
 	if (net->length == 0) return;
 	p->desc.length = net->length;
-	CB_CHECK(cb200_pool_forward(&p->desc, layer_input(current), current->output, p->pool_map, NULL));
+	if (p->fused_norm) {
+		layer *norm = current->previous;
+		norm_param *np = (norm_param *)norm->param;
+		np->desc.length = net->length;
+		CB_CHECK(cb200_norm_pool_forward(&np->desc, &p->desc, norm->previous->output, current->output, p->pool_map,
+			np->gamma, np->beta, np->mean, np->var, np->workspace, NULL));
+	} else
+		CB_CHECK(cb200_pool_forward(&p->desc, layer_input(current), current->output, p->pool_map, NULL));
 	if (current->activation_type == SOFTMAX)
 		CB_CHECK(cb200_softmax(current->output, net->dtype, net->batch_size, net->length, current->out_c, current->out_h, current->out_w, NULL));
 }
@@ -355,6 +387,7 @@ static void backward_pool_layer(layer *current)
 	network *net = current->c_network;
 	pool_param *p = (pool_param *)current->param;
 	p->desc.length = net->length;
+	if (p->fused_norm) return;      /* the norm layer's backward consumes this layer's delta and map directly */
 	if (current->previous != NULL)
 		CB_CHECK(cb200_pool_backward(&p->desc, current->delta_o, p->pool_map, current->previous->delta_o,
 			&current->previous->activ, current->previous->output, NULL));
@@ -412,6 +445,15 @@ int pool_create(network *net, layer *previous, int *pool_size, int *stride, int 
 		current->delta_o = dev_alloc(act_bytes(net, current->out_c, current->out_h, current->out_w));
 		if (p->pool_type == MAX_pool)
 			p->pool_map = (uint8_t *)dev_alloc((size_t)net->batch_size * current->out_h * current->out_w * cb200_round_channels(pc));
+	}
+	if (previous != NULL && previous->type == NORM && fusion_on() && (p->pool_map != NULL || net->inference_only)
+	    && cb200_norm_pool_fusable(&((norm_param *)previous->param)->desc, &p->desc)) {
+		/* group-norm + 2x2 max-pool run as one pass each way; the normalised full-resolution tensor is never stored */
+		norm_param *np = (norm_param *)previous->param;
+		np->fused_pool = current;
+		p->fused_norm = 1;
+		CB_CHECK(cb200_free(previous->output)); previous->output = NULL;
+		if (previous->delta_o != NULL) { CB_CHECK(cb200_free(previous->delta_o)); previous->delta_o = NULL; }
 	}
 	current->forward = forward_pool_layer;
 	current->backprop = backward_pool_layer;
@@ -481,6 +523,7 @@ static void forward_norm_layer(layer *current)
 	norm_param *p = (norm_param *)current->param;
 	if (net->length == 0) return;
 	p->desc.length = net->length;
+	if (p->fused_pool != NULL) return;      /* evaluated by the following pool layer (cb200_norm_pool_forward) */
 	CB_CHECK(cb200_norm_forward(&p->desc, current->previous->output, current->output, p->gamma, p->beta, p->mean, p->var, p->workspace, NULL));
 }
 
@@ -497,8 +540,15 @@ static void backward_norm_layer(layer *current)
 			conv_param *cp = (conv_param *)prev->param;
 			if (cp->bias_grad_from_next) colsum = cp->w.grad_b;
 		}
-		CB_CHECK(cb200_norm_backward(&p->desc, prev->output, current->delta_o, prev->delta_o,
-			p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, NULL));
+		if (p->fused_pool != NULL) {
+			layer *pool = p->fused_pool;
+			pool_param *pp = (pool_param *)pool->param;
+			pp->desc.length = net->length;
+			CB_CHECK(cb200_norm_pool_backward(&p->desc, &pp->desc, prev->output, pool->delta_o, pp->pool_map, prev->delta_o,
+				p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, NULL));
+		} else
+			CB_CHECK(cb200_norm_backward(&p->desc, prev->output, current->delta_o, prev->delta_o,
+				p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, NULL));
 	}
 	if (!current->frozen)
 		CB_CHECK(cb200_norm_reduce_grads(&p->desc, p->d_gamma, p->d_beta, p->gsum, NULL));

@@ -778,8 +778,36 @@ static void export_act(network *net, layer *l, const void *src, float *dst)
 	cb200_free(tmp);
 }
 
-void cb_layer_export_output(network *net, int l, float *dst) { export_act(net, net->net_layers[l], net->net_layers[l]->output, dst); }
-void cb_layer_export_delta(network *net, int l, float *dst) { export_act(net, net->net_layers[l], net->net_layers[l]->delta_o, dst); }
+/* A group-norm layer fused with the following max-pool keeps neither its full-resolution output nor its delta
+ * (host/layers.c): the read-back helpers rebuild them on demand with the un-fused kernels - the output from the stored
+ * input with the CURRENT gamma / beta (so: ask before the optimizer step), the delta from the pool layer's delta + map. */
+static void *materialize_fused_norm(network *net, layer *l, int want_delta)
+{
+	norm_param *np = (norm_param *)l->param;
+	layer *pool = np->fused_pool;
+	pool_param *pp = (pool_param *)pool->param;
+	void *tmp = NULL;
+	CB_CHECK(cb200_malloc(&tmp, (size_t)net->batch_size * l->out_h * l->out_w * cb200_round_channels(l->out_c) * cb200_dtype_size(net->dtype)));
+	if (!want_delta)
+		CB_CHECK(cb200_norm_forward(&np->desc, l->previous->output, tmp, np->gamma, np->beta, np->mean, np->var, np->workspace, NULL));
+	else
+		CB_CHECK(cb200_pool_backward(&pp->desc, pool->delta_o, pp->pool_map, tmp, NULL, NULL, NULL));
+	return tmp;
+}
+
+static void export_maybe_fused(network *net, int l, float *dst, int want_delta)
+{
+	layer *cur = net->net_layers[l];
+	if (cur->type == NORM && ((norm_param *)cur->param)->fused_pool != NULL) {
+		void *tmp = materialize_fused_norm(net, cur, want_delta);
+		export_act(net, cur, tmp, dst);
+		cb200_free(tmp);
+	} else
+		export_act(net, cur, want_delta ? cur->delta_o : cur->output, dst);
+}
+
+void cb_layer_export_output(network *net, int l, float *dst) { export_maybe_fused(net, l, dst, 0); }
+void cb_layer_export_delta(network *net, int l, float *dst) { export_maybe_fused(net, l, dst, 1); }
 
 void cb_layer_export_pool_map(network *net, int l, int *dst)
 {

@@ -286,6 +286,24 @@ int cb200_norm_reduce_grads(const cb200_norm_desc* d, const float* d_gamma, cons
 int cb200_norm_update(const cb200_norm_desc* d, float* gamma, float* beta, float* gamma_upd, float* beta_upd,
                       const float* gsum, const float* hyper, void* stream);
 
+/* ---- group-norm followed by a max-pool over disjoint 2x2 windows, fused (no upstream counterpart: upstream runs
+ * cuda_forward_norm_layer then cuda_forward_pool_layer and the reverse pair, cuda_norm_layer.cu:361-461,
+ * cuda_pool_layer.cu:429-547).  Same results as cb200_norm_forward + cb200_pool_forward (values rounded to the
+ * storage type before they are compared, so the argmax map is identical) and as cb200_pool_backward +
+ * cb200_norm_backward, without ever writing or reading the full-resolution normalised tensor / its delta:
+ * forward moves 2.4 instead of 4.4 passes over the input-sized tensor, backward 3.4 instead of 6.4.
+ * Supported when cb200_norm_pool_fusable() returns 1: MAX pool, 2x2 window, stride 2, no padding, even input
+ * size, LINEAR pool activation, nd->{c,h,w} == pd->{c,in_h,in_w}. */
+int cb200_norm_pool_fusable(const cb200_norm_desc* nd, const cb200_pool_desc* pd);
+int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, void* pooled,
+                            uint8_t* pool_map, const float* gamma, const float* beta, float* mean, float* var,
+                            void* workspace, void* stream);
+/* d_pooled: delta of the pool OUTPUT; dx: delta of the norm INPUT (previous layer's derivative hook included). */
+int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, const void* d_pooled,
+                             const uint8_t* pool_map, void* dx, const float* gamma, const float* mean,
+                             const float* var, float* d_gamma, float* d_beta, const cb200_activ* prev_activ,
+                             float* dx_colsum, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------ local response normalisation */
 typedef struct {
 	int dtype;

@@ -253,3 +253,57 @@ def test_group_norm_vs_oracle(cabi, cfg, dtype_name):
     # fused by-product: per-channel sums of dx (bias-column gradient of the convolution in front of the norm layer)
     cs = nl.colsum.to_numpy(np.float32, (C,))
     assert rel_err(cs, ref_dx.astype(np.float64).sum(axis=(1, 2))) < (1e-4 if dtype_name == "FP32" else TOL_MIXED)
+
+
+@pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
+@pytest.mark.parametrize("cfg", [(4, 32, 12, 4, 0, 4, "RELU"), (3, 16, 8, 8, 1, 2, "LIN"), (2, 64, 40, 16, 0, 2, "RELU"), (2, 8, 6, 8, 0, 2, "RELU"), (2, 20, 10, 4, 0, 2, "LIN")])
+def test_group_norm_max_pool_fused_equals_unfused(cabi, cfg, dtype_name):
+    """cb200_norm_pool_forward / _backward against cb200_norm_forward + cb200_pool_forward and cb200_pool_backward +
+    cb200_norm_backward on the same tensors: pooled values and argmax map IDENTICAL (the fused kernel rounds the
+    normalised values to the storage type before comparing them), statistics and dx equal to accumulation order"""
+    B, C, S, gs, set_off, length, prev = cfg
+    dtype = getattr(cabi, dtype_name)
+    tol = TOL_FP32 if dtype_name == "FP32" else TOL_MIXED
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal((C, B, S * S)) * 1.5 + 0.3).astype(np.float32)
+    x[:, :, ::7] = np.round(x[:, :, ::7])            # some exact ties inside windows
+    G = (C + gs - 1) // gs
+    gamma = (1 + 0.3 * rng.standard_normal(G)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(G)).astype(np.float32)
+    pa = cabi.activ(cabi.RELU) if prev == "RELU" else None
+    xb = cabi.upload_act(x, dtype, B, C, S, S)
+    So = S // 2
+    dp = rng.standard_normal((C, B, So * So)).astype(np.float32)
+    dp[:, length:, :] = 0
+    dpb = cabi.upload_act(dp, dtype, B, C, So, So)
+    # un-fused pair
+    n1 = cabi.NormLayer(dtype, B, C, S, S, gs, set_off, length)
+    n1.set_params(gamma, beta)
+    p1 = cabi.PoolLayer(dtype, B, C, S, S, 2, 2, 0, cabi.POOL_MAX, length=length)
+    y1 = cabi.download_act(p1.forward(n1.forward(xb)), dtype, B, C, So, So)
+    m1 = p1.map_ref_layout()
+    dyb = p1.backward(dpb)
+    dx1 = cabi.download_act(n1.backward(xb, dyb, pa), dtype, B, C, S, S)
+    st1 = n1.stats()
+    cs1 = n1.colsum.to_numpy(np.float32, (C,))
+    # fused pair
+    n2 = cabi.NormLayer(dtype, B, C, S, S, gs, set_off, length)
+    n2.set_params(gamma, beta)
+    p2 = cabi.PoolLayer(dtype, B, C, S, S, 2, 2, 0, cabi.POOL_MAX, length=length)
+    y2 = cabi.download_act(n2.forward_pool(xb, p2), dtype, B, C, So, So)
+    m2 = p2.map_ref_layout()
+    dx2 = cabi.download_act(n2.backward_pool(xb, dpb, p2, pa), dtype, B, C, S, S)
+    st2 = n2.stats()
+    cs2 = n2.colsum.to_numpy(np.float32, (C,))
+    assert np.array_equal(y1, y2), "pooled values differ"
+    assert np.array_equal(m1, m2), "argmax map differs"
+    for a, b in zip(st1, st2):
+        assert rel_err(b, a) < 1e-5
+    assert rel_err(dx2, dx1) < (1e-5 if dtype_name == "FP32" else tol)
+    assert rel_err(cs2, cs1) < (1e-4 if dtype_name == "FP32" else tol)
+    # and against the oracle, end to end
+    ref_y, mean, var = co.group_norm_forward(x if dtype_name == "FP32" else cabi.download_act(xb, dtype, B, C, S, S), gamma, beta, gs, set_off, length)
+    ref_p, ref_m = co.pool_forward(ref_y, B, C, S, S, 2, 2, 0, "MAX")
+    assert rel_err(y2, ref_p) < tol
+    if dtype_name == "FP32":
+        assert (m2 != ref_m).mean() < 1e-3      # only exact FP32 ties may resolve differently after rounding
