@@ -17,6 +17,10 @@ bool conv_tc_wgrad_supported(const cb200_conv_desc*);
 int conv_forward_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t);
 int conv_dgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, const cb200_activ*, const void*, cudaStream_t);
 int conv_wgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
+// first layer straight from the dataset batch, patch rows built in shared memory (conv_first.cu)
+bool conv_first_supported(const cb200_conv_desc*);
+int conv_first_forward(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t);
+int conv_first_wgrad(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
 
 // master [out_c][taps*in_c + 1] (column = c*taps + tap, bias last) -> compute operands.
 // One thread per master element; the same mapping is used by the optimizer below.
@@ -125,6 +129,10 @@ using namespace cb200;
 
 extern "C" {
 
+int cb200_conv_first_direct(const cb200_conv_desc* d) {
+	return d != nullptr && d->input_is_patches != 0 && !g_force_simt && conv_first_supported(d) ? 1 : 0;
+}
+
 size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d) {
 	if (d->input_is_patches) return (size_t)d->out_c * cb200_patch_width(d->in_c, d->f_h, d->f_w);
 	return (size_t)d->out_c * d->f_h * d->f_w * round8(d->in_c);
@@ -168,6 +176,14 @@ int cb200_conv_forward(const cb200_conv_desc* d_in, const cb200_conv_weights* w,
 	const cb200_conv_desc* d = &eff;
 	// algorithmic FLOPs: 2*M*N*K with K including the bias column, excluding any channel padding
 	const double flops = 2.0 * d_in->batch * d_in->out_h * d_in->out_w * (double)d_in->out_c * ((double)d_in->f_h * d_in->f_w * d_in->in_c + 1);
+	if (d_in->input_is_patches == 2) {
+		if (!conv_first_supported(d_in)) { set_error("cb200_conv_forward: input_is_patches = 2 is not available for this layer (cb200_conv_first_direct)"); return CB200_ERR_UNSUPPORTED; }
+		g_last_conv_impl = "tcgen05";
+		prof_begin(PROF_CONV_FWD_TC, flops, as_stream(s));
+		rc = conv_first_forward(d_in, w, x, y, as_stream(s));
+		prof_end(as_stream(s));
+		return rc;
+	}
 	const bool tc = !g_force_simt && conv_tc_fwd_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_FWD_TC : PROF_CONV_FWD_SIMT, flops, as_stream(s));
@@ -207,6 +223,14 @@ int cb200_conv_backward_weights_ex(const cb200_conv_desc* d_in, const cb200_conv
 		if (rc) return rc;
 	}
 	const double flops = 2.0 * P * (double)d_in->out_c * ((double)d_in->f_h * d_in->f_w * d_in->in_c + 1);
+	if (d_in->input_is_patches == 2) {
+		if (!conv_first_supported(d_in)) { set_error("cb200_conv_backward_weights: input_is_patches = 2 is not available for this layer"); return CB200_ERR_UNSUPPORTED; }
+		g_last_conv_impl = "tcgen05";
+		prof_begin(PROF_CONV_WGRAD_TC, flops, st);
+		rc = conv_first_wgrad(d_in, w, x, dy, st);
+		prof_end(st);
+		return rc;
+	}
 	const bool tc = !g_force_simt && conv_tc_wgrad_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_WGRAD_TC : PROF_CONV_WGRAD_SIMT, flops, st);

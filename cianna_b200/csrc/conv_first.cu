@@ -1,0 +1,488 @@
+// conv_first.cu - the network's first convolution, straight from the dataset batch, on the tensor cores.
+//
+// A first layer has 1-3 input channels: its GEMM K is tiny (3x3x3+1 = 28) and both passes are bound by memory traffic.
+// Upstream unrolls the receptive fields to memory (im2col_kernel, src/cuda/cuda_conv_layer.cu:36-103: 28 values written
+// and read back per output pixel) and so did this core's first version (cb200_import_input_patches: 1.6 GB written + read
+// per pass at batch 128, 448 px).  Here the unrolled rows only ever exist in SHARED memory: builder warps read the planar
+// dataset rows [B][C*H*W+1] (L1/L2 resident: every input value is used by f_h*f_w neighbouring pixels), assemble the GEMM
+// operand tile in the canonical swizzled layout the tensor core expects - byte for byte what a TMA load of the
+// materialised patch rows would have produced - and hand it to the MMA warp through an mbarrier (generic-proxy writes
+// are made visible to the tensor core's async proxy with fence.proxy.async).  HBM traffic per pass drops to "read the
+// images once, write (forward) or read (weight gradient) the layer's output once".
+//
+//   forward : D[128 px][BN filters] = patch[128 px][KP] * W[filters][KP]^T     (K-major A built on chip, B by TMA once)
+//             8 builder warps (two groups alternating tiles), 1 MMA warp, 4 epilogue warps, TMEM accumulator ring
+//   wgrad   : G[filters][KP] += dy[px][filters]^T * patch[px][KP]               (both MN-major; dy by TMA, patches built)
+//             persistent CTAs over contiguous pixel ranges, FP32 red.add of the per-CTA partial at the end
+// Column order of a patch row = upstream's filter column order c*taps + tap, then the bias input, zero padded to KP.
+#include <cuda.h>
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cb200 {
+
+using namespace ptx;
+
+int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n, int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw);
+int make_w_map(CUtensorMap* m, const void* base, int dtype, int cp, int taps, int rows, int bc, int brow, CUtensorMapSwizzle sw);
+void choose_rect(int W, int H, int N, int npix, int& tw, int& th, int& tn);
+CUtensorMapSwizzle swizzle_for(int bk);
+
+struct FirstParams {
+	const void* src;             // dataset batch, [N][c*h*w + 1] values of the compute type
+	int c, h, w, s_h, s_w, p_h, p_w;
+	int W, H, N;                 // output pixel grid
+	int tw, th, tn, tiles_w, tiles_h, tiles_n, num_tiles;
+	int n_real, n_pad, length;
+	float bias_value;
+	cb200_activ activ;
+	void* out;                   // forward: layer output [N][H][W][n_pad]
+	float* grad;                 // wgrad: [n_real][KP]
+	int tiles_per_cta;           // wgrad
+	uint32_t idesc;
+};
+
+template <int KP> struct PatchCfg {
+	static constexpr int ROW_BYTES = KP * 2;
+	static constexpr uint32_t LAYOUT = KP == 64 ? 2u : (KP == 32 ? 4u : 6u);           // 128B / 64B / 32B swizzle
+	static constexpr int SW_SHIFT = KP == 64 ? 0 : (KP == 32 ? 1 : 2);                  // row bits that feed the XOR
+	static constexpr int SW_MASK = KP / 8 - 1;
+	static constexpr uint32_t SBO = 8 * ROW_BYTES;
+};
+
+// Assemble the patch row of output pixel (py, px) of image `img` and store it as row `row` of a tile at smem address
+// `tile` (16-byte chunks XOR-swizzled exactly like CU_TENSOR_MAP_SWIZZLE_{128,64,32}B does for rows of KP*2 bytes).
+template <typename T, int C, int FH, int FW, int KP>
+__device__ __forceinline__ void build_patch_row(const T* __restrict__ img, bool valid, int h, int w, int iy0, int ix0,
+                                                unsigned short bias_bits, uint32_t tile, int row) {
+	using PC = PatchCfg<KP>;
+	constexpr int TAPS = FH * FW, KREAL = C * TAPS;
+	static_assert(KREAL + 1 <= KP, "patch row does not fit");
+	const unsigned short* __restrict__ src = reinterpret_cast<const unsigned short*>(img);
+	uint32_t packed[KP / 2];
+#pragma unroll
+	for (int i = 0; i < KP / 2; i++) packed[i] = 0u;
+	bool col_ok[FW];
+#pragma unroll
+	for (int kx = 0; kx < FW; kx++) col_ok[kx] = valid && (ix0 + kx) >= 0 && (ix0 + kx) < w;
+#pragma unroll
+	for (int ch = 0; ch < C; ch++) {
+#pragma unroll
+		for (int ky = 0; ky < FH; ky++) {
+			const int iy = iy0 + ky;
+			const bool row_ok = iy >= 0 && iy < h;
+			const unsigned short* __restrict__ line = src + ((size_t)ch * h + (row_ok ? iy : 0)) * w + ix0;
+#pragma unroll
+			for (int kx = 0; kx < FW; kx++) {
+				const int k = (ch * FH + ky) * FW + kx;
+				const uint32_t v = (row_ok && col_ok[kx]) ? (uint32_t)__ldg(line + kx) : 0u;
+				packed[k >> 1] |= v << (16 * (k & 1));
+			}
+		}
+	}
+	if (valid) packed[KREAL >> 1] |= (uint32_t)bias_bits << (16 * (KREAL & 1));
+	const uint32_t base = tile + (uint32_t)row * PC::ROW_BYTES;
+	const int x = (row >> PC::SW_SHIFT) & PC::SW_MASK;
+#pragma unroll
+	for (int j = 0; j < KP / 8; j++) {
+		const uint32_t dst = base + (uint32_t)((j ^ x) << 4);
+		asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]), "r"(packed[4 * j + 1]),
+		             "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+	}
+}
+
+template <typename T> __device__ __forceinline__ unsigned short bits_of(float v);
+template <> __device__ __forceinline__ unsigned short bits_of<__half>(float v) { return __half_as_ushort(__float2half_rn(v)); }
+template <> __device__ __forceinline__ unsigned short bits_of<__nv_bfloat16>(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+// ================================================================ forward
+constexpr int FWD_BUILD_WARPS = 8, FWD_THREADS = (FWD_BUILD_WARPS + 1 + 4) * 32;
+template <int KP, int BN> struct FirstFwdCfg {
+	static constexpr int A_BYTES = 128 * KP * 2;
+	static constexpr int STAGES = 8;
+	static constexpr int B_BYTES = BN * KP * 2;
+	static constexpr int ACC_STAGES = 4;
+	static constexpr int TMEM_COLS = ACC_STAGES * BN <= 128 ? 128 : 256;
+	static constexpr int SMEM_BYTES = STAGES * A_BYTES + ((B_BYTES + 1023) & ~1023) + 1024 + 256;
+};
+
+template <typename T, int C, int FH, int FW, int KP, int BN>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstParams p) {
+	using Cfg = FirstFwdCfg<KP, BN>;
+	using PC = PatchCfg<KP>;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t b_smem = smem_base + Cfg::STAGES * Cfg::A_BYTES;
+	const uint32_t bar_base = b_smem + ((Cfg::B_BYTES + 1023) & ~1023);
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };
+	const uint32_t bfull_bar = bar_base + 8u * (2 * Cfg::STAGES + 8);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 9);
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	constexpr int MMA_WARP = FWD_BUILD_WARPS;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_b);
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+		mbar_init(bfull_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	if (warp < FWD_BUILD_WARPS) {
+		// ===================== builders: group g fills the stages of the CTA's tiles g, g+2, ... =====================
+		const int grp = warp >> 2;
+		const int row = (warp & 3) * 32 + lane;
+		const T* __restrict__ src = reinterpret_cast<const T*>(p.src);
+		const size_t img_stride = (size_t)p.c * p.h * p.w + 1;
+		const unsigned short bias_bits = bits_of<T>(p.bias_value);
+		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		int it = 0;
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+			if ((it & 1) != grp) continue;
+			const int stage = it % Cfg::STAGES;
+			const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
+			const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
+			const int px = twi * p.tw + rx, py = thi * p.th + ry, pn = tni * p.tn + rn;
+			const bool valid = px < p.W && py < p.H && pn < p.N;
+			mbar_wait(empty_bar(stage), phase ^ 1u);
+			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
+				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::A_BYTES, row);
+			fence_proxy_async();
+			mbar_arrive(full_bar(stage));
+		}
+	} else if (warp == MMA_WARP) {
+		// ===================== MMA issuer (also fetches the filters once) =====================
+		if (lane == 0) {
+			mbar_arrive_expect_tx(bfull_bar, Cfg::B_BYTES);
+			tma_load_3d(b_smem, &tmap_b, bfull_bar, 0, 0, 0);
+			mbar_wait(bfull_bar, 0);
+			int it = 0;
+			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+				const int stage = it % Cfg::STAGES, acc = it % Cfg::ACC_STAGES;
+				const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u, acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
+				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+				mbar_wait(full_bar(stage), phase);
+				tc_fence_after();
+				const uint32_t sa = smem_base + stage * Cfg::A_BYTES;
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+				for (int kk = 0; kk < KP / 16; kk++) {
+					const uint64_t da = make_smem_desc(sa + kk * 32, 16, PC::SBO, PC::LAYOUT);
+					const uint64_t db = make_smem_desc(b_smem + kk * 32, 16, PC::SBO, PC::LAYOUT);
+					mma_f16_ss(d_tmem, da, db, p.idesc, kk != 0 ? 1u : 0u);
+				}
+				mma_commit(empty_bar(stage));
+				mma_commit(tfull_bar(acc));
+			}
+		}
+	} else {
+		// ===================== epilogue: activation, cast, store (the bias is a GEMM column) =====================
+		const int quad = warp & 3;
+		const int row = quad * 32 + lane;
+		T* __restrict__ out = reinterpret_cast<T*>(p.out);
+		const int act = p.activ.type, n_real = p.n_real, n_pad = p.n_pad;
+		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta;
+		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
+		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		int it = 0;
+		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+			const int acc = it % Cfg::ACC_STAGES;
+			const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
+			const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
+			const int px = twi * p.tw + rx, py = thi * p.th + ry, pn = tni * p.tn + rn;
+			const bool row_ok = px < p.W && py < p.H && pn < p.N;
+			const size_t pix = ((size_t)pn * p.H + py) * p.W + px;
+			const bool dead = mask_tail && pn >= p.length;
+			mbar_wait(tfull_bar(acc), acc_phase);
+			tc_fence_after();
+			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+			for (int c0 = 0; c0 < BN; c0 += 32) {
+				uint32_t r[32];
+				tmem_ld_32x32(t_row + c0, r);
+				tmem_ld_wait();
+#pragma unroll
+				for (int v = 0; v < 4; v++) {
+					const int col = c0 + v * 8;
+					if (!row_ok || col >= n_pad) continue;
+					float o[8];
+#pragma unroll
+					for (int j = 0; j < 8; j++) o[j] = dead ? 0.0f : __uint_as_float(r[v * 8 + j]);
+					if (act == CB200_RELU) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							const float z = o[j];
+							const float hi = sat + (z - sat) * leak;
+							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+						}
+					} else if (act == CB200_LOGISTIC) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) o[j] = dead ? 0.0f : 1.0f / (1.0f + expf(fminf(-beta * o[j], sat)));
+					}
+					if (col + 8 > n_real) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+					}
+					store8<T>(out + pix * n_pad + col, o);
+				}
+				__syncwarp();
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(tempty_bar(acc));
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == MMA_WARP) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ================================================================ weight gradient
+constexpr int WG_BUILD_WARPS = 8, WG_THREADS = (2 + 4 + WG_BUILD_WARPS) * 32;
+template <int KP> struct FirstWgCfg {
+	static constexpr int KPIX = 64;
+	static constexpr int A_SLAB_BYTES = KPIX * 128;                 // dy: [64 px][64 filters], 128B swizzle
+	static constexpr int A_BYTES = 2 * A_SLAB_BYTES;                // M = 128 filter rows (rows past the tensor are zero-filled)
+	static constexpr int B_BYTES = KPIX * KP * 2;
+	static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) & ~1023);
+	static constexpr int STAGES = 8;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+	static constexpr int TMEM_COLS = 32 > KP ? 32 : KP;
+};
+
+template <typename T, int C, int FH, int FW, int KP>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const FirstParams p) {
+	using Cfg = FirstWgCfg<KP>;
+	using PC = PatchCfg<KP>;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+	const uint32_t done_bar = bar_base + 8u * (2 * Cfg::STAGES);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_dy);
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1 + Cfg::KPIX); mbar_init(empty_bar(s), 1); }
+		mbar_init(done_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	const int t_begin = blockIdx.x * p.tiles_per_cta;
+	int t_end = t_begin + p.tiles_per_cta;
+	if (t_end > p.num_tiles) t_end = p.num_tiles;
+	const int n_steps = t_end > t_begin ? t_end - t_begin : 0;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			for (int k = 0; k < n_steps; k++) {
+				const int t = t_begin + k;
+				const int stage = k % Cfg::STAGES;
+				const uint32_t phase = (uint32_t)(k / Cfg::STAGES) & 1u;
+				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
+				mbar_wait(empty_bar(stage), phase ^ 1u);
+				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+				mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES);
+				tma_load_4d(sa, &tmap_dy, full_bar(stage), 0, twi * p.tw, thi * p.th, tni * p.tn);
+				tma_load_4d(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), 64, twi * p.tw, thi * p.th, tni * p.tn);
+			}
+		}
+	} else if (warp == 1) {
+		if (lane == 0) {
+			for (int k = 0; k < n_steps; k++) {
+				const int stage = k % Cfg::STAGES;
+				const uint32_t phase = (uint32_t)(k / Cfg::STAGES) & 1u;
+				mbar_wait(full_bar(stage), phase);
+				tc_fence_after();
+				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+				for (int kk = 0; kk < Cfg::KPIX / 16; kk++) {
+					const uint64_t da = make_smem_desc(sa + kk * 2048, Cfg::A_SLAB_BYTES, 1024, 2);
+					const uint64_t db = make_smem_desc(sb + kk * 16 * PC::ROW_BYTES, Cfg::B_BYTES, PC::SBO, PC::LAYOUT);
+					mma_f16_ss(tmem_base, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
+				}
+				mma_commit(empty_bar(stage));
+			}
+			mma_commit(done_bar);
+		}
+	} else if (warp < 6) {
+		if (n_steps > 0) {
+			const int quad = warp & 3;
+			mbar_wait(done_bar, 0);
+			tc_fence_after();
+			const int f = quad * 32 + lane;
+			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+			for (int c0 = 0; c0 < KP; c0 += 32) {
+				uint32_t r[32];
+				if (KP - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
+				else { uint32_t hh[16]; tmem_ld_32x16(t_row + c0, hh);
+#pragma unroll
+					for (int j = 0; j < 16; j++) { r[j] = hh[j]; r[16 + j] = 0; } }
+				tmem_ld_wait();
+				if (f < p.n_real) {
+					float* dst = p.grad + (size_t)f * KP + c0;
+#pragma unroll
+					for (int j = 0; j < 32; j += 4)
+						if (c0 + j < KP)
+							asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+							             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+				}
+				__syncwarp();
+			}
+		}
+	} else {
+		// ===================== builders: pair q fills the patch tile of steps q, q+4, ... =====================
+		const int bw = warp - 6;
+		const int pair = bw >> 1;
+		const int row = (bw & 1) * 32 + lane;
+		const T* __restrict__ src = reinterpret_cast<const T*>(p.src);
+		const size_t img_stride = (size_t)p.c * p.h * p.w + 1;
+		const unsigned short bias_bits = bits_of<T>(p.bias_value);
+		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		for (int k = pair; k < n_steps; k += WG_BUILD_WARPS / 2) {
+			const int t = t_begin + k;
+			const int stage = k % Cfg::STAGES;
+			const uint32_t phase = (uint32_t)(k / Cfg::STAGES) & 1u;
+			const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
+			const int px = twi * p.tw + rx, py = thi * p.th + ry, pn = tni * p.tn + rn;
+			const bool valid = px < p.W && py < p.H && pn < p.N;
+			mbar_wait(empty_bar(stage), phase ^ 1u);
+			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
+				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, row);
+			fence_proxy_async();
+			mbar_arrive(full_bar(stage));
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ================================================================ host side
+static int kp_of(const cb200_conv_desc* d) { return cb200_patch_width(d->in_c, d->f_h, d->f_w); }
+
+bool conv_first_supported(const cb200_conv_desc* d) {
+	if (d->dtype != CB200_FP16 && d->dtype != CB200_BF16) return false;
+	const bool shape = (d->in_c == 3 && d->f_h == 3 && d->f_w == 3) || (d->in_c == 1 && d->f_h == 3 && d->f_w == 3) ||
+	                   (d->in_c == 1 && d->f_h == 5 && d->f_w == 5) || (d->in_c == 2 && d->f_h == 3 && d->f_w == 3);
+	return shape && round8(d->out_c) <= 64 && d->out_c >= 8;
+}
+
+static void fill_params(const cb200_conv_desc* d, const void* src, int npix, FirstParams& p) {
+	memset(&p, 0, sizeof(p));
+	p.src = src;
+	p.c = d->in_c; p.h = d->in_h; p.w = d->in_w; p.s_h = d->stride_h; p.s_w = d->stride_w; p.p_h = d->pad_h; p.p_w = d->pad_w;
+	p.W = d->out_w; p.H = d->out_h; p.N = d->batch;
+	choose_rect(p.W, p.H, p.N, npix, p.tw, p.th, p.tn);
+	p.tiles_w = ceil_div(p.W, p.tw); p.tiles_h = ceil_div(p.H, p.th); p.tiles_n = ceil_div(p.N, p.tn);
+	p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+	p.n_real = d->out_c; p.n_pad = round8(d->out_c); p.length = d->length;
+	p.bias_value = d->bias_value; p.activ = d->activ;
+}
+
+template <typename T, int C, int FH, int FW, int KP, int BN>
+static int launch_first_fwd(const CUtensorMap& mb, const FirstParams& p, cudaStream_t st) {
+	using Cfg = FirstFwdCfg<KP, BN>;
+	static bool configured = false;
+	auto kern = conv_first_fwd_kernel<T, C, FH, FW, KP, BN>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+	kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(mb, p);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+template <typename T, int C, int FH, int FW, int KP>
+static int launch_first_wgrad(const CUtensorMap& mdy, const FirstParams& p, int grid, cudaStream_t st) {
+	using Cfg = FirstWgCfg<KP>;
+	static bool configured = false;
+	auto kern = conv_first_wgrad_kernel<T, C, FH, FW, KP>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	kern<<<grid, WG_THREADS, Cfg::SMEM_BYTES, st>>>(mdy, p);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+#define FIRST_SHAPES(X)  X(3, 3, 3, 32) X(1, 3, 3, 16) X(1, 5, 5, 32) X(2, 3, 3, 32)
+
+template <typename T>
+static int first_fwd_typed(const cb200_conv_desc* d, const CUtensorMap& mb, const FirstParams& p, cudaStream_t st) {
+	const int bn = p.n_pad > 32 ? 64 : 32;
+#define X(C_, FH_, FW_, KP_) \
+	if (d->in_c == C_ && d->f_h == FH_ && d->f_w == FW_) \
+		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, p, st) : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, p, st);
+	FIRST_SHAPES(X)
+#undef X
+	set_error("conv_first: no kernel instance"); return CB200_ERR_UNSUPPORTED;
+}
+template <typename T>
+static int first_wgrad_typed(const cb200_conv_desc* d, const CUtensorMap& mdy, const FirstParams& p, int grid, cudaStream_t st) {
+#define X(C_, FH_, FW_, KP_) \
+	if (d->in_c == C_ && d->f_h == FH_ && d->f_w == FW_) return launch_first_wgrad<T, C_, FH_, FW_, KP_>(mdy, p, grid, st);
+	FIRST_SHAPES(X)
+#undef X
+	set_error("conv_first: no kernel instance"); return CB200_ERR_UNSUPPORTED;
+}
+
+int conv_first_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, void* y, cudaStream_t st) {
+	const int kp = kp_of(d);
+	FirstParams p;
+	fill_params(d, x_raw, 128, p);
+	p.out = y;
+	const int bn = p.n_pad > 32 ? 64 : 32;
+	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, bn, 0, 0);
+	CUtensorMap mb;
+	int rc = make_w_map(&mb, w->w_fwd, d->dtype, kp, 1, d->out_c, kp, bn, swizzle_for(kp));
+	if (rc) return rc;
+	if (d->dtype == CB200_FP16) return first_fwd_typed<__half>(d, mb, p, st);
+	return first_fwd_typed<__nv_bfloat16>(d, mb, p, st);
+}
+
+int conv_first_wgrad(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, const void* dy, cudaStream_t st) {
+	const int kp = kp_of(d);
+	FirstParams p;
+	fill_params(d, x_raw, 64, p);
+	p.grad = w->grad;
+	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, kp, 1, 1);
+	CUtensorMap mdy;
+	int rc = make_act_map(&mdy, dy, d->dtype, p.n_pad, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B);
+	if (rc) return rc;
+	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+	p.tiles_per_cta = ceil_div(p.num_tiles, grid);
+	grid = ceil_div(p.num_tiles, p.tiles_per_cta);
+	if (cudaMemsetAsync(w->grad, 0, sizeof(float) * (size_t)d->out_c * kp, st) != cudaSuccess) { set_error("wgrad memset failed"); return CB200_ERR_CUDA; }
+	if (d->dtype == CB200_FP16) return first_wgrad_typed<__half>(d, mdy, p, grid, st);
+	return first_wgrad_typed<__nv_bfloat16>(d, mdy, p, grid, st);
+}
+
+}  // namespace cb200

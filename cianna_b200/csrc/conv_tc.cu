@@ -51,7 +51,7 @@ static int load_encode() {
 }
 
 // rank-4 map over act[n][y][x][c] (c fastest).  box = (bc, bw, bh, bn)
-static int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n,
+int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n,
                         int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw) {
 	int rc = load_encode(); if (rc) return rc;
 	const cuuint64_t es = 2;
@@ -66,7 +66,7 @@ static int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int
 	return CB200_OK;
 }
 // rank-3 map over w[row][tap][c] (c fastest). box = (bc, 1, brow)
-static int make_w_map(CUtensorMap* m, const void* base, int dtype, int cp, int taps, int rows, int bc, int brow, CUtensorMapSwizzle sw) {
+int make_w_map(CUtensorMap* m, const void* base, int dtype, int cp, int taps, int rows, int bc, int brow, CUtensorMapSwizzle sw) {
 	int rc = load_encode(); if (rc) return rc;
 	const cuuint64_t es = 2;
 	cuuint64_t dims[3] = {(cuuint64_t)cp, (cuuint64_t)taps, (cuuint64_t)rows};
@@ -81,7 +81,7 @@ static int make_w_map(CUtensorMap* m, const void* base, int dtype, int cp, int t
 }
 
 // choose the TWxTHxTN pixel rectangle (product = npix, all powers of two) that wastes the least work
-static void choose_rect(int W, int H, int N, int npix, int& tw, int& th, int& tn) {
+void choose_rect(int W, int H, int N, int npix, int& tw, int& th, int& tn) {
 	double best = 1e30;
 	tw = npix; th = 1; tn = 1;
 	for (int a = 1; a <= npix; a <<= 1)
@@ -350,7 +350,7 @@ static int dispatch_igemm(int bn, int bk, const CUtensorMap& ma, const CUtensorM
 // channel block of the K loop: the last block of a tap may run past the tensor (TMA zero-fills it)
 static int pick_bk(int cp) { return cp >= 64 ? 64 : (cp >= 32 ? 32 : (cp >= 16 ? 16 : 0)); }
 static int pick_bn(int n_pad) { return n_pad > 128 ? 256 : n_pad > 64 ? 128 : n_pad > 32 ? 64 : n_pad > 16 ? 32 : 16; }
-static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B; }
+CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B; }
 
 static bool tc_common_ok(const cb200_conv_desc* d) {
 	if (d->dtype != CB200_FP16 && d->dtype != CB200_BF16) return false;

@@ -184,7 +184,14 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	/* first layer on an input with very few channels (RGB / grey): the layout import unrolls the receptive fields into
 	 * patch rows so that the layer runs on the tensor-core GEMM kernels (include/cianna_b200.h, cb200_import_input_patches) */
 	p->desc.input_is_patches = (previous == NULL && cb200_round_channels(pc) < 16) ? 1 : 0;
-	if (p->desc.input_is_patches) {
+	if (p->desc.input_is_patches && cb200_conv_first_direct(&p->desc)) {
+		/* ... or, for the usual first-layer shapes, the kernels build those rows in shared memory straight from the
+		 * dataset batch: no import pass, no patch tensor in HBM; the layer's input pointer is the batch itself */
+		p->desc.input_is_patches = 2;
+		CB_CHECK(cb200_free(net->input));
+		net->input = NULL;
+		net->patch_desc = &p->desc;
+	} else if (p->desc.input_is_patches) {
 		size_t bytes = (size_t)net->batch_size * current->out_h * current->out_w * cb200_patch_width(pc, f_size[1], f_size[0]) * cb200_dtype_size(net->dtype);
 		CB_CHECK(cb200_free(net->input));
 		net->input = dev_alloc(bytes);

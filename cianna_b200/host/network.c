@@ -261,7 +261,9 @@ void cb_load_batch(network *net, const float *input, const float *target)
 static void use_device_batch(network *net, const void *input_dev)
 {
 	/* dataset layout -> channels-last (or -> first-layer patch rows) */
-	if (net->patch_desc != NULL) {
+	if (net->patch_desc != NULL && net->patch_desc->input_is_patches == 2) {
+		net->input = (void *)input_dev;      /* the first layer reads the dataset batch directly */
+	} else if (net->patch_desc != NULL) {
 		const cb200_conv_desc *d = net->patch_desc;
 		CB_CHECK(cb200_import_input_patches(net->input, input_dev, net->dtype, net->batch_size, d->in_c, d->in_h, d->in_w,
 			d->f_h, d->f_w, d->stride_h, d->stride_w, d->pad_h, d->pad_w, d->out_h, d->out_w, d->bias_value, NULL));

@@ -158,8 +158,14 @@ typedef struct {
 	cb200_activ activ;    /* this layer's activation (fused in the forward epilogue) */
 	int input_is_patches; /* 1: `x` is the patch tensor made by cb200_import_input_patches (first layer with few
 	                         input channels); the layer then runs as a 1x1 GEMM over cb200_patch_width() columns
-	                         whose last real column is the bias input, w_fwd/grad are [out_c][patch_width] */
+	                         whose last real column is the bias input, w_fwd/grad are [out_c][patch_width];
+	                         2: `x` is the dataset batch itself, [batch][in_c*in_h*in_w + 1] values of `dtype`: the patch
+	                         rows are built in shared memory inside the forward / weight-gradient kernels and never
+	                         touch HBM (allowed when cb200_conv_first_direct() returns 1; weight buffers as in mode 1) */
 } cb200_conv_desc;
+/* 1 when a first layer described by `d` (input_is_patches != 0) can run in mode 2: 16-bit compute type, 3x3 filters on
+ * 1-3 channels or 5x5 on one channel, 8..64 filters, tensor-core path not disabled by cb200_force_simt. */
+int cb200_conv_first_direct(const cb200_conv_desc* d);
 
 /* Compute-side weights of one conv (or dense) layer, all device pointers owned by the caller:
  *   master : FP32 [out_c][k_ref] in the REFERENCE layout (k_ref = f_h*f_w*in_c + 1, column order

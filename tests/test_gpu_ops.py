@@ -312,3 +312,94 @@ def test_group_norm_max_pool_fused_equals_unfused(cabi, cfg, dtype_name):
     assert rel_err(y2, ref_p) < tol
     if dtype_name == "FP32":
         assert (m2 != ref_m).mean() < 1e-3      # only exact FP32 ties may resolve differently after rounding
+
+
+# geometry: (batch, in_c, height, width, out_c, f, pad, stride)
+FIRST_DIRECT = [
+    (4, 3, 16, 20, 32, 3, 1, 1),    # the Darknet19 first layer in small: RGB, 3x3, 32 filters (KP=32, 64B swizzle)
+    (3, 3, 13, 11, 24, 3, 1, 1),    # odd sizes, partial tiles, filters not a multiple of 32
+    (2, 1, 28, 28, 16, 5, 2, 1),    # grey 5x5 (KP=32)
+    (5, 1, 12, 12, 8, 3, 0, 1),     # grey 3x3, no padding (KP=16, 32B swizzle)
+    (2, 2, 10, 14, 64, 3, 1, 1),    # two channels, 64 filters (BN=64)
+    (3, 3, 17, 17, 40, 3, 1, 2),    # stride 2
+    (130, 3, 4, 4, 32, 3, 1, 1),    # tiles spanning many images
+]
+
+
+@pytest.mark.parametrize("dtype_name", ["FP16", "BF16"])
+@pytest.mark.parametrize("cfg", FIRST_DIRECT)
+def test_first_layer_direct_bit_exact(cabi, cfg, dtype_name):
+    """input_is_patches = 2: the first layer reads the dataset batch and builds its patch rows in shared memory
+    (conv_first.cu). Integer-valued tensors -> every product and partial sum is exact: forward and weight gradient must
+    equal the im2col oracle BIT FOR BIT (receptive-field addressing, zero padding, swizzled operand layout, bias column)."""
+    import ctypes
+    B, C, H, W, N, f, pad, stride = cfg
+    dtype = getattr(cabi, dtype_name)
+    L = cabi.lib()
+    L.cb200_patch_width.restype = ctypes.c_int
+    rng = np.random.default_rng(13)
+    x = np.empty((B, C * H * W + 1), np.float32)
+    x[:, :-1] = _int_tensor(rng, (B, C * H * W), 0.3)
+    x[:, -1] = 1.0
+    w = _int_tensor(rng, (N, f * f * C + 1), 0.4)
+    Ho, Wo = (H + 2 * pad - f) // stride + 1, (W + 2 * pad - f) // stride + 1
+    d = cabi.ConvDesc(dtype, B, B, C, H, W, N, Ho, Wo, f, f, stride, stride, pad, pad, 1.0, cabi.activ(cabi.LINEAR), 1)
+    assert L.cb200_conv_first_direct(ctypes.byref(d)) == 1
+    d.input_is_patches = 2
+    kp = L.cb200_patch_width(C, f, f)
+    es = L.cb200_dtype_size(dtype)
+    bufs = dict(master=cabi.DevBuf.from_numpy(w), moment=cabi.DevBuf(w.nbytes), w_fwd=cabi.DevBuf(N * kp * es),
+                w_bwd=cabi.DevBuf(C * f * f * cabi.round8(N) * es), bias_w=cabi.DevBuf(N * 4), grad=cabi.DevBuf(N * kp * 4), grad_b=cabi.DevBuf(N * 4))
+    wts = cabi.ConvWeights(*[bufs[k].ptr for k in ("master", "moment", "w_fwd", "w_bwd", "bias_w", "grad", "grad_b")])
+    cabi.check(L.cb200_conv_prepare_weights(ctypes.byref(d), ctypes.byref(wts), None))
+    xt = np.empty(x.size, np.uint16)
+    cabi.check(L.cb200_host_cast_from_f32(xt.ctypes.data, dtype, x.ctypes.data, x.size))
+    src = cabi.DevBuf.from_numpy(xt)
+    y = cabi.DevBuf(B * Ho * Wo * cabi.round8(N) * es)
+    cabi.check(L.cb200_conv_forward(ctypes.byref(d), ctypes.byref(wts), src.ptr, y.ptr, None))
+    assert L.cb200_last_conv_impl().decode() == "tcgen05"
+    # oracle on a square-agnostic im2col: reuse the generic routine through explicit patches
+    xi = x[:, :-1].reshape(B, C, H, W)
+    xp = np.pad(xi, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    cols = np.empty((B, Ho * Wo, C * f * f + 1), np.float32)
+    for oy in range(Ho):
+        for ox in range(Wo):
+            cols[:, oy * Wo + ox, :-1] = xp[:, :, oy * stride: oy * stride + f, ox * stride: ox * stride + f].reshape(B, -1)
+    cols[:, :, -1] = 1.0
+    ref = np.einsum("bpk,nk->nbp", cols.astype(np.float64), w.astype(np.float64)).astype(np.float32)
+    got = cabi.download_act(y, dtype, B, N, Ho, Wo)
+    assert np.array_equal(got, ref), "forward differs: max |d| = %g" % np.abs(got - ref).max()
+    dy = _int_tensor(rng, (N, B, Ho * Wo), 0.6)
+    dyb = cabi.upload_act(dy, dtype, B, N, Ho, Wo)
+    cabi.check(L.cb200_conv_backward_weights(ctypes.byref(d), ctypes.byref(wts), src.ptr, dyb.ptr, None))
+    g = bufs["grad"].to_numpy(np.float32, (N, kp))
+    gref = np.einsum("nbp,bpk->nk", dy.astype(np.float64), cols.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(g[:, : C * f * f + 1], gref), "weight gradient differs: max |d| = %g" % np.abs(g[:, : C * f * f + 1] - gref).max()
+    assert not g[:, C * f * f + 1:].any()
+    for b in list(bufs.values()) + [src, y, dyb]:
+        b.free()
+
+
+def test_first_layer_direct_activation_and_tail(cabi):
+    """ReLU epilogue, samples beyond `length` forced to zero, pad output channels zero"""
+    import ctypes
+    B, C, H, W, N, f, pad = 6, 3, 12, 12, 20, 3, 1
+    dtype = cabi.FP16
+    L = cabi.lib()
+    L.cb200_patch_width.restype = ctypes.c_int
+    rng = np.random.default_rng(14)
+    x = np.empty((B, C * H * W + 1), np.float32)
+    x[:, :-1] = (rng.standard_normal((B, C * H * W)) * 0.5).astype(np.float16).astype(np.float32)
+    x[:, -1] = 0.1
+    w = (rng.standard_normal((N, f * f * C + 1)) * 0.3).astype(np.float32)
+    layer = cabi.ConvLayer(dtype, B, C, H, W, N, f, 1, pad, bias_value=0.1, act=cabi.activ(cabi.RELU), length=4)
+    layer.d.input_is_patches = 2
+    layer.set_weights(w)
+    xt = np.empty(x.size, np.uint16)
+    cabi.check(L.cb200_host_cast_from_f32(xt.ctypes.data, dtype, x.ctypes.data, x.size))
+    src = cabi.DevBuf.from_numpy(xt)
+    y = cabi.download_act(layer.forward(src), dtype, B, N, H, W)
+    xq = x.copy(); xq[:, -1] = np.float32(np.float16(0.1))
+    pre, _ = co.conv_forward(xq, w.astype(np.float16).astype(np.float32), True, B, C, H, H, f, 1, pad, float(np.float16(0.1)))
+    assert rel_err(y, co.relu_forward(pre, 4)) < TOL_MIXED
+    assert not y[:, 4:, :].any()
