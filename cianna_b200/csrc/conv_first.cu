@@ -11,7 +11,7 @@
 // images once, write (forward) or read (weight gradient) the layer's output once".
 //
 //   forward : D[128 px][BN filters] = patch[128 px][KP] * W[filters][KP]^T     (K-major A built on chip, B by TMA once)
-//             8 builder warps (two groups alternating tiles), 1 MMA warp, 4 epilogue warps, TMEM accumulator ring
+//             16 builder warps (four groups taking tiles in turn), 1 MMA warp, 8 epilogue warps (two groups), TMEM accumulator ring
 //   wgrad   : G[filters][KP] += dy[px][filters]^T * patch[px][KP]               (both MN-major; dy by TMA, patches built)
 //             persistent CTAs over contiguous pixel ranges, FP32 red.add of the per-CTA partial at the end
 // Column order of a patch row = upstream's filter column order c*taps + tap, then the bias input, zero padded to KP.
@@ -38,7 +38,7 @@ struct FirstParams {
 	cb200_activ activ;
 	void* out;                   // forward: layer output [N][H][W][n_pad]
 	float* grad;                 // wgrad: [n_real][KP]
-	int tiles_per_cta;           // wgrad
+	int tiles_per_cta;           // contiguous run of tiles owned by one CTA
 	uint32_t idesc;
 };
 
@@ -96,7 +96,8 @@ template <> __device__ __forceinline__ unsigned short bits_of<__half>(float v) {
 template <> __device__ __forceinline__ unsigned short bits_of<__nv_bfloat16>(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
 // ================================================================ forward
-constexpr int FWD_BUILD_WARPS = 8, FWD_THREADS = (FWD_BUILD_WARPS + 1 + 4) * 32;
+constexpr int FWD_BUILD_GROUPS = 4, FWD_BUILD_WARPS = 4 * FWD_BUILD_GROUPS, FWD_EPI_GROUPS = 2;
+constexpr int FWD_THREADS = (FWD_BUILD_WARPS + 1 + 4 * FWD_EPI_GROUPS) * 32;
 template <int KP, int BN> struct FirstFwdCfg {
 	static constexpr int A_BYTES = 128 * KP * 2;
 	static constexpr int STAGES = 8;
@@ -137,18 +138,20 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot_ptr;
+	// a CTA owns a contiguous run of tiles: neighbouring tiles share input rows, which keeps them in L1
+	const int tile0 = blockIdx.x * p.tiles_per_cta;
+	const int n_tiles = min(p.tiles_per_cta, p.num_tiles - tile0);
 
 	if (warp < FWD_BUILD_WARPS) {
-		// ===================== builders: group g fills the stages of the CTA's tiles g, g+2, ... =====================
+		// ===================== builders: group g fills the stages of the tiles g, g+4, ... of the run =====================
 		const int grp = warp >> 2;
 		const int row = (warp & 3) * 32 + lane;
 		const T* __restrict__ src = reinterpret_cast<const T*>(p.src);
 		const size_t img_stride = (size_t)p.c * p.h * p.w + 1;
 		const unsigned short bias_bits = bits_of<T>(p.bias_value);
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
-		int it = 0;
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
-			if ((it & 1) != grp) continue;
+		for (int it = grp; it < n_tiles; it += FWD_BUILD_GROUPS) {
+			const int tile = tile0 + it;
 			const int stage = it % Cfg::STAGES;
 			const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
 			const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
@@ -166,8 +169,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 			mbar_arrive_expect_tx(bfull_bar, Cfg::B_BYTES);
 			tma_load_3d(b_smem, &tmap_b, bfull_bar, 0, 0, 0);
 			mbar_wait(bfull_bar, 0);
-			int it = 0;
-			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+			for (int it = 0; it < n_tiles; it++) {
 				const int stage = it % Cfg::STAGES, acc = it % Cfg::ACC_STAGES;
 				const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u, acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -188,14 +190,15 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 	} else {
 		// ===================== epilogue: activation, cast, store (the bias is a GEMM column) =====================
 		const int quad = warp & 3;
+		const int egrp = (warp - MMA_WARP - 1) >> 2;
 		const int row = quad * 32 + lane;
 		T* __restrict__ out = reinterpret_cast<T*>(p.out);
 		const int act = p.activ.type, n_real = p.n_real, n_pad = p.n_pad;
 		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta;
 		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
-		int it = 0;
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+		for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
+			const int tile = tile0 + it;
 			const int acc = it % Cfg::ACC_STAGES;
 			const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
 			const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
@@ -248,7 +251,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 }
 
 // ================================================================ weight gradient
-constexpr int WG_BUILD_WARPS = 8, WG_THREADS = (2 + 4 + WG_BUILD_WARPS) * 32;
+constexpr int WG_BUILD_WARPS = 16, WG_THREADS = (2 + 4 + WG_BUILD_WARPS) * 32;
 template <int KP> struct FirstWgCfg {
 	static constexpr int KPIX = 64;
 	static constexpr int A_SLAB_BYTES = KPIX * 128;                 // dy: [64 px][64 filters], 128B swizzle
@@ -351,7 +354,7 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 			}
 		}
 	} else {
-		// ===================== builders: pair q fills the patch tile of steps q, q+4, ... =====================
+		// ===================== builders: warp pair q fills the patch tile of steps q, q+8, ... =====================
 		const int bw = warp - 6;
 		const int pair = bw >> 1;
 		const int row = (bw & 1) * 32 + lane;
@@ -401,7 +404,7 @@ static void fill_params(const cb200_conv_desc* d, const void* src, int npix, Fir
 }
 
 template <typename T, int C, int FH, int FW, int KP, int BN>
-static int launch_first_fwd(const CUtensorMap& mb, const FirstParams& p, cudaStream_t st) {
+static int launch_first_fwd(const CUtensorMap& mb, const FirstParams& p, int grid, cudaStream_t st) {
 	using Cfg = FirstFwdCfg<KP, BN>;
 	static bool configured = false;
 	auto kern = conv_first_fwd_kernel<T, C, FH, FW, KP, BN>;
@@ -411,7 +414,6 @@ static int launch_first_fwd(const CUtensorMap& mb, const FirstParams& p, cudaStr
 		}
 		configured = true;
 	}
-	const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
 	kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(mb, p);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
@@ -436,11 +438,11 @@ static int launch_first_wgrad(const CUtensorMap& mdy, const FirstParams& p, int 
 #define FIRST_SHAPES(X)  X(3, 3, 3, 32) X(1, 3, 3, 16) X(1, 5, 5, 32) X(2, 3, 3, 32)
 
 template <typename T>
-static int first_fwd_typed(const cb200_conv_desc* d, const CUtensorMap& mb, const FirstParams& p, cudaStream_t st) {
+static int first_fwd_typed(const cb200_conv_desc* d, const CUtensorMap& mb, const FirstParams& p, int grid, cudaStream_t st) {
 	const int bn = p.n_pad > 32 ? 64 : 32;
 #define X(C_, FH_, FW_, KP_) \
 	if (d->in_c == C_ && d->f_h == FH_ && d->f_w == FW_) \
-		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, p, st) : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, p, st);
+		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, p, grid, st) : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, p, grid, st);
 	FIRST_SHAPES(X)
 #undef X
 	set_error("conv_first: no kernel instance"); return CB200_ERR_UNSUPPORTED;
@@ -464,8 +466,11 @@ int conv_first_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	CUtensorMap mb;
 	int rc = make_w_map(&mb, w->w_fwd, d->dtype, kp, 1, d->out_c, kp, bn, swizzle_for(kp));
 	if (rc) return rc;
-	if (d->dtype == CB200_FP16) return first_fwd_typed<__half>(d, mb, p, st);
-	return first_fwd_typed<__nv_bfloat16>(d, mb, p, st);
+	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+	p.tiles_per_cta = ceil_div(p.num_tiles, grid);
+	grid = ceil_div(p.num_tiles, p.tiles_per_cta);
+	if (d->dtype == CB200_FP16) return first_fwd_typed<__half>(d, mb, p, grid, st);
+	return first_fwd_typed<__nv_bfloat16>(d, mb, p, grid, st);
 }
 
 int conv_first_wgrad(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, const void* dy, cudaStream_t st) {
