@@ -111,7 +111,119 @@ struct IgemmParams {
 	const void* prev_out;
 	cb200_activ activ;           // forward: this layer; dgrad: the previous layer
 	uint32_t idesc;
+	// halo-reuse variant (conv_halo_kernel)
+	int halo_w;                  // pixels per halo row = tw + f_w - 1
+	int a_stage_bytes, a_stages; // one halo tile (rounded up to 1024 B), ring depth
+	int b_blk_bytes;             // one (tap, channel block) of the resident filter bank
 };
+
+// ---------------------------------------------------------------- shared epilogue of the forward / dgrad kernels
+// Eight epilogue warps in two groups of four (one warp per TMEM lane quadrant): group g drains the accumulators of the
+// CTA's tiles g, g+2, g+4, ... so two tiles are in their epilogue at any time while the MMA warp runs up to ACC_STAGES
+// tiles ahead.  tcgen05.ld -> bias + activation (forward) or the previous layer's derivative (dgrad) -> cast -> store.
+template <typename T, int BN, int ACC_STAGES>
+__device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              float* bias_rows, int warp, int lane, int first_warp) {
+	const int ew = warp - first_warp;                // 0..7
+	const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+	const int grp = ew >> 2;                         // epilogue group
+	const int gtid = (ew & 3) * 32 + lane;           // 0..127 inside the group
+	const int row = quad * 32 + lane;                // row of the 128-pixel tile
+	T* __restrict__ out = reinterpret_cast<T*>(p.out);
+	const T* __restrict__ prev = reinterpret_cast<const T*>(p.prev_out);
+	// everything the inner loop needs, in registers (the parameter block lives in constant memory)
+	const int act = p.activ.type, mode = p.mode, n_real = p.n_real, n_pad = p.n_pad, length = p.length;
+	const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta, bias_value = p.bias_value;
+	const float* __restrict__ bias_w = p.bias_w;
+	const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+	const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
+	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
+	float* bs = bias_rows + grp * 256;
+	int it = 0;
+	for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+		if ((it & 1) != grp) continue;
+		const int acc = it % ACC_STAGES;
+		const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
+		const int mt = tile % tiles_m, nt = tile / tiles_m;
+		const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
+		const int px = twi * tw + (row % tw);
+		const int py = thi * th + (row / tw) % th;
+		const int pn = tni * tn + row / (tw * th);
+		const bool row_ok = px < PW && py < PH && pn < PN;
+		const size_t pix = ((size_t)pn * PH + py) * PW + px;
+		const bool dead = mask_tail && pn >= length;
+		// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
+		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
+		if (mode == 0)
+			for (int c = gtid; c < BN; c += 128) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
+		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+
+		mbar_wait(tfull0 + 8u * acc, acc_phase);
+		tc_fence_after();
+		const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+		for (int c0 = 0; c0 < BN; c0 += 32) {
+			uint32_t r[32];
+			if (BN - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
+			else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
+#pragma unroll
+				for (int j = 0; j < 16; j++) { r[j] = h[j]; r[16 + j] = 0; } }
+			tmem_ld_wait();
+			const int col0 = nt * BN + c0;
+#pragma unroll
+			for (int v = 0; v < 4; v++) {
+				const int col = col0 + v * 8;
+				if (!row_ok || col >= n_pad || c0 + v * 8 >= BN) continue;
+				float o[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++) o[j] = __uint_as_float(r[v * 8 + j]);
+				if (dead) {
+#pragma unroll
+					for (int j = 0; j < 8; j++) o[j] = 0.0f;
+				} else if (mode == 0) {
+					const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
+					o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+					if (act == CB200_RELU) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							const float z = o[j];
+							const float hi = sat + (z - sat) * leak;
+							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+						}
+					} else if (act == CB200_LOGISTIC) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) o[j] = 1.0f / (1.0f + expf(fminf(-beta * o[j], sat)));
+					}
+					if (col + 8 > n_real) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+					}
+				} else {
+					if (hook) {
+						float pv[8];
+						load8<T>(prev + pix * n_pad + col, pv);
+						if (act == CB200_RELU) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) o[j] = (pv[j] <= 0.0f || pv[j] > sat) ? o[j] * leak : o[j];
+						} else {
+#pragma unroll
+							for (int j = 0; j < 8; j++) o[j] = o[j] * beta * pv[j] * (1.0f - pv[j]);
+						}
+					}
+					if (col + 8 > n_real) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+					}
+				}
+				store8<T>(out + pix * n_pad + col, o);
+			}
+			__syncwarp();        // reconverge before the next warp-collective tcgen05.ld
+		}
+		tc_fence_before();
+		__syncwarp();
+		if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+	}
+}
 
 template <int BN, int BK>
 struct IgemmCfg {
@@ -210,108 +322,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 			}
 		}
 	} else {
-		// ===================== epilogue warps: two groups of four (one warp per TMEM lane quadrant) =====================
-		// group g drains the accumulators of the CTA's tiles g, g+2, g+4, ... so two tiles are in their epilogue at any
-		// time while the MMA warp runs up to ACC_STAGES tiles ahead
-		const int ew = warp - 2;                         // 0..7
-		const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-		const int grp = ew >> 2;                         // epilogue group
-		const int gtid = (ew & 3) * 32 + lane;           // 0..127 inside the group
-		const int row = quad * 32 + lane;                // row of the 128-pixel tile
-		T* __restrict__ out = reinterpret_cast<T*>(p.out);
-		const T* __restrict__ prev = reinterpret_cast<const T*>(p.prev_out);
-		// everything the inner loop needs, in registers (the parameter block lives in constant memory)
-		const int act = p.activ.type, mode = p.mode, n_real = p.n_real, n_pad = p.n_pad, length = p.length;
-		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta, bias_value = p.bias_value;
-		const float* __restrict__ bias_w = p.bias_w;
-		const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
-		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
-		const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
-		float* bs = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw))) + grp * 256;
-		int it = 0;
-		for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
-			if ((it & 1) != grp) continue;
-			const int acc = it % Cfg::ACC_STAGES;
-			const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
-			const int mt = tile % tiles_m, nt = tile / tiles_m;
-			const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
-			const int px = twi * tw + (row % tw);
-			const int py = thi * th + (row / tw) % th;
-			const int pn = tni * tn + row / (tw * th);
-			const bool row_ok = px < PW && py < PH && pn < PN;
-			const size_t pix = ((size_t)pn * PH + py) * PW + px;
-			const bool dead = mask_tail && pn >= length;
-			// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
-			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
-			if (mode == 0)
-				for (int c = gtid; c < BN; c += 128) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
-			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-
-			mbar_wait(tfull_bar(acc), acc_phase);
-			tc_fence_after();
-			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-			for (int c0 = 0; c0 < BN; c0 += 32) {
-				uint32_t r[32];
-				if (BN - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
-				else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
-#pragma unroll
-					for (int j = 0; j < 16; j++) { r[j] = h[j]; r[16 + j] = 0; } }
-				tmem_ld_wait();
-				const int col0 = nt * BN + c0;
-#pragma unroll
-				for (int v = 0; v < 4; v++) {
-					const int col = col0 + v * 8;
-					if (!row_ok || col >= n_pad || c0 + v * 8 >= BN) continue;
-					float o[8];
-#pragma unroll
-					for (int j = 0; j < 8; j++) o[j] = __uint_as_float(r[v * 8 + j]);
-					if (dead) {
-#pragma unroll
-						for (int j = 0; j < 8; j++) o[j] = 0.0f;
-					} else if (mode == 0) {
-						const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
-						o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-						if (act == CB200_RELU) {
-#pragma unroll
-							for (int j = 0; j < 8; j++) {
-								const float z = o[j];
-								const float hi = sat + (z - sat) * leak;
-								o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
-							}
-						} else if (act == CB200_LOGISTIC) {
-#pragma unroll
-							for (int j = 0; j < 8; j++) o[j] = 1.0f / (1.0f + expf(fminf(-beta * o[j], sat)));
-						}
-						if (col + 8 > n_real) {
-#pragma unroll
-							for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
-						}
-					} else {
-						if (hook) {
-							float pv[8];
-							load8<T>(prev + pix * n_pad + col, pv);
-							if (act == CB200_RELU) {
-#pragma unroll
-								for (int j = 0; j < 8; j++) o[j] = (pv[j] <= 0.0f || pv[j] > sat) ? o[j] * leak : o[j];
-							} else {
-#pragma unroll
-								for (int j = 0; j < 8; j++) o[j] = o[j] * beta * pv[j] * (1.0f - pv[j]);
-							}
-						}
-						if (col + 8 > n_real) {
-#pragma unroll
-							for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
-						}
-					}
-					store8<T>(out + pix * n_pad + col, o);
-				}
-				__syncwarp();        // reconverge before the next warp-collective tcgen05.ld
-			}
-			tc_fence_before();
-			__syncwarp();
-			if (lane == 0) mbar_arrive(tempty_bar(acc));
-		}
+		// ===================== epilogue warps =====================
+		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+		epilogue_loop<T, BN, Cfg::ACC_STAGES>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 2);
 	}
 
 	tc_fence_before();
@@ -361,6 +374,180 @@ static bool tc_common_ok(const cb200_conv_desc* d) {
 bool conv_tc_fwd_supported(const cb200_conv_desc* d) { return tc_common_ok(d) && pick_bk(round8(d->in_c)) != 0; }
 bool conv_tc_dgrad_supported(const cb200_conv_desc* d) { return tc_common_ok(d) && pick_bk(round8(d->out_c)) != 0 && round8(d->in_c) >= 16; }
 
+// ================================================================ halo-reuse forward / dgrad kernel
+// For filters larger than 1x1 on LARGE maps with FEW channels the per-tap kernel above is bound by the L2 -> SM path:
+// every tap re-fetches its own shifted copy of the 128-pixel tile (9x the activation bytes for 3x3) and, per tile, the
+// whole filter bank.  This variant fetches, per channel block, ONE halo tile [(16+f_h-1) rows][(8+f_w-1) px][BK ch] with a
+// single TMA box and runs all taps from it: tap (ky,kx) is the same shared-memory tile read through a K-major descriptor
+// whose start address is moved by (ky*halo_w + kx) pixel rows and whose stride between 8-row groups is one halo row
+// (M tile = 16 image rows x 8 pixels, so 8-row group g is image row g).  The swizzle XOR is a function of the absolute
+// shared-memory address, so such unaligned starts address exactly the bytes TMA wrote (scripts/exp/halo_desc_probe.cu
+// checks this on the hardware for the 128B and 64B swizzles).  The filter bank of the layer (all taps, all channel
+// blocks, <= ~150 KB) is loaded once per CTA and stays resident.  L2 -> SM traffic per tile: 1.4x the tile's activation
+// bytes instead of 9x + the filters.
+template <int BN>
+struct HaloCfg {
+	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;
+	static constexpr int ACC_COLS = ACC_STAGES * BN;
+	static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+	static constexpr int MAX_A_STAGES = 6;
+};
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_THREADS = 11 * 32;    // A producer, B loader, MMA issuer, 8 epilogue warps
+
+template <typename T, int BN, int BK>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
+	using Cfg = HaloCfg<BN>;
+	constexpr uint32_t ROWB = BK * 2;
+	constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const int taps = p.f_h * p.f_w;
+	const uint32_t b_smem = smem_base + (uint32_t)(p.a_stages * p.a_stage_bytes);
+	const uint32_t bar_base = b_smem + (uint32_t)(taps * p.kc_blocks * p.b_blk_bytes);
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::MAX_A_STAGES + s); };
+	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_A_STAGES + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::MAX_A_STAGES + 4 + s); };
+	const uint32_t bfull_bar = bar_base + 8u * (2 * Cfg::MAX_A_STAGES + 8);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::MAX_A_STAGES + 9);
+	const uint32_t bias_smem = bar_base + 256u;
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_a);
+		prefetch_tensormap(&tmap_b);
+		for (int s = 0; s < p.a_stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+		mbar_init(bfull_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == 2) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+	const uint32_t a_tx = (uint32_t)((HALO_TH + p.f_h - 1) * p.halo_w) * ROWB;
+
+	if (warp == 0) {
+		// ===================== halo producer: one TMA box per (tile, channel block) =====================
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+				const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
+				for (int cb = 0; cb < p.kc_blocks; cb++) {
+					mbar_wait(empty_bar(stage), phase ^ 1u);
+					mbar_arrive_expect_tx(full_bar(stage), a_tx);
+					tma_load_4d(smem_base + (uint32_t)(stage * p.a_stage_bytes), &tmap_a, full_bar(stage), cb * BK,
+					            twi * HALO_TW + p.off_w, thi * HALO_TH + p.off_h, tni);
+					if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===================== filter bank: loaded once, resident for the CTA's life =====================
+		if (lane == 0) {
+			mbar_arrive_expect_tx(bfull_bar, (uint32_t)(taps * p.kc_blocks * p.b_blk_bytes));
+			for (int tap = 0; tap < taps; tap++)
+				for (int cb = 0; cb < p.kc_blocks; cb++)
+					tma_load_3d(b_smem + (uint32_t)((tap * p.kc_blocks + cb) * p.b_blk_bytes), &tmap_b, bfull_bar, cb * BK, tap, 0);
+		}
+	} else if (warp == 2) {
+		// ===================== MMA issuer =====================
+		if (lane == 0) {
+			mbar_wait(bfull_bar, 0);
+			int stage = 0; uint32_t phase = 0;
+			int acc = 0; uint32_t acc_phase = 0;
+			const uint32_t sbo = (uint32_t)p.halo_w * ROWB;
+			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+				for (int cb = 0; cb < p.kc_blocks; cb++) {
+					mbar_wait(full_bar(stage), phase);
+					tc_fence_after();
+					const uint32_t sa = smem_base + (uint32_t)(stage * p.a_stage_bytes);
+					for (int tap = 0; tap < taps; tap++) {
+						const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
+						const uint32_t a0 = sa + (uint32_t)(ky * p.halo_w + kx) * ROWB;
+						const uint32_t b0 = b_smem + (uint32_t)((tap * p.kc_blocks + cb) * p.b_blk_bytes);
+#pragma unroll
+						for (int kk = 0; kk < BK / 16; kk++) {
+							const uint64_t da = make_smem_desc(a0 + kk * 32, 16, sbo, LAYOUT);
+							const uint64_t db = make_smem_desc(b0 + kk * 32, 16, 8 * ROWB, LAYOUT);
+							mma_f16_ss(d_tmem, da, db, p.idesc, (cb | tap | kk) != 0 ? 1u : 0u);
+						}
+					}
+					mma_commit(empty_bar(stage));
+					if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
+				}
+				mma_commit(tfull_bar(acc));
+				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+			}
+		}
+	} else {
+		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+		epilogue_loop<T, BN, Cfg::ACC_STAGES>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 3);
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 2) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+constexpr int HALO_SMEM_MAX = 225 * 1024;
+
+template <typename T, int BN, int BK>
+static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem_bytes, cudaStream_t st) {
+	static bool configured = false;
+	auto kern = conv_halo_kernel<T, BN, BK>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", HALO_SMEM_MAX); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+	kern<<<grid, HALO_THREADS, smem_bytes, st>>>(ma, mb, p);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+template <typename T>
+static int dispatch_halo(int bn, int bk, const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem, cudaStream_t st) {
+#define CASE(BN_, BK_) if (bn == BN_ && bk == BK_) return launch_halo<T, BN_, BK_>(ma, mb, p, smem, st)
+	CASE(128, 64); CASE(64, 64); CASE(32, 64); CASE(16, 64);
+	CASE(128, 32); CASE(64, 32); CASE(32, 32); CASE(16, 32);
+#undef CASE
+	set_error("conv_tc: no halo kernel instance for BN=%d BK=%d", bn, bk);
+	return CB200_ERR_UNSUPPORTED;
+}
+
+extern const char* g_last_conv_impl;
+int g_disable_halo = 0;     // test hook (cb200_force_simt bit 1): route everything through the per-tap kernel
+
+// Decide whether the layer goes to the halo kernel and, if so, fill its tiling; returns the dynamic smem size or 0.
+static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_w, int bk, int bn, IgemmParams& p) {
+	if (g_disable_halo || f_h * f_w == 1 || f_h > 5 || f_w > 5) return 0;
+	if (bk < 32 || bn > 128 || n_pad > bn) return 0;
+	if (out_w < HALO_TW || out_h < HALO_TH) return 0;
+	const double cover = (double)ceil_div(out_w, HALO_TW) * HALO_TW * ceil_div(out_h, HALO_TH) * HALO_TH / ((double)out_w * out_h);
+	if (cover > 1.15) return 0;
+	const int kcb = ceil_div(cin_p, bk);
+	const int b_blk = bn * bk * 2;
+	const int b_bytes = f_h * f_w * kcb * b_blk;
+	const int halo_w = HALO_TW + f_w - 1, halo_h = HALO_TH + f_h - 1;
+	const int a_stage = (halo_h * halo_w * bk * 2 + 1023) & ~1023;
+	const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias rows*/;
+	int stages = (HALO_SMEM_MAX - fixed - b_bytes) / a_stage;
+	if (stages > HaloCfg<16>::MAX_A_STAGES) stages = HaloCfg<16>::MAX_A_STAGES;
+	if (stages < 2) return 0;
+	p.halo_w = halo_w; p.a_stage_bytes = a_stage; p.a_stages = stages; p.b_blk_bytes = b_blk;
+	return fixed + b_bytes + stages * a_stage;
+}
+
 // GEMM over: input tensor `src` with cin_p channels on an (in_h, in_w) grid, weights wmat[rows=n_real][taps][cin_p],
 // output pixel grid (out_h, out_w), tap (0,0) reads input pixel (oy + off_h, ox + off_w).
 static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, int batch,
@@ -369,9 +556,32 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	const int bk = pick_bk(cin_p);
 	const int n_pad = round8(n_real);
 	const int bn = pick_bn(n_pad);
+	CUtensorMap ma, mb;
+	{
+		IgemmParams ph = p;
+		const int smem = halo_plan(cin_p, n_pad, f_h, f_w, out_h, out_w, bk, bn, ph);
+		if (smem > 0) {
+			int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, ph.halo_w, HALO_TH + f_h - 1, 1, swizzle_for(bk));
+			if (rc) return rc;
+			rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, bn, swizzle_for(bk));
+			if (rc) return rc;
+			ph.W = out_w; ph.H = out_h; ph.N = batch;
+			ph.tw = HALO_TW; ph.th = HALO_TH; ph.tn = 1;
+			ph.tiles_w = ceil_div(out_w, HALO_TW); ph.tiles_h = ceil_div(out_h, HALO_TH); ph.tiles_n = batch;
+			ph.tiles_m = ph.tiles_w * ph.tiles_h * ph.tiles_n;
+			ph.tiles_nn = 1;
+			ph.num_tiles = ph.tiles_m;
+			ph.f_h = f_h; ph.f_w = f_w; ph.off_h = off_h; ph.off_w = off_w;
+			ph.kc_blocks = ceil_div(cin_p, bk);
+			ph.n_real = n_real; ph.n_pad = n_pad;
+			ph.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
+			g_last_conv_impl = "tcgen05-halo";
+			if (dtype == CB200_FP16) return dispatch_halo<__half>(bn, bk, ma, mb, ph, smem, st);
+			return dispatch_halo<__nv_bfloat16>(bn, bk, ma, mb, ph, smem, st);
+		}
+	}
 	int tw, th, tn;
 	choose_rect(out_w, out_h, batch, 128, tw, th, tn);
-	CUtensorMap ma, mb;
 	int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, tw, th, tn, swizzle_for(bk));
 	if (rc) return rc;
 	rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, bn, swizzle_for(bk));

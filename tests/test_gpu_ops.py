@@ -403,3 +403,55 @@ def test_first_layer_direct_activation_and_tail(cabi):
     pre, _ = co.conv_forward(xq, w.astype(np.float16).astype(np.float32), True, B, C, H, H, f, 1, pad, float(np.float16(0.1)))
     assert rel_err(y, co.relu_forward(pre, 4)) < TOL_MIXED
     assert not y[:, 4:, :].any()
+
+
+# geometry: (batch, in_c, size, out_c, f, pad) - maps large enough for the 8x16 halo tile
+HALO_SHAPES = [
+    (2, 32, 32, 64, 3, 1),     # the Darknet19 second layer in small: BK=32 (64B swizzle), BN=64
+    (2, 64, 32, 128, 3, 1),    # third / fifth layer: BK=64 (128B swizzle), BN=128
+    (1, 128, 16, 64, 3, 1),    # two channel blocks (their data gradients: 128 -> 64)
+    (2, 64, 30, 32, 5, 2),     # 5x5 filter, partial tiles in both directions
+    (3, 40, 32, 24, 3, 1),     # channel counts that are not multiples of the block (zero-filled tails)
+    (2, 32, 40, 48, 3, 0),     # no padding (output 38x38, data gradient with full padding)
+]
+
+
+@pytest.mark.parametrize("dtype_name", ["FP16", "BF16"])
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+def test_conv_halo_kernel_bit_exact(cabi, shape, dtype_name):
+    """filters larger than 1x1 on large maps go through conv_halo_kernel (one halo tile per channel block, all taps read
+    from it through shifted descriptors, filter bank resident): bit for bit the im2col oracle, and identical to the
+    per-tap kernel on the same data"""
+    B, C, S, N, f, pad = shape
+    dtype = cabi.FP16 if dtype_name == "FP16" else cabi.BF16
+    L = cabi.lib()
+    rng = np.random.default_rng(hash(shape) % 2**31)
+    x = _int_tensor(rng, (C, B, S * S), 0.6)
+    w = _int_tensor(rng, (N, f * f * C + 1), 0.7)
+    w[:, -1] = rng.integers(-2, 3, N)
+    layer = cabi.ConvLayer(dtype, B, C, S, S, N, f, 1, pad, bias_value=1.0)
+    layer.set_weights(w)
+    xb = cabi.upload_act(x, dtype, B, C, S, S)
+    So = S + 2 * pad - f + 1
+    y = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+    assert L.cb200_last_conv_impl() == b"tcgen05-halo"
+    ref, col = co.conv_forward(x, w, False, B, C, S, S, f, 1, pad, 1.0)
+    assert np.abs(ref).max() < 256
+    assert np.array_equal(y, ref), "forward: %d wrong" % int((y != ref).sum())
+    dy = _int_tensor(rng, (N, B, So * So), 0.8)
+    dyb = cabi.upload_act(dy, dtype, B, N, So, So)
+    dx = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
+    halo_dgrad = L.cb200_last_conv_impl() == b"tcgen05-halo"
+    ref_dx = co.conv_backward_data(dy, w, B, C, S, S, f, 1, pad)
+    assert np.abs(ref_dx).max() < 256
+    assert np.array_equal(dx, ref_dx), "data gradient: %d wrong" % int((dx != ref_dx).sum())
+    assert halo_dgrad or cabi.round8(C) > 128 or cabi.round8(N) < 32
+    # A/B against the per-tap kernel
+    L.cb200_force_simt(2)
+    try:
+        y2 = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+        assert L.cb200_last_conv_impl() == b"tcgen05"
+    finally:
+        L.cb200_force_simt(0)
+    assert np.array_equal(y, y2)
+    layer.free(); xb.free(); dyb.free()
