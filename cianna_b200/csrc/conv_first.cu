@@ -196,6 +196,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 		const int act = p.activ.type, n_real = p.n_real, n_pad = p.n_pad;
 		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta;
 		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
+		const bool relu_minmax = leak >= 0.0f && leak <= 1.0f;
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
 		for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
 			const int tile = tile0 + it;
@@ -225,8 +226,9 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 #pragma unroll
 						for (int j = 0; j < 8; j++) {
 							const float z = o[j];
-							const float hi = sat + (z - sat) * leak;
-							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+							const float hi = fmaf(z - sat, leak, sat);
+							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks hi exactly when z > sat
+							o[j] = relu_minmax ? fminf(fmaxf(z, z * leak), hi) : (z <= 0.0f ? z * leak : (z > sat ? hi : z));
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll

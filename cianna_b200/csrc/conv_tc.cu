@@ -121,9 +121,10 @@ struct IgemmParams {
 // Eight epilogue warps in two groups of four (one warp per TMEM lane quadrant): group g drains the accumulators of the
 // CTA's tiles g, g+2, g+4, ... so two tiles are in their epilogue at any time while the MMA warp runs up to ACC_STAGES
 // tiles ahead.  tcgen05.ld -> bias + activation (forward) or the previous layer's derivative (dgrad) -> cast -> store.
-template <typename T, int BN, int ACC_STAGES>
+template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2>
 __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               float* bias_rows, int warp, int lane, int first_warp) {
+	static_assert(NGROUPS <= ACC_STAGES, "an accumulator stage belongs to one epilogue group at a time");
 	const int ew = warp - first_warp;                // 0..7
 	const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
 	const int grp = ew >> 2;                         // epilogue group
@@ -138,10 +139,11 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
 	const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
+	const bool relu_minmax = leak >= 0.0f && leak <= 1.0f;
 	float* bs = bias_rows + grp * 256;
 	int it = 0;
 	for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
-		if ((it & 1) != grp) continue;
+		if ((it % NGROUPS) != grp) continue;
 		const int acc = it % ACC_STAGES;
 		const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
 		const int mt = tile % tiles_m, nt = tile / tiles_m;
@@ -187,8 +189,9 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 #pragma unroll
 						for (int j = 0; j < 8; j++) {
 							const float z = o[j];
-							const float hi = sat + (z - sat) * leak;
-							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+							const float hi = fmaf(z - sat, leak, sat);
+							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks hi exactly when z > sat
+							o[j] = relu_minmax ? fminf(fmaxf(z, z * leak), hi) : (z <= 0.0f ? z * leak : (z > sat ? hi : z));
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll
@@ -387,13 +390,14 @@ bool conv_tc_dgrad_supported(const cb200_conv_desc* d) { return tc_common_ok(d) 
 // bytes instead of 9x + the filters.
 template <int BN>
 struct HaloCfg {
-	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;
+	static constexpr int ACC_STAGES = 4;                 // BN <= 128
 	static constexpr int ACC_COLS = ACC_STAGES * BN;
 	static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
 	static constexpr int MAX_A_STAGES = 6;
 };
 constexpr int HALO_TW = 8, HALO_TH = 16;
-constexpr int HALO_THREADS = 11 * 32;    // A producer, B loader, MMA issuer, 8 epilogue warps
+constexpr int HALO_EPI_GROUPS = 4;
+constexpr int HALO_THREADS = (3 + 4 * HALO_EPI_GROUPS) * 32;    // A producer, B loader, MMA issuer, 4 epilogue groups of 4 warps
 
 template <typename T, int BN, int BK>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
@@ -489,7 +493,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 		}
 	} else {
 		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-		epilogue_loop<T, BN, Cfg::ACC_STAGES>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 3);
+		epilogue_loop<T, BN, Cfg::ACC_STAGES, HALO_EPI_GROUPS>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 3);
 	}
 
 	tc_fence_before();
@@ -540,7 +544,7 @@ static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_
 	const int b_bytes = f_h * f_w * kcb * b_blk;
 	const int halo_w = HALO_TW + f_w - 1, halo_h = HALO_TH + f_h - 1;
 	const int a_stage = (halo_h * halo_w * bk * 2 + 1023) & ~1023;
-	const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias rows*/;
+	const int fixed = 1024 /*align*/ + 256 /*barriers*/ + HALO_EPI_GROUPS * 1024 /*bias rows*/;
 	int stages = (HALO_SMEM_MAX - fixed - b_bytes) / a_stage;
 	if (stages > HaloCfg<16>::MAX_A_STAGES) stages = HaloCfg<16>::MAX_A_STAGES;
 	if (stages < 2) return 0;
