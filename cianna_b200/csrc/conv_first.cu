@@ -223,12 +223,16 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 #pragma unroll
 					for (int j = 0; j < 8; j++) o[j] = dead ? 0.0f : __uint_as_float(r[v * 8 + j]);
 					if (act == CB200_RELU) {
+						if (relu_minmax) {
+							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks the saturated branch exactly when z > sat
 #pragma unroll
-						for (int j = 0; j < 8; j++) {
-							const float z = o[j];
-							const float hi = fmaf(z - sat, leak, sat);
-							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks hi exactly when z > sat
-							o[j] = relu_minmax ? fminf(fmaxf(z, z * leak), hi) : (z <= 0.0f ? z * leak : (z > sat ? hi : z));
+							for (int j = 0; j < 8; j++) o[j] = fminf(fmaxf(o[j], o[j] * leak), fmaf(o[j] - sat, leak, sat));
+						} else {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const float z = o[j];
+								o[j] = z <= 0.0f ? z * leak : (z > sat ? fmaf(z - sat, leak, sat) : z);
+							}
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll

@@ -186,12 +186,16 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 					const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
 					o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
 					if (act == CB200_RELU) {
+						if (relu_minmax) {
+							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks the saturated branch exactly when z > sat
 #pragma unroll
-						for (int j = 0; j < 8; j++) {
-							const float z = o[j];
-							const float hi = fmaf(z - sat, leak, sat);
-							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks hi exactly when z > sat
-							o[j] = relu_minmax ? fminf(fmaxf(z, z * leak), hi) : (z <= 0.0f ? z * leak : (z > sat ? hi : z));
+							for (int j = 0; j < 8; j++) o[j] = fminf(fmaxf(o[j], o[j] * leak), fmaf(o[j] - sat, leak, sat));
+						} else {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const float z = o[j];
+								o[j] = z <= 0.0f ? z * leak : (z > sat ? fmaf(z - sat, leak, sat) : z);
+							}
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll
@@ -303,20 +307,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		if (lane == 0) {
 			int stage = 0; uint32_t phase = 0;
 			int acc = 0; uint32_t acc_phase = 0;
-			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
+			const uint32_t idesc = p.idesc;
+			const int num_tiles = p.num_tiles;
+			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
 				for (int k = 0; k < k_iters; k++) {
 					mbar_wait(full_bar(stage), phase);
 					tc_fence_after();
-					const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+					// (descriptor = prototype + start address >> 4: the issuing thread is alone, keep its path short)
+					const uint64_t da = desc_proto + ((smem_base + (uint32_t)(stage * Cfg::STAGE_BYTES)) >> 4);
+					const uint64_t db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
-					for (int kk = 0; kk < BK / 16; kk++) {
-						const uint64_t da = make_smem_desc(sa + kk * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-						const uint64_t db = make_smem_desc(sb + kk * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-						mma_f16_ss(d_tmem, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
-					}
+					for (int kk = 0; kk < BK / 16; kk++)
+						mma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
 					mma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
 					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 				}
@@ -399,7 +405,7 @@ constexpr int HALO_TW = 8, HALO_TH = 16;
 constexpr int HALO_EPI_GROUPS = 4;
 constexpr int HALO_THREADS = (3 + 4 * HALO_EPI_GROUPS) * 32;    // A producer, B loader, MMA issuer, 4 epilogue groups of 4 warps
 
-template <typename T, int BN, int BK>
+template <typename T, int BN, int BK, int FS>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
 	using Cfg = HaloCfg<BN>;
@@ -407,7 +413,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 	constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-	const int taps = p.f_h * p.f_w;
+	constexpr int taps = FS * FS, HALO_W = HALO_TW + FS - 1, HALO_H = HALO_TH + FS - 1;
 	const uint32_t b_smem = smem_base + (uint32_t)(p.a_stages * p.a_stage_bytes);
 	const uint32_t bar_base = b_smem + (uint32_t)(taps * p.kc_blocks * p.b_blk_bytes);
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -433,7 +439,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot_ptr;
-	const uint32_t a_tx = (uint32_t)((HALO_TH + p.f_h - 1) * p.halo_w) * ROWB;
+	constexpr uint32_t a_tx = (uint32_t)(HALO_H * HALO_W) * ROWB;
 
 	if (warp == 0) {
 		// ===================== halo producer: one TMA box per (tile, channel block) =====================
@@ -464,28 +470,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 			mbar_wait(bfull_bar, 0);
 			int stage = 0; uint32_t phase = 0;
 			int acc = 0; uint32_t acc_phase = 0;
-			const uint32_t sbo = (uint32_t)p.halo_w * ROWB;
-			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			// The issuing thread is alone: every instruction between two MMAs is on the critical path of a tile whose MMAs
+			// are short (N <= 128).  Descriptors are therefore one 64-bit add away from a per-stage base: the start-address
+			// field holds addr >> 4 in the low 14 bits and shared memory is < 256 KB, so adding (byte offset >> 4) never
+			// carries out of the field; tap offsets are compile-time constants.
+			const uint64_t da_proto = make_smem_desc(0, 16, (uint32_t)HALO_W * ROWB, LAYOUT);
+			const uint64_t db_proto = make_smem_desc(0, 16, 8 * ROWB, LAYOUT);
+			const uint32_t b_tap_step = (uint32_t)(p.kc_blocks * p.b_blk_bytes) >> 4;
+			const uint32_t idesc = p.idesc;
+			const int kc_blocks = p.kc_blocks, a_stages = p.a_stages, a_stage_bytes = p.a_stage_bytes, b_blk_bytes = p.b_blk_bytes;
+			const int num_tiles = p.num_tiles;
+			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-				for (int cb = 0; cb < p.kc_blocks; cb++) {
+				for (int cb = 0; cb < kc_blocks; cb++) {
 					mbar_wait(full_bar(stage), phase);
 					tc_fence_after();
-					const uint32_t sa = smem_base + (uint32_t)(stage * p.a_stage_bytes);
-					for (int tap = 0; tap < taps; tap++) {
-						const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
-						const uint32_t a0 = sa + (uint32_t)(ky * p.halo_w + kx) * ROWB;
-						const uint32_t b0 = b_smem + (uint32_t)((tap * p.kc_blocks + cb) * p.b_blk_bytes);
+					const uint64_t da0 = da_proto + ((smem_base + (uint32_t)(stage * a_stage_bytes)) >> 4);
+					uint64_t db_t = db_proto + ((b_smem + (uint32_t)(cb * b_blk_bytes)) >> 4);
 #pragma unroll
-						for (int kk = 0; kk < BK / 16; kk++) {
-							const uint64_t da = make_smem_desc(a0 + kk * 32, 16, sbo, LAYOUT);
-							const uint64_t db = make_smem_desc(b0 + kk * 32, 16, 8 * ROWB, LAYOUT);
-							mma_f16_ss(d_tmem, da, db, p.idesc, (cb | tap | kk) != 0 ? 1u : 0u);
-						}
+					for (int tap = 0; tap < taps; tap++) {
+						const uint64_t da_t = da0 + (((uint32_t)((tap / FS) * HALO_W + (tap % FS)) * ROWB) >> 4);
+#pragma unroll
+						for (int kk = 0; kk < BK / 16; kk++)
+							mma_f16_ss(d_tmem, da_t + 2 * kk, db_t + 2 * kk, idesc, (tap | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
+						db_t += b_tap_step;
 					}
 					mma_commit(empty_bar(stage));
-					if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
+					if (++stage == a_stages) { stage = 0; phase ^= 1u; }
 				}
 				mma_commit(tfull_bar(acc));
 				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
@@ -503,10 +516,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 constexpr int HALO_SMEM_MAX = 225 * 1024;
 
-template <typename T, int BN, int BK>
+template <typename T, int BN, int BK, int FS>
 static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem_bytes, cudaStream_t st) {
 	static bool configured = false;
-	auto kern = conv_halo_kernel<T, BN, BK>;
+	auto kern = conv_halo_kernel<T, BN, BK, FS>;
 	if (!configured) {
 		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX) != cudaSuccess) {
 			set_error("cudaFuncSetAttribute(smem=%d) failed", HALO_SMEM_MAX); return CB200_ERR_CUDA;
@@ -520,10 +533,10 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const Igemm
 }
 
 template <typename T>
-static int dispatch_halo(int bn, int bk, const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem, cudaStream_t st) {
-#define CASE(BN_, BK_) if (bn == BN_ && bk == BK_) return launch_halo<T, BN_, BK_>(ma, mb, p, smem, st)
-	CASE(128, 64); CASE(64, 64); CASE(32, 64); CASE(16, 64);
-	CASE(128, 32); CASE(64, 32); CASE(32, 32); CASE(16, 32);
+static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem, cudaStream_t st) {
+#define CASE(BN_, BK_) if (bn == BN_ && bk == BK_) return fs == 3 ? launch_halo<T, BN_, BK_, 3>(ma, mb, p, smem, st) : launch_halo<T, BN_, BK_, 5>(ma, mb, p, smem, st)
+	CASE(128, 64); CASE(64, 64); CASE(32, 64);
+	CASE(128, 32); CASE(64, 32); CASE(32, 32);
 #undef CASE
 	set_error("conv_tc: no halo kernel instance for BN=%d BK=%d", bn, bk);
 	return CB200_ERR_UNSUPPORTED;
@@ -534,8 +547,8 @@ int g_disable_halo = 0;     // test hook (cb200_force_simt bit 1): route everyth
 
 // Decide whether the layer goes to the halo kernel and, if so, fill its tiling; returns the dynamic smem size or 0.
 static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_w, int bk, int bn, IgemmParams& p) {
-	if (g_disable_halo || f_h * f_w == 1 || f_h > 5 || f_w > 5) return 0;
-	if (bk < 32 || bn > 128 || n_pad > bn) return 0;
+	if (g_disable_halo || f_h != f_w || (f_h != 3 && f_h != 5)) return 0;
+	if (bk < 32 || bn > 128 || bn < 32 || n_pad > bn) return 0;
 	if (out_w < HALO_TW || out_h < HALO_TH) return 0;
 	const double cover = (double)ceil_div(out_w, HALO_TW) * HALO_TW * ceil_div(out_h, HALO_TH) * HALO_TH / ((double)out_w * out_h);
 	if (cover > 1.15) return 0;
@@ -580,8 +593,8 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 			ph.n_real = n_real; ph.n_pad = n_pad;
 			ph.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
 			g_last_conv_impl = "tcgen05-halo";
-			if (dtype == CB200_FP16) return dispatch_halo<__half>(bn, bk, ma, mb, ph, smem, st);
-			return dispatch_halo<__nv_bfloat16>(bn, bk, ma, mb, ph, smem, st);
+			if (dtype == CB200_FP16) return dispatch_halo<__half>(bn, bk, f_h, ma, mb, ph, smem, st);
+			return dispatch_halo<__nv_bfloat16>(bn, bk, f_h, ma, mb, ph, smem, st);
 		}
 	}
 	int tw, th, tn;
