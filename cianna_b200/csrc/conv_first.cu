@@ -196,8 +196,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 		const int act = p.activ.type, n_real = p.n_real, n_pad = p.n_pad;
 		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta;
 		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
-		const bool relu_minmax = leak >= 0.0f && leak <= 1.0f;
-		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+			const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
 		for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
 			const int tile = tile0 + it;
 			const int acc = it % Cfg::ACC_STAGES;
@@ -223,16 +222,11 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 #pragma unroll
 					for (int j = 0; j < 8; j++) o[j] = dead ? 0.0f : __uint_as_float(r[v * 8 + j]);
 					if (act == CB200_RELU) {
-						if (relu_minmax) {
-							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks the saturated branch exactly when z > sat
 #pragma unroll
-							for (int j = 0; j < 8; j++) o[j] = fminf(fmaxf(o[j], o[j] * leak), fmaf(o[j] - sat, leak, sat));
-						} else {
-#pragma unroll
-							for (int j = 0; j < 8; j++) {
-								const float z = o[j];
-								o[j] = z <= 0.0f ? z * leak : (z > sat ? fmaf(z - sat, leak, sat) : z);
-							}
+						for (int j = 0; j < 8; j++) {
+							const float z = o[j];
+							const float hi = sat + (z - sat) * leak;
+							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll
@@ -317,18 +311,19 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 		}
 	} else if (warp == 1) {
 		if (lane == 0) {
+			const uint64_t da_proto = make_smem_desc(0, Cfg::A_SLAB_BYTES, 1024, 2);
+			const uint64_t db_proto = make_smem_desc(0, Cfg::B_BYTES, PC::SBO, PC::LAYOUT);
+			const uint32_t idesc = p.idesc;
 			for (int k = 0; k < n_steps; k++) {
 				const int stage = k % Cfg::STAGES;
 				const uint32_t phase = (uint32_t)(k / Cfg::STAGES) & 1u;
 				mbar_wait(full_bar(stage), phase);
 				tc_fence_after();
-				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+				const uint64_t da = da_proto + (sa >> 4), db = db_proto + ((sa + Cfg::A_BYTES) >> 4);
 #pragma unroll
-				for (int kk = 0; kk < Cfg::KPIX / 16; kk++) {
-					const uint64_t da = make_smem_desc(sa + kk * 2048, Cfg::A_SLAB_BYTES, 1024, 2);
-					const uint64_t db = make_smem_desc(sb + kk * 16 * PC::ROW_BYTES, Cfg::B_BYTES, PC::SBO, PC::LAYOUT);
-					mma_f16_ss(tmem_base, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
-				}
+				for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
+					mma_f16_ss(tmem_base, da + ((kk * 2048) >> 4), db + ((kk * 16 * PC::ROW_BYTES) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
 				mma_commit(empty_bar(stage));
 			}
 			mma_commit(done_bar);

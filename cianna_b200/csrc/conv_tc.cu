@@ -139,7 +139,6 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
 	const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
-	const bool relu_minmax = leak >= 0.0f && leak <= 1.0f;
 	float* bs = bias_rows + grp * 256;
 	int it = 0;
 	for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
@@ -186,16 +185,11 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 					const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
 					o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
 					if (act == CB200_RELU) {
-						if (relu_minmax) {
-							// 0 <= leak <= 1: max picks z*leak exactly when z <= 0, min picks the saturated branch exactly when z > sat
 #pragma unroll
-							for (int j = 0; j < 8; j++) o[j] = fminf(fmaxf(o[j], o[j] * leak), fmaf(o[j] - sat, leak, sat));
-						} else {
-#pragma unroll
-							for (int j = 0; j < 8; j++) {
-								const float z = o[j];
-								o[j] = z <= 0.0f ? z * leak : (z > sat ? fmaf(z - sat, leak, sat) : z);
-							}
+						for (int j = 0; j < 8; j++) {
+							const float z = o[j];
+							const float hi = sat + (z - sat) * leak;
+							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll
@@ -744,22 +738,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 	} else if (warp == 1) {
 		if (lane == 0) {
 			int stage = 0; uint32_t phase = 0;
+			const uint64_t da_proto = make_smem_desc(0, Cfg::A_SLAB_BYTES, 1024, 2);
+			const uint64_t db_proto = make_smem_desc(0, Cfg::B_SLAB_BYTES, 8 * Cfg::B_ROW_BYTES, Cfg::B_LAYOUT);
+			const uint32_t idesc = p.idesc;
+			const int tg = p.tg;
 			for (int k = 0; k < n_steps; k++) {
 				mbar_wait(full_bar(stage), phase);
 				tc_fence_after();
-				const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + MF * Cfg::A_BYTES;
+				// MN-major: 8 pixel rows per K group -> SBO; channel slabs -> LBO; 16 pixel rows per MMA.  Descriptors are a
+				// 64-bit add away from the per-stage base (single issuing thread: keep its instruction path short).
+				const uint32_t sa = smem_base + stage * stage_bytes;
+				const uint64_t da_s = da_proto + (sa >> 4);
+				const uint64_t db_s = db_proto + ((sa + MF * Cfg::A_BYTES) >> 4);
+				const uint32_t accum = k != 0 ? 1u : 0u;
 #pragma unroll
 				for (int mf = 0; mf < MF; mf++) {
+					uint64_t db_t = db_s;
+					uint32_t d_tmem = tmem_base + (uint32_t)(mf * tg * BNC);
 					for (int ti = 0; ti < ntap; ti++) {
-						const uint32_t d_tmem = tmem_base + (uint32_t)((mf * p.tg + ti) * BNC);
 #pragma unroll
-						for (int kk = 0; kk < Cfg::KPIX / 16; kk++) {
-							// MN-major: 8 pixel rows per K group -> SBO; channel slabs -> LBO; 16 pixel rows per MMA
-							const uint64_t da = make_smem_desc(sa + mf * Cfg::A_BYTES + kk * 2048, Cfg::A_SLAB_BYTES, 1024, 2);
-							const uint64_t db = make_smem_desc(sb + ti * Cfg::B_BYTES + kk * 16 * Cfg::B_ROW_BYTES, Cfg::B_SLAB_BYTES,
-							                                   8 * Cfg::B_ROW_BYTES, Cfg::B_LAYOUT);
-							mma_f16_ss(d_tmem, da, db, p.idesc, (k | kk) != 0 ? 1u : 0u);
-						}
+						for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
+							mma_f16_ss(d_tmem, da_s + ((mf * Cfg::A_BYTES + kk * 2048) >> 4), db_t + ((kk * 16 * Cfg::B_ROW_BYTES) >> 4), idesc,
+							           kk != 0 ? 1u : accum);
+						db_t += Cfg::B_BYTES >> 4;
+						d_tmem += BNC;
 					}
 				}
 				mma_commit(empty_bar(stage));

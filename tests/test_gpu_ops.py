@@ -445,7 +445,7 @@ def test_conv_halo_kernel_bit_exact(cabi, shape, dtype_name):
     ref_dx = co.conv_backward_data(dy, w, B, C, S, S, f, 1, pad)
     assert np.abs(ref_dx).max() < 256
     assert np.array_equal(dx, ref_dx), "data gradient: %d wrong" % int((dx != ref_dx).sum())
-    assert halo_dgrad or pad == 0
+    assert halo_dgrad or pad == 0 or cabi.round8(N) < 32      # (dy with < 32 channels runs 16-channel blocks: per-tap kernel)
     # A/B against the per-tap kernel
     L.cb200_force_simt(2)
     try:
