@@ -189,6 +189,9 @@ struct network {
 	void *out_host;        /* pinned staging of the last layer's output (inference read-back) */
 	/* double-buffered host->device staging of dynamic_load batches on a copy stream (overlaps the previous step) */
 	void *copy_stream;
+	/* weight-gradient kernels run on their own stream: the rest of the backward sweep does not depend on them, and the
+	 * bandwidth-bound group-norm / pool kernels of the layers below fill the SMs next to the tensor-core bound wgrad CTAs */
+	void *wgrad_stream;
 	void *stage_in[2], *stage_tg[2];
 	const void *staged_src[2];   /* host batch currently (being) copied into each slot */
 	int stage_slot;

@@ -215,6 +215,10 @@ static void prepare_training(network *net)
 			p->gsum = net->grad_arena + p->grad_offset;
 		}
 	}
+	{
+		const char *e = getenv("CB200_NO_WGRAD_STREAM");
+		if (!(e != NULL && e[0] != '\0' && e[0] != '0')) CB_CHECK(cb200_stream_create(&net->wgrad_stream));
+	}
 	net->training_ready = 1;
 }
 
@@ -326,6 +330,7 @@ static void apply_updates(network *net)
 			norm_len = p->grad_offset + 2 * (size_t)p->nb_group - norm_begin;
 		}
 	}
+	if (net->wgrad_stream != NULL) CB_CHECK(cb200_stream_wait(NULL, net->wgrad_stream));   /* all weight gradients are in */
 	if (net->dp_world > 1) {
 		if (any_norm) CB_CHECK(cb200_dp_allreduce(net->grad_arena + norm_begin, norm_len, NULL));
 		CB_CHECK(cb200_dp_join(NULL));
