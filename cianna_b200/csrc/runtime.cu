@@ -93,7 +93,13 @@ int cb200_init(int device) {
 	// debugging aid: CB200_FORCE_SIMT=1 routes every conv through the generic kernels (see cb200_force_simt)
 	const char* fs = getenv("CB200_FORCE_SIMT");
 	if (fs && fs[0] == '1') g_force_simt = 1;
-	if (!g_stream) CB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+	if (!g_stream) {
+		// the compute stream carries the critical path: highest priority, so that work put on side streams (weight gradients)
+		// only takes the SMs the critical path leaves free
+		int lo = 0, hi = 0;
+		CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CB_CUDA(cudaStreamCreateWithPriority(&g_stream, cudaStreamNonBlocking, hi));
+	}
 	g_have_device = true;
 	return CB200_OK;
 }
@@ -128,6 +134,12 @@ int cb200_d2d(void* d, const void* s_, size_t bytes, void* s) {
 }
 int cb200_stream_create(void** s) {
 	CB_REQUIRE_DEVICE(); cudaStream_t st; CB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = st; return CB200_OK;
+}
+int cb200_stream_create_low_priority(void** s) {
+	CB_REQUIRE_DEVICE();
+	int lo = 0, hi = 0;
+	CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = numerically largest = least urgent
+	cudaStream_t st; CB_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo)); *s = st; return CB200_OK;
 }
 int cb200_stream_destroy(void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamDestroy((cudaStream_t)s)); return CB200_OK; }
 int cb200_stream_sync(void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamSynchronize(as_stream(s))); return CB200_OK; }

@@ -104,14 +104,16 @@ static void backward_conv_layer(layer *current)
 	network *net = current->c_network;
 	conv_param *p = (conv_param *)current->param;
 	p->desc.length = net->length;
+	/* the weight gradient only needs what is already enqueued (this layer's delta and, when the following norm layer
+	 * produced it, grad_b): it goes to the low-priority side stream, ordered after that point, BEFORE the data gradient
+	 * is enqueued on the compute stream, so the critical path never waits for it; joined again before the optimizer
+	 * (network.c: apply_updates) */
+	if (!current->frozen && net->wgrad_stream != NULL) CB_CHECK(cb200_stream_wait(net->wgrad_stream, NULL));
 	if (current->previous != NULL)
 		CB_CHECK(cb200_conv_backward_data(&p->desc, &p->w, current->delta_o, current->previous->delta_o,
 			&current->previous->activ, current->previous->output, NULL));
 	if (!current->frozen) {
-		/* side stream: ordered after everything enqueued so far (this layer's delta and, when the following norm layer
-		 * produced it, grad_b), joined again before the optimizer (network.c: apply_updates) */
 		void *ws = net->wgrad_stream;
-		if (ws != NULL) CB_CHECK(cb200_stream_wait(ws, NULL));
 		CB_CHECK(cb200_conv_backward_weights_ex(&p->desc, &p->w, layer_input(current), current->delta_o, p->bias_grad_from_next, ws));
 		if (net->dp_world > 1) CB_CHECK(cb200_dp_allreduce(p->w.grad, p->grad_len, ws));
 	}

@@ -217,7 +217,7 @@ static void prepare_training(network *net)
 	}
 	{
 		const char *e = getenv("CB200_NO_WGRAD_STREAM");
-		if (!(e != NULL && e[0] != '\0' && e[0] != '0')) CB_CHECK(cb200_stream_create(&net->wgrad_stream));
+		if (!(e != NULL && e[0] != '\0' && e[0] != '0')) CB_CHECK(cb200_stream_create_low_priority(&net->wgrad_stream));
 	}
 	net->training_ready = 1;
 }

@@ -96,6 +96,9 @@ int  cb200_h2d(void* dev_dst, const void* host_src, size_t bytes, void* stream);
 int  cb200_d2h(void* host_dst, const void* dev_src, size_t bytes, void* stream);
 int  cb200_d2d(void* dev_dst, const void* dev_src, size_t bytes, void* stream);
 int  cb200_stream_create(void** stream);
+/* a stream of the lowest priority; the core's default compute stream has the highest, so kernels put here (the host
+ * library's weight gradients) only take the SMs the critical path leaves free */
+int  cb200_stream_create_low_priority(void** stream);
 int  cb200_stream_destroy(void* stream);
 int  cb200_stream_sync(void* stream);                     /* NULL: default compute stream */
 int  cb200_device_sync(void);
