@@ -192,6 +192,7 @@ struct network {
 	/* weight-gradient kernels run on their own stream: the rest of the backward sweep does not depend on them, and the
 	 * bandwidth-bound group-norm / pool kernels of the layers below fill the SMs next to the tensor-core bound wgrad CTAs */
 	void *wgrad_stream;
+	void *wgrad_stream_off;    /* parked here while cb_set_wgrad_overlap(net, 0) is in effect */
 	void *stage_in[2], *stage_tg[2];
 	const void *staged_src[2];   /* host batch currently (being) copied into each slot */
 	int stage_slot;
@@ -302,6 +303,8 @@ void cb_yolo_export_boxes(network *net, float *dst);
 void cb_net_set_iter(network *net, int iter, int train_size);
 /* group-norm + max-pool fusion for the layers created from now on (default on; CB200_NO_FUSION=1 in the environment turns it off) */
 void cb_set_fusion(int on);
+/* 0: weight gradients back on the compute stream (one kernel at a time: what per-kernel event timing needs), 1: overlap */
+void cb_set_wgrad_overlap(network *net, int on);
 
 #define CB_CHECK(call) do { int rc__ = (call); if (rc__ != 0) { \
 	printf("\nERROR: %s failed (%d): %s\n", #call, rc__, cb200_last_error()); exit(EXIT_FAILURE); } } while (0)

@@ -1001,6 +1001,12 @@ void cb_net_set_iter(network *net, int iter, int train_size)
 	net->iter = iter;
 	if (train_size > 0 && net->train.input == NULL) net->train.size = train_size;
 }
+void cb_set_wgrad_overlap(network *net, int on)
+{
+	CB_CHECK(cb200_device_sync());
+	if (!on && net->wgrad_stream != NULL) { net->wgrad_stream_off = net->wgrad_stream; net->wgrad_stream = NULL; }
+	else if (on && net->wgrad_stream == NULL && net->wgrad_stream_off != NULL) { net->wgrad_stream = net->wgrad_stream_off; net->wgrad_stream_off = NULL; }
+}
 void cb_net_in_dims(network *net, int *out4) { int i; for (i = 0; i < 4; i++) out4[i] = net->in_dims[i]; }
 /* loss scaling is only honoured by the FP16 mode (upstream cuda_set_TC_scale_factor, src/cuda/cuda_main.cu:63-76) */
 void cb_set_TC_scale_factor(network *net, float v) { net->TC_scale_factor = net->use_cuda_TC == FP16C_FP32A ? v : 1.0f; }
