@@ -77,6 +77,66 @@ __global__ void conv_update_kernel(float* __restrict__ master, float* __restrict
 	}
 }
 
+// Conv layers (master in the conv layout, ms_c == 1): the same update with threads in OPERAND order (f, tap, c) instead
+// of master order, so the raw gradient is read and w_fwd written fully coalesced; the master / momentum accesses of a
+// warp then stride by `taps` floats but stay inside one filter's contiguous span (L1 resident).  The transposed +
+// rotated copy for the data gradient is produced by a tiled transpose of w_fwd (both sides coalesced) instead of one
+// scattered 2-byte store per weight.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_update_operand_kernel(float* __restrict__ master, float* __restrict__ moment, const float* __restrict__ grad,
+                           const float* __restrict__ grad_b, const float* __restrict__ hyper, float bias_value,
+                           T* __restrict__ w_fwd, float* __restrict__ bias_w, int out_c, int taps, int in_c, int in_cp) {
+	const int kref = taps * in_c + 1;
+	const size_t total = (size_t)out_c * taps * in_cp;
+	const float alpha = hyper[0], mom = hyper[1], wdlr = hyper[2], S = hyper[3];
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int c = (int)(i % in_cp);
+		const size_t r = i / in_cp;
+		const int tap = (int)(r % taps), f = (int)(r / taps);
+		if (c < in_c) {
+			const size_t mi = (size_t)f * kref + (size_t)c * taps + tap;
+			float wv = master[mi];
+			float m = alpha * grad[i] + mom * moment[mi];
+			m += wdlr * wv * S;
+			wv -= m / S;
+			moment[mi] = m;
+			master[mi] = wv;
+			w_fwd[i] = from_f32<T>(wv);
+		}
+		if (c == 0 && tap == 0) {      // this filter's bias column
+			const size_t mi = (size_t)f * kref + kref - 1;
+			float wv = master[mi];
+			float m = alpha * (bias_value * grad_b[f]) + mom * moment[mi];
+			m += wdlr * wv * S;
+			wv -= m / S;
+			moment[mi] = m;
+			master[mi] = wv;
+			bias_w[f] = wv;
+		}
+	}
+}
+
+// w_bwd[c][taps-1-tap][f] = w_fwd[f][tap][c] through a 32x32 shared-memory tile; grid (c tiles, f tiles, taps)
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wbwd_transpose_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_bwd, int out_c, int out_cp, int taps, int in_c, int in_cp) {
+	__shared__ T tile[32][33];
+	const int tap = blockIdx.z, c0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int f = f0 + ty + 8 * k, c = c0 + tx;
+		tile[ty + 8 * k][tx] = (f < out_c && c < in_cp) ? w_fwd[((size_t)f * taps + tap) * in_cp + c] : from_f32<T>(0.0f);
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int c = c0 + ty + 8 * k, f = f0 + tx;
+		if (c < in_c && f < out_cp) w_bwd[((size_t)c * taps + (taps - 1 - tap)) * out_cp + f] = tile[tx][ty + 8 * k];
+	}
+}
+
 // ---- first layer run on patch rows (cb200_import_input_patches): a 1x1 GEMM over kp columns, bias inside the GEMM
 static cb200_conv_desc effective_desc(const cb200_conv_desc* d) {
 	cb200_conv_desc e = *d;
@@ -252,6 +312,18 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	}
 	const int taps = d->f_h * d->f_w;
 	long long total = (long long)cb200_conv_master_elems(d);
+	if (ms_c == 1 && !is_pivot && ms_f == (size_t)taps * d->in_c + 1) {
+		const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
+		const long long op_total = (long long)d->out_c * taps * in_cp;
+		CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_operand_kernel<T><<<grid_for(op_total, 256), 256, 0, as_stream(s)>>>(
+			w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, (T*)w->w_fwd, w->bias_w, d->out_c, taps, d->in_c, in_cp)));
+		CB_LAUNCH_CHECK();
+		dim3 tgrid((unsigned)ceil_div(d->in_c, 32), (unsigned)ceil_div(out_cp, 32), (unsigned)taps);
+		CB_DISPATCH_DTYPE(d->dtype, T, (conv_wbwd_transpose_kernel<T><<<tgrid, 256, 0, as_stream(s)>>>(
+			(const T*)w->w_fwd, (T*)w->w_bwd, d->out_c, out_cp, taps, d->in_c, in_cp)));
+		CB_LAUNCH_CHECK();
+		return CB200_OK;
+	}
 	CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
 		w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, is_pivot,
 		(T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c)));
