@@ -549,6 +549,14 @@ def last_perf(network=None):
     return float(L.cb_net_last_items_per_s(net)), float(L.cb_net_last_epoch_loss(net))
 
 
+def last_accuracy(network=None):
+    """fraction of correct argmax predictions of the last validation pass run with confmat > 0"""
+    L = _load()
+    L.cb_net_last_accuracy.restype = ctypes.c_double
+    L.cb_net_last_accuracy.argtypes = [ctypes.c_void_p]
+    return float(L.cb_net_last_accuracy(_net(network)))
+
+
 def reset():
     """Forget all networks (device memory of earlier networks is not reclaimed, as upstream)."""
     L = _load()

@@ -115,3 +115,58 @@ int cb200_output_loss(float* loss, const void* y, const void* target, int dtype,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- classification read-out
+// Per-sample argmax of the network output and of the target row (first maximum wins, like upstream's argmax /
+// conv_argmax, src/auxil.c:1365-1426): what the confusion matrix of compute_error needs - two ints per sample come back
+// instead of the whole output tensor.
+namespace cb200 {
+template <typename T>
+__global__ void output_argmax_kernel(int* __restrict__ pred, int* __restrict__ truth, const T* __restrict__ y,
+                                     const T* __restrict__ target, int length, int c, int cp, int hw) {
+	__shared__ float best_v[2][32];
+	__shared__ int best_i[2][32];
+	const int b = blockIdx.x;
+	const int n = c * hw;
+	float v[2] = {-INFINITY, -INFINITY};
+	int idx[2] = {0x7fffffff, 0x7fffffff};
+	if (b < length) {
+		for (int o = threadIdx.x; o < n; o += blockDim.x) {      // o = class-major index ch*hw + p, the target's own order
+			const int ch = o / hw, p = o - ch * hw;
+			const float a = to_f32<T>(y[((size_t)b * hw + p) * cp + ch]);
+			const float t = to_f32<T>(target[(size_t)b * n + o]);
+			if (a > v[0]) { v[0] = a; idx[0] = o; }
+			if (t > v[1]) { v[1] = t; idx[1] = o; }
+		}
+	}
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < 2; k++) {
+		for (int off = 16; off > 0; off >>= 1) {
+			const float ov = __shfl_xor_sync(0xffffffffu, v[k], off);
+			const int oi = __shfl_xor_sync(0xffffffffu, idx[k], off);
+			if (ov > v[k] || (ov == v[k] && oi < idx[k])) { v[k] = ov; idx[k] = oi; }
+		}
+		if (lane == 0) { best_v[k][wid] = v[k]; best_i[k][wid] = idx[k]; }
+	}
+	__syncthreads();
+	if (threadIdx.x < 2) {
+		const int k = threadIdx.x;
+		float bv = best_v[k][0];
+		int bi = best_i[k][0];
+		for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+			if (best_v[k][w] > bv || (best_v[k][w] == bv && best_i[k][w] < bi)) { bv = best_v[k][w]; bi = best_i[k][w]; }
+		(k == 0 ? pred : truth)[b] = b < length ? bi : -1;
+	}
+}
+}  // namespace cb200
+
+extern "C" int cb200_output_argmax(int* pred, int* truth, const void* y, const void* target, int dtype, int batch, int length,
+                                   int c, int h, int w, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_ARG(pred != nullptr && truth != nullptr && batch > 0 && c > 0);
+	CB_DISPATCH_DTYPE(dtype, T, (cb200::output_argmax_kernel<T><<<batch, 256, 0, cb200::as_stream(s)>>>(
+		pred, truth, (const T*)y, (const T*)target, length, c, cb200::round8(c), h * w)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}

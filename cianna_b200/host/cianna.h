@@ -186,6 +186,7 @@ struct network {
 	float last_batch_loss;
 	double last_epoch_loss;
 	float last_items_per_s;
+	double last_accuracy;  /* of the last compute_error run with a confusion matrix (fraction of correct argmax) */
 	void *out_host;        /* pinned staging of the last layer's output (inference read-back) */
 	/* double-buffered host->device staging of dynamic_load batches on a copy stream (overlaps the previous step) */
 	void *copy_stream;
@@ -286,6 +287,7 @@ layer *cb_net_layer(network *net, int idx);
 int cb_net_batch_size(network *net);
 float cb_net_last_items_per_s(network *net);
 double cb_net_last_epoch_loss(network *net);
+double cb_net_last_accuracy(network *net);
 void cb_net_set_no_error(network *net, int v);
 Dataset *cb_net_dataset(network *net, const char *name);
 void cb_set_dataset(network *net, const char *name, int size, const float *input, const float *target);

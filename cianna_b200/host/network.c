@@ -602,9 +602,16 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 	yolo_param *yolo = last->activation_type == YOLO ? (yolo_param *)last->activ_param : NULL;
 	double part_err[6] = {0, 0, 0, 0, 0, 0}, sum_IoU = 0.0, sum_obj = 0.0;
 	long nb_IoU = 0, nb_good_IoU = 0;
-	(void)confusion_matrix; (void)repeat;
+	/* confusion matrix (src/auxil.c:1137-1146, 1384-1426): classification read-out, i.e. one output per class */
+	int o = net->output_dim, *am_dev = NULL, *am_host = NULL;
+	double *mat = NULL;
 
 	last_layer_dims(net, &c, &h, &w);
+	if (confusion_matrix > 0 && !net->no_error && repeat <= 1 && yolo == NULL && o > 0 && c * h * w == o) {
+		mat = (double *)calloc((size_t)o * o, sizeof(double));
+		CB_CHECK(cb200_malloc((void **)&am_dev, 2 * (size_t)net->batch_size * sizeof(int)));
+		CB_CHECK(cb200_host_alloc((void **)&am_host, 2 * (size_t)net->batch_size * sizeof(int)));
+	}
 	out_elems = last->type == DENSE ? (size_t)net->batch_size * (c + 1) : (size_t)net->batch_size * c * h * w;
 	if (saving > 0) {
 		if (stat("fwd_res", &st) == -1) mkdir("fwd_res", 0700);
@@ -636,6 +643,10 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 				CB_CHECK(cb200_d2h(yolo->monitor_host, yolo->monitor_dev, (size_t)net->batch_size * h * w * yolo->nb_box * 2 * sizeof(float), NULL));
 			}
 		}
+		if (mat != NULL) {
+			CB_CHECK(cb200_output_argmax(am_dev, am_dev + net->batch_size, last->output, tgt, net->dtype, net->batch_size, net->length, c, h, w, NULL));
+			CB_CHECK(cb200_d2h(am_host, am_dev, 2 * (size_t)net->batch_size * sizeof(int), NULL));
+		}
 		if (saving > 0) {
 			if (yolo != NULL && net->y_param->raw_output == 0) CB_CHECK(cb200_yolo_export_boxes(&yolo->desc, out_dev, last->output, NULL));
 			else if (last->type == DENSE) CB_CHECK(cb200_export_dense(out_dev, last->output, net->dtype, net->batch_size, c, 0.0f, NULL));
@@ -644,6 +655,11 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		}
 		CB_CHECK(cb200_stream_sync(NULL));
 		if (!net->no_error) for (k = 0; k < net->length; k++) total_error += net->loss_host[k];
+		if (mat != NULL)
+			for (k = 0; k < net->length; k++) {
+				const int truth = am_host[net->batch_size + k], pred = am_host[k];
+				if (truth >= 0 && truth < o && pred >= 0 && pred < o) mat[(size_t)truth * o + pred] += 1.0;
+			}
 		if (!net->no_error && yolo != NULL) {
 			/* loss split and association statistics of the batch (src/auxil.c:1429-1486) */
 			size_t m, nm = (size_t)net->batch_size * h * w * yolo->nb_box;
@@ -694,6 +710,46 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		}
 	}
 	if (f_save != NULL) { fclose(f_save); cb200_free(out_dev); cb200_host_free(out_host); }
+	if (mat != NULL) {
+		/* same three report levels as upstream (src/auxil.c:1562-1652): rows = true class, columns = predicted class */
+		double *recall = (double *)calloc(o, sizeof(double)), *prec = (double *)calloc(o, sizeof(double)), count = 0.0;
+		int a, b;
+		for (a = 0; a < o; a++) {
+			double row = 0.0, col = 0.0;
+			for (b = 0; b < o; b++) { row += mat[(size_t)a * o + b]; col += mat[(size_t)b * o + a]; }
+			recall[a] = mat[(size_t)a * o + a] / row * 100.0;
+			prec[a] = mat[(size_t)a * o + a] / col * 100.0;
+			count += mat[(size_t)a * o + a];
+		}
+		net->last_accuracy = data.size > 0 ? count / data.size : 0.0;
+		if (silent != 1) {
+			if (confusion_matrix == 1) {
+				int width = (o * 10) / 2;
+				printf("\n   ");
+				for (a = 0; a < width - 3; a++) printf("*");
+				printf("  ConfMat  ");
+				for (a = 0; a < width - 3; a++) printf("*");
+				printf("   Recall\n");
+				for (a = 0; a < o; a++) {
+					printf("%*s", 5, " ");
+					for (b = 0; b < o; b++) printf("%8d |", (int)mat[(size_t)a * o + b]);
+					printf("%11.2f%%\n", recall[a]);
+				}
+				printf("%6s", "Prec. ");
+				for (a = 0; a < o; a++) printf("%7.2f%%  ", prec[a]);
+				printf("Acc %6.2f%%\n", count / data.size * 100);
+			} else if (confusion_matrix == 2) {
+				printf("\n   \n Recall:   ");
+				for (a = 0; a < o; a++) printf("%7.2f%%  ", recall[a]);
+				printf("\n Precision:");
+				for (a = 0; a < o; a++) printf("%7.2f%%  ", prec[a]);
+				printf("\n Accuracy: %6.2f%%\n", count / data.size * 100);
+			} else
+				printf("\n Accuracy: %6.2f%%\n", count / data.size * 100);
+		}
+		free(recall); free(prec); free(mat);
+		cb200_free(am_dev); cb200_host_free(am_host);
+	}
 }
 
 void forward_testset(network *net, int saving, int repeat, int drop_mode, int silent)
@@ -919,6 +975,7 @@ layer *cb_net_layer(network *net, int idx) { return (idx >= 0 && idx < net->nb_l
 int cb_net_batch_size(network *net) { return net->batch_size; }
 float cb_net_last_items_per_s(network *net) { return net->last_items_per_s; }
 double cb_net_last_epoch_loss(network *net) { return net->last_epoch_loss; }
+double cb_net_last_accuracy(network *net) { return net->last_accuracy; }
 void cb_net_set_no_error(network *net, int v) { net->no_error = v; }
 
 Dataset *cb_net_dataset(network *net, const char *name)

@@ -344,6 +344,12 @@ int cb200_output_delta(void* delta, const void* y, const void* target, int dtype
 int cb200_output_loss(float* loss, const void* y, const void* target, int dtype,
                       int batch, int length, int c, int h, int w, int kind, void* stream);
 
+/* per-sample argmax (class-major index over the c*h*w outputs, first maximum wins) of the output and of the target
+ * row into two device int32 [batch] arrays (-1 for b >= length): the inputs of the confusion matrix of
+ * compute_error (src/auxil.c:1365-1426, 1562-1658) without copying the output tensor to the host. */
+int cb200_output_argmax(int* pred, int* truth, const void* y, const void* target, int dtype,
+                        int batch, int length, int c, int h, int w, void* stream);
+
 /* ------------------------------------------------------------------ YOLO output layer */
 /* Detection head of the reference (src/activ_functions.c:970-1477 for the parameters,
  * src/cuda/cuda_activ_functions.cu:477-597 activation, :700-1406 association + error signal,

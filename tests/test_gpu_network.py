@@ -242,3 +242,42 @@ def test_checkpoint_files_are_interchangeable(cnn, tmp_path, monkeypatch):
         cnn.load("theirs.dat", 0, network=0, bin=1)
     for i, w in mine.items():
         assert np.array_equal(cnn.layer_weights(i), w)
+
+
+@pytest.mark.parametrize("spec_name", ["lenet", "mini_darknet"])
+def test_confusion_matrix_of_the_validation_pass(cnn, spec_name, tmp_path, monkeypatch, capfd):
+    """train(confmat=1) runs compute_error on the VALID set with the confusion matrix of upstream (src/auxil.c:1562-1603):
+    per-sample argmax on the device, matrix and accuracy on the host. Checked against the argmax of the read-back outputs
+    (dense head and conv + global-average-pool head)."""
+    monkeypatch.chdir(tmp_path)
+    spec = netdefs.lenet(batch=4, size=16, d1=24, d2=12) if spec_name == "lenet" else netdefs.mini_darknet(batch=4, size=16, classes=6)
+    ncls = spec["out_dim"]
+    rng = np.random.default_rng(3)
+    n = 10        # last batch partial
+    dim = spec["in_dim"][0] * spec["in_dim"][1] * spec["in_ch"]
+    data = (rng.random((n, dim), dtype=np.float32) - 0.4).astype(np.float32)
+    targ = np.zeros((n, ncls), np.float32)
+    targ[np.arange(n), rng.integers(0, ncls, n)] = 1
+    _build(cnn, spec, "off")
+    with rd._Quiet():
+        cnn.create_dataset("TRAIN", n, data, targ, network=0, silent=1)
+        cnn.create_dataset("VALID", n, data, targ, network=0, silent=1)
+    cnn.train(nb_iter=1, learning_rate=0.0, control_interv=1, confmat=1, shuffle_every=0, silent=0, network=0)
+    out = capfd.readouterr().out
+    assert "ConfMat" in out and "Acc" in out
+    # reference accuracy from the outputs themselves
+    last = len(spec["layers"]) - 1
+    correct = 0
+    for b0 in range(0, n, 4):
+        xb = np.zeros((4, dim + 1), np.float32)
+        m = min(4, n - b0)
+        xb[:m, :dim] = data[b0:b0 + m]
+        xb[:, dim] = spec.get("bias", 0.1)
+        tb = np.zeros((4, ncls), np.float32)
+        tb[:m] = targ[b0:b0 + m]
+        cnn.load_batch(xb, tb)
+        cnn.forward_batch(m)
+        o = cnn.layer_output(last)
+        scores = o[:, :ncls] if o.ndim == 2 else o[:, :, 0].T       # dense [B][n+1] or [C][B][1]
+        correct += int((scores[:m].argmax(axis=1) == tb[:m].argmax(axis=1)).sum())
+    assert abs(cnn.last_accuracy(network=0) - correct / n) < 1e-9
