@@ -62,21 +62,40 @@ __device__ __forceinline__ void build_patch_row(const T* __restrict__ img, bool 
 	uint32_t packed[KP / 2];
 #pragma unroll
 	for (int i = 0; i < KP / 2; i++) packed[i] = 0u;
-	bool col_ok[FW];
+	if (valid && iy0 >= 0 && iy0 + FH <= h && ix0 >= 0 && ix0 + FW <= w) {
+		// interior pixel (all but the image border): every tap is inside, plain loads at fixed offsets from one pointer
+		// per (channel, filter row) - the builders are instruction-bound, so this path carries no predicates
+		const unsigned short* __restrict__ p0 = src + (size_t)iy0 * w + ix0;
+		const size_t chs = (size_t)h * w;
 #pragma unroll
-	for (int kx = 0; kx < FW; kx++) col_ok[kx] = valid && (ix0 + kx) >= 0 && (ix0 + kx) < w;
+		for (int ch = 0; ch < C; ch++) {
 #pragma unroll
-	for (int ch = 0; ch < C; ch++) {
+			for (int ky = 0; ky < FH; ky++) {
+				const unsigned short* __restrict__ line = p0 + ch * chs + (size_t)(ky * w);
 #pragma unroll
-		for (int ky = 0; ky < FH; ky++) {
-			const int iy = iy0 + ky;
-			const bool row_ok = iy >= 0 && iy < h;
-			const unsigned short* __restrict__ line = src + ((size_t)ch * h + (row_ok ? iy : 0)) * w + ix0;
+				for (int kx = 0; kx < FW; kx++) {
+					const int k = (ch * FH + ky) * FW + kx;
+					packed[k >> 1] |= (uint32_t)__ldg(line + kx) << (16 * (k & 1));
+				}
+			}
+		}
+	} else {
+		bool col_ok[FW];
 #pragma unroll
-			for (int kx = 0; kx < FW; kx++) {
-				const int k = (ch * FH + ky) * FW + kx;
-				const uint32_t v = (row_ok && col_ok[kx]) ? (uint32_t)__ldg(line + kx) : 0u;
-				packed[k >> 1] |= v << (16 * (k & 1));
+		for (int kx = 0; kx < FW; kx++) col_ok[kx] = valid && (ix0 + kx) >= 0 && (ix0 + kx) < w;
+#pragma unroll
+		for (int ch = 0; ch < C; ch++) {
+#pragma unroll
+			for (int ky = 0; ky < FH; ky++) {
+				const int iy = iy0 + ky;
+				const bool row_ok = iy >= 0 && iy < h;
+				const unsigned short* __restrict__ line = src + ((size_t)ch * h + (row_ok ? iy : 0)) * w + ix0;
+#pragma unroll
+				for (int kx = 0; kx < FW; kx++) {
+					const int k = (ch * FH + ky) * FW + kx;
+					const uint32_t v = (row_ok && col_ok[kx]) ? (uint32_t)__ldg(line + kx) : 0u;
+					packed[k >> 1] |= v << (16 * (k & 1));
+				}
 			}
 		}
 	}
@@ -150,12 +169,15 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 		const size_t img_stride = (size_t)p.c * p.h * p.w + 1;
 		const unsigned short bias_bits = bits_of<T>(p.bias_value);
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		// tile coordinates advance incrementally (one division at the start instead of three per tile)
+		const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+		int twi = (tile0 + grp) % tiles_w, thi = ((tile0 + grp) / tiles_w) % tiles_h, tni = (tile0 + grp) / (tiles_w * tiles_h);
 		for (int it = grp; it < n_tiles; it += FWD_BUILD_GROUPS) {
-			const int tile = tile0 + it;
 			const int stage = it % Cfg::STAGES;
 			const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
-			const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
 			const int px = twi * p.tw + rx, py = thi * p.th + ry, pn = tni * p.tn + rn;
+			twi += FWD_BUILD_GROUPS;
+			while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
 			const bool valid = px < p.W && py < p.H && pn < p.N;
 			mbar_wait(empty_bar(stage), phase ^ 1u);
 			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
@@ -363,12 +385,14 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 		const size_t img_stride = (size_t)p.c * p.h * p.w + 1;
 		const unsigned short bias_bits = bits_of<T>(p.bias_value);
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+		int twi = (t_begin + pair) % tiles_w, thi = ((t_begin + pair) / tiles_w) % tiles_h, tni = (t_begin + pair) / (tiles_w * tiles_h);
 		for (int k = pair; k < n_steps; k += WG_BUILD_WARPS / 2) {
-			const int t = t_begin + k;
 			const int stage = k % Cfg::STAGES;
 			const uint32_t phase = (uint32_t)(k / Cfg::STAGES) & 1u;
-			const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
 			const int px = twi * p.tw + rx, py = thi * p.th + ry, pn = tni * p.tn + rn;
+			twi += WG_BUILD_WARPS / 2;
+			while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
 			const bool valid = px < p.W && py < p.H && pn < p.N;
 			mbar_wait(empty_bar(stage), phase ^ 1u);
 			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
