@@ -147,7 +147,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 
 	if (threadIdx.x == 0) {
 		prefetch_tensormap(&tmap_b);
-		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
 		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
 		mbar_init(bfull_bar, 1);
 		fence_barrier_init();
@@ -182,8 +182,9 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 			mbar_wait(empty_bar(stage), phase ^ 1u);
 			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
 				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::A_BYTES, row);
-			fence_proxy_async();
-			mbar_arrive(full_bar(stage));
+			fence_proxy_async();          // each writer publishes its row to the async proxy ...
+			__syncwarp();
+			if (lane == 0) mbar_arrive(full_bar(stage));     // ... then one arrival per warp
 		}
 	} else if (warp == MMA_WARP) {
 		// ===================== MMA issuer (also fetches the filters once) =====================
@@ -302,7 +303,7 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 
 	if (threadIdx.x == 0) {
 		prefetch_tensormap(&tmap_dy);
-		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1 + Cfg::KPIX); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1 + Cfg::KPIX / 32); mbar_init(empty_bar(s), 1); }
 		mbar_init(done_bar, 1);
 		fence_barrier_init();
 	}
@@ -397,8 +398,9 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 			mbar_wait(empty_bar(stage), phase ^ 1u);
 			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
 				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, row);
-			fence_proxy_async();
-			mbar_arrive(full_bar(stage));
+			fence_proxy_async();          // each writer publishes its row to the async proxy ...
+			__syncwarp();
+			if (lane == 0) mbar_arrive(full_bar(stage));     // ... then one arrival per warp
 		}
 	}
 	tc_fence_before();
