@@ -115,7 +115,11 @@ template <> __device__ __forceinline__ unsigned short bits_of<__half>(float v) {
 template <> __device__ __forceinline__ unsigned short bits_of<__nv_bfloat16>(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
 // ================================================================ forward
-constexpr int FWD_BUILD_GROUPS = 4, FWD_BUILD_WARPS = 4 * FWD_BUILD_GROUPS, FWD_EPI_GROUPS = 2;
+// ncu (stall sampling) on the first version showed the builders waiting for free stages 30 % of the time and the
+// epilogue groups waiting for accumulators: the limiter is the LATENCY of one tile's epilogue (tcgen05.ld -> activation ->
+// stores is a ~2000-cycle dependent chain for a warp sharing its scheduler with six others), so tiles in flight in the
+// epilogue matter more than builder warps: 2 builder groups, 4 epilogue groups (= accumulator stages)
+constexpr int FWD_BUILD_GROUPS = 2, FWD_BUILD_WARPS = 4 * FWD_BUILD_GROUPS, FWD_EPI_GROUPS = 4;
 constexpr int FWD_THREADS = (FWD_BUILD_WARPS + 1 + 4 * FWD_EPI_GROUPS) * 32;
 template <int KP, int BN> struct FirstFwdCfg {
 	static constexpr int A_BYTES = 128 * KP * 2;

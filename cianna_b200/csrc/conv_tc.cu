@@ -233,8 +233,11 @@ struct IgemmCfg {
 	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
 	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias rows*/;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias rows*/;
 	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;                      // accumulator ring in TMEM (512 columns)
+	// one tile's epilogue is a long dependent chain: what matters is how many tiles are in their epilogue at once
+	static constexpr int EPI_GROUPS = ACC_STAGES;
+	static constexpr int THREADS = (2 + 4 * EPI_GROUPS) * 32;
 	static constexpr int ACC_COLS = ACC_STAGES * BN;
 	static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
 	static constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);   // 128B / 64B / 32B swizzle
@@ -242,7 +245,7 @@ struct IgemmCfg {
 };
 
 template <typename T, int BN, int BK>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(IgemmCfg<BN, BK>::THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
 	using Cfg = IgemmCfg<BN, BK>;
 	extern __shared__ uint8_t smem_raw[];
@@ -327,7 +330,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 	} else {
 		// ===================== epilogue warps =====================
 		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-		epilogue_loop<T, BN, Cfg::ACC_STAGES>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 2);
+		epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 2);
 	}
 
 	tc_fence_before();
@@ -347,7 +350,7 @@ static int launch_igemm(const CUtensorMap& ma, const CUtensorMap& mb, const Igem
 		configured = true;
 	}
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-	kern<<<grid, 320, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+	kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }
