@@ -117,6 +117,59 @@ conv_update_operand_kernel(float* __restrict__ master, float* __restrict__ momen
 	}
 }
 
+// The same update with one block per filter: the filter's master and momentum rows (k_ref contiguous floats each) are
+// staged in shared memory with coalesced loads, updated there in operand order (tap, c) - coalesced gradient reads and
+// w_fwd writes, conflict-free strided shared-memory accesses (stride `taps` is odd for 1x1 / 3x3 / 5x5) - and written
+// back coalesced.  22 bytes per weight, all of them in full lines (the one-thread-per-weight forms above cost a
+// 32-byte sector per 2- or 4-byte access on one side or the other).
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_update_rows_kernel(float* __restrict__ master, float* __restrict__ moment, const float* __restrict__ grad,
+                        const float* __restrict__ grad_b, const float* __restrict__ hyper, float bias_value,
+                        T* __restrict__ w_fwd, float* __restrict__ bias_w, int taps, int in_c, int in_cp) {
+	extern __shared__ float rows[];                 // [2][kref]: master row, momentum row
+	const int kref = taps * in_c + 1;
+	const int f = blockIdx.x;
+	float* sm_w = rows;
+	float* sm_m = rows + kref;
+	const float alpha = hyper[0], mom = hyper[1], wdlr = hyper[2], S = hyper[3];
+	for (int i = threadIdx.x; i < kref; i += blockDim.x) {
+		sm_w[i] = master[(size_t)f * kref + i];
+		sm_m[i] = moment[(size_t)f * kref + i];
+	}
+	__syncthreads();
+	const int n_op = taps * in_cp;
+	const float* __restrict__ g = grad + (size_t)f * n_op;
+	T* __restrict__ wf = w_fwd + (size_t)f * n_op;
+	for (int j = threadIdx.x; j < n_op; j += blockDim.x) {
+		const int tap = j / in_cp, c = j - tap * in_cp;
+		if (c >= in_c) continue;
+		const int mi = c * taps + tap;
+		float wv = sm_w[mi];
+		float m = alpha * g[j] + mom * sm_m[mi];
+		m += wdlr * wv * S;
+		wv -= m / S;
+		sm_m[mi] = m;
+		sm_w[mi] = wv;
+		wf[j] = from_f32<T>(wv);
+	}
+	if (threadIdx.x == 0) {
+		const int mi = kref - 1;
+		float wv = sm_w[mi];
+		float m = alpha * (bias_value * grad_b[f]) + mom * sm_m[mi];
+		m += wdlr * wv * S;
+		wv -= m / S;
+		sm_m[mi] = m;
+		sm_w[mi] = wv;
+		bias_w[f] = wv;
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < kref; i += blockDim.x) {
+		master[(size_t)f * kref + i] = sm_w[i];
+		moment[(size_t)f * kref + i] = sm_m[i];
+	}
+}
+
 // w_bwd[c][taps-1-tap][f] = w_fwd[f][tap][c] through a 32x32 shared-memory tile; grid (c tiles, f tiles, taps)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -316,8 +369,21 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	if (!old_update && ms_c == 1 && !is_pivot && ms_f == (size_t)taps * d->in_c + 1) {
 		const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
 		const long long op_total = (long long)d->out_c * taps * in_cp;
-		CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_operand_kernel<T><<<grid_for(op_total, 256), 256, 0, as_stream(s)>>>(
-			w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, (T*)w->w_fwd, w->bias_w, d->out_c, taps, d->in_c, in_cp)));
+		const size_t row_smem = 2 * ((size_t)taps * d->in_c + 1) * sizeof(float);
+		if (row_smem <= 96 * 1024) {
+			static bool configured = false;
+			if (!configured) {
+				CB_CUDA(cudaFuncSetAttribute(conv_update_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+				CB_CUDA(cudaFuncSetAttribute(conv_update_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+				CB_CUDA(cudaFuncSetAttribute(conv_update_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+				configured = true;
+			}
+			CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_rows_kernel<T><<<d->out_c, 256, row_smem, as_stream(s)>>>(
+				w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, (T*)w->w_fwd, w->bias_w, taps, d->in_c, in_cp)));
+		} else {
+			CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_operand_kernel<T><<<grid_for(op_total, 256), 256, 0, as_stream(s)>>>(
+				w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, (T*)w->w_fwd, w->bias_w, d->out_c, taps, d->in_c, in_cp)));
+		}
 		CB_LAUNCH_CHECK();
 		dim3 tgrid((unsigned)ceil_div(d->in_c, 32), (unsigned)ceil_div(out_cp, 32), (unsigned)taps);
 		CB_DISPATCH_DTYPE(d->dtype, T, (conv_wbwd_transpose_kernel<T><<<tgrid, 256, 0, as_stream(s)>>>(

@@ -235,8 +235,9 @@ struct IgemmCfg {
 	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
 	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias rows*/;
 	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;                      // accumulator ring in TMEM (512 columns)
-	// one tile's epilogue is a long dependent chain: what matters is how many tiles are in their epilogue at once
-	static constexpr int EPI_GROUPS = ACC_STAGES;
+	// (measured: four groups for BN <= 128 do not help this kernel - its small-N launches are issue-bound, not
+	//  epilogue-latency-bound - and cost registers)
+	static constexpr int EPI_GROUPS = 2;
 	static constexpr int THREADS = (2 + 4 * EPI_GROUPS) * 32;
 	static constexpr int ACC_COLS = ACC_STAGES * BN;
 	static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
