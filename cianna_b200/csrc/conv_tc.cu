@@ -115,7 +115,17 @@ struct IgemmParams {
 	int halo_w;                  // pixels per halo row = tw + f_w - 1
 	int a_stage_bytes, a_stages; // one halo tile (rounded up to 1024 B), ring depth
 	int b_blk_bytes;             // one (tap, channel block) of the resident filter bank
+	// 2-CTA cluster variant of conv_igemm_kernel: the two CTAs of a cluster work on two M tiles of the same N tile and
+	// each fetches half of the filter block, multicast to both
+	int cluster, pairs_m;
 };
+
+// tile index -> (M tile, N tile).  Cluster mode enumerates pairs: tile = 2*pair + rank, so that with an even grid the
+// two CTAs of a cluster always hold the two tiles of one pair (a pair past the last M tile gets a dummy, all-OOB tile).
+__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& mt, int& nt) {
+	if (p.cluster) { const int q = tile >> 1; nt = q / p.pairs_m; mt = 2 * (q - nt * p.pairs_m) + (tile & 1); }
+	else { nt = tile / p.tiles_m; mt = tile - nt * p.tiles_m; }
+}
 
 // ---------------------------------------------------------------- shared epilogue of the forward / dgrad kernels
 // Eight epilogue warps in two groups of four (one warp per TMEM lane quadrant): group g drains the accumulators of the
@@ -136,7 +146,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const int act = p.activ.type, mode = p.mode, n_real = p.n_real, n_pad = p.n_pad, length = p.length;
 	const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta, bias_value = p.bias_value;
 	const float* __restrict__ bias_w = p.bias_w;
-	const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_m = p.tiles_m, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+	const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
 	const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
 	float* bs = bias_rows + grp * 256;
@@ -145,7 +155,8 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		if ((it % NGROUPS) != grp) continue;
 		const int acc = it % ACC_STAGES;
 		const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-		const int mt = tile % tiles_m, nt = tile / tiles_m;
+		int mt, nt;
+		decode_tile(p, tile, mt, nt);
 		const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
 		const int px = twi * tw + (row % tw);
 		const int py = thi * th + (row / tw) % th;
@@ -266,15 +277,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 	if (threadIdx.x == 0) {
 		prefetch_tensormap(&tmap_a);
 		prefetch_tensormap(&tmap_b);
-		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		// cluster mode: a stage is free again when BOTH CTAs have consumed it (each writes half of B into both)
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.cluster ? 2 : 1); }
 		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
 		fence_barrier_init();
 	}
 	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
 	tc_fence_before();
 	__syncthreads();
+	if (p.cluster) cluster_sync();        // the peer's barriers exist before anything is multicast to them
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot_ptr;
+	const uint32_t rank = p.cluster ? cluster_ctarank() : 0u;
 
 	const int taps = p.f_h * p.f_w;
 	const int k_iters = taps * p.kc_blocks;
@@ -284,7 +298,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		if (lane == 0) {
 			int stage = 0; uint32_t phase = 0;
 			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-				const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+				int mt, nt;
+				decode_tile(p, tile, mt, nt);
 				const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
 				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
 				for (int tap = 0; tap < taps; tap++) {
@@ -294,7 +309,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 						const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
 						mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
 						tma_load_4d(sa, &tmap_a, full_bar(stage), cb * BK, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
-						tma_load_3d(sb, &tmap_b, full_bar(stage), cb * BK, tap, nt * BN);
+						if (p.cluster)     // this CTA's half of the filter block, to both CTAs (tmap_b boxes are BN/2 rows here)
+							tma_load_3d_multicast(sb + rank * (Cfg::B_BYTES / 2), &tmap_b, full_bar(stage), cb * BK, tap,
+							                      nt * BN + (int)rank * (BN / 2), (uint16_t)3);
+						else
+							tma_load_3d(sb, &tmap_b, full_bar(stage), cb * BK, tap, nt * BN);
 						if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 					}
 				}
@@ -308,6 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
 			const uint32_t idesc = p.idesc;
 			const int num_tiles = p.num_tiles;
+			const bool cluster = p.cluster != 0;
 			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
 				tc_fence_after();
@@ -321,7 +341,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
 					for (int kk = 0; kk < BK / 16; kk++)
 						mma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-					mma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+					if (cluster) mma_commit_multicast(empty_bar(stage), (uint16_t)3);   // frees the slot in both CTAs
+					else mma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
 					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 				}
 				mma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
@@ -336,6 +357,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 	tc_fence_before();
 	__syncthreads();
+	if (p.cluster) cluster_sync();        // neither CTA leaves while the other may still signal its barriers
 	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -351,6 +373,29 @@ static int launch_igemm(const CUtensorMap& ma, const CUtensorMap& mb, const Igem
 		configured = true;
 	}
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+	if (p.cluster) {
+		// clusters of two CTAs (one per SM): as many as the device can keep resident at once, so that the persistent
+		// tile loop of every cluster starts together
+		static int max_clusters = -1;
+		cudaLaunchConfig_t cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+		cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+		if (max_clusters < 0) {
+			cfg.gridDim = dim3((unsigned)(g_num_sms & ~1));
+			int n = 0;
+			if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = g_num_sms / 2 - 2;
+			max_clusters = n;
+		}
+		grid = 2 * max_clusters;
+		if (grid > p.num_tiles) grid = p.num_tiles;          // (num_tiles is even in cluster mode)
+		cfg.gridDim = dim3((unsigned)grid);
+		if (cudaLaunchKernelEx(&cfg, kern, ma, mb, p) != cudaSuccess) { set_error("cluster launch of conv_igemm_kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return CB200_ERR_CUDA; }
+		g_launches++;
+		return CB200_OK;
+	}
 	kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
@@ -599,14 +644,23 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	choose_rect(out_w, out_h, batch, 128, tw, th, tn);
 	int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, tw, th, tn, swizzle_for(bk));
 	if (rc) return rc;
-	rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, bn, swizzle_for(bk));
-	if (rc) return rc;
 	p.W = out_w; p.H = out_h; p.N = batch;
 	p.tw = tw; p.th = th; p.tn = tn;
 	p.tiles_w = ceil_div(out_w, tw); p.tiles_h = ceil_div(out_h, th); p.tiles_n = ceil_div(batch, tn);
 	p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 	p.tiles_nn = ceil_div(n_pad, bn);
 	p.num_tiles = p.tiles_m * p.tiles_nn;
+	// Wide-N layers are bound by the L2 -> SM path (A 16 KB + B 32 KB per 128x256x64 MACs = 87 FLOP/B against the ~128
+	// the tensor pipe needs at 64 B/clk/SM): two CTAs of a cluster take two M tiles of the same N tile and each fetches
+	// half of the filter block, multicast to both, which removes a third of the traffic.
+	static const bool no_cluster = getenv("CB200_NO_CLUSTER") != nullptr;
+	p.cluster = (!no_cluster && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
+	if (p.cluster) {
+		p.pairs_m = ceil_div(p.tiles_m, 2);
+		p.num_tiles = 2 * p.pairs_m * p.tiles_nn;
+	}
+	rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, p.cluster ? bn / 2 : bn, swizzle_for(bk));
+	if (rc) return rc;
 	p.f_h = f_h; p.f_w = f_w; p.off_h = off_h; p.off_w = off_w;
 	p.kc_blocks = ceil_div(cin_p, bk);
 	p.n_real = n_real; p.n_pad = n_pad;

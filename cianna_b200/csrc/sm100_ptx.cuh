@@ -49,6 +49,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one TMA box written to the same CTA-relative shared-memory offset of every CTA in `cta_mask`, signalling the mbarrier
+// at the same offset in each of them
+__device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint16_t cta_mask) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 // whole-warp instructions (.sync.aligned): call with all 32 lanes converged
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
@@ -73,6 +85,10 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
 // arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same, arriving on the mbarrier at this CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // 32 lanes x 32 consecutive columns of 32-bit: thread i of the warp receives lane (base+i), columns c..c+31
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

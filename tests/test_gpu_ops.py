@@ -43,6 +43,8 @@ TC_SHAPES = [
     (128, 64, 1, 40, 1, 0),    # dense-like: 1x1 map, tile spans 128 images
     (4, 32, 12, 32, 1, 0),     # 32 -> 32 channels: the shape of a first layer run on patch rows (weight-gradient slab wider than the tensor)
     (2, 16, 9, 24, 3, 1),      # 16-channel operands everywhere
+    (65, 64, 28, 128, 1, 0),   # 399 M tiles (odd): enough work for the 2-CTA cluster variant (multicast filter halves, dummy last tile)
+    (49, 64, 28, 256, 3, 1),   # cluster variant with BN=256, 3x3, 301 M tiles
 ]
 
 
