@@ -586,6 +586,7 @@ static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CU
 }
 
 extern const char* g_last_conv_impl;
+int g_enable_cluster = 0;   // cb200_force_simt bit 2: 2-CTA multicast variant of conv_igemm_kernel (off by default, see run_igemm)
 int g_disable_halo = 0;     // test hook (cb200_force_simt bit 1): route everything through the per-tap kernel
 
 // Decide whether the layer goes to the halo kernel and, if so, fill its tiling; returns the dynamic smem size or 0.
@@ -650,11 +651,14 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 	p.tiles_nn = ceil_div(n_pad, bn);
 	p.num_tiles = p.tiles_m * p.tiles_nn;
-	// Wide-N layers are bound by the L2 -> SM path (A 16 KB + B 32 KB per 128x256x64 MACs = 87 FLOP/B against the ~128
-	// the tensor pipe needs at 64 B/clk/SM): two CTAs of a cluster take two M tiles of the same N tile and each fetches
-	// half of the filter block, multicast to both, which removes a third of the traffic.
-	static const bool no_cluster = getenv("CB200_NO_CLUSTER") != nullptr;
-	p.cluster = (!no_cluster && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
+	// Optional 2-CTA cluster variant (cb200_force_simt bit 2): two CTAs take two M tiles of the same N tile and each
+	// fetches half of the filter block, TMA-multicast to both - a third less L2 output traffic.  Measured on the wide-N
+	// layers of Darknet19: no gain (71.5 % vs 70.5 % tensor-pipe activity).  Those launches are bound by SHARED-MEMORY
+	// bandwidth, not by L2: per K=16 step the MMA reads 4 KB of A + 8 KB of B while TMA refills 12 KB, 180 B/clk at full
+	// tensor rate against 128 B/clk per SM, i.e. a 71 % ceiling that multicast does not move (each SM still receives and
+	// reads the whole B block).  Lifting it takes cta_group::2 MMAs (B split between the two SMs) - next round.  The path
+	// stays as a tested option.
+	p.cluster = (g_enable_cluster && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
 	if (p.cluster) {
 		p.pairs_m = ceil_div(p.tiles_m, 2);
 		p.num_tiles = 2 * p.pairs_m * p.tiles_nn;

@@ -69,7 +69,9 @@ const char* cb200_version(void);
 /* which implementation the last conv/dense call dispatched to: "tcgen05" or "simt" */
 const char* cb200_last_conv_impl(void);
 /* bit 0: force the generic SIMT kernels (parity cross-checks of the tcgen05 path); bit 1: keep the tcgen05 path but
- * route every layer through the per-tap kernel instead of the halo-reuse kernel (A/B checks); 0 = auto */
+ * route every layer through the per-tap kernel instead of the halo-reuse kernel (A/B checks); bit 2: enable the
+ * 2-CTA cluster variant of the per-tap kernel (filter halves TMA-multicast to both CTAs; measured neutral, off by
+ * default); 0 = auto */
 void cb200_force_simt(int on);
 /* number of kernels launched by this library since the last reset */
 long long cb200_launch_count(int reset);

@@ -83,6 +83,14 @@ def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
     assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
     ref_g = co.conv_weight_grad(col, dy).astype(np.float32)
     assert np.array_equal(got, ref_g)
+    if B * So * So >= 128 * 2 * 148 and N >= 96:
+        # enough M tiles for the optional 2-CTA cluster variant (filter halves multicast to both CTAs): same bits
+        cabi.lib().cb200_force_simt(4)
+        try:
+            y2 = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+        finally:
+            cabi.lib().cb200_force_simt(0)
+        assert np.array_equal(y2, ref)
     layer.free(); xb.free(); dyb.free()
 
 
