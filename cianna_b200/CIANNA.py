@@ -13,8 +13,8 @@ libcianna_b200.so (CUDA core, C-ABI of include/cianna_b200.h).  Usage is unchang
     cnn.train(nb_iter=1, learning_rate=0.003, momentum=0.9, ...)
 
 There is no CPU path: comp_meth must be "C_CUDA" and a missing CUDA extension / device is an error.
-Methods that belong to parts of upstream outside this round's scope (lrn, print_arch_tex) raise
-NotImplementedError rather than silently doing nothing.
+Options of upstream that the B200 core does not cover yet ("not covered") stop with an explicit
+error rather than silently doing nothing.
 """
 import ctypes
 import math
@@ -57,6 +57,8 @@ def _load():
     L.conv_create.argtypes = [vp, vp, ip, ci, ip, ip, ip, ip, cs, fp, cf, cs, cf, vp, ci]
     L.pool_create.argtypes = [vp, vp, ip, ip, ip, cs, cs, ci, cf]
     L.norm_create.argtypes = [vp, vp, cs, cs, ci, ci, vp, ci]
+    L.lrn_create.argtypes = [vp, vp, cs, ci, cf, cf, cf, vp, ci]
+    L.print_architecture_tex.argtypes = [vp, cs, cs] + [ci] * 11
     L.dense_create.argtypes = [vp, vp, ci, cs, fp, cf, ci, cs, cf, vp, ci]
     L.train_network.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, ci, ci, ci, ci, ci, cf, ci]
     L.forward_testset.argtypes = [vp, ci, ci, ci, ci]
@@ -249,8 +251,11 @@ def norm(normalization="GN", activation="LIN", prev_layer=-1, group_size=8, set_
     return L.norm_create(net, _prev(L, net, prev_layer), _s(normalization), _s(activation), int(group_size), int(set_off), None, 0)
 
 
-def lrn(*args, **kwargs):
-    raise NotImplementedError("lrn layers are not part of this round's hot-path scope (SURVEY.md 8a16)")
+def lrn(activation="LIN", prev_layer=-1, range=5, k=1.0, alpha=1.0, beta=0.5, network=None):
+    """Local response normalisation across channels; keywords and defaults of src/python_module.c:551-575."""
+    L = _load()
+    net = _net(network)
+    return L.lrn_create(net, _prev(L, net, prev_layer), _s(activation), int(range), float(k), float(alpha), float(beta), None, 0)
 
 
 def set_frozen_layers(froz_array, network=None):
@@ -374,8 +379,13 @@ def forward(saving=1, drop_mode="AVG_MODEL", no_error=0, repeat=1, network=None,
     L.forward_testset(net, int(saving), int(repeat), 1 if drop_mode == "MC_MODEL" else 0, int(silent))
 
 
-def print_arch_tex(*args, **kwargs):
-    raise NotImplementedError("print_arch_tex (LaTeX export) is outside the hot-path scope (SURVEY.md 8f rank 4)")
+def print_arch_tex(path, file_name, size=1, in_size=1, f_size=1, out_size=1, stride=1, padding=1, in_padding=0,
+                   activation=0, bias=0, dropout=0, param_count=0, network=None):
+    """Architecture table as path/file_name.tex (+ .pdf when pdflatex is installed); keywords and defaults of
+    src/python_module.c:991-1009."""
+    _load().print_architecture_tex(_net(network), _s(path), _s(file_name), int(size), int(in_size), int(f_size),
+                                   int(out_size), int(stride), int(padding), int(in_padding), int(activation),
+                                   int(bias), int(dropout), int(param_count))
 
 
 # ------------------------------------------------------------------ additions: explicit mini-batch control / read-back

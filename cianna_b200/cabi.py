@@ -304,6 +304,40 @@ class NormLayer:
                 self.d_gamma.to_numpy(np.float32, shp), self.d_beta.to_numpy(np.float32, shp))
 
 
+class LrnDesc(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int), ("c", ctypes.c_int),
+                ("h", ctypes.c_int), ("w", ctypes.c_int), ("range", ctypes.c_int), ("k", ctypes.c_float),
+                ("alpha", ctypes.c_float), ("beta", ctypes.c_float)]
+
+
+class LrnLayer:
+    def __init__(self, dtype, batch, c, h, w, rng=5, k=1.0, alpha=1.0, beta=0.5, length=None):
+        L = lib()
+        L.cb200_lrn_forward.argtypes = [ctypes.c_void_p] * 5
+        L.cb200_lrn_backward.argtypes = [ctypes.c_void_p] * 9
+        self.d = LrnDesc(dtype, batch, batch if length is None else length, c, h, w, rng, k, alpha, beta)
+        n = batch * h * w * round8(c)
+        self.n = n
+        self.y, self.dx = DevBuf(n * L.cb200_dtype_size(dtype)), DevBuf(n * L.cb200_dtype_size(dtype))
+        self.scale = DevBuf(n * 4)
+
+    def forward(self, x_buf, keep_scale=True):
+        check(lib().cb200_lrn_forward(ctypes.byref(self.d), x_buf.ptr, self.y.ptr, self.scale.ptr if keep_scale else None, None))
+        return self.y
+
+    def backward(self, x_buf, dy_buf, prev_act=None, prev_out=None):
+        pa = ctypes.byref(prev_act) if prev_act is not None else None
+        po = prev_out.ptr if prev_out is not None else None
+        check(lib().cb200_lrn_backward(ctypes.byref(self.d), x_buf.ptr, self.y.ptr, dy_buf.ptr, self.dx.ptr, self.scale.ptr, pa, po, None))
+        return self.dx
+
+    def scale_ref_layout(self):
+        """local_scale as [C][B][H*W]"""
+        d = self.d
+        s = self.scale.to_numpy(np.float32, (d.batch, d.h * d.w, round8(d.c)))
+        return np.ascontiguousarray(s[:, :, :d.c].transpose(2, 0, 1))
+
+
 class YoloDesc(ctypes.Structure):
     _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int), ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
                 ("nb_box", ctypes.c_int), ("nb_class", ctypes.c_int), ("nb_param", ctypes.c_int), ("max_nb_obj", ctypes.c_int),

@@ -106,6 +106,14 @@ typedef struct norm_param {
 	layer *fused_pool;
 } norm_param;
 
+/* local response normalisation across channels (src/structs.h lrn_param, src/lrn_layer.c) */
+typedef struct lrn_param {
+	int range, n_dim, dim_offset;
+	float k, alpha, beta;
+	cb200_lrn_desc desc;
+	float *local_scale;    /* device, FP32, one value per activation (training only) */
+} lrn_param;
+
 typedef struct dense_param {
 	int in_size;           /* inputs incl. the bias node */
 	int nb_neurons;
@@ -225,8 +233,15 @@ void pool_save(FILE *f, layer *current, int f_bin);
 void pool_load(network *net, FILE *f, int f_bin);
 void norm_save(FILE *f, layer *current, int f_bin);
 void norm_load(network *net, FILE *f, int f_bin);
+int lrn_create(network *net, layer *previous, const char *activation, int range, float k, float alpha, float beta, FILE *f_load, int f_bin);
+void lrn_save(FILE *f, layer *current, int f_bin);
+void lrn_load(network *net, FILE *f, int f_bin);
+int cb_lrn_range(layer *current);
 void dense_save(FILE *f, layer *current, int f_bin);
 void dense_load(network *net, FILE *f, int f_bin);
+void print_architecture_tex(network *net, const char *path, const char *file_name, int l_size, int l_in_size,
+	int l_f_size, int l_out_size, int l_stride, int l_padding, int l_in_padding, int l_activation, int l_bias,
+	int l_dropout, int l_param_count);
 void save_network(network *net, const char *filename, int f_bin);
 void load_network(network *net, const char *filename, int epoch, int nb_layers, int f_bin);
 void set_frozen_layers(network *net, int *tab, int dim);

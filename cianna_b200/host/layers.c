@@ -687,3 +687,108 @@ void norm_load(network *net, FILE *f, int f_bin)
 	previous = net->nb_layers <= 0 ? NULL : net->net_layers[net->nb_layers - 1];
 	norm_create(net, previous, norm, activ_type, group_size, set_off, f, f_bin);
 }
+
+/* ------------------------------------------------------------------ local response normalisation
+ * Same layer as upstream's lrn_create / cuda_forward_lrn_layer / cuda_backward_lrn_layer (src/lrn_layer.c:96-214,
+ * src/cuda/cuda_lrn_layer.cu:172-215): no weights, a per-activation scale kept between the two passes. */
+static void forward_lrn_layer(layer *current)
+{
+	network *net = current->c_network;
+	lrn_param *p = (lrn_param *)current->param;
+	if (net->length == 0) return;
+	p->desc.length = net->length;
+	CB_CHECK(cb200_lrn_forward(&p->desc, current->previous->output, current->output, p->local_scale, NULL));
+}
+
+static void backward_lrn_layer(layer *current)
+{
+	network *net = current->c_network;
+	lrn_param *p = (lrn_param *)current->param;
+	layer *prev = current->previous;
+	p->desc.length = net->length;
+	CB_CHECK(cb200_lrn_backward(&p->desc, prev->output, current->output, current->delta_o, prev->delta_o, p->local_scale,
+		&prev->activ, prev->output, NULL));
+}
+
+int lrn_create(network *net, layer *previous, const char *activation, int range, float k, float alpha, float beta, FILE *f_load, int f_bin)
+{
+	layer *current = new_layer(net, LRN, previous);
+	lrn_param *p;
+	size_t n_act;
+	char activ[40];
+	(void)f_load; (void)f_bin;
+
+	printf("L:%d - CREATING LOCAL RESPONSE NORMALIZATION LAYER ...\n", net->nb_layers);
+	if (previous == NULL) { printf("\nERROR: normalization layer is not autorized as first layer.\n"); exit(EXIT_FAILURE); }
+	if (previous->type == DENSE) { printf("\nERROR: normalization layer is not authorized after dense layers atm.\n"); exit(EXIT_FAILURE); }
+	if (previous->type == NORM || previous->type == LRN) { printf("\nERROR: stacking two normalization layers is not allowed.\n"); exit(EXIT_FAILURE); }
+	if (range <= 0) { printf("\nERROR: LRN range must be > 0.\n"); exit(EXIT_FAILURE); }
+
+	p = (lrn_param *)calloc(1, sizeof(lrn_param));
+	p->range = range; p->k = k; p->alpha = alpha; p->beta = beta;
+	p->n_dim = previous->out_c; p->dim_offset = previous->out_h * previous->out_w;
+	current->out_c = previous->out_c; current->out_h = previous->out_h; current->out_w = previous->out_w;
+	current->param = p;
+	load_activ_param(current, activation);
+	if (current->activation_type == SOFTMAX) { printf("\nERROR: softmax activation for normalization layer is not authorized\n"); exit(EXIT_FAILURE); }
+	if (current->activation_type == YOLO) { printf("\nERROR: YOLO activation for normalization layer is not authorized\n"); exit(EXIT_FAILURE); }
+	if (current->activation_type != LINEAR) { printf("\nERROR: only the LIN activation is supported on normalization layers by the B200 core yet.\n"); exit(EXIT_FAILURE); }
+	set_activ_defaults(current, activation);
+
+	p->desc.dtype = net->dtype; p->desc.batch = net->batch_size; p->desc.length = net->batch_size;
+	p->desc.c = p->n_dim; p->desc.h = current->out_h; p->desc.w = current->out_w;
+	p->desc.range = range; p->desc.k = k; p->desc.alpha = alpha; p->desc.beta = beta;
+
+	n_act = act_bytes(net, current->out_c, current->out_h, current->out_w);
+	current->output = dev_alloc(n_act);
+	if (!net->inference_only) {
+		p->local_scale = (float *)dev_alloc(n_act / cb200_dtype_size(net->dtype) * sizeof(float));
+		current->delta_o = dev_alloc(n_act);
+	}
+	current->forward = forward_lrn_layer;
+	current->backprop = backward_lrn_layer;
+	current->nb_params = 0;
+	print_string_activ_param(current, activ);
+	printf("      Range: %d, k: %f, Alpha: %f, Beta: %f, Activation: %s\n", p->range, p->k, p->alpha, p->beta, activ);
+	return net->nb_layers - 1;
+}
+
+int cb_lrn_range(layer *current) { return ((lrn_param *)current->param)->range; }
+
+void lrn_save(FILE *f, layer *current, int f_bin)
+{
+	lrn_param *p = (lrn_param *)current->param;
+	char layer_type = 'L';
+	if (f_bin) {
+		fwrite(&layer_type, sizeof(char), 1, f);
+		fwrite(&p->range, sizeof(int), 1, f);
+		fwrite(&p->k, sizeof(float), 1, f);
+		fwrite(&p->alpha, sizeof(float), 1, f);
+		fwrite(&p->beta, sizeof(float), 1, f);
+		print_activ_param(f, current, f_bin);
+	} else {
+		fprintf(f, "L %d %f %f %f ", p->range, p->k, p->alpha, p->beta);
+		print_activ_param(f, current, f_bin);
+		fprintf(f, "\n");
+	}
+}
+
+void lrn_load(network *net, FILE *f, int f_bin)
+{
+	int range;
+	float k, alpha, beta;
+	char activ_type[40];
+	layer *previous;
+	printf("Loading Local Response Normalization layer, L:%d\n", net->nb_layers + 1);
+	if (f_bin) {
+		fread(&range, sizeof(int), 1, f);
+		fread(&k, sizeof(float), 1, f);
+		fread(&alpha, sizeof(float), 1, f);
+		fread(&beta, sizeof(float), 1, f);
+		fread(activ_type, sizeof(char), 40, f);
+	} else {
+		fscanf(f, " %d %f %f %f %s", &range, &k, &alpha, &beta, activ_type);
+	}
+	previous = net->nb_layers <= 0 ? NULL : net->net_layers[net->nb_layers - 1];
+	lrn_create(net, previous, activ_type, range, k, alpha, beta, f, f_bin);
+}

@@ -776,6 +776,7 @@ void save_network(network *net, const char *filename, int f_bin)
 		case CONV: conv_save(f, net->net_layers[i], f_bin); break;
 		case POOL: pool_save(f, net->net_layers[i], f_bin); break;
 		case NORM: norm_save(f, net->net_layers[i], f_bin); break;
+		case LRN: lrn_save(f, net->net_layers[i], f_bin); break;
 		case DENSE: dense_save(f, net->net_layers[i], f_bin); break;
 		default: printf("ERROR: layer type cannot be saved\n"); exit(EXIT_FAILURE);
 		}
@@ -806,7 +807,7 @@ void load_network(network *net, const char *filename, int iter, int nb_layers, i
 		case 'P': pool_load(net, f, f_bin); break;
 		case 'N': norm_load(net, f, f_bin); break;
 		case 'D': dense_load(net, f, f_bin); break;
-		case 'L': printf("ERROR: LRN layers cannot be loaded by the B200 core yet.\n"); exit(EXIT_FAILURE); break;
+		case 'L': lrn_load(net, f, f_bin); break;
 		case ' ':
 		case '\n': layer_count--; break;
 		default: printf("ERROR: Layer type not recognized when loading the save model, likely file format error!\n"); exit(EXIT_FAILURE);

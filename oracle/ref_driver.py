@@ -62,6 +62,8 @@ def build_network(cnn, spec, comp_meth, mixed_precision="off", network=None, dyn
             cnn.norm(**a)
         elif kind == "dense":
             cnn.dense(**a)
+        elif kind == "lrn":
+            cnn.lrn(**a)
         else:
             raise ValueError(kind)
 
