@@ -439,6 +439,29 @@ def layer_delta(l, network=None):
     return a
 
 
+def set_dropout_seed(seed, network=None):
+    """Dropout masks are a function of (seed, layer, forward-pass counter, position); the default seed is time based."""
+    L = _load()
+    L.cb_set_dropout_seed.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong]
+    L.cb_set_dropout_seed(_net(network), int(seed))
+
+
+def set_inference_drop_mode(drop_mode="AVG_MODEL", network=None):
+    """for forward_batch(is_inference=1); forward() takes drop_mode itself like upstream"""
+    L = _load()
+    L.cb_set_inference_drop_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.cb_set_inference_drop_mode(_net(network), 1 if drop_mode == "MC_MODEL" else 0)
+
+
+def layer_dropout_mask(l, network=None):
+    """0/1 mask layer l used in its last forward pass, same layout as layer_output (a dense layer's bias node reads 0)."""
+    L = _load()
+    L.cb_layer_export_dropout_mask.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    a = _act_array(l, network)
+    L.cb_layer_export_dropout_mask(_net(network), int(l), a.ctypes.data)
+    return a
+
+
 def layer_pool_map(l, network=None):
     L = _load()
     net = _net(network)

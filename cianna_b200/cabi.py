@@ -338,6 +338,41 @@ class LrnLayer:
         return np.ascontiguousarray(s[:, :, :d.c].transpose(2, 0, 1))
 
 
+class DropoutDesc(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int), ("c", ctypes.c_int),
+                ("h", ctypes.c_int), ("w", ctypes.c_int), ("drop_rate", ctypes.c_float), ("stream_id", ctypes.c_uint),
+                ("seed", ctypes.c_ulonglong), ("draw", ctypes.c_ulonglong), ("activ", Activ)]
+
+
+class Dropout:
+    """cb200_dropout_forward / _backward on caller-owned tensors (in place)"""
+
+    def __init__(self, dtype, batch, c, h, w, rate, act=None, seed=1, stream_id=0, draw=1, length=None):
+        L = lib()
+        L.cb200_dropout_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.cb200_dropout_backward.argtypes = [ctypes.c_void_p] * 3
+        self.d = DropoutDesc(dtype, batch, batch if length is None else length, c, h, w, rate, stream_id, seed, draw,
+                             act if act is not None else activ(LINEAR))
+
+    def forward(self, y_buf, scale_only=False):
+        check(lib().cb200_dropout_forward(ctypes.byref(self.d), y_buf.ptr, 1 if scale_only else 0, None))
+        return y_buf
+
+    def backward(self, dy_buf):
+        check(lib().cb200_dropout_backward(ctypes.byref(self.d), dy_buf.ptr, None))
+        return dy_buf
+
+    def mask(self):
+        """the 0/1 mask in the reference layout [C][B][H*W] (the mask function evaluated on a tensor of ones)"""
+        d = self.d
+        ones = upload_act(np.ones((d.c, d.batch, d.h * d.w), np.float32), d.dtype, d.batch, d.c, d.h, d.w)
+        lin = Dropout(d.dtype, d.batch, d.c, d.h, d.w, d.drop_rate, None, d.seed, d.stream_id, d.draw)
+        lin.forward(ones)
+        m = download_act(ones, d.dtype, d.batch, d.c, d.h, d.w)
+        ones.free()
+        return m
+
+
 class YoloDesc(ctypes.Structure):
     _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("length", ctypes.c_int), ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
                 ("nb_box", ctypes.c_int), ("nb_class", ctypes.c_int), ("nb_param", ctypes.c_int), ("max_nb_obj", ctypes.c_int),

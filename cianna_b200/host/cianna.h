@@ -68,6 +68,7 @@ struct layer {
 	float dropout_rate;
 	cb200_activ activ;
 	void *activ_param;     /* yolo_param of a YOLO output layer (own copy, device tables attached), else NULL */
+	cb200_dropout_desc drop; /* dropout_rate > 0.01: mask + activation pass run after the layer's own kernel (cb_dropout_*) */
 	void (*forward)(layer *current);
 	void (*backprop)(layer *current);
 	int nb_params;
@@ -207,6 +208,8 @@ struct network {
 	int stage_slot;
 	const cb200_conv_desc *patch_desc;   /* first conv layer when it consumes patch rows (few input channels), else NULL */
 	yolo_param *y_param;   /* network-level YOLO set-up (set_yolo_params), copied into the YOLO layer at creation */
+	unsigned long long drop_seed;   /* dropout masks are a function of (seed, layer, draw, position): see cb200_dropout_desc */
+	unsigned long long drop_draw;   /* counts the forward passes that drew masks */
 };
 
 extern network *networks[MAX_NETWORKS_NB];
@@ -237,6 +240,14 @@ int lrn_create(network *net, layer *previous, const char *activation, int range,
 void lrn_save(FILE *f, layer *current, int f_bin);
 void lrn_load(network *net, FILE *f, int f_bin);
 int cb_lrn_range(layer *current);
+/* dropout of a layer's output (rate > 0.01 as upstream): set-up at creation, mask/scale + activation after the layer's
+ * forward kernel, mask on the layer's delta before its backward kernels (layers.c) */
+void cb_dropout_setup(layer *current);
+void cb_dropout_forward(layer *current);
+void cb_dropout_backward(layer *current);
+void cb_set_dropout_seed(network *net, unsigned long long seed);
+void cb_set_inference_drop_mode(network *net, int mode);
+void cb_layer_export_dropout_mask(network *net, int l, float *dst);
 void dense_save(FILE *f, layer *current, int f_bin);
 void dense_load(network *net, FILE *f, int f_bin);
 void print_architecture_tex(network *net, const char *path, const char *file_name, int l_size, int l_in_size,

@@ -31,6 +31,7 @@ static void forward_dense_layer(layer *current)
 	if (net->length == 0) return;
 	p->desc.length = net->length;
 	CB_CHECK(cb200_conv_forward(&p->desc, &p->w, dense_input(current), current->output, NULL));
+	cb_dropout_forward(current);
 	if (current->activation_type == SOFTMAX)
 		CB_CHECK(cb200_softmax(current->output, net->dtype, net->batch_size, net->length, current->out_c, 1, 1, NULL));
 }
@@ -40,6 +41,7 @@ static void backward_dense_layer(layer *current)
 	network *net = current->c_network;
 	dense_param *p = (dense_param *)current->param;
 	p->desc.length = net->length;
+	cb_dropout_backward(current);
 	if (current->previous != NULL)
 		CB_CHECK(cb200_conv_backward_data(&p->desc, &p->w, current->delta_o, current->previous->delta_o,
 			&current->previous->activ, current->previous->output, NULL));
@@ -82,7 +84,6 @@ int dense_create(network *net, layer *previous, int nb_neurons, const char *acti
 	current->type = DENSE;
 	current->previous = previous;
 	printf("L:%d - CREATING DENSE LAYER ...\n", net->nb_layers);
-	if (drop_rate > 0.01f) { printf("\nERROR: dropout on dense layers is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
 	current->dropout_rate = drop_rate;
 	load_activ_param(current, activation);
 
@@ -138,6 +139,8 @@ int dense_create(network *net, layer *previous, int nb_neurons, const char *acti
 	p->desc.bias_value = dense_bias_input(current, prev_master);
 	p->desc.activ = current->activ;
 	if (current->activation_type == SOFTMAX) p->desc.activ.type = CB200_LINEAR;
+	if (drop_rate > 0.01f) p->desc.activ.type = CB200_LINEAR;   /* the activation runs in the dropout pass, after the mask */
+	cb_dropout_setup(current);
 	free(prev_master);
 
 	{

@@ -82,6 +82,49 @@ static layer *new_layer(network *net, int type, layer *previous)
 	return current;
 }
 
+/* ------------------------------------------------------------------ dropout (shared by conv / pool / dense layers)
+ * Call order of upstream kept (src/cuda/cuda_conv_layer.cu:399-421,440-447 and the dense / pool twins): mask or scale
+ * the pre-activation output, then activate; mask the delta before anything else in the backward pass. */
+static int drop_on(layer *current) { return current->dropout_rate > 0.01f; }
+static int drop_draws_mask(network *net) { return net->is_inference == 0 || net->inference_drop_mode == MC_MODEL; }
+
+void cb_dropout_setup(layer *current)
+{
+	network *net = current->c_network;
+	cb200_dropout_desc *d = &current->drop;
+	if (!drop_on(current)) return;
+	d->dtype = net->dtype; d->batch = net->batch_size; d->length = net->batch_size;
+	d->c = current->out_c; d->h = current->out_h; d->w = current->out_w;
+	d->drop_rate = current->dropout_rate;
+	d->stream_id = (unsigned int)current->index;
+	d->activ = current->activ;
+	if (current->activation_type == SOFTMAX || current->activation_type == YOLO) d->activ.type = CB200_LINEAR;
+}
+
+void cb_dropout_forward(layer *current)
+{
+	network *net = current->c_network;
+	cb200_dropout_desc *d = &current->drop;
+	if (!drop_on(current)) return;
+	d->length = net->length;
+	if (drop_draws_mask(net)) {
+		d->seed = net->drop_seed;
+		d->draw = ++net->drop_draw;
+		CB_CHECK(cb200_dropout_forward(d, current->output, 0, NULL));
+	} else
+		CB_CHECK(cb200_dropout_forward(d, current->output, 1, NULL));
+}
+
+void cb_dropout_backward(layer *current)
+{
+	if (!drop_on(current) || !drop_draws_mask(current->c_network)) return;
+	CB_CHECK(cb200_dropout_backward(&current->drop, current->delta_o, NULL));
+}
+
+void cb_set_dropout_seed(network *net, unsigned long long seed) { net->drop_seed = seed; }
+/* AVG_MODEL (0) / MC_MODEL (1) for cb_forward(.., is_inference = 1); forward_testset takes it as an argument like upstream */
+void cb_set_inference_drop_mode(network *net, int mode) { net->inference_drop_mode = mode ? MC_MODEL : AVG_MODEL; }
+
 /* ------------------------------------------------------------------ convolution */
 static void forward_conv_layer(layer *current)
 {
@@ -90,6 +133,7 @@ static void forward_conv_layer(layer *current)
 	if (net->length == 0) return;
 	p->desc.length = net->length;
 	CB_CHECK(cb200_conv_forward(&p->desc, &p->w, layer_input(current), current->output, NULL));
+	cb_dropout_forward(current);
 	if (current->activation_type == SOFTMAX)
 		CB_CHECK(cb200_softmax(current->output, net->dtype, net->batch_size, net->length, current->out_c, current->out_h, current->out_w, NULL));
 	else if (current->activation_type == YOLO) {
@@ -104,6 +148,7 @@ static void backward_conv_layer(layer *current)
 	network *net = current->c_network;
 	conv_param *p = (conv_param *)current->param;
 	p->desc.length = net->length;
+	cb_dropout_backward(current);
 	/* the weight gradient only needs what is already enqueued (this layer's delta and, when the following norm layer
 	 * produced it, grad_b): it goes to the low-priority side stream, ordered after that point, BEFORE the data gradient
 	 * is enqueued on the compute stream, so the critical path never waits for it; joined again before the optimizer
@@ -156,7 +201,6 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	}
 	if (f_size[2] != 1 || net->in_dims[2] != 1) { printf("\nERROR: 3D convolutions (depth > 1) are not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
 	if (int_padding[0] != 0 || int_padding[1] != 0) { printf("\nERROR: internal padding (transposed convolution) is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
-	if (drop_rate > 0.01f) { printf("\nERROR: dropout on conv layers is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
 	p->nb_filters = nb_filters;
 	current->dropout_rate = drop_rate;
 
@@ -187,6 +231,8 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	p->desc.activ = current->activ;
 	if (current->activation_type == SOFTMAX || current->activation_type == YOLO)
 		p->desc.activ.type = CB200_LINEAR;   /* softmax / the YOLO head are separate passes on the linear output */
+	if (drop_rate > 0.01f) p->desc.activ.type = CB200_LINEAR;   /* the activation runs in the dropout pass, after the mask */
+	cb_dropout_setup(current);
 	/* first layer on an input with very few channels (RGB / grey): the layout import unrolls the receptive fields into
 	 * patch rows so that the layer runs on the tensor-core GEMM kernels (include/cianna_b200.h, cb200_import_input_patches) */
 	p->desc.input_is_patches = (previous == NULL && cb200_round_channels(pc) < 16) ? 1 : 0;
@@ -391,6 +437,7 @@ static void forward_pool_layer(layer *current)
 			np->gamma, np->beta, np->mean, np->var, np->workspace, NULL));
 	} else
 		CB_CHECK(cb200_pool_forward(&p->desc, layer_input(current), current->output, p->pool_map, NULL));
+	cb_dropout_forward(current);
 	if (current->activation_type == SOFTMAX)
 		CB_CHECK(cb200_softmax(current->output, net->dtype, net->batch_size, net->length, current->out_c, current->out_h, current->out_w, NULL));
 }
@@ -400,6 +447,7 @@ static void backward_pool_layer(layer *current)
 	network *net = current->c_network;
 	pool_param *p = (pool_param *)current->param;
 	p->desc.length = net->length;
+	cb_dropout_backward(current);
 	if (p->fused_norm) return;      /* the norm layer's backward consumes this layer's delta and map directly */
 	if (current->previous != NULL)
 		CB_CHECK(cb200_pool_backward(&p->desc, current->delta_o, p->pool_map, current->previous->delta_o,
@@ -417,7 +465,6 @@ int pool_create(network *net, layer *previous, int *pool_size, int *stride, int 
 	printf("L:%d - CREATING POOL LAYER ...\n", net->nb_layers);
 	load_activ_param(current, activation);
 	current->dropout_rate = drop_rate;
-	if (drop_rate > 0.01f) { printf("\nERROR: dropout on pool layers is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
 	if (previous != NULL && previous->dropout_rate > 0.01f) {
 		printf("\nERROR: A pooling layer cannot be set if dropout is used in the previous layer due to problem with weight/output rescaling.\n");
 		exit(EXIT_FAILURE);
@@ -452,6 +499,8 @@ int pool_create(network *net, layer *previous, int *pool_size, int *stride, int 
 	p->desc.pool_type = p->pool_type == AVG_pool ? CB200_POOL_AVG : CB200_POOL_MAX;
 	p->desc.activ = current->activ;
 	if (current->activation_type == SOFTMAX) p->desc.activ.type = CB200_LINEAR;
+	if (drop_rate > 0.01f) p->desc.activ.type = CB200_LINEAR;   /* the activation runs in the dropout pass, after the mask */
+	cb_dropout_setup(current);
 
 	current->output = dev_alloc(act_bytes(net, current->out_c, current->out_h, current->out_w));
 	if (!net->inference_only) {
@@ -583,8 +632,8 @@ int norm_create(network *net, layer *previous, const char *norm_type, const char
 	if (previous->type == NORM || previous->type == LRN) { printf("\nERROR: stacking two normalization layers is not allowed.\n"); exit(EXIT_FAILURE); }
 
 	p = (norm_param *)calloc(1, sizeof(norm_param));
-	if (previous->type == CONV && !((conv_param *)previous->param)->desc.input_is_patches)
-		((conv_param *)previous->param)->bias_grad_from_next = 1;
+	if (previous->type == CONV && !((conv_param *)previous->param)->desc.input_is_patches && !drop_on(previous))
+		((conv_param *)previous->param)->bias_grad_from_next = 1;   /* (with dropout the conv masks its delta first) */
 	p->group_size = group_size; p->set_off = set_off;
 	p->n_dim = previous->out_c; p->dim_offset = previous->out_h * previous->out_w;
 	p->nb_group = p->n_dim % group_size == 0 ? p->n_dim / group_size : p->n_dim / group_size + 1;

@@ -76,6 +76,8 @@ void init_network(int network_number, int u_input_dim[4], int u_output_dim, floa
 	net->adv_size = adv_size <= 0 ? 30 : adv_size;
 	net->TC_scale_factor = 1.0f;
 	net->dp_world = 1;
+	/* time-seeded like upstream's generators (src/auxil.c:164, src/cuda/cuda_main.cu:1051-1052); cb_set_dropout_seed makes runs repeatable */
+	net->drop_seed = (unsigned long long)time(NULL) * 0x9E3779B97F4A7C15ULL + (unsigned long long)network_number;
 	net->length = net->batch_size;
 	net->train_buf.localization = NO_LOC; net->test_buf.localization = NO_LOC; net->valid_buf.localization = NO_LOC;
 	/* empty YOLO set-up (src/auxil.c:261-295); set_yolo_params fills it before the YOLO layer is created */
@@ -391,6 +393,7 @@ void cb_dp_init(network *net, const void *id128, int rank, int world)
 {
 	CB_CHECK(cb200_dp_init(id128, rank, world));
 	net->dp_world = world;
+	net->drop_seed += 0xD1B54A32D192ED03ULL * (unsigned long long)(rank + 1);   /* each rank draws its own dropout masks */
 }
 
 /* ------------------------------------------------------------------ training loop */
@@ -872,6 +875,29 @@ static void export_maybe_fused(network *net, int l, float *dst, int want_delta)
 
 void cb_layer_export_output(network *net, int l, float *dst) { export_maybe_fused(net, l, dst, 0); }
 void cb_layer_export_delta(network *net, int l, float *dst) { export_maybe_fused(net, l, dst, 1); }
+
+/* the 0/1 dropout mask layer l used in its last forward pass, in the layout of cb_layer_export_output (parity tests):
+ * masks are never stored, so this re-evaluates the layer's mask function on a tensor of ones */
+void cb_layer_export_dropout_mask(network *net, int l, float *dst)
+{
+	layer *cur = net->net_layers[l];
+	size_t count = (size_t)net->batch_size * cur->out_h * cur->out_w * cb200_round_channels(cur->out_c), i;
+	size_t es = cb200_dtype_size(net->dtype);
+	void *host = malloc(count * es), *tmp = NULL;
+	cb200_dropout_desc d = cur->drop;
+	if (!(cur->dropout_rate > 0.01f)) { printf("ERROR: layer %d has no dropout\n", l); exit(EXIT_FAILURE); }
+	for (i = 0; i < count; i++) {
+		if (es == 4) ((float *)host)[i] = 1.0f;
+		else ((uint16_t *)host)[i] = net->dtype == CB200_FP16 ? 0x3C00 : 0x3F80;
+	}
+	CB_CHECK(cb200_malloc(&tmp, count * es));
+	CB_CHECK(cb200_h2d(tmp, host, count * es, NULL));
+	d.activ.type = CB200_LINEAR; d.length = net->batch_size;
+	CB_CHECK(cb200_dropout_forward(&d, tmp, 0, NULL));
+	export_act(net, cur, tmp, dst);
+	cb200_free(tmp);
+	free(host);
+}
 
 void cb_layer_export_pool_map(network *net, int l, int *dst)
 {

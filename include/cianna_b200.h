@@ -329,6 +329,29 @@ int cb200_lrn_forward(const cb200_lrn_desc* d, const void* x, void* y, float* lo
 int cb200_lrn_backward(const cb200_lrn_desc* d, const void* x, const void* y, const void* dy, void* dx,
                        const float* local_scale, const cb200_activ* prev_activ, const void* prev_out, void* stream);
 
+/* ------------------------------------------------------------------ dropout (conv / pool / dense outputs) */
+/* Replaces cuda_dropout_apply_{conv,dense,pool} / cuda_dropout_scale_* and the cuRAND mask tensors they read
+ * (src/cuda/cuda_conv_layer.cu:131-163,399-420,440-447; cuda_dense_layer.cu:78-112,375-411; cuda_pool_layer.cu:280-312,
+ * 472-508).  Same arithmetic: the PRE-activation output is multiplied by a 0/1 mask (kept when a uniform draw >=
+ * drop_rate, no rescale while training) or, at inference in AVG_MODEL, by (1 - drop_rate); then the layer's activation
+ * runs; the backward pass multiplies the layer's delta by the same mask.  The mask is not stored: it is a function of
+ * (seed, stream_id, draw, element position) that both passes evaluate, so the layer that produced `y` must have run
+ * with a LINEAR epilogue and `activ` is applied here, in the same pass.  A dense layer is c = nb_neurons, h = w = 1
+ * (its bias node is not part of the tensor, so it is "always kept" as upstream requires). */
+typedef struct {
+	int dtype;
+	int batch, length;
+	int c, h, w;
+	float drop_rate;
+	unsigned int stream_id;        /* which layer: decorrelates the layers of one network */
+	unsigned long long seed;       /* per network (and per data-parallel rank) */
+	unsigned long long draw;       /* which forward pass: the backward pass reuses the value of its forward pass */
+	cb200_activ activ;             /* applied after the mask / scale in the forward call */
+} cb200_dropout_desc;
+/* y (tensor in internal layout [B][h][w][Cp]) is updated in place. scale_only != 0: the AVG_MODEL inference branch. */
+int cb200_dropout_forward(const cb200_dropout_desc* d, void* y, int scale_only, void* stream);
+int cb200_dropout_backward(const cb200_dropout_desc* d, void* dy, void* stream);
+
 /* ------------------------------------------------------------------ output layer: softmax / losses */
 /* All three take the last layer's tensor in internal layout [B][h][w][Cp] and the target batch in the
  * reference's target layout [B][c*h*w] (per sample c-major, src/cuda/cuda_activ_functions.cu:114-194),

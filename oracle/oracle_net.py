@@ -64,15 +64,31 @@ class OracleNet:
                 c, h, w = n, 1, 1
             else:
                 raise ValueError(kind)
+            # dropout (conv / pool / dense): active above 0.01 as upstream; the 0/1 mask of a training pass is GIVEN
+            # (L["mask"], layout of the layer's output) because it is a random draw on either side
+            L["drop"] = float(a.get("drop_rate", 0.0)) if kind != "norm" else 0.0
             L.update(out_c=c, out_h=h, out_w=w)
             self.layers.append(L)
             prev_kind = kind
 
     # ------------------------------------------------------------------
-    def forward(self, x, length=None):
+    def _dropout(self, L, pre):
+        """src/naiv/naiv_pool_layer.c:320-356 and the conv / dense twins: the PRE-activation output times the mask
+        (training, MC_MODEL inference) or times (1 - rate) (AVG_MODEL inference; a dense layer's bias node is left alone)"""
+        if L["drop"] <= 0.01:
+            return pre
+        if self.inference:
+            out = (pre * np.float32(1.0 - L["drop"])).astype(np.float32)
+            if L["kind"] == "dense":
+                out[:, -1] = pre[:, -1]
+            return out
+        return (pre * L["mask"]).astype(np.float32)
+
+    def forward(self, x, length=None, inference=False):
         B = self.B
         length = B if length is None else length
         self.length = length
+        self.inference = inference
         cur = x
         for L in self.layers:
             first = L["idx"] == 0
@@ -80,11 +96,11 @@ class OracleNet:
             if L["kind"] == "conv":
                 pre, col = co.conv_forward(cur, L["weights"], first, B, L["in_c"], L["in_h"], L["in_w"], L["k"], L["stride"], L["pad"], L["bias"])
                 L["col"] = col
-                cur = self._activate(L, pre, length)
+                cur = self._activate(L, self._dropout(L, pre), length)
             elif L["kind"] == "pool":
                 out, pmap = co.pool_forward(cur, B, L["in_c"], L["in_h"], L["in_w"], L["p"], L["stride"], L["pad"], L["type"])
                 L["map"] = pmap
-                cur = self._activate(L, out, length)
+                cur = self._activate(L, self._dropout(L, out), length)
             elif L["kind"] == "norm":
                 cur, L["mean"], L["var"] = co.group_norm_forward(cur, L["gamma"], L["beta"], L["gs"], L["set_off"], length)
             elif L["kind"] == "dense":
@@ -95,7 +111,7 @@ class OracleNet:
                 else:
                     flat = co.flatten_for_dense(cur, L["bias"])
                 L["flat"] = flat
-                pre = co.dense_forward(flat, L["weights"])
+                pre = self._dropout(L, co.dense_forward(flat, L["weights"]))
                 if L["act"] == "RELU":
                     cur = co.relu_forward_dense(pre, length)
                 elif L["act"] == "SMAX":
@@ -133,6 +149,8 @@ class OracleNet:
         else:
             delta = co.output_delta_conv(last["output"], target, self.length)
         for L in reversed(self.layers):
+            if L["drop"] > 0.01:      # the layer's delta is masked in place before anything reads it
+                delta = (delta * L["mask"]).astype(np.float32)
             L["delta"] = delta
             first = L["idx"] == 0
             prev = self.layers[L["idx"] - 1] if not first else None

@@ -155,6 +155,11 @@ class RefNet:
     def pool_map(self, l):
         return self._array(l, 4, self.out_shape(l), np.int32).copy()
 
+    def dropout_mask(self, l):
+        """0/1 mask of the last forward pass that drew one (layout of output(l)); None without dropout"""
+        a = self._array(l, 16, self.out_shape(l))
+        return None if a is None else a.copy()
+
     def norm_view(self, l, what):
         g = self.geom(l)
         names = {"gamma": 5, "beta": 6, "mean": 7, "var": 8, "d_gamma": 9, "d_beta": 10, "gamma_update": 11, "beta_update": 12}

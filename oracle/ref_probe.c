@@ -59,7 +59,8 @@ void probe_layer_geom(int net_id, int l, int *out)
 
 /* what: 0 output, 1 delta_o, 2 weights (filters / dense weights), 3 update (momentum buffer),
  * 4 pool_map (int*), 5 gamma, 6 beta, 7 mean, 8 var, 9 d_gamma, 10 d_beta,
- * 11 gamma_update, 12 beta_update, 13 im2col_input, 14 lrn local_scale, 15 input */
+ * 11 gamma_update, 12 beta_update, 13 im2col_input, 14 lrn local_scale, 15 input,
+ * 16 dropout_mask (conv / dense / pool: the 0/1 floats of the last forward pass that drew one) */
 void* probe_ptr(int net_id, int l, int what)
 {
 	layer *cur = networks[net_id]->net_layers[l];
@@ -73,15 +74,18 @@ void* probe_ptr(int net_id, int l, int what)
 			if(what == 2) return p->filters;
 			if(what == 3) return p->update;
 			if(what == 13) return p->im2col_input;
+			if(what == 16) return cur->dropout_rate > 0.01f ? p->dropout_mask : NULL;	/* (not allocated otherwise) */
 			break; }
 		case DENSE: {
 			dense_param *p = (dense_param*) cur->param;
 			if(what == 2) return p->weights;
 			if(what == 3) return p->update;
+			if(what == 16) return cur->dropout_rate > 0.01f ? p->dropout_mask : NULL;	/* (not allocated otherwise) */
 			break; }
 		case POOL: {
 			pool_param *p = (pool_param*) cur->param;
 			if(what == 4) return p->pool_map;
+			if(what == 16) return cur->dropout_rate > 0.01f ? p->dropout_mask : NULL;	/* (not allocated otherwise) */
 			break; }
 		case NORM: {
 			norm_param *p = (norm_param*) cur->param;

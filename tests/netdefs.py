@@ -40,6 +40,20 @@ def tc_darknet(batch=8, size=16, classes=16):
     ])
 
 
+def dropout_net(batch=6, size=12):
+    """dropout on every layer kind that has it upstream (conv: examples/SKAO_SDC1/train_network.py:136, dense:
+    examples/MNIST/mnist_train.py:71-72, pool), rates on and off 1/65536 steps"""
+    return dict(in_dim=(size, size), in_ch=2, out_dim=5, bias=0.1, batch=batch, layers=[
+        ("conv", dict(f_size=(3, 3), nb_filters=12, padding=(1, 1), activation="RELU", drop_rate=0.25)),
+        ("conv", dict(f_size=(3, 3), nb_filters=16, padding=(1, 1), activation="RELU")),
+        ("pool", dict(p_size=(2, 2), p_type="MAX", drop_rate=0.3)),
+        ("conv", dict(f_size=(1, 1), nb_filters=8, activation="LIN", drop_rate=0.1)),
+        ("dense", dict(nb_neurons=24, strict_size=1, activation="RELU", drop_rate=0.5)),
+        ("dense", dict(nb_neurons=12, strict_size=1, activation="RELU", drop_rate=0.2)),
+        ("dense", dict(nb_neurons=5, strict_size=1, activation="SMAX")),
+    ])
+
+
 def yolo_head(name, batch=3, grid=6, cell=8):
     """One-layer network whose only layer is the YOLO head (conv with filter = stride = cell): the kernel-level parity
     cases of tests/test_gpu_yolo.py and of the golden fixtures tests/golden/yolo_<name>.npz.  Every case forces the
