@@ -153,6 +153,40 @@ def delete_dataset(dataset, network=None, silent=0):
     L.free_dataset(L.cb_net_dataset(_net(network), _s(dataset)))
 
 
+def shuffle_dataset(dataset="TRAIN", network=None):
+    """the permutation train() applies every shuffle_every epochs, on demand"""
+    L = _load()
+    L.shuffle_dataset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.shuffle_dataset(_net(network), L.cb_net_dataset(_net(network), _s(dataset)))
+
+
+def dataset_rows(dataset, indices, network=None, device=False):
+    """(inputs [n][input_dim+1], targets [n][output_dim]) of the given samples as stored (FP32 view of the storage type)"""
+    L = _load()
+    net = _net(network)
+    L.cb_dataset_read_row.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.cb_net_io_dims.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    dims = (ctypes.c_longlong * 3)()
+    L.cb_net_io_dims(net, dims)
+    in_dim, out_dim, dtype = int(dims[0]), int(dims[1]), int(dims[2])
+    np_t = np.float32 if dtype == 0 else np.uint16
+    data = L.cb_net_dataset(net, _s(dataset))
+    xs = np.zeros((len(indices), in_dim + 1), np_t)
+    ts = np.zeros((len(indices), max(out_dim, 1)), np_t)
+    for k, i in enumerate(indices):
+        L.cb_dataset_read_row(net, data, int(i), 0, int(device), xs[k].ctypes.data)
+        if out_dim:
+            L.cb_dataset_read_row(net, data, int(i), 1, int(device), ts[k].ctypes.data)
+
+    def widen(a):
+        if dtype == 0:
+            return a
+        if dtype == 1:
+            return a.view(np.float16).astype(np.float32)
+        return (a.astype(np.uint32) << 16).view(np.float32)
+    return widen(xs), widen(ts[:, :out_dim])
+
+
 def swap_data_buffers(dataset, network=None):
     _load().cb_swap_data_buffers(_net(network), _s(dataset))
 

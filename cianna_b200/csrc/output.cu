@@ -48,7 +48,7 @@ __global__ void softmax_kernel(T* __restrict__ y, int length, int c, int cp, int
 
 template <typename T>
 __global__ void output_delta_kernel(T* __restrict__ delta, const T* __restrict__ y, const T* __restrict__ target,
-                                    int batch, int length, int c, int cp, int hw, float scale) {
+                                    int batch, int length, int c, int cp, int hw, float scale, cb200_activ act) {
 	const size_t total = (size_t)batch * hw * cp;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
 		const int ch = (int)(i % cp);
@@ -56,7 +56,12 @@ __global__ void output_delta_kernel(T* __restrict__ delta, const T* __restrict__
 		const int p = (int)(pix % hw);
 		const int b = (int)(pix / hw);
 		float v = 0.0f;
-		if (ch < c && b < length) v = (to_f32<T>(y[i]) - to_f32<T>(target[((size_t)b * c + ch) * hw + p])) * scale;
+		if (ch < c && b < length) {
+			const float o = to_f32<T>(y[i]);
+			v = (o - to_f32<T>(target[((size_t)b * c + ch) * hw + p])) * scale;
+			// RELU / LOGI output layers: upstream stores (o - t) * S, then runs the layer's own derivative kernel on it
+			if (act.type != CB200_LINEAR) v = activ_deriv_mul(act, to_f32<T>(from_f32<T>(v)), o);
+		}
 		delta[i] = from_f32<T>(v);
 	}
 }
@@ -95,14 +100,20 @@ int cb200_softmax(void* y, int dtype, int batch, int length, int c, int h, int w
 	return CB200_OK;
 }
 
-int cb200_output_delta(void* delta, const void* y, const void* target, int dtype, int batch, int length,
-                       int c, int h, int w, float scale, void* s) {
+int cb200_output_delta_activ(void* delta, const void* y, const void* target, int dtype, int batch, int length,
+                             int c, int h, int w, float scale, const cb200_activ* activ, void* s) {
 	CB_REQUIRE_DEVICE();
 	long long total = (long long)batch * h * w * round8(c);
+	cb200_activ act; act.type = CB200_LINEAR; act.leak = 0; act.saturation = 0; act.beta = 0;
+	if (activ != nullptr && (activ->type == CB200_RELU || activ->type == CB200_LOGISTIC)) act = *activ;
 	CB_DISPATCH_DTYPE(dtype, T, (output_delta_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
-		(T*)delta, (const T*)y, (const T*)target, batch, length, c, round8(c), h * w, scale)));
+		(T*)delta, (const T*)y, (const T*)target, batch, length, c, round8(c), h * w, scale, act)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
+}
+int cb200_output_delta(void* delta, const void* y, const void* target, int dtype, int batch, int length,
+                       int c, int h, int w, float scale, void* s) {
+	return cb200_output_delta_activ(delta, y, target, dtype, batch, length, c, h, w, scale, nullptr, s);
 }
 
 int cb200_output_loss(float* loss, const void* y, const void* target, int dtype, int batch, int length,

@@ -282,6 +282,9 @@ void init_weights(float *tab, int dim_in, int dim_out, const char *init_fct, flo
  * Dataset.cont_copy (src/cuda/cuda_main.cu:355-371) */
 void dataset_set_sample(network *net, Dataset *data, int index, const float *input, const float *target);
 void dataset_upload(network *net, Dataset *data);   /* dynamic_load == 0: make device-resident copies */
+void shuffle_dataset(network *net, Dataset *data);  /* what train_network does every shuffle_every epochs */
+void cb_dataset_read_row(network *net, Dataset *data, int index, int which, int from_device, void *dst);
+void cb_net_io_dims(network *net, long long *out3);   /* input_dim, output_dim, cb200 dtype */
 /* data-parallel set-up: call on every rank after init_network, before training */
 void cb_dp_unique_id(void *id128);
 void cb_dp_init(network *net, const void *id128, int rank, int world);

@@ -170,6 +170,61 @@ void dataset_upload(network *net, Dataset *data)
 	data->localization = DEVICE;
 }
 
+/* Uniform random permutation of the samples of a data set, across its batches (Fisher-Yates on whole rows, input and
+ * target together).  Same effect as upstream's cuda_host_only_shuffle / cuda_host_shuffle / cuda_shuffle
+ * (src/cuda/cuda_main.cu:590-768, called from src/auxil.c:1768-1789); rows are moved as bytes, so one routine serves
+ * every storage type.  Device-resident sets (dynamic_load == 0) are refreshed from the shuffled host copy. */
+static unsigned char *sample_row(void **batches, int batch_size, size_t row_bytes, int sample)
+{
+	return (unsigned char *)batches[sample / batch_size] + (size_t)(sample % batch_size) * row_bytes;
+}
+
+static void swap_rows(unsigned char *a, unsigned char *b, unsigned char *tmp, size_t bytes)
+{
+	memcpy(tmp, a, bytes); memcpy(a, b, bytes); memcpy(b, tmp, bytes);
+}
+
+void shuffle_dataset(network *net, Dataset *data)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t in_row = (net->input_dim + 1) * es, out_row = (size_t)net->output_dim * es;
+	unsigned char *tmp = (unsigned char *)malloc(in_row > out_row ? in_row : out_row);
+	int i;
+	for (i = 0; i < data->size - 1; i++) {
+		int j = i + (int)((rand() / ((double)RAND_MAX + 1.0)) * (double)(data->size - i));
+		if (j == i) continue;
+		swap_rows(sample_row(data->input, net->batch_size, in_row, i), sample_row(data->input, net->batch_size, in_row, j), tmp, in_row);
+		if (out_row)
+			swap_rows(sample_row(data->target, net->batch_size, out_row, i), sample_row(data->target, net->batch_size, out_row, j), tmp, out_row);
+	}
+	free(tmp);
+	if (data->input_device != NULL) {
+		for (i = 0; i < data->nb_batch; i++) {
+			CB_CHECK(cb200_h2d(data->input_device[i], data->input[i], (size_t)net->batch_size * in_row, NULL));
+			if (out_row) CB_CHECK(cb200_h2d(data->target_device[i], data->target[i], (size_t)net->batch_size * out_row, NULL));
+		}
+		CB_CHECK(cb200_stream_sync(NULL));
+	}
+}
+
+void cb_net_io_dims(network *net, long long *out3) { out3[0] = (long long)net->input_dim; out3[1] = net->output_dim; out3[2] = net->dtype; }
+
+/* raw bytes (storage type of the network) of one sample's input (which = 0, input_dim + 1 values) or target row
+ * (which = 1); from_device != 0 reads the device-resident copy instead of the host one (tests) */
+void cb_dataset_read_row(network *net, Dataset *data, int index, int which, int from_device, void *dst)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t row = which == 0 ? (net->input_dim + 1) * es : (size_t)net->output_dim * es;
+	int b = index / net->batch_size, j = index % net->batch_size;
+	if (index < 0 || index >= data->size) { printf("ERROR: cb_dataset_read_row index out of range\n"); exit(EXIT_FAILURE); }
+	if (from_device) {
+		if (data->input_device == NULL) { printf("ERROR: the data set has no device-resident copy\n"); exit(EXIT_FAILURE); }
+		CB_CHECK(cb200_d2h(dst, (char *)(which == 0 ? data->input_device[b] : data->target_device[b]) + (size_t)j * row, row, NULL));
+		CB_CHECK(cb200_stream_sync(NULL));
+	} else
+		memcpy(dst, (char *)(which == 0 ? data->input[b] : data->target[b]) + (size_t)j * row, row);
+}
+
 /* ------------------------------------------------------------------ training preparation */
 static void prepare_training(network *net)
 {
@@ -299,12 +354,9 @@ static void output_deriv_error(network *net, const void *target_dev)
 		return;
 	}
 	/* quadratic (LIN / RELU / LOGI outputs) and cross-entropy (SMAX) share delta = (o - t) * S upstream */
-	CB_CHECK(cb200_output_delta(last->delta_o, last->output, target_dev, net->dtype, net->batch_size, net->length,
-		last->out_c, last->out_h, last->out_w, net->TC_scale_factor, NULL));
-	if (last->activation_type == RELU || last->activation_type == LOGISTIC) {
-		printf("\nERROR: RELU / LOGI output layers are not supported by the B200 core yet (use LIN or SMAX).\n");
-		exit(EXIT_FAILURE);
-	}
+	/* ... and RELU / LOGI outputs then take their own derivative (src/cuda/cuda_activ_functions.cu:2221-2233,2273-2285) */
+	CB_CHECK(cb200_output_delta_activ(last->delta_o, last->output, target_dev, net->dtype, net->batch_size, net->length,
+		last->out_c, last->out_h, last->out_w, net->TC_scale_factor, &last->activ, NULL));
 }
 
 static void output_error(network *net, const void *target_dev)
@@ -553,8 +605,12 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		float lr = u_end_learning_rate + (u_begin_learning_rate - u_end_learning_rate) * expf(-net->decay * net->iter);
 		if (silent < 1) printf("\n");
 		net->iter++;
-		if (shuffle_every > 0 && (net->iter + 1) % shuffle_every == 0 && net->batch_param != SGD && silent < 1)
-			printf(" (note) dataset shuffling is left to the caller in this build\n");
+		if (shuffle_every > 0 && (net->iter + 1) % shuffle_every == 0 && net->batch_param != SGD) {
+			/* no copy of the previous epoch may still be reading the host batches */
+			if (net->copy_stream != NULL) CB_CHECK(cb200_stream_sync(net->copy_stream));
+			CB_CHECK(cb200_stream_sync(NULL));
+			shuffle_dataset(net, &net->train);
+		}
 		set_hyper(net, lr, net->momentum, net->weight_decay);
 		stage_invalidate(net);
 		net->is_inference = 0;

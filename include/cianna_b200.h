@@ -363,6 +363,12 @@ int cb200_softmax(void* y, int dtype, int batch, int length, int c, int h, int w
  * Replaces quadratic/cross_entropy_deriv_output_error (cuda_activ_functions.cu:114-155,384-425). */
 int cb200_output_delta(void* delta, const void* y, const void* target, int dtype,
                        int batch, int length, int c, int h, int w, float scale, void* stream);
+/* the same for an output layer with a RELU / LOGISTIC activation: upstream stores (y - t) * scale and then runs the
+ * layer's own derivative kernel on it (cuda_ReLU_deriv_output_error / cuda_logistic_deriv_output_error,
+ * cuda_activ_functions.cu:2221-2233,2273-2285); one pass here, same intermediate rounding. activ NULL / LINEAR /
+ * SOFTMAX = cb200_output_delta. */
+int cb200_output_delta_activ(void* delta, const void* y, const void* target, int dtype, int batch, int length,
+                             int c, int h, int w, float scale, const cb200_activ* activ, void* stream);
 /* per-sample loss summed over the sample's outputs -> loss[batch] (FP32), kind 0: 0.5*(y-t)^2,
  * kind 1: -t*log(max(y,1e-6)).  Replaces *_output_error kernels + the host-side summation of the
  * whole per-element tensor (cuda_activ_functions.cu:157-194,427-470; src/auxil.c:1851-1917). */

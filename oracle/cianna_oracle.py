@@ -304,3 +304,47 @@ def output_delta_dense(out, target, length):
     d[:, :-1] = out[:, :-1] - target
     d[length:] = 0
     return d
+
+
+def quadratic_dense(out, target, length):
+    """per-element 0.5*(o-t)^2 of a dense output layer, bias node and tail samples 0 (src/activ_functions.c:534-546)."""
+    e = np.zeros_like(out, dtype=np.float32)
+    e[:, :-1] = 0.5 * (out[:, :-1] - target) ** 2
+    e[length:] = 0
+    return e
+
+
+# ------------------------------------------------------------------ logistic activation
+def _logistic(x, beta, saturation):
+    """src/activ_functions.c:636-639: the EXPONENT's argument -beta*x is clamped from above, all in float"""
+    t = np.minimum(-np.float32(beta) * x.astype(np.float32), np.float32(saturation)).astype(np.float32)
+    return (np.float32(1.0) / (np.float32(1.0) + np.exp(t, dtype=np.float32))).astype(np.float32)
+
+
+def logistic_forward(x, length, beta=1.0, saturation=6.0):
+    """conv layout [C][B][A] (src/activ_functions.c:644-655); defaults of set_logistic_activ (:593-594)."""
+    y = _logistic(x, beta, saturation)
+    y[:, length:, :] = 0
+    return y
+
+
+def logistic_forward_dense(x, length, beta=1.0, saturation=6.0):
+    """dense layout [B][n+1] (src/activ_functions.c:632-643): bias node -> 0"""
+    y = _logistic(x, beta, saturation)
+    y[:, -1] = 0
+    y[length:] = 0
+    return y
+
+
+def logistic_deriv(delta, value, length, beta=1.0):
+    """src/activ_functions.c:668-694: delta *= beta * y * (1 - y) on the activated value"""
+    d = (delta * (np.float32(beta) * value * (1.0 - value.astype(np.float64)))).astype(np.float32)
+    d[:, length:, :] = 0
+    return d
+
+
+def logistic_deriv_dense(delta, value, length, beta=1.0):
+    d = (delta * (np.float32(beta) * value * (1.0 - value.astype(np.float64)))).astype(np.float32)
+    d[:, -1] = 0
+    d[length:] = 0
+    return d

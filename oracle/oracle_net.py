@@ -114,6 +114,8 @@ class OracleNet:
                 pre = self._dropout(L, co.dense_forward(flat, L["weights"]))
                 if L["act"] == "RELU":
                     cur = co.relu_forward_dense(pre, length)
+                elif L["act"] == "LOGI":
+                    cur = co.logistic_forward_dense(pre, length)
                 elif L["act"] == "SMAX":
                     cur = co.softmax_dense(pre, length)
                 else:
@@ -125,6 +127,8 @@ class OracleNet:
     def _activate(L, pre, length):
         if L["act"] == "RELU":
             return co.relu_forward(pre, length)
+        if L["act"] == "LOGI":
+            return co.logistic_forward(pre, length)
         if L["act"] == "SMAX":
             return co.softmax_conv(pre, length)
         return pre
@@ -139,6 +143,10 @@ class OracleNet:
             if L["kind"] == "dense":
                 return co.relu_deriv_dense(delta, value, self.length)
             return co.relu_deriv(delta, value, self.length)
+        if L["act"] == "LOGI":
+            if L["kind"] == "dense":
+                return co.logistic_deriv_dense(delta, L["output"], self.length)
+            return co.logistic_deriv(delta, L["output"], self.length)
         return delta
 
     def backward(self, target, lr, momentum=0.0, weight_decay=0.0):
@@ -148,6 +156,10 @@ class OracleNet:
             delta = co.output_delta_dense(last["output"], target, self.length)
         else:
             delta = co.output_delta_conv(last["output"], target, self.length)
+        if last["act"] in ("RELU", "LOGI"):
+            # quadratic error of a non-linear output layer goes through the layer's own derivative
+            # (ReLU_deriv_output_error / logistic_deriv_output_error, src/activ_functions.c:469-478,697-705)
+            delta = self._deriv(last, delta)
         for L in reversed(self.layers):
             if L["drop"] > 0.01:      # the layer's delta is masked in place before anything reads it
                 delta = (delta * L["mask"]).astype(np.float32)
@@ -183,7 +195,9 @@ class OracleNet:
     def loss(self, target):
         last = self.layers[-1]
         if last["kind"] == "dense":
-            raise NotImplementedError
+            if last["act"] == "SMAX":
+                raise NotImplementedError
+            return co.quadratic_dense(last["output"], target, self.length)
         if last["act"] == "SMAX":
             return co.cross_entropy_conv(last["output"], target, self.length)
         return co.quadratic_conv(last["output"], target, self.length)

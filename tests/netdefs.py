@@ -54,6 +54,26 @@ def dropout_net(batch=6, size=12):
     ])
 
 
+def regression_net(out_act="LIN", head="dense", batch=5, size=10):
+    """quadratic-loss networks (the regression use of upstream, e.g. its 3-D extinction-profile model): logistic hidden
+    layers and a LIN / RELU / LOGI output layer, dense or convolutional"""
+    layers = [
+        ("conv", dict(f_size=(3, 3), nb_filters=8, padding=(1, 1), activation="LOGI")),
+        ("pool", dict(p_size=(2, 2), p_type="AVG")),
+    ]
+    if head == "dense":
+        layers += [("dense", dict(nb_neurons=16, strict_size=1, activation="LOGI")),
+                   ("dense", dict(nb_neurons=6, strict_size=1, activation=out_act))]
+        out_dim = 6
+    else:
+        layers += [("conv", dict(f_size=(3, 3), nb_filters=4, padding=(1, 1), activation=out_act))]
+        out_dim = 4 * (size // 2) ** 2
+    return dict(in_dim=(size, size), in_ch=2, out_dim=out_dim, bias=0.1, batch=batch, layers=layers)
+
+
+REGRESSION_CASES = [("LIN", "dense"), ("RELU", "dense"), ("LOGI", "dense"), ("RELU", "conv"), ("LOGI", "conv")]
+
+
 def yolo_head(name, batch=3, grid=6, cell=8):
     """One-layer network whose only layer is the YOLO head (conv with filter = stride = cell): the kernel-level parity
     cases of tests/test_gpu_yolo.py and of the golden fixtures tests/golden/yolo_<name>.npz.  Every case forces the
