@@ -52,6 +52,14 @@ inline cudaStream_t as_stream(void* s) { return s ? (cudaStream_t)s : g_stream; 
 	}
 
 __host__ __device__ inline int round8(int c) { return (c + 7) & ~7; }
+// A filter that covers its whole (unpadded) input map - a dense layer behind a conv / pool layer.  In the channels-last
+// layout one image of the input is then a single run of f_h*f_w*Cp values in exactly the order of the filter's operand
+// rows, so the layer is a 1x1 convolution over that many "channels"; its data-gradient operand keeps the same order
+// (conv.cu: wbwd_row).
+__host__ __device__ inline bool conv_whole_map(const cb200_conv_desc* d) {
+	return d->out_h == 1 && d->out_w == 1 && d->pad_h == 0 && d->pad_w == 0 && d->f_h == d->in_h && d->f_w == d->in_w &&
+	       d->f_h * d->f_w > 1 && d->input_is_patches == 0;
+}
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

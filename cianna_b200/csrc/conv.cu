@@ -24,19 +24,25 @@ int conv_first_wgrad(const cb200_conv_desc*, const cb200_conv_weights*, const vo
 
 // master [out_c][taps*in_c + 1] (column = c*taps + tap, bias last) -> compute operands.
 // One thread per master element; the same mapping is used by the optimizer below.
+// w_bwd row of input channel c, filter tap `tap`: (c, rotated tap) for the data-gradient correlation, or - for a filter
+// that covers its whole input map (conv_whole_map, common.cuh: dense layers behind conv / pool) - (tap, c), the order of
+// the input tensor itself, so that the layer runs as ONE 1x1 GEMM over f_h*f_w*Cp "channels" in all three passes
+__device__ __forceinline__ size_t wbwd_row(int c, int tap, int taps, int in_cp, int wb_dense) {
+	return wb_dense ? (size_t)tap * in_cp + c : (size_t)c * taps + (taps - 1 - tap);
+}
 template <typename T>
 __device__ __forceinline__ void scatter_weight(float wv, int f, int col, int taps, int in_c, int in_cp, int out_cp,
-                                               T* __restrict__ w_fwd, T* __restrict__ w_bwd, float* __restrict__ bias_w) {
+                                               T* __restrict__ w_fwd, T* __restrict__ w_bwd, float* __restrict__ bias_w, int wb_dense) {
 	if (col == taps * in_c) { bias_w[f] = wv; return; }
 	const int c = col / taps, tap = col - c * taps;
 	w_fwd[((size_t)f * taps + tap) * in_cp + c] = from_f32<T>(wv);
-	w_bwd[((size_t)c * taps + (taps - 1 - tap)) * out_cp + f] = from_f32<T>(wv);
+	w_bwd[wbwd_row(c, tap, taps, in_cp, wb_dense) * out_cp + f] = from_f32<T>(wv);
 }
 
 template <typename T>
 __global__ void conv_prepare_kernel(const float* __restrict__ master, T* __restrict__ w_fwd, T* __restrict__ w_bwd,
                                     float* __restrict__ bias_w, int out_c, int taps, int in_c, int in_cp, int out_cp,
-                                    size_t ms_f, size_t ms_c) {
+                                    size_t ms_f, size_t ms_c, int wb_dense) {
 	// master element (filter f, column col) lives at f*ms_f + col*ms_c:
 	//   conv  layout [out_c][kref]      -> ms_f = kref, ms_c = 1
 	//   dense layout [in_size][n + 1]   -> ms_f = 1,    ms_c = n + 1   (src/dense_layer.c:253-268)
@@ -44,7 +50,7 @@ __global__ void conv_prepare_kernel(const float* __restrict__ master, T* __restr
 	const size_t total = (size_t)out_c * kref;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
 		const int f = (int)(i / kref), col = (int)(i - (size_t)f * kref);
-		scatter_weight<T>(master[f * ms_f + col * ms_c], f, col, taps, in_c, in_cp, out_cp, w_fwd, w_bwd, bias_w);
+		scatter_weight<T>(master[f * ms_f + col * ms_c], f, col, taps, in_c, in_cp, out_cp, w_fwd, w_bwd, bias_w, wb_dense);
 	}
 }
 
@@ -55,7 +61,7 @@ __global__ void conv_update_kernel(float* __restrict__ master, float* __restrict
                                    const float* __restrict__ grad, const float* __restrict__ grad_b,
                                    const float* __restrict__ hyper, float bias_value, int is_pivot,
                                    T* __restrict__ w_fwd, T* __restrict__ w_bwd, float* __restrict__ bias_w,
-                                   int out_c, int taps, int in_c, int in_cp, int out_cp, size_t ms_f, size_t ms_c) {
+                                   int out_c, int taps, int in_c, int in_cp, int out_cp, size_t ms_f, size_t ms_c, int wb_dense) {
 	const int kref = taps * in_c + 1;
 	const size_t total = (size_t)out_c * kref;
 	const float alpha = hyper[0], mom = hyper[1], wdlr = hyper[2], S = hyper[3];
@@ -73,7 +79,7 @@ __global__ void conv_update_kernel(float* __restrict__ master, float* __restrict
 			moment[mi] = m;
 			master[mi] = wv;
 		}
-		scatter_weight<T>(wv, f, col, taps, in_c, in_cp, out_cp, w_fwd, w_bwd, bias_w);
+		scatter_weight<T>(wv, f, col, taps, in_c, in_cp, out_cp, w_fwd, w_bwd, bias_w, wb_dense);
 	}
 }
 
@@ -173,7 +179,7 @@ conv_update_rows_kernel(float* __restrict__ master, float* __restrict__ moment, 
 // w_bwd[c][taps-1-tap][f] = w_fwd[f][tap][c] through a 32x32 shared-memory tile; grid (c tiles, f tiles, taps)
 template <typename T>
 __global__ void __launch_bounds__(256)
-conv_wbwd_transpose_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_bwd, int out_c, int out_cp, int taps, int in_c, int in_cp) {
+conv_wbwd_transpose_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_bwd, int out_c, int out_cp, int taps, int in_c, int in_cp, int wb_dense) {
 	__shared__ T tile[32][33];
 	const int tap = blockIdx.z, c0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
 	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -186,7 +192,7 @@ conv_wbwd_transpose_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_bwd, i
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		const int c = c0 + ty + 8 * k, f = f0 + tx;
-		if (c < in_c && f < out_cp) w_bwd[((size_t)c * taps + (taps - 1 - tap)) * out_cp + f] = tile[tx][ty + 8 * k];
+		if (c < in_c && f < out_cp) w_bwd[wbwd_row(c, tap, taps, in_cp, wb_dense) * out_cp + f] = tile[tx][ty + 8 * k];
 	}
 }
 
@@ -250,7 +256,10 @@ size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d) {
 	if (d->input_is_patches) return (size_t)d->out_c * cb200_patch_width(d->in_c, d->f_h, d->f_w);
 	return (size_t)d->out_c * d->f_h * d->f_w * round8(d->in_c);
 }
-size_t cb200_conv_wbwd_elems(const cb200_conv_desc* d) { return (size_t)d->in_c * d->f_h * d->f_w * round8(d->out_c); }
+size_t cb200_conv_wbwd_elems(const cb200_conv_desc* d) {
+	// (whole-map filters keep one row per element of the padded input tensor, see wbwd_row)
+	return (size_t)(conv_whole_map(d) ? round8(d->in_c) : d->in_c) * d->f_h * d->f_w * round8(d->out_c);
+}
 size_t cb200_conv_grad_elems(const cb200_conv_desc* d) { return cb200_conv_wfwd_elems(d); }
 size_t cb200_conv_master_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * ((size_t)d->f_h * d->f_w * d->in_c + 1); }
 
@@ -271,7 +280,8 @@ static int prepare_weights_impl(const cb200_conv_desc* d, const cb200_conv_weigh
 	const int taps = d->f_h * d->f_w;
 	long long total = (long long)cb200_conv_master_elems(d);
 	CB_DISPATCH_DTYPE(d->dtype, T, (conv_prepare_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
-		w->master, (T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c)));
+		w->master, (T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c,
+		conv_whole_map(d) ? 1 : 0)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }
@@ -387,13 +397,14 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 		CB_LAUNCH_CHECK();
 		dim3 tgrid((unsigned)ceil_div(d->in_c, 32), (unsigned)ceil_div(out_cp, 32), (unsigned)taps);
 		CB_DISPATCH_DTYPE(d->dtype, T, (conv_wbwd_transpose_kernel<T><<<tgrid, 256, 0, as_stream(s)>>>(
-			(const T*)w->w_fwd, (T*)w->w_bwd, d->out_c, out_cp, taps, d->in_c, in_cp)));
+			(const T*)w->w_fwd, (T*)w->w_bwd, d->out_c, out_cp, taps, d->in_c, in_cp, conv_whole_map(d) ? 1 : 0)));
 		CB_LAUNCH_CHECK();
 		return CB200_OK;
 	}
 	CB_DISPATCH_DTYPE(d->dtype, T, (conv_update_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
 		w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, is_pivot,
-		(T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c)));
+		(T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c,
+		conv_whole_map(d) ? 1 : 0)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }

@@ -23,7 +23,7 @@ namespace cb200 {
 
 using namespace ptx;
 
-int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n, int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw);
+int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n, int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw, int pix_stride);
 int make_w_map(CUtensorMap* m, const void* base, int dtype, int cp, int taps, int rows, int bc, int brow, CUtensorMapSwizzle sw);
 void choose_rect(int W, int H, int N, int npix, int& tw, int& th, int& tn);
 CUtensorMapSwizzle swizzle_for(int bk);
@@ -511,7 +511,7 @@ int conv_first_wgrad(const cb200_conv_desc* d, const cb200_conv_weights* w, cons
 	p.grad = w->grad;
 	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, kp, 1, 1);
 	CUtensorMap mdy;
-	int rc = make_act_map(&mdy, dy, d->dtype, p.n_pad, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B);
+	int rc = make_act_map(&mdy, dy, d->dtype, p.n_pad, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B, 1);
 	if (rc) return rc;
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
 	p.tiles_per_cta = ceil_div(p.num_tiles, grid);

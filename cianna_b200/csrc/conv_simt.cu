@@ -18,6 +18,7 @@ struct ConvGeom {
 	int in_c, in_cp, in_h, in_w;
 	int out_c, out_cp, out_h, out_w;
 	int f_h, f_w, s_h, s_w, p_h, p_w;
+	int wb_dense;                // row order of w_bwd (conv_whole_map)
 	float bias_value;
 	cb200_activ activ;
 };
@@ -29,6 +30,7 @@ static ConvGeom make_geom(const cb200_conv_desc* d) {
 	g.out_c = d->out_c; g.out_cp = round8(d->out_c); g.out_h = d->out_h; g.out_w = d->out_w;
 	g.f_h = d->f_h; g.f_w = d->f_w; g.s_h = d->stride_h; g.s_w = d->stride_w; g.p_h = d->pad_h; g.p_w = d->pad_w;
 	g.bias_value = d->bias_value; g.activ = d->activ;
+	g.wb_dense = conv_whole_map(d) ? 1 : 0;
 	return g;
 }
 
@@ -156,7 +158,9 @@ conv_dgrad_simt_kernel(const T* __restrict__ dy, const T* __restrict__ wb, T* __
 				}
 			}
 			if (ln_ok) {
-				const T* p = wb + (long long)ln * K + k;
+				// rows (c, rotated tap), or (tap, c) for a whole-map filter (conv.cu: wbwd_row)
+				const T* p = g.wb_dense ? wb + ((long long)(g.f_h * g.f_w - 1 - tapr) * g.in_cp + ln) * g.out_cp + f
+				                        : wb + (long long)ln * K + k;
 #pragma unroll
 				for (int i = 0; i < 4; i++) bv[i] = to_f32<T>(p[i]);
 			}

@@ -51,14 +51,18 @@ static int load_encode() {
 }
 
 // rank-4 map over act[n][y][x][c] (c fastest).  box = (bc, bw, bh, bn)
+// pix_stride > 1 (strided convolutions): the box still DELIVERS bw x bh pixels, taken every pix_stride-th pixel of the
+// tensor in x and y (TMA traversal stride: a box dimension of N * stride loads N elements)
 int make_act_map(CUtensorMap* m, const void* base, int dtype, int cp, int w, int h, int n,
-                        int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw) {
+                        int bc, int bw, int bh, int bn, CUtensorMapSwizzle sw, int pix_stride) {
 	int rc = load_encode(); if (rc) return rc;
 	const cuuint64_t es = 2;
+	const int s = pix_stride < 1 ? 1 : pix_stride;
+	if (bw * s > 256 || bh * s > 256) { set_error("make_act_map: box %dx%d with pixel stride %d exceeds the TMA box limit", bw, bh, s); return CB200_ERR_UNSUPPORTED; }
 	cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
 	cuuint64_t strides[3] = {(cuuint64_t)cp * es, (cuuint64_t)w * cp * es, (cuuint64_t)h * w * cp * es};
-	cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-	cuuint32_t estr[4] = {1, 1, 1, 1};
+	cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)(bw * s), (cuuint32_t)(bh * s), (cuuint32_t)bn};
+	cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
 	CUresult r = g_encode(m, dtype == CB200_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
 	                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
 	                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -118,6 +122,13 @@ struct IgemmParams {
 	// 2-CTA cluster variant of conv_igemm_kernel: the two CTAs of a cluster work on two M tiles of the same N tile and
 	// each fetches half of the filter block, multicast to both
 	int cluster, pairs_m;
+	// strided convolutions.  Forward: output pixel (x, y) reads input pixel (x * stride + tap) - the TMA box traverses
+	// the input with that stride.  Data gradient of a filter that tiles the input (f == stride, no padding): one launch
+	// per tap; GEMM pixel (x, y) of dy is written to dx pixel (x * out_s + out_ox, y * out_s + out_oy) of the
+	// (out_W, out_H) map, and the filter tap it uses is w_tap0 of the w_taps taps in the weight tensor.
+	int stride;                  // 0 / 1 = dense
+	int out_s, out_ox, out_oy, out_W, out_H;   // out_s == 0: output pixel grid == GEMM pixel grid
+	int w_tap0, w_taps;          // w_taps == 0: the weight tensor holds f_h * f_w taps and all of them are used
 };
 
 // tile index -> (M tile, N tile).  Cluster mode enumerates pairs: tile = 2*pair + rank, so that with an even grid the
@@ -147,6 +158,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta, bias_value = p.bias_value;
 	const float* __restrict__ bias_w = p.bias_w;
 	const int tw = p.tw, th = p.th, tn = p.tn, PW = p.W, PH = p.H, PN = p.N, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+	const int out_s = p.out_s, out_ox = p.out_ox, out_oy = p.out_oy, OW = p.out_W, OH = p.out_H;
 	const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
 	float* bs = bias_rows + grp * 256;
@@ -162,7 +174,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		const int py = thi * th + (row / tw) % th;
 		const int pn = tni * tn + row / (tw * th);
 		const bool row_ok = px < PW && py < PH && pn < PN;
-		const size_t pix = ((size_t)pn * PH + py) * PW + px;
+		const size_t pix = ((size_t)pn * OH + (py * out_s + out_oy)) * OW + (px * out_s + out_ox);
 		const bool dead = mask_tail && pn >= length;
 		// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
 		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
@@ -308,12 +320,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 						mbar_wait(empty_bar(stage), phase ^ 1u);
 						const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
 						mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-						tma_load_4d(sa, &tmap_a, full_bar(stage), cb * BK, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
+						tma_load_4d(sa, &tmap_a, full_bar(stage), cb * BK, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
 						if (p.cluster)     // this CTA's half of the filter block, to both CTAs (tmap_b boxes are BN/2 rows here)
-							tma_load_3d_multicast(sb + rank * (Cfg::B_BYTES / 2), &tmap_b, full_bar(stage), cb * BK, tap,
+							tma_load_3d_multicast(sb + rank * (Cfg::B_BYTES / 2), &tmap_b, full_bar(stage), cb * BK, tap + p.w_tap0,
 							                      nt * BN + (int)rank * (BN / 2), (uint16_t)3);
 						else
-							tma_load_3d(sb, &tmap_b, full_bar(stage), cb * BK, tap, nt * BN);
+							tma_load_3d(sb, &tmap_b, full_bar(stage), cb * BK, tap + p.w_tap0, nt * BN);
 						if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 					}
 				}
@@ -417,14 +429,39 @@ static int pick_bk(int cp) { return cp >= 64 ? 64 : (cp >= 32 ? 32 : (cp >= 16 ?
 static int pick_bn(int n_pad) { return n_pad > 128 ? 256 : n_pad > 64 ? 128 : n_pad > 32 ? 64 : n_pad > 16 ? 32 : 16; }
 CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B; }
 
+// whole-map filters (dense layers behind conv / pool, common.cuh: conv_whole_map) as the 1x1 convolution they are in the
+// channels-last layout: f_h*f_w*Cp input "channels" on a 1x1 map.  Operand buffers need no change: w_fwd / grad rows
+// [f][tap][c] ARE [f][tap*Cp + c], and w_bwd is kept in (tap, c) row order for these layers (conv.cu: wbwd_row).
+// Without this a 32x32x12 -> 3072 dense layer would run 1024 taps of K = 16 instead of 256 K blocks of 64.
+static cb200_conv_desc tc_view(const cb200_conv_desc* d) {
+	cb200_conv_desc v = *d;
+	if (conv_whole_map(d)) {
+		v.in_c = d->f_h * d->f_w * round8(d->in_c);
+		v.in_h = 1; v.in_w = 1; v.f_h = 1; v.f_w = 1;
+	}
+	return v;
+}
+
 static bool tc_common_ok(const cb200_conv_desc* d) {
 	if (d->dtype != CB200_FP16 && d->dtype != CB200_BF16) return false;
-	if (d->stride_h != 1 || d->stride_w != 1) return false;
+	// strided layers: the same kernels with a TMA traversal stride (square strides; 128-pixel rows times the stride must
+	// fit a TMA box, so 2 only - what upstream's networks use in place of pooling)
+	if (d->stride_h != d->stride_w || d->stride_w < 1 || d->stride_w > 2) return false;
 	if (d->pad_h > d->f_h - 1 || d->pad_w > d->f_w - 1) return false;
 	return true;
 }
-bool conv_tc_fwd_supported(const cb200_conv_desc* d) { return tc_common_ok(d) && pick_bk(round8(d->in_c)) != 0; }
-bool conv_tc_dgrad_supported(const cb200_conv_desc* d) { return tc_common_ok(d) && pick_bk(round8(d->out_c)) != 0 && round8(d->in_c) >= 16; }
+bool conv_tc_fwd_supported(const cb200_conv_desc* d_in) {
+	const cb200_conv_desc v = tc_view(d_in), *d = &v;
+	return tc_common_ok(d) && pick_bk(round8(d->in_c)) != 0;
+}
+bool conv_tc_dgrad_supported(const cb200_conv_desc* d_in) {
+	const cb200_conv_desc v = tc_view(d_in), *d = &v;
+	if (!(tc_common_ok(d) && pick_bk(round8(d->out_c)) != 0 && round8(d->in_c) >= 16)) return false;
+	if (d->stride_w == 1) return true;
+	// strided: only filters that tile the input exactly (every input pixel has one tap and one output pixel)
+	return d->f_h == d->stride_h && d->f_w == d->stride_w && d->pad_h == 0 && d->pad_w == 0 &&
+	       d->in_h == d->stride_h * d->out_h && d->in_w == d->stride_w * d->out_w;
+}
 
 // ================================================================ halo-reuse forward / dgrad kernel
 // For filters larger than 1x1 on LARGE maps with FEW channels the per-tap kernel above is bound by the L2 -> SM path:
@@ -618,11 +655,15 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	const int n_pad = round8(n_real);
 	const int bn = pick_bn(n_pad);
 	CUtensorMap ma, mb;
-	{
+	if (p.stride < 1) p.stride = 1;
+	if (p.out_s < 1) { p.out_s = 1; p.out_ox = 0; p.out_oy = 0; p.out_W = out_w; p.out_H = out_h; }
+	const int w_taps = p.w_taps > 0 ? p.w_taps : f_h * f_w;
+	const bool dense = p.stride == 1 && p.out_s == 1 && p.w_taps == 0;
+	if (dense) {
 		IgemmParams ph = p;
 		const int smem = halo_plan(cin_p, n_pad, f_h, f_w, out_h, out_w, bk, bn, ph);
 		if (smem > 0) {
-			int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, ph.halo_w, HALO_TH + f_h - 1, 1, swizzle_for(bk));
+			int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, ph.halo_w, HALO_TH + f_h - 1, 1, swizzle_for(bk), 1);
 			if (rc) return rc;
 			rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, bn, swizzle_for(bk));
 			if (rc) return rc;
@@ -643,7 +684,7 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	}
 	int tw, th, tn;
 	choose_rect(out_w, out_h, batch, 128, tw, th, tn);
-	int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, tw, th, tn, swizzle_for(bk));
+	int rc = make_act_map(&ma, src, dtype, cin_p, in_w, in_h, batch, bk, tw, th, tn, swizzle_for(bk), p.stride);
 	if (rc) return rc;
 	p.W = out_w; p.H = out_h; p.N = batch;
 	p.tw = tw; p.th = th; p.tn = tn;
@@ -658,12 +699,12 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	// tensor rate against 128 B/clk per SM, i.e. a 71 % ceiling that multicast does not move (each SM still receives and
 	// reads the whole B block).  Lifting it takes cta_group::2 MMAs (B split between the two SMs) - next round.  The path
 	// stays as a tested option.
-	p.cluster = (g_enable_cluster && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
+	p.cluster = (g_enable_cluster && dense && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
 	if (p.cluster) {
 		p.pairs_m = ceil_div(p.tiles_m, 2);
 		p.num_tiles = 2 * p.pairs_m * p.tiles_nn;
 	}
-	rc = make_w_map(&mb, wmat, dtype, cin_p, f_h * f_w, n_real, bk, p.cluster ? bn / 2 : bn, swizzle_for(bk));
+	rc = make_w_map(&mb, wmat, dtype, cin_p, w_taps, n_real, bk, p.cluster ? bn / 2 : bn, swizzle_for(bk));
 	if (rc) return rc;
 	p.f_h = f_h; p.f_w = f_w; p.off_h = off_h; p.off_w = off_w;
 	p.kc_blocks = ceil_div(cin_p, bk);
@@ -673,23 +714,41 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	return dispatch_igemm<__nv_bfloat16>(bn, bk, ma, mb, p, st);
 }
 
-int conv_forward_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y, cudaStream_t st) {
+int conv_forward_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, void* y, cudaStream_t st) {
+	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	IgemmParams p;
 	memset(&p, 0, sizeof(p));
 	p.mode = 0; p.length = d->length; p.bias_value = d->bias_value; p.bias_w = w->bias_w;
 	p.out = y; p.prev_out = nullptr; p.activ = d->activ;
+	p.stride = d->stride_w;
 	return run_igemm(d->dtype, x, round8(d->in_c), d->in_h, d->in_w, d->batch, w->w_fwd, d->out_c,
 	                 d->f_h, d->f_w, -d->pad_h, -d->pad_w, d->out_h, d->out_w, p, st);
 }
 
-int conv_dgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* dy, void* dx,
+int conv_dgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* dy, void* dx,
                   const cb200_activ* prev_activ, const void* prev_out, cudaStream_t st) {
+	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	IgemmParams p;
 	memset(&p, 0, sizeof(p));
 	p.mode = 1; p.length = d->length; p.bias_value = 0.0f; p.bias_w = nullptr;
 	p.out = dx; p.prev_out = prev_out;
 	p.activ.type = CB200_LINEAR;
 	if (prev_activ && prev_out) p.activ = *prev_activ;
+	if (d->stride_w > 1) {
+		// the filter tiles the input (f == stride, no padding: conv_tc_dgrad_supported): input pixel (s*oy + ky, s*ox + kx)
+		// receives dy(oy, ox) through tap (ky, kx) only - one 1x1 GEMM per tap, scattered with stride s into dx
+		const int s = d->stride_w, taps = d->f_h * d->f_w;
+		for (int ky = 0; ky < d->f_h; ky++)
+			for (int kx = 0; kx < d->f_w; kx++) {
+				IgemmParams q = p;
+				q.out_s = s; q.out_oy = ky; q.out_ox = kx; q.out_W = d->in_w; q.out_H = d->in_h;
+				q.w_taps = taps; q.w_tap0 = taps - 1 - (ky * d->f_w + kx);        // w_bwd keeps the taps in rotated order
+				int rc = run_igemm(d->dtype, dy, round8(d->out_c), d->out_h, d->out_w, d->batch, w->w_bwd, d->in_c,
+				                   1, 1, 0, 0, d->out_h, d->out_w, q, st);
+				if (rc) return rc;
+			}
+		return CB200_OK;
+	}
 	// full correlation of dy with the rotated filters: padding f-1-p
 	return run_igemm(d->dtype, dy, round8(d->out_c), d->out_h, d->out_w, d->batch, w->w_bwd, d->in_c,
 	                 d->f_h, d->f_w, -(d->f_h - 1 - d->pad_h), -(d->f_w - 1 - d->pad_w), d->in_h, d->in_w, p, st);
@@ -705,6 +764,7 @@ struct WgradParams {
 	int tw, th, tn;              // pixel rectangle of one K step (64 pixels)
 	int tiles_w, tiles_h, tiles_n, pix_tiles;
 	int f_h, f_w, off_h, off_w;
+	int stride;                  // x pixel = dy pixel * stride + tap offset
 	int f_groups, c_tiles, tap_groups, tg;   // job grid; tg = taps per group (<= TGMAX)
 	int splits, tiles_per_split, stages;
 	int out_c, in_cp;
@@ -792,7 +852,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 #pragma unroll
 					for (int sl = 0; sl < Cfg::B_SLABS; sl++)
 						tma_load_4d(sb + ti * Cfg::B_BYTES + sl * Cfg::B_SLAB_BYTES, &tmap_x, full_bar(stage),
-						            ct * BNC + sl * SLAB_C, w0 + kx + p.off_w, h0 + ky + p.off_h, n0);
+						            ct * BNC + sl * SLAB_C, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
 				}
 				if (++stage == stages) { stage = 0; phase ^= 1u; }
 			}
@@ -867,7 +927,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
-bool conv_tc_wgrad_supported(const cb200_conv_desc* d) {
+bool conv_tc_wgrad_supported(const cb200_conv_desc* d_in) {
+	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	if (!tc_common_ok(d)) return false;
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
 	// (a 64-channel dy slab on a tensor with fewer channels relies on TMA zero-filling the missing ones)
@@ -890,7 +951,8 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
 	return CB200_OK;
 }
 
-int conv_wgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
+int conv_wgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
+	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
 	const int taps = d->f_h * d->f_w;
 	const int slab_c = in_cp >= 64 ? 64 : in_cp;
@@ -907,10 +969,11 @@ int conv_wgrad_tc(const cb200_conv_desc* d, const cb200_conv_weights* w, const v
 	memset(&p, 0, sizeof(p));
 	choose_rect(d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn);
 	CUtensorMap mdy, mx;
-	int rc = make_act_map(&mdy, dy, d->dtype, out_cp, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B);
+	int rc = make_act_map(&mdy, dy, d->dtype, out_cp, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B, 1);
 	if (rc) return rc;
-	rc = make_act_map(&mx, x, d->dtype, in_cp, d->in_w, d->in_h, d->batch, slab_c, p.tw, p.th, p.tn, swizzle_for(slab_c));
+	rc = make_act_map(&mx, x, d->dtype, in_cp, d->in_w, d->in_h, d->batch, slab_c, p.tw, p.th, p.tn, swizzle_for(slab_c), d->stride_w);
 	if (rc) return rc;
+	p.stride = d->stride_w;
 	p.W = d->out_w; p.H = d->out_h; p.N = d->batch;
 	p.tiles_w = ceil_div(p.W, p.tw); p.tiles_h = ceil_div(p.H, p.th); p.tiles_n = ceil_div(p.N, p.tn);
 	p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;

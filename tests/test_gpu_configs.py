@@ -1,0 +1,175 @@
+"""The other BASELINE.json configurations at their FULL sizes (cianna_b200/configs.py): the COCO Darknet19-YOLO detector
+at 416 px, the SKA SDC1 17-conv YOLO detector at 512 px (stride-2 convolutions, dropout, 1360 target slots), the
+dense-heavy extinction-profile regression network at 64 px, and the MNIST example network with its dropout.
+
+No reference output exists at these sizes (the CPU reference needs minutes per step), so the checks are the
+size-independent ones: every tensor finite, the sample axis is independent (a permuted batch gives the permuted output),
+a partially filled batch equals the full one on its samples, repeated steps on one batch reduce its loss, YOLO
+association states are consistent with the targets.  Step times are written to gpurun_out/configs_report.json
+(host wall clock around a synchronising read-back: a secondary table, not bench.py's metric).
+"""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from cianna_b200 import configs
+from oracle import ref_driver as rd
+
+pytestmark = pytest.mark.gpu
+
+REPORT = {}
+
+
+@pytest.fixture(scope="module")
+def cnn():
+    from cianna_b200 import CIANNA as m
+    yield m
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "configs_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1)
+
+
+def _build(cnn, spec, mode):
+    with rd._Quiet():
+        rd.build_network(cnn, spec, "C_CUDA", mode, network=0)
+
+
+def _inputs(spec, seed):
+    rng = np.random.default_rng(seed)
+    dim = spec["in_dim"][0] * spec["in_dim"][1] * spec["in_ch"]
+    x = np.zeros((spec["batch"], dim + 1), np.float32)
+    x[:, :dim] = rng.standard_normal((spec["batch"], dim)).astype(np.float32)
+    return x
+
+
+def _time_steps(cnn, n, lr):
+    cnn.batch_loss(network=0)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        cnn.forward_batch(network=0)
+        cnn.backward_batch(lr, 0.9, network=0)
+    cnn.batch_loss(network=0)
+    return (time.perf_counter() - t0) / n
+
+
+CASES = {
+    # name: (spec factory, batch, mode, learning rate, steps)
+    "darknet19_yolo_416": (lambda b: configs.darknet19_yolo(b, 416), 16, "FP16C_FP32A", 2e-4, 12),
+    "sdc1_yolo_512_fp16": (lambda b: configs.sdc1_yolo(b, 512), 8, "FP16C_FP32A", 2e-4, 12),
+    "sdc1_yolo_256_fp32": (lambda b: configs.sdc1_yolo(b, 256), 4, "off", 2e-4, 6),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_yolo_detectors_at_full_size(cnn, name):
+    make, B, mode, lr, steps = CASES[name]
+    spec = make(B)
+    y = spec["yolo"]
+    _build(cnn, spec, mode)
+    cnn.set_TC_scale_factor(16.0, network=0)
+    cnn.set_dropout_seed(3, network=0)
+    cnn.yolo_set_seed(5, network=0)
+    cnn.set_iter(10, 100000, network=0)              # past the random start-up phase
+    x = _inputs(spec, 1)
+    n_obj = min(40, y["max_nb_obj_per_image"])
+    t = rd.make_yolo_targets(spec, 2, n_obj=n_obj)
+    last = len(spec["layers"]) - 1
+    nb_box = y["nb_box"]
+    cnn.load_batch(x, t, network=0)
+    cnn.forward_batch(network=0)
+    out = cnn.layer_output(last, network=0)
+    assert np.isfinite(out).all()
+    grid = spec["in_dim"][0] // 32 if "darknet" in name else spec["in_dim"][0] // 16
+    assert out.shape == (nb_box * (8 + y.get("nb_class", 0) + y.get("nb_param", 0)), B, grid * grid)
+    loss0 = cnn.batch_loss(network=0)
+    assert np.isfinite(loss0) and loss0 > 0
+    cnn.backward_batch(lr, 0.9, network=0)
+    state = cnn.yolo_box_state(nb_box, network=0)
+    assert set(np.unique(state)) <= {0, 1, 2}
+    # every target is associated to exactly one box unless its cell is full (cells hold nb_box boxes)
+    per_image = (state == 2).reshape(B, -1).sum(axis=1)
+    assert (per_image <= n_obj).all() and (per_image >= min(n_obj, 1)).all()
+    cx = ((t[:, 1:].reshape(B, y["max_nb_obj_per_image"], -1)[:, :n_obj, 1] + t[:, 1:].reshape(B, y["max_nb_obj_per_image"], -1)[:, :n_obj, 4]) / 2)
+    cy = ((t[:, 1:].reshape(B, y["max_nb_obj_per_image"], -1)[:, :n_obj, 2] + t[:, 1:].reshape(B, y["max_nb_obj_per_image"], -1)[:, :n_obj, 5]) / 2)
+    cell = spec["in_dim"][0] // grid
+    for b in range(B):
+        want_cells = set((np.floor(cy[b] / cell).astype(int) * grid + np.floor(cx[b] / cell).astype(int)).tolist())
+        got_cells = set(np.nonzero((state[b] == 2).any(axis=1))[0].tolist())
+        # ("difficult" targets of the COCO set-up may be left unassociated; nothing is ever associated outside a target's cell)
+        assert got_cells <= want_cells, (b, sorted(got_cells - want_cells))
+        if not y.get("diff_flag", 0):
+            assert got_cells == want_cells, (b, sorted(got_cells ^ want_cells))
+    for i in (0, last // 2, last):
+        assert np.isfinite(cnn.layer_delta(i, network=0)).all(), i
+    # repeated steps on this batch reduce its loss
+    losses = [loss0]
+    for _ in range(steps):
+        cnn.forward_batch(network=0)
+        losses.append(cnn.batch_loss(network=0))
+        cnn.backward_batch(lr, 0.9, network=0)
+    assert np.isfinite(losses).all() and min(losses[-3:]) < losses[0], losses
+    dt = _time_steps(cnn, 5, 0.0)
+    REPORT[name] = {"batch": B, "mode": mode, "ms_per_step": 1e3 * dt, "img_per_s": B / dt, "loss_first_last": [losses[0], losses[-1]]}
+    # the sample axis is independent: inference on the reversed batch gives the reversed output (dropout off in AVG_MODEL)
+    cnn.forward_batch(is_inference=1, network=0)
+    a = cnn.layer_output(last, network=0)
+    cnn.load_batch(x[::-1].copy(), t[::-1].copy(), network=0)
+    cnn.forward_batch(is_inference=1, network=0)
+    r = cnn.layer_output(last, network=0)
+    scale = np.abs(a).max()
+    assert np.abs(r[:, ::-1, :] - a).max() < 2e-3 * scale
+    # a partially filled batch computes the same values for its samples
+    half = B // 2
+    cnn.load_batch(x, t, network=0)
+    cnn.forward_batch(half, is_inference=1, network=0)
+    p = cnn.layer_output(last, network=0)
+    assert np.abs(p[:, :half, :] - a[:, :half, :]).max() < 2e-3 * scale
+
+
+def test_extinction_profile_regression_at_full_size(cnn):
+    B = 128
+    spec = configs.extinction_profile(B)
+    _build(cnn, spec, "FP16C_FP32A")
+    cnn.set_TC_scale_factor(64.0, network=0)
+    cnn.set_dropout_seed(3, network=0)
+    rng = np.random.default_rng(0)
+    x = _inputs(spec, 1)
+    # a smooth target profile that depends on the input (its mean and a few pixels): learnable
+    dim = 64 * 64
+    feat = np.stack([x[:, :dim].mean(axis=1), x[:, 0], x[:, 1]], axis=1)
+    basis = rng.standard_normal((3, 128)).astype(np.float32)
+    t = (0.5 + 0.2 * np.tanh(feat @ basis)).astype(np.float32)
+    cnn.load_batch(x, t, network=0)
+    losses = []
+    for _ in range(60):          # (sum-of-squares loss over 128 outputs behind 2048-wide layers: small steps)
+        cnn.forward_batch(network=0)
+        losses.append(cnn.batch_loss(network=0))
+        cnn.backward_batch(2e-5, 0.9, network=0)
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.5 * losses[0], (losses[0], losses[-5:])
+    for i in range(len(spec["layers"])):
+        assert np.isfinite(cnn.layer_output(i, network=0)).all(), i
+    dt = _time_steps(cnn, 10, 0.0)
+    REPORT["extinction_profile_64"] = {"batch": B, "mode": "FP16C_FP32A", "ms_per_step": 1e3 * dt, "img_per_s": B / dt,
+                                       "loss_first_last": [losses[0], float(np.mean(losses[-5:]))]}
+    cnn.forward_batch(is_inference=1, network=0)
+    a = cnn.layer_output(5, network=0)
+    cnn.load_batch(x[::-1].copy(), t[::-1].copy(), network=0)
+    cnn.forward_batch(is_inference=1, network=0)
+    r = cnn.layer_output(5, network=0)
+    assert np.abs(r[::-1] - a).max() < 2e-3 * np.abs(a).max()
+
+
+def test_mnist_example_network_step_time(cnn):
+    spec = configs.lenet(batch=64, dropout=True)
+    _build(cnn, spec, "FP16C_FP32A")
+    x = _inputs(spec, 1)
+    t = np.zeros((64, 10), np.float32)
+    t[np.arange(64), np.arange(64) % 10] = 1
+    cnn.load_batch(x, t, network=0)
+    dt = _time_steps(cnn, 50, 0.001)
+    REPORT["mnist_lenet_28"] = {"batch": 64, "mode": "FP16C_FP32A", "ms_per_step": 1e3 * dt, "img_per_s": 64 / dt}
+    assert np.isfinite(cnn.batch_loss(network=0))
