@@ -83,6 +83,70 @@ __global__ void conv_update_kernel(float* __restrict__ master, float* __restrict
 	}
 }
 
+// Dense layers (master [in_size][n + 1]: one ROW per input, neurons contiguous): the same update on 32 x 32 tiles.  The raw
+// gradient and w_fwd are [n][K] (K = taps * in_cp contiguous), master / momentum / w_bwd are [K][n]-oriented, so the tile
+// goes through shared memory once each way and every global access is a full 64 - 128 B row segment - the generic kernel
+// above reads 4 B out of every 32 B sector of master and momentum (measured on the 12289 x 3072 layer of the
+// extinction-profile network: 3.4 ms, 27 GB of L2 traffic for 1 GB of data).
+template <typename T>
+__global__ void __launch_bounds__(256)
+dense_update_tiled_kernel(float* __restrict__ master, float* __restrict__ moment, const float* __restrict__ grad,
+                          const float* __restrict__ grad_b, const float* __restrict__ hyper, float bias_value,
+                          T* __restrict__ w_fwd, T* __restrict__ w_bwd, float* __restrict__ bias_w,
+                          int n, int taps, int in_c, int in_cp, int out_cp, int wb_dense) {
+	__shared__ float gt[32][33];      // gradient tile [neuron][k]
+	__shared__ float wt[32][33];      // updated weights [k][neuron]
+	const int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	const int K = taps * in_cp;
+	const size_t ms_c = (size_t)n + 1;
+	const float alpha = hyper[0], mom = hyper[1], wdlr = hyper[2], S = hyper[3];
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int f = f0 + r, k = k0 + tx;
+		gt[r][tx] = (f < n && k < K) ? grad[(size_t)f * K + k] : 0.0f;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int k = k0 + r, f = f0 + tx;
+		float wv = 0.0f;
+		if (k < K && f < n) {
+			const int tap = k / in_cp, c = k - tap * in_cp;
+			if (c < in_c) {
+				const size_t mi = ((size_t)c * taps + tap) * ms_c + f;      // master row of (channel c, tap): upstream's flatten order
+				wv = master[mi];
+				float m = alpha * gt[tx][r] + mom * moment[mi];
+				m += wdlr * wv * S;
+				wv -= m / S;
+				moment[mi] = m;
+				master[mi] = wv;
+				w_bwd[wbwd_row(c, tap, taps, in_cp, wb_dense) * out_cp + f] = from_f32<T>(wv);
+			}
+		}
+		wt[r][tx] = wv;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int f = f0 + r, k = k0 + tx;
+		if (f < n && k < K && (k % in_cp) < in_c) w_fwd[(size_t)f * K + k] = from_f32<T>(wt[tx][r]);
+	}
+	if (blockIdx.x == 0 && ty == 0) {         // the bias row (input in_size - 1)
+		const int f = f0 + tx;
+		if (f < n) {
+			const size_t mi = (size_t)taps * in_c * ms_c + f;
+			float wv = master[mi];
+			float m = alpha * (bias_value * grad_b[f]) + mom * moment[mi];
+			m += wdlr * wv * S;
+			wv -= m / S;
+			moment[mi] = m;
+			master[mi] = wv;
+			bias_w[f] = wv;
+		}
+	}
+}
+
 // Conv layers (master in the conv layout, ms_c == 1): the same update with threads in OPERAND order (f, tap, c) instead
 // of master order, so the raw gradient is read and w_fwd written fully coalesced; the master / momentum accesses of a
 // warp then stride by `taps` floats but stay inside one filter's contiguous span (L1 resident).  The transposed +
@@ -398,6 +462,15 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 		dim3 tgrid((unsigned)ceil_div(d->in_c, 32), (unsigned)ceil_div(out_cp, 32), (unsigned)taps);
 		CB_DISPATCH_DTYPE(d->dtype, T, (conv_wbwd_transpose_kernel<T><<<tgrid, 256, 0, as_stream(s)>>>(
 			(const T*)w->w_fwd, (T*)w->w_bwd, d->out_c, out_cp, taps, d->in_c, in_cp, conv_whole_map(d) ? 1 : 0)));
+		CB_LAUNCH_CHECK();
+		return CB200_OK;
+	}
+	if (!old_update && ms_f == 1 && ms_c == (size_t)d->out_c + 1 && !is_pivot) {
+		const int in_cp = round8(d->in_c), K = taps * in_cp;
+		const dim3 tgrid((unsigned)ceil_div(K, 32), (unsigned)ceil_div(d->out_c, 32));
+		CB_DISPATCH_DTYPE(d->dtype, T, (dense_update_tiled_kernel<T><<<tgrid, 256, 0, as_stream(s)>>>(
+			w->master, w->moment, w->grad, w->grad_b, hyper, d->bias_value, (T*)w->w_fwd, (T*)w->w_bwd, w->bias_w,
+			d->out_c, taps, d->in_c, in_cp, round8(d->out_c), conv_whole_map(d) ? 1 : 0)));
 		CB_LAUNCH_CHECK();
 		return CB200_OK;
 	}

@@ -931,8 +931,9 @@ bool conv_tc_wgrad_supported(const cb200_conv_desc* d_in) {
 	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	if (!tc_common_ok(d)) return false;
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
-	// (a 64-channel dy slab on a tensor with fewer channels relies on TMA zero-filling the missing ones)
-	return out_cp >= 16 && (in_cp >= 64 || in_cp == 32 || in_cp == 16);
+	// (a 64-channel dy slab on a tensor with fewer channels relies on TMA zero-filling the missing ones; so does an x slab
+	//  of 32 / 64 channels on a tensor with 24 / 40 / 48 / 56 - the epilogue only adds the real columns)
+	return out_cp >= 16 && in_cp >= 16;
 }
 
 template <int BNC, int SLAB_C, int MF, int TGMAX>
@@ -955,8 +956,8 @@ int conv_wgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, cons
 	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
 	const int taps = d->f_h * d->f_w;
-	const int slab_c = in_cp >= 64 ? 64 : in_cp;
-	const int bnc = in_cp < 64 ? in_cp : (in_cp > 128 ? 256 : (in_cp > 64 ? 128 : 64));
+	const int slab_c = in_cp > 32 ? 64 : (in_cp > 16 ? 32 : 16);
+	const int bnc = in_cp > 128 ? 256 : (in_cp > 64 ? 128 : slab_c);
 	// blocks of 128 output channels per CTA and taps per CTA, bounded by the 512 TMEM columns
 	const int mf = (out_cp > 128 && bnc >= 128) ? 2 : 1;
 	int tg_cap = 512 / (mf * bnc);

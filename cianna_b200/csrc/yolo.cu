@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(128) yolo_delta_kernel(cb200_yolo_desc d, T* _
 	const int b = blockIdx.x, cells = d.grid_h * d.grid_w;
 	const int C = d.nb_box * (8 + d.nb_class + d.nb_param), cp = round8(C);
 	float acc[6];
-	for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+	// grid (image, cell chunk): cells are independent (a target belongs to exactly one cell, the scratch is per target)
+	for (int cell = blockIdx.y * blockDim.x + threadIdx.x; cell < cells; cell += gridDim.y * blockDim.x) {
 		T* dl = delta + ((size_t)b * cells + cell) * cp;
 		for (int c = C; c < cp; c++) dl[c] = from_f32<T>(0.0f);
 		if (b >= d.length) {
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(128) yolo_loss_kernel(cb200_yolo_desc d, float
 	float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 	YoloRng rng;
 	rng.key = 0; rng.draw = 0;
-	for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+	for (int cell = blockIdx.y * blockDim.x + threadIdx.x; cell < cells; cell += gridDim.y * blockDim.x) {
 		float* mon = monitor != nullptr ? monitor + ((size_t)b * cells + cell) * d.nb_box * 2 : nullptr;
 		if (b >= d.length) {
 			if (mon != nullptr)
@@ -459,13 +460,14 @@ __global__ void __launch_bounds__(128) yolo_loss_kernel(cb200_yolo_desc d, float
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		// (loss / parts are cleared by the launcher; one block per image when the grid has a single chunk)
 		float total = 0.0f;
 		for (int p = 0; p < 6; p++) {
 			const float v = red[0][p] + red[1][p] + red[2][p] + red[3][p];
-			if (parts != nullptr) parts[b * 6 + p] = v;
+			if (parts != nullptr) atomicAdd(parts + b * 6 + p, v);
 			total += v;
 		}
-		loss[b] = total;
+		atomicAdd(loss + b, total);
 	}
 }
 
@@ -576,7 +578,8 @@ int cb200_yolo_delta(const cb200_yolo_desc* d, void* delta, const void* y, const
 	int rc = check_desc(d, __func__);
 	if (rc != CB200_OK) return rc;
 	CB_ARG(delta != nullptr && y != nullptr && target != nullptr && workspace != nullptr);
-	CB_DISPATCH_DTYPE(d->dtype, T, (yolo_delta_kernel<T><<<d->batch, 128, 0, as_stream(s)>>>(*d, (T*)delta, (const T*)y, (const T*)target,
+	const dim3 grid((unsigned)d->batch, (unsigned)ceil_div(d->grid_h * d->grid_w, 128));
+	CB_DISPATCH_DTYPE(d->dtype, T, (yolo_delta_kernel<T><<<grid, 128, 0, as_stream(s)>>>(*d, (T*)delta, (const T*)y, (const T*)target,
 		tc_scale, nb_im_iter, seed, step, box_state, workspace)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
@@ -588,7 +591,10 @@ int cb200_yolo_loss(const cb200_yolo_desc* d, float* loss, float* parts, float* 
 	int rc = check_desc(d, __func__);
 	if (rc != CB200_OK) return rc;
 	CB_ARG(loss != nullptr && y != nullptr && target != nullptr && workspace != nullptr);
-	CB_DISPATCH_DTYPE(d->dtype, T, (yolo_loss_kernel<T><<<d->batch, 128, 0, as_stream(s)>>>(*d, loss, parts, monitor, (const T*)y,
+	const dim3 grid((unsigned)d->batch, (unsigned)ceil_div(d->grid_h * d->grid_w, 128));
+	CB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * (size_t)d->batch, as_stream(s)));
+	if (parts != nullptr) CB_CUDA(cudaMemsetAsync(parts, 0, sizeof(float) * 6 * (size_t)d->batch, as_stream(s)));
+	CB_DISPATCH_DTYPE(d->dtype, T, (yolo_loss_kernel<T><<<grid, 128, 0, as_stream(s)>>>(*d, loss, parts, monitor, (const T*)y,
 		(const T*)target, workspace)));
 	CB_LAUNCH_CHECK();
 	return CB200_OK;

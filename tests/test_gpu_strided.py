@@ -32,6 +32,11 @@ STRIDED = [
     (2, 384, 8, 512, 2, 2, 0, True),     # SDC1 layer 13 shape (wide)
     (4, 32, 15, 32, 3, 2, 1, False),     # overlapping 3x3 stride 2: forward / weight gradient strided, data gradient on CUDA cores
     (2, 32, 15, 32, 2, 2, 0, False),     # input not covered by the filters (15 = 2*7 + 1): last row / column gets no gradient
+    # channel counts between the operand slab widths (SDC1 layers 3-4: 16 -> 24 -> 32 channels): the weight gradient reads a
+    # 32- / 64-channel slab from a 24- / 40-channel tensor (TMA zero-fills the rest)
+    (4, 24, 12, 32, 3, 1, 1, True),
+    (3, 40, 9, 48, 3, 1, 1, True),
+    (2, 24, 16, 64, 2, 2, 0, True),
 ]
 
 
