@@ -295,6 +295,8 @@ def run_ours(args, rank, local_rank, world):
         if rem:
             H.cb_train_steps(net, rem, lr, mom, wd, 0, 1)
     H.cb_train_steps(net, min(args.warmup, 2), lr, mom, wd, 0, 1)
+    with quiet:   # one untimed epoch through train(): also takes the per-layer perf_eval sample of the first epoch
+        cnn.train(nb_iter=1, control_interv=10 ** 6, shuffle_every=0, silent=1, network=0, TC_scale_factor=256.0, **HYPER)
     ms_e2e = timed(e2e_run)
 
     # ---- inference (forward only), device resident and end to end

@@ -391,6 +391,17 @@ def perf_eval(network=None):
     _load().perf_eval_display(_net(network))
 
 
+def perf_eval_table(network=None):
+    """(forward_us[nb_layers], backprop_us[nb_layers], number of sampled mini-batches) behind perf_eval()'s table"""
+    L = _load()
+    net = _net(network)
+    n = L.cb_net_nb_layers(net)
+    fwd, back = np.zeros(n, np.float64), np.zeros(n, np.float64)
+    L.cb_perf_eval_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    samples = L.cb_perf_eval_read(net, fwd.ctypes.data, back.ctypes.data)
+    return fwd, back, int(samples)
+
+
 def load(file, iteration, network=None, nb_layers=0, bin=0):
     _load().load_network(_net(network), _s(file), int(iteration), int(nb_layers), int(bin))
 

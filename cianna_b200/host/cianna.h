@@ -208,6 +208,12 @@ struct network {
 	int stage_slot;
 	const cb200_conv_desc *patch_desc;   /* first conv layer when it consumes patch rows (few input channels), else NULL */
 	yolo_param *y_param;   /* network-level YOLO set-up (set_yolo_params), copied into the YOLO layer at creation */
+	/* per-layer timing table of perf_eval (src/auxil.c:698-870 upstream): sampled on the first mini-batch of every epoch
+	 * with events between the layers (3 x (nb_layers + 1): forward, backward, optimizer), no synchronisation inside */
+	void **perf_ev;
+	int perf_sample;
+	double *fwd_perf, *back_perf;   /* accumulated microseconds per layer */
+	int perf_n;
 	unsigned long long drop_seed;   /* dropout masks are a function of (seed, layer, draw, position): see cb200_dropout_desc */
 	unsigned long long drop_draw;   /* counts the forward passes that drew masks */
 };
@@ -261,6 +267,7 @@ void train_network(network *net, int nb_epochs, int control_interv, float u_begi
 void forward_testset(network *net, int saving, int repeat, int drop_mode, int silent);
 void compute_error(network *net, Dataset data, int saving, int confusion_matrix, int repeat, int silent);
 void perf_eval_display(network *net);
+int cb_perf_eval_read(network *net, double *fwd, double *back);
 
 /* activation helpers (src/activ_functions.c:260-374, 580-610) */
 void load_activ_param(layer *current, const char *activ);

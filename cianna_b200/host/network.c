@@ -332,6 +332,42 @@ static void use_device_batch(network *net, const void *input_dev)
 		CB_CHECK(cb200_import_input(net->input, input_dev, net->dtype, net->batch_size, net->in_dims[3], net->in_dims[1], net->in_dims[0], NULL));
 }
 
+/* ---- per-layer timing sample (perf_eval): slot s of pass p (0 forward, 1 backward, 2 optimizer) */
+static void perf_mark(network *net, int pass, int slot)
+{
+	if (net->perf_sample) CB_CHECK(cb200_event_record(net->perf_ev[pass * (net->nb_layers + 1) + slot], NULL));
+}
+
+static void perf_begin_sample(network *net)
+{
+	int i, n = 3 * (net->nb_layers + 1);
+	if (net->perf_ev == NULL) {
+		net->perf_ev = (void **)calloc(n, sizeof(void *));
+		for (i = 0; i < n; i++) CB_CHECK(cb200_event_create(&net->perf_ev[i]));
+		net->fwd_perf = (double *)calloc(net->nb_layers, sizeof(double));
+		net->back_perf = (double *)calloc(net->nb_layers, sizeof(double));
+	}
+	net->perf_sample = 1;
+}
+
+/* after the sampled batch has completed: forward slot k .. k+1 brackets layer k, backward slot i .. i+1 brackets layer
+ * nb_layers-1-i (slot 0 .. 1 also holds the output error, like upstream), optimizer slot k .. k+1 layer k's update */
+static void perf_end_sample(network *net)
+{
+	int k, L = net->nb_layers;
+	float ms;
+	net->perf_sample = 0;
+	for (k = 0; k < L; k++) {
+		CB_CHECK(cb200_event_elapsed_ms(net->perf_ev[k], net->perf_ev[k + 1], &ms));
+		net->fwd_perf[k] += 1e3 * ms;
+		CB_CHECK(cb200_event_elapsed_ms(net->perf_ev[(L + 1) + k], net->perf_ev[(L + 1) + k + 1], &ms));
+		net->back_perf[L - 1 - k] += 1e3 * ms;
+		CB_CHECK(cb200_event_elapsed_ms(net->perf_ev[2 * (L + 1) + k], net->perf_ev[2 * (L + 1) + k + 1], &ms));
+		net->back_perf[k] += 1e3 * ms;
+	}
+	net->perf_n++;
+}
+
 void cb_forward(network *net, int length, int is_inference)
 {
 	int k;
@@ -389,8 +425,10 @@ static void apply_updates(network *net)
 		if (any_norm) CB_CHECK(cb200_dp_allreduce(net->grad_arena + norm_begin, norm_len, NULL));
 		CB_CHECK(cb200_dp_join(NULL));
 	}
+	perf_mark(net, 2, 0);
 	for (k = 0; k < net->nb_layers; k++) {
 		layer *l = net->net_layers[k];
+		if (k > 0) perf_mark(net, 2, k);
 		if (l->frozen) continue;
 		if (l->type == CONV) {
 			conv_param *p = (conv_param *)l->param;
@@ -403,14 +441,18 @@ static void apply_updates(network *net)
 			CB_CHECK(cb200_norm_update(&p->desc, p->gamma, p->beta, p->gamma_update, p->beta_update, p->gsum, net->hyper_dev, NULL));
 		}
 	}
+	perf_mark(net, 2, net->nb_layers);
 }
 
 static void backward_pass(network *net, const void *target_dev)
 {
 	int k;
+	perf_mark(net, 1, 0);
 	output_deriv_error(net, target_dev);
-	for (k = net->nb_layers - 1; k >= 0; k--)
+	for (k = net->nb_layers - 1; k >= 0; k--) {
 		net->net_layers[k]->backprop(net->net_layers[k]);
+		perf_mark(net, 1, net->nb_layers - k);
+	}
 	apply_updates(net);
 }
 
@@ -516,7 +558,11 @@ static void train_one_batch(network *net, Dataset *data, int j, int resident, in
 		use_device_batch(net, data->input_device[j]);
 		tgt = data->target_device[j];
 	}
-	for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
+	perf_mark(net, 0, 0);
+	for (k = 0; k < net->nb_layers; k++) {
+		net->net_layers[k]->forward(net->net_layers[k]);
+		perf_mark(net, 0, k + 1);
+	}
 	/* the loss monitor reads the forward output, so it can be queued before the backward sweep */
 	output_error(net, tgt);
 	CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
@@ -616,8 +662,14 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		net->is_inference = 0;
 		for (j = 0; j < net->train.nb_batch; j++) {
 			double t_batch = now_s(), batch_error = 0.0;
+			/* perf_eval: the first batch of the first epoch and of every 16th epoch is timed layer by layer, with the weight
+			 * gradients on the compute stream so that every kernel lands between its own layer's events */
+			const int sample = net->perf_eval && j == 0 && (net->perf_n == 0 || net->iter % 16 == 0);   /* (a sample, not a census) */
+			void *side = net->wgrad_stream;
+			if (sample) { perf_begin_sample(net); net->wgrad_stream = NULL; }
 			train_one_batch(net, &net->train, j, !net->dynamic_load, j + 1 < net->train.nb_batch ? j + 1 : -1);
 			CB_CHECK(cb200_stream_sync(NULL));
+			if (sample) { net->wgrad_stream = side; perf_end_sample(net); }
 			for (k = 0; k < net->length; k++) { batch_error += net->loss_host[k]; total_error += net->loss_host[k]; }
 			batch_error /= net->length;
 			if (isnan(batch_error)) { printf("\nERROR: Network divergence detected (Nan)!\n\n"); exit(EXIT_FAILURE); }
@@ -882,10 +934,38 @@ void set_frozen_layers(network *net, int *tab, int dim)
 	for (i = 0; i < dim; i++) net->net_layers[tab[i]]->frozen = 1;
 }
 
+/* Table of upstream's perf_eval_display (src/auxil.c:802-870): mean time of every layer, forward and backprop (weight
+ * update included), from the sampled mini-batches (see train_network). */
 void perf_eval_display(network *net)
 {
-	printf("\n  Per-layer timing is collected with ncu / CUDA events on demand in this build (no per-layer device sync in the loop);\n"
-	       "  last epoch: %.2f it/s\n", net->last_items_per_s);
+	static const char type_char[5] = { 'C', 'P', 'D', 'N', 'L' };   /* layer_type_enum order */
+	double total_fwd = 0.0, total_back = 0.0, total;
+	int i;
+	if (net->perf_eval == 0) return;
+	printf("\nTotal Net. nb weights: %lld\n", net->total_nb_param);
+	if (net->perf_n == 0) { printf(" WARNING: no layer was benchmarked yet (the table is sampled while training)\n"); return; }
+	for (i = 0; i < net->nb_layers; i++) { total_fwd += net->fwd_perf[i] / net->perf_n; total_back += net->back_perf[i] / net->perf_n; }
+	total = total_fwd + total_back;
+	printf("\n     Layer  Type       Forward             Backprop             Cumulated\n");
+	printf("       N     T      [µs]  /  [%%]         [µs]  /  [%%]         [µs]  /  [%%]\n");
+	printf("  -------------------------------------------------------------------\n");
+	for (i = 0; i < net->nb_layers; i++) {
+		const double f = net->fwd_perf[i] / net->perf_n, b = net->back_perf[i] / net->perf_n;
+		printf("   %5d     %c   %8.1f / %4.1f      %8.1f / %4.1f      %8.1f / %4.1f\n", i + 1, type_char[net->net_layers[i]->type],
+			f, f / total_fwd * 100.0, b, total_back > 0.0 ? b / total_back * 100.0 : 0.0, f + b, (f + b) / total * 100.0);
+	}
+	printf("  -------------------------------------------------------------------\n");
+	printf("   Total         %8.1f µs          %8.1f µs          %8.1f µs       \n\n", total_fwd, total_back, total);
+	printf("  (sampled on %d mini-batch(es); last epoch: %.2f it/s)\n", net->perf_n, net->last_items_per_s);
+	fflush(stdout);
+}
+
+/* per-layer mean times in microseconds (tests): fwd[nb_layers], back[nb_layers]; returns the number of samples */
+int cb_perf_eval_read(network *net, double *fwd, double *back)
+{
+	int i;
+	for (i = 0; i < net->nb_layers && net->perf_n > 0; i++) { fwd[i] = net->fwd_perf[i] / net->perf_n; back[i] = net->back_perf[i] / net->perf_n; }
+	return net->perf_n;
 }
 
 /* ------------------------------------------------------------------ read-back helpers (tests, parity) */
