@@ -650,15 +650,21 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		double total_error = 0.0, t_epoch = now_s();
 		float lr = u_end_learning_rate + (u_begin_learning_rate - u_end_learning_rate) * expf(-net->decay * net->iter);
 		if (silent < 1) printf("\n");
+		int shuffled = 0, next_epoch_first = -1;
 		net->iter++;
 		if (shuffle_every > 0 && (net->iter + 1) % shuffle_every == 0 && net->batch_param != SGD) {
 			/* no copy of the previous epoch may still be reading the host batches */
 			if (net->copy_stream != NULL) CB_CHECK(cb200_stream_sync(net->copy_stream));
 			CB_CHECK(cb200_stream_sync(NULL));
 			shuffle_dataset(net, &net->train);
+			shuffled = 1;
 		}
 		set_hyper(net, lr, net->momentum, net->weight_decay);
-		stage_invalidate(net);
+		/* staged copies survive into the next epoch of this call when the host batches cannot have changed in between;
+		 * the last batch of such an epoch prefetches the first batch of the next one */
+		if (i == 0 || shuffled) stage_invalidate(net);
+		if (i + 1 < nb_iter && !(shuffle_every > 0 && (net->iter + 2) % shuffle_every == 0 && net->batch_param != SGD))
+			next_epoch_first = 0;
 		net->is_inference = 0;
 		for (j = 0; j < net->train.nb_batch; j++) {
 			double t_batch = now_s(), batch_error = 0.0;
@@ -667,7 +673,7 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 			const int sample = net->perf_eval && j == 0 && (net->perf_n == 0 || net->iter % 16 == 0);   /* (a sample, not a census) */
 			void *side = net->wgrad_stream;
 			if (sample) { perf_begin_sample(net); net->wgrad_stream = NULL; }
-			train_one_batch(net, &net->train, j, !net->dynamic_load, j + 1 < net->train.nb_batch ? j + 1 : -1);
+			train_one_batch(net, &net->train, j, !net->dynamic_load, j + 1 < net->train.nb_batch ? j + 1 : next_epoch_first);
 			CB_CHECK(cb200_stream_sync(NULL));
 			if (sample) { net->wgrad_stream = side; perf_end_sample(net); }
 			for (k = 0; k < net->length; k++) { batch_error += net->loss_host[k]; total_error += net->loss_host[k]; }
