@@ -927,6 +927,222 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+// ---------------------------------------------------------------- weight gradient of thin 3x3 layers, operands swapped
+// For layers with few channels on large maps (Darknet19 layers 2, 3, 5: 32 -> 64 channels at 224 x 224, 64 -> 128 at
+// 112 x 112) the kernel above is bound by shared-memory bandwidth, not by the tensor pipe: with M = output channels it
+// issues one 128 x C x 16 MMA per tap and 16-pixel step, each re-reading the dy slab (for 64 filters half of its 128 rows
+// are padding): 9 MMAs and 45 KB of shared-memory reads per 16 pixels for C = 32 (measured 24 % tensor activity).
+// Here the roles are swapped: M = (filter tap, input channel) - the x tiles of consecutive taps sit one after the other
+// in shared memory, so 128 / C of them are the channel slabs of ONE MN-major A operand (LBO = tile size; a slab past
+// the CTA's last tap is whatever follows and is ignored) - and N = the real output channels.  C = 32: 3 MMAs of
+// 128 x 64 x 16 and 18 KB of reads per 16 pixels (914 -> 414 us on layer 2).  C = 64: the 9 x 64 x 128 FP32 accumulators
+// exceed TMEM, so taps 0-4 and 5-8 go to two groups of CTAs sized 3 : 2 like their MMA counts.
+struct WswapParams {
+	WgradParams g;               // pixel tiling, taps, gradient pointer (tiles_per_split / splits unused)
+	int ctas0, tps0, tps1;       // CTAs [0, ctas0) take taps [0, taps0) with tps0 pixel tiles each, the rest taps [taps0, 9) with tps1
+	int taps0;
+};
+
+template <int C, int NF>
+struct WswapCfg {
+	static constexpr int KPIX = 64;
+	static constexpr int SLOTS = 128 / C;                     // taps per MMA
+	static constexpr int MAXT = C == 32 ? 9 : 5;              // taps per CTA
+	static constexpr int NACC = (MAXT + SLOTS - 1) / SLOTS;   // accumulators of NF columns
+	static constexpr int DY_SLAB = KPIX * 128;                // [64 px][64 ch], 128B swizzle
+	static constexpr int DY_BYTES = (NF / 64) * DY_SLAB;
+	static constexpr int X_ROW = C * 2;
+	static constexpr int X_TILE = KPIX * X_ROW;               // one tap: [64 px][C ch]
+	static constexpr int STAGE_BYTES = DY_BYTES + MAXT * X_TILE;
+	static constexpr int STAGES = C == 32 ? 4 : 3;
+	static constexpr int SMEM_DATA = STAGES * STAGE_BYTES + SLOTS * X_TILE;   // + the ignored slabs behind the last tile
+	static constexpr int SMEM_BYTES = ((SMEM_DATA + 1023) & ~1023) + 1024 + 256;
+	static constexpr uint32_t X_LAYOUT = C == 64 ? 2u : 4u;
+	static constexpr uint32_t TMEM_COLS = NACC * NF <= 256 ? 256 : 512;
+	static_assert((C == 32 && NF == 64) || (C == 64 && NF == 128), "instantiated shapes");
+	static_assert(STAGE_BYTES % 1024 == 0, "stage bases stay aligned for the 128B swizzle");
+};
+
+template <int C, int NF>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_swap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WswapParams q) {
+	using Cfg = WswapCfg<C, NF>;
+	const WgradParams& p = q.g;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + ((Cfg::SMEM_DATA + 1023) & ~1023);
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+	const uint32_t done_bar = bar_base + 8u * (2 * Cfg::STAGES);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_dy);
+		prefetch_tensormap(&tmap_x);
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		mbar_init(done_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	// this CTA's taps and pixel tiles
+	const bool first = (int)blockIdx.x < q.ctas0;
+	const int tap0 = C == 32 ? 0 : (first ? 0 : q.taps0);                       // (C = 32: one group of nine taps, all
+	const int ntap = C == 32 ? 9 : (first ? q.taps0 : 9 - q.taps0);             //  loop bounds below fold to constants)
+	const int tps = first ? q.tps0 : q.tps1;
+	const int t_begin = (first ? (int)blockIdx.x : (int)blockIdx.x - q.ctas0) * tps;
+	int t_end = t_begin + tps;
+	if (t_end > p.pix_tiles) t_end = p.pix_tiles;
+	const int n_steps = t_end > t_begin ? t_end - t_begin : 0;
+	const int n_mma = (ntap + Cfg::SLOTS - 1) / Cfg::SLOTS;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			const uint32_t tx_bytes = (uint32_t)(Cfg::DY_BYTES + ntap * Cfg::X_TILE);
+			int tap_dx[Cfg::MAXT], tap_dy[Cfg::MAXT];       // pixel offset of this CTA's taps (registers once unrolled)
+#pragma unroll
+			for (int s = 0; s < Cfg::MAXT; s++) { const int tap = tap0 + s; tap_dy[s] = tap / 3 + p.off_h; tap_dx[s] = tap % 3 + p.off_w; }
+			for (int t = t_begin; t < t_end; t++) {
+				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
+				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+				mbar_wait(empty_bar(stage), phase ^ 1u);
+				const uint32_t sd = smem_base + stage * Cfg::STAGE_BYTES, sx = sd + Cfg::DY_BYTES;
+				mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+#pragma unroll
+				for (int sl = 0; sl < NF / 64; sl++) tma_load_4d(sd + sl * Cfg::DY_SLAB, &tmap_dy, full_bar(stage), sl * 64, w0, h0, n0);
+#pragma unroll
+				for (int s = 0; s < Cfg::MAXT; s++)
+					if (s < ntap) tma_load_4d(sx + s * Cfg::X_TILE, &tmap_x, full_bar(stage), 0, w0 + tap_dx[s], h0 + tap_dy[s], n0);
+				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+			}
+		}
+	} else if (warp == 1) {
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			// both operands MN-major (pixels are the contraction index): 8 pixel rows per K group -> SBO, channel slabs -> LBO
+			const uint64_t da_proto = make_smem_desc(0, Cfg::X_TILE, 8 * Cfg::X_ROW, Cfg::X_LAYOUT);
+			const uint64_t db_proto = make_smem_desc(0, Cfg::DY_SLAB, 1024, 2);
+			const uint32_t idesc = p.idesc;
+			for (int k = 0; k < n_steps; k++) {
+				mbar_wait(full_bar(stage), phase);
+				tc_fence_after();
+				const uint32_t sd = smem_base + stage * Cfg::STAGE_BYTES;
+				const uint64_t db_s = db_proto + (sd >> 4);
+				const uint64_t da_s = da_proto + ((sd + Cfg::DY_BYTES) >> 4);
+				// (fully unrolled: the issuing thread is alone, every descriptor offset below is a compile-time constant)
+#pragma unroll
+				for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
+#pragma unroll
+					for (int i = 0; i < Cfg::NACC; i++)
+						if (i < n_mma)
+							mma_f16_ss(tmem_base + (uint32_t)(i * NF), da_s + ((i * Cfg::SLOTS * Cfg::X_TILE + kk * 16 * Cfg::X_ROW) >> 4),
+							           db_s + ((kk * 16 * 128) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
+				mma_commit(empty_bar(stage));
+				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+			}
+			mma_commit(done_bar);
+		}
+	} else if (n_steps > 0) {
+		const int quad = warp & 3;                // accumulator row quad*32 + lane = (tap slot row / C, channel row % C)
+		mbar_wait(done_bar, 0);
+		tc_fence_after();
+		const int row = quad * 32 + lane, slot_in = row / C, c = row % C;
+		for (int i = 0; i < n_mma; i++) {
+			const int s = i * Cfg::SLOTS + slot_in;
+#pragma unroll 1
+			for (int c0 = 0; c0 < NF; c0 += 32) {
+				uint32_t r[32];
+				tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(i * NF + c0), r);
+				tmem_ld_wait();
+				if (s < ntap && c < p.in_cp) {
+					float* dst = p.grad + (size_t)(tap0 + s) * p.in_cp + c;
+#pragma unroll
+					for (int j = 0; j < 32; j++)
+						if (c0 + j < p.out_c) atomicAdd(dst + (size_t)(c0 + j) * 9 * p.in_cp, __uint_as_float(r[j]));
+				}
+				__syncwarp();
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+static bool wgrad_swap_ok(const cb200_conv_desc* d) {
+	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
+	if (!(d->f_h == 3 && d->f_w == 3 && d->stride_h == 1 && d->stride_w == 1)) return false;
+	if ((long long)d->batch * d->out_h * d->out_w < 64LL * 4 * g_num_sms) return false;      // enough pixel tiles to fill the machine
+	return (in_cp >= 16 && in_cp <= 32 && out_cp >= 16 && out_cp <= 64) || (in_cp > 32 && in_cp <= 64 && out_cp > 64 && out_cp <= 128);
+}
+
+template <int C, int NF>
+static int launch_wgrad_swap(const CUtensorMap& mdy, const CUtensorMap& mx, const WswapParams& q, int ctas, cudaStream_t st) {
+	using Cfg = WswapCfg<C, NF>;
+	static bool configured = false;
+	auto kern = conv_wgrad_swap_kernel<C, NF>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	kern<<<ctas, 192, Cfg::SMEM_BYTES, st>>>(mdy, mx, q);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+static int conv_wgrad_swap(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
+	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
+	const bool wide = in_cp > 32;                 // C = 64, NF = 128, two tap groups
+	WswapParams q;
+	memset(&q, 0, sizeof(q));
+	WgradParams& p = q.g;
+	choose_rect(d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn);
+	CUtensorMap mdy, mx;
+	int rc = make_act_map(&mdy, dy, d->dtype, out_cp, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B, 1);
+	if (rc) return rc;
+	rc = make_act_map(&mx, x, d->dtype, in_cp, d->in_w, d->in_h, d->batch, wide ? 64 : 32, p.tw, p.th, p.tn,
+	                  wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, 1);
+	if (rc) return rc;
+	p.stride = 1;
+	p.W = d->out_w; p.H = d->out_h; p.N = d->batch;
+	p.tiles_w = ceil_div(p.W, p.tw); p.tiles_h = ceil_div(p.H, p.th); p.tiles_n = ceil_div(p.N, p.tn);
+	p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+	p.f_h = 3; p.f_w = 3; p.off_h = -d->pad_h; p.off_w = -d->pad_w;
+	p.out_c = d->out_c; p.in_cp = in_cp;
+	p.grad = w->grad;
+	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, wide ? 128 : 64, 1, 1);
+	int ctas;
+	if (!wide) {
+		q.taps0 = 9;
+		q.ctas0 = g_num_sms < p.pix_tiles ? g_num_sms : p.pix_tiles;
+		q.tps0 = ceil_div(p.pix_tiles, q.ctas0);
+		q.ctas0 = ceil_div(p.pix_tiles, q.tps0);
+		q.tps1 = 0;
+		ctas = q.ctas0;
+	} else {
+		// taps 0-4 (3 MMAs per step) and 5-8 (2 MMAs): CTAs in the same proportion, so both groups finish together
+		q.taps0 = 5;
+		int c0 = (g_num_sms * 3 + 2) / 5, c1 = g_num_sms - c0;
+		if (c0 > p.pix_tiles) c0 = p.pix_tiles;
+		if (c1 > p.pix_tiles) c1 = p.pix_tiles;
+		q.tps0 = ceil_div(p.pix_tiles, c0); q.ctas0 = ceil_div(p.pix_tiles, q.tps0);
+		q.tps1 = ceil_div(p.pix_tiles, c1);
+		ctas = q.ctas0 + ceil_div(p.pix_tiles, q.tps1);
+	}
+	if (cudaMemsetAsync(w->grad, 0, sizeof(float) * (size_t)d->out_c * 9 * in_cp, st) != cudaSuccess) { set_error("wgrad memset failed"); return CB200_ERR_CUDA; }
+	if (wide) return launch_wgrad_swap<64, 128>(mdy, mx, q, ctas, st);
+	return launch_wgrad_swap<32, 64>(mdy, mx, q, ctas, st);
+}
+
 bool conv_tc_wgrad_supported(const cb200_conv_desc* d_in) {
 	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	if (!tc_common_ok(d)) return false;
@@ -954,6 +1170,8 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
 
 int conv_wgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
 	const cb200_conv_desc v = tc_view(d_in), *d = &v;
+	static const bool no_swap = getenv("CB200_NO_WGRAD_SWAP") != nullptr;
+	if (!no_swap && wgrad_swap_ok(d)) return conv_wgrad_swap(d, w, x, dy, st);
 	const int in_cp = round8(d->in_c), out_cp = round8(d->out_c);
 	const int taps = d->f_h * d->f_w;
 	const int slab_c = in_cp > 32 ? 64 : (in_cp > 16 ? 32 : 16);

@@ -37,6 +37,13 @@ STRIDED = [
     (4, 24, 12, 32, 3, 1, 1, True),
     (3, 40, 9, 48, 3, 1, 1, True),
     (2, 24, 16, 64, 2, 2, 0, True),
+    # thin 3x3 layers on large maps (>= 4 x 148 pixel tiles): weight gradient with swapped operands (conv_wgrad_swap_kernel:
+    # M = (filter row, input channel), N = filters)
+    (8, 32, 72, 64, 3, 1, 1, True),      # Darknet19 layer 2 channel counts
+    (6, 24, 90, 40, 3, 1, 1, True),      # 24 / 40 channels: slabs wider than the tensors
+    (5, 16, 96, 16, 3, 1, 0, True),      # no padding, 16 channels both sides
+    (4, 64, 100, 128, 3, 1, 1, True),    # Darknet19 layers 3 / 5 channel counts: two tap groups (5 + 4 taps), 64-channel slabs
+    (3, 40, 120, 96, 3, 1, 1, True),     # 40 / 96 channels in the same class
 ]
 
 
@@ -54,7 +61,7 @@ def test_strided_conv_bit_exact(cabi, shape, dtype_name):
     xb = cabi.upload_act(x, dtype, B, C, S, S)
     So = (S + 2 * pad - f) // stride + 1
     y = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
-    assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
+    assert cabi.lib().cb200_last_conv_impl().startswith(b"tcgen05")          # (the halo variant on large stride-1 maps)
     ref, col = co.conv_forward(x, w, False, B, C, S, S, f, stride, pad, 1.0)
     assert np.abs(ref).max() < 256
     assert np.array_equal(y, ref)
@@ -62,7 +69,7 @@ def test_strided_conv_bit_exact(cabi, shape, dtype_name):
     dy = _int_tensor(rng, (N, B, So * So), 0.8)
     dyb = cabi.upload_act(dy, dtype, B, N, So, So)
     dx = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
-    assert (cabi.lib().cb200_last_conv_impl() == b"tcgen05") == tc_dgrad
+    assert cabi.lib().cb200_last_conv_impl().startswith(b"tcgen05") == tc_dgrad
     ref_dx = co.conv_backward_data(dy, w, B, C, S, S, f, stride, pad)
     assert np.abs(ref_dx).max() < 256
     assert np.array_equal(dx, ref_dx)
