@@ -7,6 +7,7 @@
 //     FP64 across threads/blocks), instead of a mean pass followed by a variance pass;
 //   - gamma/beta and their momentum live on the device; the update is a kernel, not a host
 //     loop behind four blocking memcpys (cuda_norm_layer.cu:434-457).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cb200 {
@@ -68,19 +69,18 @@ __device__ __forceinline__ void fold_into_groups(float (&s0)[8], float (&s1)[8],
 // Accumulate, for every channel vector owned by the thread, sum(a) and sum(a*b) over the block's
 // pixel range; b == a gives (sum x, sum x^2), b == x with a == delta gives (sum d, sum d*x).
 // ws layout: double [batch][nb_group][2].
+// (vbx, b) = the block's pixel range and sample: blockIdx of the plain kernels, a virtual block of the pipelined ones
 template <typename T, bool TWO_INPUTS>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double* __restrict__ ws, NormGeom g) {
-	extern __shared__ float sm_acc[];    // [nb_group][2] block-level partial sums
+__device__ __forceinline__ void norm_stats_body(const T* __restrict__ a_in, const T* __restrict__ b_in, double* __restrict__ ws,
+                                                const NormGeom& g, int vbx, int b, float* sm_acc /* [nb_group][2] block-level partial sums */) {
 	const int cv = g.cp >> 3;
-	const int b = blockIdx.y;
 	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x) sm_acc[i] = 0.0f;
 	__syncthreads();
 
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
-	const int p0 = blockIdx.x * g.ppb;
+	const int p0 = vbx * g.ppb;
 	int p1 = p0 + g.ppb;
 	if (p1 > g.hw) p1 = g.hw;
 
@@ -125,42 +125,54 @@ norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double
 		atomicAdd(&ws[(size_t)b * g.nb_group * 2 + i], (double)sm_acc[i]);
 }
 
+template <typename T, bool TWO_INPUTS>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double* __restrict__ ws, NormGeom g) {
+	extern __shared__ float sm_acc[];
+	norm_stats_body<T, TWO_INPUTS>(a_in, b_in, ws, g, blockIdx.x, blockIdx.y, sm_acc);
+}
+
 // mean = S1/n ; var = S2/n - mean^2  (biased variance, as upstream)
-__global__ void norm_finalize_fwd_kernel(const double* __restrict__ ws, float* __restrict__ mean, float* __restrict__ var, NormGeom g) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= g.batch * g.nb_group) return;
+__device__ __forceinline__ void norm_finalize_fwd_one(const double* ws, float* mean, float* var, const NormGeom& g, int i) {
 	const double n = (double)g.group_size * g.hw;
-	const double m = ws[2 * i] / n;
-	double v = ws[2 * i + 1] / n - m * m;
+	const double m = __ldcg(ws + 2 * i) / n;
+	double v = __ldcg(ws + 2 * i + 1) / n - m * m;
 	if (v < 0.0) v = 0.0;
 	mean[i] = (float)m;
 	var[i] = (float)v;
 }
+__global__ void norm_finalize_fwd_kernel(const double* __restrict__ ws, float* __restrict__ mean, float* __restrict__ var, NormGeom g) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= g.batch * g.nb_group) return;
+	norm_finalize_fwd_one(ws, mean, var, g, i);
+}
 
 // d_beta = sum d ; d_gamma = (sum d*x - mean*sum d) / sqrt(var+eps)
+__device__ __forceinline__ void norm_finalize_bwd_one(const double* ws, const float* mean, const float* var, float* d_gamma, float* d_beta,
+                                                      const NormGeom& g, int i) {
+	const double sd = __ldcg(ws + 2 * i), sdx = __ldcg(ws + 2 * i + 1);
+	d_beta[i] = (float)sd;
+	d_gamma[i] = (float)((sdx - (double)__ldcg(mean + i) * sd) / sqrt((double)__ldcg(var + i) + (double)g.eps));
+}
 __global__ void norm_finalize_bwd_kernel(const double* __restrict__ ws, const float* __restrict__ mean, const float* __restrict__ var,
                                          float* __restrict__ d_gamma, float* __restrict__ d_beta, NormGeom g) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= g.batch * g.nb_group) return;
-	const double sd = ws[2 * i], sdx = ws[2 * i + 1];
-	d_beta[i] = (float)sd;
-	d_gamma[i] = (float)((sdx - (double)mean[i] * sd) / sqrt((double)var[i] + (double)g.eps));
+	norm_finalize_bwd_one(ws, mean, var, d_gamma, d_beta, g, i);
 }
 
 // Apply kernels: same thread -> (channel vector, pixel lane) mapping as the statistics kernel, one sample per
 // blockIdx.y.  A thread keeps ONE channel vector, so the per-channel affine constants are computed once outside
 // the pixel loop and the loop body is: 128-bit load(s), 8 FMAs, 128-bit store - no integer division, several loads in flight.
 template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  const float* __restrict__ mean, const float* __restrict__ var, NormGeom g) {
+__device__ __forceinline__ void norm_apply_body(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* mean, const float* var, const NormGeom& g, int vbx, int b) {
 	const int cv = g.cp >> 3;
-	const int b = blockIdx.y;
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
 	if (lane_p >= lanes_p) return;
-	const int p0 = blockIdx.x * g.ppb;
+	const int p0 = vbx * g.ppb;
 	int p1 = p0 + g.ppb;
 	if (p1 > g.hw) p1 = g.hw;
 	const bool dead = b >= g.length;
@@ -174,9 +186,9 @@ norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
 			if (ch < g.c && !dead) {
 				const int grp = ch / g.group_size;
 				if (grp < g.nb_group - g.set_off) {
-					const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
+					const float rstd = 1.0f / sqrtf(__ldcg(var + b * g.nb_group + grp) + g.eps);
 					sc[j] = gamma[grp] * rstd;
-					sh[j] = beta[grp] - mean[b * g.nb_group + grp] * sc[j];
+					sh[j] = beta[grp] - __ldcg(mean + b * g.nb_group + grp) * sc[j];
 				} else sc[j] = 1.0f;
 			}
 		}
@@ -199,53 +211,75 @@ norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
 	}
 }
 
-// dx = gamma*rstd/n * (n*d - d_beta - xhat*d_gamma), then the previous layer's deriv hook on x
 template <typename T>
 __global__ void __launch_bounds__(NORM_THREADS)
-norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
-                      const float* __restrict__ mean, const float* __restrict__ var,
-                      const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                      cb200_activ prev_activ, float* __restrict__ colsum, NormGeom g) {
-	extern __shared__ float cs_acc[];          // [cp] per-block column sums of dx (only when colsum != nullptr)
-	const int cv = g.cp >> 3;
-	const int b = blockIdx.y;
-	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
-	const int lanes_p = NORM_THREADS / lanes_c;
-	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
-	if (colsum != nullptr) {
-		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
-		__syncthreads();
-	}
-	const bool active_thread = lane_p < lanes_p;
-	const int p0 = blockIdx.x * g.ppb;
-	int p1 = p0 + g.ppb;
-	if (p1 > g.hw) p1 = g.hw;
+norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ mean, const float* __restrict__ var, NormGeom g) {
+	norm_apply_body<T>(x, y, gamma, beta, mean, var, g, blockIdx.x, blockIdx.y);
+}
+
+// per-channel constants of the backward apply: dx = k0*(n*d - d_beta - (x - mu)*rstd*d_gamma) rewritten per channel as
+// ca*d + cx*x + cc; pass-through groups (set_off): ca = 1; dead samples / pad channels: all zero.  The statistics may
+// have been written earlier in the same (pipelined) kernel by another CTA: they are read through L2 (__ldcg).
+__device__ __forceinline__ void bwd_constants(const NormGeom& g, int b, int v, const float* __restrict__ gamma, const float* mean, const float* var,
+                                              const float* d_gamma, const float* d_beta, float (&ca)[8], float (&cx)[8], float (&cc)[8]) {
 	const bool dead = b >= g.length;
 	const float n = (float)(g.group_size * g.hw);
 	const float inv_n = 1.0f / n;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int ch = v * 8 + j;
+		ca[j] = 0.0f; cx[j] = 0.0f; cc[j] = 0.0f;
+		if (ch < g.c && !dead) {
+			const int grp = ch / g.group_size;
+			if (grp < g.nb_group - g.set_off) {
+				const int s = b * g.nb_group + grp;
+				const float rstd = 1.0f / sqrtf(__ldcg(var + s) + g.eps);
+				const float k0 = inv_n * gamma[grp] * rstd;
+				const float dg = __ldcg(d_gamma + s);
+				ca[j] = k0 * n;
+				cx[j] = -k0 * rstd * dg;
+				cc[j] = k0 * (__ldcg(mean + s) * rstd * dg - __ldcg(d_beta + s));
+			} else ca[j] = 1.0f;
+		}
+	}
+}
+
+// a thread's column sums of dx -> the CTA's shared accumulators (lanes that own the same channel vector first)
+__device__ __forceinline__ void fold_colsum(float (&csum)[8], int v, int lanes_c, bool active_thread, float* cs_acc) {
+	bool writer = active_thread;
+	if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+			for (int off = lanes_c; off < 32; off <<= 1) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], off);
+		writer = (threadIdx.x & 31) < lanes_c;
+	}
+	if (writer) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) atomicAdd(&cs_acc[v * 8 + j], csum[j]);
+	}
+}
+
+// dx = gamma*rstd/n * (n*d - d_beta - xhat*d_gamma), then the previous layer's deriv hook on x.
+// cs_acc: [cp] column sums of dx accumulated in shared memory (nullptr: not wanted); zeroed and flushed by the caller.
+template <typename T>
+__device__ __forceinline__ void norm_bwd_apply_body(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
+                                                    const float* mean, const float* var, const float* d_gamma, const float* d_beta,
+                                                    const cb200_activ& prev_activ, float* cs_acc, const NormGeom& g, int vbx, int b) {
+	const int cv = g.cp >> 3;
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	const bool active_thread = lane_p < lanes_p;
+	const int p0 = vbx * g.ppb;
+	int p1 = p0 + g.ppb;
+	if (p1 > g.hw) p1 = g.hw;
 	const int act = prev_activ.type;
 	const float leak = prev_activ.leak, sat = prev_activ.saturation, abeta = prev_activ.beta;
 	constexpr int U = 2;
 	for (int v = lane_c; v < cv; v += lanes_c) {
-		// dx = k0*(n*d - d_beta - (x - mu)*rstd*d_gamma) rewritten per channel as ca*d + cx*x + cc (three constants);
-		// pass-through groups (set_off): ca = 1; dead samples / pad channels: all zero
 		float ca[8], cx[8], cc[8];
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const int ch = v * 8 + j;
-			ca[j] = 0.0f; cx[j] = 0.0f; cc[j] = 0.0f;
-			if (ch < g.c && !dead) {
-				const int grp = ch / g.group_size;
-				if (grp < g.nb_group - g.set_off) {
-					const int s = b * g.nb_group + grp;
-					const float rstd = 1.0f / sqrtf(var[s] + g.eps);
-					const float k0 = inv_n * gamma[grp] * rstd;
-					ca[j] = k0 * n;
-					cx[j] = -k0 * rstd * d_gamma[s];
-					cc[j] = k0 * (mean[s] * rstd * d_gamma[s] - d_beta[s]);
-				} else ca[j] = 1.0f;
-			}
-		}
+		bwd_constants(g, b, v, gamma, mean, var, d_gamma, d_beta, ca, cx, cc);
 		const long long base = (long long)b * g.hw * g.cp + v * 8;
 		float csum[8];
 #pragma unroll
@@ -278,21 +312,23 @@ norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __re
 				for (int j = 0; j < 8; j++) csum[j] += out[j];
 			}
 		}
-		if (colsum != nullptr) {
-			// column sums of the delta just produced = raw bias-column gradient of the preceding convolution
-			bool writer = active_thread;
-			if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
-#pragma unroll
-				for (int j = 0; j < 8; j++)
-					for (int off = lanes_c; off < 32; off <<= 1) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], off);
-				writer = (threadIdx.x & 31) < lanes_c;
-			}
-			if (writer) {
-#pragma unroll
-				for (int j = 0; j < 8; j++) atomicAdd(&cs_acc[v * 8 + j], csum[j]);
-			}
-		}
+		// column sums of the delta just produced = raw bias-column gradient of the preceding convolution
+		if (cs_acc != nullptr) fold_colsum(csum, v, lanes_c, active_thread, cs_acc);
 	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
+                      const float* __restrict__ mean, const float* __restrict__ var,
+                      const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
+                      cb200_activ prev_activ, float* __restrict__ colsum, NormGeom g) {
+	extern __shared__ float cs_acc[];          // [cp] per-block column sums of dx (only when colsum != nullptr)
+	if (colsum != nullptr) {
+		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
+		__syncthreads();
+	}
+	norm_bwd_apply_body<T>(x, dy, dx, gamma, mean, var, d_gamma, d_beta, prev_activ, colsum != nullptr ? cs_acc : nullptr, g, blockIdx.x, blockIdx.y);
 	if (colsum != nullptr) {
 		__syncthreads();
 		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
@@ -341,7 +377,7 @@ __device__ __forceinline__ uint32_t map_byte(const uint2& m, int j) { return ((j
 
 // per-channel affine constants of the forward apply (zero for pad channels and samples beyond `length`)
 __device__ __forceinline__ void fwd_constants(const NormGeom& g, int b, int v, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                              const float* __restrict__ mean, const float* __restrict__ var, float (&sc)[8], float (&sh)[8]) {
+                                              const float* mean, const float* var, float (&sc)[8], float (&sh)[8]) {
 	const bool dead = b >= g.length;
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
@@ -350,9 +386,9 @@ __device__ __forceinline__ void fwd_constants(const NormGeom& g, int b, int v, c
 		if (ch < g.c && !dead) {
 			const int grp = ch / g.group_size;
 			if (grp < g.nb_group - g.set_off) {
-				const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
+				const float rstd = 1.0f / sqrtf(__ldcg(var + b * g.nb_group + grp) + g.eps);
 				sc[j] = gamma[grp] * rstd;
-				sh[j] = beta[grp] - mean[b * g.nb_group + grp] * sc[j];
+				sh[j] = beta[grp] - __ldcg(mean + b * g.nb_group + grp) * sc[j];
 			} else sc[j] = 1.0f;
 		}
 	}
@@ -361,17 +397,15 @@ __device__ __forceinline__ void fwd_constants(const NormGeom& g, int b, int v, c
 // y = x*sc + sh rounded to the storage type (what the unfused apply would have stored), then the first strict maximum
 // of the window in scan order (0,0) (0,1) (1,0) (1,1); only the pooled value and its window index are written
 template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ map, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var, FusedGeom f) {
+__device__ __forceinline__ void norm_pool_fwd_body(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ map, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, const float* mean, const float* var, const FusedGeom& f, int vbx, int b) {
 	const NormGeom& g = f.n;
 	const int cv = g.cp >> 3;
-	const int b = blockIdx.y;
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
 	if (lane_p >= lanes_p) return;
-	const int q0 = blockIdx.x * f.ppb_out;
+	const int q0 = vbx * f.ppb_out;
 	int q1 = q0 + f.ppb_out;
 	if (q1 > f.out_hw) q1 = f.out_hw;
 	const long long row = (long long)f.in_w * g.cp;
@@ -409,22 +443,27 @@ norm_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* _
 	}
 }
 
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ map, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var, FusedGeom f) {
+	norm_pool_fwd_body<T>(x, pooled, map, gamma, beta, mean, var, f, blockIdx.x, blockIdx.y);
+}
+
 // backward reductions: the delta of the normalised tensor is the pooled delta at the selected window position and
 // zero elsewhere, so sum(d) and sum(d*x) run over the pooled pixels, reading x at the position the map names
 template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_pool_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, double* __restrict__ ws, FusedGeom f) {
-	extern __shared__ float sm_acc[];
+__device__ __forceinline__ void norm_pool_bwd_stats_body(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map,
+                                                         double* __restrict__ ws, const FusedGeom& f, int vbx, int b, float* sm_acc) {
 	const NormGeom& g = f.n;
 	const int cv = g.cp >> 3;
-	const int b = blockIdx.y;
 	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x) sm_acc[i] = 0.0f;
 	__syncthreads();
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
 	const bool active = lane_p < lanes_p;
-	const int q0 = blockIdx.x * f.ppb_out;
+	const int q0 = vbx * f.ppb_out;
 	int q1 = q0 + f.ppb_out;
 	if (q1 > f.out_hw) q1 = f.out_hw;
 	const long long row = (long long)f.in_w * g.cp;
@@ -457,53 +496,35 @@ norm_pool_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dp, co
 		atomicAdd(&ws[(size_t)b * g.nb_group * 2 + i], (double)sm_acc[i]);
 }
 
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, double* __restrict__ ws, FusedGeom f) {
+	extern __shared__ float sm_acc[];
+	norm_pool_bwd_stats_body<T>(x, dp, map, ws, f, blockIdx.x, blockIdx.y, sm_acc);
+}
+
 // dx of the four input pixels of each window: ca*d + cx*x + cc with d = pooled delta at the selected position, else 0;
 // then the previous layer's derivative hook and the column sums, exactly like norm_bwd_apply_kernel
 template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, T* __restrict__ dx,
-                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ var,
-                           const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                           cb200_activ prev_activ, float* __restrict__ colsum, FusedGeom f) {
-	extern __shared__ float cs_acc[];
+__device__ __forceinline__ void norm_pool_bwd_apply_body(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, T* __restrict__ dx,
+                                                         const float* __restrict__ gamma, const float* mean, const float* var,
+                                                         const float* d_gamma, const float* d_beta, const cb200_activ& prev_activ,
+                                                         float* cs_acc, const FusedGeom& f, int vbx, int b) {
 	const NormGeom& g = f.n;
 	const int cv = g.cp >> 3;
-	const int b = blockIdx.y;
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
 	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
-	if (colsum != nullptr) {
-		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
-		__syncthreads();
-	}
 	const bool active_thread = lane_p < lanes_p;
-	const int q0 = blockIdx.x * f.ppb_out;
+	const int q0 = vbx * f.ppb_out;
 	int q1 = q0 + f.ppb_out;
 	if (q1 > f.out_hw) q1 = f.out_hw;
-	const bool dead = b >= g.length;
-	const float n = (float)(g.group_size * g.hw);
-	const float inv_n = 1.0f / n;
 	const int act = prev_activ.type;
 	const float leak = prev_activ.leak, sat = prev_activ.saturation, abeta = prev_activ.beta;
 	const long long row = (long long)f.in_w * g.cp;
 	for (int v = lane_c; v < cv; v += lanes_c) {
 		float ca[8], cx[8], cc[8];
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const int ch = v * 8 + j;
-			ca[j] = 0.0f; cx[j] = 0.0f; cc[j] = 0.0f;
-			if (ch < g.c && !dead) {
-				const int grp = ch / g.group_size;
-				if (grp < g.nb_group - g.set_off) {
-					const int s = b * g.nb_group + grp;
-					const float rstd = 1.0f / sqrtf(var[s] + g.eps);
-					const float k0 = inv_n * gamma[grp] * rstd;
-					ca[j] = k0 * n;
-					cx[j] = -k0 * rstd * d_gamma[s];
-					cc[j] = k0 * (mean[s] * rstd * d_gamma[s] - d_beta[s]);
-				} else ca[j] = 1.0f;
-			}
-		}
+		bwd_constants(g, b, v, gamma, mean, var, d_gamma, d_beta, ca, cx, cc);
 		const long long xb = (long long)b * g.hw * g.cp + v * 8;
 		const long long ob = (long long)b * f.out_hw * g.cp + v * 8;
 		float csum[8];
@@ -541,24 +562,220 @@ norm_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dp, co
 				for (int j = 0; j < 8; j++) csum[j] += out[j];
 			}
 		}
-		if (colsum != nullptr) {
-			bool writer = active_thread;
-			if (lanes_c < 32 && (lanes_c & (lanes_c - 1)) == 0) {
-#pragma unroll
-				for (int j = 0; j < 8; j++)
-					for (int off = lanes_c; off < 32; off <<= 1) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], off);
-				writer = (threadIdx.x & 31) < lanes_c;
-			}
-			if (writer) {
-#pragma unroll
-				for (int j = 0; j < 8; j++) atomicAdd(&cs_acc[v * 8 + j], csum[j]);
-			}
-		}
+		if (cs_acc != nullptr) fold_colsum(csum, v, lanes_c, active_thread, cs_acc);
 	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, T* __restrict__ dx,
+                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ var,
+                           const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
+                           cb200_activ prev_activ, float* __restrict__ colsum, FusedGeom f) {
+	extern __shared__ float cs_acc[];
+	const NormGeom& g = f.n;
+	if (colsum != nullptr) {
+		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
+		__syncthreads();
+	}
+	norm_pool_bwd_apply_body<T>(x, dp, map, dx, gamma, mean, var, d_gamma, d_beta, prev_activ, colsum != nullptr ? cs_acc : nullptr, f, blockIdx.x, blockIdx.y);
 	if (colsum != nullptr) {
 		__syncthreads();
 		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
 	}
+}
+
+// ---------------------------------------------------------------- statistics -> apply in ONE pipelined launch
+// The two-launch form streams the tensor from HBM twice: once for the statistics, once for the apply.  Here one
+// persistent (cooperative) kernel walks the batch in chunks of a few images sized to stay in L2: every CTA runs
+// "statistics of chunk c" and then "apply of chunk c-1", so that the apply re-reads its chunk from L2 (126 MB) instead
+// of HBM - forward 3 -> 2 passes over HBM, backward 5 -> 3 - and the finalize step and two launches disappear.
+// Hand-over per chunk: each CTA's partial sums are added to the FP64 workspace, thread 0 arrives on the chunk's counter
+// (fence + atomic); the LAST CTA to arrive turns the sums into mean/var (or d_gamma/d_beta) and releases the chunk's
+// ready flag.  A CTA only waits for the flag of the chunk BEFORE the one it just reduced, i.e. for a hand-over that
+// started a whole chunk earlier, so nobody idles unless the CTAs drift by more than a chunk.  All CTAs must be
+// co-resident: the launch is cooperative and the grid is sized from the occupancy query.  A spin that exceeds ~2 s sets
+// the error word and goes on (wrong numbers in a failing test instead of a hung device).
+struct PipeGeom {
+	int batch, k, nchunks;       // images per chunk, chunks
+	int nbx_a, nbx_b;            // virtual blocks per image in the statistics / apply phase
+	unsigned int* sync;          // [nchunks] arrival counters, [nchunks] ready flags, [1] error word
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+	unsigned int v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class Op, int MIN_CTAS>
+__global__ void __launch_bounds__(NORM_THREADS, MIN_CTAS)
+norm_pipeline_kernel(const Op op, const PipeGeom pg) {
+	extern __shared__ float pipe_smem[];
+	__shared__ int s_last;
+	op.begin(pipe_smem);
+	unsigned int* arrive = pg.sync;
+	unsigned int* ready = pg.sync + pg.nchunks;
+	unsigned int* err = pg.sync + 2 * pg.nchunks;
+	for (int c = 0; c <= pg.nchunks; c++) {
+		if (c < pg.nchunks) {
+			const int b0 = c * pg.k, nb = min(pg.k, pg.batch - b0);
+			for (int vb = blockIdx.x; vb < nb * pg.nbx_a; vb += gridDim.x) {
+				const int bi = vb / pg.nbx_a;
+				op.phase_a(vb - bi * pg.nbx_a, b0 + bi, pipe_smem);
+			}
+			__syncthreads();                                  // every thread's workspace atomics are issued
+			if (threadIdx.x == 0) {
+				__threadfence();
+				s_last = atomicAdd(&arrive[c], 1u) == gridDim.x - 1;
+			}
+			__syncthreads();
+			if (s_last) {                                      // block-uniform
+				__threadfence();
+				for (int i = threadIdx.x; i < nb * op.groups(); i += blockDim.x) op.finalize(b0 * op.groups() + i);
+				__threadfence();
+				__syncthreads();
+				if (threadIdx.x == 0) st_release_u32(&ready[c], 1u);
+			}
+		}
+		if (c > 0) {
+			if (threadIdx.x == 0) {
+				const long long t0 = clock64();
+				while (ld_acquire_u32(&ready[c - 1]) == 0u) {
+					__nanosleep(100);
+					if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+				}
+			}
+			__syncthreads();
+			const int b0 = (c - 1) * pg.k, nb = min(pg.k, pg.batch - b0);
+			for (int vb = blockIdx.x; vb < nb * pg.nbx_b; vb += gridDim.x) {
+				const int bi = vb / pg.nbx_b;
+				op.phase_b(vb - bi * pg.nbx_b, b0 + bi, pipe_smem);
+			}
+		}
+	}
+	op.end(pipe_smem);
+}
+
+// shared memory of the pipelined kernels: [2 * nb_group] statistics accumulators, then [cp] column sums of dx
+template <typename T> struct NormFwdOp {
+	const T* x; T* y; const float* gamma; const float* beta; float* mean; float* var; double* ws; NormGeom g;
+	__device__ __forceinline__ int groups() const { return g.nb_group; }
+	__device__ __forceinline__ void begin(float*) const {}
+	__device__ __forceinline__ void end(float*) const {}
+	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_stats_body<T, false>(x, nullptr, ws, g, vbx, b, sm); }
+	__device__ __forceinline__ void finalize(int i) const { norm_finalize_fwd_one(ws, mean, var, g, i); }
+	__device__ __forceinline__ void phase_b(int vbx, int b, float*) const { norm_apply_body<T>(x, y, gamma, beta, mean, var, g, vbx, b); }
+};
+template <typename T> struct NormPoolFwdOp {
+	const T* x; T* pooled; uint8_t* map; const float* gamma; const float* beta; float* mean; float* var; double* ws; FusedGeom f;
+	__device__ __forceinline__ int groups() const { return f.n.nb_group; }
+	__device__ __forceinline__ void begin(float*) const {}
+	__device__ __forceinline__ void end(float*) const {}
+	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_stats_body<T, false>(x, nullptr, ws, f.n, vbx, b, sm); }
+	__device__ __forceinline__ void finalize(int i) const { norm_finalize_fwd_one(ws, mean, var, f.n, i); }
+	__device__ __forceinline__ void phase_b(int vbx, int b, float*) const { norm_pool_fwd_body<T>(x, pooled, map, gamma, beta, mean, var, f, vbx, b); }
+};
+// column sums of dx: accumulated in shared memory over all the CTA's blocks, added to global memory once at the end
+struct ColsumAcc {
+	float* colsum; int c, cp, off;
+	__device__ __forceinline__ float* acc(float* sm) const { return colsum != nullptr ? sm + off : nullptr; }
+	__device__ __forceinline__ void begin(float* sm) const {
+		if (colsum == nullptr) return;
+		for (int i = threadIdx.x; i < cp; i += blockDim.x) sm[off + i] = 0.0f;
+		__syncthreads();
+	}
+	__device__ __forceinline__ void end(float* sm) const {
+		if (colsum == nullptr) return;
+		__syncthreads();
+		for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&colsum[i], sm[off + i]);
+	}
+};
+template <typename T> struct NormBwdOp {
+	const T* x; const T* dy; T* dx; const float* gamma; const float* mean; const float* var; float* d_gamma; float* d_beta;
+	cb200_activ pa; ColsumAcc cs; double* ws; NormGeom g;
+	__device__ __forceinline__ int groups() const { return g.nb_group; }
+	__device__ __forceinline__ void begin(float* sm) const { cs.begin(sm); }
+	__device__ __forceinline__ void end(float* sm) const { cs.end(sm); }
+	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_stats_body<T, true>(dy, x, ws, g, vbx, b, sm); }
+	__device__ __forceinline__ void finalize(int i) const { norm_finalize_bwd_one(ws, mean, var, d_gamma, d_beta, g, i); }
+	__device__ __forceinline__ void phase_b(int vbx, int b, float* sm) const {
+		norm_bwd_apply_body<T>(x, dy, dx, gamma, mean, var, d_gamma, d_beta, pa, cs.acc(sm), g, vbx, b);
+	}
+};
+template <typename T> struct NormPoolBwdOp {
+	const T* x; const T* dp; const uint8_t* map; T* dx; const float* gamma; const float* mean; const float* var; float* d_gamma; float* d_beta;
+	cb200_activ pa; ColsumAcc cs; double* ws; FusedGeom f;
+	__device__ __forceinline__ int groups() const { return f.n.nb_group; }
+	__device__ __forceinline__ void begin(float* sm) const { cs.begin(sm); }
+	__device__ __forceinline__ void end(float* sm) const { cs.end(sm); }
+	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_pool_bwd_stats_body<T>(x, dp, map, ws, f, vbx, b, sm); }
+	__device__ __forceinline__ void finalize(int i) const { norm_finalize_bwd_one(ws, mean, var, d_gamma, d_beta, f.n, i); }
+	__device__ __forceinline__ void phase_b(int vbx, int b, float* sm) const {
+		norm_pool_bwd_apply_body<T>(x, dp, map, dx, gamma, mean, var, d_gamma, d_beta, pa, cs.acc(sm), f, vbx, b);
+	}
+};
+
+// ---- host side of the pipelined launches
+static int env_int(const char* name, int dflt) {
+	const char* e = getenv(name);
+	return (e != nullptr && *e != '\0') ? atoi(e) : dflt;
+}
+// 0: the two-launch kernels (kept as the reference implementation of the same arithmetic, tests compare both)
+static int g_norm_pipeline = -1, g_norm_chunk_kb = 0, g_norm_ctas_per_sm = 0;
+static bool norm_pipeline_on() {
+	if (g_norm_pipeline < 0) {
+		g_norm_pipeline = env_int("CB200_GN_PIPELINE", 1) != 0;
+		if (g_norm_chunk_kb <= 0) g_norm_chunk_kb = env_int("CB200_GN_CHUNK_MB", 12) * 1024;
+		if (g_norm_ctas_per_sm <= 0) g_norm_ctas_per_sm = env_int("CB200_GN_CTAS_PER_SM", 3);
+	}
+	return g_norm_pipeline != 0;
+}
+
+static size_t norm_stats_bytes(const cb200_norm_desc* d) { return sizeof(double) * 2 * (size_t)d->batch * d->nb_group; }
+
+// pixels per virtual block such that one chunk of k images gives every CTA about `per_cta` blocks
+static int pipe_ppb(int hw, int k, int cv, int grid, int per_cta) {
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	long long want = (long long)grid * per_cta;
+	long long ppb = ((long long)hw * k + want - 1) / want;
+	const int min_ppb = lanes_p * 4;
+	if (ppb < min_ppb) ppb = min_ppb;
+	if (ppb > hw) ppb = hw;
+	return (int)ppb;
+}
+
+// chunk = as many images as fit `CB200_GN_CHUNK_MB` of phase-A input (x, or x + dy): two chunks being read plus the
+// previous chunk's output in flight have to stay inside L2
+template <class Op>
+static int launch_pipeline(Op& op, PipeGeom& pg, int* ppb_a, int hw_a, int* ppb_b, int hw_b, int cv, double bytes_per_image,
+                           size_t smem, void* sync_words, cudaStream_t st) {
+	// 3 CTAs of 256 threads per SM (80 registers, a few spilled constants) or 2 (no spills): CB200_GN_CTAS_PER_SM
+	const int want_per_sm = g_norm_ctas_per_sm;
+	const void* kern = want_per_sm >= 3 ? (const void*)norm_pipeline_kernel<Op, 3> : (const void*)norm_pipeline_kernel<Op, 2>;
+	int per_sm = 0;
+	CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NORM_THREADS, smem));
+	if (per_sm > want_per_sm) per_sm = want_per_sm;
+	if (per_sm < 1) { set_error("norm pipeline: kernel does not fit on an SM"); return CB200_ERR_CUDA; }
+	const int grid = g_num_sms * per_sm;
+	const double chunk_bytes = (double)g_norm_chunk_kb * 1024.0;
+	int k = (int)(chunk_bytes / bytes_per_image);
+	if (k < 1) k = 1;
+	if (k > pg.batch) k = pg.batch;
+	pg.k = k;
+	pg.nchunks = (pg.batch + k - 1) / k;
+	*ppb_a = pipe_ppb(hw_a, k, cv, grid, 2);
+	*ppb_b = pipe_ppb(hw_b, k, cv, grid, 2);
+	pg.nbx_a = ceil_div(hw_a, *ppb_a);
+	pg.nbx_b = ceil_div(hw_b, *ppb_b);
+	pg.sync = (unsigned int*)sync_words;
+	void* args[2] = {(void*)&op, (void*)&pg};
+	CB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(NORM_THREADS), args, smem, st));
+	return CB200_OK;
 }
 
 static int fill_geom(const cb200_norm_desc* d, NormGeom& g) {
@@ -574,7 +791,15 @@ using namespace cb200;
 
 extern "C" {
 
-size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d) { return sizeof(double) * 2 * (size_t)d->batch * d->nb_group; }
+// FP64 sums [batch][nb_group][2], then the pipelined kernels' hand-over words (one counter + one flag per chunk, error word)
+size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d) { return norm_stats_bytes(d) + sizeof(unsigned int) * (2 * (size_t)d->batch + 2); }
+
+void cb200_norm_set_pipeline(int on, int chunk_kb, int ctas_per_sm) {
+	norm_pipeline_on();                    // environment defaults first
+	g_norm_pipeline = on != 0;
+	if (chunk_kb > 0) g_norm_chunk_kb = chunk_kb;
+	if (ctas_per_sm > 0) g_norm_ctas_per_sm = ctas_per_sm;
+}
 
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const float* gamma, const float* beta,
                        float* mean, float* var, void* workspace, void* s) {
@@ -587,6 +812,19 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	// algorithmic bytes: read x (stats) + read x + write y = 3 passes over the real elements
 	prof_begin(PROF_NORM, 3.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
+	if (norm_pipeline_on()) {
+		PipeGeom pg; pg.batch = g.batch;
+		void* sync = (char*)workspace + norm_stats_bytes(d);
+		const double per_image = (double)g.hw * g.cp * cb200_dtype_size(d->dtype);
+		CB_DISPATCH_DTYPE(d->dtype, T, {
+			NormFwdOp<T> op{(const T*)x, (T*)y, gamma, beta, mean, var, ws, g};
+			rc = launch_pipeline(op, pg, &op.g.ppb, g.hw, &op.g.ppb, g.hw, g.cp >> 3, per_image, sizeof(float) * 2 * g.nb_group, sync, st);
+		});
+		if (rc) return rc;
+		CB_LAUNCH_CHECK();
+		prof_end(st);
+		return CB200_OK;
+	}
 	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
 	size_t smem = sizeof(float) * 2 * g.nb_group;
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, smem, st>>>((const T*)x, nullptr, ws, g)));
@@ -613,6 +851,22 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	// algorithmic bytes: (dy, x) for the reductions + (dy, x) + write dx = 5 passes
 	prof_begin(PROF_NORM, 5.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
+	if (norm_pipeline_on()) {
+		if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
+		PipeGeom pg; pg.batch = g.batch;
+		void* sync = (char*)workspace + norm_stats_bytes(d);
+		const double per_image = 2.0 * g.hw * g.cp * cb200_dtype_size(d->dtype);
+		const size_t smem_p = sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0));
+		CB_DISPATCH_DTYPE(d->dtype, T, {
+			NormBwdOp<T> op{(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa,
+			                ColsumAcc{dx_colsum, g.c, g.cp, 2 * g.nb_group}, ws, g};
+			rc = launch_pipeline(op, pg, &op.g.ppb, g.hw, &op.g.ppb, g.hw, g.cp >> 3, per_image, smem_p, sync, st);
+		});
+		if (rc) return rc;
+		CB_LAUNCH_CHECK();
+		prof_end(st);
+		return CB200_OK;
+	}
 	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
 	size_t smem = sizeof(float) * 2 * g.nb_group;
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, true><<<grid, NORM_THREADS, smem, st>>>((const T*)dy, (const T*)x, ws, g)));
@@ -656,6 +910,19 @@ int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 	// algorithmic bytes: read x (statistics) + read x + write pooled values and their 1-byte window index
 	prof_begin(PROF_NORM, 2.0 * E * es + 0.25 * E * (es + 1.0), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
+	if (norm_pipeline_on()) {
+		PipeGeom pg; pg.batch = g.batch;
+		void* sync = (char*)workspace + norm_stats_bytes(nd);
+		const double per_image = (double)g.hw * g.cp * es;
+		CB_DISPATCH_DTYPE(nd->dtype, T, {
+			NormPoolFwdOp<T> op{(const T*)x, (T*)pooled, pool_map, gamma, beta, mean, var, ws, f};
+			rc = launch_pipeline(op, pg, &op.f.n.ppb, g.hw, &op.f.ppb_out, f.out_hw, g.cp >> 3, per_image, sizeof(float) * 2 * g.nb_group, sync, st);
+		});
+		if (rc) return rc;
+		CB_LAUNCH_CHECK();
+		prof_end(st);
+		return CB200_OK;
+	}
 	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
 	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>((const T*)x, nullptr, ws, g)));
 	CB_LAUNCH_CHECK();
@@ -684,6 +951,22 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
 	// algorithmic bytes: x for the reductions, x again + dx for the apply, the pooled delta and its map twice
 	prof_begin(PROF_NORM, 3.0 * E * es + 0.5 * E * (es + 1.0), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
+	if (norm_pipeline_on()) {
+		if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
+		PipeGeom pg; pg.batch = g.batch;
+		void* sync = (char*)workspace + norm_stats_bytes(nd);
+		const double per_image = (double)g.hw * g.cp * es + 0.25 * g.hw * g.cp * (es + 1.0);
+		const size_t smem_p = sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0));
+		CB_DISPATCH_DTYPE(nd->dtype, T, {
+			NormPoolBwdOp<T> op{(const T*)x, (const T*)d_pooled, pool_map, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa,
+			                    ColsumAcc{dx_colsum, g.c, g.cp, 2 * g.nb_group}, ws, f};
+			rc = launch_pipeline(op, pg, &op.f.ppb_out, f.out_hw, &op.f.ppb_out, f.out_hw, g.cp >> 3, per_image, smem_p, sync, st);
+		});
+		if (rc) return rc;
+		CB_LAUNCH_CHECK();
+		prof_end(st);
+		return CB200_OK;
+	}
 	dim3 grid_o((unsigned)ceil_div(f.out_hw, f.ppb_out), (unsigned)g.batch);
 	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_stats_kernel<T><<<grid_o, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
 		(const T*)x, (const T*)d_pooled, pool_map, ws, f)));

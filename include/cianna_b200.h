@@ -276,7 +276,12 @@ typedef struct {
 
 /* mean/var: FP32 [batch][nb_group]; gamma/beta: FP32 [nb_group] (device).
  * Replaces cuda_forward_norm_layer (src/cuda/cuda_norm_layer.cu:361-397). */
-size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial sums, caller-owned */
+size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial sums + hand-over words, caller-owned */
+/* The forward / backward entry points below (and the fused norm + pool pair) run statistics and apply as ONE pipelined
+ * cooperative launch over L2-sized chunks of the batch (on = 1, default; env CB200_GN_PIPELINE), or as the
+ * statistics / finalize / apply launches (on = 0): same arithmetic, kept for comparison in tests and profiles.
+ * chunk_kb: phase-A input bytes per chunk (0: keep; default 12 MB, env CB200_GN_CHUNK_MB); ctas_per_sm: 2 or 3 (0: keep). */
+void cb200_norm_set_pipeline(int on, int chunk_kb, int ctas_per_sm);
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y,
                        const float* gamma, const float* beta, float* mean, float* var,
                        void* workspace, void* stream);

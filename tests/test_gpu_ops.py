@@ -324,6 +324,69 @@ def test_group_norm_max_pool_fused_equals_unfused(cabi, cfg, dtype_name):
         assert (m2 != ref_m).mean() < 1e-3      # only exact FP32 ties may resolve differently after rounding
 
 
+@pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
+@pytest.mark.parametrize("cfg", [(7, 32, 24, 16, 0, 7, 96, 3), (5, 64, 16, 16, 0, 4, 40, 2), (9, 24, 12, 8, 1, 9, 16, 3), (3, 136, 10, 8, 0, 3, 4096, 3)])
+def test_group_norm_pipelined_equals_two_launch(cabi, cfg, dtype_name):
+    """The pipelined cooperative launch (statistics of chunk c, apply of chunk c-1; chunk hand-over through counters in
+    the workspace) against the statistics / finalize / apply launches it replaces, plain and fused with the max-pool,
+    forward and backward: chunks of one to a few images, ragged last chunk, dead samples, several blocks per CTA.
+    Same arithmetic per block; only the order of the atomic accumulation differs."""
+    B, C, S, gs, set_off, length, chunk_kb, ctas = cfg
+    dtype = getattr(cabi, dtype_name)
+    tol = TOL_FP32 if dtype_name == "FP32" else TOL_MIXED
+    L = cabi.lib()
+    rng = np.random.default_rng(23)
+    x = (rng.standard_normal((C, B, S * S)) * 1.5 + 0.3).astype(np.float32)
+    G = (C + gs - 1) // gs
+    gamma = (1 + 0.3 * rng.standard_normal(G)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(G)).astype(np.float32)
+    pa = cabi.activ(cabi.RELU)
+    xb = cabi.upload_act(x, dtype, B, C, S, S)
+    So = S // 2
+    dy = rng.standard_normal((C, B, S * S)).astype(np.float32)
+    dy[:, length:, :] = 0
+    dyb = cabi.upload_act(dy, dtype, B, C, S, S)
+    dp = rng.standard_normal((C, B, So * So)).astype(np.float32)
+    dp[:, length:, :] = 0
+    dpb = cabi.upload_act(dp, dtype, B, C, So, So)
+    res = []
+    try:
+        for on in (0, 1):
+            L.cb200_norm_set_pipeline(on, chunk_kb, ctas)
+            n = cabi.NormLayer(dtype, B, C, S, S, gs, set_off, length)
+            n.set_params(gamma, beta)
+            y = cabi.download_act(n.forward(xb), dtype, B, C, S, S)
+            dx = cabi.download_act(n.backward(xb, dyb, pa), dtype, B, C, S, S)
+            st = n.stats()
+            cs = n.colsum.to_numpy(np.float32, (C,))
+            n2 = cabi.NormLayer(dtype, B, C, S, S, gs, set_off, length)
+            n2.set_params(gamma, beta)
+            p2 = cabi.PoolLayer(dtype, B, C, S, S, 2, 2, 0, cabi.POOL_MAX, length=length)
+            yp = cabi.download_act(n2.forward_pool(xb, p2), dtype, B, C, So, So)
+            mp = p2.map_ref_layout()
+            dxp = cabi.download_act(n2.backward_pool(xb, dpb, p2, pa), dtype, B, C, S, S)
+            stp = n2.stats()
+            csp = n2.colsum.to_numpy(np.float32, (C,))
+            res.append((y, dx, st, cs, yp, mp, dxp, stp, csp))
+    finally:
+        L.cb200_norm_set_pipeline(1, 12 * 1024, 3)
+    (y0, dx0, st0, cs0, yp0, mp0, dxp0, stp0, csp0), (y1, dx1, st1, cs1, yp1, mp1, dxp1, stp1, csp1) = res
+    # (mean / var of the two runs may differ in the last bit: a couple of units of the storage type on y)
+    ulp = {"FP32": 2.0 ** -21, "FP16": 2.0 ** -10, "BF16": 2.0 ** -7}[dtype_name]
+    assert rel_err(y1, y0) <= ulp and rel_err(yp1, yp0) <= ulp
+    assert (mp0 != mp1).mean() < 2e-3
+    for a, b in zip(st0 + stp0, st1 + stp1):
+        assert rel_err(b, a) < 1e-5
+    assert rel_err(dx1, dx0) < (1e-5 if dtype_name == "FP32" else tol)
+    assert rel_err(dxp1, dxp0) < (1e-5 if dtype_name == "FP32" else tol)
+    assert rel_err(cs1, cs0) < (1e-4 if dtype_name == "FP32" else tol)
+    assert rel_err(csp1, csp0) < (1e-4 if dtype_name == "FP32" else tol)
+    # and the pipelined forward against the oracle
+    xq = x if dtype_name == "FP32" else cabi.download_act(xb, dtype, B, C, S, S)
+    ref_y, _, _ = co.group_norm_forward(xq, gamma, beta, gs, set_off, length)
+    assert rel_err(y1, ref_y) < tol
+
+
 # geometry: (batch, in_c, height, width, out_c, f, pad, stride)
 FIRST_DIRECT = [
     (4, 3, 16, 20, 32, 3, 1, 1),    # the Darknet19 first layer in small: RGB, 3x3, 32 filters (KP=32, 64B swizzle)
