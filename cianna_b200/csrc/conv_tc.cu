@@ -142,7 +142,9 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int&
 // Eight epilogue warps in two groups of four (one warp per TMEM lane quadrant): group g drains the accumulators of the
 // CTA's tiles g, g+2, g+4, ... so two tiles are in their epilogue at any time while the MMA warp runs up to ACC_STAGES
 // tiles ahead.  tcgen05.ld -> bias + activation (forward) or the previous layer's derivative (dgrad) -> cast -> store.
-template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2>
+// PAIR (cta_group::2 kernels): only the leader CTA's MMA warp waits for drained accumulators, so the epilogue warps of
+// both CTAs arrive on the LEADER's barriers (tempty0 is then a shared::cluster address).
+template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2, bool PAIR = false>
 __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               float* bias_rows, int warp, int lane, int first_warp) {
 	static_assert(NGROUPS <= ACC_STAGES, "an accumulator stage belongs to one epilogue group at a time");
@@ -245,7 +247,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		}
 		tc_fence_before();
 		__syncwarp();
-		if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+		if (lane == 0) { if (PAIR) mbar_arrive_cluster(tempty0 + 8u * acc); else mbar_arrive(tempty0 + 8u * acc); }
 	}
 }
 
@@ -371,6 +373,162 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 	__syncthreads();
 	if (p.cluster) cluster_sync();        // neither CTA leaves while the other may still signal its barriers
 	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2) for the wide-N layers
+// With one SM per tile every K = 16 step of a 128 x 256 MMA reads 4 KB of A + 8 KB of B from shared memory while TMA
+// refills the same 12 KB: 180 B/clk at full tensor rate against the SM's 128 B/clk (the ~70 % ceiling measured on the
+// N >= 256 layers).  Here two SMs run ONE MMA of M = 256: each CTA holds its own M tile of A and HALF of the
+// filter block (its N half), 8 KB read + 8 KB written per step and SM.  The pair takes two M tiles of the same N tile
+// (decode_tile's pair order).  Roles per CTA: warp 0 TMA producer (its A tile and B half; the bytes complete on the
+// LEADER's full barrier), warp 1 allocates TMEM in both CTAs and - in the leader only - issues the MMAs and commits to
+// the barriers of both CTAs, 8 epilogue warps drain the CTA's own 128 accumulator rows and report to the leader.
+// Operand / accumulator placement as checked on the hardware by scripts/exp/cta_pair_probe.cu.
+template <int BN, int BK>
+struct PairCfg {
+	static constexpr int A_BYTES = 128 * BK * 2;
+	static constexpr int B_BYTES = (BN / 2) * BK * 2;                          // this CTA's half of the filter block
+	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4096;
+	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;
+	static constexpr int EPI_GROUPS = 2;
+	static constexpr int THREADS = (2 + 4 * EPI_GROUPS) * 32;
+	static constexpr int TMEM_COLS = ACC_STAGES * BN <= 256 ? 256 : 512;
+	static constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);
+	static constexpr uint32_t SBO = 8 * BK * 2;
+};
+
+template <typename T, int BN, int BK>
+__global__ void __launch_bounds__(PairCfg<BN, BK>::THREADS, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
+	using Cfg = PairCfg<BN, BK>;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };
+	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 8);
+	const uint32_t bias_smem = bar_base + 256u;
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_a);
+		prefetch_tensormap(&tmap_b);
+		// full: the leader's producer arrives once (with the byte count of both CTAs' loads); empty / tfull: one commit of
+		// the leader's MMA thread, multicast to both CTAs; tempty (used in the leader only): 4 epilogue warps of each CTA
+		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+		fence_barrier_init();
+	}
+	if (warp == 1) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+	tc_fence_before();
+	__syncthreads();
+	cluster_sync();                       // the peer's barriers exist before anything is signalled on them
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+	const uint32_t rank = cluster_ctarank();
+
+	const int taps = p.f_h * p.f_w;
+	const int k_iters = taps * p.kc_blocks;
+
+	if (warp == 0) {
+		// ===================== TMA producer (both CTAs) =====================
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			const uint32_t lead_full0 = mapa_rank(full_bar(0), 0);
+			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+				int mt, nt;
+				decode_tile(p, tile, mt, nt);
+				const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+				for (int tap = 0; tap < taps; tap++) {
+					const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
+					for (int cb = 0; cb < p.kc_blocks; cb++) {
+						mbar_wait(empty_bar(stage), phase ^ 1u);
+						const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+						if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+						const uint32_t lead_full = lead_full0 + 8u * stage;
+						tma_load_4d_pair(sa, &tmap_a, lead_full, cb * BK, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
+						tma_load_3d_pair(sb, &tmap_b, lead_full, cb * BK, tap + p.w_tap0, nt * BN + (int)rank * (BN / 2));
+						if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===================== MMA issuer (leader CTA only) =====================
+		if (lane == 0 && rank == 0) {
+			int stage = 0; uint32_t phase = 0;
+			int acc = 0; uint32_t acc_phase = 0;
+			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
+			const uint32_t idesc = p.idesc;                  // M = 256
+			const int num_tiles = p.num_tiles;
+			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+				for (int k = 0; k < k_iters; k++) {
+					mbar_wait(full_bar(stage), phase);
+					tc_fence_after();
+					const uint64_t da = desc_proto + ((smem_base + (uint32_t)(stage * Cfg::STAGE_BYTES)) >> 4);
+					const uint64_t db = da + (Cfg::A_BYTES >> 4);
+#pragma unroll
+					for (int kk = 0; kk < BK / 16; kk++)
+						mma_f16_ss_pair(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+					mma_commit_pair(empty_bar(stage), (uint16_t)3);      // frees the slot in both CTAs
+					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+				}
+				mma_commit_pair(tfull_bar(acc), (uint16_t)3);           // both CTAs' accumulator halves are complete
+				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+			}
+		}
+	} else {
+		// ===================== epilogue warps (both CTAs: their own 128 rows) =====================
+		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+		epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS, true>(p, tmem_base, tfull_bar(0), mapa_rank(tempty_bar(0), 0), bias_rows, warp, lane, 2);
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	cluster_sync();                       // neither CTA leaves while the other may still signal its barriers / read its smem
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); }
+}
+
+template <typename T, int BN, int BK>
+static int launch_igemm_pair(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, cudaStream_t st) {
+	using Cfg = PairCfg<BN, BK>;
+	static bool configured = false;
+	static int max_clusters = -1;
+	auto kern = conv_igemm_pair_kernel<T, BN, BK>;
+	if (!configured) {
+		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
+		}
+		configured = true;
+	}
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+	if (max_clusters < 0) {
+		cfg.gridDim = dim3((unsigned)(g_num_sms & ~1));
+		int n = 0;
+		if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = g_num_sms / 2 - 2;
+		max_clusters = n;
+	}
+	int grid = 2 * max_clusters;
+	if (grid > p.num_tiles) grid = p.num_tiles;              // (num_tiles is even in pair order)
+	cfg.gridDim = dim3((unsigned)grid);
+	if (cudaLaunchKernelEx(&cfg, kern, ma, mb, p) != cudaSuccess) { set_error("cluster launch of conv_igemm_pair_kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return CB200_ERR_CUDA; }
+	g_launches++;
+	return CB200_OK;
 }
 
 template <typename T, int BN, int BK>
@@ -624,6 +782,7 @@ static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CU
 
 extern const char* g_last_conv_impl;
 int g_enable_cluster = 0;   // cb200_force_simt bit 2: 2-CTA multicast variant of conv_igemm_kernel (off by default, see run_igemm)
+int g_enable_pair = 0;      // cb200_force_simt bit 3 / env CB200_CTA_PAIR: cta_group::2 kernel for the wide-N layers (conv_igemm_pair_kernel)
 int g_disable_halo = 0;     // test hook (cb200_force_simt bit 1): route everything through the per-tap kernel
 
 // Decide whether the layer goes to the halo kernel and, if so, fill its tiling; returns the dynamic smem size or 0.
@@ -700,6 +859,8 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	// reads the whole B block).  Lifting it takes cta_group::2 MMAs (B split between the two SMs) - next round.  The path
 	// stays as a tested option.
 	p.cluster = (g_enable_cluster && dense && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
+	// CTA-pair kernel (cta_group::2: one M = 256 MMA over two SMs, each holding half of the filter block): N tiles of 256
+	if (g_enable_pair && dense && bn == 256 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) p.cluster = 2;
 	if (p.cluster) {
 		p.pairs_m = ceil_div(p.tiles_m, 2);
 		p.num_tiles = 2 * p.pairs_m * p.tiles_nn;
@@ -709,7 +870,12 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	p.f_h = f_h; p.f_w = f_w; p.off_h = off_h; p.off_w = off_w;
 	p.kc_blocks = ceil_div(cin_p, bk);
 	p.n_real = n_real; p.n_pad = n_pad;
-	p.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
+	p.idesc = make_idesc_f16(dtype == CB200_BF16, p.cluster == 2 ? 256 : 128, bn, 0, 0);
+	if (p.cluster == 2) {
+		g_last_conv_impl = "tcgen05-pair";
+		if (dtype == CB200_FP16) return launch_igemm_pair<__half, 256, 64>(ma, mb, p, st);
+		return launch_igemm_pair<__nv_bfloat16, 256, 64>(ma, mb, p, st);
+	}
 	if (dtype == CB200_FP16) return dispatch_igemm<__half>(bn, bk, ma, mb, p, st);
 	return dispatch_igemm<__nv_bfloat16>(bn, bk, ma, mb, p, st);
 }

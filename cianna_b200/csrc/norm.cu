@@ -135,8 +135,8 @@ norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double
 // mean = S1/n ; var = S2/n - mean^2  (biased variance, as upstream)
 __device__ __forceinline__ void norm_finalize_fwd_one(const double* ws, float* mean, float* var, const NormGeom& g, int i) {
 	const double n = (double)g.group_size * g.hw;
-	const double m = __ldcg(ws + 2 * i) / n;
-	double v = __ldcg(ws + 2 * i + 1) / n - m * m;
+	const double m = ws[2 * i] / n;
+	double v = ws[2 * i + 1] / n - m * m;
 	if (v < 0.0) v = 0.0;
 	mean[i] = (float)m;
 	var[i] = (float)v;
@@ -150,9 +150,9 @@ __global__ void norm_finalize_fwd_kernel(const double* __restrict__ ws, float* _
 // d_beta = sum d ; d_gamma = (sum d*x - mean*sum d) / sqrt(var+eps)
 __device__ __forceinline__ void norm_finalize_bwd_one(const double* ws, const float* mean, const float* var, float* d_gamma, float* d_beta,
                                                       const NormGeom& g, int i) {
-	const double sd = __ldcg(ws + 2 * i), sdx = __ldcg(ws + 2 * i + 1);
+	const double sd = ws[2 * i], sdx = ws[2 * i + 1];
 	d_beta[i] = (float)sd;
-	d_gamma[i] = (float)((sdx - (double)__ldcg(mean + i) * sd) / sqrt((double)__ldcg(var + i) + (double)g.eps));
+	d_gamma[i] = (float)((sdx - (double)mean[i] * sd) / sqrt((double)var[i] + (double)g.eps));
 }
 __global__ void norm_finalize_bwd_kernel(const double* __restrict__ ws, const float* __restrict__ mean, const float* __restrict__ var,
                                          float* __restrict__ d_gamma, float* __restrict__ d_beta, NormGeom g) {
@@ -186,9 +186,9 @@ __device__ __forceinline__ void norm_apply_body(const T* __restrict__ x, T* __re
 			if (ch < g.c && !dead) {
 				const int grp = ch / g.group_size;
 				if (grp < g.nb_group - g.set_off) {
-					const float rstd = 1.0f / sqrtf(__ldcg(var + b * g.nb_group + grp) + g.eps);
+					const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
 					sc[j] = gamma[grp] * rstd;
-					sh[j] = beta[grp] - __ldcg(mean + b * g.nb_group + grp) * sc[j];
+					sh[j] = beta[grp] - mean[b * g.nb_group + grp] * sc[j];
 				} else sc[j] = 1.0f;
 			}
 		}
@@ -219,8 +219,8 @@ norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
 }
 
 // per-channel constants of the backward apply: dx = k0*(n*d - d_beta - (x - mu)*rstd*d_gamma) rewritten per channel as
-// ca*d + cx*x + cc; pass-through groups (set_off): ca = 1; dead samples / pad channels: all zero.  The statistics may
-// have been written earlier in the same (pipelined) kernel by another CTA: they are read through L2 (__ldcg).
+// ca*d + cx*x + cc; pass-through groups (set_off): ca = 1; dead samples / pad channels: all zero.  d_gamma / d_beta
+// (forward: mean / var) may point into shared memory (chunked kernels): generic loads, no __restrict__.
 __device__ __forceinline__ void bwd_constants(const NormGeom& g, int b, int v, const float* __restrict__ gamma, const float* mean, const float* var,
                                               const float* d_gamma, const float* d_beta, float (&ca)[8], float (&cx)[8], float (&cc)[8]) {
 	const bool dead = b >= g.length;
@@ -234,12 +234,12 @@ __device__ __forceinline__ void bwd_constants(const NormGeom& g, int b, int v, c
 			const int grp = ch / g.group_size;
 			if (grp < g.nb_group - g.set_off) {
 				const int s = b * g.nb_group + grp;
-				const float rstd = 1.0f / sqrtf(__ldcg(var + s) + g.eps);
+				const float rstd = 1.0f / sqrtf(var[s] + g.eps);
 				const float k0 = inv_n * gamma[grp] * rstd;
-				const float dg = __ldcg(d_gamma + s);
+				const float dg = d_gamma[s];
 				ca[j] = k0 * n;
 				cx[j] = -k0 * rstd * dg;
-				cc[j] = k0 * (__ldcg(mean + s) * rstd * dg - __ldcg(d_beta + s));
+				cc[j] = k0 * (mean[s] * rstd * dg - d_beta[s]);
 			} else ca[j] = 1.0f;
 		}
 	}
@@ -386,9 +386,9 @@ __device__ __forceinline__ void fwd_constants(const NormGeom& g, int b, int v, c
 		if (ch < g.c && !dead) {
 			const int grp = ch / g.group_size;
 			if (grp < g.nb_group - g.set_off) {
-				const float rstd = 1.0f / sqrtf(__ldcg(var + b * g.nb_group + grp) + g.eps);
+				const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
 				sc[j] = gamma[grp] * rstd;
-				sh[j] = beta[grp] - __ldcg(mean + b * g.nb_group + grp) * sc[j];
+				sh[j] = beta[grp] - mean[b * g.nb_group + grp] * sc[j];
 			} else sc[j] = 1.0f;
 		}
 	}
@@ -585,197 +585,180 @@ norm_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dp, co
 	}
 }
 
-// ---------------------------------------------------------------- statistics -> apply in ONE pipelined launch
-// The two-launch form streams the tensor from HBM twice: once for the statistics, once for the apply.  Here one
-// persistent (cooperative) kernel walks the batch in chunks of a few images sized to stay in L2: every CTA runs
-// "statistics of chunk c" and then "apply of chunk c-1", so that the apply re-reads its chunk from L2 (126 MB) instead
-// of HBM - forward 3 -> 2 passes over HBM, backward 5 -> 3 - and the finalize step and two launches disappear.
-// Hand-over per chunk: each CTA's partial sums are added to the FP64 workspace, thread 0 arrives on the chunk's counter
-// (fence + atomic); the LAST CTA to arrive turns the sums into mean/var (or d_gamma/d_beta) and releases the chunk's
-// ready flag.  A CTA only waits for the flag of the chunk BEFORE the one it just reduced, i.e. for a hand-over that
-// started a whole chunk earlier, so nobody idles unless the CTAs drift by more than a chunk.  All CTAs must be
-// co-resident: the launch is cooperative and the grid is sized from the occupancy query.  A spin that exceeds ~2 s sets
-// the error word and goes on (wrong numbers in a failing test instead of a hung device).
-struct PipeGeom {
-	int batch, k, nchunks;       // images per chunk, chunks
-	int nbx_a, nbx_b;            // virtual blocks per image in the statistics / apply phase
-	unsigned int* sync;          // [nchunks] arrival counters, [nchunks] ready flags, [1] error word
+// ---------------------------------------------------------------- statistics -> apply over L2-sized chunks of the batch
+// The two-pass form streams the tensor from HBM twice: once for the statistics, once for the apply.  The chunked form
+// walks the batch in chunks of a few images sized to stay in L2 (126 MB): launch i runs, side by side in ONE grid,
+// the statistics blocks of chunk i and the apply blocks of chunk i-1, so the apply re-reads its chunk from L2 while the
+// statistics blocks stream the next one from HBM - forward 3 -> 2 passes over HBM, backward 5 -> 3 - and the finalize
+// launch disappears: every apply block turns the FP64 sums of its sample into mean / var (or d_gamma / d_beta) in
+// shared memory itself (the first block of a sample also stores them for the backward pass / the optimizer).
+// Dependencies are plain stream order (statistics of chunk i-1 were launch i-1); blocks keep the occupancy of the
+// separate kernels.
+// MEASURED (B200, batch 128, Darknet19 shapes, profiles/r1_gn_chunked_sweep.txt): SLOWER than the two passes at every
+// chunk size (1.3-2x on the 448 / 224 px layers, 1.2-1.5x on the 112 / 56 px ones): a launch that moves 25-75 MB lasts
+// 15-35 us where the bytes alone would take 5-14 us - short grids never reach the steady state in which the two-pass
+// kernels stream at 4.5-5.5 TB/s - so what the apply saves by finding its chunk in L2 is lost several times over.  A
+// persistent cooperative kernel with per-chunk counters was measured before that and lost 2-4x (2-3 CTAs per SM, one
+// batch of loads per phase in flight, hand-over latency exposed: profiles/r1_gn_pipeline_sweep.txt).  The chunked form
+// therefore stays OFF by default (cb200_norm_set_pipeline / CB200_GN_PIPELINE=1), kept as a tested option; getting
+// under two HBM passes needs the tile to stay on chip (TMA-staged slabs per CTA cluster), not a second launch.
+struct ChunkGeom {
+	int nblk_a, nbx_a, a_b0;     // statistics role: blocks in this launch, blocks per sample, first sample
+	int nbx_b, b_b0;             // apply role: blocks per sample, first sample
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-	unsigned int v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <class Op, int MIN_CTAS>
-__global__ void __launch_bounds__(NORM_THREADS, MIN_CTAS)
-norm_pipeline_kernel(const Op op, const PipeGeom pg) {
-	extern __shared__ float pipe_smem[];
-	__shared__ int s_last;
-	op.begin(pipe_smem);
-	unsigned int* arrive = pg.sync;
-	unsigned int* ready = pg.sync + pg.nchunks;
-	unsigned int* err = pg.sync + 2 * pg.nchunks;
-	for (int c = 0; c <= pg.nchunks; c++) {
-		if (c < pg.nchunks) {
-			const int b0 = c * pg.k, nb = min(pg.k, pg.batch - b0);
-			for (int vb = blockIdx.x; vb < nb * pg.nbx_a; vb += gridDim.x) {
-				const int bi = vb / pg.nbx_a;
-				op.phase_a(vb - bi * pg.nbx_a, b0 + bi, pipe_smem);
-			}
-			__syncthreads();                                  // every thread's workspace atomics are issued
-			if (threadIdx.x == 0) {
-				__threadfence();
-				s_last = atomicAdd(&arrive[c], 1u) == gridDim.x - 1;
-			}
-			__syncthreads();
-			if (s_last) {                                      // block-uniform
-				__threadfence();
-				for (int i = threadIdx.x; i < nb * op.groups(); i += blockDim.x) op.finalize(b0 * op.groups() + i);
-				__threadfence();
-				__syncthreads();
-				if (threadIdx.x == 0) st_release_u32(&ready[c], 1u);
-			}
-		}
-		if (c > 0) {
-			if (threadIdx.x == 0) {
-				const long long t0 = clock64();
-				while (ld_acquire_u32(&ready[c - 1]) == 0u) {
-					__nanosleep(100);
-					if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
-				}
-			}
-			__syncthreads();
-			const int b0 = (c - 1) * pg.k, nb = min(pg.k, pg.batch - b0);
-			for (int vb = blockIdx.x; vb < nb * pg.nbx_b; vb += gridDim.x) {
-				const int bi = vb / pg.nbx_b;
-				op.phase_b(vb - bi * pg.nbx_b, b0 + bi, pipe_smem);
-			}
-		}
+// statistics of sample b -> shared memory [mean | var] (forward) ; the first block of the sample keeps them for backward
+__device__ __forceinline__ void chunk_finalize_fwd(const double* ws, float* mean, float* var, const NormGeom& g, int b, bool keep, float* sm) {
+	const double n = (double)g.group_size * g.hw;
+	for (int i = threadIdx.x; i < g.nb_group; i += blockDim.x) {
+		const int s = b * g.nb_group + i;
+		const double m = ws[2 * s] / n;
+		double v = ws[2 * s + 1] / n - m * m;
+		if (v < 0.0) v = 0.0;
+		sm[i] = (float)m;
+		sm[g.nb_group + i] = (float)v;
+		if (keep) { mean[s] = (float)m; var[s] = (float)v; }
 	}
-	op.end(pipe_smem);
+	__syncthreads();
+}
+// sums of sample b -> shared memory [d_gamma | d_beta] (backward); the first block stores them for the optimizer
+__device__ __forceinline__ void chunk_finalize_bwd(const double* ws, const float* mean, const float* var, float* d_gamma, float* d_beta,
+                                                   const NormGeom& g, int b, bool keep, float* sm) {
+	for (int i = threadIdx.x; i < g.nb_group; i += blockDim.x) {
+		const int s = b * g.nb_group + i;
+		const double sd = ws[2 * s], sdx = ws[2 * s + 1];
+		const float db = (float)sd;
+		const float dg = (float)((sdx - (double)mean[s] * sd) / sqrt((double)var[s] + (double)g.eps));
+		sm[i] = dg;
+		sm[g.nb_group + i] = db;
+		if (keep) { d_gamma[s] = dg; d_beta[s] = db; }
+	}
+	__syncthreads();
 }
 
-// shared memory of the pipelined kernels: [2 * nb_group] statistics accumulators, then [cp] column sums of dx
-template <typename T> struct NormFwdOp {
-	const T* x; T* y; const float* gamma; const float* beta; float* mean; float* var; double* ws; NormGeom g;
-	__device__ __forceinline__ int groups() const { return g.nb_group; }
-	__device__ __forceinline__ void begin(float*) const {}
-	__device__ __forceinline__ void end(float*) const {}
-	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_stats_body<T, false>(x, nullptr, ws, g, vbx, b, sm); }
-	__device__ __forceinline__ void finalize(int i) const { norm_finalize_fwd_one(ws, mean, var, g, i); }
-	__device__ __forceinline__ void phase_b(int vbx, int b, float*) const { norm_apply_body<T>(x, y, gamma, beta, mean, var, g, vbx, b); }
-};
-template <typename T> struct NormPoolFwdOp {
-	const T* x; T* pooled; uint8_t* map; const float* gamma; const float* beta; float* mean; float* var; double* ws; FusedGeom f;
-	__device__ __forceinline__ int groups() const { return f.n.nb_group; }
-	__device__ __forceinline__ void begin(float*) const {}
-	__device__ __forceinline__ void end(float*) const {}
-	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_stats_body<T, false>(x, nullptr, ws, f.n, vbx, b, sm); }
-	__device__ __forceinline__ void finalize(int i) const { norm_finalize_fwd_one(ws, mean, var, f.n, i); }
-	__device__ __forceinline__ void phase_b(int vbx, int b, float*) const { norm_pool_fwd_body<T>(x, pooled, map, gamma, beta, mean, var, f, vbx, b); }
-};
-// column sums of dx: accumulated in shared memory over all the CTA's blocks, added to global memory once at the end
-struct ColsumAcc {
-	float* colsum; int c, cp, off;
-	__device__ __forceinline__ float* acc(float* sm) const { return colsum != nullptr ? sm + off : nullptr; }
-	__device__ __forceinline__ void begin(float* sm) const {
-		if (colsum == nullptr) return;
-		for (int i = threadIdx.x; i < cp; i += blockDim.x) sm[off + i] = 0.0f;
+// shared memory: [2 * nb_group] (block sums of the statistics role, per-sample constants of the apply role), then [cp]
+// column sums of dx in the backward kernels
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_fwd_chunk_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* mean, float* var, double* ws, NormGeom g, ChunkGeom cg) {
+	extern __shared__ float sm[];
+	if ((int)blockIdx.x < cg.nblk_a) {
+		const int bi = blockIdx.x / cg.nbx_a;
+		norm_stats_body<T, false>(x, nullptr, ws, g, blockIdx.x - bi * cg.nbx_a, cg.a_b0 + bi, sm);
+		return;
+	}
+	const int vb = blockIdx.x - cg.nblk_a, bi = vb / cg.nbx_b, vbx = vb - bi * cg.nbx_b, b = cg.b_b0 + bi;
+	chunk_finalize_fwd(ws, mean, var, g, b, vbx == 0, sm);
+	norm_apply_body<T>(x, y, gamma, beta, sm - b * g.nb_group, sm + g.nb_group - b * g.nb_group, g, vbx, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_fwd_chunk_kernel(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ map, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, float* mean, float* var, double* ws, FusedGeom f, ChunkGeom cg) {
+	extern __shared__ float sm[];
+	const NormGeom& g = f.n;
+	if ((int)blockIdx.x < cg.nblk_a) {
+		const int bi = blockIdx.x / cg.nbx_a;
+		norm_stats_body<T, false>(x, nullptr, ws, g, blockIdx.x - bi * cg.nbx_a, cg.a_b0 + bi, sm);
+		return;
+	}
+	const int vb = blockIdx.x - cg.nblk_a, bi = vb / cg.nbx_b, vbx = vb - bi * cg.nbx_b, b = cg.b_b0 + bi;
+	chunk_finalize_fwd(ws, mean, var, g, b, vbx == 0, sm);
+	norm_pool_fwd_body<T>(x, pooled, map, gamma, beta, sm - b * g.nb_group, sm + g.nb_group - b * g.nb_group, f, vbx, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS, 3)
+norm_bwd_chunk_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
+                      const float* __restrict__ mean, const float* __restrict__ var, float* d_gamma, float* d_beta,
+                      cb200_activ prev_activ, float* __restrict__ colsum, double* ws, NormGeom g, ChunkGeom cg) {
+	extern __shared__ float sm[];
+	if ((int)blockIdx.x < cg.nblk_a) {
+		const int bi = blockIdx.x / cg.nbx_a;
+		norm_stats_body<T, true>(dy, x, ws, g, blockIdx.x - bi * cg.nbx_a, cg.a_b0 + bi, sm);
+		return;
+	}
+	const int vb = blockIdx.x - cg.nblk_a, bi = vb / cg.nbx_b, vbx = vb - bi * cg.nbx_b, b = cg.b_b0 + bi;
+	float* cs_acc = colsum != nullptr ? sm + 2 * g.nb_group : nullptr;
+	if (cs_acc != nullptr) for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
+	chunk_finalize_bwd(ws, mean, var, d_gamma, d_beta, g, b, vbx == 0, sm);
+	norm_bwd_apply_body<T>(x, dy, dx, gamma, mean, var, sm - b * g.nb_group, sm + g.nb_group - b * g.nb_group, prev_activ, cs_acc, g, vbx, b);
+	if (cs_acc != nullptr) {
 		__syncthreads();
+		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
 	}
-	__device__ __forceinline__ void end(float* sm) const {
-		if (colsum == nullptr) return;
-		__syncthreads();
-		for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&colsum[i], sm[off + i]);
-	}
-};
-template <typename T> struct NormBwdOp {
-	const T* x; const T* dy; T* dx; const float* gamma; const float* mean; const float* var; float* d_gamma; float* d_beta;
-	cb200_activ pa; ColsumAcc cs; double* ws; NormGeom g;
-	__device__ __forceinline__ int groups() const { return g.nb_group; }
-	__device__ __forceinline__ void begin(float* sm) const { cs.begin(sm); }
-	__device__ __forceinline__ void end(float* sm) const { cs.end(sm); }
-	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_stats_body<T, true>(dy, x, ws, g, vbx, b, sm); }
-	__device__ __forceinline__ void finalize(int i) const { norm_finalize_bwd_one(ws, mean, var, d_gamma, d_beta, g, i); }
-	__device__ __forceinline__ void phase_b(int vbx, int b, float* sm) const {
-		norm_bwd_apply_body<T>(x, dy, dx, gamma, mean, var, d_gamma, d_beta, pa, cs.acc(sm), g, vbx, b);
-	}
-};
-template <typename T> struct NormPoolBwdOp {
-	const T* x; const T* dp; const uint8_t* map; T* dx; const float* gamma; const float* mean; const float* var; float* d_gamma; float* d_beta;
-	cb200_activ pa; ColsumAcc cs; double* ws; FusedGeom f;
-	__device__ __forceinline__ int groups() const { return f.n.nb_group; }
-	__device__ __forceinline__ void begin(float* sm) const { cs.begin(sm); }
-	__device__ __forceinline__ void end(float* sm) const { cs.end(sm); }
-	__device__ __forceinline__ void phase_a(int vbx, int b, float* sm) const { norm_pool_bwd_stats_body<T>(x, dp, map, ws, f, vbx, b, sm); }
-	__device__ __forceinline__ void finalize(int i) const { norm_finalize_bwd_one(ws, mean, var, d_gamma, d_beta, f.n, i); }
-	__device__ __forceinline__ void phase_b(int vbx, int b, float* sm) const {
-		norm_pool_bwd_apply_body<T>(x, dp, map, dx, gamma, mean, var, d_gamma, d_beta, pa, cs.acc(sm), f, vbx, b);
-	}
-};
+}
 
-// ---- host side of the pipelined launches
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_bwd_chunk_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, T* __restrict__ dx,
+                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ var,
+                           float* d_gamma, float* d_beta, cb200_activ prev_activ, float* __restrict__ colsum, double* ws,
+                           FusedGeom f, ChunkGeom cg) {
+	extern __shared__ float sm[];
+	const NormGeom& g = f.n;
+	if ((int)blockIdx.x < cg.nblk_a) {
+		const int bi = blockIdx.x / cg.nbx_a;
+		norm_pool_bwd_stats_body<T>(x, dp, map, ws, f, blockIdx.x - bi * cg.nbx_a, cg.a_b0 + bi, sm);
+		return;
+	}
+	const int vb = blockIdx.x - cg.nblk_a, bi = vb / cg.nbx_b, vbx = vb - bi * cg.nbx_b, b = cg.b_b0 + bi;
+	float* cs_acc = colsum != nullptr ? sm + 2 * g.nb_group : nullptr;
+	if (cs_acc != nullptr) for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
+	chunk_finalize_bwd(ws, mean, var, d_gamma, d_beta, g, b, vbx == 0, sm);
+	norm_pool_bwd_apply_body<T>(x, dp, map, dx, gamma, mean, var, sm - b * g.nb_group, sm + g.nb_group - b * g.nb_group, prev_activ, cs_acc, f, vbx, b);
+	if (cs_acc != nullptr) {
+		__syncthreads();
+		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
+	}
+}
+
+// ---- host side of the chunked launches
 static int env_int(const char* name, int dflt) {
 	const char* e = getenv(name);
 	return (e != nullptr && *e != '\0') ? atoi(e) : dflt;
 }
-// 0: the two-launch kernels (kept as the reference implementation of the same arithmetic, tests compare both)
-static int g_norm_pipeline = -1, g_norm_chunk_kb = 0, g_norm_ctas_per_sm = 0;
+// on = 0: the statistics / finalize / apply launches over the whole batch (kept as the reference implementation of the
+// same arithmetic; tests compare both)
+static int g_norm_pipeline = -1, g_norm_chunk_kb = 0, g_norm_blocks_per_sm = 0;
 static bool norm_pipeline_on() {
 	if (g_norm_pipeline < 0) {
-		g_norm_pipeline = env_int("CB200_GN_PIPELINE", 1) != 0;
-		if (g_norm_chunk_kb <= 0) g_norm_chunk_kb = env_int("CB200_GN_CHUNK_MB", 12) * 1024;
-		if (g_norm_ctas_per_sm <= 0) g_norm_ctas_per_sm = env_int("CB200_GN_CTAS_PER_SM", 3);
+		g_norm_pipeline = env_int("CB200_GN_PIPELINE", 0) != 0;
+		if (g_norm_chunk_kb <= 0) g_norm_chunk_kb = env_int("CB200_GN_CHUNK_MB", 24) * 1024;
+		if (g_norm_blocks_per_sm <= 0) g_norm_blocks_per_sm = env_int("CB200_GN_BLOCKS_PER_SM", 6);
 	}
 	return g_norm_pipeline != 0;
 }
 
-static size_t norm_stats_bytes(const cb200_norm_desc* d) { return sizeof(double) * 2 * (size_t)d->batch * d->nb_group; }
-
-// pixels per virtual block such that one chunk of k images gives every CTA about `per_cta` blocks
-static int pipe_ppb(int hw, int k, int cv, int grid, int per_cta) {
+// samples per chunk: as many as fit the chunk size in bytes read by the statistics role (x, or x + dy)
+static int chunk_samples(int batch, double bytes_per_sample) {
+	int k = (int)((double)g_norm_chunk_kb * 1024.0 / bytes_per_sample);
+	if (k < 1) k = 1;
+	return k > batch ? batch : k;
+}
+// pixels per block such that one chunk of k samples gives each role about blocks_per_sm blocks per SM
+static int chunk_ppb(int hw, int k, int cv) {
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
-	long long want = (long long)grid * per_cta;
+	const long long want = (long long)g_num_sms * g_norm_blocks_per_sm;
 	long long ppb = ((long long)hw * k + want - 1) / want;
 	const int min_ppb = lanes_p * 4;
 	if (ppb < min_ppb) ppb = min_ppb;
-	if (ppb > hw) ppb = hw;
+	if (ppb > 1024) ppb = 1024;
 	return (int)ppb;
 }
-
-// chunk = as many images as fit `CB200_GN_CHUNK_MB` of phase-A input (x, or x + dy): two chunks being read plus the
-// previous chunk's output in flight have to stay inside L2
-template <class Op>
-static int launch_pipeline(Op& op, PipeGeom& pg, int* ppb_a, int hw_a, int* ppb_b, int hw_b, int cv, double bytes_per_image,
-                           size_t smem, void* sync_words, cudaStream_t st) {
-	// 3 CTAs of 256 threads per SM (80 registers, a few spilled constants) or 2 (no spills): CB200_GN_CTAS_PER_SM
-	const int want_per_sm = g_norm_ctas_per_sm;
-	const void* kern = want_per_sm >= 3 ? (const void*)norm_pipeline_kernel<Op, 3> : (const void*)norm_pipeline_kernel<Op, 2>;
-	int per_sm = 0;
-	CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NORM_THREADS, smem));
-	if (per_sm > want_per_sm) per_sm = want_per_sm;
-	if (per_sm < 1) { set_error("norm pipeline: kernel does not fit on an SM"); return CB200_ERR_CUDA; }
-	const int grid = g_num_sms * per_sm;
-	const double chunk_bytes = (double)g_norm_chunk_kb * 1024.0;
-	int k = (int)(chunk_bytes / bytes_per_image);
-	if (k < 1) k = 1;
-	if (k > pg.batch) k = pg.batch;
-	pg.k = k;
-	pg.nchunks = (pg.batch + k - 1) / k;
-	*ppb_a = pipe_ppb(hw_a, k, cv, grid, 2);
-	*ppb_b = pipe_ppb(hw_b, k, cv, grid, 2);
-	pg.nbx_a = ceil_div(hw_a, *ppb_a);
-	pg.nbx_b = ceil_div(hw_b, *ppb_b);
-	pg.sync = (unsigned int*)sync_words;
-	void* args[2] = {(void*)&op, (void*)&pg};
-	CB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(NORM_THREADS), args, smem, st));
-	return CB200_OK;
+// launch i of nchunks + 1: statistics of chunk i, apply of chunk i - 1
+static bool chunk_launch_geom(int i, int batch, int k, int nbx_a, int nbx_b, ChunkGeom& cg, unsigned& grid) {
+	const int nchunks = (batch + k - 1) / k;
+	if (i > nchunks) return false;
+	const int a_nb = i < nchunks ? (batch - i * k < k ? batch - i * k : k) : 0;
+	const int b_nb = i >= 1 ? (batch - (i - 1) * k < k ? batch - (i - 1) * k : k) : 0;
+	cg.nbx_a = nbx_a; cg.nblk_a = a_nb * nbx_a; cg.a_b0 = i * k;
+	cg.nbx_b = nbx_b; cg.b_b0 = (i - 1) * k;
+	grid = (unsigned)(cg.nblk_a + b_nb * nbx_b);
+	return true;
 }
 
 static int fill_geom(const cb200_norm_desc* d, NormGeom& g) {
@@ -791,14 +774,14 @@ using namespace cb200;
 
 extern "C" {
 
-// FP64 sums [batch][nb_group][2], then the pipelined kernels' hand-over words (one counter + one flag per chunk, error word)
-size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d) { return norm_stats_bytes(d) + sizeof(unsigned int) * (2 * (size_t)d->batch + 2); }
+// FP64 sums [batch][nb_group][2]
+size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d) { return sizeof(double) * 2 * (size_t)d->batch * d->nb_group; }
 
-void cb200_norm_set_pipeline(int on, int chunk_kb, int ctas_per_sm) {
+void cb200_norm_set_pipeline(int on, int chunk_kb, int blocks_per_sm) {
 	norm_pipeline_on();                    // environment defaults first
 	g_norm_pipeline = on != 0;
 	if (chunk_kb > 0) g_norm_chunk_kb = chunk_kb;
-	if (ctas_per_sm > 0) g_norm_ctas_per_sm = ctas_per_sm;
+	if (blocks_per_sm > 0) g_norm_blocks_per_sm = blocks_per_sm;
 }
 
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const float* gamma, const float* beta,
@@ -813,15 +796,15 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	prof_begin(PROF_NORM, 3.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
 	if (norm_pipeline_on()) {
-		PipeGeom pg; pg.batch = g.batch;
-		void* sync = (char*)workspace + norm_stats_bytes(d);
-		const double per_image = (double)g.hw * g.cp * cb200_dtype_size(d->dtype);
-		CB_DISPATCH_DTYPE(d->dtype, T, {
-			NormFwdOp<T> op{(const T*)x, (T*)y, gamma, beta, mean, var, ws, g};
-			rc = launch_pipeline(op, pg, &op.g.ppb, g.hw, &op.g.ppb, g.hw, g.cp >> 3, per_image, sizeof(float) * 2 * g.nb_group, sync, st);
-		});
-		if (rc) return rc;
-		CB_LAUNCH_CHECK();
+		const int k = chunk_samples(g.batch, (double)g.hw * g.cp * cb200_dtype_size(d->dtype));
+		g.ppb = chunk_ppb(g.hw, k, g.cp >> 3);
+		const int nbx = ceil_div(g.hw, g.ppb);
+		ChunkGeom cg; unsigned grid;
+		for (int i = 0; chunk_launch_geom(i, g.batch, k, nbx, nbx, cg, grid); i++) {
+			CB_DISPATCH_DTYPE(d->dtype, T, (norm_fwd_chunk_kernel<T><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
+				(const T*)x, (T*)y, gamma, beta, mean, var, ws, g, cg)));
+			CB_LAUNCH_CHECK();
+		}
 		prof_end(st);
 		return CB200_OK;
 	}
@@ -853,17 +836,16 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
 	if (norm_pipeline_on()) {
 		if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
-		PipeGeom pg; pg.batch = g.batch;
-		void* sync = (char*)workspace + norm_stats_bytes(d);
-		const double per_image = 2.0 * g.hw * g.cp * cb200_dtype_size(d->dtype);
-		const size_t smem_p = sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0));
-		CB_DISPATCH_DTYPE(d->dtype, T, {
-			NormBwdOp<T> op{(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa,
-			                ColsumAcc{dx_colsum, g.c, g.cp, 2 * g.nb_group}, ws, g};
-			rc = launch_pipeline(op, pg, &op.g.ppb, g.hw, &op.g.ppb, g.hw, g.cp >> 3, per_image, smem_p, sync, st);
-		});
-		if (rc) return rc;
-		CB_LAUNCH_CHECK();
+		const int k = chunk_samples(g.batch, 2.0 * g.hw * g.cp * cb200_dtype_size(d->dtype));
+		g.ppb = chunk_ppb(g.hw, k, g.cp >> 3);
+		const int nbx = ceil_div(g.hw, g.ppb);
+		const size_t smem_c = sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0));
+		ChunkGeom cg; unsigned grid;
+		for (int i = 0; chunk_launch_geom(i, g.batch, k, nbx, nbx, cg, grid); i++) {
+			CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_chunk_kernel<T><<<grid, NORM_THREADS, smem_c, st>>>(
+				(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, ws, g, cg)));
+			CB_LAUNCH_CHECK();
+		}
 		prof_end(st);
 		return CB200_OK;
 	}
@@ -911,15 +893,15 @@ int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 	prof_begin(PROF_NORM, 2.0 * E * es + 0.25 * E * (es + 1.0), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
 	if (norm_pipeline_on()) {
-		PipeGeom pg; pg.batch = g.batch;
-		void* sync = (char*)workspace + norm_stats_bytes(nd);
-		const double per_image = (double)g.hw * g.cp * es;
-		CB_DISPATCH_DTYPE(nd->dtype, T, {
-			NormPoolFwdOp<T> op{(const T*)x, (T*)pooled, pool_map, gamma, beta, mean, var, ws, f};
-			rc = launch_pipeline(op, pg, &op.f.n.ppb, g.hw, &op.f.ppb_out, f.out_hw, g.cp >> 3, per_image, sizeof(float) * 2 * g.nb_group, sync, st);
-		});
-		if (rc) return rc;
-		CB_LAUNCH_CHECK();
+		const int k = chunk_samples(g.batch, (double)g.hw * g.cp * es);
+		f.n.ppb = chunk_ppb(g.hw, k, g.cp >> 3);
+		f.ppb_out = chunk_ppb(f.out_hw, k, g.cp >> 3);
+		ChunkGeom cg; unsigned grid;
+		for (int i = 0; chunk_launch_geom(i, g.batch, k, ceil_div(g.hw, g.ppb), ceil_div(f.out_hw, f.ppb_out), cg, grid); i++) {
+			CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_fwd_chunk_kernel<T><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
+				(const T*)x, (T*)pooled, pool_map, gamma, beta, mean, var, ws, f, cg)));
+			CB_LAUNCH_CHECK();
+		}
 		prof_end(st);
 		return CB200_OK;
 	}
@@ -953,17 +935,16 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
 	if (norm_pipeline_on()) {
 		if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
-		PipeGeom pg; pg.batch = g.batch;
-		void* sync = (char*)workspace + norm_stats_bytes(nd);
-		const double per_image = (double)g.hw * g.cp * es + 0.25 * g.hw * g.cp * (es + 1.0);
-		const size_t smem_p = sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0));
-		CB_DISPATCH_DTYPE(nd->dtype, T, {
-			NormPoolBwdOp<T> op{(const T*)x, (const T*)d_pooled, pool_map, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa,
-			                    ColsumAcc{dx_colsum, g.c, g.cp, 2 * g.nb_group}, ws, f};
-			rc = launch_pipeline(op, pg, &op.f.ppb_out, f.out_hw, &op.f.ppb_out, f.out_hw, g.cp >> 3, per_image, smem_p, sync, st);
-		});
-		if (rc) return rc;
-		CB_LAUNCH_CHECK();
+		const int k = chunk_samples(g.batch, (double)g.hw * g.cp * es + 0.25 * g.hw * g.cp * (es + 1.0));
+		f.ppb_out = chunk_ppb(f.out_hw, k, g.cp >> 3);
+		const int nbx = ceil_div(f.out_hw, f.ppb_out);
+		const size_t smem_c = sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0));
+		ChunkGeom cg; unsigned grid;
+		for (int i = 0; chunk_launch_geom(i, g.batch, k, nbx, nbx, cg, grid); i++) {
+			CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_chunk_kernel<T><<<grid, NORM_THREADS, smem_c, st>>>(
+				(const T*)x, (const T*)d_pooled, pool_map, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, ws, f, cg)));
+			CB_LAUNCH_CHECK();
+		}
 		prof_end(st);
 		return CB200_OK;
 	}

@@ -14,6 +14,7 @@ const char* g_last_conv_impl = "none";
 int g_force_simt = 0;
 extern int g_disable_halo;
 extern int g_enable_cluster;
+extern int g_enable_pair;
 
 // ---- opt-in per-kernel-family timing (CUDA event pairs on the launching stream, harvested lazily:
 // replaces the always-on per-layer cudaEventSynchronize of upstream's perf_eval, src/auxil.c:698-766)
@@ -51,7 +52,7 @@ extern "C" {
 const char* cb200_last_error(void) { return g_error; }
 const char* cb200_version(void) { return "cianna_b200 0.1 (sm_100a)"; }
 const char* cb200_last_conv_impl(void) { return g_last_conv_impl; }
-void cb200_force_simt(int on) { g_force_simt = on & 1; g_disable_halo = (on >> 1) & 1; g_enable_cluster = (on >> 2) & 1; }
+void cb200_force_simt(int on) { g_force_simt = on & 1; g_disable_halo = (on >> 1) & 1; g_enable_cluster = (on >> 2) & 1; g_enable_pair = (on >> 3) & 1; }
 long long cb200_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
 void cb200_profile_enable(int on) { g_prof_on = on; }
 int cb200_profile_collect(int family, double* ms, double* work, long long* launches) {

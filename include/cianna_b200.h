@@ -276,12 +276,14 @@ typedef struct {
 
 /* mean/var: FP32 [batch][nb_group]; gamma/beta: FP32 [nb_group] (device).
  * Replaces cuda_forward_norm_layer (src/cuda/cuda_norm_layer.cu:361-397). */
-size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial sums + hand-over words, caller-owned */
-/* The forward / backward entry points below (and the fused norm + pool pair) run statistics and apply as ONE pipelined
- * cooperative launch over L2-sized chunks of the batch (on = 1, default; env CB200_GN_PIPELINE), or as the
- * statistics / finalize / apply launches (on = 0): same arithmetic, kept for comparison in tests and profiles.
- * chunk_kb: phase-A input bytes per chunk (0: keep; default 12 MB, env CB200_GN_CHUNK_MB); ctas_per_sm: 2 or 3 (0: keep). */
-void cb200_norm_set_pipeline(int on, int chunk_kb, int ctas_per_sm);
+size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial sums, caller-owned */
+/* The forward / backward entry points below (and the fused norm + pool pair) run as statistics / finalize / apply launches
+ * over the whole batch (on = 0, default), or walk the batch in L2-sized chunks (on = 1, env CB200_GN_PIPELINE=1): launch i
+ * holds the statistics blocks of chunk i and the apply blocks of chunk i-1, which re-read their chunk from L2 instead of
+ * HBM - same arithmetic, measured slower on B200 (csrc/norm.cu), kept as a tested option.
+ * chunk_kb: bytes read by the statistics blocks of one launch (0: keep; default 24 MB, env CB200_GN_CHUNK_MB);
+ * blocks_per_sm: blocks per SM and role in one launch (0: keep; default 6, env CB200_GN_BLOCKS_PER_SM). */
+void cb200_norm_set_pipeline(int on, int chunk_kb, int blocks_per_sm);
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y,
                        const float* gamma, const float* beta, float* mean, float* var,
                        void* workspace, void* stream);

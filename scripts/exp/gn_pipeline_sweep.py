@@ -1,4 +1,4 @@
-"""Group-norm statistics -> apply: two launches against the pipelined cooperative launch, on the Darknet19-448 layer
+"""Group-norm statistics -> apply: two passes over the whole batch against the chunked launches, on the Darknet19-448 layer
 shapes at batch 128 (FP16).  Prints ms per call (mean of REPS after warm-up, CUDA events on the compute stream) for the
 forward and the backward pass; tensors of the large layers exceed L2, the small ones run back to back as in the step.
 
@@ -15,11 +15,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from cianna_b200 import cabi  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-REPS = 5
+REPS = int(os.environ.get("GN_SWEEP_REPS", "5"))
 # (channels, map size, group size, followed by a 2x2 max-pool)
 SHAPES = [(32, 448, 4, True), (64, 224, 8, True), (128, 112, 8, False), (128, 112, 8, True), (256, 56, 16, False),
           (256, 56, 16, True), (512, 28, 16, False), (1024, 14, 32, False)]
-VARIANTS = [("two-launch", 0, 0, 0)] + [("pipe %2d MB x%d" % (mb, c), 1, mb * 1024, c) for c in (3, 2) for mb in (6, 12, 24, 48)]
+VARIANTS = [("two-pass", 0, 0, 0)] + [("chunk %2d MB x%d" % (mb, c), 1, mb * 1024, c) for c in (2, 1, 3) for mb in (24, 32, 48, 64)]
+# GN_SWEEP_SHAPES=0,1  GN_SWEEP_VARIANTS=0:0,48:2 (chunk MB : blocks per SM and role; 0:0 = two-pass) restrict the run (ncu captures)
+if os.environ.get("GN_SWEEP_SHAPES"):
+    SHAPES = [SHAPES[int(i)] for i in os.environ["GN_SWEEP_SHAPES"].split(",")]
+if os.environ.get("GN_SWEEP_VARIANTS"):
+    VARIANTS = []
+    for v in os.environ["GN_SWEEP_VARIANTS"].split(","):
+        mb, c = (int(t) for t in v.split(":"))
+        VARIANTS.append(("two-pass", 0, 0, 0) if mb == 0 else ("chunk %2d MB x%d" % (mb, c), 1, mb * 1024, c))
 
 
 def timed(L, fn):
@@ -37,6 +45,7 @@ def timed(L, fn):
 
 
 def main():
+    cabi.init_device(0)
     L = cabi.lib()
     L.cb200_event_elapsed_ms.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.cb200_d2d.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
@@ -78,13 +87,12 @@ def main():
             print("%-22s %-14s fwd %7.3f ms (%5.2f TB/s alg)  bwd %7.3f ms (%5.2f TB/s alg)" % (
                 row["shape"], name, tf, bytes_f / tf / 1e9, tb, bytes_b / tb / 1e9), flush=True)
         out.append(row)
-        for b in (xb, x, nl.y, nl.dx):
-            b.free()
+        bufs = [xb, x, nl.y, nl.dx, dpb if pooled else dyb]
         if pooled:
-            dpb.free(); pool.y.free(); pool.dx.free()
-        else:
-            dyb.free()
-    L.cb200_norm_set_pipeline(1, 12 * 1024, 3)
+            bufs += [getattr(pool, a) for a in ("y", "dx", "map") if hasattr(pool, a)]
+        for b in bufs:
+            b.free()
+    L.cb200_norm_set_pipeline(0, 24 * 1024, 6)
     print(json.dumps(out))
 
 

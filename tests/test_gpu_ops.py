@@ -44,7 +44,9 @@ TC_SHAPES = [
     (4, 32, 12, 32, 1, 0),     # 32 -> 32 channels: the shape of a first layer run on patch rows (weight-gradient slab wider than the tensor)
     (2, 16, 9, 24, 3, 1),      # 16-channel operands everywhere
     (65, 64, 28, 128, 1, 0),   # 399 M tiles (odd): enough work for the 2-CTA cluster variant (multicast filter halves, dummy last tile)
-    (49, 64, 28, 256, 3, 1),   # cluster variant with BN=256, 3x3, 301 M tiles
+    (49, 64, 28, 256, 3, 1),   # cluster variant with BN=256, 3x3, 301 M tiles; CTA-pair kernel (forward)
+    (49, 256, 28, 256, 1, 0),  # CTA-pair kernel forward and data gradient (256 channels both sides), odd number of M tiles
+    (50, 192, 28, 512, 1, 0),  # CTA-pair kernel: two N tiles of 256, partial last K block (192 channels = 3 blocks of 64)
 ]
 
 
@@ -91,6 +93,20 @@ def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
         finally:
             cabi.lib().cb200_force_simt(0)
         assert np.array_equal(y2, ref)
+    if B * So * So >= 128 * 2 * 148 and N > 128:
+        # the CTA-pair kernel (cta_group::2, M = 256 over two SMs, half of the filter block per SM): same bits
+        cabi.lib().cb200_force_simt(8)
+        try:
+            y3 = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+            assert cabi.lib().cb200_last_conv_impl() == b"tcgen05-pair"
+            if C > 128:
+                dx3 = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
+                assert cabi.lib().cb200_last_conv_impl() == b"tcgen05-pair"
+        finally:
+            cabi.lib().cb200_force_simt(0)
+        assert np.array_equal(y3, ref)
+        if C > 128:
+            assert np.array_equal(dx3, ref_dx)
     layer.free(); xb.free(); dyb.free()
 
 
@@ -327,10 +343,11 @@ def test_group_norm_max_pool_fused_equals_unfused(cabi, cfg, dtype_name):
 @pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
 @pytest.mark.parametrize("cfg", [(7, 32, 24, 16, 0, 7, 96, 3), (5, 64, 16, 16, 0, 4, 40, 2), (9, 24, 12, 8, 1, 9, 16, 3), (3, 136, 10, 8, 0, 3, 4096, 3)])
 def test_group_norm_pipelined_equals_two_launch(cabi, cfg, dtype_name):
-    """The pipelined cooperative launch (statistics of chunk c, apply of chunk c-1; chunk hand-over through counters in
-    the workspace) against the statistics / finalize / apply launches it replaces, plain and fused with the max-pool,
-    forward and backward: chunks of one to a few images, ragged last chunk, dead samples, several blocks per CTA.
-    Same arithmetic per block; only the order of the atomic accumulation differs."""
+    """The chunked launches (launch i = statistics blocks of chunk i next to apply blocks of chunk i-1, mean / var and
+    d_gamma / d_beta finalised inside the apply blocks) against the statistics / finalize / apply launches over the whole
+    batch, plain and fused with the max-pool, forward and backward: chunks of one to a few samples, ragged last chunk,
+    dead samples, one chunk for the whole batch.  Same arithmetic per block; only the order of the atomic accumulation
+    differs."""
     B, C, S, gs, set_off, length, chunk_kb, ctas = cfg
     dtype = getattr(cabi, dtype_name)
     tol = TOL_FP32 if dtype_name == "FP32" else TOL_MIXED
@@ -369,7 +386,7 @@ def test_group_norm_pipelined_equals_two_launch(cabi, cfg, dtype_name):
             csp = n2.colsum.to_numpy(np.float32, (C,))
             res.append((y, dx, st, cs, yp, mp, dxp, stp, csp))
     finally:
-        L.cb200_norm_set_pipeline(1, 12 * 1024, 3)
+        L.cb200_norm_set_pipeline(0, 24 * 1024, 6)
     (y0, dx0, st0, cs0, yp0, mp0, dxp0, stp0, csp0), (y1, dx1, st1, cs1, yp1, mp1, dxp1, stp1, csp1) = res
     # (mean / var of the two runs may differ in the last bit: a couple of units of the storage type on y)
     ulp = {"FP32": 2.0 ** -21, "FP16": 2.0 ** -10, "BF16": 2.0 ** -7}[dtype_name]
