@@ -782,7 +782,7 @@ static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CU
 
 extern const char* g_last_conv_impl;
 int g_enable_cluster = 0;   // cb200_force_simt bit 2: 2-CTA multicast variant of conv_igemm_kernel (off by default, see run_igemm)
-int g_enable_pair = 0;      // cb200_force_simt bit 3 / env CB200_CTA_PAIR: cta_group::2 kernel for the wide-N layers (conv_igemm_pair_kernel)
+int g_enable_pair = 1;      // cta_group::2 kernel for the wide-N layers (conv_igemm_pair_kernel); cb200_force_simt bit 3 on / bit 4 off, env CB200_CTA_PAIR=0
 int g_disable_halo = 0;     // test hook (cb200_force_simt bit 1): route everything through the per-tap kernel
 
 // Decide whether the layer goes to the halo kernel and, if so, fill its tiling; returns the dynamic smem size or 0.
@@ -1093,6 +1093,151 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+// ---------------------------------------------------------------- weight gradient on a CTA pair (cta_group::2)
+// The wide layers (>= 256 channels on both sides) ran two 128 x 256 x 16 MMAs per 16-pixel step on ONE SM (MF = 2 blocks
+// of output channels sharing the x tile): 24 KB of shared-memory operand reads + 16 KB of TMA writes per 262 tensor
+// clocks = 153 B/clk against the SM's 128 B/clk (measured 60 % tensor activity).  Here the two blocks of output channels
+// sit on two SMs and run ONE M = 256 MMA: each CTA fetches its own dy block and HALF of the x tile's channels
+// (MN-major operands: pixels are the contraction index), up to two taps sharing the dy slabs: 16 KB read + 12 KB written
+// per 262 clocks and SM.  Accumulators: CTA r's TMEM lanes = output channels of block 2 fg + r, 256 columns per tap.
+// grid.x = 2 * (f_groups * c_tiles * tap_groups), cluster (2, 1, 1); grid.y = splits.
+struct WgradPairCfg {
+	static constexpr int KPIX = 64, BNC = 256;
+	static constexpr int SLAB_BYTES = KPIX * 128;                   // [64 pix][64 ch], 128B swizzle
+	static constexpr int A_BYTES = 2 * SLAB_BYTES;                  // this CTA's 128 output channels of dy
+	static constexpr int B_BYTES = 2 * SLAB_BYTES;                  // this CTA's 128 of the tile's 256 input channels, one tap
+	static constexpr int SMEM_DATA = 192 * 1024;
+	static constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
+	using Cfg = WgradPairCfg;
+	constexpr int MAX_STAGES = 8;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + Cfg::SMEM_DATA;
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+	const uint32_t done_bar = bar_base + 8u * (2 * MAX_STAGES);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
+	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t rank = cluster_ctarank();
+
+	const int taps = p.f_h * p.f_w;
+	int job = blockIdx.x >> 1;
+	const int tgi = job % p.tap_groups; job /= p.tap_groups;
+	const int ct = job % p.c_tiles;
+	const int fg = job / p.c_tiles;
+	const int tap0 = tgi * p.tg;
+	const int ntap = min(p.tg, taps - tap0);
+	const uint32_t stage_bytes = (uint32_t)(Cfg::A_BYTES + p.tg * Cfg::B_BYTES);
+	const uint32_t tx_bytes = 2u * (uint32_t)(Cfg::A_BYTES + ntap * Cfg::B_BYTES);      // both CTAs' loads
+	const int stages = p.stages;
+
+	if (threadIdx.x == 0) {
+		prefetch_tensormap(&tmap_dy);
+		prefetch_tensormap(&tmap_x);
+		for (int s = 0; s < stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+		mbar_init(done_bar, 1);
+		fence_barrier_init();
+	}
+	if (warp == 1) { tmem_alloc_pair(tmem_slot, p.tmem_cols); tmem_relinquish_pair(); }
+	tc_fence_before();
+	__syncthreads();
+	cluster_sync();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	const int t_begin = blockIdx.y * p.tiles_per_split;
+	int t_end = t_begin + p.tiles_per_split;
+	if (t_end > p.pix_tiles) t_end = p.pix_tiles;
+	const int n_steps = t_end - t_begin;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int stage = 0; uint32_t phase = 0;
+			const uint32_t lead_full0 = mapa_rank(full_bar(0), 0);
+			const int ch0 = (fg * 2 + (int)rank) * 128;                    // this CTA's output channels
+			const int xc0 = ct * Cfg::BNC + (int)rank * 128;               // this CTA's half of the input-channel tile
+			for (int t = t_begin; t < t_end; t++) {
+				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
+				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+				mbar_wait(empty_bar(stage), phase ^ 1u);
+				const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + Cfg::A_BYTES;
+				if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+				const uint32_t lead_full = lead_full0 + 8u * stage;
+				tma_load_4d_pair(sa, &tmap_dy, lead_full, ch0, w0, h0, n0);
+				tma_load_4d_pair(sa + Cfg::SLAB_BYTES, &tmap_dy, lead_full, ch0 + 64, w0, h0, n0);
+				for (int ti = 0; ti < ntap; ti++) {
+					const int tap = tap0 + ti;
+					const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
+#pragma unroll
+					for (int sl = 0; sl < 2; sl++)
+						tma_load_4d_pair(sb + ti * Cfg::B_BYTES + sl * Cfg::SLAB_BYTES, &tmap_x, lead_full,
+						                 xc0 + sl * 64, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
+				}
+				if (++stage == stages) { stage = 0; phase ^= 1u; }
+			}
+		}
+	} else if (warp == 1) {
+		if (lane == 0 && rank == 0) {
+			int stage = 0; uint32_t phase = 0;
+			const uint64_t d_proto = make_smem_desc(0, Cfg::SLAB_BYTES, 1024, 2);      // MN-major: channel slabs -> LBO, 8 pixel rows -> SBO
+			const uint32_t idesc = p.idesc;                                            // M = 256, N = 256
+			for (int k = 0; k < n_steps; k++) {
+				mbar_wait(full_bar(stage), phase);
+				tc_fence_after();
+				const uint32_t sa = smem_base + stage * stage_bytes;
+				const uint64_t da_s = d_proto + (sa >> 4);
+				uint64_t db_t = d_proto + ((sa + Cfg::A_BYTES) >> 4);
+				const uint32_t accum = k != 0 ? 1u : 0u;
+				uint32_t d_tmem = tmem_base;
+				for (int ti = 0; ti < ntap; ti++) {
+#pragma unroll
+					for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
+						mma_f16_ss_pair(d_tmem, da_s + ((kk * 2048) >> 4), db_t + ((kk * 2048) >> 4), idesc, kk != 0 ? 1u : accum);
+					db_t += Cfg::B_BYTES >> 4;
+					d_tmem += Cfg::BNC;
+				}
+				mma_commit_pair(empty_bar(stage), (uint16_t)3);
+				if (++stage == stages) { stage = 0; phase ^= 1u; }
+			}
+			mma_commit_pair(done_bar, (uint16_t)3);
+		}
+	} else if (n_steps > 0) {
+		const int quad = warp & 3;
+		mbar_wait(done_bar, 0);
+		tc_fence_after();
+		const int f = (fg * 2 + (int)rank) * 128 + quad * 32 + lane;
+		for (int ti = 0; ti < ntap; ti++) {
+			const int tap = tap0 + ti;
+			const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ti * Cfg::BNC);
+#pragma unroll 1
+			for (int c0 = 0; c0 < Cfg::BNC; c0 += 32) {
+				uint32_t r[32];
+				tmem_ld_32x32(t_row + c0, r);
+				tmem_ld_wait();
+				if (f < p.out_c) {
+					float* dst = p.grad + ((size_t)f * taps + tap) * p.in_cp + ct * Cfg::BNC + c0;
+#pragma unroll
+					for (int j = 0; j < 32; j += 4) {
+						if (ct * Cfg::BNC + c0 + j < p.in_cp)
+							asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+							             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+					}
+				}
+				__syncwarp();
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	cluster_sync();
+	if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc_pair(tmem_base, p.tmem_cols); }
+}
+
 // ---------------------------------------------------------------- weight gradient of thin 3x3 layers, operands swapped
 // For layers with few channels on large maps (Darknet19 layers 2, 3, 5: 32 -> 64 channels at 224 x 224, 64 -> 128 at
 // 112 x 112) the kernel above is bound by shared-memory bandwidth, not by the tensor pipe: with M = output channels it
@@ -1349,6 +1494,9 @@ int conv_wgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, cons
 	if (bnc == 128 && mf == 1) tg_cap = 3;
 	if (bnc == 64) tg_cap = 5;
 	if (bnc <= 32) tg_cap = 9;
+	// wide layers: the two blocks of output channels on a CTA pair (conv_wgrad_pair_kernel), up to two taps per pair
+	const bool pair = g_enable_pair && bnc == 256 && mf == 2 && d->stride_w == 1;
+	if (pair) tg_cap = 2;
 	const int tg = taps < tg_cap ? taps : tg_cap;
 	WgradParams p;
 	memset(&p, 0, sizeof(p));
@@ -1365,27 +1513,66 @@ int conv_wgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, cons
 	p.f_h = d->f_h; p.f_w = d->f_w; p.off_h = -d->pad_h; p.off_w = -d->pad_w;
 	p.f_groups = ceil_div(out_cp, 128 * mf); p.c_tiles = ceil_div(in_cp, bnc);
 	p.tg = tg; p.tap_groups = ceil_div(taps, tg);
-	const int stage_bytes = mf * 16384 + tg * 64 * bnc * 2;
-	p.stages = (196 * 1024) / stage_bytes;
+	const int stage_bytes = pair ? WgradPairCfg::A_BYTES + tg * WgradPairCfg::B_BYTES : mf * 16384 + tg * 64 * bnc * 2;
+	p.stages = ((pair ? 192 : 196) * 1024) / stage_bytes;
 	if (p.stages > 8) p.stages = 8;
-	const int acc_cols = mf * tg * bnc;
+	const int acc_cols = pair ? tg * bnc : mf * tg * bnc;
 	p.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
 	const int jobs = p.f_groups * p.c_tiles * p.tap_groups;
-	int splits = ceil_div(g_num_sms * 2, jobs);
+	// Pixel-range splits per job.  These launches last 0.1-0.3 ms with one CTA (pair) per SM (pair of SMs), so whole waves
+	// matter: take the split count that minimises waves x (steps per CTA x cost of a 64-pixel step + epilogue), with the
+	// step bound by the tensor pipe (131 clk per 128 x 256 x 16 MMA) or by the operand bytes it pulls through L2 (~50 B/clk
+	// per SM), and the FP32 red.add epilogue at ~30 B/clk.
 	const int max_splits = ceil_div(p.pix_tiles, 8);
-	if (splits > max_splits) splits = max_splits;
-	if (splits < 1) splits = 1;
+	int splits = 1;
+	{
+		const int slots = pair ? g_num_sms / 2 : g_num_sms;
+		const double mma_clk = 4.0 * 131.0 * bnc / 256.0 * tg * (pair ? 1 : mf);
+		const double step_clk = fmax(mma_clk, (double)stage_bytes / 50.0);
+		const double epi_clk = (pair ? 1 : mf) * tg * 128.0 * bnc * 4.0 / 30.0 + 2000.0;
+		double best = 1e30;
+		for (int sp = 1; sp <= max_splits; sp++) {
+			const int tps = ceil_div(p.pix_tiles, sp);
+			const int real = ceil_div(p.pix_tiles, tps);
+			if (real != sp) continue;
+			const double waves = (double)ceil_div(jobs * sp, slots);
+			const double cost = waves * (tps * step_clk + epi_clk);
+			if (cost < best) { best = cost; splits = sp; }
+		}
+	}
 	p.tiles_per_split = ceil_div(p.pix_tiles, splits);
 	splits = ceil_div(p.pix_tiles, p.tiles_per_split);
 	p.splits = splits;
 	p.out_c = d->out_c; p.in_cp = in_cp;
 	p.grad = w->grad;
-	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, bnc, 1, 1);
+	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, pair ? 256 : 128, bnc, 1, 1);
 	if (p.stages < 2 || acc_cols > 512) { set_error("conv_wgrad_tc: bad tiling (stages %d, tmem %d)", p.stages, acc_cols); return CB200_ERR_UNSUPPORTED; }
 	if (cudaMemsetAsync(w->grad, 0, sizeof(float) * (size_t)d->out_c * taps * in_cp, st) != cudaSuccess) {
 		set_error("wgrad memset failed"); return CB200_ERR_CUDA;
 	}
 	dim3 grid((unsigned)jobs, (unsigned)splits);
+	if (pair) {
+		static bool configured = false;
+		if (!configured) {
+			if (cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradPairCfg::SMEM_BYTES) != cudaSuccess) {
+				set_error("cudaFuncSetAttribute(smem=%d) failed", WgradPairCfg::SMEM_BYTES); return CB200_ERR_CUDA;
+			}
+			configured = true;
+		}
+		cudaLaunchConfig_t cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+		cfg.gridDim = dim3((unsigned)(2 * jobs), (unsigned)splits); cfg.blockDim = dim3(192);
+		cfg.dynamicSmemBytes = WgradPairCfg::SMEM_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+		if (cudaLaunchKernelEx(&cfg, conv_wgrad_pair_kernel, mdy, mx, p) != cudaSuccess) {
+			set_error("cluster launch of conv_wgrad_pair_kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return CB200_ERR_CUDA;
+		}
+		g_launches++;
+		g_last_conv_impl = "tcgen05-pair";
+		return CB200_OK;
+	}
 	if (bnc == 256 && mf == 2) return launch_wgrad<256, 64, 2, 1>(mdy, mx, p, grid, st);
 	if (bnc == 256) return launch_wgrad<256, 64, 1, 2>(mdy, mx, p, grid, st);
 	if (bnc == 128 && mf == 2) return launch_wgrad<128, 64, 2, 2>(mdy, mx, p, grid, st);

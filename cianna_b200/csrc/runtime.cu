@@ -52,7 +52,11 @@ extern "C" {
 const char* cb200_last_error(void) { return g_error; }
 const char* cb200_version(void) { return "cianna_b200 0.1 (sm_100a)"; }
 const char* cb200_last_conv_impl(void) { return g_last_conv_impl; }
-void cb200_force_simt(int on) { g_force_simt = on & 1; g_disable_halo = (on >> 1) & 1; g_enable_cluster = (on >> 2) & 1; g_enable_pair = (on >> 3) & 1; }
+static int g_pair_default = 1;     // env CB200_CTA_PAIR=0: keep the wide-N layers on the one-SM kernel
+void cb200_force_simt(int on) {
+	g_force_simt = on & 1; g_disable_halo = (on >> 1) & 1; g_enable_cluster = (on >> 2) & 1;
+	g_enable_pair = (on & 16) ? 0 : ((on & 8) ? 1 : g_pair_default);
+}
 long long cb200_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
 void cb200_profile_enable(int on) { g_prof_on = on; }
 int cb200_profile_collect(int family, double* ms, double* work, long long* launches) {
@@ -95,6 +99,9 @@ int cb200_init(int device) {
 	// debugging aid: CB200_FORCE_SIMT=1 routes every conv through the generic kernels (see cb200_force_simt)
 	const char* fs = getenv("CB200_FORCE_SIMT");
 	if (fs && fs[0] == '1') g_force_simt = 1;
+	const char* cp = getenv("CB200_CTA_PAIR");
+	g_pair_default = (cp && cp[0] == '0') ? 0 : 1;
+	g_enable_pair = g_pair_default;
 	if (!g_stream) {
 		// the compute stream carries the critical path: highest priority, so that work put on side streams (weight gradients)
 		// only takes the SMs the critical path leaves free

@@ -1,7 +1,6 @@
 #!/bin/bash
-# CTA-pair (cta_group::2) hardware probe, then the bit-exact tests of conv_igemm_pair_kernel (bounded: a hang costs 120 s)
+# full GPU suite, then bench lines with / without the CTA-pair kernels (same box, back to back)
 mkdir -p gpurun_out
-(cd scripts/exp && nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o cta_pair_probe cta_pair_probe.cu -lcuda 2>&1 | tail -3; timeout 60 ./cta_pair_probe) > gpurun_out/cta_pair_probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/cta_pair_probe.log; cat gpurun_out/cta_pair_probe.log
-if grep -q "mode 0 (K-major) K=256: exact" gpurun_out/cta_pair_probe.log; then
-  timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q --tb=short -x -k "address_mapping" > gpurun_out/tests_pair.log 2>&1; tail -15 gpurun_out/tests_pair.log
-fi
+timeout 1200 python -m pytest tests -m gpu -q --tb=short --maxfail=20 > gpurun_out/tests_gpu.log 2>&1; tail -12 gpurun_out/tests_gpu.log
+timeout 600 python bench.py --steps 10 --warmup 3 --batch 128 --no-cpu-baseline > gpurun_out/bench_pair.json 2> gpurun_out/bench_pair.err; tail -c 300 gpurun_out/bench_pair.err; python scripts/bench_summary.py gpurun_out/bench_pair.json
+CB200_CTA_PAIR=0 timeout 600 python bench.py --steps 10 --warmup 3 --batch 128 --no-cpu-baseline > gpurun_out/bench_nopair.json 2> gpurun_out/bench_nopair.err; tail -c 300 gpurun_out/bench_nopair.err; python scripts/bench_summary.py gpurun_out/bench_nopair.json

@@ -47,6 +47,7 @@ TC_SHAPES = [
     (49, 64, 28, 256, 3, 1),   # cluster variant with BN=256, 3x3, 301 M tiles; CTA-pair kernel (forward)
     (49, 256, 28, 256, 1, 0),  # CTA-pair kernel forward and data gradient (256 channels both sides), odd number of M tiles
     (50, 192, 28, 512, 1, 0),  # CTA-pair kernel: two N tiles of 256, partial last K block (192 channels = 3 blocks of 64)
+    (49, 256, 28, 256, 3, 1),  # CTA-pair kernels with 3x3 filters: weight gradient with two taps per pair (last group: one)
 ]
 
 
@@ -66,6 +67,7 @@ def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
     layer.set_weights(w)
     xb = cabi.upload_act(x, dtype, B, C, S, S)
     So = S + 2 * pad - f + 1
+    cabi.lib().cb200_force_simt(16)          # one-SM kernels first (the CTA-pair kernel is checked against the same bits below)
     y = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
     assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
     ref, col = co.conv_forward(x, w, False, B, C, S, S, f, 1, pad, 1.0)
@@ -76,15 +78,25 @@ def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
     dyb = cabi.upload_act(dy, dtype, B, N, So, So)
     dx = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
     assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
+    cabi.lib().cb200_force_simt(0)
     ref_dx = co.conv_backward_data(dy, w, B, C, S, S, f, 1, pad)
     assert np.abs(ref_dx).max() < 256
     assert np.array_equal(dx, ref_dx)
 
     layer.backward_weights(xb, dyb)
     got = layer.grad_ref_layout()
-    assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
+    # (layers with more than 128 channels on both sides: the weight gradient runs on CTA pairs, cta_group::2)
+    assert cabi.lib().cb200_last_conv_impl() == (b"tcgen05-pair" if C > 128 and N > 128 else b"tcgen05")
     ref_g = co.conv_weight_grad(col, dy).astype(np.float32)
     assert np.array_equal(got, ref_g)
+    if C > 128 and N > 128:
+        cabi.lib().cb200_force_simt(16)          # the one-SM weight-gradient kernel on the same tensors
+        try:
+            layer.backward_weights(xb, dyb)
+            assert cabi.lib().cb200_last_conv_impl() == b"tcgen05"
+            assert np.array_equal(layer.grad_ref_layout(), ref_g)
+        finally:
+            cabi.lib().cb200_force_simt(0)
     if B * So * So >= 128 * 2 * 148 and N >= 96:
         # enough M tiles for the optional 2-CTA cluster variant (filter halves multicast to both CTAs): same bits
         cabi.lib().cb200_force_simt(4)

@@ -49,7 +49,7 @@ def test_whole_map_filter_bit_exact(cabi, shape, dtype_name):
     xb = cabi.upload_act(x, dtype, B, C, S, S)
     impl = b"tcgen05" if dtype_name != "FP32" else b"simt"
     y = cabi.download_act(layer.forward(xb), dtype, B, N, 1, 1)
-    assert cabi.lib().cb200_last_conv_impl() == impl
+    assert cabi.lib().cb200_last_conv_impl().startswith(impl)      # (tcgen05 / tcgen05-pair)
     ref, col = co.conv_forward(x, w, False, B, C, S, S, S, 1, 0, 1.0)
     assert np.abs(ref).max() < 256
     assert np.array_equal(y, ref)
@@ -57,13 +57,13 @@ def test_whole_map_filter_bit_exact(cabi, shape, dtype_name):
     dy = _int_tensor(rng, (N, B, 1), 0.8)
     dyb = cabi.upload_act(dy, dtype, B, N, 1, 1)
     dx = cabi.download_act(layer.backward_data(dyb), dtype, B, C, S, S)
-    assert cabi.lib().cb200_last_conv_impl() == impl
+    assert cabi.lib().cb200_last_conv_impl().startswith(impl)      # (tcgen05 / tcgen05-pair)
     ref_dx = co.conv_backward_data(dy, w, B, C, S, S, S, 1, 0)
     assert np.abs(ref_dx).max() < 256
     assert np.array_equal(dx, ref_dx)
 
     layer.backward_weights(xb, dyb)
-    assert cabi.lib().cb200_last_conv_impl() == impl
+    assert cabi.lib().cb200_last_conv_impl().startswith(impl)      # (tcgen05 / tcgen05-pair)
     assert np.array_equal(layer.grad_ref_layout(), co.conv_weight_grad(col, dy).astype(np.float32))
 
     if dtype_name != "FP32":
