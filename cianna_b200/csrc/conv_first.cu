@@ -223,7 +223,11 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 		const int act = p.activ.type, n_real = p.n_real, n_pad = p.n_pad;
 		const float leak = p.activ.leak, sat = p.activ.saturation, beta = p.activ.beta;
 		const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
-			const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		// 0 <= leak <= 1, sat >= 0: z <= 0 ? z*leak : (z > sat ? hi : z) == min(max(z, z*leak), hi) value for value (hi >= z
+		// below the saturation, hi < z above it) - two FMNMX instead of two compares and two selects per element: this
+		// epilogue is bound by the ALU pipe (profiles/r1_conv_first_fwd_full_raw.csv: 65 % busy)
+		const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
+		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
 		for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
 			const int tile = tile0 + it;
 			const int acc = it % Cfg::ACC_STAGES;
@@ -247,13 +251,25 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 					if (!row_ok || col >= n_pad) continue;
 					float o[8];
 #pragma unroll
-					for (int j = 0; j < 8; j++) o[j] = dead ? 0.0f : __uint_as_float(r[v * 8 + j]);
-					if (act == CB200_RELU) {
+					for (int j = 0; j < 8; j++) o[j] = __uint_as_float(r[v * 8 + j]);
+					if (dead) {
 #pragma unroll
-						for (int j = 0; j < 8; j++) {
-							const float z = o[j];
-							const float hi = sat + (z - sat) * leak;
-							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+						for (int j = 0; j < 8; j++) o[j] = 0.0f;
+					} else if (act == CB200_RELU) {
+						if (relu_minmax) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const float z = o[j];
+								const float hi = sat + (z - sat) * leak;
+								o[j] = fminf(fmaxf(z, z * leak), hi);
+							}
+						} else {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const float z = o[j];
+								const float hi = sat + (z - sat) * leak;
+								o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+							}
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll

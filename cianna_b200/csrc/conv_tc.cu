@@ -163,6 +163,8 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const int out_s = p.out_s, out_ox = p.out_ox, out_oy = p.out_oy, OW = p.out_W, OH = p.out_H;
 	const bool mask_tail = act == CB200_RELU || act == CB200_LOGISTIC || act == CB200_SOFTMAX;
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
+	// 0 <= leak <= 1, sat >= 0: z <= 0 ? z*leak : (z > sat ? hi : z) == min(max(z, z*leak), hi) value for value
+	const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
 	float* bs = bias_rows + grp * 256;
 	int it = 0;
 	for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
@@ -210,11 +212,20 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 					const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
 					o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
 					if (act == CB200_RELU) {
+						if (relu_minmax) {
 #pragma unroll
-						for (int j = 0; j < 8; j++) {
-							const float z = o[j];
-							const float hi = sat + (z - sat) * leak;
-							o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+							for (int j = 0; j < 8; j++) {
+								const float z = o[j];
+								const float hi = sat + (z - sat) * leak;
+								o[j] = fminf(fmaxf(z, z * leak), hi);
+							}
+						} else {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								const float z = o[j];
+								const float hi = sat + (z - sat) * leak;
+								o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z);
+							}
 						}
 					} else if (act == CB200_LOGISTIC) {
 #pragma unroll
@@ -783,6 +794,7 @@ static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CU
 extern const char* g_last_conv_impl;
 int g_enable_cluster = 0;   // cb200_force_simt bit 2: 2-CTA multicast variant of conv_igemm_kernel (off by default, see run_igemm)
 int g_enable_pair = 1;      // cta_group::2 kernel for the wide-N layers (conv_igemm_pair_kernel); cb200_force_simt bit 3 on / bit 4 off, env CB200_CTA_PAIR=0
+int g_enable_pair_wgrad = 0;   // conv_wgrad_pair_kernel: off by default (measured 4.03 vs 3.92 ms per step for the family), same bits, env CB200_WGRAD_PAIR=1
 int g_disable_halo = 0;     // test hook (cb200_force_simt bit 1): route everything through the per-tap kernel
 
 // Decide whether the layer goes to the halo kernel and, if so, fill its tiling; returns the dynamic smem size or 0.
@@ -1100,6 +1112,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 // sit on two SMs and run ONE M = 256 MMA: each CTA fetches its own dy block and HALF of the x tile's channels
 // (MN-major operands: pixels are the contraction index), up to two taps sharing the dy slabs: 16 KB read + 12 KB written
 // per 262 clocks and SM.  Accumulators: CTA r's TMEM lanes = output channels of block 2 fg + r, 256 columns per tap.
+// MEASURED (Darknet19-448, batch 128): no gain - the family takes 4.03 ms per step with it, 3.92 without (both with the
+// wave-aware splits below, 4.40 before them): these launches are bound by the operand bytes pulled through L2 and by
+// whole waves of 0.1-0.3 ms CTAs, not by shared-memory bandwidth, and five tap groups of (2,2,2,2,1) taps balance worse
+// than nine of one.  Kept bit-exact and tested, off by default (cb200_force_simt bit 3 / CB200_WGRAD_PAIR=1).
 // grid.x = 2 * (f_groups * c_tiles * tap_groups), cluster (2, 1, 1); grid.y = splits.
 struct WgradPairCfg {
 	static constexpr int KPIX = 64, BNC = 256;
@@ -1495,7 +1511,7 @@ int conv_wgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, cons
 	if (bnc == 64) tg_cap = 5;
 	if (bnc <= 32) tg_cap = 9;
 	// wide layers: the two blocks of output channels on a CTA pair (conv_wgrad_pair_kernel), up to two taps per pair
-	const bool pair = g_enable_pair && bnc == 256 && mf == 2 && d->stride_w == 1;
+	const bool pair = g_enable_pair_wgrad && bnc == 256 && mf == 2 && d->stride_w == 1;
 	if (pair) tg_cap = 2;
 	const int tg = taps < tg_cap ? taps : tg_cap;
 	WgradParams p;

@@ -15,6 +15,7 @@ int g_force_simt = 0;
 extern int g_disable_halo;
 extern int g_enable_cluster;
 extern int g_enable_pair;
+extern int g_enable_pair_wgrad;
 
 // ---- opt-in per-kernel-family timing (CUDA event pairs on the launching stream, harvested lazily:
 // replaces the always-on per-layer cudaEventSynchronize of upstream's perf_eval, src/auxil.c:698-766)
@@ -53,9 +54,11 @@ const char* cb200_last_error(void) { return g_error; }
 const char* cb200_version(void) { return "cianna_b200 0.1 (sm_100a)"; }
 const char* cb200_last_conv_impl(void) { return g_last_conv_impl; }
 static int g_pair_default = 1;     // env CB200_CTA_PAIR=0: keep the wide-N layers on the one-SM kernel
+static int g_pair_wgrad_default = 0;   // env CB200_WGRAD_PAIR=1: weight gradient of the wide layers on CTA pairs (measured 3 % slower)
 void cb200_force_simt(int on) {
 	g_force_simt = on & 1; g_disable_halo = (on >> 1) & 1; g_enable_cluster = (on >> 2) & 1;
 	g_enable_pair = (on & 16) ? 0 : ((on & 8) ? 1 : g_pair_default);
+	g_enable_pair_wgrad = (on & 16) ? 0 : ((on & 8) ? 1 : g_pair_wgrad_default);
 }
 long long cb200_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
 void cb200_profile_enable(int on) { g_prof_on = on; }
@@ -102,6 +105,9 @@ int cb200_init(int device) {
 	const char* cp = getenv("CB200_CTA_PAIR");
 	g_pair_default = (cp && cp[0] == '0') ? 0 : 1;
 	g_enable_pair = g_pair_default;
+	const char* wp = getenv("CB200_WGRAD_PAIR");
+	g_pair_wgrad_default = (wp && wp[0] == '1') ? 1 : 0;
+	g_enable_pair_wgrad = g_pair_wgrad_default;
 	if (!g_stream) {
 		// the compute stream carries the critical path: highest priority, so that work put on side streams (weight gradients)
 		// only takes the SMs the critical path leaves free

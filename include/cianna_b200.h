@@ -71,8 +71,9 @@ const char* cb200_last_conv_impl(void);
 /* bit 0: force the generic SIMT kernels (parity cross-checks of the tcgen05 path); bit 1: keep the tcgen05 path but
  * route every layer through the per-tap kernel instead of the halo-reuse kernel (A/B checks); bit 2: enable the
  * 2-CTA cluster variant of the per-tap kernel (filter halves TMA-multicast to both CTAs; measured neutral, off by
- * default); bit 3 / bit 4: force the CTA-pair kernel (cta_group::2, N tiles of 256 on layers with enough tiles) on / off
- * (default on, env CB200_CTA_PAIR=0 turns it off); 0 = auto */
+ * default); bit 3 / bit 4: force the CTA-pair kernels (cta_group::2) on / off - forward / data gradient with N tiles of
+ * 256 on layers with enough tiles (default on, env CB200_CTA_PAIR=0) and the weight gradient of layers with more than
+ * 128 channels on both sides (default off, env CB200_WGRAD_PAIR=1); 0 = auto */
 void cb200_force_simt(int on);
 /* number of kernels launched by this library since the last reset */
 long long cb200_launch_count(int reset);
