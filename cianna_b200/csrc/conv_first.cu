@@ -65,13 +65,14 @@ __device__ __forceinline__ void build_patch_row(const T* __restrict__ img, bool 
 	if (valid && iy0 >= 0 && iy0 + FH <= h && ix0 >= 0 && ix0 + FW <= w) {
 		// interior pixel (all but the image border): every tap is inside, plain loads at fixed offsets from one pointer
 		// per (channel, filter row) - the builders are instruction-bound, so this path carries no predicates
-		const unsigned short* __restrict__ p0 = src + (size_t)iy0 * w + ix0;
-		const size_t chs = (size_t)h * w;
+		// (32-bit element offsets inside one image - c*h*w < 2^31 - keep the nine line pointers at one IMAD.WIDE each)
+		const int off0 = iy0 * w + ix0;
+		const int chs = h * w;
 #pragma unroll
 		for (int ch = 0; ch < C; ch++) {
 #pragma unroll
 			for (int ky = 0; ky < FH; ky++) {
-				const unsigned short* __restrict__ line = p0 + ch * chs + (size_t)(ky * w);
+				const unsigned short* __restrict__ line = src + (off0 + ch * chs + ky * w);
 #pragma unroll
 				for (int kx = 0; kx < FW; kx++) {
 					const int k = (ch * FH + ky) * FW + kx;

@@ -19,7 +19,7 @@ for r in rows[start + 1:]:
     e[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
 ids = sorted(by)
 last = [by[i] for i in ids[len(ids) // 2:]]
-groups = {"igemm": ("conv_igemm_kernel", "conv_halo_kernel", "conv_first_fwd_kernel"), "wgrad": ("conv_wgrad_kernel", "conv_wgrad_swap_kernel", "conv_first_wgrad_kernel")}
+groups = {"igemm": ("conv_igemm_kernel", "conv_igemm_pair_kernel", "conv_halo_kernel", "conv_first_fwd_kernel"), "wgrad": ("conv_wgrad_kernel", "conv_wgrad_pair_kernel", "conv_wgrad_swap_kernel", "conv_first_wgrad_kernel")}
 out = {"batch": batch, "note": "ncu per-launch metrics of one Darknet19-448 FP16C_FP32A training step (scripts/gpu_step_metrics.sh -> %s)" % src}
 for key, names in groups.items():
     sel = [e for e in last if any(n in e["k"] for n in names)]
