@@ -121,6 +121,37 @@ def test_conv_tcgen05_address_mapping_bit_exact(cabi, shape, dtype_name):
     layer.free(); xb.free(); dyb.free()
 
 
+@pytest.mark.parametrize("dtype_name", ["FP16", "BF16"])
+@pytest.mark.parametrize("shape", [(3, 32, 12, 40, 3, 1), (2, 64, 40, 64, 3, 1), (4, 64, 9, 256, 1, 0)])
+@pytest.mark.parametrize("sat", [800.0, 6.0, 2.5])
+def test_conv_relu_epilogue_saturation_bit_exact(cabi, shape, sat, dtype_name):
+    """The leaky-saturated ReLU fused in the tensor-core epilogues (per-tap and halo kernels) runs as max(z, z*leak) with a
+    packed check for elements above the saturation and falls back to the select form for those: integer pre-activations
+    and leak = 1/4 make every branch exact, so the output must equal the oracle bit for bit - with the saturation far away
+    (800, upstream's value: fast path only), in the middle of the value range (6) and between two integers (2.5: every
+    element from 3 up takes the saturated branch)."""
+    B, C, S, N, f, pad = shape
+    dtype = cabi.FP16 if dtype_name == "FP16" else cabi.BF16
+    rng = np.random.default_rng(31)
+    x = _int_tensor(rng, (C, B, S * S), 0.6)
+    w = _int_tensor(rng, (N, f * f * C + 1), 0.7)
+    w[:, -1] = rng.integers(-2, 3, N)
+    layer = cabi.ConvLayer(dtype, B, C, S, S, N, f, 1, pad, bias_value=1.0, act=cabi.activ(cabi.RELU, 0.25, sat), length=B - 1)
+    layer.set_weights(w)
+    xb = cabi.upload_act(x, dtype, B, C, S, S)
+    So = S + 2 * pad - f + 1
+    y = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+    assert cabi.lib().cb200_last_conv_impl().startswith(b"tcgen05")
+    pre, _ = co.conv_forward(x, w, False, B, C, S, S, f, 1, pad, 1.0)
+    assert np.abs(pre).max() < 64
+    ref = co.relu_forward(pre, B - 1, saturation=sat, leak=0.25)
+    if sat < 800:
+        assert (pre > sat).mean() > 0.01, "the test must reach the saturated branch"
+    # quarter-integers up to 64 are exact in both storage types
+    assert np.array_equal(y, ref), "%d wrong" % int((y != ref).sum())
+    layer.free(); xb.free()
+
+
 @pytest.mark.parametrize("dtype_name", ["FP32", "FP16", "BF16"])
 @pytest.mark.parametrize("cfg", [(4, 3, 16, 32, 3, 1, 1), (3, 1, 12, 8, 5, 2, 1), (2, 3, 9, 16, 3, 0, 2)])
 def test_first_layer_patch_rows(cabi, cfg, dtype_name):
