@@ -16,6 +16,7 @@
 //             persistent CTAs over contiguous pixel ranges, FP32 red.add of the per-CTA partial at the end
 // Column order of a patch row = upstream's filter column order c*taps + tap, then the bias input, zero padded to KP.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -40,6 +41,7 @@ struct FirstParams {
 	float* grad;                 // wgrad: [n_real][KP]
 	int tiles_per_cta;           // contiguous run of tiles owned by one CTA
 	uint32_t idesc;
+	int tma_store;               // forward: the output tile leaves through shared memory + one TMA store per tile
 };
 
 template <int KP> struct PatchCfg {
@@ -128,12 +130,13 @@ template <int KP, int BN> struct FirstFwdCfg {
 	static constexpr int B_BYTES = BN * KP * 2;
 	static constexpr int ACC_STAGES = 4;
 	static constexpr int TMEM_COLS = ACC_STAGES * BN <= 128 ? 128 : 256;
-	static constexpr int SMEM_BYTES = STAGES * A_BYTES + ((B_BYTES + 1023) & ~1023) + 1024 + 256;
+	static constexpr int OUT_TILE_BYTES = 128 * BN * 2;                 // staging tile of one epilogue group (TMA store)
+	static constexpr int SMEM_BYTES = STAGES * A_BYTES + ((B_BYTES + 1023) & ~1023) + 1024 + 1024 + FWD_EPI_GROUPS * OUT_TILE_BYTES;
 };
 
 template <typename T, int C, int FH, int FW, int KP, int BN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstParams p) {
+conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out, const FirstParams p) {
 	using Cfg = FirstFwdCfg<KP, BN>;
 	using PC = PatchCfg<KP>;
 	extern __shared__ uint8_t smem_raw[];
@@ -146,12 +149,14 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };
 	const uint32_t bfull_bar = bar_base + 8u * (2 * Cfg::STAGES + 8);
 	const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 9);
+	const uint32_t out_smem = bar_base + 1024u;          // FWD_EPI_GROUPS staging tiles (1024-byte aligned like everything above)
 	uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	constexpr int MMA_WARP = FWD_BUILD_WARPS;
 
 	if (threadIdx.x == 0) {
 		prefetch_tensormap(&tmap_b);
+		if (p.tma_store) prefetch_tensormap(&tmap_out);
 		for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
 		for (int s = 0; s < Cfg::ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
 		mbar_init(bfull_bar, 1);
@@ -229,6 +234,76 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const FirstPar
 		// epilogue is bound by the ALU pipe (profiles/r1_conv_first_fwd_full_raw.csv: 65 % busy)
 		const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+		if (p.tma_store) {
+			// Output through shared memory: with one pixel row per thread a 128-bit global store of a warp touches 32
+			// different lines (16 of them for 32 filters) - the epilogue stores were 60 % of this kernel's LSU wavefronts,
+			// its busiest unit (profiles/r1_first_halo_full_digest.txt).  Here each thread writes its packed row into the
+			// group's staging tile (the TMA swizzle keeps the 128-bit shared stores conflict-free), and one thread hands the
+			// tile to the TMA unit, which also clips rows outside the tensor.
+			const int gtid = (warp - MMA_WARP - 1 - 4 * egrp) * 32 + lane;          // 0..127 inside the group
+			const uint32_t stg = out_smem + (uint32_t)egrp * Cfg::OUT_TILE_BYTES;
+			uint8_t* stg_ptr = smem_raw + (stg - smem_u32(smem_raw));
+			constexpr int CHUNKS = BN / 8;                                         // 16-byte chunks per row: 4 (64B swizzle) or 8 (128B)
+			const int sw_x = BN == 32 ? ((row >> 1) & 3) : (row & 7);
+			for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
+				const int tile = tile0 + it;
+				const int acc = it % Cfg::ACC_STAGES;
+				const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
+				const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
+				const int pn = tni * p.tn + rn;
+				const bool dead = mask_tail && pn >= p.length;
+				mbar_wait(tfull_bar(acc), acc_phase);
+				tc_fence_after();
+				if (gtid == 0) bulk_wait_read0();                                    // the previous tile of this group has left the buffer
+				asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
+				const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+				for (int c0 = 0; c0 < BN; c0 += 32) {
+					uint32_t r[32];
+					tmem_ld_32x32(t_row + c0, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (int v = 0; v < 4; v++) {
+						const int col = c0 + v * 8;
+						float o[8];
+#pragma unroll
+						for (int j = 0; j < 8; j++) o[j] = __uint_as_float(r[v * 8 + j]);
+						if (dead) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) o[j] = 0.0f;
+						} else if (act == CB200_RELU) {
+							if (relu_minmax) {
+#pragma unroll
+								for (int j = 0; j < 8; j++) { const float z = o[j]; o[j] = fminf(fmaxf(z, z * leak), sat + (z - sat) * leak); }
+							} else {
+#pragma unroll
+								for (int j = 0; j < 8; j++) { const float z = o[j]; const float hi = sat + (z - sat) * leak; o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z); }
+							}
+						} else if (act == CB200_LOGISTIC) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) o[j] = 1.0f / (1.0f + expf(fminf(-beta * o[j], sat)));
+						}
+						if (col + 8 > n_real) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+						}
+						const int chunk = ((col >> 3) ^ sw_x) & (CHUNKS - 1);
+						store8<T>(reinterpret_cast<T*>(stg_ptr + row * (BN * 2) + chunk * 16), o);
+					}
+					__syncwarp();
+				}
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(tempty_bar(acc));
+				fence_proxy_async();                                                 // generic-proxy writes -> visible to the TMA unit
+				asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
+				if (gtid == 0) {
+					tma_store_4d(&tmap_out, stg, 0, twi * p.tw, thi * p.th, tni * p.tn);
+					bulk_commit();
+				}
+			}
+			if (gtid == 0) bulk_wait0();
+		} else
 		for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
 			const int tile = tile0 + it;
 			const int acc = it % Cfg::ACC_STAGES;
@@ -452,7 +527,7 @@ static void fill_params(const cb200_conv_desc* d, const void* src, int npix, Fir
 }
 
 template <typename T, int C, int FH, int FW, int KP, int BN>
-static int launch_first_fwd(const CUtensorMap& mb, const FirstParams& p, int grid, cudaStream_t st) {
+static int launch_first_fwd(const CUtensorMap& mb, const CUtensorMap& mo, const FirstParams& p, int grid, cudaStream_t st) {
 	using Cfg = FirstFwdCfg<KP, BN>;
 	static bool configured = false;
 	auto kern = conv_first_fwd_kernel<T, C, FH, FW, KP, BN>;
@@ -462,7 +537,7 @@ static int launch_first_fwd(const CUtensorMap& mb, const FirstParams& p, int gri
 		}
 		configured = true;
 	}
-	kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(mb, p);
+	kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(mb, mo, p);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }
@@ -486,11 +561,11 @@ static int launch_first_wgrad(const CUtensorMap& mdy, const FirstParams& p, int 
 #define FIRST_SHAPES(X)  X(3, 3, 3, 32) X(1, 3, 3, 16) X(1, 5, 5, 32) X(2, 3, 3, 32)
 
 template <typename T>
-static int first_fwd_typed(const cb200_conv_desc* d, const CUtensorMap& mb, const FirstParams& p, int grid, cudaStream_t st) {
+static int first_fwd_typed(const cb200_conv_desc* d, const CUtensorMap& mb, const CUtensorMap& mo, const FirstParams& p, int grid, cudaStream_t st) {
 	const int bn = p.n_pad > 32 ? 64 : 32;
 #define X(C_, FH_, FW_, KP_) \
 	if (d->in_c == C_ && d->f_h == FH_ && d->f_w == FW_) \
-		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, p, grid, st) : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, p, grid, st);
+		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, mo, p, grid, st) : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, mo, p, grid, st);
 	FIRST_SHAPES(X)
 #undef X
 	set_error("conv_first: no kernel instance"); return CB200_ERR_UNSUPPORTED;
@@ -514,11 +589,19 @@ int conv_first_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	CUtensorMap mb;
 	int rc = make_w_map(&mb, w->w_fwd, d->dtype, kp, 1, d->out_c, kp, bn, swizzle_for(kp));
 	if (rc) return rc;
+	// output tile through shared memory + TMA store when a row of the tile is exactly one swizzle span (32 / 64 filters)
+	static const bool no_tma_store = getenv("CB200_NO_TMA_STORE") != nullptr;
+	CUtensorMap mo = mb;
+	p.tma_store = (!no_tma_store && p.n_pad == bn) ? 1 : 0;
+	if (p.tma_store) {
+		rc = make_act_map(&mo, y, d->dtype, p.n_pad, p.W, p.H, p.N, bn, p.tw, p.th, p.tn, bn == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, 1);
+		if (rc) return rc;
+	}
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
 	p.tiles_per_cta = ceil_div(p.num_tiles, grid);
 	grid = ceil_div(p.num_tiles, p.tiles_per_cta);
-	if (d->dtype == CB200_FP16) return first_fwd_typed<__half>(d, mb, p, grid, st);
-	return first_fwd_typed<__nv_bfloat16>(d, mb, p, grid, st);
+	if (d->dtype == CB200_FP16) return first_fwd_typed<__half>(d, mb, mo, p, grid, st);
+	return first_fwd_typed<__nv_bfloat16>(d, mb, mo, p, grid, st);
 }
 
 int conv_first_wgrad(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, const void* dy, cudaStream_t st) {
