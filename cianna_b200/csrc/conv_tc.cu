@@ -129,6 +129,10 @@ struct IgemmParams {
 	int stride;                  // 0 / 1 = dense
 	int out_s, out_ox, out_oy, out_W, out_H;   // out_s == 0: output pixel grid == GEMM pixel grid
 	int w_tap0, w_taps;          // w_taps == 0: the weight tensor holds f_h * f_w taps and all of them are used
+	// halo kernel, forward, n_pad == BN <= 64: the output tile leaves through a swizzled shared-memory staging tile per
+	// epilogue group and ONE TMA store (one pixel row per thread makes a 128-bit warp store touch 32 different lines:
+	// the layer-2 forward kernel had its LSU data pipe 73 % busy with them, profiles/r1_first_halo_full_digest.txt)
+	int tma_out;
 };
 
 // tile index -> (M tile, N tile).  Cluster mode enumerates pairs: tile = 2*pair + rank, so that with an even grid the
@@ -144,9 +148,10 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int&
 // tiles ahead.  tcgen05.ld -> bias + activation (forward) or the previous layer's derivative (dgrad) -> cast -> store.
 // PAIR (cta_group::2 kernels): only the leader CTA's MMA warp waits for drained accumulators, so the epilogue warps of
 // both CTAs arrive on the LEADER's barriers (tempty0 is then a shared::cluster address).
-template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2, bool PAIR = false>
+template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2, bool PAIR = false, bool TMA_OUT = false>
 __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                              float* bias_rows, int warp, int lane, int first_warp) {
+                                              float* bias_rows, int warp, int lane, int first_warp,
+                                              const CUtensorMap* tmap_out = nullptr, uint32_t stg = 0, uint8_t* stg_ptr = nullptr) {
 	static_assert(NGROUPS <= ACC_STAGES, "an accumulator stage belongs to one epilogue group at a time");
 	const int ew = warp - first_warp;                // 0..7
 	const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
@@ -180,6 +185,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		const bool row_ok = px < PW && py < PH && pn < PN;
 		const size_t pix = ((size_t)pn * OH + (py * out_s + out_oy)) * OW + (px * out_s + out_ox);
 		const bool dead = mask_tail && pn >= length;
+		if (TMA_OUT && gtid == 0) bulk_wait_read0();                       // the group's previous tile has left the staging buffer
 		// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
 		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
 		if (mode == 0)
@@ -252,6 +258,12 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 						for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
 					}
 				}
+				if (TMA_OUT) {
+					// staging tile [128 rows][BN channels], 16-byte chunks XOR-swizzled like the TMA map of the output (64B / 128B)
+					const int sw_x = BN == 32 ? ((row >> 1) & 3) : (row & 7);
+					const int chunk = (((c0 >> 3) + v) ^ sw_x) & (BN / 8 - 1);
+					store8<T>(reinterpret_cast<T*>(stg_ptr + row * (BN * 2) + chunk * 16), o);
+				} else
 				store8<T>(out + pix * n_pad + col, o);
 			}
 			__syncwarp();        // reconverge before the next warp-collective tcgen05.ld
@@ -259,7 +271,13 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		tc_fence_before();
 		__syncwarp();
 		if (lane == 0) { if (PAIR) mbar_arrive_cluster(tempty0 + 8u * acc); else mbar_arrive(tempty0 + 8u * acc); }
+		if (TMA_OUT) {
+			fence_proxy_async();                                             // generic-proxy writes -> visible to the TMA unit
+			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+			if (gtid == 0) { tma_store_4d(tmap_out, stg, 0, twi * tw, thi * th, tni * tn); bulk_commit(); }   // rows outside the tensor are clipped
+		}
 	}
+	if (TMA_OUT && gtid == 0) bulk_wait0();
 }
 
 template <int BN, int BK>
@@ -656,7 +674,8 @@ constexpr int HALO_THREADS = (3 + 4 * HALO_EPI_GROUPS) * 32;    // A producer, B
 
 template <typename T, int BN, int BK, int FS>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const IgemmParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const IgemmParams p) {
 	using Cfg = HaloCfg<BN>;
 	constexpr uint32_t ROWB = BK * 2;
 	constexpr uint32_t LAYOUT = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);
@@ -755,7 +774,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 		}
 	} else {
 		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-		epilogue_loop<T, BN, Cfg::ACC_STAGES, HALO_EPI_GROUPS>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 3);
+		bool done = false;
+		if constexpr (BN <= 64) {
+			if (p.tma_out) {
+				// staging tiles behind the bias rows: bar_base is 1024-byte aligned, 256 B of barriers + 4 KB of bias rows -> + 5 KB
+				const uint32_t stg = bar_base + 5120u + (uint32_t)((warp - 3) >> 2) * (128 * BN * 2);
+				epilogue_loop<T, BN, Cfg::ACC_STAGES, HALO_EPI_GROUPS, false, true>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 3,
+					&tmap_out, stg, smem_raw + (stg - smem_u32(smem_raw)));
+				done = true;
+			}
+		}
+		if (!done) epilogue_loop<T, BN, Cfg::ACC_STAGES, HALO_EPI_GROUPS>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 3);
 	}
 
 	tc_fence_before();
@@ -766,7 +795,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 constexpr int HALO_SMEM_MAX = 225 * 1024;
 
 template <typename T, int BN, int BK, int FS>
-static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem_bytes, cudaStream_t st) {
+static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const IgemmParams& p, int smem_bytes, cudaStream_t st) {
 	static bool configured = false;
 	auto kern = conv_halo_kernel<T, BN, BK, FS>;
 	if (!configured) {
@@ -776,14 +805,14 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const Igemm
 		configured = true;
 	}
 	const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-	kern<<<grid, HALO_THREADS, smem_bytes, st>>>(ma, mb, p);
+	kern<<<grid, HALO_THREADS, smem_bytes, st>>>(ma, mb, mo, p);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }
 
 template <typename T>
-static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CUtensorMap& mb, const IgemmParams& p, int smem, cudaStream_t st) {
-#define CASE(BN_, BK_) if (bn == BN_ && bk == BK_) return fs == 3 ? launch_halo<T, BN_, BK_, 3>(ma, mb, p, smem, st) : launch_halo<T, BN_, BK_, 5>(ma, mb, p, smem, st)
+static int dispatch_halo(int bn, int bk, int fs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const IgemmParams& p, int smem, cudaStream_t st) {
+#define CASE(BN_, BK_) if (bn == BN_ && bk == BK_) return fs == 3 ? launch_halo<T, BN_, BK_, 3>(ma, mb, mo, p, smem, st) : launch_halo<T, BN_, BK_, 5>(ma, mb, mo, p, smem, st)
 	CASE(128, 64); CASE(64, 64); CASE(32, 64);
 	CASE(128, 32); CASE(64, 32); CASE(32, 32);
 #undef CASE
@@ -809,7 +838,14 @@ static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_
 	const int b_bytes = f_h * f_w * kcb * b_blk;
 	const int halo_w = HALO_TW + f_w - 1, halo_h = HALO_TH + f_h - 1;
 	const int a_stage = (halo_h * halo_w * bk * 2 + 1023) & ~1023;
-	const int fixed = 1024 /*align*/ + 256 /*barriers*/ + HALO_EPI_GROUPS * 1024 /*bias rows*/;
+	int fixed = 1024 /*align*/ + 256 /*barriers*/ + HALO_EPI_GROUPS * 1024 /*bias rows*/;
+	// forward with exactly one swizzle span of filters per pixel: output through staging tiles + TMA store, if they fit
+	static const bool no_tma_store = getenv("CB200_NO_TMA_STORE") != nullptr;
+	p.tma_out = 0;
+	if (!no_tma_store && p.mode == 0 && n_pad == bn && bn <= 64) {
+		const int fixed_out = 1024 + 5120 + HALO_EPI_GROUPS * 128 * bn * 2;
+		if ((HALO_SMEM_MAX - fixed_out - b_bytes) / a_stage >= 3) { p.tma_out = 1; fixed = fixed_out; }
+	}
 	int stages = (HALO_SMEM_MAX - fixed - b_bytes) / a_stage;
 	if (stages > HaloCfg<16>::MAX_A_STAGES) stages = HaloCfg<16>::MAX_A_STAGES;
 	if (stages < 2) return 0;
@@ -849,8 +885,14 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 			ph.n_real = n_real; ph.n_pad = n_pad;
 			ph.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
 			g_last_conv_impl = "tcgen05-halo";
-			if (dtype == CB200_FP16) return dispatch_halo<__half>(bn, bk, f_h, ma, mb, ph, smem, st);
-			return dispatch_halo<__nv_bfloat16>(bn, bk, f_h, ma, mb, ph, smem, st);
+			CUtensorMap mo = mb;
+			if (ph.tma_out) {
+				rc = make_act_map(&mo, ph.out, dtype, n_pad, out_w, out_h, batch, bn, HALO_TW, HALO_TH, 1,
+				                  bn == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, 1);
+				if (rc) return rc;
+			}
+			if (dtype == CB200_FP16) return dispatch_halo<__half>(bn, bk, f_h, ma, mb, mo, ph, smem, st);
+			return dispatch_halo<__nv_bfloat16>(bn, bk, f_h, ma, mb, mo, ph, smem, st);
 		}
 	}
 	int tw, th, tn;
