@@ -129,9 +129,10 @@ struct IgemmParams {
 	int stride;                  // 0 / 1 = dense
 	int out_s, out_ox, out_oy, out_W, out_H;   // out_s == 0: output pixel grid == GEMM pixel grid
 	int w_tap0, w_taps;          // w_taps == 0: the weight tensor holds f_h * f_w taps and all of them are used
-	// halo kernel, forward, n_pad == BN <= 64: the output tile leaves through a swizzled shared-memory staging tile per
-	// epilogue group and ONE TMA store (one pixel row per thread makes a 128-bit warp store touch 32 different lines:
-	// the layer-2 forward kernel had its LSU data pipe 73 % busy with them, profiles/r1_first_halo_full_digest.txt)
+	// halo kernel, forward, n_pad == BN <= 64 (optional, CB200_HALO_TMA_STORE=1): the output tile leaves through a swizzled
+	// shared-memory staging tile and one TMA store per warp (one pixel row per thread makes a 128-bit warp store touch 32
+	// different lines: the layer-2 forward kernel has its LSU data pipe 73-79 % busy with them,
+	// profiles/r1_first_halo_full_digest.txt) - measured slower there, see halo_plan
 	int tma_out;
 };
 
@@ -185,7 +186,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		const bool row_ok = px < PW && py < PH && pn < PN;
 		const size_t pix = ((size_t)pn * OH + (py * out_s + out_oy)) * OW + (px * out_s + out_ox);
 		const bool dead = mask_tail && pn >= length;
-		if (TMA_OUT && gtid == 0) bulk_wait_read0();                       // the group's previous tile has left the staging buffer
+		if (TMA_OUT && lane == 0) bulk_wait_read0();                       // this warp's previous rows have left the staging buffer
 		// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
 		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
 		if (mode == 0)
@@ -272,12 +273,17 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		__syncwarp();
 		if (lane == 0) { if (PAIR) mbar_arrive_cluster(tempty0 + 8u * acc); else mbar_arrive(tempty0 + 8u * acc); }
 		if (TMA_OUT) {
+			// each warp stores its own 32 rows = (32 / tw) pixel rows of the tile rectangle (box of the output map): no group
+			// barrier in the epilogue's latency chain (a per-group store measured 13 % slower than plain global stores)
 			fence_proxy_async();                                             // generic-proxy writes -> visible to the TMA unit
-			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-			if (gtid == 0) { tma_store_4d(tmap_out, stg, 0, twi * tw, thi * th, tni * tn); bulk_commit(); }   // rows outside the tensor are clipped
+			__syncwarp();
+			if (lane == 0) {                                                 // rows outside the tensor are clipped
+				tma_store_4d(tmap_out, stg + (uint32_t)(quad * 32 * BN * 2), 0, twi * tw, thi * th + quad * (32 / tw), tni * tn);
+				bulk_commit();
+			}
 		}
 	}
-	if (TMA_OUT && gtid == 0) bulk_wait0();
+	if (TMA_OUT && lane == 0) bulk_wait0();
 }
 
 template <int BN, int BK>
@@ -839,10 +845,14 @@ static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_
 	const int halo_w = HALO_TW + f_w - 1, halo_h = HALO_TH + f_h - 1;
 	const int a_stage = (halo_h * halo_w * bk * 2 + 1023) & ~1023;
 	int fixed = 1024 /*align*/ + 256 /*barriers*/ + HALO_EPI_GROUPS * 1024 /*bias rows*/;
-	// forward with exactly one swizzle span of filters per pixel: output through staging tiles + TMA store, if they fit
-	static const bool no_tma_store = getenv("CB200_NO_TMA_STORE") != nullptr;
+	// forward with exactly one swizzle span of filters per pixel: output through staging tiles + TMA stores, if they fit.
+	// OFF by default: measured on the layer-2 forward of Darknet19 (batch 128) the LSU data pipe drops from 79 % to 29 %
+	// busy but the launch gets SLOWER, 410 -> 451 us (467 with one store per epilogue group instead of one per warp): this
+	// kernel is bound by the latency of a tile's epilogue chain, which the staging + proxy fence lengthen, and its TMA
+	// unit already carries the halo loads.  (The first-layer kernel, conv_first.cu, gains 9 % from the same idea.)
+	const char* halo_tma = getenv("CB200_HALO_TMA_STORE");
 	p.tma_out = 0;
-	if (!no_tma_store && p.mode == 0 && n_pad == bn && bn <= 64) {
+	if (halo_tma != nullptr && halo_tma[0] == '1' && p.mode == 0 && n_pad == bn && bn <= 64) {
 		const int fixed_out = 1024 + 5120 + HALO_EPI_GROUPS * 128 * bn * 2;
 		if ((HALO_SMEM_MAX - fixed_out - b_bytes) / a_stage >= 3) { p.tma_out = 1; fixed = fixed_out; }
 	}
@@ -887,7 +897,7 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 			g_last_conv_impl = "tcgen05-halo";
 			CUtensorMap mo = mb;
 			if (ph.tma_out) {
-				rc = make_act_map(&mo, ph.out, dtype, n_pad, out_w, out_h, batch, bn, HALO_TW, HALO_TH, 1,
+				rc = make_act_map(&mo, ph.out, dtype, n_pad, out_w, out_h, batch, bn, HALO_TW, 32 / HALO_TW, 1,     // one warp's rows
 				                  bn == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, 1);
 				if (rc) return rc;
 			}

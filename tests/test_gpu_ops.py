@@ -578,6 +578,14 @@ def test_conv_halo_kernel_bit_exact(cabi, shape, dtype_name):
     assert np.abs(ref_dx).max() < 256
     assert np.array_equal(dx, ref_dx), "data gradient: %d wrong" % int((dx != ref_dx).sum())
     assert halo_dgrad or pad == 0 or cabi.round8(N) < 32      # (dy with < 32 channels runs 16-channel blocks: per-tap kernel)
+    # optional output path: staging tile + one TMA store per warp (CB200_HALO_TMA_STORE=1; used when N fills the block): same bits
+    os.environ["CB200_HALO_TMA_STORE"] = "1"
+    try:
+        y_tma = cabi.download_act(layer.forward(xb), dtype, B, N, So, So)
+        assert L.cb200_last_conv_impl() == b"tcgen05-halo"
+    finally:
+        del os.environ["CB200_HALO_TMA_STORE"]
+    assert np.array_equal(y_tma, y)
     # A/B against the per-tap kernel
     L.cb200_force_simt(2)
     try:
