@@ -920,7 +920,7 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	// layers of Darknet19: no gain (71.5 % vs 70.5 % tensor-pipe activity).  Those launches are bound by SHARED-MEMORY
 	// bandwidth, not by L2: per K=16 step the MMA reads 4 KB of A + 8 KB of B while TMA refills 12 KB, 180 B/clk at full
 	// tensor rate against 128 B/clk per SM, i.e. a 71 % ceiling that multicast does not move (each SM still receives and
-	// reads the whole B block).  Lifting it takes cta_group::2 MMAs (B split between the two SMs) - next round.  The path
+	// reads the whole B block).  Lifting it took cta_group::2 MMAs (B split between the two SMs): conv_igemm_pair_kernel below.  The path
 	// stays as a tested option.
 	p.cluster = (g_enable_cluster && dense && bn >= 128 && bk == 64 && p.tiles_m >= 4 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
 	// CTA-pair kernel (cta_group::2: one M = 256 MMA over two SMs, each holding half of the filter block): N tiles of 256
