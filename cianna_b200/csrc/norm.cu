@@ -132,35 +132,6 @@ norm_stats_kernel(const T* __restrict__ a_in, const T* __restrict__ b_in, double
 	norm_stats_body<T, TWO_INPUTS>(a_in, b_in, ws, g, blockIdx.x, blockIdx.y, sm_acc);
 }
 
-// mean = S1/n ; var = S2/n - mean^2  (biased variance, as upstream)
-__device__ __forceinline__ void norm_finalize_fwd_one(const double* ws, float* mean, float* var, const NormGeom& g, int i) {
-	const double n = (double)g.group_size * g.hw;
-	const double m = ws[2 * i] / n;
-	double v = ws[2 * i + 1] / n - m * m;
-	if (v < 0.0) v = 0.0;
-	mean[i] = (float)m;
-	var[i] = (float)v;
-}
-__global__ void norm_finalize_fwd_kernel(const double* __restrict__ ws, float* __restrict__ mean, float* __restrict__ var, NormGeom g) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= g.batch * g.nb_group) return;
-	norm_finalize_fwd_one(ws, mean, var, g, i);
-}
-
-// d_beta = sum d ; d_gamma = (sum d*x - mean*sum d) / sqrt(var+eps)
-__device__ __forceinline__ void norm_finalize_bwd_one(const double* ws, const float* mean, const float* var, float* d_gamma, float* d_beta,
-                                                      const NormGeom& g, int i) {
-	const double sd = ws[2 * i], sdx = ws[2 * i + 1];
-	d_beta[i] = (float)sd;
-	d_gamma[i] = (float)((sdx - (double)mean[i] * sd) / sqrt((double)var[i] + (double)g.eps));
-}
-__global__ void norm_finalize_bwd_kernel(const double* __restrict__ ws, const float* __restrict__ mean, const float* __restrict__ var,
-                                         float* __restrict__ d_gamma, float* __restrict__ d_beta, NormGeom g) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= g.batch * g.nb_group) return;
-	norm_finalize_bwd_one(ws, mean, var, d_gamma, d_beta, g, i);
-}
-
 // Apply kernels: same thread -> (channel vector, pixel lane) mapping as the statistics kernel, one sample per
 // blockIdx.y.  A thread keeps ONE channel vector, so the per-channel affine constants are computed once outside
 // the pixel loop and the loop body is: 128-bit load(s), 8 FMAs, 128-bit store - no integer division, several loads in flight.
@@ -209,13 +180,6 @@ __device__ __forceinline__ void norm_apply_body(const T* __restrict__ x, T* __re
 			}
 		}
 	}
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  const float* __restrict__ mean, const float* __restrict__ var, NormGeom g) {
-	norm_apply_body<T>(x, y, gamma, beta, mean, var, g, blockIdx.x, blockIdx.y);
 }
 
 // per-channel constants of the backward apply: dx = k0*(n*d - d_beta - (x - mu)*rstd*d_gamma) rewritten per channel as
@@ -314,24 +278,6 @@ __device__ __forceinline__ void norm_bwd_apply_body(const T* __restrict__ x, con
 		}
 		// column sums of the delta just produced = raw bias-column gradient of the preceding convolution
 		if (cs_acc != nullptr) fold_colsum(csum, v, lanes_c, active_thread, cs_acc);
-	}
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ gamma,
-                      const float* __restrict__ mean, const float* __restrict__ var,
-                      const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                      cb200_activ prev_activ, float* __restrict__ colsum, NormGeom g) {
-	extern __shared__ float cs_acc[];          // [cp] per-block column sums of dx (only when colsum != nullptr)
-	if (colsum != nullptr) {
-		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
-		__syncthreads();
-	}
-	norm_bwd_apply_body<T>(x, dy, dx, gamma, mean, var, d_gamma, d_beta, prev_activ, colsum != nullptr ? cs_acc : nullptr, g, blockIdx.x, blockIdx.y);
-	if (colsum != nullptr) {
-		__syncthreads();
-		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
 	}
 }
 
@@ -441,13 +387,6 @@ __device__ __forceinline__ void norm_pool_fwd_body(const T* __restrict__ x, T* _
 			if (map != nullptr) *reinterpret_cast<uint2*>(map + o) = packed;
 		}
 	}
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ map, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var, FusedGeom f) {
-	norm_pool_fwd_body<T>(x, pooled, map, gamma, beta, mean, var, f, blockIdx.x, blockIdx.y);
 }
 
 // backward reductions: the delta of the normalised tensor is the pooled delta at the selected window position and
@@ -566,27 +505,11 @@ __device__ __forceinline__ void norm_pool_bwd_apply_body(const T* __restrict__ x
 	}
 }
 
-template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS)
-norm_pool_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, T* __restrict__ dx,
-                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ var,
-                           const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                           cb200_activ prev_activ, float* __restrict__ colsum, FusedGeom f) {
-	extern __shared__ float cs_acc[];
-	const NormGeom& g = f.n;
-	if (colsum != nullptr) {
-		for (int i = threadIdx.x; i < g.cp; i += blockDim.x) cs_acc[i] = 0.0f;
-		__syncthreads();
-	}
-	norm_pool_bwd_apply_body<T>(x, dp, map, dx, gamma, mean, var, d_gamma, d_beta, prev_activ, colsum != nullptr ? cs_acc : nullptr, f, blockIdx.x, blockIdx.y);
-	if (colsum != nullptr) {
-		__syncthreads();
-		for (int i = threadIdx.x; i < g.c; i += blockDim.x) atomicAdd(&colsum[i], cs_acc[i]);
-	}
-}
-
-// ---------------------------------------------------------------- statistics -> apply over L2-sized chunks of the batch
-// The two-pass form streams the tensor from HBM twice: once for the statistics, once for the apply.  The chunked form
+// ---------------------------------------------------------------- launches: statistics role / apply role in one grid
+// DEFAULT (two passes): a statistics launch over the whole batch, then ONE launch whose blocks all take the apply role and
+// turn the FP64 sums of their sample into mean / var (forward) or d_gamma / d_beta (backward) themselves - no separate
+// finalize launch on the critical path (36 tiny launches per Darknet19 step).
+// OPTIONAL (chunked, cb200_norm_set_pipeline): the two-pass form streams the tensor from HBM twice; the chunked form
 // walks the batch in chunks of a few images sized to stay in L2 (126 MB): launch i runs, side by side in ONE grid,
 // the statistics blocks of chunk i and the apply blocks of chunk i-1, so the apply re-reads its chunk from L2 while the
 // statistics blocks stream the next one from HBM - forward 3 -> 2 passes over HBM, backward 5 -> 3 - and the finalize
@@ -607,7 +530,8 @@ struct ChunkGeom {
 	int nbx_b, b_b0;             // apply role: blocks per sample, first sample
 };
 
-// statistics of sample b -> shared memory [mean | var] (forward) ; the first block of the sample keeps them for backward
+// statistics of sample b -> shared memory [mean | var] (forward): mean = S1/n, var = S2/n - mean^2 (biased, as upstream);
+// the first block of the sample keeps them for backward
 __device__ __forceinline__ void chunk_finalize_fwd(const double* ws, float* mean, float* var, const NormGeom& g, int b, bool keep, float* sm) {
 	const double n = (double)g.group_size * g.hw;
 	for (int i = threadIdx.x; i < g.nb_group; i += blockDim.x) {
@@ -621,7 +545,8 @@ __device__ __forceinline__ void chunk_finalize_fwd(const double* ws, float* mean
 	}
 	__syncthreads();
 }
-// sums of sample b -> shared memory [d_gamma | d_beta] (backward); the first block stores them for the optimizer
+// sums of sample b -> shared memory [d_gamma | d_beta] (backward): d_beta = sum d, d_gamma = (sum d*x - mean*sum d) / sqrt(var+eps);
+// the first block stores them for the optimizer
 __device__ __forceinline__ void chunk_finalize_bwd(const double* ws, const float* mean, const float* var, float* d_gamma, float* d_beta,
                                                    const NormGeom& g, int b, bool keep, float* sm) {
 	for (int i = threadIdx.x; i < g.nb_group; i += blockDim.x) {
@@ -749,6 +674,13 @@ static int chunk_ppb(int hw, int k, int cv) {
 	if (ppb > 1024) ppb = 1024;
 	return (int)ppb;
 }
+// whole batch, apply role only (the default two-pass form: statistics launch, then finalize + apply in one launch)
+static ChunkGeom apply_only_geom(int batch, int nbx, unsigned& grid) {
+	ChunkGeom cg;
+	cg.nblk_a = 0; cg.nbx_a = 1; cg.a_b0 = 0; cg.nbx_b = nbx; cg.b_b0 = 0;
+	grid = (unsigned)(batch * nbx);
+	return cg;
+}
 // launch i of nchunks + 1: statistics of chunk i, apply of chunk i - 1
 static bool chunk_launch_geom(int i, int batch, int k, int nbx_a, int nbx_b, ChunkGeom& cg, unsigned& grid) {
 	const int nchunks = (batch + k - 1) / k;
@@ -812,9 +744,11 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	size_t smem = sizeof(float) * 2 * g.nb_group;
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, smem, st>>>((const T*)x, nullptr, ws, g)));
 	CB_LAUNCH_CHECK();
-	norm_finalize_fwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, g);
-	CB_LAUNCH_CHECK();
-	CB_DISPATCH_DTYPE(d->dtype, T, (norm_apply_kernel<T><<<grid, NORM_THREADS, 0, st>>>((const T*)x, (T*)y, gamma, beta, mean, var, g)));
+	// finalize folded into the apply blocks (each turns its sample's FP64 sums into mean / var in shared memory): one tiny
+	// launch less on the critical path per layer and pass
+	unsigned agrid;
+	const ChunkGeom cg = apply_only_geom(g.batch, (int)grid.x, agrid);
+	CB_DISPATCH_DTYPE(d->dtype, T, (norm_fwd_chunk_kernel<T><<<agrid, NORM_THREADS, smem, st>>>((const T*)x, (T*)y, gamma, beta, mean, var, ws, g, cg)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);
 	return CB200_OK;
@@ -853,11 +787,11 @@ int cb200_norm_backward(const cb200_norm_desc* d, const void* x, const void* dy,
 	size_t smem = sizeof(float) * 2 * g.nb_group;
 	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, true><<<grid, NORM_THREADS, smem, st>>>((const T*)dy, (const T*)x, ws, g)));
 	CB_LAUNCH_CHECK();
-	norm_finalize_bwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, d_gamma, d_beta, g);
-	CB_LAUNCH_CHECK();
 	if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
-	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_apply_kernel<T><<<grid, NORM_THREADS, dx_colsum ? sizeof(float) * g.cp : 0, st>>>(
-		(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, g)));
+	unsigned agrid;
+	const ChunkGeom cg = apply_only_geom(g.batch, (int)grid.x, agrid);
+	CB_DISPATCH_DTYPE(d->dtype, T, (norm_bwd_chunk_kernel<T><<<agrid, NORM_THREADS, sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0)), st>>>(
+		(const T*)x, (const T*)dy, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, ws, g, cg)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);
 	return CB200_OK;
@@ -908,10 +842,10 @@ int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
 	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>((const T*)x, nullptr, ws, g)));
 	CB_LAUNCH_CHECK();
-	norm_finalize_fwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, g);
-	CB_LAUNCH_CHECK();
-	dim3 grid_o((unsigned)ceil_div(f.out_hw, f.ppb_out), (unsigned)g.batch);
-	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_fwd_kernel<T><<<grid_o, NORM_THREADS, 0, st>>>((const T*)x, (T*)pooled, pool_map, gamma, beta, mean, var, f)));
+	unsigned agrid;
+	const ChunkGeom cg = apply_only_geom(g.batch, ceil_div(f.out_hw, f.ppb_out), agrid);
+	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_fwd_chunk_kernel<T><<<agrid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
+		(const T*)x, (T*)pooled, pool_map, gamma, beta, mean, var, ws, f, cg)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);
 	return CB200_OK;
@@ -952,11 +886,11 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
 	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_stats_kernel<T><<<grid_o, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
 		(const T*)x, (const T*)d_pooled, pool_map, ws, f)));
 	CB_LAUNCH_CHECK();
-	norm_finalize_bwd_kernel<<<ceil_div(g.batch * g.nb_group, 128), 128, 0, st>>>(ws, mean, var, d_gamma, d_beta, g);
-	CB_LAUNCH_CHECK();
 	if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
-	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_apply_kernel<T><<<grid_o, NORM_THREADS, dx_colsum ? sizeof(float) * g.cp : 0, st>>>(
-		(const T*)x, (const T*)d_pooled, pool_map, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, f)));
+	unsigned agrid;
+	const ChunkGeom cg = apply_only_geom(g.batch, (int)grid_o.x, agrid);
+	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_chunk_kernel<T><<<agrid, NORM_THREADS, sizeof(float) * (2 * g.nb_group + (dx_colsum ? g.cp : 0)), st>>>(
+		(const T*)x, (const T*)d_pooled, pool_map, (T*)dx, gamma, mean, var, d_gamma, d_beta, pa, dx_colsum, ws, f, cg)));
 	CB_LAUNCH_CHECK();
 	prof_end(st);
 	return CB200_OK;

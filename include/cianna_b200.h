@@ -279,8 +279,8 @@ typedef struct {
 /* mean/var: FP32 [batch][nb_group]; gamma/beta: FP32 [nb_group] (device).
  * Replaces cuda_forward_norm_layer (src/cuda/cuda_norm_layer.cu:361-397). */
 size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial sums, caller-owned */
-/* The forward / backward entry points below (and the fused norm + pool pair) run as statistics / finalize / apply launches
- * over the whole batch (on = 0, default), or walk the batch in L2-sized chunks (on = 1, env CB200_GN_PIPELINE=1): launch i
+/* The forward / backward entry points below (and the fused norm + pool pair) run as two launches over the whole batch -
+ * statistics, then apply with the finalize step folded into its blocks - (on = 0, default), or walk the batch in L2-sized chunks (on = 1, env CB200_GN_PIPELINE=1): launch i
  * holds the statistics blocks of chunk i and the apply blocks of chunk i-1, which re-read their chunk from L2 instead of
  * HBM - same arithmetic, measured slower on B200 (csrc/norm.cu), kept as a tested option.
  * chunk_kb: bytes read by the statistics blocks of one launch (0: keep; default 24 MB, env CB200_GN_CHUNK_MB);
