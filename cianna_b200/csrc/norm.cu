@@ -309,6 +309,31 @@ __global__ void norm_update_kernel(float* __restrict__ gamma, float* __restrict_
 	beta[grp] -= bu / S;
 }
 
+// single-GPU form of the two kernels above in one launch (no all-reduce between them): one warp per group sums the
+// per-sample gradients over the batch and its first lane applies the update; same arithmetic, gsum still written
+__global__ void norm_reduce_update_kernel(const float* __restrict__ d_gamma, const float* __restrict__ d_beta, float* __restrict__ gsum,
+                                          float* __restrict__ gamma, float* __restrict__ beta, float* __restrict__ gamma_upd,
+                                          float* __restrict__ beta_upd, const float* __restrict__ hyper, int batch, int nb_group, int set_off) {
+	const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (grp >= nb_group) return;
+	double sg = 0.0, sb = 0.0;
+	for (int b = lane; b < batch; b += 32) { sg += d_gamma[b * nb_group + grp]; sb += d_beta[b * nb_group + grp]; }
+	sg = warp_sum(sg);
+	sb = warp_sum(sb);
+	if (lane != 0) return;
+	const float fg = (float)sg, fb = (float)sb;
+	gsum[grp] = fg; gsum[nb_group + grp] = fb;
+	if (grp >= nb_group - set_off) return;
+	const float alpha = hyper[0], mom = hyper[1], S = hyper[3];
+	const float gu = mom * gamma_upd[grp] + alpha * fg;
+	const float bu = mom * beta_upd[grp] + alpha * fb;
+	gamma_upd[grp] = gu;
+	beta_upd[grp] = bu;
+	gamma[grp] -= gu / S;
+	beta[grp] -= bu / S;
+}
+
 // ---------------------------------------------------------------- group-norm + 2x2 max-pool, fused
 // Geometry of the pooled side; the norm geometry `n` describes the input-sized tensor (n.hw = in_h * in_w).
 struct FusedGeom {
@@ -899,6 +924,15 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
 int cb200_norm_reduce_grads(const cb200_norm_desc* d, const float* d_gamma, const float* d_beta, float* gsum, void* s) {
 	CB_REQUIRE_DEVICE();
 	norm_reduce_grads_kernel<<<ceil_div(d->nb_group * 32, 128), 128, 0, as_stream(s)>>>(d_gamma, d_beta, gsum, d->batch, d->nb_group);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_norm_reduce_update(const cb200_norm_desc* d, const float* d_gamma, const float* d_beta, float* gsum, float* gamma, float* beta,
+                             float* gamma_upd, float* beta_upd, const float* hyper, void* s) {
+	CB_REQUIRE_DEVICE();
+	norm_reduce_update_kernel<<<ceil_div(d->nb_group * 32, 128), 128, 0, as_stream(s)>>>(d_gamma, d_beta, gsum, gamma, beta, gamma_upd, beta_upd,
+	                                                                                    hyper, d->batch, d->nb_group, d->set_off);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }

@@ -438,7 +438,11 @@ static void apply_updates(network *net)
 			CB_CHECK(cb200_dense_update(&p->desc, &p->w, net->hyper_dev, NULL));
 		} else if (l->type == NORM) {
 			norm_param *p = (norm_param *)l->param;
-			CB_CHECK(cb200_norm_update(&p->desc, p->gamma, p->beta, p->gamma_update, p->beta_update, p->gsum, net->hyper_dev, NULL));
+			if (cb200_dp_world() > 1)
+				CB_CHECK(cb200_norm_update(&p->desc, p->gamma, p->beta, p->gamma_update, p->beta_update, p->gsum, net->hyper_dev, NULL));
+			else
+				CB_CHECK(cb200_norm_reduce_update(&p->desc, p->d_gamma, p->d_beta, p->gsum, p->gamma, p->beta, p->gamma_update,
+					p->beta_update, net->hyper_dev, NULL));
 		}
 	}
 	perf_mark(net, 2, net->nb_layers);

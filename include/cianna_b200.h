@@ -306,6 +306,10 @@ int cb200_norm_reduce_grads(const cb200_norm_desc* d, const float* d_gamma, cons
                             float* gsum, void* stream);
 int cb200_norm_update(const cb200_norm_desc* d, float* gamma, float* beta, float* gamma_upd, float* beta_upd,
                       const float* gsum, const float* hyper, void* stream);
+/* cb200_norm_reduce_grads + cb200_norm_update in one launch, for runs without a gradient all-reduce between them
+ * (single GPU): same arithmetic, gsum is still written. */
+int cb200_norm_reduce_update(const cb200_norm_desc* d, const float* d_gamma, const float* d_beta, float* gsum,
+                             float* gamma, float* beta, float* gamma_upd, float* beta_upd, const float* hyper, void* stream);
 
 /* ---- group-norm followed by a max-pool over disjoint 2x2 windows, fused (no upstream counterpart: upstream runs
  * cuda_forward_norm_layer then cuda_forward_pool_layer and the reverse pair, cuda_norm_layer.cu:361-461,

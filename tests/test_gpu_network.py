@@ -194,8 +194,9 @@ def test_training_steps_match_live_reference(cnn, mode):
             d_mine, d_ref = np.where(sure, cnn.layer_delta(0) / S, 0), np.where(sure, ref.delta(0), 0)
             scale = np.abs(d_ref).max()
             per_image = np.abs(d_mine - d_ref).max(axis=(0, 2)) / scale
-            flipped = per_image >= 5 * tol
-            REPORT["live/%s" % mode]["delta0_step%d" % step] = float(per_image[~flipped].max())
+            # (after a counted flip every image sees slightly different weights: same slack as the other comparisons)
+            flipped = per_image >= 5 * tol * (FLIP_SLACK if n_flips else 1)
+            REPORT["live/%s" % mode]["delta0_step%d" % step] = float(per_image[~flipped].max()) if (~flipped).any() else float(per_image.max())
             REPORT["live/%s" % mode]["deep_relu_flips_step%d" % step] = int(flipped.sum())
             assert flipped.sum() <= 2 and per_image.max() < 0.05, (step, per_image.tolist())
             n_flips += int(flipped.sum())
