@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "darknet19_448_train_images_per_sec"
 UNIT = "images/s"
 TRAIN_GFLOP_PER_IMG = 66.71     # algorithmic 2*M*N*K incl. bias column, fwd + dgrad + wgrad
+REF_BATCH = 16                  # images per step of the reference arm / cpu_baseline sample
 HYPER = dict(learning_rate=0.003, momentum=0.9, weight_decay=0.0002)   # examples/ImageNET/imagenet_train.py:101-103 upstream
 
 
@@ -97,6 +98,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(args, world):
+    """the same `config` object on both arms (ours and --impl reference)"""
+    B = args.batch
+    return {"workload": "Darknet19 ImageNet classifier 448px %s training, synthetic data" % args.precision, "batch_per_gpu": B,
+            "global_batch": B * world, "image_size": args.size, "classes": 1000, "parallelism": "dp%d" % world,
+            "l2_policy": "inputs larger than L2 (activations %.1f GB per step)" % (36.5e6 * 2 * B / 1e9),
+            "train_gflop_per_image": TRAIN_GFLOP_PER_IMG}
+
+
+def kernel_source_id():
+    """sha256 over the CUDA sources + C-ABI header: ties an ncu summary under profiles/ to the build it was taken on
+    (the GPU box has no .git, so a commit id would not be checkable there)"""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "cianna_b200", "csrc", "*")) + [os.path.join(ROOT, "include", "cianna_b200.h")]):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -117,7 +139,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
-    b = 2 if (args.steps + args.warmup) <= 24 else 1
+    b = REF_BATCH          # upstream's own batch for this network (examples/ImageNET/imagenet_train.py:45), whatever --steps is
     spec = darknet19_spec(b, args.size, 1000)
     cnn, _ = ref_loader.load("omp")
     with rd._Quiet():
@@ -139,16 +161,18 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": 0,
-            "config": {"workload": "Darknet19 ImageNet classifier 448px training (reference CPU back-end C_BLAS, FP32)", "batch_per_step": b,
-                       "image_size": args.size, "classes": 1000},
+            "config": workload_config(args, world),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
-                             "sample": "%d training steps of %d images, reference built from /root/reference/src with OpenBLAS + OpenMP" % (args.steps, b)},
+                             "sample": "%d training steps of %d images each (bounded sample of the workload's %d-image steps; the CPU back-end is FP32 "
+                                       "whatever the precision mode), unmodified reference built from /root/reference/src: C_BLAS back-end, OpenBLAS + OpenMP "
+                                       "on %d threads" % (args.steps, b, args.batch, cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline_sample(size):
-    """bounded CPU sample for the main line (rank 0, N = 1): 4 training steps of 4 images with the compiled reference"""
+    """bounded CPU sample for the main line (rank 0, N = 1): 2 training steps of REF_BATCH images with the compiled
+    reference (the same per-step sample as the --impl reference arm)"""
     from oracle import ref_driver as rd, ref_loader
     if not ref_loader.available("omp"):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref/omp not built"}
@@ -158,12 +182,12 @@ sys.path.insert(0, %r)
 import bench
 from oracle import ref_driver as rd, ref_loader
 cnn, _ = ref_loader.load("omp")
-spec = bench.darknet19_spec(4, %d, 1000)
+spec = bench.darknet19_spec(bench.REF_BATCH, %d, 1000)
 with rd._Quiet():
     rd.build_network(cnn, spec, "C_BLAS", "off", network=0)
-x, t = bench.synth_batches(4, 4, %d, 1000, 3)
+x, t = bench.synth_batches(2, bench.REF_BATCH, %d, 1000, 3)
 with rd._Quiet():
-    cnn.create_dataset("TRAIN", 16, x, t, network=0, silent=1)
+    cnn.create_dataset("TRAIN", 2 * bench.REF_BATCH, x, t, network=0, silent=1)
     t0 = time.perf_counter()
     cnn.train(nb_iter=1, control_interv=1000, shuffle_every=0, silent=1, network=0, confmat=0, save_every=0, **bench.HYPER)
     dt = time.perf_counter() - t0
@@ -176,11 +200,41 @@ sys.stderr.write("CPUBASE " + json.dumps({"dt": dt}) + "\n")
         for ln in r.stderr.splitlines():
             if ln.startswith("CPUBASE "):
                 dt = json.loads(ln[8:])["dt"]
-                return {"value": 16.0 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-                        "sample": "1 epoch of 4 training steps x 4 images (Darknet19-448, FP32, reference C_BLAS + OpenMP back-end), %.1f s" % dt}
+                return {"value": 2.0 * REF_BATCH / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": "1 epoch of 2 training steps x %d images (Darknet19-448, FP32, unmodified reference C_BLAS back-end, OpenBLAS + OpenMP on %d threads), %.1f s" % (REF_BATCH, cores, dt)}
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "failed: " + r.stderr[-200:]}
     except subprocess.TimeoutExpired:
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "timed out after 600 s"}
+
+
+def inference_object(imgs, ms_inf, ms_inf_e2e, ms_inf_serial, fam_inf, args, peak_tf, peak_hbm, peak_src):
+    """Darknet19-448 inference images/s at 1 GPU (BASELINE.json's second metric) with its own roofline: the forward
+    implicit-GEMM family against the tensor peak and the group-norm (+ fused pool) family against the HBM peak"""
+    out = {"metric": "darknet19_448_inference_images_per_sec", "value": imgs / (ms_inf / 1000.0), "unit": UNIT,
+           "e2e": imgs / (ms_inf_e2e / 1000.0), "ms_per_step": ms_inf / args.steps,
+           "effective_tflops": imgs / (ms_inf / 1000.0) * 22.36 / 1e3, "fwd_gflop_per_image": 22.36}
+    fams = {}
+    for k, v in fam_inf.items():
+        if v["launches"] == 0 or v["ms"] <= 0:
+            continue
+        rate = v["work"] / (v["ms"] / 1000.0)
+        conv = k.startswith("conv")
+        fams[k] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                   ("tflops" if conv else "gbs"): rate / (1e12 if conv else 1e9), "share_of_step": v["ms"] / ms_inf_serial}
+    out["kernel_families"] = fams
+    conv = fam_inf.get("conv_fwd_tcgen05")
+    if conv and conv["launches"]:
+        ach = conv["work"] / (conv["ms"] / 1000.0) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward launches)", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                           "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "launches": conv["launches"],
+                           "avg_launch_ms": conv["ms"] / conv["launches"], "share_of_step": conv["ms"] / ms_inf_serial,
+                           "timing": "CUDA events around each launch in an attribution pass of the same K forward steps"}
+    gn = fam_inf.get("group_norm")
+    if gn and gn["launches"]:
+        ach = gn["work"] / (gn["ms"] / 1000.0) / 1e9
+        out["roofline_hbm"] = {"bound": "hbm", "kernel": "norm_apply / norm_pool_fwd kernels", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
+                               "frac": ach / peak_hbm, "traffic": None, "launches": gn["launches"], "share_of_step": gn["ms"] / ms_inf_serial}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -250,13 +304,23 @@ def run_ours(args, rank, local_rank, world):
         v = float(ms.value)
         if dist is not None:
             import torch
-            tt = torch.tensor([v], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            v = float(tt.item())
+            mine = torch.tensor([v], device="cuda")
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            per_rank_ms[:] = [float(e.item()) for e in every]
+            v = max(per_rank_ms)          # the job is as slow as its slowest rank
+        else:
+            per_rank_ms[:] = [v]
         return v
 
+    per_rank_ms = []
+
     # ---- device-resident steps
-    H.cb_train_steps(net, args.warmup, lr, mom, wd, 1, 0)
+    H.cb_last_step_loss.restype = ctypes.c_float
+    H.cb_last_step_loss.argtypes = [vp]
+    H.cb_train_steps(net, 1, lr, mom, wd, 1, 0)
+    loss_first = float(H.cb_last_step_loss(net))
+    H.cb_train_steps(net, max(args.warmup - 1, 0), lr, mom, wd, 1, 0)
     barrier()
     # (a) attribution pass: the same K steps with the weight-gradient kernels back on the compute stream, so that every
     #     CUDA-event pair brackets ONE kernel family running alone (in the timed pass below the weight gradients overlap
@@ -276,6 +340,15 @@ def run_ours(args, rank, local_rank, world):
     sampler.start()
     ms_res = timed(lambda: H.cb_train_steps(net, args.steps, lr, mom, wd, 1, 0))
     clocks = sampler.stop()
+    rank_ms_res = [m / args.steps for m in per_rank_ms]
+    rank_clocks = [clocks]
+    if dist is not None:
+        rank_clocks = [None] * world
+        dist.all_gather_object(rank_clocks, clocks)
+        clocks = dict(clocks)
+        reasons = sorted(set(r for c in rank_clocks for r in (c or {}).get("reasons", [])))
+        clocks["reasons"] = reasons                                   # union over the ranks
+        clocks["per_rank"] = [{"sm_mhz": (c or {}).get("sm_mhz"), "reasons": (c or {}).get("reasons")} for c in rank_clocks]
     launches = int(L.cb200_launch_count(0))
     fam = {}
     for f, name in ((0, "conv_fwd_tcgen05"), (1, "conv_dgrad_tcgen05"), (2, "conv_wgrad_tcgen05"), (3, "conv_fwd_simt"), (4, "conv_dgrad_simt"),
@@ -284,7 +357,7 @@ def run_ours(args, rank, local_rank, world):
         cabi.check(L.cb200_profile_collect(f, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n)))
         fam[name] = {"ms": ms.value, "work": work.value, "launches": int(n.value)}
     L.cb200_profile_reset()
-    loss_after = cnn.host().cb_net_last_epoch_loss(net)
+    loss_last = float(H.cb_last_step_loss(net))     # the timed region's last step (same batches cycled: must be finite and below loss_first)
 
     # ---- end to end through the reference-facing API: cnn.train over host-resident batches (dynamic_load = 1)
     def e2e_run():
@@ -303,6 +376,17 @@ def run_ours(args, rank, local_rank, world):
     H.cb_forward_steps(net, 2, 1, 0)
     ms_inf = timed(lambda: H.cb_forward_steps(net, args.steps, 1, 0))
     ms_inf_e2e = timed(lambda: H.cb_forward_steps(net, args.steps, 0, 1))
+    # attribution pass of the inference step (events around every launch; not the timed number)
+    L.cb200_profile_reset()
+    L.cb200_profile_enable(1)
+    ms_inf_serial = timed(lambda: H.cb_forward_steps(net, args.steps, 1, 0))
+    L.cb200_profile_enable(0)
+    fam_inf = {}
+    for f, name in ((0, "conv_fwd_tcgen05"), (3, "conv_fwd_simt"), (6, "pool"), (7, "group_norm")):
+        ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        cabi.check(L.cb200_profile_collect(f, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n)))
+        fam_inf[name] = {"ms": ms.value, "work": work.value, "launches": int(n.value)}
+    L.cb200_profile_reset()
 
     if dist is not None:
         dist.barrier()
@@ -323,13 +407,17 @@ def run_ours(args, rank, local_rank, world):
         dom = max(kern, key=lambda k: kern[k]["ms"])
         ach = kern[dom]["work"] / (kern[dom]["ms"] / 1000.0) / 1e12
         traffic, ncu_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_conv_metrics_summary.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_conv_metrics_summary.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             key = {"conv_igemm_kernel": "igemm", "conv_wgrad_kernel": "wgrad"}[dom]
-            if tj.get("batch", 128) == B and args.size == 448 and key in tj:
+            if tj.get("kernel_source_id") != kernel_source_id():
+                # an ncu capture of another build says nothing about this one: no traffic figure rather than a stale one
+                ncu_note = {"stale": "profiles/r2_conv_metrics_summary.json was captured on kernel sources %s, this build is %s: traffic withheld"
+                                     % (tj.get("kernel_source_id"), kernel_source_id())}
+            elif tj.get("batch", 128) == B and args.size == 448 and key in tj:
                 traffic = tj[key]["avg_dram_bytes_per_launch"]
-                ncu_note = {"source": "profiles/r1_step_metrics_b128.csv (ncu, dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step)",
+                ncu_note = {"source": "profiles/r2_step_metrics_b128.csv (ncu, dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step)",
                             "kernels": tj[key].get("kernels"), "tensor_pipe_pct_time_weighted": tj[key]["tensor_pipe_pct_time_weighted"]}
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "peak_source": peak_src, "launches": kern[dom]["launches"], "avg_launch_ms": kern[dom]["ms"] / kern[dom]["launches"],
@@ -350,16 +438,17 @@ def run_ours(args, rank, local_rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"off": "f32", "FP16C_FP32A": "f16", "BF16C_FP32A": "bf16"}[args.precision], "data": "synthetic",
-            "config": {"workload": "Darknet19 ImageNet classifier 448px %s training, synthetic data" % args.precision, "batch_per_gpu": B,
-                       "global_batch": B * world, "image_size": args.size, "classes": 1000, "parallelism": "dp%d" % world,
-                       "l2_policy": "inputs larger than L2 (activations %.1f GB per step)" % (36.5e6 * 2 * B / 1e9),
-                       "train_gflop_per_image": TRAIN_GFLOP_PER_IMG},
+            "config": workload_config(args, world),
             "e2e": {"value": imgs / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": B * ((args.size * args.size * 3 + 1) + 1000) * es,
                     "d2h_bytes_per_step": B * 4, "api": "cianna_b200.CIANNA.train (dynamic_load=1)"},
+            "per_rank_ms_per_step": rank_ms_res,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_families": families,
             "effective_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
-            "inference": {"value": imgs / (ms_inf / 1000.0), "unit": UNIT, "e2e": imgs / (ms_inf_e2e / 1000.0)},
-            "last_epoch_loss": loss_after}
+            "inference": inference_object(imgs, ms_inf, ms_inf_e2e, ms_inf_serial, fam_inf, args, peak_tf, peak_hbm, peak_src),
+            "loss": {"first_step": loss_first, "last_timed_step": loss_last,
+                     "note": "mean cross-entropy of the step's batch; %d synthetic batches are cycled, ln(1000) = 6.91 at random init" % nb}}
+    if not (np.isfinite(loss_last) and np.isfinite(loss_first)):
+        line["invalid"] = "non-finite loss in the timed region"
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args.size)
     else:

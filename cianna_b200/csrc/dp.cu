@@ -16,6 +16,7 @@ struct NcclApi {
 	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -33,9 +34,10 @@ static int load_nccl() {
 	g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.handle, "ncclGetUniqueId");
 	g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.handle, "ncclCommInitRank");
 	g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.handle, "ncclAllReduce");
+	g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(g_nccl.handle, "ncclBroadcast");
 	g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
 	g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
-	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.CommDestroy) {
 		set_error("libnccl is missing required symbols"); return CB200_ERR_NCCL;
 	}
 	return CB200_OK;
@@ -67,7 +69,13 @@ int cb200_dp_init(const void* id128, int rank, int world) {
 	ncclUniqueId id;
 	memcpy(&id, id128, sizeof(id));
 	CB_NCCL(g_nccl.CommInitRank(&g_comm, world, id, rank));
-	CB_CUDA(cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking));
+	{
+		// the exchange is short and everything after the backward sweep waits for it: its CTAs go first whenever an SM frees
+		// up (the weight-gradient stream has the lowest priority, the compute stream the highest - the same as this one)
+		int lo = 0, hi = 0;
+		CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CB_CUDA(cudaStreamCreateWithPriority(&g_comm_stream, cudaStreamNonBlocking, hi));
+	}
 	CB_CUDA(cudaEventCreateWithFlags(&g_ev_ready, cudaEventDisableTiming));
 	CB_CUDA(cudaEventCreateWithFlags(&g_ev_done, cudaEventDisableTiming));
 	return CB200_OK;
@@ -85,6 +93,25 @@ int cb200_dp_allreduce(float* buf, size_t n, void* after_stream) {
 	CB_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat, ncclSum, g_comm, g_comm_stream));
 	return CB200_OK;
 }
+
+int cb200_dp_after(void* stream) {
+	CB_REQUIRE_DEVICE();
+	if (g_world == 1) return CB200_OK;
+	CB_ARG(g_comm != nullptr);
+	CB_CUDA(cudaEventRecord(g_ev_ready, as_stream(stream)));
+	CB_CUDA(cudaStreamWaitEvent(g_comm_stream, g_ev_ready, 0));
+	return CB200_OK;
+}
+
+int cb200_dp_broadcast(void* buf, size_t bytes, int root, void* stream) {
+	CB_REQUIRE_DEVICE();
+	if (g_world == 1 || bytes == 0) return CB200_OK;
+	CB_ARG(g_comm != nullptr && root >= 0 && root < g_world);
+	CB_NCCL(g_nccl.Broadcast(buf, buf, bytes, ncclChar, root, g_comm, as_stream(stream)));
+	return CB200_OK;
+}
+
+int cb200_dp_rank(void) { return g_rank; }
 
 int cb200_dp_join(void* stream) {
 	CB_REQUIRE_DEVICE();

@@ -39,6 +39,7 @@ enum memory_localization_enum { NO_LOC, HOST, DEVICE };
 enum pool_types_enum { MAX_pool, AVG_pool };
 enum TC_comp_mode { FP32C_FP32A, TF32C_FP32A, FP16C_FP32A, FP16C_FP16A, BF16C_FP32A };
 
+#define CB_DP_MAX_BUCKETS 8
 typedef struct network network;
 typedef struct layer layer;
 typedef struct yolo_param yolo_param;
@@ -192,6 +193,11 @@ struct network {
 	size_t grad_arena_len;
 	int training_ready;
 	int dp_world;          /* data-parallel world size (1 = single GPU) */
+	/* gradient exchange buckets (cb_dp_plan): contiguous arena slices, each all-reduced in ONE call as soon as its
+	 * lowest layer's weight gradient is enqueued (the backward sweep runs from the last layer down) */
+	int dp_nb_bucket;
+	size_t dp_bucket_begin[CB_DP_MAX_BUCKETS], dp_bucket_len[CB_DP_MAX_BUCKETS];
+	int dp_bucket_trigger[CB_DP_MAX_BUCKETS];      /* index of the layer whose backward pass issues the bucket */
 	float last_batch_loss;
 	double last_epoch_loss;
 	float last_items_per_s;
@@ -295,6 +301,14 @@ void cb_net_io_dims(network *net, long long *out3);   /* input_dim, output_dim, 
 /* data-parallel set-up: call on every rank after init_network, before training */
 void cb_dp_unique_id(void *id128);
 void cb_dp_init(network *net, const void *id128, int rank, int world);
+/* Pure planning arithmetic (no device needed; also driven by tests/test_dp_gloo.py): lays out the gradient arena -
+ * `head` floats of group-norm sums first, then the n weight-gradient slices of len[i] floats (each rounded up to 64)
+ * in layer order - and cuts it into at most CB_DP_MAX_BUCKETS contiguous buckets for the exchange.  offset[i] receives
+ * slice i's position; bucket b is [begin[b], begin[b] + blen[b]) and is complete once slice first[b] (its lowest) is
+ * written.  Buckets are listed in the order they complete (last layers first).  Returns the number of buckets. */
+int cb_dp_plan(int n, const size_t *len, size_t head, size_t *offset, size_t *begin, size_t *blen, int *first);
+/* called by every conv / dense layer's backward pass once its weight gradient is enqueued */
+void cb_dp_layer_done(network *net, layer *current);
 /* one mini-batch from explicit host arrays (FP32, dataset layout [B][input_dim+1] and [B][output_dim]) */
 void cb_load_batch(network *net, const float *input, const float *target);
 void cb_load_batch_typed(network *net, const void *input_typed, const void *target_typed);

@@ -47,8 +47,8 @@ static void backward_dense_layer(layer *current)
 			&current->previous->activ, current->previous->output, NULL));
 	if (!current->frozen) {
 		CB_CHECK(cb200_conv_backward_weights(&p->desc, &p->w, dense_input(current), current->delta_o, NULL));
-		if (net->dp_world > 1) CB_CHECK(cb200_dp_allreduce(p->w.grad, p->grad_len, NULL));
 	}
+	cb_dp_layer_done(net, current);
 }
 
 /* value carried by the bias node this layer reads */
@@ -178,8 +178,27 @@ void dense_get_weights(layer *cur, float *dst, int moment)
 void dense_set_weights(layer *cur, const float *src)
 {
 	dense_param *p = (dense_param *)cur->param;
+	network *net = cur->c_network;
+	int k;
 	CB_CHECK(cb200_h2d(p->w.master, src, (size_t)p->in_size * (p->nb_neurons + 1) * sizeof(float), NULL));
 	CB_CHECK(cb200_stream_sync(NULL));
+	CB_CHECK(cb200_dense_prepare_weights(&p->desc, &p->w, NULL));
+	/* a dense layer reading this one's bias node holds pivot * bias_in as a constant (dense_bias_input): the pivot may
+	 * just have changed.  (Limitation kept: behind a LINEAR dense layer upstream's bias node is a trained output column -
+	 * its non-pivot rows receive gradient - whereas here it stays the constant pivot * bias_in.) */
+	for (k = cur->index + 1; k < net->nb_layers; k++) {
+		layer *next = net->net_layers[k];
+		if (next->type == DENSE && next->previous == cur) {
+			dense_param *np = (dense_param *)next->param;
+			np->desc.bias_value = dense_bias_input(next, src);
+		}
+	}
+}
+
+/* rebuild the 16-bit operand copies after the FP32 master changed in place (data-parallel parameter broadcast) */
+void dense_refresh_operands(layer *cur)
+{
+	dense_param *p = (dense_param *)cur->param;
 	CB_CHECK(cb200_dense_prepare_weights(&p->desc, &p->w, NULL));
 }
 

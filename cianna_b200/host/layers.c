@@ -160,8 +160,8 @@ static void backward_conv_layer(layer *current)
 	if (!current->frozen) {
 		void *ws = net->wgrad_stream;
 		CB_CHECK(cb200_conv_backward_weights_ex(&p->desc, &p->w, layer_input(current), current->delta_o, p->bias_grad_from_next, ws));
-		if (net->dp_world > 1) CB_CHECK(cb200_dp_allreduce(p->w.grad, p->grad_len, ws));
 	}
+	cb_dp_layer_done(net, current);
 }
 
 static void conv_alloc_weights(network *net, cb200_conv_desc *d, cb200_conv_weights *w)

@@ -226,45 +226,78 @@ void cb_dataset_read_row(network *net, Dataset *data, int index, int which, int 
 }
 
 /* ------------------------------------------------------------------ training preparation */
-static void prepare_training(network *net)
+int cb_dp_plan(int n, const size_t *len, size_t head, size_t *offset, size_t *begin, size_t *blen, int *first)
 {
-	int k;
-	size_t total = 0;
-	if (net->training_ready) return;
-	if (net->inference_only) { printf("\nERROR: network was created in inference only mode, it cannot be trained.\n"); exit(EXIT_FAILURE); }
-	for (k = 0; k < net->nb_layers; k++) {
-		layer *l = net->net_layers[k];
-		if (l->type == CONV) {
-			conv_param *p = (conv_param *)l->param;
-			p->grad_offset = total;
-			p->grad_len = cb200_conv_grad_elems(&p->desc) + p->desc.out_c;
-			total += (p->grad_len + 63) & ~(size_t)63;
-		} else if (l->type == DENSE) {
-			dense_param *p = (dense_param *)l->param;
-			p->grad_offset = total;
-			p->grad_len = cb200_conv_grad_elems(&p->desc) + p->desc.out_c;
-			total += (p->grad_len + 63) & ~(size_t)63;
+	size_t total = (head + 63) & ~(size_t)63, weights, acc, target;
+	int i, nb = 0, hi;
+	const size_t tail_cap = (size_t)1 << 20;      /* the last bucket to complete sits on the critical path: <= 4 MB */
+	for (i = 0; i < n; i++) { offset[i] = total; total += (len[i] + 63) & ~(size_t)63; }
+	if (n == 0) { if (head > 0) { begin[0] = 0; blen[0] = total; first[0] = -1; return 1; } return 0; }
+	weights = total - offset[0];
+	target = weights / 4 > tail_cap ? weights / 4 : tail_cap;      /* ~4 large buckets: launch latency, not link count */
+	/* walk from the last slice down (the order the backward sweep produces them) */
+	hi = n;             /* current bucket = slices [i, hi) */
+	acc = 0;
+	for (i = n - 1; i >= 0; i--) {
+		size_t below = offset[i] - offset[0];      /* floats of the slices under i */
+		acc += (len[i] + 63) & ~(size_t)63;
+		if (i == 0) break;
+		/* close when large enough, or when what remains below is the small tail and this bucket is not tiny itself */
+		if ((acc >= target || (below <= tail_cap && acc > tail_cap)) && nb < CB_DP_MAX_BUCKETS - 1) {
+			begin[nb] = offset[i]; blen[nb] = acc; first[nb] = i; nb++;
+			hi = i; acc = 0;
 		}
 	}
-	/* the (tiny) norm gradients sit together at the end: one all-reduce for all of them */
+	(void)hi;
+	/* the final bucket also carries the group-norm sums at the head of the arena */
+	begin[nb] = 0; blen[nb] = offset[0] + acc; first[nb] = 0; nb++;
+	return nb;
+}
+
+static void prepare_training(network *net)
+{
+	int k, n = 0, b;
+	size_t head = 0, total;
+	size_t len[MAX_LAYERS_NB], offset[MAX_LAYERS_NB];
+	int owner[MAX_LAYERS_NB], first[CB_DP_MAX_BUCKETS];
+	if (net->training_ready) return;
+	if (net->inference_only) { printf("\nERROR: network was created in inference only mode, it cannot be trained.\n"); exit(EXIT_FAILURE); }
+	/* the (tiny) group-norm gradient sums sit together at the head of the arena and travel with the last bucket */
 	for (k = 0; k < net->nb_layers; k++) {
 		layer *l = net->net_layers[k];
 		if (l->type == NORM) {
 			norm_param *p = (norm_param *)l->param;
-			p->grad_offset = total;
-			total += 2 * (size_t)p->nb_group;
+			p->grad_offset = head;
+			head += 2 * (size_t)p->nb_group;
+		} else if (l->type == CONV) {
+			conv_param *p = (conv_param *)l->param;
+			p->grad_len = cb200_conv_grad_elems(&p->desc) + p->desc.out_c;
+			len[n] = p->grad_len; owner[n++] = k;
+		} else if (l->type == DENSE) {
+			dense_param *p = (dense_param *)l->param;
+			p->grad_len = cb200_conv_grad_elems(&p->desc) + p->desc.out_c;
+			len[n] = p->grad_len; owner[n++] = k;
 		}
+	}
+	net->dp_nb_bucket = cb_dp_plan(n, len, head, offset, net->dp_bucket_begin, net->dp_bucket_len, first);
+	total = n > 0 ? offset[n - 1] + ((len[n - 1] + 63) & ~(size_t)63) : ((head + 63) & ~(size_t)63);
+	for (b = 0; b < net->dp_nb_bucket; b++) {
+		net->dp_bucket_trigger[b] = first[b] >= 0 ? owner[first[b]] : -1;
 	}
 	net->grad_arena_len = total;
 	CB_CHECK(cb200_malloc((void **)&net->grad_arena, (total ? total : 1) * sizeof(float)));
+	CB_CHECK(cb200_memset(net->grad_arena, 0, (total ? total : 1) * sizeof(float), NULL));
+	n = 0;
 	for (k = 0; k < net->nb_layers; k++) {
 		layer *l = net->net_layers[k];
 		if (l->type == CONV) {
 			conv_param *p = (conv_param *)l->param;
+			p->grad_offset = offset[n++];
 			p->w.grad = net->grad_arena + p->grad_offset;
 			p->w.grad_b = p->w.grad + cb200_conv_grad_elems(&p->desc);
 		} else if (l->type == DENSE) {
 			dense_param *p = (dense_param *)l->param;
+			p->grad_offset = offset[n++];
 			p->w.grad = net->grad_arena + p->grad_offset;
 			p->w.grad_b = p->w.grad + cb200_conv_grad_elems(&p->desc);
 		} else if (l->type == NORM) {
@@ -277,6 +310,21 @@ static void prepare_training(network *net)
 		if (!(e != NULL && e[0] != '\0' && e[0] != '0')) CB_CHECK(cb200_stream_create_low_priority(&net->wgrad_stream));
 	}
 	net->training_ready = 1;
+}
+
+/* data parallel: layer `current` has just enqueued its weight gradient (or skipped it: frozen).  If it is the lowest
+ * layer of an exchange bucket, everything the bucket holds is now enqueued - convolution weight gradients on the
+ * weight-gradient stream, dense ones, bias columns written by a following norm layer and the group-norm sums on the
+ * compute stream - and the whole slice goes out in ONE all-reduce on the communication stream. */
+void cb_dp_layer_done(network *net, layer *current)
+{
+	int b;
+	if (net->dp_world <= 1) return;
+	for (b = 0; b < net->dp_nb_bucket; b++) {
+		if (net->dp_bucket_trigger[b] != current->index) continue;
+		if (net->wgrad_stream != NULL) CB_CHECK(cb200_dp_after(NULL));
+		CB_CHECK(cb200_dp_allreduce(net->grad_arena + net->dp_bucket_begin[b], net->dp_bucket_len[b], net->wgrad_stream));
+	}
 }
 
 static void last_layer_dims(network *net, int *c, int *h, int *w)
@@ -410,19 +458,12 @@ static void output_error(network *net, const void *target_dev)
 
 static void apply_updates(network *net)
 {
-	int k, any_norm = 0;
-	size_t norm_begin = 0, norm_len = 0;
-	for (k = 0; k < net->nb_layers; k++) {
-		layer *l = net->net_layers[k];
-		if (l->type == NORM && !l->frozen) {
-			norm_param *p = (norm_param *)l->param;
-			if (!any_norm) { norm_begin = p->grad_offset; any_norm = 1; }
-			norm_len = p->grad_offset + 2 * (size_t)p->nb_group - norm_begin;
-		}
-	}
+	int k;
 	if (net->wgrad_stream != NULL) CB_CHECK(cb200_stream_wait(NULL, net->wgrad_stream));   /* all weight gradients are in */
 	if (net->dp_world > 1) {
-		if (any_norm) CB_CHECK(cb200_dp_allreduce(net->grad_arena + norm_begin, norm_len, NULL));
+		/* a network without conv / dense layers below its norm layers has no trigger layer: exchange the head now */
+		if (net->dp_nb_bucket > 0 && net->dp_bucket_trigger[net->dp_nb_bucket - 1] < 0)
+			CB_CHECK(cb200_dp_allreduce(net->grad_arena, net->dp_bucket_len[net->dp_nb_bucket - 1], NULL));
 		CB_CHECK(cb200_dp_join(NULL));
 	}
 	perf_mark(net, 2, 0);
@@ -486,12 +527,60 @@ void cb_train_step(network *net, float lr, float momentum, float weight_decay)
 
 void cb_sync(void) { CB_CHECK(cb200_device_sync()); }
 
+/* mean per-sample loss of the LAST training step that was enqueued (train_one_batch's monitor copy), after a sync */
+float cb_last_step_loss(network *net)
+{
+	int k;
+	double s = 0.0;
+	CB_CHECK(cb200_stream_sync(NULL));
+	for (k = 0; k < net->length; k++) s += net->loss_host[k];
+	return net->length > 0 ? (float)(s / net->length) : 0.0f;
+}
+
 void cb_dp_unique_id(void *id128) { CB_CHECK(cb200_dp_unique_id(id128)); }
+extern void dense_refresh_operands(layer *cur);
+
+/* Every replica starts from rank 0's parameters and optimizer state: the initialisers are time-seeded per process
+ * (init_network) and a rank may have loaded another checkpoint, and nothing but gradients is exchanged afterwards.
+ * Broadcast the FP32 master weights and momentum buffers (conv / dense) and gamma / beta with their update buffers
+ * (norm), then rebuild the 16-bit operand copies from the masters.  Call after the layers exist (and again after a
+ * load) - replicas that diverged before this call are made identical, not detected. */
+void cb_dp_sync_parameters(network *net)
+{
+	int k;
+	if (net->dp_world <= 1) return;
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->type == CONV) {
+			conv_param *p = (conv_param *)l->param;
+			size_t bytes = cb200_conv_master_elems(&p->desc) * sizeof(float);
+			CB_CHECK(cb200_dp_broadcast(p->w.master, bytes, 0, NULL));
+			if (p->w.moment != NULL) CB_CHECK(cb200_dp_broadcast(p->w.moment, bytes, 0, NULL));
+			CB_CHECK(cb200_conv_prepare_weights(&p->desc, &p->w, NULL));
+		} else if (l->type == DENSE) {
+			dense_param *p = (dense_param *)l->param;
+			size_t bytes = (size_t)p->in_size * (p->nb_neurons + 1) * sizeof(float);
+			CB_CHECK(cb200_dp_broadcast(p->w.master, bytes, 0, NULL));
+			if (p->w.moment != NULL) CB_CHECK(cb200_dp_broadcast(p->w.moment, bytes, 0, NULL));
+			dense_refresh_operands(l);
+		} else if (l->type == NORM) {
+			norm_param *p = (norm_param *)l->param;
+			size_t bytes = (size_t)p->nb_group * sizeof(float);
+			CB_CHECK(cb200_dp_broadcast(p->gamma, bytes, 0, NULL));
+			CB_CHECK(cb200_dp_broadcast(p->beta, bytes, 0, NULL));
+			if (p->gamma_update != NULL) CB_CHECK(cb200_dp_broadcast(p->gamma_update, bytes, 0, NULL));
+			if (p->beta_update != NULL) CB_CHECK(cb200_dp_broadcast(p->beta_update, bytes, 0, NULL));
+		}
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+}
+
 void cb_dp_init(network *net, const void *id128, int rank, int world)
 {
 	CB_CHECK(cb200_dp_init(id128, rank, world));
 	net->dp_world = world;
 	net->drop_seed += 0xD1B54A32D192ED03ULL * (unsigned long long)(rank + 1);   /* each rank draws its own dropout masks */
+	cb_dp_sync_parameters(net);
 }
 
 /* ------------------------------------------------------------------ training loop */
@@ -654,7 +743,7 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		double total_error = 0.0, t_epoch = now_s();
 		float lr = u_end_learning_rate + (u_begin_learning_rate - u_end_learning_rate) * expf(-net->decay * net->iter);
 		if (silent < 1) printf("\n");
-		int shuffled = 0, next_epoch_first = -1;
+		int shuffled = 0, next_epoch_first = -1, batch_loc = 0, sgd_next = 0;
 		net->iter++;
 		if (shuffle_every > 0 && (net->iter + 1) % shuffle_every == 0 && net->batch_param != SGD) {
 			/* no copy of the previous epoch may still be reading the host batches */
@@ -670,6 +759,7 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 		if (i + 1 < nb_iter && !(shuffle_every > 0 && (net->iter + 2) % shuffle_every == 0 && net->batch_param != SGD))
 			next_epoch_first = 0;
 		net->is_inference = 0;
+		net->inference_drop_mode = AVG_MODEL;      /* src/auxil.c:1793: the in-training validation pass never draws masks */
 		for (j = 0; j < net->train.nb_batch; j++) {
 			double t_batch = now_s(), batch_error = 0.0;
 			/* perf_eval: the first batch of the first epoch and of every 16th epoch is timed layer by layer, with the weight
@@ -677,6 +767,14 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 			const int sample = net->perf_eval && j == 0 && (net->perf_n == 0 || net->iter % 16 == 0);   /* (a sample, not a census) */
 			void *side = net->wgrad_stream;
 			if (sample) { perf_begin_sample(net); net->wgrad_stream = NULL; }
+			/* batch_size == 1 ("SGD" scheme): a random sample per step instead of a sweep (src/auxil.c:1806-1809); the draw for
+			 * the next step is made now so that its host->device copy can still be prefetched */
+			if (net->batch_param == SGD) {
+				if (j == 0) sgd_next = (int)((rand() / ((double)RAND_MAX + 1.0)) * net->train.size);
+				batch_loc = sgd_next;
+				sgd_next = (int)((rand() / ((double)RAND_MAX + 1.0)) * net->train.size);
+				train_one_batch(net, &net->train, batch_loc, !net->dynamic_load, j + 1 < net->train.nb_batch ? sgd_next : -1);
+			} else
 			train_one_batch(net, &net->train, j, !net->dynamic_load, j + 1 < net->train.nb_batch ? j + 1 : next_epoch_first);
 			CB_CHECK(cb200_stream_sync(NULL));
 			if (sample) { net->wgrad_stream = side; perf_end_sample(net); }
@@ -742,20 +840,38 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		CB_CHECK(cb200_malloc((void **)&out_dev, out_elems * sizeof(float)));
 		CB_CHECK(cb200_host_alloc((void **)&out_host, out_elems * sizeof(float)));
 	}
-	if (!net->dynamic_load) dataset_upload(net, &data);
+	if (!net->dynamic_load && data.input_device == NULL) {
+		/* `data` is a by-value copy (upstream's signature): make the device-resident copies on the network's own object so
+		 * that they are created once and found again on the next call */
+		Dataset *own = data.input == net->valid.input ? &net->valid : data.input == net->test.input ? &net->test :
+			data.input == net->train.input ? &net->train : NULL;
+		if (own != NULL) { dataset_upload(net, own); data = *own; }
+		else dataset_upload(net, &data);      /* a caller-owned Dataset: the copy lives as long as the caller keeps `data` */
+	}
+	if (repeat < 1) repeat = 1;
 	net->is_inference = 1;
+	stage_invalidate(net);
 	for (j = 0; j < data.nb_batch; j++) {
 		const void *tgt;
+		int r, repeat_start = 0;
 		net->length = (j == data.nb_batch - 1 && data.size % net->batch_size > 0) ? data.size % net->batch_size : net->batch_size;
 		if (net->dynamic_load) {
-			cb_load_batch_typed(net, data.input[j], data.target[j]);
-			use_device_batch(net, net->input_raw);
-			tgt = net->target;
+			/* batch j + 1 travels host -> device on the copy stream while batch j computes (upstream: blocking copy per batch) */
+			int slot = stage_acquire(net, data.input[j], data.target[j],
+				j + 1 < data.nb_batch ? data.input[j + 1] : NULL, j + 1 < data.nb_batch ? data.target[j + 1] : NULL);
+			use_device_batch(net, net->stage_in[slot]);
+			tgt = net->stage_tg[slot];
 		} else {
 			use_device_batch(net, data.input_device[j]);
 			tgt = data.target_device[j];
 		}
-		for (k = 0; k < net->nb_layers; k++) net->net_layers[k]->forward(net->net_layers[k]);
+		/* MC-dropout: `repeat` forward passes per batch, restarted from the first layer that has dropout (everything
+		 * below it is deterministic), every pass saved and counted in the loss (src/auxil.c:1216-1226) */
+		for (r = 0; r < repeat; r++) {
+		for (k = repeat_start; k < net->nb_layers; k++) {
+			if (repeat_start == 0 && net->net_layers[k]->dropout_rate > 0.01f) repeat_start = k;
+			net->net_layers[k]->forward(net->net_layers[k]);
+		}
 		if (!net->no_error) {
 			output_error(net, tgt);
 			CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
@@ -794,7 +910,8 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 				}
 		}
 		if (saving > 0) {
-			/* one line / record per sample, sample-major like upstream's fwd_res files (src/auxil.c:1346-1400) */
+			/* one line / record per sample, sample-major like upstream's fwd_res files (src/auxil.c:1346-1400); with
+			 * repeat > 1 the file holds, batch after batch, `repeat` consecutive blocks of the batch's samples */
 			int b, o, per = last->type == DENSE ? c : c * h * w;
 			for (b = 0; b < net->length; b++) {
 				for (o = 0; o < per; o++) {
@@ -805,24 +922,28 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 				if (saving == 1) fprintf(f_save, "\n");
 			}
 		}
+		}
 	}
 	net->last_items_per_s = (float)(data.size / (now_s() - t0));
-	net->last_epoch_loss = data.size > 0 ? total_error / data.size : 0.0;
+	/* mean over samples AND repeats on the screen (src/auxil.c:1506-1513); error.txt keeps upstream's total / data.size */
+	net->last_epoch_loss = data.size > 0 ? total_error / ((double)data.size * repeat) : 0.0;
+	if (!net->no_error && isnan(total_error)) { printf("\nERROR: Network divergence detected (Nan)!\n\n"); exit(EXIT_FAILURE); }
 	if (silent < 1) {
+		const double norm = (double)data.size * repeat;
 		printf("\n%*s", 14, " ");
-		printf("Average forward perf: %0.2f it/s |", net->last_items_per_s);
-		if (!net->no_error) printf(" Cumulated error: \t %g", net->last_epoch_loss);
+		printf("Average forward perf : %0.2f it/s ", net->last_items_per_s);
+		if (!net->no_error) printf("| Mean Loss: %.5g", net->last_epoch_loss);
 		if (!net->no_error && yolo != NULL && data.size > 0)
 			printf("\nLoss dist. ||Pos: %.5f |Size: %.5f |Prob: %.5f |Obj: %.5f |Class: %.5f |Param: %.5f ||M IoU = %.4f |M Obj = %0.4f |P Good = %0.4f",
-				part_err[0] / data.size, part_err[1] / data.size, part_err[2] / data.size, part_err[3] / data.size, part_err[4] / data.size,
-				part_err[5] / data.size, sum_IoU / nb_IoU, sum_obj / nb_IoU, (float)nb_good_IoU / (float)nb_IoU);
+				part_err[0] / norm, part_err[1] / norm, part_err[2] / norm, part_err[3] / norm, part_err[4] / norm,
+				part_err[5] / norm, sum_IoU / nb_IoU, sum_obj / nb_IoU, (float)nb_good_IoU / (float)nb_IoU);
 		printf("\n");
 	}
 	if (net->no_error == 0 && silent != 1) {
 		/* learning-curve file, same columns as upstream (src/auxil.c:1528-1547) */
 		FILE *f_err = fopen("error.txt", "a");
 		if (f_err != NULL) {
-			fprintf(f_err, "%d %g", net->iter, net->last_epoch_loss);
+			fprintf(f_err, "%d %g", net->iter, data.size > 0 ? total_error / data.size : 0.0);
 			if (yolo != NULL && data.size > 0)
 				fprintf(f_err, " %g %g %g %g %g %g", part_err[0] / data.size, part_err[1] / data.size, part_err[2] / data.size,
 					part_err[3] / data.size, part_err[4] / data.size, part_err[5] / data.size);
@@ -876,6 +997,7 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 void forward_testset(network *net, int saving, int repeat, int drop_mode, int silent)
 {
 	if (net->test.input == NULL) { printf("\nERROR: no TEST dataset defined\n"); exit(EXIT_FAILURE); }
+	if (repeat > 1 && silent != 1) printf("Forwarding with repeat = %d\n", repeat);
 	net->inference_drop_mode = drop_mode;
 	net->is_inference = 1;
 	compute_error(net, net->test, saving, 0, repeat, silent);

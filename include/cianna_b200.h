@@ -462,7 +462,14 @@ int cb200_dp_world(void);
  * after everything enqueued so far on `after_stream`; cb200_dp_join makes `stream` wait for all
  * all-reduces issued so far.  No-ops when world == 1. */
 int cb200_dp_allreduce(float* buf, size_t n, void* after_stream);
+/* the communication stream additionally waits for everything enqueued so far on `stream` (a bucket whose
+ * gradients were produced on two streams: cb200_dp_after(a); cb200_dp_allreduce(buf, n, b)) */
+int cb200_dp_after(void* stream);
 int cb200_dp_join(void* stream);
+/* in-place broadcast of `bytes` bytes from rank `root`, enqueued on `stream` (replica initialisation:
+ * every rank must start from rank 0's parameters and optimizer state) */
+int cb200_dp_broadcast(void* buf, size_t bytes, int root, void* stream);
+int cb200_dp_rank(void);
 int cb200_dp_finalize(void);
 
 #ifdef __cplusplus

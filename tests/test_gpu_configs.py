@@ -2,8 +2,8 @@
 at 416 px, the SKA SDC1 17-conv YOLO detector at 512 px (stride-2 convolutions, dropout, 1360 target slots), the
 dense-heavy extinction-profile regression network at 64 px, and the MNIST example network with its dropout.
 
-No reference output exists at these sizes (the CPU reference needs minutes per step), so the checks are the
-size-independent ones: every tensor finite, the sample axis is independent (a permuted batch gives the permuted output),
+The checks here are the size-independent ones (values against the reference at full size: the headline network in
+tests/test_gpu_darknet19_full.py): every tensor finite, the sample axis is independent (a permuted batch gives the permuted output),
 a partially filled batch equals the full one on its samples, repeated steps on one batch reduce its loss, YOLO
 association states are consistent with the targets.  Step times are written to gpurun_out/configs_report.json
 (host wall clock around a synchronising read-back: a secondary table, not bench.py's metric).
@@ -128,6 +128,48 @@ def test_yolo_detectors_at_full_size(cnn, name):
     cnn.forward_batch(half, is_inference=1, network=0)
     p = cnn.layer_output(last, network=0)
     assert np.abs(p[:, :half, :] - a[:, :half, :]).max() < 2e-3 * scale
+
+
+def test_darknet19_448_headline_batch_128(cnn):
+    """the bench configuration itself (Darknet19 448 px, FP16C_FP32A, batch 128, upstream's hyper-parameters): finite
+    tensors, loss reduced by repeated steps on one batch, sample-axis independence, partial batch = full batch on its
+    samples.  (Values against the reference at this size: tests/test_gpu_darknet19_full.py, batch 16.)"""
+    import ctypes
+    B = 128
+    spec = configs.darknet19(B, 448, 1000)
+    _build(cnn, spec, "FP16C_FP32A")
+    cnn.set_TC_scale_factor(256.0, network=0)
+    rng = np.random.default_rng(11)
+    dim = 448 * 448 * 3
+    x = np.zeros((B, dim + 1), np.float32)
+    x[:, :dim] = (rng.random((B, dim), dtype=np.float32) * 255.0 - 100.0) / 155.0
+    x[:, dim] = 0.1
+    t = np.zeros((B, 1000), np.float32)
+    t[np.arange(B), rng.integers(0, 1000, B)] = 1.0
+    last = len(spec["layers"]) - 1
+    cnn.load_batch(x, t, network=0)
+    losses = []
+    for _ in range(12):
+        cnn.forward_batch(network=0)
+        losses.append(cnn.batch_loss(network=0))
+        cnn.backward_batch(0.003, 0.9, 0.0002, network=0)
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 0.05, losses
+    for i in (0, 1, last // 2, last - 1, last):
+        assert np.isfinite(cnn.layer_delta(i, network=0)).all(), i
+    dt = _time_steps(cnn, 5, 0.0)
+    REPORT["darknet19_448_b128"] = {"batch": B, "mode": "FP16C_FP32A", "ms_per_step": 1e3 * dt, "img_per_s": B / dt, "loss_first_last": [losses[0], losses[-1]]}
+    cnn.forward_batch(is_inference=1, network=0)
+    a = cnn.layer_output(last, network=0)
+    assert np.isfinite(a).all() and np.allclose(a.sum(axis=0), 1.0, atol=2e-3)
+    cnn.load_batch(x[::-1].copy(), t[::-1].copy(), network=0)
+    cnn.forward_batch(is_inference=1, network=0)
+    r = cnn.layer_output(last, network=0)
+    assert np.abs(r[:, ::-1, :] - a).max() < 2e-3 * np.abs(a).max()
+    cnn.load_batch(x, t, network=0)
+    cnn.forward_batch(B // 2 + 3, is_inference=1, network=0)
+    p = cnn.layer_output(last, network=0)
+    assert np.abs(p[:, :B // 2 + 3, :] - a[:, :B // 2 + 3, :]).max() < 2e-3 * np.abs(a).max()
+    assert np.abs(p[:, B // 2 + 3:, :]).max() == 0.0
 
 
 def test_extinction_profile_regression_at_full_size(cnn):

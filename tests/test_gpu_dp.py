@@ -25,4 +25,4 @@ def test_two_gpu_step_equals_single_gpu_step(mode):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "scripts", "dp_check.py"), mode]
     r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert "DP_CHECK_OK" in r.stdout, r.stdout[-3000:]
+    assert r.returncode == 0 and "DP_CHECK_OK" in r.stdout and "DP_CHECK_FAIL" not in r.stdout, r.stdout[-3000:]

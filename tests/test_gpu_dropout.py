@@ -223,3 +223,70 @@ def test_mnist_example_network_with_its_dropout_trains(cnn):
     cnn.forward_batch(is_inference=1, network=0)
     pred = cnn.layer_output(6, network=0)[:, :10].argmax(axis=1)
     assert (pred == lab).mean() > 0.8
+
+
+@pytest.mark.skipif(not rd.ref_loader.available("serial"), reason="oracle/_ref not present on this box")
+def test_forward_repeat_mc_dropout_file_matches_reference_layout(cnn, tmp_path, monkeypatch):
+    """forward(repeat=N): every batch is forwarded N times from the first dropout layer on and every pass is written to
+    fwd_res (src/auxil.c:1216-1226, 1346-1400).  AVG_MODEL has no randomness: the product's file must equal the one the
+    compiled reference writes for the same network, weights and TEST set (10 samples, batch 6: a partial last batch), value
+    for value and record for record.  MC_MODEL: same record layout, passes differ from each other, the part below the
+    first dropout layer is not re-drawn (layer 0 has dropout here, so every pass is a full pass), and the mean over many
+    passes approaches the AVG_MODEL prediction."""
+    spec = netdefs.dropout_net(batch=6, size=12)
+    kinds = [k for k, _ in spec["layers"]]
+    n, rep = 10, 3
+    rng = np.random.default_rng(21)
+    dim = 12 * 12 * 2
+    data = (rng.random((n, dim), dtype=np.float32) - 0.4).astype(np.float32)
+    targ = np.zeros((n, 5), np.float32)
+    targ[np.arange(n), rng.integers(0, 5, n)] = 1
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "mine").mkdir()
+    monkeypatch.chdir(tmp_path / "ref")
+    ref = rd.RefNet(spec, "C_BLAS")
+    w0 = {i: ref.weights_view(i).copy() for i, k in enumerate(kinds) if k in ("conv", "dense")}
+    with rd._Quiet():
+        ref.cnn.create_dataset("TEST", n, data, targ, network=0, silent=1)
+        ref.cnn.forward(saving=2, drop_mode="AVG_MODEL", repeat=rep, network=0, silent=1)
+    theirs = np.fromfile(tmp_path / "ref" / "fwd_res" / "net0_0000.dat", dtype=np.float32)
+    monkeypatch.chdir(tmp_path / "mine")
+    with rd._Quiet():
+        rd.build_network(cnn, spec, "C_CUDA", "off", network=0)
+    for i, w in w0.items():
+        cnn.set_layer_weights(i, w)
+    cnn.set_dropout_seed(5, network=0)
+    with rd._Quiet():
+        cnn.create_dataset("TEST", n, data, targ, network=0, silent=1)
+        cnn.forward(saving=2, drop_mode="AVG_MODEL", repeat=rep, network=0, silent=1)
+    mine = np.fromfile(tmp_path / "mine" / "fwd_res" / "net0_0000.dat", dtype=np.float32)
+    assert mine.size == theirs.size == n * rep * 5
+    assert rel_err(mine, theirs) < 1e-5
+    # record layout: batch after batch, `rep` consecutive blocks of the batch's samples
+    blocks = [mine[:6 * rep * 5].reshape(rep, 6, 5), mine[6 * rep * 5:].reshape(rep, 4, 5)]
+    for blk in blocks:
+        for r in range(1, rep):
+            assert np.array_equal(blk[r], blk[0])
+    avg = np.concatenate([blocks[0][0], blocks[1][0]])
+    loss_avg = cnn.last_perf(network=0)[1]
+    ref_loss = float(-(targ * np.log(np.maximum(avg, 1e-6))).sum() / n)
+    assert abs(loss_avg - ref_loss) < 1e-4 * max(1.0, ref_loss)        # mean over samples AND repeats
+    # MC_MODEL
+    rep_mc = 64
+    with rd._Quiet():
+        cnn.forward(saving=2, drop_mode="MC_MODEL", repeat=rep_mc, network=0, silent=1)
+    mc = np.fromfile(tmp_path / "mine" / "fwd_res" / "net0_0000.dat", dtype=np.float32)
+    assert mc.size == n * rep_mc * 5
+    b0 = mc[:6 * rep_mc * 5].reshape(rep_mc, 6, 5)
+    assert not np.array_equal(b0[0], b0[1])
+    assert np.allclose(b0.sum(axis=2), 1.0, atol=1e-4)
+    assert np.abs(b0.mean(axis=0) - blocks[0][0]).max() < 0.15
+    # training afterwards goes back to AVG_MODEL for its validation pass (src/auxil.c:1793)
+    with rd._Quiet():
+        cnn.create_dataset("TRAIN", n, data, targ, network=0, silent=1)
+        cnn.create_dataset("VALID", n, data, targ, network=0, silent=1)
+        cnn.train(nb_iter=1, learning_rate=0.0, control_interv=1, shuffle_every=0, silent=1, network=0)
+    a = cnn.last_perf(network=0)[1]
+    with rd._Quiet():
+        cnn.train(nb_iter=1, learning_rate=0.0, control_interv=1, shuffle_every=0, silent=1, network=0)
+    assert cnn.last_perf(network=0)[1] == a        # no masks drawn: two validation passes agree exactly

@@ -19,8 +19,6 @@ gpurun_out/parity_report.json.  Pool argmax maps must be identical in FP32.
 import json
 import os
 
-import time
-
 import numpy as np
 import pytest
 
@@ -147,83 +145,63 @@ def test_training_step_matches_golden(cnn, name, mode):
     assert not bad, bad
 
 
+def _seeded_weights(ref, cnn, kinds, seed):
+    """ONE deterministic draw on both sides: He-normal filters written straight into the reference's own weight arrays
+    (its generators are time-seeded, src/auxil.c:164) and into the product"""
+    rng = np.random.default_rng(seed)
+    for i, k in enumerate(kinds):
+        if k in ("conv", "dense"):
+            w = ref.weights_view(i)
+            w[...] = (rng.standard_normal(w.shape) * np.sqrt(2.0 / w.shape[1])).astype(np.float32)
+            cnn.set_layer_weights(i, w)
+        elif k == "norm":
+            g, b = ref.norm_view(i, "gamma"), ref.norm_view(i, "beta")
+            g[...] = (1.0 + 0.2 * rng.standard_normal(g.shape)).astype(np.float32)
+            b[...] = (0.1 * rng.standard_normal(b.shape)).astype(np.float32)
+            cnn.set_layer_weights(i, np.concatenate([g, b]))
+
+
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref not present on this box")
 @pytest.mark.parametrize("mode", ["off", "FP16C_FP32A"])
 def test_training_steps_match_live_reference(cnn, mode):
-    """fresh seeds, three consecutive steps with momentum and weight decay, against the compiled reference.
-    The reference draws its weights from a time-seeded generator, and in this tiny network (8 images of 16 x 16) a draw
-    in which some leaky-ReLU pre-activation lands within rounding of zero decides x1 vs x0.05 differently on the two
-    sides (measured: about one draw in five, deviations of 1e-3..7e-3 that the flip accounting below does not always
-    attribute).  A wrong kernel fails EVERY draw, so the comparison is repeated on a new draw, at most three times."""
-    failures = []
-    for attempt in range(3):
-        try:
-            _live_reference_once(cnn, mode)
-            REPORT.setdefault("live/%s" % mode, {})["attempts"] = attempt + 1
-            return
-        except (AssertionError, ValueError) as e:
-            failures.append(repr(e)[:300])
-            time.sleep(1.1)          # next second -> next seed of the reference
-    raise AssertionError("three independent draws failed: %s" % failures)
-
-
-def _live_reference_once(cnn, mode):
+    """three consecutive steps with momentum and weight decay next to the compiled reference run live, on seeded inputs
+    and SEEDED weights injected into both sides: one deterministic draw, one strict comparison, no retry.
+    FP32: every step's output, first-layer delta and the final weights at 3 x 1e-5 (three chained optimizer steps);
+    FP16: outputs at 3 x 2e-2 max-norm, final weights at 3 x 2e-2 in relative L2."""
     spec = netdefs.tc_darknet(batch=8, size=16, classes=16)
     kinds = _layer_kinds(spec)
     ref = rd.RefNet(spec, "C_BLAS")
     _build(cnn, spec, mode)
     S = 64.0 if mode == "FP16C_FP32A" else 1.0
     cnn.set_TC_scale_factor(S, network=0)
-    gerr = rel_err if mode == "off" else rel_l2
-    for i, k in enumerate(kinds):
-        if k in ("conv", "dense"):
-            cnn.set_layer_weights(i, ref.weights_view(i))
-    tol = TOL[mode] * 3     # three chained optimizer steps
-    # In this tiny network (8 images of 16 x 16) ONE element taking the other leaky-ReLU slope in the backward pass (x1 vs
-    # x0.05; its pre-activation is within rounding of zero, the reference's weights are time-seeded) moves the next step's
-    # weights and outputs by ~1e-3 relative (observed: 7e-3 on delta, 1e-3 on the following output).  Such flips are
-    # detected image by image on the first layer's delta, counted in the report, and only then the later comparisons of
-    # this run are held to 100 x tol (3e-3 in FP32) - a wrong kernel is off by orders of magnitude more.
-    FLIP_SLACK = 100
-    n_flips = 0
+    # (the seed was screened offline with the reference alone: over the three steps the smallest leaky-ReLU pre-activation
+    #  of this draw is 2.4e-6 of its layer's largest, an order of magnitude above FP32 summation-order noise, so no slope
+    #  decision depends on who sums first)
+    _seeded_weights(ref, cnn, kinds, seed=2033)
+    tol = TOL[mode] * 3
+    rep = REPORT.setdefault("live/%s" % mode, {})
+    last = len(kinds) - 1
     for step in range(3):
         x, t = rd.make_inputs(spec, 100 + step)
         ref.forward(x)
         cnn.load_batch(x, t)
         cnn.forward_batch()
-        last = len(kinds) - 1
         e_out = rel_err(cnn.layer_output(last), ref.output(last))
-        REPORT.setdefault("live/%s" % mode, {})["out_step%d" % step] = e_out
-        assert e_out < tol * (FLIP_SLACK if n_flips else 1), (step, e_out)      # (weights after a counted flip: see below)
+        rep["out_step%d" % step] = e_out
+        assert e_out < tol, (step, e_out)
         ref.backward(t, 0.05, 0.9, 0.0005)
         cnn.backward_batch(0.05, 0.9, 0.0005)
-        if mode == "off":     # (mixed precision deltas: see the conditioned-oracle comparison above)
-            # elements whose pre-activation is within rounding of zero may take the other leaky-ReLU slope (x1 vs x0.05):
-            # they are counted and excluded, everything else must match
-            r0, m0 = ref.output(0), cnn.layer_output(0)
-            big = np.abs(r0) > 1e-5 * np.abs(r0).max()
-            assert np.all((r0 > 0)[big] == (m0 > 0)[big])
-            sure = big
-            REPORT["live/%s" % mode]["relu_near_zero_step%d" % step] = int((~big).sum())
-            assert (~big).mean() < 1e-3
-            # The same can happen at a ReLU of a DEEPER layer (the reference's weights are time-seeded): one element taking
-            # the other slope changes delta(0) inside that element's receptive field of ONE image by a few 1e-3.  Compare
-            # image by image: all of them within tolerance, except that at most one per step may carry such a flip
-            # (bounded, counted in the report) - anything systematic shows in every image.
-            d_mine, d_ref = np.where(sure, cnn.layer_delta(0) / S, 0), np.where(sure, ref.delta(0), 0)
-            scale = np.abs(d_ref).max()
-            per_image = np.abs(d_mine - d_ref).max(axis=(0, 2)) / scale
-            # (after a counted flip every image sees slightly different weights: same slack as the other comparisons)
-            flipped = per_image >= 5 * tol * (FLIP_SLACK if n_flips else 1)
-            REPORT["live/%s" % mode]["delta0_step%d" % step] = float(per_image[~flipped].max()) if (~flipped).any() else float(per_image.max())
-            REPORT["live/%s" % mode]["deep_relu_flips_step%d" % step] = int(flipped.sum())
-            assert flipped.sum() <= 2 and per_image.max() < 0.05, (step, per_image.tolist())
-            n_flips += int(flipped.sum())
-    # (a flipped element also enters the weight gradients of the layers below it: looser bound only after one occurred)
-    wtol = tol * (FLIP_SLACK if n_flips else 1)
+        if mode == "off":
+            e_d = rel_err(cnn.layer_delta(0) / S, ref.delta(0))
+            rep["delta0_step%d" % step] = e_d
+            assert e_d < tol, (step, e_d)
+    gerr = rel_err if mode == "off" else rel_l2
     for i, k in enumerate(kinds):
-        if k == "conv":
-            assert gerr(cnn.layer_weights(i), ref.weights_view(i)) < wtol, i
+        if k in ("conv", "norm"):
+            w_ref = ref.weights_view(i) if k == "conv" else np.concatenate([ref.norm_view(i, "gamma"), ref.norm_view(i, "beta")])
+            e_w = gerr(cnn.layer_weights(i), w_ref)
+            rep["w_%d" % i] = e_w
+            assert e_w < tol, (i, e_w)
 
 
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref not present on this box")
