@@ -153,11 +153,20 @@ def delete_dataset(dataset, network=None, silent=0):
     L.free_dataset(L.cb_net_dataset(_net(network), _s(dataset)))
 
 
-def shuffle_dataset(dataset="TRAIN", network=None):
-    """the permutation train() applies every shuffle_every epochs, on demand"""
+def shuffle_dataset(dataset="TRAIN", network=None, device=False):
+    """the permutation train() applies every shuffle_every epochs, on demand; device=True: the on-device variant of
+    train(shuffle_gpu=1) for a resident set (dynamic_load=0)"""
     L = _load()
-    L.shuffle_dataset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    L.shuffle_dataset(_net(network), L.cb_net_dataset(_net(network), _s(dataset)))
+    fn = L.shuffle_dataset_device if device else L.shuffle_dataset
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    fn(_net(network), L.cb_net_dataset(_net(network), _s(dataset)))
+
+
+def upload_dataset(dataset="TRAIN", network=None):
+    """make the set device-resident now (train() does it itself when dynamic_load=0)"""
+    L = _load()
+    L.dataset_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dataset_upload(_net(network), L.cb_net_dataset(_net(network), _s(dataset)))
 
 
 def dataset_rows(dataset, indices, network=None, device=False):

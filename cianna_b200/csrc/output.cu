@@ -87,6 +87,41 @@ __global__ void output_loss_kernel(float* __restrict__ loss, const T* __restrict
 	s = block_reduce(s, red, false);
 	if (threadIdx.x == 0) loss[b] = s;
 }
+
+// per-ELEMENT loss in upstream's own table layout (what *_output_error kernels fill: conv / pool outputs
+// err[ch][batch][hw], dense outputs err[b][c + 1] with the bias node left at zero) - only the upstream-side back-end shim
+// needs it (upstream's host code sums the table itself, src/auxil.c:1871-1913); the host library reduces on the device.
+template <typename T>
+__global__ void output_error_elems_kernel(float* __restrict__ err, const T* __restrict__ y, const T* __restrict__ target,
+                                          int batch, int length, int c, int cp, int hw, int kind, int dense) {
+	const size_t total = (size_t)length * hw * c;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int ch = (int)(i % c);
+		const size_t pix = i / c;
+		const int p = (int)(pix % hw);
+		const int b = (int)(pix / hw);
+		const float o = to_f32<T>(y[((size_t)b * hw + p) * cp + ch]);
+		const float t = to_f32<T>(target[((size_t)b * c + ch) * hw + p]);
+		const float e = kind == 0 ? 0.5f * (o - t) * (o - t) : -t * logf(o > 0.000001f ? o : 0.000001f);
+		if (dense) err[(size_t)b * (c + 1) + ch] = e;
+		else err[((size_t)ch * batch + b) * hw + p] = e;
+	}
+}
+
+// YOLO: the loss monitor of this library reduces to one value + six parts per image; upstream's host code re-derives
+// the six parts by summing the per-element table by channel class (src/auxil.c:1429-1455).  Each part is written to the
+// first element of its class (box 0, cell 0: position x / size w / probability / objectness / first class / first
+// parameter channel) of upstream's table err[ch][batch][cells]; every sum upstream forms is preserved.
+__global__ void yolo_scatter_parts_kernel(float* __restrict__ err, const float* __restrict__ parts, int batch, int length,
+                                          int cells, int nb_class, int nb_param) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= length) return;
+	const int ch_of_part[6] = {0, 3, 6, 7, 8, 8 + nb_class};
+	for (int k = 0; k < 6; k++) {
+		if ((k == 4 && nb_class <= 0) || (k == 5 && nb_param <= 0)) continue;
+		err[((size_t)ch_of_part[k] * batch + b) * cells] = parts[(size_t)b * 6 + k];
+	}
+}
 }  // namespace cb200
 using namespace cb200;
 
@@ -121,6 +156,26 @@ int cb200_output_loss(float* loss, const void* y, const void* target, int dtype,
 	CB_REQUIRE_DEVICE();
 	CB_DISPATCH_DTYPE(dtype, T, (output_loss_kernel<T><<<batch, 256, 0, as_stream(s)>>>(
 		loss, (const T*)y, (const T*)target, length, c, round8(c), h * w, kind)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_output_error_elems(float* err, const void* y, const void* target, int dtype, int batch, int length,
+                             int c, int h, int w, int kind, int dense_layout, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_ARG(err != nullptr && batch > 0 && c > 0);
+	long long total = (long long)length * h * w * c;
+	if (total <= 0) return CB200_OK;
+	CB_DISPATCH_DTYPE(dtype, T, (output_error_elems_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(
+		err, (const T*)y, (const T*)target, batch, length, c, round8(c), h * w, kind, dense_layout)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_yolo_scatter_parts(float* err, const float* parts, int batch, int length, int cells, int nb_class, int nb_param, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_ARG(err != nullptr && parts != nullptr && batch > 0 && cells > 0);
+	yolo_scatter_parts_kernel<<<(batch + 127) / 128, 128, 0, as_stream(s)>>>(err, parts, batch, length, cells, nb_class, nb_param);
 	CB_LAUNCH_CHECK();
 	return CB200_OK;
 }

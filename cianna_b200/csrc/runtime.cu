@@ -207,6 +207,46 @@ __global__ void cast_to_f32_kernel(float* __restrict__ dst, const T* __restrict_
 		dst[i] = to_f32<T>(src[i]);
 }
 
+// dataset conversion on the device: round toward zero, value for value what the reference's host loop produces
+// (copy_to_FP16 / copy_to_BF16 with __float2half_rz / __float2bfloat16_rz, src/cuda/cuda_main.cu:108-113,790,813)
+template <typename T> __device__ __forceinline__ T from_f32_rz(float v);
+template <> __device__ __forceinline__ float from_f32_rz<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32_rz<__half>(float v) { return __float2half_rz(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32_rz<__nv_bfloat16>(float v) { return __float2bfloat16_rz(v); }
+template <typename T>
+__global__ void cast_from_f32_rz_kernel(T* __restrict__ dst, const float* __restrict__ src, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		dst[i] = from_f32_rz<T>(src[i]);
+}
+
+// FP32 sample rows [rows][src_row] -> typed dataset rows [rows][dst_row] (dst_row >= src_row; the extra slots, the bias
+// slot of an input row, take tail_value), round toward zero
+template <typename T>
+__global__ void dataset_pack_kernel(T* __restrict__ dst, const float* __restrict__ src, size_t rows, size_t src_row, size_t dst_row, float tail_value) {
+	const size_t total = rows * dst_row;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t r = i / dst_row, c = i - r * dst_row;
+		dst[i] = from_f32_rz<T>(c < src_row ? src[r * src_row + c] : tail_value);
+	}
+}
+
+// dataset shuffle: row i of the source batches goes to row index[i] of the destination batches (index == nullptr:
+// identity = the copy back).  One warp per row, 16-byte chunks when the row pitch allows, else 2- or 4-byte elements.
+// Replaces shfl_kern / get_back_shuffle (src/cuda/cuda_main.cu:590-640: one THREAD per row there, uncoalesced).
+template <typename V>
+__global__ void rows_permute_kernel(void* const* __restrict__ dst_batches, void* const* __restrict__ src_batches,
+                                    const int* __restrict__ index, long long n_rows, int batch_size, size_t row_units) {
+	const int lane = threadIdx.x & 31;
+	const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+	const long long nwarp = (gridDim.x * (long long)blockDim.x) >> 5;
+	for (long long i = warp0; i < n_rows; i += nwarp) {
+		const long long j = index != nullptr ? (long long)index[i] : i;
+		const V* s = (const V*)src_batches[i / batch_size] + (size_t)(i % batch_size) * row_units;
+		V* d = (V*)dst_batches[j / batch_size] + (size_t)(j % batch_size) * row_units;
+		for (size_t k = lane; k < row_units; k += 32) d[k] = s[k];
+	}
+}
+
 // ---------------------------------------------------------------- layout conversions
 // dataset row [C*H*W + 1] (channel-major planes, bias slot last) -> act[b][y][x][Cp]
 template <typename T>
@@ -333,6 +373,40 @@ int cb200_cast_to_f32(float* dst, const void* src, int dtype, size_t n, void* s)
 	return CB200_OK;
 }
 
+int cb200_cast_from_f32_rz(void* dst, int dtype, const float* src, size_t n, void* s) {
+	CB_REQUIRE_DEVICE();
+	if (n == 0) return CB200_OK;
+	CB_DISPATCH_DTYPE(dtype, T, (cast_from_f32_rz_kernel<T><<<grid_for((long long)n, 256), 256, 0, as_stream(s)>>>((T*)dst, src, n)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_dataset_pack(void* dst, int dtype, const float* src, size_t rows, size_t src_row, size_t dst_row, float tail_value, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_ARG(dst_row >= src_row);
+	if (rows == 0 || dst_row == 0) return CB200_OK;
+	CB_DISPATCH_DTYPE(dtype, T, (dataset_pack_kernel<T><<<grid_for((long long)(rows * dst_row), 256), 256, 0, as_stream(s)>>>((T*)dst, src, rows, src_row, dst_row, tail_value)));
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
+int cb200_rows_permute(void* const* dst_batches, void* const* src_batches, const int* index, long long n_rows, int batch_size,
+                       size_t row_bytes, void* s) {
+	CB_REQUIRE_DEVICE();
+	CB_ARG(dst_batches != nullptr && src_batches != nullptr && batch_size > 0);
+	if (n_rows <= 0 || row_bytes == 0) return CB200_OK;
+	const int threads = 256;
+	long long blocks = (n_rows * 32 + threads - 1) / threads;
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	// every batch comes from cudaMalloc (256-byte aligned): the row pitch alone decides the widest safe access
+	if (row_bytes % 16 == 0) rows_permute_kernel<uint4><<<(unsigned)blocks, threads, 0, as_stream(s)>>>(dst_batches, src_batches, index, n_rows, batch_size, row_bytes / 16);
+	else if (row_bytes % 4 == 0) rows_permute_kernel<uint32_t><<<(unsigned)blocks, threads, 0, as_stream(s)>>>(dst_batches, src_batches, index, n_rows, batch_size, row_bytes / 4);
+	else if (row_bytes % 2 == 0) rows_permute_kernel<uint16_t><<<(unsigned)blocks, threads, 0, as_stream(s)>>>(dst_batches, src_batches, index, n_rows, batch_size, row_bytes / 2);
+	else rows_permute_kernel<uint8_t><<<(unsigned)blocks, threads, 0, as_stream(s)>>>(dst_batches, src_batches, index, n_rows, batch_size, row_bytes);
+	CB_LAUNCH_CHECK();
+	return CB200_OK;
+}
+
 // round-toward-zero host conversion (the reference converts datasets on the host with
 // __float2half_rz / __float2bfloat16_rz, src/cuda/cuda_main.cu:790,813)
 static inline uint16_t f32_to_bf16_rz(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }
@@ -356,6 +430,24 @@ int cb200_host_cast_from_f32(void* dst, int dtype, const float* src, size_t n) {
 	if (dtype == CB200_FP16) for (size_t i = 0; i < n; i++) o[i] = f32_to_f16_rz(src[i]);
 	else if (dtype == CB200_BF16) for (size_t i = 0; i < n; i++) o[i] = f32_to_bf16_rz(src[i]);
 	else { set_error("cb200_host_cast_from_f32: unknown dtype %d", dtype); return CB200_ERR_ARG; }
+	return CB200_OK;
+}
+
+static inline float f16_to_f32(uint16_t h) {
+	uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu, u;
+	if (exp == 0) {
+		if (man == 0) u = sign;
+		else { int e = -1; do { e++; man <<= 1; } while (!(man & 0x400u)); u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13); }
+	} else if (exp == 31) u = sign | 0x7f800000u | (man << 13);
+	else u = sign | ((exp - 15 + 127) << 23) | (man << 13);
+	float f; memcpy(&f, &u, 4); return f;
+}
+int cb200_host_cast_to_f32(float* dst, const void* src, int dtype, size_t n) {
+	if (dtype == CB200_FP32) { memcpy(dst, src, n * 4); return CB200_OK; }
+	const uint16_t* in = (const uint16_t*)src;
+	if (dtype == CB200_FP16) for (size_t i = 0; i < n; i++) dst[i] = f16_to_f32(in[i]);
+	else if (dtype == CB200_BF16) for (size_t i = 0; i < n; i++) { uint32_t u = (uint32_t)in[i] << 16; memcpy(&dst[i], &u, 4); }
+	else { set_error("cb200_host_cast_to_f32: unknown dtype %d", dtype); return CB200_ERR_ARG; }
 	return CB200_OK;
 }
 

@@ -52,6 +52,8 @@ typedef struct Dataset {
 	void **target;         /* [nb_batch] pinned host batches, compute dtype, [batch_size][output_dim] */
 	void **input_device;   /* device-resident copies when dynamic_load == 0 */
 	void **target_device;
+	void *shuffle_ws;      /* device-side shuffle state of a resident set (duplicate batches, pointer tables, index) */
+	int host_stale;        /* the resident copy was permuted on the device: the host batches follow on demand */
 } Dataset;
 
 struct layer {
@@ -296,6 +298,8 @@ void init_weights(float *tab, int dim_in, int dim_out, const char *init_fct, flo
 void dataset_set_sample(network *net, Dataset *data, int index, const float *input, const float *target);
 void dataset_upload(network *net, Dataset *data);   /* dynamic_load == 0: make device-resident copies */
 void shuffle_dataset(network *net, Dataset *data);  /* what train_network does every shuffle_every epochs */
+void shuffle_dataset_device(network *net, Dataset *data);   /* ... with shuffle_gpu = 1 on a device-resident set */
+void dataset_host_refresh(network *net, Dataset *data);     /* host batches <- resident copy after a device shuffle */
 void cb_dataset_read_row(network *net, Dataset *data, int index, int which, int from_device, void *dst);
 void cb_net_io_dims(network *net, long long *out3);   /* input_dim, output_dim, cb200 dtype */
 /* data-parallel set-up: call on every rank after init_network, before training */

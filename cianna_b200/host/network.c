@@ -126,6 +126,8 @@ Dataset create_dataset(network *net, int nb_elem)
 	return data;
 }
 
+static void shuffle_ws_free(Dataset *data);
+
 void free_dataset(Dataset *data)
 {
 	int i;
@@ -135,6 +137,7 @@ void free_dataset(Dataset *data)
 		cb200_host_free(data->target[i]);
 		if (data->input_device) { cb200_free(data->input_device[i]); cb200_free(data->target_device[i]); }
 	}
+	shuffle_ws_free(data);
 	free(data->input); free(data->target);
 	free(data->input_device); free(data->target_device);
 	memset(data, 0, sizeof(*data));
@@ -184,12 +187,93 @@ static void swap_rows(unsigned char *a, unsigned char *b, unsigned char *tmp, si
 	memcpy(tmp, a, bytes); memcpy(a, b, bytes); memcpy(b, tmp, bytes);
 }
 
+/* ---- the same permutation applied ON THE DEVICE to a resident set (train(shuffle_gpu = 1), dynamic_load == 0):
+ * upstream's cuda_shuffle (src/cuda/cuda_main.cu:642-666, src/auxil.c:1700-1709): a persistent index table takes one
+ * Fisher-Yates pass on the host, goes to the device, the rows are scattered into a duplicate set and copied back.  Here
+ * both moves are cb200_rows_permute launches (one warp per row); the pinned host batches are refreshed only when
+ * something reads them (dataset_host_refresh). */
+typedef struct {
+	int nb_batch, size;
+	void **dup_in, **dup_tg;                   /* host arrays of device batches */
+	void *ptr_in, *ptr_tg, *ptr_dup_in, *ptr_dup_tg;   /* device arrays of nb_batch device pointers */
+	int *index, *index_dev;
+} shuffle_ws;
+
+static void shuffle_ws_free(Dataset *data)
+{
+	shuffle_ws *ws = (shuffle_ws *)data->shuffle_ws;
+	int i;
+	if (ws == NULL) return;
+	for (i = 0; i < ws->nb_batch; i++) { cb200_free(ws->dup_in[i]); cb200_free(ws->dup_tg[i]); }
+	cb200_free(ws->ptr_in); cb200_free(ws->ptr_tg); cb200_free(ws->ptr_dup_in); cb200_free(ws->ptr_dup_tg);
+	cb200_free(ws->index_dev);
+	free(ws->dup_in); free(ws->dup_tg); free(ws->index); free(ws);
+	data->shuffle_ws = NULL;
+}
+
+void dataset_host_refresh(network *net, Dataset *data)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t in_bytes = (size_t)net->batch_size * (net->input_dim + 1) * es, out_bytes = (size_t)net->batch_size * net->output_dim * es;
+	int i;
+	if (!data->host_stale || data->input_device == NULL) return;
+	for (i = 0; i < data->nb_batch; i++) {
+		CB_CHECK(cb200_d2h(data->input[i], data->input_device[i], in_bytes, NULL));
+		if (out_bytes) CB_CHECK(cb200_d2h(data->target[i], data->target_device[i], out_bytes, NULL));
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+	data->host_stale = 0;
+}
+
+void shuffle_dataset_device(network *net, Dataset *data)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t in_row = (net->input_dim + 1) * es, out_row = (size_t)net->output_dim * es;
+	shuffle_ws *ws = (shuffle_ws *)data->shuffle_ws;
+	int i;
+	if (data->input_device == NULL) { printf("\nERROR: shuffle_dataset_device: the data set has no device-resident copy\n"); exit(EXIT_FAILURE); }
+	if (ws == NULL) {
+		size_t pb = (size_t)data->nb_batch * sizeof(void *);
+		ws = (shuffle_ws *)calloc(1, sizeof(shuffle_ws));
+		ws->nb_batch = data->nb_batch; ws->size = data->size;
+		ws->dup_in = (void **)calloc(data->nb_batch, sizeof(void *));
+		ws->dup_tg = (void **)calloc(data->nb_batch, sizeof(void *));
+		for (i = 0; i < data->nb_batch; i++) {
+			CB_CHECK(cb200_malloc(&ws->dup_in[i], (size_t)net->batch_size * in_row));
+			CB_CHECK(cb200_malloc(&ws->dup_tg[i], out_row ? (size_t)net->batch_size * out_row : 16));
+		}
+		CB_CHECK(cb200_malloc(&ws->ptr_in, pb)); CB_CHECK(cb200_malloc(&ws->ptr_tg, pb));
+		CB_CHECK(cb200_malloc(&ws->ptr_dup_in, pb)); CB_CHECK(cb200_malloc(&ws->ptr_dup_tg, pb));
+		CB_CHECK(cb200_h2d(ws->ptr_in, data->input_device, pb, NULL)); CB_CHECK(cb200_h2d(ws->ptr_tg, data->target_device, pb, NULL));
+		CB_CHECK(cb200_h2d(ws->ptr_dup_in, ws->dup_in, pb, NULL)); CB_CHECK(cb200_h2d(ws->ptr_dup_tg, ws->dup_tg, pb, NULL));
+		ws->index = (int *)malloc((size_t)data->size * sizeof(int));
+		for (i = 0; i < data->size; i++) ws->index[i] = i;
+		CB_CHECK(cb200_malloc((void **)&ws->index_dev, (size_t)data->size * sizeof(int)));
+		CB_CHECK(cb200_stream_sync(NULL));
+		data->shuffle_ws = ws;
+	}
+	for (i = 0; i < data->size - 1; i++) {
+		int j = i + (int)((rand() / ((double)RAND_MAX + 1.0)) * (double)(data->size - i));
+		int t = ws->index[i]; ws->index[i] = ws->index[j]; ws->index[j] = t;
+	}
+	CB_CHECK(cb200_h2d(ws->index_dev, ws->index, (size_t)data->size * sizeof(int), NULL));
+	CB_CHECK(cb200_rows_permute((void *const *)ws->ptr_dup_in, (void *const *)ws->ptr_in, ws->index_dev, data->size, net->batch_size, in_row, NULL));
+	CB_CHECK(cb200_rows_permute((void *const *)ws->ptr_in, (void *const *)ws->ptr_dup_in, NULL, data->size, net->batch_size, in_row, NULL));
+	if (out_row) {
+		CB_CHECK(cb200_rows_permute((void *const *)ws->ptr_dup_tg, (void *const *)ws->ptr_tg, ws->index_dev, data->size, net->batch_size, out_row, NULL));
+		CB_CHECK(cb200_rows_permute((void *const *)ws->ptr_tg, (void *const *)ws->ptr_dup_tg, NULL, data->size, net->batch_size, out_row, NULL));
+	}
+	CB_CHECK(cb200_stream_sync(NULL));      /* ws->index is rewritten by the next call */
+	data->host_stale = 1;
+}
+
 void shuffle_dataset(network *net, Dataset *data)
 {
 	size_t es = cb200_dtype_size(net->dtype);
 	size_t in_row = (net->input_dim + 1) * es, out_row = (size_t)net->output_dim * es;
 	unsigned char *tmp = (unsigned char *)malloc(in_row > out_row ? in_row : out_row);
 	int i;
+	dataset_host_refresh(net, data);
 	for (i = 0; i < data->size - 1; i++) {
 		int j = i + (int)((rand() / ((double)RAND_MAX + 1.0)) * (double)(data->size - i));
 		if (j == i) continue;
@@ -221,8 +305,10 @@ void cb_dataset_read_row(network *net, Dataset *data, int index, int which, int 
 		if (data->input_device == NULL) { printf("ERROR: the data set has no device-resident copy\n"); exit(EXIT_FAILURE); }
 		CB_CHECK(cb200_d2h(dst, (char *)(which == 0 ? data->input_device[b] : data->target_device[b]) + (size_t)j * row, row, NULL));
 		CB_CHECK(cb200_stream_sync(NULL));
-	} else
+	} else {
+		dataset_host_refresh(net, data);
 		memcpy(dst, (char *)(which == 0 ? data->input[b] : data->target[b]) + (size_t)j * row, row);
+	}
 }
 
 /* ------------------------------------------------------------------ training preparation */
@@ -501,6 +587,15 @@ static void backward_pass(network *net, const void *target_dev)
 	apply_updates(net);
 }
 
+/* the pieces of one step under their own names, for the upstream-side back-end shim (bridge.c), which is driven layer
+ * by layer from upstream's own loops */
+void cb_use_device_batch(network *net, const void *input_dev) { use_device_batch(net, input_dev); }
+void cb_prepare_training(network *net) { prepare_training(net); }
+void cb_set_hyper(network *net, float lr, float momentum, float weight_decay) { set_hyper(net, lr, momentum, weight_decay); }
+void cb_apply_updates(network *net) { apply_updates(net); }
+void cb_output_deriv_error(network *net, const void *target_dev) { output_deriv_error(net, target_dev); }
+void cb_output_error(network *net, const void *target_dev) { output_error(net, target_dev); }
+
 void cb_backward(network *net, float lr, float momentum, float weight_decay)
 {
 	prepare_training(net);
@@ -720,7 +815,6 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 {
 	int i, j, k;
 	char name[200];
-	(void)shuffle_gpu;
 
 	if (net->inference_only) {
 		printf("\n Network was loaded in inference only mode. \n Re-init network with inference only set to false to re-eanble training capability.\n");
@@ -749,7 +843,10 @@ void train_network(network *net, int nb_iter, int control_interv, float u_begin_
 			/* no copy of the previous epoch may still be reading the host batches */
 			if (net->copy_stream != NULL) CB_CHECK(cb200_stream_sync(net->copy_stream));
 			CB_CHECK(cb200_stream_sync(NULL));
-			shuffle_dataset(net, &net->train);
+			/* as upstream (src/auxil.c:1768-1785): a resident set is permuted on the device when shuffle_gpu is set,
+			 * through the host otherwise; a dynamically loaded set only exists on the host */
+			if (shuffle_gpu && !net->dynamic_load) shuffle_dataset_device(net, &net->train);
+			else shuffle_dataset(net, &net->train);
 			shuffled = 1;
 		}
 		set_hyper(net, lr, net->momentum, net->weight_decay);
@@ -912,7 +1009,8 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		if (saving > 0) {
 			/* one line / record per sample, sample-major like upstream's fwd_res files (src/auxil.c:1346-1400); with
 			 * repeat > 1 the file holds, batch after batch, `repeat` consecutive blocks of the batch's samples */
-			int b, o, per = last->type == DENSE ? c : c * h * w;
+			/* a dense output record is out_size = nb_neurons + 1 values: upstream writes the bias node too (src/auxil.c:1262-1276) */
+			int b, o, per = last->type == DENSE ? c + 1 : c * h * w;
 			for (b = 0; b < net->length; b++) {
 				for (o = 0; o < per; o++) {
 					float v = last->type == DENSE ? out_host[(size_t)b * (c + 1) + o]
@@ -1286,13 +1384,44 @@ Dataset *cb_net_dataset(network *net, const char *name)
 }
 
 /* (re)create the named dataset and fill it from row-major FP32 arrays [size][input_dim] / [size][output_dim] */
+/* FP32 user arrays -> 16-bit dataset batches with the conversion on the device (upstream converts element by element on
+ * the host, src/python_module.c:140-165 + src/cuda/cuda_main.cu:108-113; same round-toward-zero values): one batch of
+ * FP32 rows goes up, is packed (cast + bias slot) by cb200_dataset_pack, and comes back into the pinned host batch */
+static void dataset_fill_on_device(network *net, Dataset *d, const float *input, const float *target)
+{
+	size_t es = cb200_dtype_size(net->dtype);
+	size_t in_row = net->input_dim + 1, out_row = (size_t)net->output_dim;
+	size_t cap = (size_t)net->batch_size * (in_row > out_row ? in_row : out_row);
+	float *stage = NULL;
+	void *typed = NULL;
+	int b;
+	CB_CHECK(cb200_malloc((void **)&stage, cap * sizeof(float)));
+	CB_CHECK(cb200_malloc(&typed, cap * es));
+	for (b = 0; b < d->nb_batch; b++) {
+		size_t first = (size_t)b * net->batch_size;
+		size_t rows = (size_t)d->size - first < (size_t)net->batch_size ? (size_t)d->size - first : (size_t)net->batch_size;
+		CB_CHECK(cb200_h2d(stage, input + first * net->input_dim, rows * net->input_dim * sizeof(float), NULL));
+		CB_CHECK(cb200_dataset_pack(typed, net->dtype, stage, rows, net->input_dim, in_row, net->input_bias, NULL));
+		CB_CHECK(cb200_d2h(d->input[b], typed, rows * in_row * es, NULL));
+		if (target != NULL && out_row > 0) {
+			CB_CHECK(cb200_h2d(stage, target + first * out_row, rows * out_row * sizeof(float), NULL));
+			CB_CHECK(cb200_dataset_pack(typed, net->dtype, stage, rows, out_row, out_row, 0.0f, NULL));
+			CB_CHECK(cb200_d2h(d->target[b], typed, rows * out_row * es, NULL));
+		}
+	}
+	CB_CHECK(cb200_stream_sync(NULL));
+	cb200_free(stage); cb200_free(typed);
+}
+
 void cb_set_dataset(network *net, const char *name, int size, const float *input, const float *target)
 {
 	Dataset *d = cb_net_dataset(net, name);
 	int i;
 	if (d->input != NULL) free_dataset(d);
 	*d = create_dataset(net, size);
-	if (input != NULL || target != NULL)
+	if (net->dtype != CB200_FP32 && input != NULL && (size_t)size * net->input_dim >= ((size_t)1 << 18))
+		dataset_fill_on_device(net, d, input, target);
+	else if (input != NULL || target != NULL)
 		for (i = 0; i < size; i++)
 			dataset_set_sample(net, d, i, input ? input + (size_t)i * net->input_dim : NULL, target ? target + (size_t)i * net->output_dim : NULL);
 	if (!net->dynamic_load) dataset_upload(net, d);

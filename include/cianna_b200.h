@@ -126,6 +126,21 @@ int  cb200_cast_to_f32(float* dev_dst, const void* dev_src, int dtype, size_t n,
 /* host-side conversion with round-toward-zero, as the reference's dataset conversion does
  * (src/cuda/cuda_main.cu:790,813) */
 int  cb200_host_cast_from_f32(void* host_dst, int dtype, const float* host_src, size_t n);
+/* the way back on the host (exact), as cuda_get_typed_host_table does (src/cuda/cuda_main.cu:245-256) */
+int  cb200_host_cast_to_f32(float* host_dst, const void* host_src, int dtype, size_t n);
+/* the same round-toward-zero conversion on the device: an FP32 batch staged in device memory -> `dtype`
+ * (moves the dataset conversion loop of cuda_convert_batched_table, src/cuda/cuda_main.cu:355-371, off the host) */
+int  cb200_cast_from_f32_rz(void* dev_dst, int dtype, const float* dev_src, size_t n, void* stream);
+/* FP32 sample rows [rows][src_row] (device) -> dataset rows [rows][dst_row] in `dtype` (device), dst_row >= src_row, the
+ * extra slots (the bias slot of an input row, src/auxil.c:320-329) set to tail_value; round toward zero.
+ * The per-element host loop of python_module.c:140-165 + copy_to_FP16 (cuda_main.cu:108-113) as one kernel. */
+int  cb200_dataset_pack(void* dev_dst, int dtype, const float* dev_src, size_t rows, size_t src_row, size_t dst_row,
+                        float tail_value, void* stream);
+/* dataset shuffle on the device: row i of the source batches -> row index[i] of the destination batches; both are
+ * device arrays of nb_batch device pointers, each batch [batch_size][row_bytes]; index (device int32 [n_rows]) may be
+ * NULL for a plain copy (the way back).  Replaces shfl_kern_* + get_back_shuffle_* (src/cuda/cuda_main.cu:590-666). */
+int  cb200_rows_permute(void* const* dst_batches_dev, void* const* src_batches_dev, const int* index_dev, long long n_rows,
+                        int batch_size, size_t row_bytes, void* stream);
 
 /* ------------------------------------------------------------------ layout import / export */
 /* Dataset rows -> internal.  src: device array [batch][C*H*W + 1] in `dtype` (reference dataset
@@ -387,6 +402,16 @@ int cb200_output_delta_activ(void* delta, const void* y, const void* target, int
  * whole per-element tensor (cuda_activ_functions.cu:157-194,427-470; src/auxil.c:1851-1917). */
 int cb200_output_loss(float* loss, const void* y, const void* target, int dtype,
                       int batch, int length, int c, int h, int w, int kind, void* stream);
+
+/* per-ELEMENT loss in upstream's table layout (conv / pool outputs err[c][batch][h*w], dense_layout: err[batch][c + 1]
+ * with the bias node untouched), FP32, rows b >= length untouched (the caller zeroes the table as upstream does,
+ * src/auxil.c:1853-1856).  For the upstream-side back-end shim: upstream's host code sums this table itself
+ * (cuda_output_error_fct, src/cuda/cuda_activ_functions.cu:2585-2602 + src/auxil.c:1871-1913). */
+int cb200_output_error_elems(float* err, const void* y, const void* target, int dtype, int batch, int length,
+                             int c, int h, int w, int kind, int dense_layout, void* stream);
+/* YOLO twin: writes the six loss parts of cb200_yolo_loss ([batch][6]) into upstream's table err[ch][batch][cells], each
+ * on the first element of its channel class, so that the per-class sums of src/auxil.c:1429-1455 come out the same. */
+int cb200_yolo_scatter_parts(float* err, const float* parts, int batch, int length, int cells, int nb_class, int nb_param, void* stream);
 
 /* per-sample argmax (class-major index over the c*h*w outputs, first maximum wins) of the output and of the target
  * row into two device int32 [batch] arrays (-1 for b >= length): the inputs of the confusion matrix of

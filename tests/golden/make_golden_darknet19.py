@@ -59,6 +59,81 @@ def summarize(out, key, arr, layer_index, what):
     out[key + "_absmax"] = np.array([np.abs(a).max()])
 
 
+def compare(g, key, arr, layer_index, what):
+    """deviation of a full tensor from the fixture's summary of it: `sample` max |a - ref| over the sampled positions /
+    max |ref tensor|, `q98` the same at the 98 % quantile, `l2` relative difference of the whole-tensor L2 norms"""
+    a = np.asarray(arr, dtype=np.float32).ravel()
+    pos = sample_positions(layer_index, what, a.size)
+    ref = g[key + "_sample"].astype(np.float64)
+    scale = max(float(g[key + "_absmax"][0]), 1e-30)
+    d = np.abs(a[pos].astype(np.float64) - ref) / scale
+    l2 = float(np.sqrt(np.sum(a.astype(np.float64) ** 2)))
+    ref_l2 = max(float(g[key + "_l2"][0]), 1e-30)
+    return {"sample": float(d.max()), "q98": float(np.quantile(d, 0.98)), "l2": abs(l2 - ref_l2) / ref_l2}
+
+
+def full_dev(a, ref):
+    return float(np.abs(np.asarray(a, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def selfdev():
+    """The reference against ITSELF: the same step on its C_NAIV back-end (plain loops, another summation order than
+    OpenBLAS) compared with the C_BLAS fixture, quantity by quantity, with the comparison the GPU test applies to the
+    product -> tests/golden/darknet19_448_b16_selfdev.npz.  This is the floor any second implementation of the same
+    arithmetic sits on: the FP32 forward pass of this 43-layer network reproduces to ~1e-6..1e-5 only, and every
+    leaky-ReLU / max-pool decision taken on a value within that distance of its threshold flips - a full-size error on
+    one delta element, spread by the layers below it."""
+    from cianna_b200 import configs
+    from oracle import ref_driver as rd
+    g = dict(np.load(os.path.join(HERE, "darknet19_448_b16.npz")))
+    spec = configs.darknet19(BATCH, SIZE, CLASSES)
+    t0 = time.time()
+    ref = rd.RefNet(spec, "C_NAIV", variant="omp")
+    for l in range(ref.n_layers):
+        t = ref.layer_type(l)
+        if t == rd.CONV:
+            w = ref.weights_view(l)
+            w[...] = seeded_weights("conv", l, w.shape)
+        elif t == rd.NORM:
+            ga, be = ref.norm_view(l, "gamma"), ref.norm_view(l, "beta")
+            gb = seeded_weights("norm", l, ga.shape)
+            ga[...], be[...] = gb[:ga.size], gb[ga.size:]
+    x, tgt = seeded_batch()
+    ref.forward(x)
+    print("reference (C_NAIV) forward: %.1f s" % (time.time() - t0)); t0 = time.time()
+    out = {}
+
+    def put(name, e):
+        for k, v in e.items():
+            out["%s_%s" % (name, k)] = np.array([v])
+    kinds = [k for k, _ in spec["layers"]]
+    for l, k in enumerate(kinds):
+        put("out_%d_%s" % (l, k), compare(g, "out_%d" % l, ref.output(l), l, 0))
+        if ref.layer_type(l) == rd.NORM:
+            out["mean_%d" % l] = np.array([full_dev(ref.norm_view(l, "mean"), g["mean_%d" % l])])
+            out["var_%d" % l] = np.array([full_dev(ref.norm_view(l, "var"), g["var_%d" % l])])
+    out["probs"] = np.array([full_dev(ref.output(ref.n_layers - 1), g["probs"])])
+    loss = float(ref.loss(tgt).sum(axis=(0, 2)).mean())
+    out["loss"] = np.array([abs(loss - float(g["loss"].mean())) / float(g["loss"].mean())])
+    ref.backward(tgt, HYPER["lr"], HYPER["momentum"], HYPER["weight_decay"])
+    print("reference (C_NAIV) backward: %.1f s" % (time.time() - t0))
+    for l, k in enumerate(kinds):
+        put("delta_%d_%s" % (l, k), compare(g, "delta_%d" % l, ref.delta(l), l, 1))
+        if k == "conv":
+            put("m1_%d" % l, compare(g, "m1_%d" % l, ref.moment_view(l), l, 2))
+            w1 = ref.weights_view(l)
+            put("dw_%d" % l, compare(g, "dw_%d" % l, w1 - seeded_weights("conv", l, w1.shape), l, 3))
+        elif k == "norm":
+            out["dgamma_%d" % l] = np.array([full_dev(ref.norm_view(l, "d_gamma"), g["dgamma_%d" % l])])
+            out["dbeta_%d" % l] = np.array([full_dev(ref.norm_view(l, "d_beta"), g["dbeta_%d" % l])])
+            w1 = np.concatenate([ref.norm_view(l, "gamma"), ref.norm_view(l, "beta")])
+            out["gn_w1_%d" % l] = np.array([full_dev(w1, g["w1_%d" % l])])
+    path = os.path.join(HERE, "darknet19_448_b16_selfdev.npz")
+    np.savez_compressed(path, **out)
+    worst = sorted(((float(v[0]), k) for k, v in out.items()), reverse=True)[:12]
+    print("wrote", path, "largest self-deviations:", worst)
+
+
 def main():
     from cianna_b200 import configs
     from oracle import ref_driver as rd
@@ -112,4 +187,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--selfdev" in sys.argv:
+        selfdev()
+    else:
+        main()

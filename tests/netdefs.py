@@ -130,3 +130,15 @@ def yolo_net(batch=4, size=32):
 
 
 from cianna_b200.configs import darknet19, lenet  # noqa: E402,F401  (shared with bench.py)
+
+
+def lrn_net(batch=4):
+    """two LRN layers (one with explicit parameters, one with upstream's defaults) between conv / pool / dense layers"""
+    return dict(in_dim=(12, 12), in_ch=3, out_dim=5, bias=0.1, batch=batch, layers=[
+        ("conv", dict(f_size=(3, 3), nb_filters=12, padding=(1, 1), activation="RELU")),
+        ("lrn", dict(range=5, k=2.0, alpha=0.3, beta=0.75)),
+        ("pool", dict(p_size=(2, 2), p_type="MAX")),
+        ("conv", dict(f_size=(3, 3), nb_filters=16, padding=(1, 1), activation="RELU")),
+        ("lrn", dict()),
+        ("dense", dict(nb_neurons=5, strict_size=1, activation="SMAX")),
+    ])

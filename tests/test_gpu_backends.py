@@ -1,0 +1,272 @@
+"""Two CIANNA.so builds of UPSTREAM's own host code (compute method C_CUDA) driven through upstream's own back-end
+boundary (src/prototypes.h:217-295) by oracle/ref_probe_cuda.c:
+
+  dropin   upstream host sources + cianna_b200/shim/cuda_b200_shim.c  -> the product as upstream's back-end.  The proof
+           of "drop-in": not one line of upstream's C / Python changes, `comp_meth="C_CUDA"` runs the sm_100a kernels.
+  cuda     upstream host sources + upstream's OWN src/cuda/*.cu + cuBLAS, compiled for sm_100 -> second oracle: what
+           upstream's GPU path itself computes in FP32 / FP16C_FP32A / BF16C_FP32A (an FP16 result the product had no
+           influence on), and the only upstream implementation of LRN.
+
+Both are compared with the CPU reference (C_BLAS) on identical weights and inputs, and the product with the second
+oracle.  Tolerances (north_star): 1e-5 FP32 (1e-4 on quantities summed over the batch), 2e-2 mixed.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_cuda_driver as rc
+from oracle import ref_driver as rd
+from tests import netdefs
+from tests.common import ref_available, rel_err, rel_l2, rel_q
+
+pytestmark = pytest.mark.gpu
+
+HYPER = dict(lr=0.02, momentum=0.9, weight_decay=0.0005)
+TOL = {"off": 1e-5, "FP16C_FP32A": 2e-2, "BF16C_FP32A": 2e-2}
+SPECS = {
+    "mini_darknet": lambda: netdefs.mini_darknet(batch=4, size=16, classes=6),
+    "tc_darknet": lambda: netdefs.tc_darknet(batch=4, size=16),
+    "lenet": lambda: netdefs.lenet(batch=4, size=16, d1=24, d2=12),
+}
+
+
+def _need(which):
+    if not ref_available():
+        pytest.skip("oracle/_ref not present on this box")
+    if not rc.available(which):
+        pytest.skip("oracle/_ref/%s/CIANNA.so not present (or no libcublas)" % which)
+
+
+def _kinds(spec):
+    return [k for k, _ in spec["layers"]]
+
+
+def _seed_from_cpu(ref, gpu, kinds):
+    """the CPU reference's random draw becomes the GPU back-end's weights (through cuda_put_table_FP32 / the host arrays)"""
+    for l, k in enumerate(kinds):
+        if k in ("conv", "dense"):
+            gpu.set_weights(l, ref.weights_view(l))
+        elif k == "norm":
+            g = ref.norm_view(l, "gamma")
+            g[...] = 1.0 + 0.1 * np.cos(np.arange(g.size, dtype=np.float32))
+            b = ref.norm_view(l, "beta")
+            b[...] = 0.05 * np.sin(np.arange(b.size, dtype=np.float32))
+            gpu.set_norm(l, g, b)
+
+
+def _step_both(which, spec, mode, TC_scale=1.0, weights=None):
+    kinds = _kinds(spec)
+    ref = rd.RefNet(spec, "C_BLAS")
+    if weights is not None:                 # repeat an earlier draw instead of the reference's new random one
+        for l, w in weights.items():
+            ref.weights_view(l)[...] = w
+    gpu = rc.CudaBackendNet(spec, mode, which=which)
+    _seed_from_cpu(ref, gpu, kinds)
+    x, t = rd.make_inputs(spec, seed=11)
+    ref.forward(x)
+    gpu.forward(x)
+    out = {"ref": ref, "gpu": gpu, "kinds": kinds, "t": t}
+    out["fwd"] = [(rel_err(gpu.output(l), ref.output(l))) for l in range(len(kinds))]
+    out["loss"] = (float(gpu.loss(t).sum()), float(ref.loss(t).sum()))
+    w0 = {l: ref.weights_view(l).copy() for l, k in enumerate(kinds) if k in ("conv", "dense")}
+    ref.backward(t, **HYPER)
+    gpu.backward(t, HYPER["lr"], HYPER["momentum"], HYPER["weight_decay"], TC_scale=TC_scale)
+    out["w0"] = w0
+    return out
+
+
+@pytest.mark.parametrize("spec_name", sorted(SPECS))
+@pytest.mark.parametrize("which", ["dropin", "cuda"])
+def test_fp32_training_step_matches_cpu_reference(which, spec_name):
+    """FP32: every layer's output, the loss, every delta and the updated weights of one training step"""
+    _need(which)
+    r = _step_both(which, SPECS[spec_name](), "off")
+    ref, gpu, kinds = r["ref"], r["gpu"], r["kinds"]
+    assert max(r["fwd"]) < 1e-5, r["fwd"]
+    assert abs(r["loss"][0] - r["loss"][1]) < 1e-5 * abs(r["loss"][1])
+    for l, k in enumerate(kinds):
+        assert rel_err(gpu.delta(l), ref.delta(l)) < 1e-4, (l, k)
+        if k in ("conv", "dense"):
+            dw_ref = ref.weights_view(l) - r["w0"][l]
+            assert rel_err(gpu.weights(l) - r["w0"][l], dw_ref) < 1e-4, (l, k)
+        elif k == "norm":
+            assert rel_err(gpu.norm(l, "gamma"), ref.norm_view(l, "gamma")) < 1e-5
+            assert rel_err(gpu.norm(l, "beta"), ref.norm_view(l, "beta")) < 1e-5
+            assert rel_err(gpu.norm(l, "mean"), ref.norm_view(l, "mean")) < 1e-5
+            assert rel_err(gpu.norm(l, "var"), ref.norm_view(l, "var")) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["FP16C_FP32A", "BF16C_FP32A"])
+@pytest.mark.parametrize("spec_name", ["tc_darknet", "lenet"])
+@pytest.mark.parametrize("which", ["dropin", "cuda"])
+def test_mixed_training_step_within_tolerance_of_cpu_reference(which, spec_name, mode):
+    """mixed precision: forward tensors point-wise at 2e-2; backward tensors at the 98 % quantile and in L2 of the
+    weight change (isolated leaky-ReLU / max-pool decision flips are full-size errors on single elements on ANY 16-bit
+    implementation - the `cuda` rows of this test show upstream's own path has them too)"""
+    _need(which)
+    S = 64.0 if mode == "FP16C_FP32A" else 1.0
+    r = _step_both(which, SPECS[spec_name](), mode, TC_scale=S)
+    ref, gpu, kinds = r["ref"], r["gpu"], r["kinds"]
+    tol = TOL[mode]
+    assert max(r["fwd"]) < tol, r["fwd"]
+    assert abs(r["loss"][0] - r["loss"][1]) < tol * abs(r["loss"][1])
+    for l, k in enumerate(kinds):
+        assert rel_q(gpu.delta(l) / S, ref.delta(l)) < tol, (l, k)
+        if k in ("conv", "dense"):
+            dw_ref = ref.weights_view(l) - r["w0"][l]
+            assert rel_l2(gpu.weights(l) - r["w0"][l], dw_ref) < 5 * tol, (l, k)
+
+
+@pytest.mark.parametrize("mode", ["FP16C_FP32A", "BF16C_FP32A"])
+def test_product_agrees_with_upstream_cuda_path_as_well_as_upstream_does_with_itself(mode):
+    """The unconditioned mixed-precision comparison: the product (through the drop-in library) and upstream's own CUDA
+    path, same weights / inputs / mode, each against the FP32 CPU reference AND against each other.  The product must
+    be at least as close to the FP32 truth as upstream's 16-bit path is (factor 1.5 + an absolute floor), and the two
+    16-bit results must agree with each other within the tolerance on every forward tensor."""
+    _need("cuda")
+    _need("dropin")
+    spec = SPECS["tc_darknet"]()
+    S = 64.0 if mode == "FP16C_FP32A" else 1.0
+    a = _step_both("dropin", spec, mode, TC_scale=S)
+    out_a = [a["gpu"].output(l) for l in range(len(a["kinds"]))]
+    del_a = [a["gpu"].delta(l) / S for l in range(len(a["kinds"]))]
+    w_a = {l: a["gpu"].weights(l) for l in a["w0"]}
+    b = _step_both("cuda", spec, mode, TC_scale=S, weights=a["w0"])
+    tol = TOL[mode]
+    for l, k in enumerate(a["kinds"]):
+        ref_out = b["ref"].output(l)
+        assert rel_err(out_a[l], b["gpu"].output(l)) < tol, (l, k)
+        e_mine, e_theirs = rel_err(out_a[l], ref_out), rel_err(b["gpu"].output(l), ref_out)
+        assert e_mine < 1.5 * e_theirs + 0.1 * tol, (l, k, e_mine, e_theirs)
+        q_mine, q_theirs = rel_q(del_a[l], b["ref"].delta(l)), rel_q(b["gpu"].delta(l) / S, b["ref"].delta(l))
+        assert q_mine < 1.5 * q_theirs + 0.1 * tol, (l, k, q_mine, q_theirs)
+    for l in a["w0"]:
+        dw_ref = b["ref"].weights_view(l) - b["w0"][l]
+        e_mine, e_theirs = rel_l2(w_a[l] - a["w0"][l], dw_ref), rel_l2(b["gpu"].weights(l) - b["w0"][l], dw_ref)
+        assert e_mine < 1.5 * e_theirs + 0.5 * tol, (l, e_mine, e_theirs)
+
+
+def _dataset(spec, n, seed=42):
+    rng = np.random.default_rng(seed)
+    dim = spec["in_dim"][0] * spec["in_dim"][1] * spec["in_ch"]
+    data = (rng.random((n, dim), dtype=np.float32) - 0.4).astype(np.float32)
+    targ = np.zeros((n, spec["out_dim"]), np.float32)
+    targ[np.arange(n), rng.integers(0, spec["out_dim"], n)] = 1
+    return data, targ
+
+
+@pytest.mark.parametrize("dynamic_load", [1, 0])
+def test_dropin_python_api_train_and_forward_match_cpu_reference(dynamic_load, tmp_path, monkeypatch):
+    """upstream's PYTHON interface (src/python_module.c, unmodified) on the drop-in library: init / conv / norm / pool /
+    create_dataset / train / forward(saving=2) / save, against the same calls on upstream's CPU back-end."""
+    _need("dropin")
+    monkeypatch.chdir(tmp_path)
+    spec = netdefs.mini_darknet(batch=4, size=16, classes=6)
+    kinds = _kinds(spec)
+    n = 10                                                  # last batch partial
+    data, targ = _dataset(spec, n)
+    kw = dict(nb_iter=2, learning_rate=0.02, end_learning_rate=0.01, control_interv=10, momentum=0.8, lr_decay=0.1,
+              weight_decay=0.001, confmat=0, save_every=0, shuffle_every=0, silent=1)
+    ref = rd.RefNet(spec, "C_BLAS")
+    w0 = {l: ref.weights_view(l).copy() for l, k in enumerate(kinds) if k == "conv"}
+    os.makedirs("ref", exist_ok=True)
+    os.makedirs("mine", exist_ok=True)
+    monkeypatch.chdir(tmp_path / "ref")
+    with rd._Quiet():
+        ref.cnn.create_dataset("TRAIN", n, data, targ, network=0, silent=1)
+        ref.cnn.create_dataset("TEST", n, data, targ, network=0, silent=1)
+        ref.cnn.train(network=0, **kw)
+        ref.cnn.forward(saving=2, network=0, silent=1)
+    monkeypatch.chdir(tmp_path / "mine")
+    gpu = rc.CudaBackendNet(spec, "off", which="dropin", dynamic_load=dynamic_load)
+    for l, w in w0.items():
+        gpu.set_weights(l, w)
+    with rd._Quiet():
+        gpu.cnn.create_dataset("TRAIN", n, data, targ, network=0, silent=1)
+        gpu.cnn.create_dataset("TEST", n, data, targ, network=0, silent=1)
+        gpu.cnn.train(network=0, **kw)
+        gpu.cnn.forward(saving=2, network=0, silent=1)
+        gpu.cnn.save("net_mine.dat", network=0, bin=1)
+    for l in w0:
+        assert rel_err(gpu.weights(l), ref.weights_view(l)) < 1e-4, l
+    for l, k in enumerate(kinds):
+        if k == "norm":
+            assert rel_err(gpu.norm(l, "gamma"), ref.norm_view(l, "gamma")) < 1e-4
+    f_ref = np.fromfile(tmp_path / "ref" / "fwd_res" / "net0_0002.dat", dtype=np.float32)
+    f_mine = np.fromfile(tmp_path / "mine" / "fwd_res" / "net0_0002.dat", dtype=np.float32)
+    assert f_ref.size == f_mine.size == n * spec["out_dim"]
+    assert rel_err(f_mine, f_ref) < 1e-4
+    # the file upstream's save wrote from the drop-in's tables loads in the CPU reference with the trained weights
+    ref_cnn, lib = rd.ref_loader.load("serial")
+    lib.probe_reset()
+    with rd._Quiet():
+        ref_cnn.init(in_dim=rd.i_ar(spec["in_dim"]), in_nb_ch=spec["in_ch"], out_dim=spec["out_dim"], bias=0.1, b_size=4,
+                     comp_meth="C_BLAS", no_logo=1, network=0)
+        ref_cnn.load("net_mine.dat", 0, network=0, bin=1)
+    back = rd.RefNet.__new__(rd.RefNet)
+    back.cnn, back.lib, back.spec, back.B = ref_cnn, lib, spec, spec["batch"]
+    for l in w0:
+        assert np.array_equal(back.weights_view(l), gpu.weights(l)), l
+
+
+def test_dropin_python_api_device_shuffle_runs(tmp_path, monkeypatch):
+    """train(shuffle_gpu=1, shuffle_every=1) on a device-resident set goes through cuda_shuffle -> cb200_rows_permute"""
+    _need("dropin")
+    monkeypatch.chdir(tmp_path)
+    spec = netdefs.mini_darknet(batch=4, size=16, classes=6)
+    n = 14
+    data, targ = _dataset(spec, n, seed=5)
+    gpu = rc.CudaBackendNet(spec, "FP16C_FP32A", which="dropin", dynamic_load=0)
+    with rd._Quiet():
+        gpu.cnn.create_dataset("TRAIN", n, data, targ, network=0, silent=1)
+        gpu.cnn.create_dataset("VALID", n, data, targ, network=0, silent=1)
+        gpu.cnn.train(network=0, nb_iter=3, learning_rate=0.01, control_interv=1, momentum=0.5, confmat=0, save_every=0,
+                      shuffle_gpu=1, shuffle_every=1, TC_scale_factor=16.0, silent=1)
+    for l, k in enumerate(_kinds(spec)):
+        if k == "conv":
+            assert np.isfinite(gpu.weights(l)).all()
+
+
+def test_lrn_of_upstream_cuda_path_pins_the_lrn_oracle():
+    """LRN exists upstream only as CUDA kernels (src/cuda/cuda_lrn_layer.cu:35-101): the second oracle is the one
+    implementation the NumPy restatement (oracle/lrn_oracle.py) and the product can be pinned to.  Writes the tensors
+    around both LRN layers to gpurun_out/lrn_refcuda.npz (committed as tests/golden/lrn_refcuda.npz, the fixture of
+    tests/test_oracle_lrn.py)."""
+    _need("cuda")
+    _need("dropin")
+    from oracle import cianna_oracle as co
+    from oracle import lrn_oracle as lo
+    spec = netdefs.lrn_net()
+    kinds = _kinds(spec)
+    B = spec["batch"]
+    up = rc.CudaBackendNet(spec, "off", which="cuda")
+    w = {l: up.weights(l) for l, k in enumerate(kinds) if k in ("conv", "dense")}
+    x, t = rd.make_inputs(spec, seed=3)
+    up.forward(x)
+    up.backward(t, 0.0)                       # lr 0: deltas only
+    up_out = [up.output(l) for l in range(len(kinds))]
+    up_del = [up.delta(l) for l in range(len(kinds))]
+    mine = rc.CudaBackendNet(spec, "off", which="dropin")
+    for l, wl in w.items():
+        mine.set_weights(l, wl)
+    mine.forward(x)
+    mine.backward(t, 0.0)
+    fixture = {}
+    for l, k in enumerate(kinds):
+        assert rel_err(mine.output(l), up_out[l]) < 1e-5, (l, k)
+        assert rel_err(mine.delta(l), up_del[l]) < 1e-4, (l, k)
+        if k == "lrn":
+            a = dict(spec["layers"][l][1])
+            r, kk, al, be = a.get("range", 5), a.get("k", 1.0), a.get("alpha", 1.0), a.get("beta", 0.5)
+            xin = up_out[l - 1]
+            y, scale = lo.lrn_forward(xin, r, kk, al, be)
+            assert rel_err(y, up_out[l]) < 1e-5, l
+            # upstream's LRN backward ends with the derivative of the activation of the layer below (leaky ReLU here)
+            dx = co.relu_deriv(lo.lrn_backward(xin, up_out[l], up_del[l], scale, r, al, be), xin, B)
+            assert rel_err(dx, up_del[l - 1]) < 1e-4, l
+            fixture.update({"x_%d" % l: xin, "y_%d" % l: up_out[l], "dy_%d" % l: up_del[l], "dx_%d" % l: up_del[l - 1],
+                            "param_%d" % l: np.array([r, kk, al, be], dtype=np.float64)})
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    np.savez_compressed(os.path.join(out, "lrn_refcuda.npz"), **fixture)

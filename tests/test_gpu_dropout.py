@@ -260,10 +260,11 @@ def test_forward_repeat_mc_dropout_file_matches_reference_layout(cnn, tmp_path, 
         cnn.create_dataset("TEST", n, data, targ, network=0, silent=1)
         cnn.forward(saving=2, drop_mode="AVG_MODEL", repeat=rep, network=0, silent=1)
     mine = np.fromfile(tmp_path / "mine" / "fwd_res" / "net0_0000.dat", dtype=np.float32)
-    assert mine.size == theirs.size == n * rep * 5
+    assert mine.size == theirs.size == n * rep * 6     # nb_neurons + the bias node, as upstream writes dense outputs
     assert rel_err(mine, theirs) < 1e-5
     # record layout: batch after batch, `rep` consecutive blocks of the batch's samples
-    blocks = [mine[:6 * rep * 5].reshape(rep, 6, 5), mine[6 * rep * 5:].reshape(rep, 4, 5)]
+    assert np.all(mine.reshape(-1, 6)[:, 5] == 0.0)
+    blocks = [mine[:6 * rep * 6].reshape(rep, 6, 6)[:, :, :5], mine[6 * rep * 6:].reshape(rep, 4, 6)[:, :, :5]]
     for blk in blocks:
         for r in range(1, rep):
             assert np.array_equal(blk[r], blk[0])
@@ -276,8 +277,8 @@ def test_forward_repeat_mc_dropout_file_matches_reference_layout(cnn, tmp_path, 
     with rd._Quiet():
         cnn.forward(saving=2, drop_mode="MC_MODEL", repeat=rep_mc, network=0, silent=1)
     mc = np.fromfile(tmp_path / "mine" / "fwd_res" / "net0_0000.dat", dtype=np.float32)
-    assert mc.size == n * rep_mc * 5
-    b0 = mc[:6 * rep_mc * 5].reshape(rep_mc, 6, 5)
+    assert mc.size == n * rep_mc * 6
+    b0 = mc[:6 * rep_mc * 6].reshape(rep_mc, 6, 6)[:, :, :5]
     assert not np.array_equal(b0[0], b0[1])
     assert np.allclose(b0.sum(axis=2), 1.0, atol=1e-4)
     assert np.abs(b0.mean(axis=0) - blocks[0][0]).max() < 0.15

@@ -74,15 +74,7 @@ def test_lrn_vs_oracle(cabi, cfg, dtype_name):
     assert np.array_equal(y, y2)
 
 
-def _lrn_net(batch=4):
-    return dict(in_dim=(12, 12), in_ch=3, out_dim=5, bias=0.1, batch=batch, layers=[
-        ("conv", dict(f_size=(3, 3), nb_filters=12, padding=(1, 1), activation="RELU")),
-        ("lrn", dict(range=5, k=2.0, alpha=0.3, beta=0.75)),
-        ("pool", dict(p_size=(2, 2), p_type="MAX")),
-        ("conv", dict(f_size=(3, 3), nb_filters=16, padding=(1, 1), activation="RELU")),
-        ("lrn", dict()),
-        ("dense", dict(nb_neurons=5, strict_size=1, activation="SMAX")),
-    ])
+_lrn_net = netdefs.lrn_net
 
 
 def _batch(spec, seed):
