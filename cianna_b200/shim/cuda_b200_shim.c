@@ -102,16 +102,19 @@ static int ensure_mirror(network *net)
 	return net->id;
 }
 
-/* upstream's pointer for a mirrored activation tensor: the mirror's own buffer, or (a group-norm layer evaluated inside
- * the following pooling kernel has none) a 256-byte token allocation that only serves as a key of the region table */
+/* upstream's pointer for a mirrored activation tensor: the mirror's own buffer, or (a group-norm layer, which may be
+ * evaluated inside the following pooling kernel and then has none) a 256-byte token allocation that only serves as a key
+ * of the region table */
 static void *act_handle(network *net, int l, int want_delta)
 {
-	void *p = cbb_act_ptr(net->id, l, want_delta);
+	void *p = net->net_layers[l]->type == NORM ? NULL : cbb_act_ptr(net->id, l, want_delta);
 	int chw[3];
 	size_t bytes;
 	if (want_delta && net->inference_only) return NULL;
 	cbb_layer_shape(net->id, l, chw);
 	bytes = (size_t)net->batch_size * chw[1] * chw[2] * cb200_round_channels(chw[0]) * esize(net);
+	/* (a norm layer's own buffers are released when the NEXT layer turns out to be a pooling layer that absorbs it:
+	 * never hand them out) */
 	if (p == NULL) { SHIM_CHECK(cb200_malloc(&p, 256)); bytes = 256; }
 	region_add(p, bytes, R_ACT, net->id, l, want_delta);
 	return p;

@@ -2,10 +2,12 @@
 
 TEST INFRASTRUCTURE ONLY (same rule as oracle/cianna_oracle.py): used by tests/ as the checker of cb200_lrn_*.
 
-Parity status: UNPINNED.  Upstream has this layer in its CUDA back-end only (lrn_create exits for C_NAIV / C_BLAS,
-src/lrn_layer.c:192-197), so the CPU reference build under oracle/_ref cannot produce outputs for it and the repository
-holds no golden vectors; this file restates the two CUDA kernels (src/cuda/cuda_lrn_layer.cu:35-101) line by line in
-the reference layout [C][B][H*W] and is cross-checked only by finite differences (tests/test_oracle.py).
+Parity status: PINNED to upstream's own CUDA kernels.  Upstream has this layer in its CUDA back-end only (lrn_create
+exits for C_NAIV / C_BLAS, src/lrn_layer.c:192-197), so the CPU reference builds cannot produce outputs for it; this
+file restates the two CUDA kernels (src/cuda/cuda_lrn_layer.cu:35-101) line by line in the reference layout
+[C][B][H*W].  It is checked against tests/golden/lrn_refcuda.npz - tensors around two LRN layers produced on a B200 by
+the UNMODIFIED src/cuda/*.cu compiled for sm_100 (oracle/_ref/cuda, oracle/build_ref.sh) - in tests/test_oracle_lrn.py
+(CPU), live against that build in tests/test_gpu_backends.py (GPU), and by finite differences.
 """
 import numpy as np
 

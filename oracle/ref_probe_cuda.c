@@ -204,4 +204,7 @@ void probe_cuda_reset(void)
 	int i;
 	for(i = 0; i < MAX_NETWORKS_NB; i++) { probe_input_dev[i] = NULL; probe_target_dev[i] = NULL; probe_err_dev[i] = NULL; }
 	nb_networks = 0;
+	/* upstream selects the cuBLAS data / compute types once per process (init_cuda, src/cuda/cuda_main.cu:925-1052): a test
+	 * process that changes the precision mode between networks has to make it select again */
+	is_cuda_init = 0;
 }

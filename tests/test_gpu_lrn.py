@@ -1,7 +1,7 @@
 """GPU parity of the local response normalisation layer and of the architecture table export.
 
-LRN: cb200_lrn_forward / _backward through the C-ABI against oracle/lrn_oracle.py (parity UNPINNED: upstream has the
-layer on CUDA only, see that file), then the host layer (lrn_create / save / load, python lrn()) inside a network.
+LRN: cb200_lrn_forward / _backward through the C-ABI against oracle/lrn_oracle.py (pinned to upstream's own CUDA
+kernels by tests/golden/lrn_refcuda.npz, see that file), then the host layer (lrn_create / save / load, python lrn()) inside a network.
 Architecture table: the .tex written by print_arch_tex must equal, byte for byte, the files the unmodified reference
 wrote for the same networks (tests/golden/arch_tex/, tests/golden/make_golden_arch_tex.py).
 """

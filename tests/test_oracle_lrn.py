@@ -1,8 +1,30 @@
-"""CPU checks of oracle/lrn_oracle.py (parity UNPINNED, see its header): closed-form values on a tiny case and the
-backward formula against central finite differences of the forward one."""
+"""CPU checks of oracle/lrn_oracle.py: the fixture upstream's OWN CUDA kernels produced on a B200
+(tests/golden/lrn_refcuda.npz, written by tests/test_gpu_backends.py::test_lrn_of_upstream_cuda_path_pins_the_lrn_oracle
+from oracle/_ref/cuda, the unmodified src/cuda/cuda_lrn_layer.cu compiled for sm_100), closed-form values on a tiny
+case and the backward formula against central finite differences of the forward one."""
+import os
+
 import numpy as np
 
+from oracle import cianna_oracle as co
 from oracle import lrn_oracle as lo
+from tests.common import GOLDEN_DIR, rel_err
+
+
+def test_lrn_oracle_matches_upstream_cuda_fixture():
+    """both LRN layers of tests/netdefs.lrn_net (explicit parameters / upstream's defaults), forward and backward
+    (upstream's backward ends with the leaky-ReLU derivative of the conv layer below, cuda_lrn_layer.cu:207-214)"""
+    g = np.load(os.path.join(GOLDEN_DIR, "lrn_refcuda.npz"))
+    layers = sorted(int(k.split("_")[1]) for k in g.files if k.startswith("param_"))
+    assert layers == [1, 4]
+    for l in layers:
+        r, k, alpha, beta = g["param_%d" % l]
+        x, y_ref, dy, dx_ref = g["x_%d" % l], g["y_%d" % l], g["dy_%d" % l], g["dx_%d" % l]
+        y, scale = lo.lrn_forward(x, int(r), k, alpha, beta)
+        assert rel_err(y, y_ref) < 1e-5
+        dx = co.relu_deriv(lo.lrn_backward(x, y_ref, dy, scale, int(r), alpha, beta), x, x.shape[1])
+        assert np.abs(dx_ref).max() > 0
+        assert rel_err(dx, dx_ref) < 1e-4
 
 
 def test_lrn_forward_known_values():
