@@ -32,7 +32,9 @@ class ConvDesc(ctypes.Structure):
                 ("out_c", ctypes.c_int), ("out_h", ctypes.c_int), ("out_w", ctypes.c_int),
                 ("f_h", ctypes.c_int), ("f_w", ctypes.c_int), ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int),
                 ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int), ("bias_value", ctypes.c_float), ("activ", Activ),
-                ("input_is_patches", ctypes.c_int)]
+                ("input_is_patches", ctypes.c_int),
+                ("in_d", ctypes.c_int), ("out_d", ctypes.c_int), ("f_d", ctypes.c_int), ("stride_d", ctypes.c_int), ("pad_d", ctypes.c_int),
+                ("ipad_w", ctypes.c_int), ("ipad_h", ctypes.c_int), ("ipad_d", ctypes.c_int)]
 
 
 class ConvWeights(ctypes.Structure):
@@ -44,7 +46,8 @@ class PoolDesc(ctypes.Structure):
     _fields_ = [("dtype", ctypes.c_int), ("batch", ctypes.c_int), ("c", ctypes.c_int), ("in_h", ctypes.c_int), ("in_w", ctypes.c_int),
                 ("out_h", ctypes.c_int), ("out_w", ctypes.c_int), ("p_h", ctypes.c_int), ("p_w", ctypes.c_int),
                 ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int), ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int),
-                ("pool_type", ctypes.c_int), ("length", ctypes.c_int), ("activ", Activ)]
+                ("pool_type", ctypes.c_int), ("length", ctypes.c_int), ("activ", Activ),
+                ("in_d", ctypes.c_int), ("out_d", ctypes.c_int), ("p_d", ctypes.c_int), ("stride_d", ctypes.c_int), ("pad_d", ctypes.c_int)]
 
 
 class NormDesc(ctypes.Structure):

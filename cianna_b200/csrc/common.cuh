@@ -56,8 +56,18 @@ __host__ __device__ inline int round8(int c) { return (c + 7) & ~7; }
 // layout one image of the input is then a single run of f_h*f_w*Cp values in exactly the order of the filter's operand
 // rows, so the layer is a 1x1 convolution over that many "channels"; its data-gradient operand keeps the same order
 // (conv.cu: wbwd_row).
+// depth geometry of cb200_conv_desc: 0 means 1 (a 2-D layer described by a zero-initialised tail of the struct)
+__host__ __device__ inline int conv_in_d(const cb200_conv_desc* d) { return d->in_d > 0 ? d->in_d : 1; }
+__host__ __device__ inline int conv_out_d(const cb200_conv_desc* d) { return d->out_d > 0 ? d->out_d : 1; }
+__host__ __device__ inline int conv_f_d(const cb200_conv_desc* d) { return d->f_d > 0 ? d->f_d : 1; }
+__host__ __device__ inline int conv_taps(const cb200_conv_desc* d) { return conv_f_d(d) * d->f_h * d->f_w; }
+// 3-D geometry or internal padding (transposed convolution): served by the generic CUDA-core kernels only
+__host__ __device__ inline bool conv_generic(const cb200_conv_desc* d) {
+	return conv_in_d(d) > 1 || conv_out_d(d) > 1 || conv_f_d(d) > 1 || d->stride_d > 1 || d->pad_d > 0 ||
+	       d->ipad_w > 0 || d->ipad_h > 0 || d->ipad_d > 0;
+}
 __host__ __device__ inline bool conv_whole_map(const cb200_conv_desc* d) {
-	return d->out_h == 1 && d->out_w == 1 && d->pad_h == 0 && d->pad_w == 0 && d->f_h == d->in_h && d->f_w == d->in_w &&
+	return !conv_generic(d) && d->out_h == 1 && d->out_w == 1 && d->pad_h == 0 && d->pad_w == 0 && d->f_h == d->in_h && d->f_w == d->in_w &&
 	       d->f_h * d->f_w > 1 && d->input_is_patches == 0;
 }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -302,8 +302,12 @@ static int check_desc(const cb200_conv_desc* d) {
 	CB_ARG(d != nullptr);
 	CB_ARG(d->batch > 0 && d->in_c > 0 && d->out_c > 0 && d->in_h > 0 && d->in_w > 0 && d->out_h > 0 && d->out_w > 0);
 	CB_ARG(d->f_h > 0 && d->f_w > 0 && d->stride_h > 0 && d->stride_w > 0 && d->pad_h >= 0 && d->pad_w >= 0);
-	CB_ARG(d->out_h == (d->in_h + 2 * d->pad_h - d->f_h) / d->stride_h + 1);
-	CB_ARG(d->out_w == (d->in_w + 2 * d->pad_w - d->f_w) / d->stride_w + 1);
+	CB_ARG(d->ipad_w >= 0 && d->ipad_h >= 0 && d->ipad_d >= 0 && d->pad_d >= 0);
+	// output size of the reference (nb_area_comp, src/conv_layer.c:32-41): the filter slides over the zero-stuffed, padded input
+	CB_ARG(d->out_h == (d->in_h + (d->in_h - 1) * d->ipad_h + 2 * d->pad_h - d->f_h) / d->stride_h + 1);
+	CB_ARG(d->out_w == (d->in_w + (d->in_w - 1) * d->ipad_w + 2 * d->pad_w - d->f_w) / d->stride_w + 1);
+	CB_ARG(conv_out_d(d) == (conv_in_d(d) + (conv_in_d(d) - 1) * d->ipad_d + 2 * d->pad_d - conv_f_d(d)) / (d->stride_d > 0 ? d->stride_d : 1) + 1);
+	CB_ARG(!(conv_generic(d) && d->input_is_patches));
 	CB_ARG(d->length >= 0 && d->length <= d->batch);
 	return CB200_OK;
 }
@@ -313,19 +317,19 @@ using namespace cb200;
 extern "C" {
 
 int cb200_conv_first_direct(const cb200_conv_desc* d) {
-	return d != nullptr && d->input_is_patches != 0 && !g_force_simt && conv_first_supported(d) ? 1 : 0;
+	return d != nullptr && d->input_is_patches != 0 && !g_force_simt && !conv_generic(d) && conv_first_supported(d) ? 1 : 0;
 }
 
 size_t cb200_conv_wfwd_elems(const cb200_conv_desc* d) {
 	if (d->input_is_patches) return (size_t)d->out_c * cb200_patch_width(d->in_c, d->f_h, d->f_w);
-	return (size_t)d->out_c * d->f_h * d->f_w * round8(d->in_c);
+	return (size_t)d->out_c * conv_taps(d) * round8(d->in_c);
 }
 size_t cb200_conv_wbwd_elems(const cb200_conv_desc* d) {
 	// (whole-map filters keep one row per element of the padded input tensor, see wbwd_row)
-	return (size_t)(conv_whole_map(d) ? round8(d->in_c) : d->in_c) * d->f_h * d->f_w * round8(d->out_c);
+	return (size_t)(conv_whole_map(d) ? round8(d->in_c) : d->in_c) * conv_taps(d) * round8(d->out_c);
 }
 size_t cb200_conv_grad_elems(const cb200_conv_desc* d) { return cb200_conv_wfwd_elems(d); }
-size_t cb200_conv_master_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * ((size_t)d->f_h * d->f_w * d->in_c + 1); }
+size_t cb200_conv_master_elems(const cb200_conv_desc* d) { return (size_t)d->out_c * ((size_t)conv_taps(d) * d->in_c + 1); }
 
 static int prepare_weights_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, size_t ms_f, size_t ms_c, void* s) {
 	CB_REQUIRE_DEVICE();
@@ -341,7 +345,7 @@ static int prepare_weights_impl(const cb200_conv_desc* d, const cb200_conv_weigh
 	// pad lanes of the operands must be zero: clear, then scatter
 	CB_CUDA(cudaMemsetAsync(w->w_fwd, 0, cb200_conv_wfwd_elems(d) * cb200_dtype_size(d->dtype), st));
 	CB_CUDA(cudaMemsetAsync(w->w_bwd, 0, cb200_conv_wbwd_elems(d) * cb200_dtype_size(d->dtype), st));
-	const int taps = d->f_h * d->f_w;
+	const int taps = conv_taps(d);
 	long long total = (long long)cb200_conv_master_elems(d);
 	CB_DISPATCH_DTYPE(d->dtype, T, (conv_prepare_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
 		w->master, (T*)w->w_fwd, (T*)w->w_bwd, w->bias_w, d->out_c, taps, d->in_c, round8(d->in_c), round8(d->out_c), ms_f, ms_c,
@@ -350,7 +354,7 @@ static int prepare_weights_impl(const cb200_conv_desc* d, const cb200_conv_weigh
 	return CB200_OK;
 }
 int cb200_conv_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, void* s) {
-	return prepare_weights_impl(d, w, (size_t)d->f_h * d->f_w * d->in_c + 1, 1, s);
+	return prepare_weights_impl(d, w, (size_t)conv_taps(d) * d->in_c + 1, 1, s);
 }
 int cb200_dense_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weights* w, void* s) {
 	return prepare_weights_impl(d, w, 1, (size_t)d->out_c + 1, s);
@@ -362,7 +366,7 @@ int cb200_conv_forward(const cb200_conv_desc* d_in, const cb200_conv_weights* w,
 	const cb200_conv_desc eff = effective_desc(d_in);
 	const cb200_conv_desc* d = &eff;
 	// algorithmic FLOPs: 2*M*N*K with K including the bias column, excluding any channel padding
-	const double flops = 2.0 * d_in->batch * d_in->out_h * d_in->out_w * (double)d_in->out_c * ((double)d_in->f_h * d_in->f_w * d_in->in_c + 1);
+	const double flops = 2.0 * d_in->batch * conv_out_d(d_in) * d_in->out_h * d_in->out_w * (double)d_in->out_c * ((double)conv_taps(d_in) * d_in->in_c + 1);
 	if (d_in->input_is_patches == 2) {
 		if (!conv_first_supported(d_in)) { set_error("cb200_conv_forward: input_is_patches = 2 is not available for this layer (cb200_conv_first_direct)"); return CB200_ERR_UNSUPPORTED; }
 		g_last_conv_impl = "tcgen05";
@@ -371,7 +375,7 @@ int cb200_conv_forward(const cb200_conv_desc* d_in, const cb200_conv_weights* w,
 		prof_end(as_stream(s));
 		return rc;
 	}
-	const bool tc = !g_force_simt && conv_tc_fwd_supported(d);
+	const bool tc = !g_force_simt && !conv_generic(d) && conv_tc_fwd_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_FWD_TC : PROF_CONV_FWD_SIMT, flops, as_stream(s));
 	rc = tc ? conv_forward_tc(d, w, x, y, as_stream(s)) : conv_forward_simt(d, w, x, y, as_stream(s));
@@ -384,8 +388,8 @@ int cb200_conv_backward_data(const cb200_conv_desc* d, const cb200_conv_weights*
 	CB_REQUIRE_DEVICE();
 	int rc = check_desc(d); if (rc) return rc;
 	if (d->input_is_patches) { set_error("cb200_conv_backward_data: a patch-input (first) layer has no data gradient"); return CB200_ERR_UNSUPPORTED; }
-	const double flops = 2.0 * d->batch * d->in_h * d->in_w * (double)d->in_c * ((double)d->f_h * d->f_w * d->out_c);
-	const bool tc = !g_force_simt && conv_tc_dgrad_supported(d);
+	const double flops = 2.0 * d->batch * conv_in_d(d) * d->in_h * d->in_w * (double)d->in_c * ((double)conv_taps(d) * d->out_c);
+	const bool tc = !g_force_simt && !conv_generic(d) && conv_tc_dgrad_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_DGRAD_TC : PROF_CONV_DGRAD_SIMT, flops, as_stream(s));
 	rc = tc ? conv_dgrad_tc(d, w, dy, dx, prev_activ, prev_out, as_stream(s)) : conv_dgrad_simt(d, w, dy, dx, prev_activ, prev_out, as_stream(s));
@@ -404,12 +408,12 @@ int cb200_conv_backward_weights_ex(const cb200_conv_desc* d_in, const cb200_conv
 	const cb200_conv_desc eff = effective_desc(d_in);
 	const cb200_conv_desc* d = &eff;
 	cudaStream_t st = as_stream(s);
-	long long P = (long long)d->batch * d->out_h * d->out_w;
+	long long P = (long long)d->batch * conv_out_d(d) * d->out_h * d->out_w;
 	if (!d_in->input_is_patches && !have_grad_b) {      // (patch rows carry the bias input as a column: its gradient comes out of the GEMM)
 		rc = conv_colsum(d->dtype, dy, w->grad_b, P, d->out_c, st);
 		if (rc) return rc;
 	}
-	const double flops = 2.0 * P * (double)d_in->out_c * ((double)d_in->f_h * d_in->f_w * d_in->in_c + 1);
+	const double flops = 2.0 * P * (double)d_in->out_c * ((double)conv_taps(d_in) * d_in->in_c + 1);
 	if (d_in->input_is_patches == 2) {
 		if (!conv_first_supported(d_in)) { set_error("cb200_conv_backward_weights: input_is_patches = 2 is not available for this layer"); return CB200_ERR_UNSUPPORTED; }
 		g_last_conv_impl = "tcgen05";
@@ -418,7 +422,7 @@ int cb200_conv_backward_weights_ex(const cb200_conv_desc* d_in, const cb200_conv
 		prof_end(st);
 		return rc;
 	}
-	const bool tc = !g_force_simt && conv_tc_wgrad_supported(d);
+	const bool tc = !g_force_simt && !conv_generic(d) && conv_tc_wgrad_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_WGRAD_TC : PROF_CONV_WGRAD_SIMT, flops, st);
 	rc = tc ? conv_wgrad_tc(d, w, x, dy, st) : conv_wgrad_simt(d, w, x, dy, st);
@@ -437,7 +441,7 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 		CB_LAUNCH_CHECK();
 		return CB200_OK;
 	}
-	const int taps = d->f_h * d->f_w;
+	const int taps = conv_taps(d);
 	long long total = (long long)cb200_conv_master_elems(d);
 	static const bool old_update = getenv("CB200_OLD_UPDATE") != nullptr;
 	if (!old_update && ms_c == 1 && !is_pivot && ms_f == (size_t)taps * d->in_c + 1) {
@@ -482,7 +486,7 @@ static int update_impl(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	return CB200_OK;
 }
 int cb200_conv_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, int is_pivot, void* s) {
-	return update_impl(d, w, hyper, is_pivot, (size_t)d->f_h * d->f_w * d->in_c + 1, 1, s);
+	return update_impl(d, w, hyper, is_pivot, (size_t)conv_taps(d) * d->in_c + 1, 1, s);
 }
 int cb200_dense_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper, void* s) {
 	return update_impl(d, w, hyper, 0, 1, (size_t)d->out_c + 1, s);

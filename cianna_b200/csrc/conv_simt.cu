@@ -15,9 +15,10 @@ constexpr int TM = 64, TN = 64, TK = 16, NTHREADS = 256;
 
 struct ConvGeom {
 	int batch, length;
-	int in_c, in_cp, in_h, in_w;
-	int out_c, out_cp, out_h, out_w;
-	int f_h, f_w, s_h, s_w, p_h, p_w;
+	int in_c, in_cp, in_d, in_h, in_w;
+	int out_c, out_cp, out_d, out_h, out_w;
+	int f_d, f_h, f_w, s_d, s_h, s_w, p_d, p_h, p_w;
+	int q_d, q_h, q_w;           // 1 + internal padding: input pixel i sits at i*q of the zero-stuffed grid the filter slides over
 	int wb_dense;                // row order of w_bwd (conv_whole_map)
 	float bias_value;
 	cb200_activ activ;
@@ -29,9 +30,35 @@ static ConvGeom make_geom(const cb200_conv_desc* d) {
 	g.in_c = d->in_c; g.in_cp = round8(d->in_c); g.in_h = d->in_h; g.in_w = d->in_w;
 	g.out_c = d->out_c; g.out_cp = round8(d->out_c); g.out_h = d->out_h; g.out_w = d->out_w;
 	g.f_h = d->f_h; g.f_w = d->f_w; g.s_h = d->stride_h; g.s_w = d->stride_w; g.p_h = d->pad_h; g.p_w = d->pad_w;
+	g.in_d = conv_in_d(d); g.out_d = conv_out_d(d); g.f_d = conv_f_d(d); g.s_d = d->stride_d > 0 ? d->stride_d : 1; g.p_d = d->pad_d;
+	g.q_d = 1 + d->ipad_d; g.q_h = 1 + d->ipad_h; g.q_w = 1 + d->ipad_w;
 	g.bias_value = d->bias_value; g.activ = d->activ;
 	g.wb_dense = conv_whole_map(d) ? 1 : 0;
 	return g;
+}
+
+// The reference's address map (im2col_kernel, src/cuda/cuda_conv_layer.cu:36-103) in gather form, all three dimensions
+// and internal padding included: output position o, filter tap k -> position v = o*stride - pad + k on the zero-stuffed
+// grid; it holds input pixel v / q when v >= 0, v % q == 0 and v / q < size, a zero otherwise.
+__device__ __forceinline__ bool tap_src(int o, int k, int stride, int pad, int q, int size, int& i) {
+	const int v = o * stride - pad + k;
+	if (v < 0) return false;
+	if (q == 1) { i = v; return v < size; }
+	if (v % q != 0) return false;
+	i = v / q;
+	return i < size;
+}
+// the transposed map of the data gradient: input pixel i, tap k -> the output position o with o*stride - pad + k == i*q
+__device__ __forceinline__ bool tap_dst(int i, int k, int stride, int pad, int q, int size, int& o) {
+	const int n = i * q + pad - k;
+	if (n < 0 || n % stride != 0) return false;
+	o = n / stride;
+	return o < size;
+}
+__device__ __forceinline__ void split_pixel(long long m, int d, int h, int w, int& b, int& z, int& y, int& x) {
+	x = (int)(m % w); long long r = m / w;
+	y = (int)(r % h); r /= h;
+	z = (int)(r % d); b = (int)(r / d);
 }
 
 // ---------------------------------------------------------------- forward
@@ -43,17 +70,17 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ wf, const fl
 	__shared__ float As[TK][TM + 4];
 	__shared__ float Bs[TK][TN + 4];
 	const int tid = threadIdx.x;
-	const long long M = (long long)g.batch * g.out_h * g.out_w;
-	const int K = g.f_h * g.f_w * g.in_cp;
+	const long long M = (long long)g.batch * g.out_d * g.out_h * g.out_w;
+	const int K = g.f_d * g.f_h * g.f_w * g.in_cp;
 	const long long m0 = (long long)blockIdx.x * TM;
 	const int n0 = blockIdx.y * TN;
 
 	// loader roles: each thread owns one row (m or n) and 4 consecutive k
 	const int lrow = tid & 63, lk = (tid >> 6) * 4;
 	const long long lm = m0 + lrow;
-	int lb = 0, loy = 0, lox = 0;
+	int lb = 0, loz = 0, loy = 0, lox = 0;
 	const bool lm_ok = lm < M;
-	if (lm_ok) { lox = (int)(lm % g.out_w); long long r = lm / g.out_w; loy = (int)(r % g.out_h); lb = (int)(r / g.out_h); }
+	if (lm_ok) split_pixel(lm, g.out_d, g.out_h, g.out_w, lb, loz, loy, lox);
 	const int ln = n0 + lrow;
 	const bool ln_ok = ln < g.out_c;
 
@@ -66,10 +93,12 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ wf, const fl
 		if (k < K) {
 			const int tap = k / g.in_cp, c = k - tap * g.in_cp;
 			if (lm_ok) {
-				const int ky = tap / g.f_w, kx = tap - ky * g.f_w;
-				const int iy = loy * g.s_h - g.p_h + ky, ix = lox * g.s_w - g.p_w + kx;
-				if (iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w) {
-					const T* p = x + (((long long)lb * g.in_h + iy) * g.in_w + ix) * g.in_cp + c;
+				const int kz = tap / (g.f_h * g.f_w), kyx = tap - kz * g.f_h * g.f_w;
+				const int ky = kyx / g.f_w, kx = kyx - ky * g.f_w;
+				int iz, iy, ix;
+				if (tap_src(loz, kz, g.s_d, g.p_d, g.q_d, g.in_d, iz) && tap_src(loy, ky, g.s_h, g.p_h, g.q_h, g.in_h, iy)
+				    && tap_src(lox, kx, g.s_w, g.p_w, g.q_w, g.in_w, ix)) {
+					const T* p = x + ((((long long)lb * g.in_d + iz) * g.in_h + iy) * g.in_w + ix) * g.in_cp + c;
 #pragma unroll
 					for (int i = 0; i < 4; i++) av[i] = to_f32<T>(p[i]);
 				}
@@ -101,7 +130,7 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ wf, const fl
 	for (int i = 0; i < 4; i++) {
 		const long long m = m0 + ty * 4 + i;
 		if (m >= M) continue;
-		const int b = (int)(m / ((long long)g.out_h * g.out_w));
+		const int b = (int)(m / ((long long)g.out_d * g.out_h * g.out_w));
 		const bool dead = mask_tail && b >= g.length;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
@@ -123,16 +152,17 @@ conv_dgrad_simt_kernel(const T* __restrict__ dy, const T* __restrict__ wb, T* __
 	__shared__ float As[TK][TM + 4];
 	__shared__ float Bs[TK][TN + 4];
 	const int tid = threadIdx.x;
-	const long long M = (long long)g.batch * g.in_h * g.in_w;
-	const int K = g.f_h * g.f_w * g.out_cp;
+	const long long M = (long long)g.batch * g.in_d * g.in_h * g.in_w;
+	const int taps = g.f_d * g.f_h * g.f_w;
+	const int K = taps * g.out_cp;
 	const long long m0 = (long long)blockIdx.x * TM;
 	const int n0 = blockIdx.y * TN;
 
 	const int lrow = tid & 63, lk = (tid >> 6) * 4;
 	const long long lm = m0 + lrow;
-	int lb = 0, liy = 0, lix = 0;
+	int lb = 0, liz = 0, liy = 0, lix = 0;
 	const bool lm_ok = lm < M;
-	if (lm_ok) { lix = (int)(lm % g.in_w); long long r = lm / g.in_w; liy = (int)(r % g.in_h); lb = (int)(r / g.in_h); }
+	if (lm_ok) split_pixel(lm, g.in_d, g.in_h, g.in_w, lb, liz, liy, lix);
 	const int ln = n0 + lrow;
 	const bool ln_ok = ln < g.in_c;
 
@@ -145,21 +175,21 @@ conv_dgrad_simt_kernel(const T* __restrict__ dy, const T* __restrict__ wb, T* __
 		if (k < K) {
 			const int tapr = k / g.out_cp, f = k - tapr * g.out_cp;
 			if (lm_ok) {
-				// rotated tap (ky',kx') <-> original tap ky = f_h-1-ky'
-				const int kyr = tapr / g.f_w, kxr = tapr - kyr * g.f_w;
-				const int ny = liy + g.p_h - (g.f_h - 1 - kyr), nx = lix + g.p_w - (g.f_w - 1 - kxr);
-				if (ny >= 0 && nx >= 0 && ny % g.s_h == 0 && nx % g.s_w == 0) {
-					const int oy = ny / g.s_h, ox = nx / g.s_w;
-					if (oy < g.out_h && ox < g.out_w) {
-						const T* p = dy + (((long long)lb * g.out_h + oy) * g.out_w + ox) * g.out_cp + f;
+				// rotated tap index <-> original tap: tap = taps - 1 - tap' (reversed in every dimension)
+				const int tap = taps - 1 - tapr;
+				const int kz = tap / (g.f_h * g.f_w), kyx = tap - kz * g.f_h * g.f_w;
+				const int ky = kyx / g.f_w, kx = kyx - ky * g.f_w;
+				int oz, oy, ox;
+				if (tap_dst(liz, kz, g.s_d, g.p_d, g.q_d, g.out_d, oz) && tap_dst(liy, ky, g.s_h, g.p_h, g.q_h, g.out_h, oy)
+				    && tap_dst(lix, kx, g.s_w, g.p_w, g.q_w, g.out_w, ox)) {
+					const T* p = dy + ((((long long)lb * g.out_d + oz) * g.out_h + oy) * g.out_w + ox) * g.out_cp + f;
 #pragma unroll
-						for (int i = 0; i < 4; i++) av[i] = to_f32<T>(p[i]);
-					}
+					for (int i = 0; i < 4; i++) av[i] = to_f32<T>(p[i]);
 				}
 			}
 			if (ln_ok) {
 				// rows (c, rotated tap), or (tap, c) for a whole-map filter (conv.cu: wbwd_row)
-				const T* p = g.wb_dense ? wb + ((long long)(g.f_h * g.f_w - 1 - tapr) * g.in_cp + ln) * g.out_cp + f
+				const T* p = g.wb_dense ? wb + ((long long)(taps - 1 - tapr) * g.in_cp + ln) * g.out_cp + f
 				                        : wb + (long long)ln * K + k;
 #pragma unroll
 				for (int i = 0; i < 4; i++) bv[i] = to_f32<T>(p[i]);
@@ -187,7 +217,7 @@ conv_dgrad_simt_kernel(const T* __restrict__ dy, const T* __restrict__ wb, T* __
 	for (int i = 0; i < 4; i++) {
 		const long long m = m0 + ty * 4 + i;
 		if (m >= M) continue;
-		const int b = (int)(m / ((long long)g.in_h * g.in_w));
+		const int b = (int)(m / ((long long)g.in_d * g.in_h * g.in_w));
 		const bool dead = mask_tail && b >= g.length;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
@@ -212,8 +242,8 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
 	__shared__ float As[TK][TM + 4];   // [pix][f]
 	__shared__ float Bs[TK][TN + 4];   // [pix][(tap,c)]
 	const int tid = threadIdx.x;
-	const long long P = (long long)g.batch * g.out_h * g.out_w;
-	const int NN = g.f_h * g.f_w * g.in_cp;
+	const long long P = (long long)g.batch * g.out_d * g.out_h * g.out_w;
+	const int NN = g.f_d * g.f_h * g.f_w * g.in_cp;
 	const int f0 = blockIdx.x * TM;
 	const int n0 = blockIdx.y * TN;
 	const long long p_begin = (long long)blockIdx.z * pix_per_split;
@@ -225,8 +255,13 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
 	const bool lf_ok = lf < g.out_c;
 	const int ln = n0 + lrow;
 	const bool ln_ok = ln < NN;
-	int ltap = 0, lc = 0, lky = 0, lkx = 0;
-	if (ln_ok) { ltap = ln / g.in_cp; lc = ln - ltap * g.in_cp; lky = ltap / g.f_w; lkx = ltap - lky * g.f_w; }
+	int ltap = 0, lc = 0, lkz = 0, lky = 0, lkx = 0;
+	if (ln_ok) {
+		ltap = ln / g.in_cp; lc = ln - ltap * g.in_cp;
+		lkz = ltap / (g.f_h * g.f_w);
+		const int kyx = ltap - lkz * g.f_h * g.f_w;
+		lky = kyx / g.f_w; lkx = kyx - lky * g.f_w;
+	}
 
 	const int tx = tid & 15, ty = tid >> 4;
 	float acc[4][4] = {};
@@ -239,13 +274,11 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
 			if (pix < p_end) {
 				if (lf_ok) a = to_f32<T>(dy[pix * g.out_cp + lf]);
 				if (ln_ok) {
-					const int ox = (int)(pix % g.out_w);
-					const long long r = pix / g.out_w;
-					const int oy = (int)(r % g.out_h);
-					const int bb = (int)(r / g.out_h);
-					const int iy = oy * g.s_h - g.p_h + lky, ix = ox * g.s_w - g.p_w + lkx;
-					if (iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w)
-						b = to_f32<T>(x[(((long long)bb * g.in_h + iy) * g.in_w + ix) * g.in_cp + lc]);
+					int bb, oz, oy, ox, iz, iy, ix;
+					split_pixel(pix, g.out_d, g.out_h, g.out_w, bb, oz, oy, ox);
+					if (tap_src(oz, lkz, g.s_d, g.p_d, g.q_d, g.in_d, iz) && tap_src(oy, lky, g.s_h, g.p_h, g.q_h, g.in_h, iy)
+					    && tap_src(ox, lkx, g.s_w, g.p_w, g.q_w, g.in_w, ix))
+						b = to_f32<T>(x[((((long long)bb * g.in_d + iz) * g.in_h + iy) * g.in_w + ix) * g.in_cp + lc]);
 				}
 			}
 			As[lk + i][lrow] = a;
@@ -304,7 +337,7 @@ __global__ void colsum_kernel(const T* __restrict__ dy, float* __restrict__ out,
 // ---------------------------------------------------------------- host launchers
 int conv_forward_simt(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y, cudaStream_t st) {
 	ConvGeom g = make_geom(d);
-	long long M = (long long)g.batch * g.out_h * g.out_w;
+	long long M = (long long)g.batch * g.out_d * g.out_h * g.out_w;
 	dim3 grid((unsigned)ceil_div_ll(M, TM), (unsigned)ceil_div(g.out_cp, TN));
 	CB_DISPATCH_DTYPE(d->dtype, T, (conv_fwd_simt_kernel<T><<<grid, NTHREADS, 0, st>>>((const T*)x, (const T*)w->w_fwd, w->bias_w, (T*)y, g)));
 	CB_LAUNCH_CHECK();
@@ -314,7 +347,7 @@ int conv_forward_simt(const cb200_conv_desc* d, const cb200_conv_weights* w, con
 int conv_dgrad_simt(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* dy, void* dx,
                     const cb200_activ* prev_activ, const void* prev_out, cudaStream_t st) {
 	ConvGeom g = make_geom(d);
-	long long M = (long long)g.batch * g.in_h * g.in_w;
+	long long M = (long long)g.batch * g.in_d * g.in_h * g.in_w;
 	dim3 grid((unsigned)ceil_div_ll(M, TM), (unsigned)ceil_div(g.in_cp, TN));
 	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
 	if (prev_activ) pa = *prev_activ;
@@ -339,8 +372,8 @@ int conv_colsum(int dtype, const void* dy, float* out, long long P, int c, cudaS
 
 int conv_wgrad_simt(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, const void* dy, cudaStream_t st) {
 	ConvGeom g = make_geom(d);
-	long long P = (long long)g.batch * g.out_h * g.out_w;
-	int NN = g.f_h * g.f_w * g.in_cp;
+	long long P = (long long)g.batch * g.out_d * g.out_h * g.out_w;
+	int NN = g.f_d * g.f_h * g.f_w * g.in_cp;
 	int tiles = ceil_div(g.out_c, TM) * ceil_div(NN, TN);
 	long long splits = ceil_div_ll((long long)g_num_sms * 4, tiles);
 	long long max_splits = ceil_div_ll(P, 4 * TK);

@@ -65,7 +65,9 @@ struct layer {
 	void *param;
 	void *output;          /* device, internal layout [B][h][w][Cp] */
 	void *delta_o;         /* device, same shape (NULL when inference_only) */
-	int out_c, out_h, out_w;
+	int out_c, out_h, out_w;   /* out_h counts ROWS: depth x height for a 3-D map (activations [B][D][H][W][Cp]); only conv and
+	                            * pool layers look inside, every other layer sees out_h * out_w pixels */
+	int out_d;                 /* depth of the map (1 for 2-D networks); true height = out_h / out_d */
 	int frozen;
 	float bias_value;
 	float dropout_rate;

@@ -89,11 +89,11 @@ int dense_create(network *net, layer *previous, int nb_neurons, const char *acti
 
 	p = (dense_param *)calloc(1, sizeof(dense_param));
 	p->nb_neurons = nb_neurons;
-	if (previous == NULL) { pc = net->in_dims[3]; ph = net->in_dims[1]; pw = net->in_dims[0]; }
+	if (previous == NULL) { pc = net->in_dims[3]; ph = net->in_dims[1] * net->in_dims[2]; pw = net->in_dims[0]; }
 	else { pc = previous->out_c; ph = previous->out_h; pw = previous->out_w; }
 	p->prev_c = pc; p->prev_h = ph; p->prev_w = pw;
 	p->in_size = pc * ph * pw + 1;
-	current->out_c = nb_neurons; current->out_h = 1; current->out_w = 1;
+	current->out_c = nb_neurons; current->out_h = 1; current->out_w = 1; current->out_d = 1;
 	current->param = p;
 	set_activ_defaults(current, activation);
 	if (bias != NULL) current->bias_value = *bias;

@@ -27,10 +27,17 @@ static void *dev_alloc(size_t bytes)
 }
 
 /* shape (c,h,w) of what a layer hands to its successor */
+/* channels, rows (depth x height) and width of the map a layer reads; prev_depth() gives the depth alone */
 static void prev_shape(network *net, layer *previous, int *c, int *h, int *w)
 {
-	if (previous == NULL) { *c = net->in_dims[3]; *h = net->in_dims[1]; *w = net->in_dims[0]; }
+	if (previous == NULL) { *c = net->in_dims[3]; *h = net->in_dims[1] * net->in_dims[2]; *w = net->in_dims[0]; }
 	else { *c = previous->out_c; *h = previous->out_h; *w = previous->out_w; }
+}
+
+static int prev_depth(network *net, layer *previous)
+{
+	int d = previous == NULL ? net->in_dims[2] : previous->out_d;
+	return d > 0 ? d : 1;
 }
 
 static const void *layer_input(layer *current)
@@ -79,6 +86,7 @@ static layer *new_layer(network *net, int type, layer *previous)
 	current->c_network = net;
 	current->type = type;
 	current->previous = previous;
+	current->out_d = previous == NULL ? (net->in_dims[2] > 0 ? net->in_dims[2] : 1) : previous->out_d;   /* conv / pool / dense set their own */
 	return current;
 }
 
@@ -186,7 +194,7 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	int *int_padding, int *in_shape, const char *activation, float *bias, float drop_rate,
 	const char *init_fct, float init_scaling, FILE *f_load, int f_bin)
 {
-	int k, pc, ph, pw;
+	int k, pc, ph, pw, pd, generic;
 	layer *current = new_layer(net, CONV, previous);
 	conv_param *p = (conv_param *)calloc(1, sizeof(conv_param));
 	float *host_w;
@@ -199,8 +207,6 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 		if (stride[k] > f_size[k]) { printf("\nERROR: filter size cannot be smaller than stride size in a given dimension !\n"); exit(EXIT_FAILURE); }
 		p->f_size[k] = f_size[k]; p->stride[k] = stride[k]; p->padding[k] = padding[k]; p->int_padding[k] = int_padding[k];
 	}
-	if (f_size[2] != 1 || net->in_dims[2] != 1) { printf("\nERROR: 3D convolutions (depth > 1) are not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
-	if (int_padding[0] != 0 || int_padding[1] != 0) { printf("\nERROR: internal padding (transposed convolution) is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
 	p->nb_filters = nb_filters;
 	current->dropout_rate = drop_rate;
 
@@ -209,12 +215,17 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 		printf("\nERROR: dense to conv stacking is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE);
 	}
 	prev_shape(net, previous, &pc, &ph, &pw);
-	p->prev_size[0] = pw; p->prev_size[1] = ph; p->prev_size[2] = 1; p->prev_depth = pc;
+	pd = prev_depth(net, previous);
+	ph /= pd;      /* true height */
+	p->prev_size[0] = pw; p->prev_size[1] = ph; p->prev_size[2] = pd; p->prev_depth = pc;
 	p->flat_f_size = f_size[0] * f_size[1] * f_size[2] * pc + 1;
 	for (k = 0; k < 3; k++)
 		p->nb_area[k] = nb_area_comp(p->prev_size[k], p->f_size[k], p->padding[k], p->int_padding[k], p->stride[k]);
+	/* three-dimensional maps and internal padding (transposed convolution) run on the generic CUDA-core kernels */
+	generic = pd > 1 || p->nb_area[2] > 1 || f_size[2] > 1 || padding[2] > 0 || int_padding[0] > 0 || int_padding[1] > 0 || int_padding[2] > 0;
 
-	current->out_c = nb_filters; current->out_w = p->nb_area[0]; current->out_h = p->nb_area[1];
+	current->out_c = nb_filters; current->out_w = p->nb_area[0]; current->out_d = p->nb_area[2];
+	current->out_h = p->nb_area[1] * p->nb_area[2];
 	current->param = p;
 	set_activ_defaults(current, activation);
 	if (bias != NULL) current->bias_value = *bias;
@@ -223,10 +234,14 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 
 	p->desc.dtype = net->dtype; p->desc.batch = net->batch_size; p->desc.length = net->batch_size;
 	p->desc.in_c = pc; p->desc.in_h = ph; p->desc.in_w = pw;
-	p->desc.out_c = nb_filters; p->desc.out_h = current->out_h; p->desc.out_w = current->out_w;
+	p->desc.out_c = nb_filters; p->desc.out_h = p->nb_area[1]; p->desc.out_w = current->out_w;
 	p->desc.f_h = f_size[1]; p->desc.f_w = f_size[0];
 	p->desc.stride_h = stride[1]; p->desc.stride_w = stride[0];
 	p->desc.pad_h = padding[1]; p->desc.pad_w = padding[0];
+	if (generic) {
+		p->desc.in_d = pd; p->desc.out_d = p->nb_area[2]; p->desc.f_d = f_size[2]; p->desc.stride_d = stride[2]; p->desc.pad_d = padding[2];
+		p->desc.ipad_w = int_padding[0]; p->desc.ipad_h = int_padding[1]; p->desc.ipad_d = int_padding[2];
+	}
 	p->desc.bias_value = current->bias_value;
 	p->desc.activ = current->activ;
 	if (current->activation_type == SOFTMAX || current->activation_type == YOLO)
@@ -235,7 +250,7 @@ int conv_create(network *net, layer *previous, int *f_size, int nb_filters, int 
 	cb_dropout_setup(current);
 	/* first layer on an input with very few channels (RGB / grey): the layout import unrolls the receptive fields into
 	 * patch rows so that the layer runs on the tensor-core GEMM kernels (include/cianna_b200.h, cb200_import_input_patches) */
-	p->desc.input_is_patches = (previous == NULL && cb200_round_channels(pc) < 16) ? 1 : 0;
+	p->desc.input_is_patches = (previous == NULL && cb200_round_channels(pc) < 16 && !generic) ? 1 : 0;
 	if (p->desc.input_is_patches && cb200_conv_first_direct(&p->desc)) {
 		/* ... or, for the usual first-layer shapes, the kernels build those rows in shared memory straight from the
 		 * dataset batch: no import pass, no patch tensor in HBM; the layer's input pointer is the batch itself */
@@ -457,7 +472,7 @@ static void backward_pool_layer(layer *current)
 int pool_create(network *net, layer *previous, int *pool_size, int *stride, int *padding,
 	const char *char_pool_type, const char *activation, int global, float drop_rate)
 {
-	int k, pc, ph, pw;
+	int k, pc, ph, pw, pd;
 	layer *current = new_layer(net, POOL, previous);
 	pool_param *p = (pool_param *)calloc(1, sizeof(pool_param));
 	char activ[40];
@@ -479,20 +494,28 @@ int pool_create(network *net, layer *previous, int *pool_size, int *stride, int 
 	if (previous != NULL && previous->type == POOL) { printf("ERROR: Bad network design, no use of two successive pooling layer.\n"); exit(EXIT_FAILURE); }
 	if (previous != NULL && previous->type == DENSE) { printf("ERROR: Unsuported layer types stacking."); exit(EXIT_FAILURE); }
 	prev_shape(net, previous, &pc, &ph, &pw);
-	p->prev_size[0] = pw; p->prev_size[1] = ph; p->prev_size[2] = 1; p->prev_depth = pc;
+	pd = prev_depth(net, previous);
+	ph /= pd;      /* true height */
+	p->prev_size[0] = pw; p->prev_size[1] = ph; p->prev_size[2] = pd; p->prev_depth = pc;
 	if (global)
 		for (k = 0; k < 3; k++) { p->p_size[k] = p->prev_size[k]; p->stride[k] = p->prev_size[k]; p->padding[k] = 0; }
-	if (p->p_size[2] != 1) { printf("\nERROR: 3D pooling is not supported by the B200 core yet.\n"); exit(EXIT_FAILURE); }
+	if (p->p_size[0] * p->p_size[1] * p->p_size[2] >= 255 && !(global && p->pool_type == AVG_pool && pd == 1)) {
+		printf("\nERROR: pooling windows of 255 elements or more are only available as global average pooling of a 2-D map.\n"); exit(EXIT_FAILURE);
+	}
 	for (k = 0; k < 3; k++)
 		p->nb_area[k] = nb_area_comp(p->prev_size[k], p->p_size[k], p->padding[k], 0, p->stride[k]);
 	p->nb_maps = pc;
-	current->out_c = pc; current->out_w = p->nb_area[0]; current->out_h = p->nb_area[1];
+	current->out_c = pc; current->out_w = p->nb_area[0]; current->out_d = p->nb_area[2];
+	current->out_h = p->nb_area[1] * p->nb_area[2];
 	current->param = p;
 	set_activ_defaults(current, activation);
 	if (current->activation_type == YOLO) { printf("\nERROR: YOLO activation on a pool layer is not supported.\n"); exit(EXIT_FAILURE); }
 
 	p->desc.dtype = net->dtype; p->desc.batch = net->batch_size; p->desc.length = net->batch_size;
-	p->desc.c = pc; p->desc.in_h = ph; p->desc.in_w = pw; p->desc.out_h = current->out_h; p->desc.out_w = current->out_w;
+	p->desc.c = pc; p->desc.in_h = ph; p->desc.in_w = pw; p->desc.out_h = p->nb_area[1]; p->desc.out_w = current->out_w;
+	if (pd > 1 || p->nb_area[2] > 1 || p->p_size[2] > 1 || p->padding[2] > 0) {      /* 3-D windows: generic kernels (pool.cu) */
+		p->desc.in_d = pd; p->desc.out_d = p->nb_area[2]; p->desc.p_d = p->p_size[2]; p->desc.stride_d = p->stride[2]; p->desc.pad_d = p->padding[2];
+	}
 	p->desc.p_h = p->p_size[1]; p->desc.p_w = p->p_size[0];
 	p->desc.stride_h = p->stride[1]; p->desc.stride_w = p->stride[0];
 	p->desc.pad_h = p->padding[1]; p->desc.pad_w = p->padding[0];

@@ -87,7 +87,7 @@ void init_network(int network_number, int u_input_dim[4], int u_output_dim, floa
 	{
 		size_t es = cb200_dtype_size(net->dtype);
 		CB_CHECK(cb200_malloc(&net->input_raw, (size_t)net->batch_size * (net->input_dim + 1) * es));
-		CB_CHECK(cb200_malloc(&net->input, (size_t)net->batch_size * net->in_dims[0] * net->in_dims[1] * cb200_round_channels(net->in_dims[3]) * es));
+		CB_CHECK(cb200_malloc(&net->input, (size_t)net->batch_size * net->in_dims[0] * net->in_dims[1] * net->in_dims[2] * cb200_round_channels(net->in_dims[3]) * es));
 		CB_CHECK(cb200_malloc(&net->target, (size_t)net->batch_size * (net->output_dim > 0 ? net->output_dim : 1) * es));
 		CB_CHECK(cb200_malloc((void **)&net->loss_dev, (size_t)net->batch_size * sizeof(float)));
 		CB_CHECK(cb200_host_alloc((void **)&net->loss_host, (size_t)net->batch_size * sizeof(float)));
@@ -463,7 +463,7 @@ static void use_device_batch(network *net, const void *input_dev)
 		CB_CHECK(cb200_import_input_patches(net->input, input_dev, net->dtype, net->batch_size, d->in_c, d->in_h, d->in_w,
 			d->f_h, d->f_w, d->stride_h, d->stride_w, d->pad_h, d->pad_w, d->out_h, d->out_w, d->bias_value, NULL));
 	} else
-		CB_CHECK(cb200_import_input(net->input, input_dev, net->dtype, net->batch_size, net->in_dims[3], net->in_dims[1], net->in_dims[0], NULL));
+		CB_CHECK(cb200_import_input(net->input, input_dev, net->dtype, net->batch_size, net->in_dims[3], net->in_dims[1] * net->in_dims[2], net->in_dims[0], NULL));
 }
 
 /* ---- per-layer timing sample (perf_eval): slot s of pass p (0 forward, 1 backward, 2 optimizer) */

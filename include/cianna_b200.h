@@ -167,7 +167,7 @@ int  cb200_export_pool_map(int32_t* dst, const uint8_t* src, int batch, int c, i
 int  cb200_export_dense(float* dst, const void* src, int dtype, int batch, int n, float bias_node, void* stream);
 
 /* ------------------------------------------------------------------ convolution */
-/* Geometry of one conv layer (2-D; depth = 1). Replaces conv_param (src/structs.h:392-415). */
+/* Geometry of one conv layer. Replaces conv_param (src/structs.h:392-415). */
 typedef struct {
 	int dtype;
 	int batch;            /* net->batch_size */
@@ -185,6 +185,13 @@ typedef struct {
 	                         2: `x` is the dataset batch itself, [batch][in_c*in_h*in_w + 1] values of `dtype`: the patch
 	                         rows are built in shared memory inside the forward / weight-gradient kernels and never
 	                         touch HBM (allowed when cb200_conv_first_direct() returns 1; weight buffers as in mode 1) */
+	/* third dimension and internal padding (src/structs.h:392-415: f_size[2], stride[2], padding[2], int_padding[3]); all
+	 * zero for a plain 2-D layer (0 depth / stride means 1).  Activations are then [batch][D][H][W][Cp], the filter taps
+	 * run depth-major (tap = (kz*f_h + ky)*f_w + kx, upstream's column order), and internal padding q-1 puts input pixel i
+	 * at position i*q of the zero-stuffed grid the filter slides over (transposed convolution,
+	 * src/cuda/cuda_conv_layer.cu:66-68).  Such layers run on the generic CUDA-core kernels (conv_simt.cu). */
+	int in_d, out_d, f_d, stride_d, pad_d;
+	int ipad_w, ipad_h, ipad_d;
 } cb200_conv_desc;
 /* 1 when a first layer described by `d` (input_is_patches != 0) can run in mode 2: 16-bit compute type, 3x3 filters on
  * 1-3 channels or 5x5 on one channel, 8..64 filters, tensor-core path not disabled by cb200_force_simt. */
@@ -273,6 +280,9 @@ typedef struct {
 	int pool_type;        /* cb200_pool_type */
 	int length;
 	cb200_activ activ;    /* layer activation applied to the pooled output (LINEAR / RELU / LOGISTIC) */
+	/* third dimension (src/structs.h:418-436: p_size[2], stride[2], padding[2]); all zero for a 2-D layer (0 = 1).
+	 * Activations are then [batch][D][H][W][Cp]; map value (z*p_h + y)*p_w + x (cuda_pool_layer.cu:108). */
+	int in_d, out_d, p_d, stride_d, pad_d;
 } cb200_pool_desc;
 
 /* Replaces cuda_forward_pool_layer (src/cuda/cuda_pool_layer.cu:429-492). map: uint8 [B][Ho][Wo][Cp],

@@ -64,7 +64,7 @@ class CudaBackendNet:
         else:
             build_network(self.cnn, spec, "C_CUDA", mode, network=0, inference_only=inference_only, dynamic_load=dynamic_load)
         self.n_layers = self.lib.probe_cuda_nb_layers(0)
-        self.in_dim = spec["in_dim"][0] * spec["in_dim"][1] * spec["in_ch"]
+        self.in_dim = int(np.prod(spec["in_dim"])) * spec["in_ch"]      # (w, h) or (w, h, d)
         self._keep = []
 
     def geom(self, l):

@@ -95,7 +95,7 @@ class RefNet:
         else:
             build_network(self.cnn, spec, comp_meth, "off", network=0)
         self.n_layers = self.lib.probe_nb_layers(0)
-        self.in_dim = spec["in_dim"][0] * spec["in_dim"][1] * spec["in_ch"]
+        self.in_dim = int(np.prod(spec["in_dim"])) * spec["in_ch"]      # (w, h) or (w, h, d)
         self._keep = []
 
     # ---- geometry
