@@ -622,6 +622,11 @@ def set_fusion(on):
     _load().cb_set_fusion(int(on))
 
 
+def set_update_plan(on):
+    """optimizer sweep of the whole network in three launches (default) or layer by layer; same results bit for bit"""
+    _load().cb_set_update_plan(int(on))
+
+
 def last_conv_impl():
     return core().cb200_last_conv_impl().decode()
 

@@ -292,13 +292,21 @@ class NormLayer:
                                         self.beta.ptr, self.mean.ptr, self.var.ptr, self.ws.ptr, None))
         return pool.y
 
-    def backward_pool(self, x_buf, dpool_buf, pool, prev_act=None):
+    def backward_pool(self, x_buf, dpool_buf, pool, prev_act=None, from_pooled_output=False):
+        """from_pooled_output: the backward reductions read the pooled delta and pool.y (cb200_norm_pool_backward_ex)
+        instead of the input-sized tensor"""
         L = lib()
         L.cb200_norm_pool_backward.argtypes = [ctypes.c_void_p] * 15
+        L.cb200_norm_pool_backward_ex.argtypes = [ctypes.c_void_p] * 17
         pa = ctypes.byref(prev_act) if prev_act is not None else None
-        check(L.cb200_norm_pool_backward(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, dpool_buf.ptr, pool.map.ptr, self.dx.ptr,
-                                         self.gamma.ptr, self.mean.ptr, self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa,
-                                         self.colsum.ptr, self.ws.ptr, None))
+        if from_pooled_output:
+            check(L.cb200_norm_pool_backward_ex(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, dpool_buf.ptr, pool.map.ptr, self.dx.ptr,
+                                                self.gamma.ptr, self.mean.ptr, self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa,
+                                                self.colsum.ptr, self.ws.ptr, pool.y.ptr, self.beta.ptr, None))
+        else:
+            check(L.cb200_norm_pool_backward(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, dpool_buf.ptr, pool.map.ptr, self.dx.ptr,
+                                             self.gamma.ptr, self.mean.ptr, self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa,
+                                             self.colsum.ptr, self.ws.ptr, None))
         return self.dx
 
     def stats(self):

@@ -192,6 +192,23 @@ __host__ __device__ __forceinline__ bool activ_masks_tail(const cb200_activ& a) 
 	return a.type == CB200_RELU || a.type == CB200_LOGISTIC || a.type == CB200_SOFTMAX;
 }
 
+// One SGD + momentum + weight-decay step on one weight (upstream: cuda_update_weights, src/cuda/cuda_main.cu:486-509, with
+// the loss-scale factor S carried by gradient and momentum).  Written with explicit round-to-nearest intrinsics so that
+// every kernel that calls it - the per-layer update kernels and the whole-network plan kernels (update_plan.cu) - gets the
+// same FMA contraction and therefore the same bits.
+__device__ __forceinline__ void sgd_momentum_step(float alpha, float mom, float wdlr, float S, float g, float& m, float& w) {
+	float t = __fmaf_rn(alpha, g, __fmul_rn(mom, m));
+	t = __fmaf_rn(__fmul_rn(wdlr, w), S, t);
+	w = __fsub_rn(w, __fdiv_rn(t, S));
+	m = t;
+}
+// group-norm parameter step (no weight decay): upd = mom * upd + alpha * sum ; param -= upd / S
+__device__ __forceinline__ void norm_param_step(float alpha, float mom, float S, float sum, float& upd, float& param) {
+	const float u = __fmaf_rn(mom, upd, __fmul_rn(alpha, sum));
+	upd = u;
+	param = __fsub_rn(param, __fdiv_rn(u, S));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -215,20 +215,16 @@ conv_update_rows_kernel(float* __restrict__ master, float* __restrict__ moment, 
 		const int tap = j / in_cp, c = j - tap * in_cp;
 		if (c >= in_c) continue;
 		const int mi = c * taps + tap;
-		float wv = sm_w[mi];
-		float m = alpha * g[j] + mom * sm_m[mi];
-		m += wdlr * wv * S;
-		wv -= m / S;
+		float wv = sm_w[mi], m = sm_m[mi];
+		sgd_momentum_step(alpha, mom, wdlr, S, g[j], m, wv);
 		sm_m[mi] = m;
 		sm_w[mi] = wv;
 		wf[j] = from_f32<T>(wv);
 	}
 	if (threadIdx.x == 0) {
 		const int mi = kref - 1;
-		float wv = sm_w[mi];
-		float m = alpha * (bias_value * grad_b[f]) + mom * sm_m[mi];
-		m += wdlr * wv * S;
-		wv -= m / S;
+		float wv = sm_w[mi], m = sm_m[mi];
+		sgd_momentum_step(alpha, mom, wdlr, S, __fmul_rn(bias_value, grad_b[f]), m, wv);
 		sm_m[mi] = m;
 		sm_w[mi] = wv;
 		bias_w[f] = wv;

@@ -301,12 +301,8 @@ __global__ void norm_update_kernel(float* __restrict__ gamma, float* __restrict_
 	const int grp = blockIdx.x * blockDim.x + threadIdx.x;
 	if (grp >= nb_group - set_off) return;
 	const float alpha = hyper[0], mom = hyper[1], S = hyper[3];
-	const float gu = mom * gamma_upd[grp] + alpha * gsum[grp];
-	const float bu = mom * beta_upd[grp] + alpha * gsum[nb_group + grp];
-	gamma_upd[grp] = gu;
-	beta_upd[grp] = bu;
-	gamma[grp] -= gu / S;
-	beta[grp] -= bu / S;
+	norm_param_step(alpha, mom, S, gsum[grp], gamma_upd[grp], gamma[grp]);
+	norm_param_step(alpha, mom, S, gsum[nb_group + grp], beta_upd[grp], beta[grp]);
 }
 
 // single-GPU form of the two kernels above in one launch (no all-reduce between them): one warp per group sums the
@@ -326,12 +322,8 @@ __global__ void norm_reduce_update_kernel(const float* __restrict__ d_gamma, con
 	gsum[grp] = fg; gsum[nb_group + grp] = fb;
 	if (grp >= nb_group - set_off) return;
 	const float alpha = hyper[0], mom = hyper[1], S = hyper[3];
-	const float gu = mom * gamma_upd[grp] + alpha * fg;
-	const float bu = mom * beta_upd[grp] + alpha * fb;
-	gamma_upd[grp] = gu;
-	beta_upd[grp] = bu;
-	gamma[grp] -= gu / S;
-	beta[grp] -= bu / S;
+	norm_param_step(alpha, mom, S, fg, gamma_upd[grp], gamma[grp]);
+	norm_param_step(alpha, mom, S, fb, beta_upd[grp], beta[grp]);
 }
 
 // ---------------------------------------------------------------- group-norm + 2x2 max-pool, fused
@@ -465,6 +457,106 @@ __global__ void __launch_bounds__(NORM_THREADS)
 norm_pool_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, double* __restrict__ ws, FusedGeom f) {
 	extern __shared__ float sm_acc[];
 	norm_pool_bwd_stats_body<T>(x, dp, map, ws, f, blockIdx.x, blockIdx.y, sm_acc);
+}
+
+// The same two sums WITHOUT reading the full-resolution input: at the selected position the forward pass stored
+// y = x*sc + sh (the pooled output, kept for the next layer's weight gradient), so x = (y - sh) / sc there and
+// sum(d*x) runs over the pooled delta and the pooled output alone - 2 quarter-size tensors instead of the input-sized
+// one + delta + map (first Darknet19 layer at batch 128: 0.82 GB instead of 2.27 GB).  y carries one rounding to the
+// storage type, like x does; dividing by sc amplifies it by |y| / |x*sc| ~ 1 + |beta / gamma|, so groups with
+// |beta| > 16 |gamma| or |gamma| < 1e-4, and dead samples (whose pooled output is zero), keep the gather from x.
+template <typename T>
+__device__ __forceinline__ void norm_pool_bwd_stats_y_body(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map,
+                                                           const T* __restrict__ yp, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ mean, const float* __restrict__ var,
+                                                           double* __restrict__ ws, const FusedGeom& f, int vbx, int b, float* sm_acc) {
+	const NormGeom& g = f.n;
+	const int cv = g.cp >> 3;
+	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x) sm_acc[i] = 0.0f;
+	__syncthreads();
+	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
+	const int lanes_p = NORM_THREADS / lanes_c;
+	const int lane_c = threadIdx.x % lanes_c, lane_p = threadIdx.x / lanes_c;
+	const bool active = lane_p < lanes_p;
+	const int q0 = vbx * f.ppb_out;
+	int q1 = q0 + f.ppb_out;
+	if (q1 > f.out_hw) q1 = f.out_hw;
+	const long long row = (long long)f.in_w * g.cp;
+	const bool dead = b >= g.length;
+	for (int v = lane_c; v < cv; v += lanes_c) {
+		float isc[8], off[8];
+		uint32_t slow = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const int ch = v * 8 + j;
+			isc[j] = 0.0f; off[j] = 0.0f;
+			if (ch >= g.c) continue;
+			const int grp = ch / g.group_size;
+			if (dead) slow |= 1u << j;
+			else if (grp < g.nb_group - g.set_off) {
+				const float ga = gamma[grp], be = beta[grp];
+				if (fabsf(ga) < 1e-4f || fabsf(be) > 16.0f * fabsf(ga)) slow |= 1u << j;
+				else {
+					const float rstd = 1.0f / sqrtf(var[b * g.nb_group + grp] + g.eps);
+					const float sc = ga * rstd;
+					const float sh = be - mean[b * g.nb_group + grp] * sc;
+					isc[j] = 1.0f / sc;
+					off[j] = -sh * isc[j];
+				}
+			} else isc[j] = 1.0f;                      // pass-through group: y == x
+		}
+		float s0[8], s1[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) { s0[j] = 0.0f; s1[j] = 0.0f; }
+		const T* xb = x + (long long)b * g.hw * g.cp + v * 8;
+		const long long ob = (long long)b * f.out_hw * g.cp + v * 8;
+		constexpr int U = 4;
+		for (int q = q0 + lane_p; active && q < q1; q += lanes_p * U) {
+			Raw8<T> rd[U], ry[U];
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const int qq = q + u * lanes_p;
+				if (qq < q1) { const long long o = ob + (long long)qq * g.cp; rd[u] = load_raw8<T>(dp + o); ry[u] = load_raw8<T>(yp + o); }
+			}
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const int qq = q + u * lanes_p;
+				if (qq >= q1) continue;
+				float d[8], yv[8], xs[8];
+				unpack8(rd[u], d); unpack8(ry[u], yv);
+#pragma unroll
+				for (int j = 0; j < 8; j++) xs[j] = fmaf(yv[j], isc[j], off[j]);
+				if (slow != 0) {
+					const int oy = qq / f.out_w, ox = qq - oy * f.out_w;
+					const T* p = xb + (long long)(2 * oy) * row + (long long)(2 * ox) * g.cp;
+					const uint2 rm = __ldg(reinterpret_cast<const uint2*>(map + ob + (long long)qq * g.cp));
+					float a0[8], a1[8], a2[8], a3[8];
+					unpack8(load_raw8<T>(p), a0); unpack8(load_raw8<T>(p + g.cp), a1);
+					unpack8(load_raw8<T>(p + row), a2); unpack8(load_raw8<T>(p + row + g.cp), a3);
+#pragma unroll
+					for (int j = 0; j < 8; j++) {
+						const uint32_t m = map_byte(rm, j);
+						if ((slow >> j) & 1u) xs[j] = m == 0 ? a0[j] : (m == 1 ? a1[j] : (m == 2 ? a2[j] : a3[j]));
+					}
+				}
+#pragma unroll
+				for (int j = 0; j < 8; j++) { s0[j] += d[j]; s1[j] += d[j] * xs[j]; }
+			}
+		}
+		fold_into_groups(s0, s1, v, lanes_c, g, sm_acc);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < g.nb_group * 2; i += blockDim.x)
+		atomicAdd(&ws[(size_t)b * g.nb_group * 2 + i], (double)sm_acc[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_pool_bwd_stats_y_kernel(const T* __restrict__ x, const T* __restrict__ dp, const uint8_t* __restrict__ map, const T* __restrict__ yp,
+                             const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                             const float* __restrict__ var, double* __restrict__ ws, FusedGeom f) {
+	extern __shared__ float sm_acc[];
+	norm_pool_bwd_stats_y_body<T>(x, dp, map, yp, gamma, beta, mean, var, ws, f, blockIdx.x, blockIdx.y, sm_acc);
 }
 
 // dx of the four input pixels of each window: ca*d + cx*x + cc with d = pooled delta at the selected position, else 0;
@@ -879,6 +971,14 @@ int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, const void* d_pooled,
                              const uint8_t* pool_map, void* dx, const float* gamma, const float* mean, const float* var,
                              float* d_gamma, float* d_beta, const cb200_activ* prev_activ, float* dx_colsum, void* workspace, void* s) {
+	return cb200_norm_pool_backward_ex(nd, pd, x, d_pooled, pool_map, dx, gamma, mean, var, d_gamma, d_beta, prev_activ, dx_colsum,
+	                                   workspace, nullptr, nullptr, s);
+}
+
+int cb200_norm_pool_backward_ex(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, const void* d_pooled,
+                                const uint8_t* pool_map, void* dx, const float* gamma, const float* mean, const float* var,
+                                float* d_gamma, float* d_beta, const cb200_activ* prev_activ, float* dx_colsum, void* workspace,
+                                const void* pooled, const float* beta, void* s) {
 	CB_REQUIRE_DEVICE();
 	FusedGeom f;
 	int rc = fill_fused(nd, pd, f); if (rc) return rc;
@@ -889,8 +989,9 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
 	cb200_activ pa; pa.type = CB200_LINEAR; pa.leak = 0; pa.saturation = 0; pa.beta = 0;
 	if (prev_activ) pa = *prev_activ;
 	const double es = (double)cb200_dtype_size(nd->dtype), E = (double)g.batch * g.hw * g.c;
-	// algorithmic bytes: x for the reductions, x again + dx for the apply, the pooled delta and its map twice
-	prof_begin(PROF_NORM, 3.0 * E * es + 0.5 * E * (es + 1.0), st);
+	// algorithmic bytes: the pooled delta + pooled output for the reductions (x + pooled delta + map without `pooled`), then
+	// x + dx + the pooled delta and its map for the apply
+	prof_begin(PROF_NORM, (pooled != nullptr && beta != nullptr ? 2.0 * E * es + 0.5 * E * es : 3.0 * E * es + 0.25 * E * (es + 1.0)) + 0.25 * E * (es + 1.0), st);
 	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
 	if (norm_pipeline_on()) {
 		if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
@@ -908,8 +1009,14 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
 		return CB200_OK;
 	}
 	dim3 grid_o((unsigned)ceil_div(f.out_hw, f.ppb_out), (unsigned)g.batch);
-	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_stats_kernel<T><<<grid_o, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
-		(const T*)x, (const T*)d_pooled, pool_map, ws, f)));
+	static const bool stats_from_y = env_int("CB200_GN_POOL_STATS_Y", 1) != 0;
+	if (pooled != nullptr && beta != nullptr && stats_from_y) {
+		// reductions over the pooled delta and the pooled OUTPUT only (see norm_pool_bwd_stats_y_body)
+		CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_stats_y_kernel<T><<<grid_o, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
+			(const T*)x, (const T*)d_pooled, pool_map, (const T*)pooled, gamma, beta, mean, var, ws, f)));
+	} else
+		CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_bwd_stats_kernel<T><<<grid_o, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(
+			(const T*)x, (const T*)d_pooled, pool_map, ws, f)));
 	CB_LAUNCH_CHECK();
 	if (dx_colsum != nullptr) CB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * g.c, st));
 	unsigned agrid;

@@ -193,6 +193,9 @@ struct network {
 	float *loss_dev;       /* FP32 [batch_size] per-sample loss */
 	float *loss_host;      /* pinned */
 	float *hyper_dev;      /* CB200_HYPER_LEN floats */
+	void *update_plan;     /* cb200_update_plan of the layers below (the optimizer sweep in three launches), or NULL */
+	unsigned update_plan_sig;   /* which layers were frozen / how the norm sums arrive when the plan was built */
+	unsigned char in_update_plan[MAX_LAYERS_NB];
 	float *grad_arena;     /* all raw gradients, contiguous (all-reduced in data-parallel runs) */
 	size_t grad_arena_len;
 	int training_ready;
@@ -323,6 +326,7 @@ void cb_backward(network *net, float lr, float momentum, float weight_decay);   
 float cb_batch_loss(network *net);                                               /* sum over samples / length */
 void cb_train_step(network *net, float lr, float momentum, float weight_decay); /* forward + backward on the loaded batch */
 void cb_sync(void);
+void cb_set_update_plan(int on);   /* optimizer sweep in three launches (csrc/update_plan.cu) or layer by layer */
 /* read-back in the reference's layouts; dst sized by the caller */
 void cb_layer_export_output(network *net, int l, float *dst);
 void cb_layer_export_delta(network *net, int l, float *dst);

@@ -629,8 +629,10 @@ static void backward_norm_layer(layer *current)
 			layer *pool = p->fused_pool;
 			pool_param *pp = (pool_param *)pool->param;
 			pp->desc.length = net->length;
-			CB_CHECK(cb200_norm_pool_backward(&p->desc, &pp->desc, prev->output, pool->delta_o, pp->pool_map, prev->delta_o,
-				p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, NULL));
+			/* (the pool layer's output - masked in place by its dropout, whose backward has already zeroed the same elements of
+			 * its delta - lets the backward reductions skip the input-sized tensor) */
+			CB_CHECK(cb200_norm_pool_backward_ex(&p->desc, &pp->desc, prev->output, pool->delta_o, pp->pool_map, prev->delta_o,
+				p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, pool->output, p->beta, NULL));
 		} else
 			CB_CHECK(cb200_norm_backward(&p->desc, prev->output, current->delta_o, prev->delta_o,
 				p->gamma, p->mean, p->var, p->d_gamma, p->d_beta, &prev->activ, colsum, p->workspace, NULL));

@@ -542,9 +542,64 @@ static void output_error(network *net, const void *target_dev)
 		last->out_c, last->out_h, last->out_w, last->activation_type == SOFTMAX ? 1 : 0, NULL));
 }
 
+static int update_plan_on = -1;   /* -1: take CB200_UPDATE_PLAN (default on) at first use */
+
+void cb_set_update_plan(int on) { update_plan_on = on ? 1 : 0; }
+
+static int update_plan_enabled(void)
+{
+	if (update_plan_on < 0) { const char *e = getenv("CB200_UPDATE_PLAN"); update_plan_on = (e != NULL && e[0] == '0') ? 0 : 1; }
+	return update_plan_on;
+}
+
+/* (re)build the plan when the set of layers it covers may have changed: first use, a layer frozen / unfrozen, the
+ * data-parallel world joined since */
+static void update_plan_refresh(network *net)
+{
+	const cb200_conv_desc *descs[MAX_LAYERS_NB];
+	const cb200_conv_weights *ws[MAX_LAYERS_NB];
+	cb200_norm_update_ref norms[MAX_LAYERS_NB];
+	unsigned sig = 2166136261u;
+	int k, nc = 0, nn = 0;
+	const int dp = cb200_dp_world() > 1;
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		sig = (sig ^ (unsigned)(l->frozen ? 2 : 1)) * 16777619u;
+		if (l->type == CONV) sig = (sig ^ (unsigned)(size_t)((conv_param *)l->param)->w.master) * 16777619u;
+		else if (l->type == NORM) sig = (sig ^ (unsigned)(size_t)((norm_param *)l->param)->gamma) * 16777619u;
+	}
+	sig = (sig ^ (unsigned)dp) * 16777619u;
+	sig = (sig ^ (unsigned)(size_t)net->grad_arena) * 16777619u;
+	if (sig == 0) sig = 1;
+	if (net->update_plan_sig == sig) return;
+	if (net->update_plan != NULL) { cb200_update_plan_destroy(net->update_plan); net->update_plan = NULL; }
+	memset(net->in_update_plan, 0, sizeof(net->in_update_plan));
+	for (k = 0; k < net->nb_layers; k++) {
+		layer *l = net->net_layers[k];
+		if (l->frozen) continue;
+		if (l->type == CONV) {
+			conv_param *p = (conv_param *)l->param;
+			if (!cb200_update_plan_accepts(&p->desc)) continue;
+			descs[nc] = &p->desc; ws[nc] = &p->w; nc++;
+			net->in_update_plan[k] = 1;
+		} else if (l->type == NORM) {
+			norm_param *p = (norm_param *)l->param;
+			norms[nn].d_gamma = p->d_gamma; norms[nn].d_beta = p->d_beta; norms[nn].gsum = p->gsum;
+			norms[nn].gamma = p->gamma; norms[nn].beta = p->beta; norms[nn].gamma_upd = p->gamma_update; norms[nn].beta_upd = p->beta_update;
+			norms[nn].batch = p->desc.batch; norms[nn].nb_group = p->desc.nb_group; norms[nn].set_off = p->desc.set_off;
+			norms[nn].reduce = dp ? 0 : 1;
+			nn++;
+			net->in_update_plan[k] = 1;
+		}
+	}
+	if (nc + nn >= 2) CB_CHECK(cb200_update_plan_create(&net->update_plan, net->dtype, descs, ws, nc, norms, nn));
+	else memset(net->in_update_plan, 0, sizeof(net->in_update_plan));
+	net->update_plan_sig = sig;
+}
+
 static void apply_updates(network *net)
 {
-	int k;
+	int k, planned = 0;
 	if (net->wgrad_stream != NULL) CB_CHECK(cb200_stream_wait(NULL, net->wgrad_stream));   /* all weight gradients are in */
 	if (net->dp_world > 1) {
 		/* a network without conv / dense layers below its norm layers has no trigger layer: exchange the head now */
@@ -553,10 +608,19 @@ static void apply_updates(network *net)
 		CB_CHECK(cb200_dp_join(NULL));
 	}
 	perf_mark(net, 2, 0);
+	/* every eligible conv layer and every group-norm layer in three launches (update_plan.cu); a perf_eval sample keeps
+	 * the layer-by-layer calls so that every kernel lands between its own layer's events */
+	if (!net->perf_sample && update_plan_enabled()) {
+		update_plan_refresh(net);
+		if (net->update_plan != NULL) {
+			CB_CHECK(cb200_update_plan_run(net->update_plan, net->hyper_dev, NULL));
+			planned = 1;
+		}
+	}
 	for (k = 0; k < net->nb_layers; k++) {
 		layer *l = net->net_layers[k];
 		if (k > 0) perf_mark(net, 2, k);
-		if (l->frozen) continue;
+		if (l->frozen || (planned && net->in_update_plan[k])) continue;
 		if (l->type == CONV) {
 			conv_param *p = (conv_param *)l->param;
 			CB_CHECK(cb200_conv_update(&p->desc, &p->w, net->hyper_dev, 0, NULL));

@@ -259,6 +259,23 @@ int cb200_conv_backward_weights_ex(const cb200_conv_desc* d, const cb200_conv_we
 int cb200_conv_update(const cb200_conv_desc* d, const cb200_conv_weights* w, const float* hyper,
                       int is_pivot, void* stream);
 
+/* ---- the optimizer sweep of a whole network in three launches (update_plan.cu): every conv layer's
+ * cb200_conv_update and every group-norm layer's cb200_norm_reduce_update / cb200_norm_update, bit-identical results.
+ * A plan captures the device pointers of the layers it is given: rebuild it when they change (or when a layer is frozen).
+ * Layers cb200_update_plan_accepts() refuses (first layer on patch rows, filters whose FP32 row pair exceeds 96 KB of
+ * shared memory) and dense layers keep their own cb200_conv_update / cb200_dense_update call. */
+typedef struct {
+	const float* d_gamma; const float* d_beta;   /* [batch][nb_group] per-sample gradients (reduce = 1) */
+	float* gsum;                                 /* [2][nb_group]: written when reduce = 1, read (all-reduced sums) when 0 */
+	float* gamma; float* beta; float* gamma_upd; float* beta_upd;
+	int batch, nb_group, set_off, reduce;
+} cb200_norm_update_ref;
+int cb200_update_plan_accepts(const cb200_conv_desc* d);
+int cb200_update_plan_create(void** plan, int dtype, const cb200_conv_desc* const* conv_desc, const cb200_conv_weights* const* conv_w,
+                             int n_conv, const cb200_norm_update_ref* norms, int n_norm);
+int cb200_update_plan_run(const void* plan, const float* hyper, void* stream);
+int cb200_update_plan_destroy(void* plan);
+
 /* ------------------------------------------------------------------ dense */
 /* A dense layer runs through the convolution entry points above with a descriptor whose filter covers
  * the whole input map (f_h = in_h, f_w = in_w, no padding, 1x1 output): the reference's flatten order
@@ -353,6 +370,14 @@ int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* p
                              const uint8_t* pool_map, void* dx, const float* gamma, const float* mean,
                              const float* var, float* d_gamma, float* d_beta, const cb200_activ* prev_activ,
                              float* dx_colsum, void* workspace, void* stream);
+/* The same with the pool layer's OUTPUT and beta at hand: the backward reductions sum(d), sum(d*x) then read the pooled
+ * delta and the pooled output only (x = (y - shift) / scale at the selected position) instead of the input-sized
+ * tensor, its map and the pooled delta; groups where that inversion is ill-conditioned (|gamma| < 1e-4 or
+ * |beta| > 16 |gamma|) and dead samples keep the gather from x.  pooled == NULL or beta == NULL: as above. */
+int cb200_norm_pool_backward_ex(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, const void* d_pooled,
+                                const uint8_t* pool_map, void* dx, const float* gamma, const float* mean,
+                                const float* var, float* d_gamma, float* d_beta, const cb200_activ* prev_activ,
+                                float* dx_colsum, void* workspace, const void* pooled, const float* beta, void* stream);
 
 /* ------------------------------------------------------------------ local response normalisation */
 typedef struct {

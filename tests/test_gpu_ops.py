@@ -374,6 +374,29 @@ def test_group_norm_max_pool_fused_equals_unfused(cabi, cfg, dtype_name):
         assert rel_err(b, a) < 1e-5
     assert rel_err(dx2, dx1) < (1e-5 if dtype_name == "FP32" else tol)
     assert rel_err(cs2, cs1) < (1e-4 if dtype_name == "FP32" else tol)
+    # backward reductions from the pooled delta and the pooled OUTPUT (cb200_norm_pool_backward_ex: x = (y - shift) / scale
+    # at the selected position, one rounding of y to the storage type instead of one of x): same d_gamma / d_beta / dx
+    dx3 = cabi.download_act(n2.backward_pool(xb, dpb, p2, pa, from_pooled_output=True), dtype, B, C, S, S)
+    st3 = n2.stats()
+    for a, b in zip(st1, st3):
+        assert rel_err(b, a) < (1e-5 if dtype_name == "FP32" else tol)
+    assert rel_err(dx3, dx1) < (1e-5 if dtype_name == "FP32" else tol)
+    assert rel_err(n2.colsum.to_numpy(np.float32, (C,)), cs1) < (1e-4 if dtype_name == "FP32" else tol)
+    # ... groups where that inversion is ill-conditioned (tiny gamma, |beta| >> |gamma|) keep the gather from x
+    g_bad, b_bad = gamma.copy(), beta.copy()
+    g_bad[0] = 3e-5
+    b_bad[-1] = 40.0 * abs(g_bad[-1])
+    outs = []
+    for from_y in (False, True):
+        n4 = cabi.NormLayer(dtype, B, C, S, S, gs, set_off, length)
+        n4.set_params(g_bad, b_bad)
+        p4 = cabi.PoolLayer(dtype, B, C, S, S, 2, 2, 0, cabi.POOL_MAX, length=length)
+        n4.forward_pool(xb, p4)
+        dx4 = cabi.download_act(n4.backward_pool(xb, dpb, p4, pa, from_pooled_output=from_y), dtype, B, C, S, S)
+        outs.append((dx4, n4.stats()))
+    assert rel_err(outs[1][0], outs[0][0]) < (1e-5 if dtype_name == "FP32" else tol)
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert rel_err(b, a) < (1e-5 if dtype_name == "FP32" else tol)
     # and against the oracle, end to end
     ref_y, mean, var = co.group_norm_forward(x if dtype_name == "FP32" else cabi.download_act(xb, dtype, B, C, S, S), gamma, beta, gs, set_off, length)
     ref_p, ref_m = co.pool_forward(ref_y, B, C, S, S, 2, 2, 0, "MAX")
