@@ -447,7 +447,18 @@ def load_batch(inputs, targets, network=None):
     """inputs: [batch][input_dim+1] FP32 rows in the dataset layout (bias slot last); targets: [batch][out_dim]."""
     x = np.ascontiguousarray(inputs, dtype=np.float32)
     t = np.ascontiguousarray(targets, dtype=np.float32) if targets is not None else None
-    _load().cb_load_batch(_net(network), x.ctypes.data, t.ctypes.data if t is not None else None)
+    L = _load()
+    net = _net(network)
+    dims = (ctypes.c_longlong * 3)()
+    L.cb_net_io_dims.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    L.cb_net_io_dims(net, dims)
+    b = L.cb_net_batch_size(net)
+    if x.size != b * (dims[0] + 1):
+        raise ValueError("load_batch: inputs hold %d values, the network takes %d rows of input_dim + 1 = %d (bias slot last)"
+                         % (x.size, b, dims[0] + 1))
+    if t is not None and dims[1] > 0 and t.size != b * dims[1]:
+        raise ValueError("load_batch: targets hold %d values, the network takes %d rows of %d" % (t.size, b, dims[1]))
+    L.cb_load_batch(net, x.ctypes.data, t.ctypes.data if t is not None else None)
 
 
 def forward_batch(length=None, is_inference=0, network=None):

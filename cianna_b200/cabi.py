@@ -180,6 +180,16 @@ class ConvLayer:
         check(lib().cb200_conv_forward(ctypes.byref(self.d), ctypes.byref(self.w), x_buf.ptr, self.y.ptr, None))
         return self.y
 
+    def forward_stats(self, x_buf, norm):
+        """forward + the following group-norm layer's (sum, sum of squares) from the epilogue (cb200_conv_forward_stats);
+        returns 1 when norm.ws now holds them"""
+        L = lib()
+        L.cb200_conv_forward_stats.argtypes = [ctypes.c_void_p] * 8
+        done = ctypes.c_int(0)
+        check(L.cb200_conv_forward_stats(ctypes.byref(self.d), ctypes.byref(self.w), x_buf.ptr, self.y.ptr, ctypes.byref(norm.d), norm.ws.ptr,
+                                         ctypes.byref(done), None))
+        return done.value
+
     def backward_data(self, dy_buf, prev_act=None, prev_out=None):
         pa = ctypes.byref(prev_act) if prev_act is not None else None
         po = prev_out.ptr if prev_out is not None else None
@@ -273,9 +283,11 @@ class NormLayer:
         self.gamma = DevBuf.from_numpy(np.ascontiguousarray(gamma, np.float32))
         self.beta = DevBuf.from_numpy(np.ascontiguousarray(beta, np.float32))
 
-    def forward(self, x_buf):
-        check(lib().cb200_norm_forward(ctypes.byref(self.d), x_buf.ptr, self.y.ptr, self.gamma.ptr, self.beta.ptr,
-                                       self.mean.ptr, self.var.ptr, self.ws.ptr, None))
+    def forward(self, x_buf, stats_ready=0):
+        L = lib()
+        L.cb200_norm_forward_ex.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int, ctypes.c_void_p]
+        check(L.cb200_norm_forward_ex(ctypes.byref(self.d), x_buf.ptr, self.y.ptr, self.gamma.ptr, self.beta.ptr,
+                                      self.mean.ptr, self.var.ptr, self.ws.ptr, int(stats_ready), None))
         return self.y
 
     def backward(self, x_buf, dy_buf, prev_act=None):
@@ -284,12 +296,12 @@ class NormLayer:
                                         self.var.ptr, self.d_gamma.ptr, self.d_beta.ptr, pa, self.colsum.ptr, self.ws.ptr, None))
         return self.dx
 
-    def forward_pool(self, x_buf, pool):
+    def forward_pool(self, x_buf, pool, stats_ready=0):
         """fused group-norm + 2x2 max-pool: writes pool.y / pool.map only"""
         L = lib()
-        L.cb200_norm_pool_forward.argtypes = [ctypes.c_void_p] * 11
-        check(L.cb200_norm_pool_forward(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, pool.y.ptr, pool.map.ptr, self.gamma.ptr,
-                                        self.beta.ptr, self.mean.ptr, self.var.ptr, self.ws.ptr, None))
+        L.cb200_norm_pool_forward_ex.argtypes = [ctypes.c_void_p] * 10 + [ctypes.c_int, ctypes.c_void_p]
+        check(L.cb200_norm_pool_forward_ex(ctypes.byref(self.d), ctypes.byref(pool.d), x_buf.ptr, pool.y.ptr, pool.map.ptr, self.gamma.ptr,
+                                           self.beta.ptr, self.mean.ptr, self.var.ptr, self.ws.ptr, int(stats_ready), None))
         return pool.y
 
     def backward_pool(self, x_buf, dpool_buf, pool, prev_act=None, from_pooled_output=False):

@@ -14,7 +14,9 @@ int conv_colsum(int dtype, const void* dy, float* out, long long P, int c, cudaS
 bool conv_tc_fwd_supported(const cb200_conv_desc*);
 bool conv_tc_dgrad_supported(const cb200_conv_desc*);
 bool conv_tc_wgrad_supported(const cb200_conv_desc*);
-int conv_forward_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t);
+extern int g_gn_epilogue_mode;
+int conv_forward_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t,
+                    const cb200_norm_desc* gn = nullptr, void* gn_ws = nullptr, int* gn_fused = nullptr);
 int conv_dgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, const cb200_activ*, const void*, cudaStream_t);
 int conv_wgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
 // first layer straight from the dataset batch, patch rows built in shared memory (conv_first.cu)
@@ -356,8 +358,17 @@ int cb200_dense_prepare_weights(const cb200_conv_desc* d, const cb200_conv_weigh
 	return prepare_weights_impl(d, w, 1, (size_t)d->out_c + 1, s);
 }
 
+void cb200_set_gn_epilogue_stats(int mode) { g_gn_epilogue_mode = mode < 0 ? -1 : (mode > 2 ? 2 : mode); }
+
 int cb200_conv_forward(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, void* y, void* s) {
+	return cb200_conv_forward_stats(d_in, w, x, y, nullptr, nullptr, nullptr, s);
+}
+
+int cb200_conv_forward_stats(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, void* y,
+                             const cb200_norm_desc* gn, void* gn_workspace, int* stats_done, void* s) {
 	CB_REQUIRE_DEVICE();
+	if (stats_done) *stats_done = 0;
+	if (stats_done == nullptr) { gn = nullptr; gn_workspace = nullptr; }
 	int rc = check_desc(d_in); if (rc) return rc;
 	const cb200_conv_desc eff = effective_desc(d_in);
 	const cb200_conv_desc* d = &eff;
@@ -374,7 +385,7 @@ int cb200_conv_forward(const cb200_conv_desc* d_in, const cb200_conv_weights* w,
 	const bool tc = !g_force_simt && !conv_generic(d) && conv_tc_fwd_supported(d);
 	g_last_conv_impl = tc ? "tcgen05" : "simt";
 	prof_begin(tc ? PROF_CONV_FWD_TC : PROF_CONV_FWD_SIMT, flops, as_stream(s));
-	rc = tc ? conv_forward_tc(d, w, x, y, as_stream(s)) : conv_forward_simt(d, w, x, y, as_stream(s));
+	rc = tc ? conv_forward_tc(d, w, x, y, as_stream(s), gn, gn_workspace, stats_done) : conv_forward_simt(d, w, x, y, as_stream(s));
 	prof_end(as_stream(s));
 	return rc;
 }

@@ -134,7 +134,39 @@ struct IgemmParams {
 	// different lines: the layer-2 forward kernel has its LSU data pipe 73-79 % busy with them,
 	// profiles/r1_first_halo_full_digest.txt) - measured slower there, see halo_plan
 	int tma_out;
+	// group-norm statistics of the layer's output, accumulated by the forward epilogue (GN variant of epilogue_loop):
+	// FP64 sums [N][gn_groups][2] = (sum y, sum y^2) per (sample, group of gn_gs output channels) of the values AS STORED
+	// (rounded to the 16-bit type) - what norm_stats_kernel would read back from HBM.  gn_gs is a multiple of 8.
+	double* gn_ws;
+	int gn_gs, gn_groups;
+	// every CTA takes a CONTIGUOUS run of tiles instead of every gridDim.x-th one (set with gn_ws: a warp then stays on one
+	// sample for many tiles and hands its sums to memory once per sample, not once per tile)
+	int contig;
 };
+
+// the tiles of this CTA: first, first + step, ... (count of them).  Strided: blockIdx.x, + gridDim.x, ...; contiguous: a
+// run of consecutive tiles (pair / cluster order: consecutive PAIRS, this CTA's tile of each).  Same count either way.
+struct TileRun { int first, step, count; };
+__device__ __forceinline__ TileRun tile_run(const IgemmParams& p) {
+	TileRun r;
+	if (!p.contig) {
+		r.first = blockIdx.x; r.step = gridDim.x;
+		r.count = r.first < p.num_tiles ? (p.num_tiles - r.first + r.step - 1) / r.step : 0;
+	} else if (p.cluster) {
+		const int nc = gridDim.x >> 1, c = blockIdx.x >> 1, np = p.num_tiles >> 1;
+		const int q = np / nc, rem = np - q * nc;
+		r.count = q + (c < rem ? 1 : 0);
+		r.first = 2 * (c * q + (c < rem ? c : rem)) + (int)(blockIdx.x & 1);
+		r.step = 2;
+	} else {
+		const int nc = gridDim.x, c = blockIdx.x;
+		const int q = p.num_tiles / nc, rem = p.num_tiles - q * nc;
+		r.count = q + (c < rem ? 1 : 0);
+		r.first = c * q + (c < rem ? c : rem);
+		r.step = 1;
+	}
+	return r;
+}
 
 // tile index -> (M tile, N tile).  Cluster mode enumerates pairs: tile = 2*pair + rank, so that with an even grid the
 // two CTAs of a cluster always hold the two tiles of one pair (a pair past the last M tile gets a dummy, all-OOB tile).
@@ -149,10 +181,58 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int&
 // tiles ahead.  tcgen05.ld -> bias + activation (forward) or the previous layer's derivative (dgrad) -> cast -> store.
 // PAIR (cta_group::2 kernels): only the leader CTA's MMA warp waits for drained accumulators, so the epilogue warps of
 // both CTAs arrive on the LEADER's barriers (tempty0 is then a shared::cluster address).
-template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2, bool PAIR = false, bool TMA_OUT = false>
+// ---- group-norm statistics in the epilogue (GN = true) ----
+// A thread owns one pixel row of the tile; per 32-column chunk it sums y and y^2 of the values it has just rounded for
+// the store, per group of gn_gs channels (NV = 2 * max(1, 32 / gs) sums: 8 / 4 / 2 for gs = 8 / 16 / >= 32).  A butterfly
+// over the low lane bits then leaves every lane with ONE of the NV sums, added over the lanes of its sample (the 32 rows
+// of a warp are min(32, tw * th) consecutive pixels of each of one or more samples), and the lane adds it to a register
+// that lives across tiles - one per chunk.  Only when the warp moves to other samples or output channels (and at the
+// end) do the registers go to memory, as FP64 atomics: with contiguous tile runs that is a few times per CTA.
+// Returns the lane's sum of value index bitrev(lane & (NV - 1)): even index = sum y, odd = sum y^2 of group index >> 1.
+__device__ __forceinline__ float gn_butterfly(float (&s)[8], int nv, int seg, int lane) {
+	if (nv == 8) {
+		const bool up = lane & 1;
+#pragma unroll
+		for (int i = 0; i < 4; i++) { const float send = up ? s[i] : s[i + 4], keep = up ? s[i + 4] : s[i]; s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1); }
+	}
+	if (nv >= 4) {
+		const int o = nv == 8 ? 2 : 1;
+		const bool up = lane & o;
+#pragma unroll
+		for (int i = 0; i < 2; i++) { const float send = up ? s[i] : s[i + 2], keep = up ? s[i + 2] : s[i]; s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o); }
+	}
+	{
+		const int o = nv >> 1;
+		const bool up = lane & o;
+		const float send = up ? s[0] : s[1], keep = up ? s[1] : s[0];
+		s[0] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+	}
+	float v = s[0];
+	for (int o = nv; o < seg; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+template <typename T> __device__ __forceinline__ uint4 pack8(const float (&in)[8]);
+template <> __device__ __forceinline__ uint4 pack8<__half>(const float (&in)[8]) {
+	uint4 r;
+	__half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+	for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(in[2 * i], in[2 * i + 1]);
+	return r;
+}
+template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&in)[8]) {
+	uint4 r;
+	__nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+	for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+	return r;
+}
+
+template <typename T, int BN, int ACC_STAGES, int NGROUPS = 2, bool PAIR = false, bool TMA_OUT = false, bool GN = false>
 __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               float* bias_rows, int warp, int lane, int first_warp,
-                                              const CUtensorMap* tmap_out = nullptr, uint32_t stg = 0, uint8_t* stg_ptr = nullptr) {
+                                              const CUtensorMap* tmap_out = nullptr, uint32_t stg = 0, uint8_t* stg_ptr = nullptr,
+                                              float* gn_smem = nullptr /* GN: [BN / 32][NGROUPS * 128] floats */) {
 	static_assert(NGROUPS <= ACC_STAGES, "an accumulator stage belongs to one epilogue group at a time");
 	const int ew = warp - first_warp;                // 0..7
 	const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
@@ -172,14 +252,47 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	// 0 <= leak <= 1, sat >= 0: z <= 0 ? z*leak : (z > sat ? hi : z) == min(max(z, z*leak), hi) value for value
 	const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
 	float* bs = bias_rows + grp * 256;
+	// group-norm statistics (GN): one running sum per lane and 32-column chunk, see gn_butterfly.  They live in shared
+	// memory, one private column per thread (conflict-free), so that the chunk loop can stay rolled: fully unrolled for
+	// register accumulators, the epilogue of a 256-column tile is ~80 KB of code that eight warps walk at different places -
+	// measured 2.2 x slower on the 3x3 128 -> 256 layer (instruction fetch), where the rolled loop costs nothing.
+	constexpr int GN_CHUNKS = (BN + 31) / 32, GN_STRIDE = NGROUPS * 128;
+	float* gn_acc = GN ? gn_smem + (ew * 32 + lane) : nullptr;
+	if (GN) {
+#pragma unroll 1
+		for (int i = 0; i < GN_CHUNKS; i++) gn_acc[i * GN_STRIDE] = 0.0f;
+	}
+	int gn_tni = -1, gn_nt = -1;
+	const int gn_gs = GN ? p.gn_gs : 8;
+	const int gn_nv = gn_gs >= 32 ? 2 : (gn_gs == 16 ? 4 : 8);
+	const int gn_seg = tw * th < 32 ? tw * th : 32;
+	auto gn_flush = [&]() {
+		// lane -> (sample, value index): the lanes of a sample whose bits above the value index are zero hold its sums
+		const int vi = gn_nv == 8 ? (((lane & 1) << 2) | (lane & 2) | ((lane >> 2) & 1)) : (gn_nv == 4 ? (((lane & 1) << 1) | ((lane >> 1) & 1)) : (lane & 1));
+		const int pn_l = gn_tni * tn + row / (tw * th);
+		const bool writer = ((lane & (gn_seg - 1)) & ~(gn_nv - 1)) == 0 && pn_l < PN;
+#pragma unroll 1
+		for (int c = 0; c < GN_CHUNKS; c++) {
+			const int g = (gn_nt * BN + c * 32) / gn_gs + (gn_gs < 32 ? (vi >> 1) : 0);
+			const float a = gn_acc[c * GN_STRIDE];
+			if (writer && g < p.gn_groups && a != 0.0f)
+				atomicAdd(p.gn_ws + ((size_t)pn_l * p.gn_groups + g) * 2 + (vi & 1), (double)a);
+			gn_acc[c * GN_STRIDE] = 0.0f;
+		}
+	};
+	const TileRun run = tile_run(p);
 	int it = 0;
-	for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+	for (int tile = run.first; it < run.count; tile += run.step, it++) {
 		if ((it % NGROUPS) != grp) continue;
 		const int acc = it % ACC_STAGES;
 		const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
 		int mt, nt;
 		decode_tile(p, tile, mt, nt);
 		const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
+		if (GN && (tni != gn_tni || nt != gn_nt)) {
+			if (gn_tni >= 0) gn_flush();
+			gn_tni = tni; gn_nt = nt;
+		}
 		const int px = twi * tw + (row % tw);
 		const int py = thi * th + (row / tw) % th;
 		const int pn = tni * tn + row / (tw * th);
@@ -198,6 +311,11 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
 		for (int c0 = 0; c0 < BN; c0 += 32) {
+			float gsum[8];
+			if (GN) {
+#pragma unroll
+				for (int i = 0; i < 8; i++) gsum[i] = 0.0f;
+			}
 			uint32_t r[32];
 			if (BN - c0 >= 32) tmem_ld_32x32(t_row + c0, r);
 			else { uint32_t h[16]; tmem_ld_32x16(t_row + c0, h);
@@ -259,7 +377,16 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 						for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
 					}
 				}
-				if (TMA_OUT) {
+				if (GN) {
+					// round once, store those bits, and sum what was stored
+					Raw8<T> pk;
+					pk.a = pack8<T>(o);
+					*reinterpret_cast<uint4*>(out + pix * n_pad + col) = pk.a;
+					float q[8];
+					unpack8(pk, q);
+#pragma unroll
+					for (int j = 0; j < 8; j++) { gsum[2 * v] += q[j]; gsum[2 * v + 1] = fmaf(q[j], q[j], gsum[2 * v + 1]); }
+				} else if (TMA_OUT) {
 					// staging tile [128 rows][BN channels], 16-byte chunks XOR-swizzled like the TMA map of the output (64B / 128B)
 					const int sw_x = BN == 32 ? ((row >> 1) & 3) : (row & 7);
 					const int chunk = (((c0 >> 3) + v) ^ sw_x) & (BN / 8 - 1);
@@ -268,6 +395,12 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 				store8<T>(out + pix * n_pad + col, o);
 			}
 			__syncwarp();        // reconverge before the next warp-collective tcgen05.ld
+			if (GN) {
+				// 8-column sums -> group sums of this chunk (gs = 8: as they are; 16: pairs; >= 32: the whole chunk)
+				if (gn_gs >= 16) { gsum[0] += gsum[2]; gsum[1] += gsum[3]; gsum[2] = gsum[4] + gsum[6]; gsum[3] = gsum[5] + gsum[7]; }
+				if (gn_gs >= 32) { gsum[0] += gsum[2]; gsum[1] += gsum[3]; }
+				gn_acc[(c0 >> 5) * GN_STRIDE] += gn_butterfly(gsum, gn_nv, gn_seg, lane);
+			}
 		}
 		tc_fence_before();
 		__syncwarp();
@@ -284,6 +417,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		}
 	}
 	if (TMA_OUT && lane == 0) bulk_wait0();
+	if (GN && gn_tni >= 0) gn_flush();
 }
 
 template <int BN, int BK>
@@ -293,7 +427,8 @@ struct IgemmCfg {
 	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
 	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias rows*/;
+	static constexpr int GN_BYTES = ((BN + 31) / 32) * 256 * 4;                 // group-norm sums of the epilogue threads (GN epilogue)
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias rows*/ + GN_BYTES;
 	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;                      // accumulator ring in TMEM (512 columns)
 	// (measured: four groups for BN <= 128 do not help this kernel - its small-N launches are issue-bound, not
 	//  epilogue-latency-bound - and cost registers)
@@ -346,7 +481,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		// ===================== TMA producer =====================
 		if (lane == 0) {
 			int stage = 0; uint32_t phase = 0;
-			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			const TileRun run = tile_run(p);
+			for (int ti = 0, tile = run.first; ti < run.count; ti++, tile += run.step) {
 				int mt, nt;
 				decode_tile(p, tile, mt, nt);
 				const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
@@ -375,9 +511,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 			int acc = 0; uint32_t acc_phase = 0;
 			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
 			const uint32_t idesc = p.idesc;
-			const int num_tiles = p.num_tiles;
 			const bool cluster = p.cluster != 0;
-			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+			const TileRun run = tile_run(p);
+			for (int ti = 0; ti < run.count; ti++) {
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -401,7 +537,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 	} else {
 		// ===================== epilogue warps =====================
 		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-		epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 2);
+		if (p.gn_ws != nullptr)
+			epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS, false, false, true>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 2,
+				nullptr, 0, nullptr, bias_rows + 1024);
+		else
+			epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_rows, warp, lane, 2);
 	}
 
 	tc_fence_before();
@@ -426,7 +566,8 @@ struct PairCfg {
 	static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 	static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
 	static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4096;
+	static constexpr int GN_BYTES = ((BN + 31) / 32) * 256 * 4;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4096 + GN_BYTES;
 	static constexpr int ACC_STAGES = BN <= 128 ? 4 : 2;
 	static constexpr int EPI_GROUPS = 2;
 	static constexpr int THREADS = (2 + 4 * EPI_GROUPS) * 32;
@@ -476,7 +617,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 		if (lane == 0) {
 			int stage = 0; uint32_t phase = 0;
 			const uint32_t lead_full0 = mapa_rank(full_bar(0), 0);
-			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			const TileRun run = tile_run(p);
+			for (int ti = 0, tile = run.first; ti < run.count; ti++, tile += run.step) {
 				int mt, nt;
 				decode_tile(p, tile, mt, nt);
 				const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
@@ -502,8 +644,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 			int acc = 0; uint32_t acc_phase = 0;
 			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
 			const uint32_t idesc = p.idesc;                  // M = 256
-			const int num_tiles = p.num_tiles;
-			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+			const TileRun run = tile_run(p);
+			for (int ti = 0; ti < run.count; ti++) {
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -525,7 +667,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 	} else {
 		// ===================== epilogue warps (both CTAs: their own 128 rows) =====================
 		float* bias_rows = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-		epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS, true>(p, tmem_base, tfull_bar(0), mapa_rank(tempty_bar(0), 0), bias_rows, warp, lane, 2);
+		if (p.gn_ws != nullptr)
+			epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS, true, false, true>(p, tmem_base, tfull_bar(0), mapa_rank(tempty_bar(0), 0), bias_rows, warp, lane, 2,
+				nullptr, 0, nullptr, bias_rows + 1024);
+		else
+			epilogue_loop<T, BN, Cfg::ACC_STAGES, Cfg::EPI_GROUPS, true>(p, tmem_base, tfull_bar(0), mapa_rank(tempty_bar(0), 0), bias_rows, warp, lane, 2);
 	}
 
 	tc_fence_before();
@@ -719,7 +865,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 		// ===================== halo producer: one TMA box per (tile, channel block) =====================
 		if (lane == 0) {
 			int stage = 0; uint32_t phase = 0;
-			for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+			const TileRun run = tile_run(p);
+			for (int ti = 0, tile = run.first; ti < run.count; ti++, tile += run.step) {
 				const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
 				for (int cb = 0; cb < p.kc_blocks; cb++) {
 					mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -753,8 +900,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 			const uint32_t b_tap_step = (uint32_t)(p.kc_blocks * p.b_blk_bytes) >> 4;
 			const uint32_t idesc = p.idesc;
 			const int kc_blocks = p.kc_blocks, a_stages = p.a_stages, a_stage_bytes = p.a_stage_bytes, b_blk_bytes = p.b_blk_bytes;
-			const int num_tiles = p.num_tiles;
-			for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+			const TileRun run = tile_run(p);
+			for (int ti = 0; ti < run.count; ti++) {
 				mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -852,7 +999,7 @@ static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_
 	// unit already carries the halo loads.  (The first-layer kernel, conv_first.cu, gains 9 % from the same idea.)
 	const char* halo_tma = getenv("CB200_HALO_TMA_STORE");
 	p.tma_out = 0;
-	if (halo_tma != nullptr && halo_tma[0] == '1' && p.mode == 0 && n_pad == bn && bn <= 64) {
+	if (halo_tma != nullptr && halo_tma[0] == '1' && p.mode == 0 && n_pad == bn && bn <= 64 && p.gn_ws == nullptr) {
 		const int fixed_out = 1024 + 5120 + HALO_EPI_GROUPS * 128 * bn * 2;
 		if ((HALO_SMEM_MAX - fixed_out - b_bytes) / a_stage >= 3) { p.tma_out = 1; fixed = fixed_out; }
 	}
@@ -865,13 +1012,34 @@ static int halo_plan(int cin_p, int n_pad, int f_h, int f_w, int out_h, int out_
 
 // GEMM over: input tensor `src` with cin_p channels on an (in_h, in_w) grid, weights wmat[rows=n_real][taps][cin_p],
 // output pixel grid (out_h, out_w), tap (0,0) reads input pixel (oy + off_h, ox + off_w).
+// group-norm statistics in the epilogue: group sizes the chunk arithmetic of epilogue_loop<GN> covers, and every lane group
+// of a sample wide enough for the butterfly (gn_butterfly: min(32, tw * th) >= number of sums per 32-column chunk)
+// mode 1 (default): only where the sums are hidden behind the tensor pipe - K loops of at least 16 blocks (3x3 filters on
+// >= 128 channels): measured at batch 128 on the Darknet19 shapes (profiles/r2_gn_epilogue_stats.txt) the epilogue sums
+// cost 9-37 us per launch there against 17-47 us for the statistics pass they replace, while on the 1x1 layers they
+// cost what they save (17-60 us against 17-49 us); mode 2: wherever the arithmetic allows (tests); mode 0: never
+int g_gn_epilogue_mode = -1;
+static bool gn_stats_ok(const IgemmParams& p, int tw, int th, int k_iters) {
+	if (p.gn_ws == nullptr || p.mode != 0) return false;
+	if (g_gn_epilogue_mode < 0) { const char* e = getenv("CB200_GN_EPILOGUE_STATS"); g_gn_epilogue_mode = e != nullptr && e[0] != '\0' ? atoi(e) : 1; }
+	if (g_gn_epilogue_mode == 0 || (g_gn_epilogue_mode == 1 && k_iters < 16)) return false;
+	const int gs = p.gn_gs;
+	if (!(gs == 8 || gs == 16 || (gs >= 32 && gs % 32 == 0))) return false;
+	const int nv = gs >= 32 ? 2 : (gs == 16 ? 4 : 8);
+	const int seg = tw * th < 32 ? tw * th : 32;
+	return seg >= nv;
+}
+
 static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, int batch,
                      const void* wmat, int n_real, int f_h, int f_w, int off_h, int off_w,
-                     int out_h, int out_w, IgemmParams p, cudaStream_t st) {
+                     int out_h, int out_w, IgemmParams p, cudaStream_t st, int* gn_fused = nullptr) {
 	const int bk = pick_bk(cin_p);
 	const int n_pad = round8(n_real);
 	const int bn = pick_bn(n_pad);
 	CUtensorMap ma, mb;
+	if (gn_fused) *gn_fused = 0;
+	static const int diag = getenv("CB200_TILE_DIAG") ? atoi(getenv("CB200_TILE_DIAG")) : 0;   // 1: contiguous tile runs everywhere (measurement only)
+	if (diag & 1) p.contig = 1;
 	if (p.stride < 1) p.stride = 1;
 	if (p.out_s < 1) { p.out_s = 1; p.out_ox = 0; p.out_oy = 0; p.out_W = out_w; p.out_H = out_h; }
 	const int w_taps = p.w_taps > 0 ? p.w_taps : f_h * f_w;
@@ -894,6 +1062,12 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 			ph.kc_blocks = ceil_div(cin_p, bk);
 			ph.n_real = n_real; ph.n_pad = n_pad;
 			ph.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
+			// No epilogue statistics in this kernel (measured, Darknet19 layers 2 / 3 / 5 at batch 128,
+			// profiles/r2_gn_epilogue_stats.txt): its launches are bound by the epilogue's latency chain and by HBM, so sums
+			// in the epilogue are paid in full, and the contiguous tile runs that keep a warp on one sample (strided runs
+			// would mean an FP64 atomic burst every 2-3 tiles) alone cost 70 us of DRAM locality per launch (148 far-apart
+			// streams of 512-byte row pieces: 414 -> 488 us, 222 -> 294 us) - more than half of the 146 / 79 us pass saved.
+			ph.gn_ws = nullptr;
 			g_last_conv_impl = "tcgen05-halo";
 			CUtensorMap mo = mb;
 			if (ph.tma_out) {
@@ -935,6 +1109,11 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	p.kc_blocks = ceil_div(cin_p, bk);
 	p.n_real = n_real; p.n_pad = n_pad;
 	p.idesc = make_idesc_f16(dtype == CB200_BF16, p.cluster == 2 ? 256 : 128, bn, 0, 0);
+	if (gn_stats_ok(p, tw, th, f_h * f_w * p.kc_blocks)) {
+		p.contig = 1;
+		if (cudaMemsetAsync(p.gn_ws, 0, sizeof(double) * 2 * (size_t)batch * p.gn_groups, st) != cudaSuccess) { set_error("cudaMemsetAsync(group-norm sums) failed"); return CB200_ERR_CUDA; }
+		if (gn_fused) *gn_fused = 1;
+	} else p.gn_ws = nullptr;
 	if (p.cluster == 2) {
 		g_last_conv_impl = "tcgen05-pair";
 		if (dtype == CB200_FP16) return launch_igemm_pair<__half, 256, 64>(ma, mb, p, st);
@@ -944,15 +1123,21 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	return dispatch_igemm<__nv_bfloat16>(bn, bk, ma, mb, p, st);
 }
 
-int conv_forward_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, void* y, cudaStream_t st) {
+// gn / gn_ws: the group-norm layer that follows and its FP64 workspace; *gn_fused = 1 when the epilogue has left the
+// layer's (sum, sum of squares) there (cb200_conv_forward_stats), 0 when the caller still has to run the statistics pass
+int conv_forward_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* x, void* y, cudaStream_t st,
+                    const cb200_norm_desc* gn, void* gn_ws, int* gn_fused) {
 	const cb200_conv_desc v = tc_view(d_in), *d = &v;
 	IgemmParams p;
 	memset(&p, 0, sizeof(p));
 	p.mode = 0; p.length = d->length; p.bias_value = d->bias_value; p.bias_w = w->bias_w;
 	p.out = y; p.prev_out = nullptr; p.activ = d->activ;
 	p.stride = d->stride_w;
+	if (gn != nullptr && gn_ws != nullptr && gn->c == d->out_c && gn->batch == d->batch && gn->h == d->out_h && gn->w == d->out_w) {
+		p.gn_ws = (double*)gn_ws; p.gn_gs = gn->group_size; p.gn_groups = gn->nb_group;
+	}
 	return run_igemm(d->dtype, x, round8(d->in_c), d->in_h, d->in_w, d->batch, w->w_fwd, d->out_c,
-	                 d->f_h, d->f_w, -d->pad_h, -d->pad_w, d->out_h, d->out_w, p, st);
+	                 d->f_h, d->f_w, -d->pad_h, -d->pad_w, d->out_h, d->out_w, p, st, gn_fused);
 }
 
 int conv_dgrad_tc(const cb200_conv_desc* d_in, const cb200_conv_weights* w, const void* dy, void* dx,

@@ -20,14 +20,15 @@ struct NormGeom {
 constexpr int NORM_THREADS = 256;
 // pixels handled by one block: sized on the host so that every launch has several waves of blocks
 // (deep layers have few pixels per sample) while a thread still streams a few 128-bit packets
+static int g_norm_want_blocks = 8, g_norm_ppb_max = 1024;     // cb200_norm_set_tuning (measurement hook)
 static int norm_pix_per_block(int hw, int batch, int cv) {
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
-	long long want_blocks = (long long)g_num_sms * 8;
+	long long want_blocks = (long long)g_num_sms * g_norm_want_blocks;
 	long long ppb = ((long long)hw * batch + want_blocks - 1) / want_blocks;
 	const int min_ppb = lanes_p * 4;
 	if (ppb < min_ppb) ppb = min_ppb;
-	if (ppb > 1024) ppb = 1024;
+	if (ppb > g_norm_ppb_max) ppb = g_norm_ppb_max;
 	return (int)ppb;
 }
 
@@ -826,6 +827,11 @@ extern "C" {
 // FP64 sums [batch][nb_group][2]
 size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d) { return sizeof(double) * 2 * (size_t)d->batch * d->nb_group; }
 
+void cb200_norm_set_tuning(int want_blocks_per_sm, int ppb_max) {
+	if (want_blocks_per_sm > 0) g_norm_want_blocks = want_blocks_per_sm;
+	if (ppb_max > 0) g_norm_ppb_max = ppb_max;
+}
+
 void cb200_norm_set_pipeline(int on, int chunk_kb, int blocks_per_sm) {
 	norm_pipeline_on();                    // environment defaults first
 	g_norm_pipeline = on != 0;
@@ -835,16 +841,21 @@ void cb200_norm_set_pipeline(int on, int chunk_kb, int blocks_per_sm) {
 
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const float* gamma, const float* beta,
                        float* mean, float* var, void* workspace, void* s) {
+	return cb200_norm_forward_ex(d, x, y, gamma, beta, mean, var, workspace, 0, s);
+}
+
+int cb200_norm_forward_ex(const cb200_norm_desc* d, const void* x, void* y, const float* gamma, const float* beta,
+                          float* mean, float* var, void* workspace, int stats_ready, void* s) {
 	CB_REQUIRE_DEVICE();
 	NormGeom g;
 	int rc = fill_geom(d, g); if (rc) return rc;
 	CB_ARG(workspace != nullptr);
 	cudaStream_t st = as_stream(s);
 	double* ws = (double*)workspace;
-	// algorithmic bytes: read x (stats) + read x + write y = 3 passes over the real elements
-	prof_begin(PROF_NORM, 3.0 * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
-	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
-	if (norm_pipeline_on()) {
+	// algorithmic bytes: read x (stats, unless the producing convolution has left them in the workspace) + read x + write y
+	prof_begin(PROF_NORM, (stats_ready ? 2.0 : 3.0) * g.batch * g.hw * (double)g.c * cb200_dtype_size(d->dtype), st);
+	if (!stats_ready) CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(d), st));
+	if (norm_pipeline_on() && !stats_ready) {
 		const int k = chunk_samples(g.batch, (double)g.hw * g.cp * cb200_dtype_size(d->dtype));
 		g.ppb = chunk_ppb(g.hw, k, g.cp >> 3);
 		const int nbx = ceil_div(g.hw, g.ppb);
@@ -859,8 +870,10 @@ int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y, const f
 	}
 	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
 	size_t smem = sizeof(float) * 2 * g.nb_group;
-	CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, smem, st>>>((const T*)x, nullptr, ws, g)));
-	CB_LAUNCH_CHECK();
+	if (!stats_ready) {
+		CB_DISPATCH_DTYPE(d->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, smem, st>>>((const T*)x, nullptr, ws, g)));
+		CB_LAUNCH_CHECK();
+	}
 	// finalize folded into the apply blocks (each turns its sample's FP64 sums into mean / var in shared memory): one tiny
 	// launch less on the critical path per layer and pass
 	unsigned agrid;
@@ -932,6 +945,11 @@ static int fill_fused(const cb200_norm_desc* nd, const cb200_pool_desc* pd, Fuse
 
 int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, void* pooled, uint8_t* pool_map,
                             const float* gamma, const float* beta, float* mean, float* var, void* workspace, void* s) {
+	return cb200_norm_pool_forward_ex(nd, pd, x, pooled, pool_map, gamma, beta, mean, var, workspace, 0, s);
+}
+
+int cb200_norm_pool_forward_ex(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, void* pooled, uint8_t* pool_map,
+                               const float* gamma, const float* beta, float* mean, float* var, void* workspace, int stats_ready, void* s) {
 	CB_REQUIRE_DEVICE();
 	FusedGeom f;
 	int rc = fill_fused(nd, pd, f); if (rc) return rc;
@@ -940,10 +958,11 @@ int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 	cudaStream_t st = as_stream(s);
 	double* ws = (double*)workspace;
 	const double es = (double)cb200_dtype_size(nd->dtype), E = (double)g.batch * g.hw * g.c;
-	// algorithmic bytes: read x (statistics) + read x + write pooled values and their 1-byte window index
-	prof_begin(PROF_NORM, 2.0 * E * es + 0.25 * E * (es + 1.0), st);
-	CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
-	if (norm_pipeline_on()) {
+	// algorithmic bytes: read x (statistics, unless the producing convolution has left them in the workspace) + read x +
+	// write pooled values and their 1-byte window index
+	prof_begin(PROF_NORM, (stats_ready ? 1.0 : 2.0) * E * es + 0.25 * E * (es + 1.0), st);
+	if (!stats_ready) CB_CUDA(cudaMemsetAsync(ws, 0, cb200_norm_workspace_bytes(nd), st));
+	if (norm_pipeline_on() && !stats_ready) {
 		const int k = chunk_samples(g.batch, (double)g.hw * g.cp * es);
 		f.n.ppb = chunk_ppb(g.hw, k, g.cp >> 3);
 		f.ppb_out = chunk_ppb(f.out_hw, k, g.cp >> 3);
@@ -957,8 +976,10 @@ int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 		return CB200_OK;
 	}
 	dim3 grid((unsigned)ceil_div(g.hw, g.ppb), (unsigned)g.batch);
-	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>((const T*)x, nullptr, ws, g)));
-	CB_LAUNCH_CHECK();
+	if (!stats_ready) {
+		CB_DISPATCH_DTYPE(nd->dtype, T, (norm_stats_kernel<T, false><<<grid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>((const T*)x, nullptr, ws, g)));
+		CB_LAUNCH_CHECK();
+	}
 	unsigned agrid;
 	const ChunkGeom cg = apply_only_geom(g.batch, ceil_div(f.out_hw, f.ppb_out), agrid);
 	CB_DISPATCH_DTYPE(nd->dtype, T, (norm_pool_fwd_chunk_kernel<T><<<agrid, NORM_THREADS, sizeof(float) * 2 * g.nb_group, st>>>(

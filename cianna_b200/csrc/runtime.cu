@@ -1,4 +1,4 @@
-// runtime.cu - device bring-up, memory/stream/event/graph plumbing and layout import/export
+// runtime.cu - device bring-up, memory/stream/event plumbing and layout import/export
 // of the B200-native CIANNA core.  Replaces src/cuda/cuda_main.cu of the reference
 // (init_cuda :922-1067, typed alloc/copy helpers :108-379, event timers :533-588).
 #include <stdarg.h>
@@ -171,27 +171,13 @@ int cb200_stream_wait(void* s, void* on) {
 int cb200_event_create(void** ev) { CB_REQUIRE_DEVICE(); cudaEvent_t e; CB_CUDA(cudaEventCreate(&e)); *ev = e; return CB200_OK; }
 int cb200_event_destroy(void* ev) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return CB200_OK; }
 int cb200_event_record(void* ev, void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventRecord((cudaEvent_t)ev, as_stream(s))); return CB200_OK; }
+int cb200_event_sync(void* ev) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventSynchronize((cudaEvent_t)ev)); return CB200_OK; }
 int cb200_event_elapsed_ms(void* a, void* b, float* ms) {
 	CB_REQUIRE_DEVICE();
 	CB_CUDA(cudaEventSynchronize((cudaEvent_t)b));
 	CB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
 	return CB200_OK;
 }
-int cb200_graph_begin(void* s) {
-	CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamBeginCapture(as_stream(s), cudaStreamCaptureModeThreadLocal)); return CB200_OK;
-}
-int cb200_graph_end(void* s, void** exec) {
-	CB_REQUIRE_DEVICE();
-	cudaGraph_t g;
-	CB_CUDA(cudaStreamEndCapture(as_stream(s), &g));
-	cudaGraphExec_t ge;
-	CB_CUDA(cudaGraphInstantiate(&ge, g, 0));
-	CB_CUDA(cudaGraphDestroy(g));
-	*exec = ge;
-	return CB200_OK;
-}
-int cb200_graph_launch(void* exec, void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, as_stream(s))); g_launches++; return CB200_OK; }
-int cb200_graph_destroy(void* exec) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)exec)); return CB200_OK; }
 
 }  // extern "C"
 

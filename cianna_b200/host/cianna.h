@@ -110,6 +110,9 @@ typedef struct norm_param {
 	/* set when the next layer is a 2x2 max-pool: the pair runs as cb200_norm_pool_forward / _backward, this layer's
 	 * full-resolution output and delta are never materialised (layer->output == layer->delta_o == NULL) */
 	layer *fused_pool;
+	/* one-shot: the convolution in front has just left this pass's (sum, sum of squares) in `workspace`
+	 * (cb200_conv_forward_stats), the forward call skips its statistics launch */
+	int stats_ready;
 } norm_param;
 
 /* local response normalisation across channels (src/structs.h lrn_param, src/lrn_layer.c) */

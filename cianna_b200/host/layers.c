@@ -140,7 +140,20 @@ static void forward_conv_layer(layer *current)
 	conv_param *p = (conv_param *)current->param;
 	if (net->length == 0) return;
 	p->desc.length = net->length;
-	CB_CHECK(cb200_conv_forward(&p->desc, &p->w, layer_input(current), current->output, NULL));
+	{
+		/* a group-norm layer next: its statistics come out of this layer's epilogue when the kernel can (no dropout in
+		 * between - it would change the tensor the statistics are about) */
+		layer *next = current->index + 1 < net->nb_layers ? net->net_layers[current->index + 1] : NULL;
+		if (next != NULL && next->type == NORM && next->previous == current && !drop_on(current)
+			&& current->activation_type != SOFTMAX && current->activation_type != YOLO) {
+			norm_param *np = (norm_param *)next->param;
+			int done = 0;
+			np->desc.length = net->length;
+			CB_CHECK(cb200_conv_forward_stats(&p->desc, &p->w, layer_input(current), current->output, &np->desc, np->workspace, &done, NULL));
+			np->stats_ready = done;
+		} else
+			CB_CHECK(cb200_conv_forward(&p->desc, &p->w, layer_input(current), current->output, NULL));
+	}
 	cb_dropout_forward(current);
 	if (current->activation_type == SOFTMAX)
 		CB_CHECK(cb200_softmax(current->output, net->dtype, net->batch_size, net->length, current->out_c, current->out_h, current->out_w, NULL));
@@ -448,8 +461,9 @@ static void forward_pool_layer(layer *current)
 		layer *norm = current->previous;
 		norm_param *np = (norm_param *)norm->param;
 		np->desc.length = net->length;
-		CB_CHECK(cb200_norm_pool_forward(&np->desc, &p->desc, norm->previous->output, current->output, p->pool_map,
-			np->gamma, np->beta, np->mean, np->var, np->workspace, NULL));
+		CB_CHECK(cb200_norm_pool_forward_ex(&np->desc, &p->desc, norm->previous->output, current->output, p->pool_map,
+			np->gamma, np->beta, np->mean, np->var, np->workspace, np->stats_ready, NULL));
+		np->stats_ready = 0;
 	} else
 		CB_CHECK(cb200_pool_forward(&p->desc, layer_input(current), current->output, p->pool_map, NULL));
 	cb_dropout_forward(current);
@@ -609,7 +623,9 @@ static void forward_norm_layer(layer *current)
 	if (net->length == 0) return;
 	p->desc.length = net->length;
 	if (p->fused_pool != NULL) return;      /* evaluated by the following pool layer (cb200_norm_pool_forward) */
-	CB_CHECK(cb200_norm_forward(&p->desc, current->previous->output, current->output, p->gamma, p->beta, p->mean, p->var, p->workspace, NULL));
+	CB_CHECK(cb200_norm_forward_ex(&p->desc, current->previous->output, current->output, p->gamma, p->beta, p->mean, p->var, p->workspace,
+		p->stats_ready, NULL));
+	p->stats_ready = 0;
 }
 
 static void backward_norm_layer(layer *current)

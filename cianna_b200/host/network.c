@@ -975,6 +975,12 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 	int c, h, w;
 	size_t out_elems;
 	float *out_dev = NULL, *out_host = NULL;
+	/* Results travel through TWO sets of pinned host buffers: the host-side half of step s (loss sums, confusion matrix,
+	 * fwd_res records - upstream formats every value with fprintf) runs while the device already computes step s + 1
+	 * (upstream: compute, blocking copies, then the host loop, src/auxil.c:1228-1400). */
+	float *loss_h[2] = {NULL, NULL}, *out_h[2] = {NULL, NULL}, *parts_h[2] = {NULL, NULL}, *monitor_h[2] = {NULL, NULL};
+	int *am_h[2] = {NULL, NULL}, slot_len[2] = {0, 0}, pending = -1, step = 0;
+	void *slot_ev[2] = {NULL, NULL};
 	FILE *f_save = NULL;
 	char name[200];
 	struct stat st;
@@ -983,14 +989,22 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 	double part_err[6] = {0, 0, 0, 0, 0, 0}, sum_IoU = 0.0, sum_obj = 0.0;
 	long nb_IoU = 0, nb_good_IoU = 0;
 	/* confusion matrix (src/auxil.c:1137-1146, 1384-1426): classification read-out, i.e. one output per class */
-	int o = net->output_dim, *am_dev = NULL, *am_host = NULL;
+	int o = net->output_dim, *am_dev = NULL;
 	double *mat = NULL;
 
 	last_layer_dims(net, &c, &h, &w);
 	if (confusion_matrix > 0 && !net->no_error && repeat <= 1 && yolo == NULL && o > 0 && c * h * w == o) {
 		mat = (double *)calloc((size_t)o * o, sizeof(double));
 		CB_CHECK(cb200_malloc((void **)&am_dev, 2 * (size_t)net->batch_size * sizeof(int)));
-		CB_CHECK(cb200_host_alloc((void **)&am_host, 2 * (size_t)net->batch_size * sizeof(int)));
+		for (k = 0; k < 2; k++) CB_CHECK(cb200_host_alloc((void **)&am_h[k], 2 * (size_t)net->batch_size * sizeof(int)));
+	}
+	for (k = 0; k < 2; k++) {
+		CB_CHECK(cb200_event_create(&slot_ev[k]));
+		CB_CHECK(cb200_host_alloc((void **)&loss_h[k], (size_t)net->batch_size * sizeof(float)));
+		if (yolo != NULL) {
+			CB_CHECK(cb200_host_alloc((void **)&parts_h[k], (size_t)net->batch_size * 6 * sizeof(float)));
+			CB_CHECK(cb200_host_alloc((void **)&monitor_h[k], (size_t)net->batch_size * h * w * yolo->nb_box * 2 * sizeof(float)));
+		}
 	}
 	out_elems = last->type == DENSE ? (size_t)net->batch_size * (c + 1) : (size_t)net->batch_size * c * h * w;
 	if (saving > 0) {
@@ -999,7 +1013,7 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		f_save = fopen(name, saving == 1 ? "w+" : "wb+");
 		if (f_save == NULL) { printf("ERROR: cannot open %s\n", name); exit(EXIT_FAILURE); }
 		CB_CHECK(cb200_malloc((void **)&out_dev, out_elems * sizeof(float)));
-		CB_CHECK(cb200_host_alloc((void **)&out_host, out_elems * sizeof(float)));
+		for (k = 0; k < 2; k++) CB_CHECK(cb200_host_alloc((void **)&out_h[k], out_elems * sizeof(float)));
 	}
 	if (!net->dynamic_load && data.input_device == NULL) {
 		/* `data` is a by-value copy (upstream's signature): make the device-resident copies on the network's own object so
@@ -1028,46 +1042,61 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 		}
 		/* MC-dropout: `repeat` forward passes per batch, restarted from the first layer that has dropout (everything
 		 * below it is deterministic), every pass saved and counted in the loss (src/auxil.c:1216-1226) */
-		for (r = 0; r < repeat; r++) {
+		for (r = 0; r <= repeat; r++) {
+		/* ---- host half of the step enqueued one turn ago (its results are in slot `pending`), while the device works on
+		 * the step just enqueued; the turn r == repeat of the last batch only drains */
+		const int drain_only = r == repeat;
+		int slot = step & 1;
+		if (drain_only && j + 1 < data.nb_batch) break;
+		if (!drain_only) {
 		for (k = repeat_start; k < net->nb_layers; k++) {
 			if (repeat_start == 0 && net->net_layers[k]->dropout_rate > 0.01f) repeat_start = k;
 			net->net_layers[k]->forward(net->net_layers[k]);
 		}
 		if (!net->no_error) {
 			output_error(net, tgt);
-			CB_CHECK(cb200_d2h(net->loss_host, net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
+			CB_CHECK(cb200_d2h(loss_h[slot], net->loss_dev, (size_t)net->batch_size * sizeof(float), NULL));
 			if (yolo != NULL) {
-				CB_CHECK(cb200_d2h(yolo->parts_host, yolo->parts_dev, (size_t)net->batch_size * 6 * sizeof(float), NULL));
-				CB_CHECK(cb200_d2h(yolo->monitor_host, yolo->monitor_dev, (size_t)net->batch_size * h * w * yolo->nb_box * 2 * sizeof(float), NULL));
+				CB_CHECK(cb200_d2h(parts_h[slot], yolo->parts_dev, (size_t)net->batch_size * 6 * sizeof(float), NULL));
+				CB_CHECK(cb200_d2h(monitor_h[slot], yolo->monitor_dev, (size_t)net->batch_size * h * w * yolo->nb_box * 2 * sizeof(float), NULL));
 			}
 		}
 		if (mat != NULL) {
 			CB_CHECK(cb200_output_argmax(am_dev, am_dev + net->batch_size, last->output, tgt, net->dtype, net->batch_size, net->length, c, h, w, NULL));
-			CB_CHECK(cb200_d2h(am_host, am_dev, 2 * (size_t)net->batch_size * sizeof(int), NULL));
+			CB_CHECK(cb200_d2h(am_h[slot], am_dev, 2 * (size_t)net->batch_size * sizeof(int), NULL));
 		}
 		if (saving > 0) {
 			if (yolo != NULL && net->y_param->raw_output == 0) CB_CHECK(cb200_yolo_export_boxes(&yolo->desc, out_dev, last->output, NULL));
 			else if (last->type == DENSE) CB_CHECK(cb200_export_dense(out_dev, last->output, net->dtype, net->batch_size, c, 0.0f, NULL));
 			else CB_CHECK(cb200_export_cbhw(out_dev, last->output, net->dtype, net->batch_size, c, h, w, NULL));
-			CB_CHECK(cb200_d2h(out_host, out_dev, out_elems * sizeof(float), NULL));
+			CB_CHECK(cb200_d2h(out_h[slot], out_dev, out_elems * sizeof(float), NULL));
 		}
-		CB_CHECK(cb200_stream_sync(NULL));
-		if (!net->no_error) for (k = 0; k < net->length; k++) total_error += net->loss_host[k];
+		CB_CHECK(cb200_event_record(slot_ev[slot], NULL));
+		slot_len[slot] = net->length;
+		step++;
+		}
+		if (pending >= 0) {
+		const int len = slot_len[pending];
+		const float *loss_host = loss_h[pending], *parts_host = parts_h[pending], *monitor_host = monitor_h[pending];
+		const int *am_host = am_h[pending];
+		out_host = out_h[pending];
+		CB_CHECK(cb200_event_sync(slot_ev[pending]));
+		if (!net->no_error) for (k = 0; k < len; k++) total_error += loss_host[k];
 		if (mat != NULL)
-			for (k = 0; k < net->length; k++) {
+			for (k = 0; k < len; k++) {
 				const int truth = am_host[net->batch_size + k], pred = am_host[k];
 				if (truth >= 0 && truth < o && pred >= 0 && pred < o) mat[(size_t)truth * o + pred] += 1.0;
 			}
 		if (!net->no_error && yolo != NULL) {
 			/* loss split and association statistics of the batch (src/auxil.c:1429-1486) */
 			size_t m, nm = (size_t)net->batch_size * h * w * yolo->nb_box;
-			for (k = 0; k < net->length * 6; k++) part_err[k % 6] += yolo->parts_host[k];
+			for (k = 0; k < len * 6; k++) part_err[k % 6] += parts_host[k];
 			for (m = 0; m < nm; m++)
-				if (yolo->monitor_host[2 * m] > -0.98f) {
+				if (monitor_host[2 * m] > -0.98f) {
 					nb_IoU++;
-					sum_obj += yolo->monitor_host[2 * m];
-					sum_IoU += yolo->monitor_host[2 * m + 1];
-					if (yolo->monitor_host[2 * m + 1] >= net->y_param->IoU_limits[0]) nb_good_IoU++;
+					sum_obj += monitor_host[2 * m];
+					sum_IoU += monitor_host[2 * m + 1];
+					if (monitor_host[2 * m + 1] >= net->y_param->IoU_limits[0]) nb_good_IoU++;
 				}
 		}
 		if (saving > 0) {
@@ -1075,7 +1104,7 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 			 * repeat > 1 the file holds, batch after batch, `repeat` consecutive blocks of the batch's samples */
 			/* a dense output record is out_size = nb_neurons + 1 values: upstream writes the bias node too (src/auxil.c:1262-1276) */
 			int b, o, per = last->type == DENSE ? c + 1 : c * h * w;
-			for (b = 0; b < net->length; b++) {
+			for (b = 0; b < len; b++) {
 				for (o = 0; o < per; o++) {
 					float v = last->type == DENSE ? out_host[(size_t)b * (c + 1) + o]
 						: out_host[((size_t)(o / (h * w)) * net->batch_size + b) * (h * w) + o % (h * w)];
@@ -1085,7 +1114,10 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 			}
 		}
 		}
+		pending = drain_only ? -1 : slot;
+		}
 	}
+	CB_CHECK(cb200_stream_sync(NULL));
 	net->last_items_per_s = (float)(data.size / (now_s() - t0));
 	/* mean over samples AND repeats on the screen (src/auxil.c:1506-1513); error.txt keeps upstream's total / data.size */
 	net->last_epoch_loss = data.size > 0 ? total_error / ((double)data.size * repeat) : 0.0;
@@ -1113,7 +1145,11 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 			fclose(f_err);
 		}
 	}
-	if (f_save != NULL) { fclose(f_save); cb200_free(out_dev); cb200_host_free(out_host); }
+	if (f_save != NULL) { fclose(f_save); cb200_free(out_dev); }
+	for (k = 0; k < 2; k++) {
+		cb200_host_free(loss_h[k]); cb200_host_free(out_h[k]); cb200_host_free(parts_h[k]); cb200_host_free(monitor_h[k]);
+		cb200_event_destroy(slot_ev[k]);
+	}
 	if (mat != NULL) {
 		/* same three report levels as upstream (src/auxil.c:1562-1652): rows = true class, columns = predicted class */
 		double *recall = (double *)calloc(o, sizeof(double)), *prec = (double *)calloc(o, sizeof(double)), count = 0.0;
@@ -1152,7 +1188,7 @@ void compute_error(network *net, Dataset data, int saving, int confusion_matrix,
 				printf("\n Accuracy: %6.2f%%\n", count / data.size * 100);
 		}
 		free(recall); free(prec); free(mat);
-		cb200_free(am_dev); cb200_host_free(am_host);
+		cb200_free(am_dev); cb200_host_free(am_h[0]); cb200_host_free(am_h[1]);
 	}
 }
 

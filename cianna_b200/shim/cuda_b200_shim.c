@@ -5,7 +5,7 @@
  * HOW A MAINTAINER USES IT: build upstream's host sources with -D CUDA exactly as its own compile script does, but link
  * this one C file (gcc, no nvcc) plus -lcianna_host -lcianna_b200 in place of the seven src/cuda/ *.cu objects, cuBLAS
  * and cuRAND.  Nothing in upstream's C or Python sources changes: `cnn.init(..., comp_meth="C_CUDA")` then runs the
- * sm_100a kernels.  oracle/build_ref.sh does exactly that (variant "dropin", tests/test_gpu_dropin.py drives it).
+ * sm_100a kernels.  oracle/build_ref.sh does exactly that (variant "dropin", tests/test_gpu_backends.py drives it).
  *
  * This file includes upstream's OWN headers (prototypes.h -> structs.h): it sees upstream's `network`, `layer`,
  * `conv_param`... and therefore cannot include cianna_b200/host/cianna.h (same names); everything it needs from the

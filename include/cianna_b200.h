@@ -112,12 +112,8 @@ int  cb200_stream_wait(void* stream, void* on_stream);
 int  cb200_event_create(void** ev);
 int  cb200_event_destroy(void* ev);
 int  cb200_event_record(void* ev, void* stream);
+int  cb200_event_sync(void* ev);                      /* host waits for the work recorded before the event */
 int  cb200_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);  /* synchronises on ev_stop */
-/* CUDA graph capture of a whole step on `stream` */
-int  cb200_graph_begin(void* stream);
-int  cb200_graph_end(void* stream, void** graph_exec);
-int  cb200_graph_launch(void* graph_exec, void* stream);
-int  cb200_graph_destroy(void* graph_exec);
 
 /* typed conversion helpers: FP32 host/device arrays <-> dtype arrays on device.
  * Replaces cuda_convert_table / cuda_get_table_to_FP32 (src/cuda/cuda_main.cu:153-300). */
@@ -249,8 +245,8 @@ int cb200_conv_backward_weights(const cb200_conv_desc* d, const cb200_conv_weigh
 int cb200_conv_backward_weights_ex(const cb200_conv_desc* d, const cb200_conv_weights* w,
                                    const void* x, const void* dy, int have_grad_b, void* stream);
 
-/* Optimizer hyper-parameters live in a small device buffer so that a captured CUDA graph can be
- * replayed with a new learning rate: hyper[0]=lr/batch_total, [1]=momentum, [2]=lr*weight_decay,
+/* Optimizer hyper-parameters live in a small device buffer (a new learning rate is one small copy, no kernel argument
+ * changes, and the whole-network update plan keeps pointing at it): hyper[0]=lr/batch_total, [1]=momentum, [2]=lr*weight_decay,
  * [3]=TC_scale_factor, [4]=lr (plain). */
 #define CB200_HYPER_LEN 8
 /* moment = hyper0*grad + mom*moment ; moment += wd_lr*master*S ; master -= moment/S ; then refresh
@@ -328,9 +324,27 @@ size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial s
  * chunk_kb: bytes read by the statistics blocks of one launch (0: keep; default 24 MB, env CB200_GN_CHUNK_MB);
  * blocks_per_sm: blocks per SM and role in one launch (0: keep; default 6, env CB200_GN_BLOCKS_PER_SM). */
 void cb200_norm_set_pipeline(int on, int chunk_kb, int blocks_per_sm);
+/* grid sizing of the group-norm kernels: blocks wanted per SM over the whole batch (default 8) and the most pixels a
+ * block takes (default 1024); 0 keeps a value.  Measurement hook (scripts/exp/gn_apply_sweep.py). */
+void cb200_norm_set_tuning(int want_blocks_per_sm, int ppb_max);
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y,
                        const float* gamma, const float* beta, float* mean, float* var,
                        void* workspace, void* stream);
+/* ---- statistics pass taken out of HBM: the convolution in front of a group-norm layer accumulates the layer's
+ * (sum, sum of squares) per (sample, group) in its epilogue, from the values it has just rounded for the store - the
+ * numbers cuda_group_mean / cuda_group_var (src/cuda/cuda_norm_layer.cu:65-138) would read back - and leaves them in the
+ * norm layer's FP64 workspace.  cb200_conv_forward_stats = cb200_conv_forward + that; *stats_done = 1 when the kernel that
+ * ran could do it (tcgen05 kernels, group size 8 / 16 / a multiple of 32, tile rows of a sample >= sums per chunk), 0
+ * when the workspace is untouched.  The _ex norm entry points take that flag: stats_ready = 1 skips their own
+ * statistics launch and the workspace reset (forward: 3 -> 2 passes over the tensor; fused with the max-pool: 2 -> 1). */
+int cb200_conv_forward_stats(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x, void* y,
+                             const cb200_norm_desc* gn, void* gn_workspace, int* stats_done, void* stream);
+/* 0: never; 1 (default, env CB200_GN_EPILOGUE_STATS): only where the sums hide behind the tensor pipe (K loops of >= 16
+ * blocks: 3x3 filters on >= 128 channels - elsewhere they cost what the statistics pass costs, csrc/conv_tc.cu); 2: always */
+void cb200_set_gn_epilogue_stats(int mode);
+int cb200_norm_forward_ex(const cb200_norm_desc* d, const void* x, void* y,
+                          const float* gamma, const float* beta, float* mean, float* var,
+                          void* workspace, int stats_ready, void* stream);
 /* d_gamma/d_beta: FP32 [batch][nb_group] per-sample sums (as upstream); dx includes the
  * previous->deriv_activation hook (prev_out == x of this layer).
  * Replaces cuda_backward_norm_layer's device half (cuda_norm_layer.cu:399-432). */
@@ -365,6 +379,9 @@ int cb200_norm_pool_fusable(const cb200_norm_desc* nd, const cb200_pool_desc* pd
 int cb200_norm_pool_forward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, void* pooled,
                             uint8_t* pool_map, const float* gamma, const float* beta, float* mean, float* var,
                             void* workspace, void* stream);
+int cb200_norm_pool_forward_ex(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, void* pooled,
+                               uint8_t* pool_map, const float* gamma, const float* beta, float* mean, float* var,
+                               void* workspace, int stats_ready, void* stream);
 /* d_pooled: delta of the pool OUTPUT; dx: delta of the norm INPUT (previous layer's derivative hook included). */
 int cb200_norm_pool_backward(const cb200_norm_desc* nd, const cb200_pool_desc* pd, const void* x, const void* d_pooled,
                              const uint8_t* pool_map, void* dx, const float* gamma, const float* mean,

@@ -74,7 +74,7 @@ build_cuda_variant() {
 if [ "${CIANNA_REF_NO_CUDA:-0}" != "1" ]; then build_cuda_variant; fi
 
 # ---- the product as upstream's back-end: upstream's UNMODIFIED host sources (-D CUDA) + cianna_b200/shim/cuda_b200_shim.c
-# in place of src/cuda/*.cu, cuBLAS and cuRAND.   oracle/_ref/dropin/CIANNA.so   (tests/test_gpu_dropin.py)
+# in place of src/cuda/*.cu, cuBLAS and cuRAND.   oracle/_ref/dropin/CIANNA.so   (tests/test_gpu_backends.py)
 # Built under oracle/_ref/ because it contains compiled reference host code; it loads ../../../cianna_b200/libcianna_host.so.
 build_dropin_variant() {
 	REPO=$(cd "$HERE/.." && pwd)

@@ -177,7 +177,9 @@ def test_network_trains_to_the_same_weights_with_and_without_the_plan(net, freez
     flat = spec["in_ch"] * int(np.prod(spec["in_dim"]))
     batches = []
     for _ in range(3):
-        x = rng.standard_normal((spec["batch"], flat)).astype(np.float32)
+        x = np.empty((spec["batch"], flat + 1), np.float32)      # dataset rows: the bias slot comes last
+        x[:, :flat] = rng.standard_normal((spec["batch"], flat))
+        x[:, flat] = spec["bias"]
         t = np.zeros((spec["batch"], spec["out_dim"]), np.float32)
         t[np.arange(spec["batch"]), rng.integers(0, spec["out_dim"], spec["batch"])] = 1
         batches.append((x, t))
