@@ -20,7 +20,9 @@ struct NormGeom {
 constexpr int NORM_THREADS = 256;
 // pixels handled by one block: sized on the host so that every launch has several waves of blocks
 // (deep layers have few pixels per sample) while a thread still streams a few 128-bit packets
-static int g_norm_want_blocks = 8, g_norm_ppb_max = 1024;     // cb200_norm_set_tuning (measurement hook)
+// blocks wanted per SM over the batch and the most pixels a block takes: 8 / 4096 measured best on the Darknet19 shapes at
+// batch 128 (profiles/r2_gn_apply_sweep.txt: 1024 pixels per block cost the 448 px layer 8-11 %, more blocks per SM 3-20 %)
+static int g_norm_want_blocks = 8, g_norm_ppb_max = 4096;
 static int norm_pix_per_block(int hw, int batch, int cv) {
 	const int lanes_c = cv < NORM_THREADS ? cv : NORM_THREADS;
 	const int lanes_p = NORM_THREADS / lanes_c;
@@ -358,6 +360,33 @@ __device__ __forceinline__ void fwd_constants(const NormGeom& g, int b, int v, c
 	}
 }
 
+// The window maximum of four 8-channel candidates in PACKED 16-bit arithmetic (the kernel is instruction-bound: 61 % ALU
+// pipe, 56 % issue slots on the first Darknet19 layer).  The candidates are rounded to the storage type first - two
+// values per cvt - and compared as stored, so value and index equal the scalar form below: first strict maximum in scan
+// order = (c1 > c0 ? 1 : 0) / (c3 > c2 ? 3 : 2), the second pair winning only when strictly larger.  Comparison masks
+// (0xffff per 16-bit lane) are combined into the 2-bit index per lane and the eight indices packed with byte permutes.
+__device__ __forceinline__ __half2 pk2(float a, float b, const __half*) { return __floats2half2_rn(a, b); }
+__device__ __forceinline__ __nv_bfloat162 pk2(float a, float b, const __nv_bfloat16*) { return __floats2bfloat162_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ void pool4_select_packed(const float (&y0)[8], const float (&y1)[8], const float (&y2)[8], const float (&y3)[8],
+                                                    uint4& best, uint2& arg) {
+	uint32_t bw[4], aw[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const auto c0 = pk2(y0[2 * i], y0[2 * i + 1], (const T*)nullptr), c1 = pk2(y1[2 * i], y1[2 * i + 1], (const T*)nullptr);
+		const auto c2 = pk2(y2[2 * i], y2[2 * i + 1], (const T*)nullptr), c3 = pk2(y3[2 * i], y3[2 * i + 1], (const T*)nullptr);
+		const auto m01 = __hmax2(c0, c1), m23 = __hmax2(c2, c3);
+		const uint32_t g1 = __hgt2_mask(c1, c0), g3 = __hgt2_mask(c3, c2), gb = __hgt2_mask(m23, m01);
+		const auto m = __hmax2(m01, m23);
+		bw[i] = *reinterpret_cast<const uint32_t*>(&m);
+		const uint32_t a = (gb & 0x00020002u) | (((g3 & gb) | (g1 & ~gb)) & 0x00010001u);      // index per 16-bit lane
+		aw[i] = a;
+	}
+	best = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+	arg.x = __byte_perm(aw[0], aw[1], 0x6420);      // bytes: lane 0 / 1 of pair 0, lane 0 / 1 of pair 1
+	arg.y = __byte_perm(aw[2], aw[3], 0x6420);
+}
+
 // y = x*sc + sh rounded to the storage type (what the unfused apply would have stored), then the first strict maximum
 // of the window in scan order (0,0) (0,1) (1,0) (1,1); only the pooled value and its window index are written
 template <typename T>
@@ -384,6 +413,21 @@ __device__ __forceinline__ void norm_pool_fwd_body(const T* __restrict__ x, T* _
 			const Raw8<T> r0 = load_raw8<T>(p), r1 = load_raw8<T>(p + g.cp), r2 = load_raw8<T>(p + row), r3 = load_raw8<T>(p + row + g.cp);
 			float a0[8], a1[8], a2[8], a3[8], best[8];
 			unpack8(r0, a0); unpack8(r1, a1); unpack8(r2, a2); unpack8(r3, a3);
+			const long long o = ob + (long long)q * g.cp;
+			if constexpr (sizeof(T) == 2) {
+				if (v * 8 + 8 <= g.c) {                 // (a vector with pad channels takes the scalar form below)
+#pragma unroll
+					for (int j = 0; j < 8; j++) {
+						a0[j] = fmaf(a0[j], sc[j], sh[j]); a1[j] = fmaf(a1[j], sc[j], sh[j]);
+						a2[j] = fmaf(a2[j], sc[j], sh[j]); a3[j] = fmaf(a3[j], sc[j], sh[j]);
+					}
+					uint4 bp; uint2 ap;
+					pool4_select_packed<T>(a0, a1, a2, a3, bp, ap);
+					*reinterpret_cast<uint4*>(pooled + o) = bp;
+					if (map != nullptr) *reinterpret_cast<uint2*>(map + o) = ap;
+					continue;
+				}
+			}
 			uint32_t arg[8];
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
@@ -397,7 +441,6 @@ __device__ __forceinline__ void norm_pool_fwd_body(const T* __restrict__ x, T* _
 				if (t > best[j]) { best[j] = t; arg[j] = 3; }
 				if (v * 8 + j >= g.c) { best[j] = 0.0f; arg[j] = 255; }
 			}
-			const long long o = ob + (long long)q * g.cp;
 			store8<T>(pooled + o, best);
 			uint2 packed;
 			packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);

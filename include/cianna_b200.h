@@ -325,7 +325,7 @@ size_t cb200_norm_workspace_bytes(const cb200_norm_desc* d);   /* FP64 partial s
  * blocks_per_sm: blocks per SM and role in one launch (0: keep; default 6, env CB200_GN_BLOCKS_PER_SM). */
 void cb200_norm_set_pipeline(int on, int chunk_kb, int blocks_per_sm);
 /* grid sizing of the group-norm kernels: blocks wanted per SM over the whole batch (default 8) and the most pixels a
- * block takes (default 1024); 0 keeps a value.  Measurement hook (scripts/exp/gn_apply_sweep.py). */
+ * block takes (default 4096); 0 keeps a value.  Measurement hook (scripts/exp/gn_apply_sweep.py). */
 void cb200_norm_set_tuning(int want_blocks_per_sm, int ppb_max);
 int cb200_norm_forward(const cb200_norm_desc* d, const void* x, void* y,
                        const float* gamma, const float* beta, float* mean, float* var,

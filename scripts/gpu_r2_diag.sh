@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for i in 1 2 3; do echo "== default $i"; timeout 300 python scripts/exp/first_net_debug.py 2>&1 | cut -c1-400 | tail -8; done
-for i in 1 2 3; do echo "== STATSY0 $i"; CB200_GN_POOL_STATS_Y=0 timeout 300 python scripts/exp/first_net_debug.py 2>&1 | cut -c1-400| tail -5; done
-for i in 1 2 3; do echo "== NO_WGRAD_STREAM $i"; CB200_NO_WGRAD_STREAM=1 timeout 300 python scripts/exp/first_net_debug.py 2>&1 | cut -c1-400| tail -5; done
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_gn_epilogue.py tests/test_gpu_network.py -m gpu -q --tb=short -x > gpurun_out/tests_ops.log 2>&1; tail -6 gpurun_out/tests_ops.log | cut -c1-300
+timeout 900 python scripts/exp/gn_apply_sweep.py > gpurun_out/gn_apply_sweep2.txt 2>&1; cat gpurun_out/gn_apply_sweep2.txt
