@@ -22,7 +22,9 @@ for r in rows[start + 1:]:
     e = by.setdefault(int(d["ID"]), {"k": d["Kernel Name"]})
     e[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
 ids = sorted(by)
-last = [by[i] for i in ids[len(ids) // 2:]]
+# the last step starts at the last launch of the network's first kernel (first-layer forward, or the input import)
+starts = [i for i in ids if "conv_first_fwd_kernel" in by[i]["k"] or "import_input" in by[i]["k"]]
+last = [by[i] for i in ids if i >= starts[-1]] if starts else [by[i] for i in ids[len(ids) // 2:]]
 groups = {"igemm": ("conv_igemm_kernel", "conv_igemm_pair_kernel", "conv_halo_kernel", "conv_first_fwd_kernel"), "wgrad": ("conv_wgrad_kernel", "conv_wgrad_pair_kernel", "conv_wgrad_swap_kernel", "conv_first_wgrad_kernel")}
 out = {"batch": batch, "kernel_source_id": kernel_source_id(), "note": "ncu per-launch metrics of one Darknet19-448 FP16C_FP32A training step (scripts/gpu_step_metrics.sh -> %s)" % src}
 for key, names in groups.items():

@@ -14,7 +14,9 @@ for r in rows[start + 1:]:
     e = by.setdefault(int(d["ID"]), {"k": d["Kernel Name"], "grid": d.get("Grid Size")})
     e[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
 ids = sorted(by)
-last = ids[len(ids) // 2:]
+# the last step starts at the last launch of the network's first kernel (first-layer forward, or the input import)
+starts = [i for i in ids if "conv_first_fwd_kernel" in by[i]["k"] or "import_input" in by[i]["k"]]
+last = [i for i in ids if i >= starts[-1]] if starts else ids[len(ids) // 2:]
 per_launch = len(sys.argv) > 2
 tot = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
 for i in last:
