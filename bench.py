@@ -62,7 +62,16 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, line)
+        self.t0 = self.t1 = None
+
+    def begin(self):
+        """the timed region starts (the process was started earlier: nvidia-smi needs 0.1-1 s to deliver its first line,
+        longer when eight ranks start one each - the timed region of ten 16 ms steps would be over by then)"""
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
@@ -74,7 +83,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -83,7 +92,16 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = (self.t1 if self.t1 is not None else time.monotonic()) + 0.12      # a line describes the 100 ms before it
+        window = [ln for t, ln in self.lines if t0 <= t <= t1]
+        scope = "timed region"
+        if not window:
+            # a region shorter than the sampling period: the closest samples under the same load (the steps of the
+            # attribution pass and the warm-up step right before the region)
+            window = [ln for t, ln in self.lines if t0 - 1.5 <= t <= t1 + 0.3]
+            scope = "timed region +- 1.5 s (same workload running)"
+        for ln in window:
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -95,7 +113,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def workload_config(args, world):
@@ -325,6 +343,8 @@ def run_ours(args, rank, local_rank, world):
     # (a) attribution pass: the same K steps with the weight-gradient kernels back on the compute stream, so that every
     #     CUDA-event pair brackets ONE kernel family running alone (in the timed pass below the weight gradients overlap
     #     the rest of the backward sweep on a low-priority stream and per-kernel durations are not separable)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     H.cb_set_wgrad_overlap.argtypes = [ctypes.c_void_p, ctypes.c_int]
     H.cb_set_wgrad_overlap(net, 0)
     L.cb200_profile_reset()
@@ -336,9 +356,9 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     # (b) the timed region of `value`
     L.cb200_launch_count(1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     ms_res = timed(lambda: H.cb_train_steps(net, args.steps, lr, mom, wd, 1, 0))
+    sampler.end()
     clocks = sampler.stop()
     rank_ms_res = [m / args.steps for m in per_rank_ms]
     rank_clocks = [clocks]
