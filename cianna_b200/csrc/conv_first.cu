@@ -42,6 +42,11 @@ struct FirstParams {
 	int tiles_per_cta;           // contiguous run of tiles owned by one CTA
 	uint32_t idesc;
 	int tma_store;               // forward: the output tile leaves through shared memory + one TMA store per tile
+	int prefetch;                // builders prefetch the next tile's receptive fields into L1 (CB200_FIRST_PREFETCH=0: off)
+	// weight gradient with <= 32 filters: dy arrives as ONE [64 px][32 filters] box (64-byte rows, 64B swizzle, 4 KB) instead
+	// of two 64-filter boxes of which three quarters are zero fill (16 KB written per step), and the M = 128 MMA reads
+	// that 32-row atom four times (leading byte offset 0: accumulator rows 32..127 repeat rows 0..31 and are never read)
+	int wg_narrow;
 };
 
 template <int KP> struct PatchCfg {
@@ -54,9 +59,15 @@ template <int KP> struct PatchCfg {
 
 // Assemble the patch row of output pixel (py, px) of image `img` and store it as row `row` of a tile at smem address
 // `tile` (16-byte chunks XOR-swizzled exactly like CU_TENSOR_MAP_SWIZZLE_{128,64,32}B does for rows of KP*2 bytes).
+// nxt != nullptr: the receptive field of the pixel this thread builds NEXT (same position in the group's next tile) is
+// prefetched into L1 right behind this row's own loads.  The builders are bound by the latency of those loads, not by
+// their number (ncu source view of the forward kernel: 80 % of the builder warps' samples wait on the first use of a
+// loaded value, while half of the epilogue warps' samples wait for accumulators), and a row's lines come from L2 /
+// HBM the first time they are touched; a prefetch needs no register.
 template <typename T, int C, int FH, int FW, int KP>
 __device__ __forceinline__ void build_patch_row(const T* __restrict__ img, bool valid, int h, int w, int iy0, int ix0,
-                                                unsigned short bias_bits, uint32_t tile, int row) {
+                                                unsigned short bias_bits, uint32_t tile, int row,
+                                                const T* __restrict__ nxt = nullptr, int niy0 = 0, int nix0 = 0) {
 	using PC = PatchCfg<KP>;
 	constexpr int TAPS = FH * FW, KREAL = C * TAPS;
 	static_assert(KREAL + 1 <= KP, "patch row does not fit");
@@ -68,8 +79,12 @@ __device__ __forceinline__ void build_patch_row(const T* __restrict__ img, bool 
 		// interior pixel (all but the image border): every tap is inside, plain loads at fixed offsets from one pointer
 		// per (channel, filter row) - the builders are instruction-bound, so this path carries no predicates
 		// (32-bit element offsets inside one image - c*h*w < 2^31 - keep the nine line pointers at one IMAD.WIDE each)
+		// ALL loads first, then the packing: with load and use interleaved in the source the compiler kept only a few
+		// loads in flight (ncu: 16 long-scoreboard stall cycles per issued instruction in the weight-gradient kernel, i.e.
+		// several L2 round trips per patch row instead of one)
 		const int off0 = iy0 * w + ix0;
 		const int chs = h * w;
+		unsigned short v[KREAL];
 #pragma unroll
 		for (int ch = 0; ch < C; ch++) {
 #pragma unroll
@@ -77,11 +92,22 @@ __device__ __forceinline__ void build_patch_row(const T* __restrict__ img, bool 
 				const unsigned short* __restrict__ line = src + (off0 + ch * chs + ky * w);
 #pragma unroll
 				for (int kx = 0; kx < FW; kx++) {
-					const int k = (ch * FH + ky) * FW + kx;
-					packed[k >> 1] |= (uint32_t)__ldg(line + kx) << (16 * (k & 1));
+					unsigned short t;
+					asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(t) : "l"(line + kx));
+					v[(ch * FH + ky) * FW + kx] = t;
 				}
 			}
 		}
+		if (nxt != nullptr && niy0 >= 0 && niy0 + FH <= h && nix0 >= 0 && nix0 + FW <= w) {
+			const unsigned short* __restrict__ nsrc = reinterpret_cast<const unsigned short*>(nxt) + (niy0 * w + nix0);
+#pragma unroll
+			for (int ch = 0; ch < C; ch++)
+#pragma unroll
+				for (int ky = 0; ky < FH; ky++)
+					asm volatile("prefetch.global.L1 [%0];" ::"l"(nsrc + (ch * chs + ky * w)));
+		}
+#pragma unroll
+		for (int k = 0; k < KREAL; k++) packed[k >> 1] |= (uint32_t)v[k] << (16 * (k & 1));
 	} else {
 		bool col_ok[FW];
 #pragma unroll
@@ -122,7 +148,11 @@ template <> __device__ __forceinline__ unsigned short bits_of<__nv_bfloat16>(flo
 // epilogue groups waiting for accumulators: the limiter is the LATENCY of one tile's epilogue (tcgen05.ld -> activation ->
 // stores is a ~2000-cycle dependent chain for a warp sharing its scheduler with six others), so tiles in flight in the
 // epilogue matter more than builder warps: 2 builder groups, 4 epilogue groups (= accumulator stages)
-constexpr int FWD_BUILD_GROUPS = 2, FWD_BUILD_WARPS = 4 * FWD_BUILD_GROUPS, FWD_EPI_GROUPS = 4;
+#ifndef CB200_FWD_BUILD_GROUPS
+#define CB200_FWD_BUILD_GROUPS 2
+#define CB200_FWD_EPI_GROUPS 4
+#endif
+constexpr int FWD_BUILD_GROUPS = CB200_FWD_BUILD_GROUPS, FWD_BUILD_WARPS = 4 * FWD_BUILD_GROUPS, FWD_EPI_GROUPS = CB200_FWD_EPI_GROUPS;
 constexpr int FWD_THREADS = (FWD_BUILD_WARPS + 1 + 4 * FWD_EPI_GROUPS) * 32;
 template <int KP, int BN> struct FirstFwdCfg {
 	static constexpr int A_BYTES = 128 * KP * 2;
@@ -181,6 +211,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
 		// tile coordinates advance incrementally (one division at the start instead of three per tile)
 		const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+		const bool prefetch_next = p.prefetch != 0;
 		int twi = (tile0 + grp) % tiles_w, thi = ((tile0 + grp) / tiles_w) % tiles_h, tni = (tile0 + grp) / (tiles_w * tiles_h);
 		for (int it = grp; it < n_tiles; it += FWD_BUILD_GROUPS) {
 			const int stage = it % Cfg::STAGES;
@@ -189,9 +220,13 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 			twi += FWD_BUILD_GROUPS;
 			while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
 			const bool valid = px < p.W && py < p.H && pn < p.N;
+			// this thread's pixel in the group's next tile (twi / thi / tni already point there)
+			const int npx = twi * p.tw + rx, npy = thi * p.th + ry, npn = tni * p.tn + rn;
+			const bool nvalid = prefetch_next && it + FWD_BUILD_GROUPS < n_tiles && npx < p.W && npy < p.H && npn < p.N;
 			mbar_wait(empty_bar(stage), phase ^ 1u);
 			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
-				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::A_BYTES, row);
+				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::A_BYTES, row,
+				nvalid ? src + (size_t)npn * img_stride : nullptr, npy * p.s_h - p.p_h, npx * p.s_w - p.p_w);
 			fence_proxy_async();          // each writer publishes its row to the async proxy ...
 			__syncwarp();
 			if (lane == 0) mbar_arrive(full_bar(stage));     // ... then one arrival per warp
@@ -245,12 +280,17 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 			uint8_t* stg_ptr = smem_raw + (stg - smem_u32(smem_raw));
 			constexpr int CHUNKS = BN / 8;                                         // 16-byte chunks per row: 4 (64B swizzle) or 8 (128B)
 			const int sw_x = BN == 32 ? ((row >> 1) & 3) : (row & 7);
+			// tile coordinates advance incrementally (three divisions by run-time values per tile were 15 % of this warp's
+			// instructions, and the kernel issues at 67 % of its slots once the builders prefetch)
+			const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+			int twi = (tile0 + egrp) % tiles_w, thi = ((tile0 + egrp) / tiles_w) % tiles_h, tni = (tile0 + egrp) / (tiles_w * tiles_h);
 			for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
-				const int tile = tile0 + it;
 				const int acc = it % Cfg::ACC_STAGES;
 				const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
-				const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
-				const int pn = tni * p.tn + rn;
+				const int c_twi = twi, c_thi = thi, c_tni = tni;
+				twi += FWD_EPI_GROUPS;
+				while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
+				const int pn = c_tni * p.tn + rn;
 				const bool dead = mask_tail && pn >= p.length;
 				mbar_wait(tfull_bar(acc), acc_phase);
 				tc_fence_after();
@@ -298,18 +338,21 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 				fence_proxy_async();                                                 // generic-proxy writes -> visible to the TMA unit
 				asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
 				if (gtid == 0) {
-					tma_store_4d(&tmap_out, stg, 0, twi * p.tw, thi * p.th, tni * p.tn);
+					tma_store_4d(&tmap_out, stg, 0, c_twi * p.tw, c_thi * p.th, c_tni * p.tn);
 					bulk_commit();
 				}
 			}
 			if (gtid == 0) bulk_wait0();
 		} else
+		{
+		const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+		int twi = (tile0 + egrp) % tiles_w, thi = ((tile0 + egrp) / tiles_w) % tiles_h, tni = (tile0 + egrp) / (tiles_w * tiles_h);
 		for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
-			const int tile = tile0 + it;
 			const int acc = it % Cfg::ACC_STAGES;
 			const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
-			const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
 			const int px = twi * p.tw + rx, py = thi * p.th + ry, pn = tni * p.tn + rn;
+			twi += FWD_EPI_GROUPS;
+			while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
 			const bool row_ok = px < p.W && py < p.H && pn < p.N;
 			const size_t pix = ((size_t)pn * p.H + py) * p.W + px;
 			const bool dead = mask_tail && pn >= p.length;
@@ -362,6 +405,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(tempty_bar(acc));
+		}
 		}
 	}
 	tc_fence_before();
@@ -423,14 +467,15 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
 				mbar_wait(empty_bar(stage), phase ^ 1u);
 				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-				mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES);
+				mbar_arrive_expect_tx(full_bar(stage), p.wg_narrow ? Cfg::KPIX * 64 : Cfg::A_BYTES);
 				tma_load_4d(sa, &tmap_dy, full_bar(stage), 0, twi * p.tw, thi * p.th, tni * p.tn);
-				tma_load_4d(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), 64, twi * p.tw, thi * p.th, tni * p.tn);
+				if (!p.wg_narrow) tma_load_4d(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), 64, twi * p.tw, thi * p.th, tni * p.tn);
 			}
 		}
 	} else if (warp == 1) {
 		if (lane == 0) {
-			const uint64_t da_proto = make_smem_desc(0, Cfg::A_SLAB_BYTES, 1024, 2);
+			const uint64_t da_proto = p.wg_narrow ? make_smem_desc(0, 0, 512, 4) : make_smem_desc(0, Cfg::A_SLAB_BYTES, 1024, 2);
+			const uint32_t a_kstep = (p.wg_narrow ? 16 * 64 : 16 * 128) >> 4;      // 16 pixels further down the slab
 			const uint64_t db_proto = make_smem_desc(0, Cfg::B_BYTES, PC::SBO, PC::LAYOUT);
 			const uint32_t idesc = p.idesc;
 			for (int k = 0; k < n_steps; k++) {
@@ -442,7 +487,7 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 				const uint64_t da = da_proto + (sa >> 4), db = db_proto + ((sa + Cfg::A_BYTES) >> 4);
 #pragma unroll
 				for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
-					mma_f16_ss(tmem_base, da + ((kk * 2048) >> 4), db + ((kk * 16 * PC::ROW_BYTES) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
+					mma_f16_ss(tmem_base, da + kk * a_kstep, db + ((kk * 16 * PC::ROW_BYTES) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
 				mma_commit(empty_bar(stage));
 			}
 			mma_commit(done_bar);
@@ -491,9 +536,13 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 			twi += WG_BUILD_WARPS / 2;
 			while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
 			const bool valid = px < p.W && py < p.H && pn < p.N;
+			const int npx = twi * p.tw + rx, npy = thi * p.th + ry, npn = tni * p.tn + rn;
+			// (measured: eight steps are in flight here, the prefetch buys nothing - 683 us with, 673 us without)
+			const bool nvalid = p.prefetch > 1 && k + WG_BUILD_WARPS / 2 < n_steps && npx < p.W && npy < p.H && npn < p.N;
 			mbar_wait(empty_bar(stage), phase ^ 1u);
 			build_patch_row<T, C, FH, FW, KP>(src + (size_t)(valid ? pn : 0) * img_stride, valid, p.h, p.w,
-				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, row);
+				py * p.s_h - p.p_h, px * p.s_w - p.p_w, bias_bits, smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, row,
+				nvalid ? src + (size_t)npn * img_stride : nullptr, npy * p.s_h - p.p_h, npx * p.s_w - p.p_w);
 			fence_proxy_async();          // each writer publishes its row to the async proxy ...
 			__syncwarp();
 			if (lane == 0) mbar_arrive(full_bar(stage));     // ... then one arrival per warp
@@ -524,6 +573,8 @@ static void fill_params(const cb200_conv_desc* d, const void* src, int npix, Fir
 	p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 	p.n_real = d->out_c; p.n_pad = round8(d->out_c); p.length = d->length;
 	p.bias_value = d->bias_value; p.activ = d->activ;
+	static const bool no_prefetch = getenv("CB200_FIRST_PREFETCH") != nullptr && getenv("CB200_FIRST_PREFETCH")[0] == '0';
+	p.prefetch = no_prefetch ? 0 : 1;
 }
 
 template <typename T, int C, int FH, int FW, int KP, int BN>
@@ -611,7 +662,10 @@ int conv_first_wgrad(const cb200_conv_desc* d, const cb200_conv_weights* w, cons
 	p.grad = w->grad;
 	p.idesc = make_idesc_f16(d->dtype == CB200_BF16, 128, kp, 1, 1);
 	CUtensorMap mdy;
-	int rc = make_act_map(&mdy, dy, d->dtype, p.n_pad, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B, 1);
+	static const bool no_narrow = getenv("CB200_FIRST_WG_NARROW") != nullptr && getenv("CB200_FIRST_WG_NARROW")[0] == '0';
+	p.wg_narrow = (p.n_pad <= 32 && !no_narrow) ? 1 : 0;
+	int rc = p.wg_narrow ? make_act_map(&mdy, dy, d->dtype, p.n_pad, d->out_w, d->out_h, d->batch, 32, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_64B, 1)
+	                     : make_act_map(&mdy, dy, d->dtype, p.n_pad, d->out_w, d->out_h, d->batch, 64, p.tw, p.th, p.tn, CU_TENSOR_MAP_SWIZZLE_128B, 1);
 	if (rc) return rc;
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
 	p.tiles_per_cta = ceil_div(p.num_tiles, grid);

@@ -142,7 +142,14 @@ struct IgemmParams {
 	// every CTA takes a CONTIGUOUS run of tiles instead of every gridDim.x-th one (set with gn_ws: a warp then stays on one
 	// sample for many tiles and hands its sums to memory once per sample, not once per tile)
 	int contig;
+	// ceil(2^64 / d) for d = tiles_m (pairs_m in pair / cluster order), tiles_w, tiles_h, tiles_w * tiles_h: the epilogue threads
+	// split a tile index with multiply-high instead of four run-time integer divisions per tile (each a dependent chain of
+	// ~20 instructions through the reciprocal unit, on the critical path of a tile's epilogue)
+	unsigned long long mg_m, mg_w, mg_h, mg_wh;
 };
+// n / d through the magic number M = ceil(2^64 / d) (exact for 32-bit n and d: n * (M - 2^64 / d) < 2^64 / d); M == 0: d == 1
+static inline unsigned long long fastdiv_magic(int d) { return d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull; }
+__device__ __forceinline__ int fastdiv(int n, unsigned long long M) { return M == 0ull ? n : (int)__umul64hi((unsigned long long)(unsigned)n, M); }
 
 // the tiles of this CTA: first, first + step, ... (count of them).  Strided: blockIdx.x, + gridDim.x, ...; contiguous: a
 // run of consecutive tiles (pair / cluster order: consecutive PAIRS, this CTA's tile of each).  Same count either way.
@@ -171,8 +178,8 @@ __device__ __forceinline__ TileRun tile_run(const IgemmParams& p) {
 // tile index -> (M tile, N tile).  Cluster mode enumerates pairs: tile = 2*pair + rank, so that with an even grid the
 // two CTAs of a cluster always hold the two tiles of one pair (a pair past the last M tile gets a dummy, all-OOB tile).
 __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& mt, int& nt) {
-	if (p.cluster) { const int q = tile >> 1; nt = q / p.pairs_m; mt = 2 * (q - nt * p.pairs_m) + (tile & 1); }
-	else { nt = tile / p.tiles_m; mt = tile - nt * p.tiles_m; }
+	if (p.cluster) { const int q = tile >> 1; nt = fastdiv(q, p.mg_m); mt = 2 * (q - nt * p.pairs_m) + (tile & 1); }
+	else { nt = fastdiv(tile, p.mg_m); mt = tile - nt * p.tiles_m; }
 }
 
 // ---------------------------------------------------------------- shared epilogue of the forward / dgrad kernels
@@ -288,7 +295,8 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
 		int mt, nt;
 		decode_tile(p, tile, mt, nt);
-		const int twi = mt % tiles_w, thi = (mt / tiles_w) % tiles_h, tni = mt / (tiles_w * tiles_h);
+		const int tni = fastdiv(mt, p.mg_wh), mrem = mt - tni * (tiles_w * tiles_h);
+		const int thi = fastdiv(mrem, p.mg_w), twi = mrem - thi * tiles_w;
 		if (GN && (tni != gn_tni || nt != gn_nt)) {
 			if (gn_tni >= 0) gn_flush();
 			gn_tni = tni; gn_nt = nt;
@@ -1062,6 +1070,8 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 			ph.kc_blocks = ceil_div(cin_p, bk);
 			ph.n_real = n_real; ph.n_pad = n_pad;
 			ph.idesc = make_idesc_f16(dtype == CB200_BF16, 128, bn, 0, 0);
+			ph.mg_m = fastdiv_magic(ph.tiles_m); ph.mg_w = fastdiv_magic(ph.tiles_w); ph.mg_h = fastdiv_magic(ph.tiles_h);
+			ph.mg_wh = fastdiv_magic(ph.tiles_w * ph.tiles_h);
 			// No epilogue statistics in this kernel (measured, Darknet19 layers 2 / 3 / 5 at batch 128,
 			// profiles/r2_gn_epilogue_stats.txt): its launches are bound by the epilogue's latency chain and by HBM, so sums
 			// in the epilogue are paid in full, and the contiguous tile runs that keep a warp on one sample (strided runs
@@ -1109,6 +1119,8 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	p.kc_blocks = ceil_div(cin_p, bk);
 	p.n_real = n_real; p.n_pad = n_pad;
 	p.idesc = make_idesc_f16(dtype == CB200_BF16, p.cluster == 2 ? 256 : 128, bn, 0, 0);
+	p.mg_m = fastdiv_magic(p.cluster ? p.pairs_m : p.tiles_m); p.mg_w = fastdiv_magic(p.tiles_w); p.mg_h = fastdiv_magic(p.tiles_h);
+	p.mg_wh = fastdiv_magic(p.tiles_w * p.tiles_h);
 	if (gn_stats_ok(p, tw, th, f_h * f_w * p.kc_blocks)) {
 		p.contig = 1;
 		if (cudaMemsetAsync(p.gn_ws, 0, sizeof(double) * 2 * (size_t)batch * p.gn_groups, st) != cudaSuccess) { set_error("cudaMemsetAsync(group-norm sums) failed"); return CB200_ERR_CUDA; }

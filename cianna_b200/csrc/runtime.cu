@@ -171,6 +171,7 @@ int cb200_stream_wait(void* s, void* on) {
 int cb200_event_create(void** ev) { CB_REQUIRE_DEVICE(); cudaEvent_t e; CB_CUDA(cudaEventCreate(&e)); *ev = e; return CB200_OK; }
 int cb200_event_destroy(void* ev) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return CB200_OK; }
 int cb200_event_record(void* ev, void* s) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventRecord((cudaEvent_t)ev, as_stream(s))); return CB200_OK; }
+int cb200_stream_wait_event(void* s, void* ev) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaStreamWaitEvent(as_stream(s), (cudaEvent_t)ev, 0)); return CB200_OK; }
 int cb200_event_sync(void* ev) { CB_REQUIRE_DEVICE(); CB_CUDA(cudaEventSynchronize((cudaEvent_t)ev)); return CB200_OK; }
 int cb200_event_elapsed_ms(void* a, void* b, float* ms) {
 	CB_REQUIRE_DEVICE();

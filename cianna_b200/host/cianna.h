@@ -196,6 +196,11 @@ struct network {
 	float *loss_dev;       /* FP32 [batch_size] per-sample loss */
 	float *loss_host;      /* pinned */
 	float *hyper_dev;      /* CB200_HYPER_LEN floats */
+	/* the optimizer of every layer but the first starts while the first layer's weight gradient - the last kernel of the
+	 * backward sweep, alone on the side stream - is still running: `upper_ev` is recorded on the side stream before that
+	 * kernel is enqueued (all other weight gradients are ahead of it), the compute stream waits for the event only */
+	void *upper_ev;
+	int upper_marked;
 	void *update_plan;     /* cb200_update_plan of the layers below (the optimizer sweep in three launches), or NULL */
 	unsigned update_plan_sig;   /* which layers were frozen / how the norm sums arrive when the plan was built */
 	unsigned char in_update_plan[MAX_LAYERS_NB];

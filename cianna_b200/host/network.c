@@ -554,7 +554,7 @@ static int update_plan_enabled(void)
 
 /* (re)build the plan when the set of layers it covers may have changed: first use, a layer frozen / unfrozen, the
  * data-parallel world joined since */
-static void update_plan_refresh(network *net)
+static void update_plan_refresh(network *net, int skip_first)
 {
 	const cb200_conv_desc *descs[MAX_LAYERS_NB];
 	const cb200_conv_weights *ws[MAX_LAYERS_NB];
@@ -569,6 +569,7 @@ static void update_plan_refresh(network *net)
 		else if (l->type == NORM) sig = (sig ^ (unsigned)(size_t)((norm_param *)l->param)->gamma) * 16777619u;
 	}
 	sig = (sig ^ (unsigned)dp) * 16777619u;
+	sig = (sig ^ (unsigned)(skip_first ? 7 : 3)) * 16777619u;
 	sig = (sig ^ (unsigned)(size_t)net->grad_arena) * 16777619u;
 	if (sig == 0) sig = 1;
 	if (net->update_plan_sig == sig) return;
@@ -576,7 +577,7 @@ static void update_plan_refresh(network *net)
 	memset(net->in_update_plan, 0, sizeof(net->in_update_plan));
 	for (k = 0; k < net->nb_layers; k++) {
 		layer *l = net->net_layers[k];
-		if (l->frozen) continue;
+		if (l->frozen || (skip_first && k == 0)) continue;
 		if (l->type == CONV) {
 			conv_param *p = (conv_param *)l->param;
 			if (!cb200_update_plan_accepts(&p->desc)) continue;
@@ -597,9 +598,67 @@ static void update_plan_refresh(network *net)
 	net->update_plan_sig = sig;
 }
 
+static void update_one_layer(network *net, layer *l)
+{
+	if (l->type == CONV) {
+		conv_param *p = (conv_param *)l->param;
+		CB_CHECK(cb200_conv_update(&p->desc, &p->w, net->hyper_dev, 0, NULL));
+	} else if (l->type == DENSE) {
+		dense_param *p = (dense_param *)l->param;
+		CB_CHECK(cb200_dense_update(&p->desc, &p->w, net->hyper_dev, NULL));
+	} else if (l->type == NORM) {
+		norm_param *p = (norm_param *)l->param;
+		if (cb200_dp_world() > 1)
+			CB_CHECK(cb200_norm_update(&p->desc, p->gamma, p->beta, p->gamma_update, p->beta_update, p->gsum, net->hyper_dev, NULL));
+		else
+			CB_CHECK(cb200_norm_reduce_update(&p->desc, p->d_gamma, p->d_beta, p->gsum, p->gamma, p->beta, p->gamma_update,
+				p->beta_update, net->hyper_dev, NULL));
+	}
+}
+
+static int early_updates_enabled(void)
+{
+	static int on = -1;
+	if (on < 0) { const char *e = getenv("CB200_EARLY_UPDATES"); on = (e != NULL && e[0] == '0') ? 0 : 1; }
+	return on;
+}
+
+/* backward_pass calls this right before the FIRST layer's backprop: from here on the side stream only receives that
+ * layer's weight gradient */
+static void mark_upper_wgrads(network *net)
+{
+	layer *first = net->net_layers[0];
+	net->upper_marked = 0;
+	if (net->wgrad_stream == NULL || net->dp_world > 1 || net->perf_sample || net->nb_layers < 2 || !early_updates_enabled()) return;
+	if (first->type != CONV || first->frozen) return;
+	if (net->upper_ev == NULL) CB_CHECK(cb200_event_create(&net->upper_ev));
+	CB_CHECK(cb200_event_record(net->upper_ev, net->wgrad_stream));
+	net->upper_marked = 1;
+}
+
 static void apply_updates(network *net)
 {
 	int k, planned = 0;
+	if (net->upper_marked) {
+		/* every layer above the first: their gradients are complete at `upper_ev` (side stream) / in stream order (compute
+		 * stream); these launches overlap the first layer's weight gradient, which is joined afterwards */
+		net->upper_marked = 0;
+		CB_CHECK(cb200_stream_wait_event(NULL, net->upper_ev));
+		perf_mark(net, 2, 0);
+		if (update_plan_enabled()) {
+			update_plan_refresh(net, 1);
+			if (net->update_plan != NULL) { CB_CHECK(cb200_update_plan_run(net->update_plan, net->hyper_dev, NULL)); planned = 1; }
+		}
+		for (k = 1; k < net->nb_layers; k++) {
+			layer *l = net->net_layers[k];
+			if (l->frozen || (planned && net->in_update_plan[k])) continue;
+			update_one_layer(net, l);
+		}
+		CB_CHECK(cb200_stream_wait(NULL, net->wgrad_stream));      /* the first layer's weight gradient */
+		update_one_layer(net, net->net_layers[0]);
+		perf_mark(net, 2, net->nb_layers);
+		return;
+	}
 	if (net->wgrad_stream != NULL) CB_CHECK(cb200_stream_wait(NULL, net->wgrad_stream));   /* all weight gradients are in */
 	if (net->dp_world > 1) {
 		/* a network without conv / dense layers below its norm layers has no trigger layer: exchange the head now */
@@ -611,7 +670,7 @@ static void apply_updates(network *net)
 	/* every eligible conv layer and every group-norm layer in three launches (update_plan.cu); a perf_eval sample keeps
 	 * the layer-by-layer calls so that every kernel lands between its own layer's events */
 	if (!net->perf_sample && update_plan_enabled()) {
-		update_plan_refresh(net);
+		update_plan_refresh(net, 0);
 		if (net->update_plan != NULL) {
 			CB_CHECK(cb200_update_plan_run(net->update_plan, net->hyper_dev, NULL));
 			planned = 1;
@@ -645,6 +704,7 @@ static void backward_pass(network *net, const void *target_dev)
 	perf_mark(net, 1, 0);
 	output_deriv_error(net, target_dev);
 	for (k = net->nb_layers - 1; k >= 0; k--) {
+		if (k == 0) mark_upper_wgrads(net);
 		net->net_layers[k]->backprop(net->net_layers[k]);
 		perf_mark(net, 1, net->nb_layers - k);
 	}

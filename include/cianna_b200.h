@@ -112,6 +112,7 @@ int  cb200_stream_wait(void* stream, void* on_stream);
 int  cb200_event_create(void** ev);
 int  cb200_event_destroy(void* ev);
 int  cb200_event_record(void* ev, void* stream);
+int  cb200_stream_wait_event(void* stream, void* ev);   /* work queued on `stream` after this call waits for the event */
 int  cb200_event_sync(void* ev);                      /* host waits for the work recorded before the event */
 int  cb200_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);  /* synchronises on ev_stop */
 
