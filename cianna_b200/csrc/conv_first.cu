@@ -236,6 +236,9 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 		if (lane == 0) {
 			mbar_arrive_expect_tx(bfull_bar, Cfg::B_BYTES);
 			tma_load_3d(b_smem, &tmap_b, bfull_bar, 0, 0, 0);
+		}
+		__syncwarp();
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (conv_tc.cu: conv_halo_kernel)
 			mbar_wait(bfull_bar, 0);
 			for (int it = 0; it < n_tiles; it++) {
 				const int stage = it % Cfg::STAGES, acc = it % Cfg::ACC_STAGES;
@@ -249,10 +252,10 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 				for (int kk = 0; kk < KP / 16; kk++) {
 					const uint64_t da = make_smem_desc(sa + kk * 32, 16, PC::SBO, PC::LAYOUT);
 					const uint64_t db = make_smem_desc(b_smem + kk * 32, 16, PC::SBO, PC::LAYOUT);
-					mma_f16_ss(d_tmem, da, db, p.idesc, kk != 0 ? 1u : 0u);
+					mma_f16_ss_warp(d_tmem, da, db, p.idesc, kk != 0 ? 1u : 0u);
 				}
-				mma_commit(empty_bar(stage));
-				mma_commit(tfull_bar(acc));
+				mma_commit_warp(empty_bar(stage));
+				mma_commit_warp(tfull_bar(acc));
 			}
 		}
 	} else {
@@ -473,7 +476,7 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 			}
 		}
 	} else if (warp == 1) {
-		if (lane == 0) {
+		{      // the whole warp, converged (see above)
 			const uint64_t da_proto = p.wg_narrow ? make_smem_desc(0, 0, 512, 4) : make_smem_desc(0, Cfg::A_SLAB_BYTES, 1024, 2);
 			const uint32_t a_kstep = (p.wg_narrow ? 16 * 64 : 16 * 128) >> 4;      // 16 pixels further down the slab
 			const uint64_t db_proto = make_smem_desc(0, Cfg::B_BYTES, PC::SBO, PC::LAYOUT);
@@ -487,10 +490,10 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 				const uint64_t da = da_proto + (sa >> 4), db = db_proto + ((sa + Cfg::A_BYTES) >> 4);
 #pragma unroll
 				for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
-					mma_f16_ss(tmem_base, da + kk * a_kstep, db + ((kk * 16 * PC::ROW_BYTES) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
-				mma_commit(empty_bar(stage));
+					mma_f16_ss_warp(tmem_base, da + kk * a_kstep, db + ((kk * 16 * PC::ROW_BYTES) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
+				mma_commit_warp(empty_bar(stage));
 			}
-			mma_commit(done_bar);
+			mma_commit_warp(done_bar);
 		}
 	} else if (warp < 6) {
 		if (n_steps > 0) {

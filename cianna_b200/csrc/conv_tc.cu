@@ -514,7 +514,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 		}
 	} else if (warp == 1) {
 		// ===================== MMA issuer =====================
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (see conv_halo_kernel)
 			int stage = 0; uint32_t phase = 0;
 			int acc = 0; uint32_t acc_phase = 0;
 			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
@@ -533,12 +533,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 					const uint64_t db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
 					for (int kk = 0; kk < BK / 16; kk++)
-						mma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-					if (cluster) mma_commit_multicast(empty_bar(stage), (uint16_t)3);   // frees the slot in both CTAs
-					else mma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+						mma_f16_ss_warp(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+					if (cluster) mma_commit_multicast_warp(empty_bar(stage), (uint16_t)3);   // frees the slot in both CTAs
+					else mma_commit_warp(empty_bar(stage));          // frees the smem slot when these MMAs retire
 					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 				}
-				mma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
+				mma_commit_warp(tfull_bar(acc));                // accumulator complete -> epilogue
 				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
 			}
 		}
@@ -647,7 +647,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 		}
 	} else if (warp == 1) {
 		// ===================== MMA issuer (leader CTA only) =====================
-		if (lane == 0 && rank == 0) {
+		if (rank == 0) {      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (see conv_halo_kernel)
 			int stage = 0; uint32_t phase = 0;
 			int acc = 0; uint32_t acc_phase = 0;
 			const uint64_t desc_proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
@@ -664,11 +664,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 					const uint64_t db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
 					for (int kk = 0; kk < BK / 16; kk++)
-						mma_f16_ss_pair(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-					mma_commit_pair(empty_bar(stage), (uint16_t)3);      // frees the slot in both CTAs
+						mma_f16_ss_pair_warp(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+					mma_commit_pair_warp(empty_bar(stage), (uint16_t)3);      // frees the slot in both CTAs
 					if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 				}
-				mma_commit_pair(tfull_bar(acc), (uint16_t)3);           // both CTAs' accumulator halves are complete
+				mma_commit_pair_warp(tfull_bar(acc), (uint16_t)3);           // both CTAs' accumulator halves are complete
 				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
 			}
 		}
@@ -895,7 +895,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 		}
 	} else if (warp == 2) {
 		// ===================== MMA issuer =====================
-		if (lane == 0) {
+		// The WHOLE warp walks this loop converged, with identical values, and elect.sync inside the asm picks the issuing lane
+		// (sm100_ptx.cuh: mma_f16_ss_warp): written as `if (lane == 0) { loop }` every operand lives in a per-thread register and the compiler wraps each
+		// UTCHMMA in an elect / branch "waterfall" (ELECT, 2 x PLOP3, BRA.U.ANY, R2UR: ~70 clocks per issue in the ncu source
+		// view) - with 36 small MMAs per tile the issuing thread, not the tensor pipe, bounded the 224 px layers.
+		{
 			mbar_wait(bfull_bar, 0);
 			int stage = 0; uint32_t phase = 0;
 			int acc = 0; uint32_t acc_phase = 0;
@@ -923,13 +927,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 						const uint64_t da_t = da0 + (((uint32_t)((tap / FS) * HALO_W + (tap % FS)) * ROWB) >> 4);
 #pragma unroll
 						for (int kk = 0; kk < BK / 16; kk++)
-							mma_f16_ss(d_tmem, da_t + 2 * kk, db_t + 2 * kk, idesc, (tap | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
+							mma_f16_ss_warp(d_tmem, da_t + 2 * kk, db_t + 2 * kk, idesc, (tap | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
 						db_t += b_tap_step;
 					}
-					mma_commit(empty_bar(stage));
+					mma_commit_warp(empty_bar(stage));
 					if (++stage == a_stages) { stage = 0; phase ^= 1u; }
 				}
-				mma_commit(tfull_bar(acc));
+				mma_commit_warp(tfull_bar(acc));
 				if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
 			}
 		}
@@ -1285,7 +1289,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 			}
 		}
 	} else if (warp == 1) {
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (see conv_halo_kernel)
 			int stage = 0; uint32_t phase = 0;
 			const uint64_t da_proto = make_smem_desc(0, Cfg::A_SLAB_BYTES, 1024, 2);
 			const uint64_t db_proto = make_smem_desc(0, Cfg::B_SLAB_BYTES, 8 * Cfg::B_ROW_BYTES, Cfg::B_LAYOUT);
@@ -1307,16 +1311,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 					for (int ti = 0; ti < ntap; ti++) {
 #pragma unroll
 						for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
-							mma_f16_ss(d_tmem, da_s + ((mf * Cfg::A_BYTES + kk * 2048) >> 4), db_t + ((kk * 16 * Cfg::B_ROW_BYTES) >> 4), idesc,
+							mma_f16_ss_warp(d_tmem, da_s + ((mf * Cfg::A_BYTES + kk * 2048) >> 4), db_t + ((kk * 16 * Cfg::B_ROW_BYTES) >> 4), idesc,
 							           kk != 0 ? 1u : accum);
 						db_t += Cfg::B_BYTES >> 4;
 						d_tmem += BNC;
 					}
 				}
-				mma_commit(empty_bar(stage));
+				mma_commit_warp(empty_bar(stage));
 				if (++stage == stages) { stage = 0; phase ^= 1u; }
 			}
-			mma_commit(done_bar);
+			mma_commit_warp(done_bar);
 		}
 	} else if (n_steps > 0) {
 		const int quad = warp & 3;
@@ -1447,7 +1451,7 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 			}
 		}
 	} else if (warp == 1) {
-		if (lane == 0 && rank == 0) {
+		if (rank == 0) {      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (see conv_halo_kernel)
 			int stage = 0; uint32_t phase = 0;
 			const uint64_t d_proto = make_smem_desc(0, Cfg::SLAB_BYTES, 1024, 2);      // MN-major: channel slabs -> LBO, 8 pixel rows -> SBO
 			const uint32_t idesc = p.idesc;                                            // M = 256, N = 256
@@ -1462,14 +1466,14 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 				for (int ti = 0; ti < ntap; ti++) {
 #pragma unroll
 					for (int kk = 0; kk < Cfg::KPIX / 16; kk++)
-						mma_f16_ss_pair(d_tmem, da_s + ((kk * 2048) >> 4), db_t + ((kk * 2048) >> 4), idesc, kk != 0 ? 1u : accum);
+						mma_f16_ss_pair_warp(d_tmem, da_s + ((kk * 2048) >> 4), db_t + ((kk * 2048) >> 4), idesc, kk != 0 ? 1u : accum);
 					db_t += Cfg::B_BYTES >> 4;
 					d_tmem += Cfg::BNC;
 				}
-				mma_commit_pair(empty_bar(stage), (uint16_t)3);
+				mma_commit_pair_warp(empty_bar(stage), (uint16_t)3);
 				if (++stage == stages) { stage = 0; phase ^= 1u; }
 			}
-			mma_commit_pair(done_bar, (uint16_t)3);
+			mma_commit_pair_warp(done_bar, (uint16_t)3);
 		}
 	} else if (n_steps > 0) {
 		const int quad = warp & 3;
@@ -1600,7 +1604,7 @@ conv_wgrad_swap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 			}
 		}
 	} else if (warp == 1) {
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (see conv_halo_kernel)
 			int stage = 0; uint32_t phase = 0;
 			// both operands MN-major (pixels are the contraction index): 8 pixel rows per K group -> SBO, channel slabs -> LBO
 			const uint64_t da_proto = make_smem_desc(0, Cfg::X_TILE, 8 * Cfg::X_ROW, Cfg::X_LAYOUT);
@@ -1618,12 +1622,12 @@ conv_wgrad_swap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 #pragma unroll
 					for (int i = 0; i < Cfg::NACC; i++)
 						if (i < n_mma)
-							mma_f16_ss(tmem_base + (uint32_t)(i * NF), da_s + ((i * Cfg::SLOTS * Cfg::X_TILE + kk * 16 * Cfg::X_ROW) >> 4),
+							mma_f16_ss_warp(tmem_base + (uint32_t)(i * NF), da_s + ((i * Cfg::SLOTS * Cfg::X_TILE + kk * 16 * Cfg::X_ROW) >> 4),
 							           db_s + ((kk * 16 * 128) >> 4), idesc, (k | kk) != 0 ? 1u : 0u);
-				mma_commit(empty_bar(stage));
+				mma_commit_warp(empty_bar(stage));
 				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 			}
-			mma_commit(done_bar);
+			mma_commit_warp(done_bar);
 		}
 	} else if (n_steps > 0) {
 		const int quad = warp & 3;                // accumulator row quad*32 + lane = (tap slot row / C, channel row % C)

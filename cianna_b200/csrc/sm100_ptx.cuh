@@ -93,6 +93,52 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
 		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
 		"}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same two instructions for a warp that walks its issue loop CONVERGED (all 32 lanes, identical operands): one lane,
+// chosen by elect.sync inside the asm, issues.  Called under `if (lane == 0)` the plain forms above make the compiler
+// wrap every UTCHMMA in an elect / branch waterfall (its operands are per-thread registers that may differ between
+// lanes); here the operands are provably uniform and the instruction is just predicated.
+__device__ __forceinline__ void mma_f16_ss_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred p, q;\n\t"
+		"elect.sync _|q, 0xffffffff;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+		"}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_warp(uint32_t bar) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred q;\n\t"
+		"elect.sync _|q, 0xffffffff;\n\t"
+		"@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+		"}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit_multicast_warp(uint32_t bar, uint16_t cta_mask) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred q;\n\t"
+		"elect.sync _|q, 0xffffffff;\n\t"
+		"@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+		"}" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_pair_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred p, q;\n\t"
+		"elect.sync _|q, 0xffffffff;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+		"}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_warp(uint32_t bar, uint16_t cta_mask) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred q;\n\t"
+		"elect.sync _|q, 0xffffffff;\n\t"
+		"@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+		"}" ::"r"(bar), "h"(cta_mask) : "memory");
+}
 // arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
