@@ -487,7 +487,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 	if (warp == 0) {
 		// ===================== TMA producer =====================
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane (see conv_halo_kernel's MMA warp)
 			int stage = 0; uint32_t phase = 0;
 			const TileRun run = tile_run(p);
 			for (int ti = 0, tile = run.first; ti < run.count; ti++, tile += run.step) {
@@ -500,13 +500,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 					for (int cb = 0; cb < p.kc_blocks; cb++) {
 						mbar_wait(empty_bar(stage), phase ^ 1u);
 						const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-						mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-						tma_load_4d(sa, &tmap_a, full_bar(stage), cb * BK, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
-						if (p.cluster)     // this CTA's half of the filter block, to both CTAs (tmap_b boxes are BN/2 rows here)
-							tma_load_3d_multicast(sb + rank * (Cfg::B_BYTES / 2), &tmap_b, full_bar(stage), cb * BK, tap + p.w_tap0,
-							                      nt * BN + (int)rank * (BN / 2), (uint16_t)3);
-						else
-							tma_load_3d(sb, &tmap_b, full_bar(stage), cb * BK, tap + p.w_tap0, nt * BN);
+						mbar_arrive_expect_tx_warp(full_bar(stage), Cfg::STAGE_BYTES);
+						tma_load_4d_warp(sa, &tmap_a, full_bar(stage), cb * BK, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
+						if (p.cluster) {   // this CTA's half of the filter block, to both CTAs (tmap_b boxes are BN/2 rows here)
+							if (lane == 0)
+								tma_load_3d_multicast(sb + rank * (Cfg::B_BYTES / 2), &tmap_b, full_bar(stage), cb * BK, tap + p.w_tap0,
+								                      nt * BN + (int)rank * (BN / 2), (uint16_t)3);
+							__syncwarp();
+						} else
+							tma_load_3d_warp(sb, &tmap_b, full_bar(stage), cb * BK, tap + p.w_tap0, nt * BN);
 						if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 					}
 				}
@@ -622,7 +624,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
 	if (warp == 0) {
 		// ===================== TMA producer (both CTAs) =====================
-		if (lane == 0) {
+		{      // the whole warp, converged (see above)
 			int stage = 0; uint32_t phase = 0;
 			const uint32_t lead_full0 = mapa_rank(full_bar(0), 0);
 			const TileRun run = tile_run(p);
@@ -636,10 +638,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 					for (int cb = 0; cb < p.kc_blocks; cb++) {
 						mbar_wait(empty_bar(stage), phase ^ 1u);
 						const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-						if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+						if (rank == 0) mbar_arrive_expect_tx_warp(full_bar(stage), 2 * Cfg::STAGE_BYTES);
 						const uint32_t lead_full = lead_full0 + 8u * stage;
-						tma_load_4d_pair(sa, &tmap_a, lead_full, cb * BK, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
-						tma_load_3d_pair(sb, &tmap_b, lead_full, cb * BK, tap + p.w_tap0, nt * BN + (int)rank * (BN / 2));
+						tma_load_4d_pair_warp(sa, &tmap_a, lead_full, cb * BK, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
+						tma_load_3d_pair_warp(sb, &tmap_b, lead_full, cb * BK, tap + p.w_tap0, nt * BN + (int)rank * (BN / 2));
 						if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 					}
 				}
@@ -871,16 +873,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 	if (warp == 0) {
 		// ===================== halo producer: one TMA box per (tile, channel block) =====================
-		if (lane == 0) {
+		{      // the whole warp, converged (see the MMA warp below)
 			int stage = 0; uint32_t phase = 0;
 			const TileRun run = tile_run(p);
 			for (int ti = 0, tile = run.first; ti < run.count; ti++, tile += run.step) {
 				const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tni = tile / (p.tiles_w * p.tiles_h);
 				for (int cb = 0; cb < p.kc_blocks; cb++) {
 					mbar_wait(empty_bar(stage), phase ^ 1u);
-					mbar_arrive_expect_tx(full_bar(stage), a_tx);
-					tma_load_4d(smem_base + (uint32_t)(stage * p.a_stage_bytes), &tmap_a, full_bar(stage), cb * BK,
-					            twi * HALO_TW + p.off_w, thi * HALO_TH + p.off_h, tni);
+					mbar_arrive_expect_tx_warp(full_bar(stage), a_tx);
+					tma_load_4d_warp(smem_base + (uint32_t)(stage * p.a_stage_bytes), &tmap_a, full_bar(stage), cb * BK,
+					                 twi * HALO_TW + p.off_w, thi * HALO_TH + p.off_h, tni);
 					if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
 				}
 			}

@@ -49,6 +49,21 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// The same for a producer warp that walks its loop converged (all 32 lanes, identical operands): elect.sync inside the asm
+// picks the lane that issues (see mma_f16_ss_warp for why).
+#define CB200_ELECT_ASM(body) "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q " body "\n\t}"
+__device__ __forceinline__ void mbar_arrive_expect_tx_warp(uint32_t bar, uint32_t bytes) {
+	asm volatile(CB200_ELECT_ASM("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;") ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+	asm volatile(CB200_ELECT_ASM("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];")
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+	asm volatile(CB200_ELECT_ASM("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];")
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // TMA store of a shared-memory box (written by generic-proxy stores + fence.proxy.async) to global memory; elements of
 // the box outside the tensor are not written.  Bulk-group completion: commit, then wait_group(.read) before the buffer
 // is reused (.read: the source has been read) or before the data must be visible (no .read).
@@ -189,6 +204,14 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap
 }
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
 	asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2) {
+	asm volatile(CB200_ELECT_ASM("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];")
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+	asm volatile(CB200_ELECT_ASM("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];")
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 // one warp of EACH CTA of the pair
