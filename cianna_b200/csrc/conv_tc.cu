@@ -146,6 +146,7 @@ struct IgemmParams {
 	// split a tile index with multiply-high instead of four run-time integer divisions per tile (each a dependent chain of
 	// ~20 instructions through the reciprocal unit, on the critical path of a tile's epilogue)
 	unsigned long long mg_m, mg_w, mg_h, mg_wh;
+	int wide_store;              // 256-bit epilogue stores (CB200_WIDE_STORE=0: off)
 };
 // n / d through the magic number M = ceil(2^64 / d) (exact for 32-bit n and d: n * (M - 2^64 / d) < 2^64 / d); M == 0: d == 1
 static inline unsigned long long fastdiv_magic(int d) { return d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull; }
@@ -219,6 +220,13 @@ __device__ __forceinline__ float gn_butterfly(float (&s)[8], int nv, int seg, in
 	return v;
 }
 
+// one 256-bit store (STG.256, sm_100): two adjacent 8-channel packets of a pixel row.  With one pixel row per thread every
+// store instruction of a warp touches 32 different lines, and the LSU data pipe - 72 % busy in the layer-2 forward kernel -
+// is what the early layers' epilogues wait for: half as many store instructions per row.
+__device__ __forceinline__ void st256(void* p, const uint4& a, const uint4& b) {
+	asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+	             "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 template <typename T> __device__ __forceinline__ uint4 pack8(const float (&in)[8]);
 template <> __device__ __forceinline__ uint4 pack8<__half>(const float (&in)[8]) {
 	uint4 r;
@@ -258,6 +266,12 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
 	// 0 <= leak <= 1, sat >= 0: z <= 0 ? z*leak : (z > sat ? hi : z) == min(max(z, z*leak), hi) value for value
 	const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
+	// rows of a multiple of 16 channels leave in 32-byte stores (packets come in valid pairs: BN is a multiple of 16 too, and
+	// a strided output grid keeps rows 32-byte aligned since n_pad * 2 is a multiple of 32)
+	// Measured per layer shape (batch 128, same box A/B): rows of >= 128 channels gain (1x1 64 -> 128 data gradient at 112 px
+	// 212 -> 142 us, 3x3 64 -> 128 forward 238 -> 226 us), 32-channel rows do not care, 64-channel rows lose 3 % (layer-2
+	// forward 455 -> 471 us): on from 128 channels.
+	const bool wide_store = (n_pad & 15) == 0 && n_pad >= 128 && p.wide_store != 0;
 	float* bs = bias_rows + grp * 256;
 	// group-norm statistics (GN): one running sum per lane and 32-column chunk, see gn_butterfly.  They live in shared
 	// memory, one private column per thread (conflict-free), so that the chunk loop can stay rolled: fully unrolled for
@@ -331,6 +345,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 				for (int j = 0; j < 16; j++) { r[j] = h[j]; r[16 + j] = 0; } }
 			tmem_ld_wait();
 			const int col0 = nt * BN + c0;
+			uint4 keep = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
 			for (int v = 0; v < 4; v++) {
 				const int col = col0 + v * 8;
@@ -389,7 +404,9 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 					// round once, store those bits, and sum what was stored
 					Raw8<T> pk;
 					pk.a = pack8<T>(o);
-					*reinterpret_cast<uint4*>(out + pix * n_pad + col) = pk.a;
+					if (!wide_store) *reinterpret_cast<uint4*>(out + pix * n_pad + col) = pk.a;
+					else if ((v & 1) == 0) keep = pk.a;
+					else st256(out + pix * n_pad + col - 8, keep, pk.a);
 					float q[8];
 					unpack8(pk, q);
 #pragma unroll
@@ -399,6 +416,10 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 					const int sw_x = BN == 32 ? ((row >> 1) & 3) : (row & 7);
 					const int chunk = (((c0 >> 3) + v) ^ sw_x) & (BN / 8 - 1);
 					store8<T>(reinterpret_cast<T*>(stg_ptr + row * (BN * 2) + chunk * 16), o);
+				} else if (wide_store) {
+					const uint4 pk = pack8<T>(o);
+					if ((v & 1) == 0) keep = pk;
+					else st256(out + pix * n_pad + col - 8, keep, pk);
 				} else
 				store8<T>(out + pix * n_pad + col, o);
 			}
@@ -1054,6 +1075,8 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	if (gn_fused) *gn_fused = 0;
 	static const int diag = getenv("CB200_TILE_DIAG") ? atoi(getenv("CB200_TILE_DIAG")) : 0;   // 1: contiguous tile runs everywhere (measurement only)
 	if (diag & 1) p.contig = 1;
+	static const bool no_wide_store = getenv("CB200_WIDE_STORE") != nullptr && getenv("CB200_WIDE_STORE")[0] == '0';
+	p.wide_store = no_wide_store ? 0 : 1;
 	if (p.stride < 1) p.stride = 1;
 	if (p.out_s < 1) { p.out_s = 1; p.out_ox = 0; p.out_oy = 0; p.out_W = out_w; p.out_H = out_h; }
 	const int w_taps = p.w_taps > 0 ? p.w_taps : f_h * f_w;
