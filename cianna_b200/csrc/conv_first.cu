@@ -462,7 +462,7 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 	const int n_steps = t_end > t_begin ? t_end - t_begin : 0;
 
 	if (warp == 0) {
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane
 			for (int k = 0; k < n_steps; k++) {
 				const int t = t_begin + k;
 				const int stage = k % Cfg::STAGES;
@@ -470,9 +470,9 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const First
 				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
 				mbar_wait(empty_bar(stage), phase ^ 1u);
 				const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-				mbar_arrive_expect_tx(full_bar(stage), p.wg_narrow ? Cfg::KPIX * 64 : Cfg::A_BYTES);
-				tma_load_4d(sa, &tmap_dy, full_bar(stage), 0, twi * p.tw, thi * p.th, tni * p.tn);
-				if (!p.wg_narrow) tma_load_4d(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), 64, twi * p.tw, thi * p.th, tni * p.tn);
+				mbar_arrive_expect_tx_warp(full_bar(stage), p.wg_narrow ? Cfg::KPIX * 64 : Cfg::A_BYTES);
+				tma_load_4d_warp(sa, &tmap_dy, full_bar(stage), 0, twi * p.tw, thi * p.th, tni * p.tn);
+				if (!p.wg_narrow) tma_load_4d_warp(sa + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), 64, twi * p.tw, thi * p.th, tni * p.tn);
 			}
 		}
 	} else if (warp == 1) {

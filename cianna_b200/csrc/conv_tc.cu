@@ -1288,26 +1288,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 	const int n_steps = t_end - t_begin;
 
 	if (warp == 0) {
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane
 			int stage = 0; uint32_t phase = 0;
 			for (int t = t_begin; t < t_end; t++) {
 				const int twi = t % p.tiles_w, thi = (t / p.tiles_w) % p.tiles_h, tni = t / (p.tiles_w * p.tiles_h);
 				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
 				mbar_wait(empty_bar(stage), phase ^ 1u);
 				const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + MF * Cfg::A_BYTES;
-				mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+				mbar_arrive_expect_tx_warp(full_bar(stage), tx_bytes);
 #pragma unroll
 				for (int mf = 0; mf < MF; mf++) {
 					const int ch0 = (fg * MF + mf) * 128;
-					tma_load_4d(sa + mf * Cfg::A_BYTES, &tmap_dy, full_bar(stage), ch0, w0, h0, n0);
-					tma_load_4d(sa + mf * Cfg::A_BYTES + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), ch0 + 64, w0, h0, n0);
+					tma_load_4d_warp(sa + mf * Cfg::A_BYTES, &tmap_dy, full_bar(stage), ch0, w0, h0, n0);
+					tma_load_4d_warp(sa + mf * Cfg::A_BYTES + Cfg::A_SLAB_BYTES, &tmap_dy, full_bar(stage), ch0 + 64, w0, h0, n0);
 				}
 				for (int ti = 0; ti < ntap; ti++) {
 					const int tap = tap0 + ti;
 					const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
 #pragma unroll
 					for (int sl = 0; sl < Cfg::B_SLABS; sl++)
-						tma_load_4d(sb + ti * Cfg::B_BYTES + sl * Cfg::B_SLAB_BYTES, &tmap_x, full_bar(stage),
+						tma_load_4d_warp(sb + ti * Cfg::B_BYTES + sl * Cfg::B_SLAB_BYTES, &tmap_x, full_bar(stage),
 						            ct * BNC + sl * SLAB_C, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
 				}
 				if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -1450,7 +1450,7 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 	const int n_steps = t_end - t_begin;
 
 	if (warp == 0) {
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane
 			int stage = 0; uint32_t phase = 0;
 			const uint32_t lead_full0 = mapa_rank(full_bar(0), 0);
 			const int ch0 = (fg * 2 + (int)rank) * 128;                    // this CTA's output channels
@@ -1460,16 +1460,16 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
 				mbar_wait(empty_bar(stage), phase ^ 1u);
 				const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + Cfg::A_BYTES;
-				if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+				if (rank == 0) mbar_arrive_expect_tx_warp(full_bar(stage), tx_bytes);
 				const uint32_t lead_full = lead_full0 + 8u * stage;
-				tma_load_4d_pair(sa, &tmap_dy, lead_full, ch0, w0, h0, n0);
-				tma_load_4d_pair(sa + Cfg::SLAB_BYTES, &tmap_dy, lead_full, ch0 + 64, w0, h0, n0);
+				tma_load_4d_pair_warp(sa, &tmap_dy, lead_full, ch0, w0, h0, n0);
+				tma_load_4d_pair_warp(sa + Cfg::SLAB_BYTES, &tmap_dy, lead_full, ch0 + 64, w0, h0, n0);
 				for (int ti = 0; ti < ntap; ti++) {
 					const int tap = tap0 + ti;
 					const int ky = tap / p.f_w, kx = tap - ky * p.f_w;
 #pragma unroll
 					for (int sl = 0; sl < 2; sl++)
-						tma_load_4d_pair(sb + ti * Cfg::B_BYTES + sl * Cfg::SLAB_BYTES, &tmap_x, lead_full,
+						tma_load_4d_pair_warp(sb + ti * Cfg::B_BYTES + sl * Cfg::SLAB_BYTES, &tmap_x, lead_full,
 						                 xc0 + sl * 64, w0 * p.stride + kx + p.off_w, h0 * p.stride + ky + p.off_h, n0);
 				}
 				if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -1608,7 +1608,7 @@ conv_wgrad_swap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 	const int n_mma = (ntap + Cfg::SLOTS - 1) / Cfg::SLOTS;
 
 	if (warp == 0) {
-		if (lane == 0) {
+		{      // the whole warp, converged: elect.sync inside the asm picks the issuing lane
 			int stage = 0; uint32_t phase = 0;
 			const uint32_t tx_bytes = (uint32_t)(Cfg::DY_BYTES + ntap * Cfg::X_TILE);
 			int tap_dx[Cfg::MAXT], tap_dy[Cfg::MAXT];       // pixel offset of this CTA's taps (registers once unrolled)
@@ -1619,12 +1619,12 @@ conv_wgrad_swap_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid
 				const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
 				mbar_wait(empty_bar(stage), phase ^ 1u);
 				const uint32_t sd = smem_base + stage * Cfg::STAGE_BYTES, sx = sd + Cfg::DY_BYTES;
-				mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+				mbar_arrive_expect_tx_warp(full_bar(stage), tx_bytes);
 #pragma unroll
-				for (int sl = 0; sl < NF / 64; sl++) tma_load_4d(sd + sl * Cfg::DY_SLAB, &tmap_dy, full_bar(stage), sl * 64, w0, h0, n0);
+				for (int sl = 0; sl < NF / 64; sl++) tma_load_4d_warp(sd + sl * Cfg::DY_SLAB, &tmap_dy, full_bar(stage), sl * 64, w0, h0, n0);
 #pragma unroll
 				for (int s = 0; s < Cfg::MAXT; s++)
-					if (s < ntap) tma_load_4d(sx + s * Cfg::X_TILE, &tmap_x, full_bar(stage), 0, w0 + tap_dx[s], h0 + tap_dy[s], n0);
+					if (s < ntap) tma_load_4d_warp(sx + s * Cfg::X_TILE, &tmap_x, full_bar(stage), 0, w0 + tap_dx[s], h0 + tap_dy[s], n0);
 				if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
 			}
 		}
