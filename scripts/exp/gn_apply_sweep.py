@@ -17,7 +17,7 @@ REPS = 5
 SHAPES = [(32, 448, 4, True), (64, 224, 8, True), (128, 112, 8, False), (128, 112, 8, True), (64, 112, 8, False), (256, 56, 16, False),
           (256, 56, 16, True), (128, 56, 16, False), (512, 28, 16, False), (512, 28, 16, True), (256, 28, 16, False), (1024, 14, 32, False), (512, 14, 16, False)]
 COUNT = [1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 2, 3, 2]      # how often the shape occurs in Darknet19
-KNOBS = [(8, 4096), (8, 1024), (8, 8192), (6, 4096)]
+KNOBS = [(8, 4096)]
 
 
 def timed(L, fn):
