@@ -147,6 +147,7 @@ struct IgemmParams {
 	// ~20 instructions through the reciprocal unit, on the critical path of a tile's epilogue)
 	unsigned long long mg_m, mg_w, mg_h, mg_wh;
 	int wide_store;              // 256-bit epilogue stores (CB200_WIDE_STORE=0: off)
+	int bias_once;               // single N tile: bias row staged once per CTA instead of per tile (CB200_BIAS_ONCE=0: off)
 };
 // n / d through the magic number M = ceil(2^64 / d) (exact for 32-bit n and d: n * (M - 2^64 / d) < 2^64 / d); M == 0: d == 1
 static inline unsigned long long fastdiv_magic(int d) { return d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull; }
@@ -302,6 +303,8 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		}
 	};
 	const TileRun run = tile_run(p);
+	const bool bias_once = p.tiles_nn == 1 && p.bias_once != 0;
+	bool bias_staged = false;
 	int it = 0;
 	for (int tile = run.first; it < run.count; tile += run.step, it++) {
 		if ((it % NGROUPS) != grp) continue;
@@ -321,12 +324,17 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 		const bool row_ok = px < PW && py < PH && pn < PN;
 		const size_t pix = ((size_t)pn * OH + (py * out_s + out_oy)) * OW + (px * out_s + out_ox);
 		const bool dead = mask_tail && pn >= length;
-		if (TMA_OUT && lane == 0) bulk_wait_read0();                       // this warp's previous rows have left the staging buffer
-		// per-tile bias row (bias_value * W[f][bias column]) staged once in shared memory by the group
-		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
-		if (mode == 0)
-			for (int c = gtid; c < BN; c += 128) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
-		asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+		if (TMA_OUT) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }  // this warp's previous rows have left the staging buffer
+		// bias row (bias_value * W[f][bias column]) of the tile's output channels, staged in shared memory by the group: once
+		// for the whole run when there is a single N tile (two group barriers less in every tile's latency chain - the early
+		// layers are bound by that chain), else per tile
+		if (!bias_once || !bias_staged) {
+			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous tile's readers are done
+			if (mode == 0)
+				for (int c = gtid; c < BN; c += 128) { const int ch = nt * BN + c; bs[c] = ch < n_real ? bias_value * __ldg(bias_w + ch) : 0.0f; }
+			asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+			bias_staged = true;
+		}
 
 		mbar_wait(tfull0 + 8u * acc, acc_phase);
 		tc_fence_after();
@@ -1077,6 +1085,8 @@ static int run_igemm(int dtype, const void* src, int cin_p, int in_h, int in_w, 
 	if (diag & 1) p.contig = 1;
 	static const bool no_wide_store = getenv("CB200_WIDE_STORE") != nullptr && getenv("CB200_WIDE_STORE")[0] == '0';
 	p.wide_store = no_wide_store ? 0 : 1;
+	static const bool no_bias_once = getenv("CB200_BIAS_ONCE") != nullptr && getenv("CB200_BIAS_ONCE")[0] == '0';
+	p.bias_once = no_bias_once ? 0 : 1;
 	if (p.stride < 1) p.stride = 1;
 	if (p.out_s < 1) { p.out_s = 1; p.out_ox = 0; p.out_oy = 0; p.out_W = out_w; p.out_H = out_h; }
 	const int w_taps = p.w_taps > 0 ? p.w_taps : f_h * f_w;
