@@ -21,7 +21,7 @@ int conv_dgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*
 int conv_wgrad_tc(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
 // first layer straight from the dataset batch, patch rows built in shared memory (conv_first.cu)
 bool conv_first_supported(const cb200_conv_desc*);
-int conv_first_forward(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t);
+int conv_first_forward(const cb200_conv_desc*, const cb200_conv_weights*, const void*, void*, cudaStream_t, const cb200_norm_desc*, void*, int*);
 int conv_first_wgrad(const cb200_conv_desc*, const cb200_conv_weights*, const void*, const void*, cudaStream_t);
 
 // master [out_c][taps*in_c + 1] (column = c*taps + tap, bias last) -> compute operands.
@@ -378,7 +378,7 @@ int cb200_conv_forward_stats(const cb200_conv_desc* d_in, const cb200_conv_weigh
 		if (!conv_first_supported(d_in)) { set_error("cb200_conv_forward: input_is_patches = 2 is not available for this layer (cb200_conv_first_direct)"); return CB200_ERR_UNSUPPORTED; }
 		g_last_conv_impl = "tcgen05";
 		prof_begin(PROF_CONV_FWD_TC, flops, as_stream(s));
-		rc = conv_first_forward(d_in, w, x, y, as_stream(s));
+		rc = conv_first_forward(d_in, w, x, y, as_stream(s), gn, gn_workspace, stats_done);
 		prof_end(as_stream(s));
 		return rc;
 	}

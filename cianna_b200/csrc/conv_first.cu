@@ -47,6 +47,11 @@ struct FirstParams {
 	// of two 64-filter boxes of which three quarters are zero fill (16 KB written per step), and the M = 128 MMA reads
 	// that 32-row atom four times (leading byte offset 0: accumulator rows 32..127 repeat rows 0..31 and are never read)
 	int wg_narrow;
+	// forward: group-norm sums of the layer output out of the epilogue (conv_first_forward): FP64 workspace
+	// [N][gn_groups][2] = (sum, sum of squares) of the group-norm layer that follows, its group size and group count
+	double* gn_ws;
+	int gn_groups;
+	uint32_t gn_map;             // group of columns 4i..4i+3 in nibble i (i = 0..7)
 };
 
 template <int KP> struct PatchCfg {
@@ -164,7 +169,7 @@ template <int KP, int BN> struct FirstFwdCfg {
 	static constexpr int SMEM_BYTES = STAGES * A_BYTES + ((B_BYTES + 1023) & ~1023) + 1024 + 1024 + FWD_EPI_GROUPS * OUT_TILE_BYTES;
 };
 
-template <typename T, int C, int FH, int FW, int KP, int BN>
+template <typename T, int C, int FH, int FW, int KP, int BN, bool GN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out, const FirstParams p) {
 	using Cfg = FirstFwdCfg<KP, BN>;
@@ -271,6 +276,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 		// below the saturation, hi < z above it) - two FMNMX instead of two compares and two selects per element: this
 		// epilogue is bound by the ALU pipe (profiles/r1_conv_first_fwd_full_raw.csv: 65 % busy)
 		const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
+		const float sat_c = sat - sat * leak;
 		const int rx = row % p.tw, ry = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
 		if (p.tma_store) {
 			// Output through shared memory: with one pixel row per thread a 128-bit global store of a warp touches 32
@@ -287,7 +293,32 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 			// instructions, and the kernel issues at 67 % of its slots once the builders prefetch)
 			const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
 			int twi = (tile0 + egrp) % tiles_w, thi = ((tile0 + egrp) / tiles_w) % tiles_h, tni = (tile0 + egrp) / (tiles_w * tiles_h);
-			for (int it = egrp; it < n_tiles; it += FWD_EPI_GROUPS) {
+			// Group-norm sums of the layer that follows (GN; every warp's 32 rows in ONE sample, BN = 32): the statistics pass over
+			// this layer's output is the largest of the network (1.6 GB at batch 128).  Every thread keeps (sum, sum of
+			// squares) of its pixel's columns 4i..4i+3, i = 0..7, as FP32 pairs fed by FADD2 / FFMA2 (one instruction per
+			// value); a warp folds them every 32 tiles or when the sample changes: butterfly over the lanes, then one FP64
+			// atomic per sum into the workspace of norm_stats_kernel (any group size that is a multiple of 4).  The values
+			// are the activated FP32 ones before the rounding to 16 bit (the sums differ from those of the stored tensor by
+			// the mean rounding error: < 1e-6 relative in FP16, < 1e-5 in BF16).
+			float gsum[GN ? BN / 4 : 1], gsq[GN ? BN / 4 : 1];
+#pragma unroll
+			for (int i = 0; i < (GN ? BN / 4 : 1); i++) { gsum[i] = 0.0f; gsq[i] = 0.0f; }
+			int gn_pn = -1, gn_cnt = 0;
+			auto gn_flush = [&]() {
+#pragma unroll
+				for (int i = 0; i < (GN ? BN / 4 : 1); i++) {
+					float a = gsum[i], b = gsq[i];
+#pragma unroll
+					for (int m = 16; m > 0; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); b += __shfl_xor_sync(0xffffffffu, b, m); }
+					const int g = (int)((p.gn_map >> (4 * i)) & 15u);
+					if ((lane >> 1) == i && g < p.gn_groups) {
+						const float v = (lane & 1) ? b : a;
+						if (v != 0.0f) atomicAdd(p.gn_ws + ((size_t)gn_pn * p.gn_groups + g) * 2 + (lane & 1), (double)v);
+					}
+					gsum[i] = 0.0f; gsq[i] = 0.0f;
+				}
+			};
+			for (int it = egrp; GN || it < n_tiles; it += FWD_EPI_GROUPS) {
 				const int acc = it % Cfg::ACC_STAGES;
 				const uint32_t acc_phase = (uint32_t)(it / Cfg::ACC_STAGES) & 1u;
 				const int c_twi = twi, c_thi = thi, c_tni = tni;
@@ -295,6 +326,17 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 				while (twi >= tiles_w) { twi -= tiles_w; if (++thi == tiles_h) { thi = 0; tni++; } }
 				const int pn = c_tni * p.tn + rn;
 				const bool dead = mask_tail && pn >= p.length;
+				bool gn_row = false;
+				if (GN) {      // (one flush site: the pass after the last tile only folds what is left)
+					const bool past = it >= n_tiles;
+					if (past || pn != gn_pn || gn_cnt == 32) {       // (pn is the same for the 32 rows of a warp: tw * th % 32 == 0)
+						if (gn_pn >= 0 && gn_pn < p.N) gn_flush();
+						gn_pn = pn; gn_cnt = 0;
+					}
+					if (past) break;
+					gn_cnt++;
+					gn_row = c_twi * p.tw + rx < p.W && c_thi * p.th + ry < p.H && pn < p.N;
+				}
 				mbar_wait(tfull_bar(acc), acc_phase);
 				tc_fence_after();
 				if (gtid == 0) bulk_wait_read0();                                    // the previous tile of this group has left the buffer
@@ -316,8 +358,10 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 							for (int j = 0; j < 8; j++) o[j] = 0.0f;
 						} else if (act == CB200_RELU) {
 							if (relu_minmax) {
+								// packed pairs (sm100_ptx.cuh: leaky_sat_f32x2): 3 instead of 5 issue slots per value in the warps
+								// that bound this kernel
 #pragma unroll
-								for (int j = 0; j < 8; j++) { const float z = o[j]; o[j] = fminf(fmaxf(z, z * leak), sat + (z - sat) * leak); }
+								for (int j = 0; j < 8; j += 2) leaky_sat_f32x2(o[j], o[j + 1], leak, sat_c);
 							} else {
 #pragma unroll
 								for (int j = 0; j < 8; j++) { const float z = o[j]; const float hi = sat + (z - sat) * leak; o[j] = z <= 0.0f ? z * leak : (z > sat ? hi : z); }
@@ -329,6 +373,15 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 						if (col + 8 > n_real) {
 #pragma unroll
 							for (int j = 0; j < 8; j++) if (col + j >= n_real) o[j] = 0.0f;
+						}
+						if (GN && gn_row) {
+							static_assert(!GN || BN == 32, "group-norm sums: one 32-column pass per tile");
+							const int h = 2 * v;                               // BN = 32: one pass of the c0 loop, columns 8v..8v+7
+#pragma unroll
+							for (int j = 0; j < 4; j++) {
+								add_f32x2(gsum[GN ? h : 0], gsum[GN ? h + 1 : 0], o[j], o[j + 4]);
+								sq_acc_f32x2(gsq[GN ? h : 0], gsq[GN ? h + 1 : 0], o[j], o[j + 4]);
+							}
 						}
 						const int chunk = ((col >> 3) ^ sw_x) & (CHUNKS - 1);
 						store8<T>(reinterpret_cast<T*>(stg_ptr + row * (BN * 2) + chunk * 16), o);
@@ -580,11 +633,11 @@ static void fill_params(const cb200_conv_desc* d, const void* src, int npix, Fir
 	p.prefetch = no_prefetch ? 0 : 1;
 }
 
-template <typename T, int C, int FH, int FW, int KP, int BN>
+template <typename T, int C, int FH, int FW, int KP, int BN, bool GN = false>
 static int launch_first_fwd(const CUtensorMap& mb, const CUtensorMap& mo, const FirstParams& p, int grid, cudaStream_t st) {
 	using Cfg = FirstFwdCfg<KP, BN>;
 	static bool configured = false;
-	auto kern = conv_first_fwd_kernel<T, C, FH, FW, KP, BN>;
+	auto kern = conv_first_fwd_kernel<T, C, FH, FW, KP, BN, GN>;
 	if (!configured) {
 		if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
 			set_error("cudaFuncSetAttribute(smem=%d) failed", Cfg::SMEM_BYTES); return CB200_ERR_CUDA;
@@ -619,7 +672,9 @@ static int first_fwd_typed(const cb200_conv_desc* d, const CUtensorMap& mb, cons
 	const int bn = p.n_pad > 32 ? 64 : 32;
 #define X(C_, FH_, FW_, KP_) \
 	if (d->in_c == C_ && d->f_h == FH_ && d->f_w == FW_) \
-		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, mo, p, grid, st) : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, mo, p, grid, st);
+		return bn == 64 ? launch_first_fwd<T, C_, FH_, FW_, KP_, 64>(mb, mo, p, grid, st) \
+		     : (p.gn_ws != nullptr ? launch_first_fwd<T, C_, FH_, FW_, KP_, 32, true>(mb, mo, p, grid, st) \
+		                           : launch_first_fwd<T, C_, FH_, FW_, KP_, 32>(mb, mo, p, grid, st));
 	FIRST_SHAPES(X)
 #undef X
 	set_error("conv_first: no kernel instance"); return CB200_ERR_UNSUPPORTED;
@@ -633,7 +688,12 @@ static int first_wgrad_typed(const cb200_conv_desc* d, const CUtensorMap& mdy, c
 	set_error("conv_first: no kernel instance"); return CB200_ERR_UNSUPPORTED;
 }
 
-int conv_first_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, void* y, cudaStream_t st) {
+// gn / gn_ws: the group-norm layer that follows and its FP64 workspace; *gn_fused = 1 when the epilogue has left the sums
+// there (conv_tc.cu: conv_forward_tc has the same contract).  CB200_FIRST_GN_STATS=0 or cb200_set_gn_epilogue_stats(0): off.
+extern int g_gn_epilogue_mode;
+int conv_first_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, void* y, cudaStream_t st,
+                       const cb200_norm_desc* gn, void* gn_ws, int* gn_fused) {
+	if (gn_fused) *gn_fused = 0;
 	const int kp = kp_of(d);
 	FirstParams p;
 	fill_params(d, x_raw, 128, p);
@@ -654,8 +714,17 @@ int conv_first_forward(const cb200_conv_desc* d, const cb200_conv_weights* w, co
 	int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
 	p.tiles_per_cta = ceil_div(p.num_tiles, grid);
 	grid = ceil_div(p.num_tiles, p.tiles_per_cta);
-	if (d->dtype == CB200_FP16) return first_fwd_typed<__half>(d, mb, mo, p, grid, st);
-	return first_fwd_typed<__nv_bfloat16>(d, mb, mo, p, grid, st);
+	static const bool no_gn = getenv("CB200_FIRST_GN_STATS") != nullptr && getenv("CB200_FIRST_GN_STATS")[0] == '0';
+	if (g_gn_epilogue_mode < 0) { const char* e = getenv("CB200_GN_EPILOGUE_STATS"); g_gn_epilogue_mode = e != nullptr && e[0] != '\0' ? atoi(e) : 1; }
+	if (gn_fused != nullptr && gn != nullptr && gn_ws != nullptr && !no_gn && g_gn_epilogue_mode != 0 && p.tma_store && bn == 32 && (p.tw * p.th) % 32 == 0 &&
+	    gn->c == d->out_c && gn->batch == d->batch && gn->h == d->out_h && gn->w == d->out_w && gn->group_size >= 4 && gn->group_size % 4 == 0) {
+		p.gn_ws = (double*)gn_ws; p.gn_groups = gn->nb_group;
+		for (int i = 0; i < 8; i++) p.gn_map |= (uint32_t)((4 * i) / gn->group_size) << (4 * i);
+		if (cudaMemsetAsync(gn_ws, 0, sizeof(double) * 2 * (size_t)d->batch * gn->nb_group, st) != cudaSuccess) { set_error("cudaMemsetAsync(group-norm sums) failed"); return CB200_ERR_CUDA; }
+	}
+	rc = d->dtype == CB200_FP16 ? first_fwd_typed<__half>(d, mb, mo, p, grid, st) : first_fwd_typed<__nv_bfloat16>(d, mb, mo, p, grid, st);
+	if (rc == CB200_OK && p.gn_ws != nullptr) *gn_fused = 1;
+	return rc;
 }
 
 int conv_first_wgrad(const cb200_conv_desc* d, const cb200_conv_weights* w, const void* x_raw, const void* dy, cudaStream_t st) {

@@ -267,6 +267,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 	const bool hook = mode == 1 && prev != nullptr && act != CB200_LINEAR;
 	// 0 <= leak <= 1, sat >= 0: z <= 0 ? z*leak : (z > sat ? hi : z) == min(max(z, z*leak), hi) value for value
 	const bool relu_minmax = leak >= 0.0f && leak <= 1.0f && sat >= 0.0f;
+	const float sat_c = sat - sat * leak;
 	// rows of a multiple of 16 channels leave in 32-byte stores (packets come in valid pairs: BN is a multiple of 16 too, and
 	// a strided output grid keeps rows 32-byte aligned since n_pad * 2 is a multiple of 32)
 	// Measured per layer shape (batch 128, same box A/B): rows of >= 128 channels gain (1x1 64 -> 128 data gradient at 112 px
@@ -366,15 +367,14 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
 					for (int j = 0; j < 8; j++) o[j] = 0.0f;
 				} else if (mode == 0) {
 					const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + v * 8), b1 = *reinterpret_cast<const float4*>(bs + c0 + v * 8 + 4);
-					o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+					// bias and activation on register pairs (sm100_ptx.cuh: FADD2, leaky_sat_f32x2): 28 instead of 48 issue
+					// slots per 8 values in the warps whose chain tcgen05.ld -> activation -> store bounds the thin layers
+					add_f32x2(o[0], o[1], b0.x, b0.y); add_f32x2(o[2], o[3], b0.z, b0.w);
+					add_f32x2(o[4], o[5], b1.x, b1.y); add_f32x2(o[6], o[7], b1.z, b1.w);
 					if (act == CB200_RELU) {
 						if (relu_minmax) {
 #pragma unroll
-							for (int j = 0; j < 8; j++) {
-								const float z = o[j];
-								const float hi = sat + (z - sat) * leak;
-								o[j] = fminf(fmaxf(z, z * leak), hi);
-							}
+							for (int j = 0; j < 8; j += 2) leaky_sat_f32x2(o[j], o[j + 1], leak, sat_c);
 						} else {
 #pragma unroll
 							for (int j = 0; j < 8; j++) {

@@ -261,4 +261,36 @@ __host__ __device__ inline uint32_t make_idesc_f16(int is_bf16, int m, int n, in
 	return d;
 }
 
+// ---------------------------------------------------------------- packed FP32 pairs (FADD2 / FMUL2 / FFMA2)
+// Two FP32 operations per issue slot on a 64-bit register pair (sm_100: add / mul / fma .f32x2, each half rounded like
+// the scalar instruction).  The epilogues that are bound by issue slots use them on neighbouring accumulator columns
+// (tcgen05.ld leaves those in a register pair) and for running sums.
+__device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1) {            // d += a
+	asm("{\n\t.reg .b64 a, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 d, {%0, %1};\n\tadd.rn.f32x2 d, a, d;\n\tmov.b64 {%0, %1}, d;\n\t}"
+	    : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void sq_acc_f32x2(float& d0, float& d1, float a0, float a1) {         // d += a * a
+	asm("{\n\t.reg .b64 a, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 d, {%0, %1};\n\tfma.rn.f32x2 d, a, a, d;\n\tmov.b64 {%0, %1}, d;\n\t}"
+	    : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void fma_f32x2(float& d0, float& d1, float a0, float a1, float s, float c) {   // d = a * s + c
+	asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmov.b64 c, {%5, %5};\n\tfma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+	    : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(s), "f"(c));
+}
+__device__ __forceinline__ void mul_f32x2(float& d0, float& d1, float a0, float a1, float s) {            // d = a * s
+	asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmul.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+	    : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(s));
+}
+// leaky ReLU with saturation on two neighbouring values: z <= 0 ? z * leak : (z > sat ? sat + (z - sat) * leak : z) as
+// min(max(z, z * leak), z * leak + sat_c), sat_c = sat - sat * leak, for 0 <= leak <= 1, sat >= 0: 3 issue slots per value
+// instead of 5.  Below the saturation the result is z or z * leak exactly as in the scalar form; above it the
+// rearranged branch can differ in the last FP32 bit (invisible after the rounding to 16 bit).
+__device__ __forceinline__ void leaky_sat_f32x2(float& z0, float& z1, float leak, float sat_c) {
+	float t0, t1, h0, h1;
+	mul_f32x2(t0, t1, z0, z1, leak);
+	fma_f32x2(h0, h1, z0, z1, leak, sat_c);
+	z0 = fminf(fmaxf(z0, t0), h0);
+	z1 = fminf(fmaxf(z1, t1), h1);
+}
+
 }}  // namespace cb200::ptx

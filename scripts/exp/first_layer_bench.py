@@ -30,3 +30,23 @@ tf = timeit(lambda: layer.forward(src))
 tw = timeit(lambda: layer.backward_weights(src, dy))
 out_gb = B * S * S * N * 2 / 1e9
 print("first layer B=%d: forward %.1f us (%.2f TB/s of output), weight gradient %.1f us (%.2f TB/s of dy)" % (B, tf, out_gb / tf * 1e6 / 1e3, tw, out_gb / tw * 1e6 / 1e3))
+
+# group-norm sums out of the forward epilogue (conv_first_fwd_kernel<GN>) against the statistics pass they replace:
+# the chain the network runs - forward, then group-norm + 2x2 max-pool
+gs = int(os.environ.get("FIRST_GS", "4"))
+norm = cabi.NormLayer(cabi.FP16, B, N, S, S, gs, 0, B)
+norm.set_params(np.ones((N + gs - 1) // gs, np.float32), np.zeros((N + gs - 1) // gs, np.float32))
+pool = cabi.PoolLayer(cabi.FP16, B, N, S, S, 2, 2, 0, cabi.POOL_MAX, length=B)
+flag = layer.forward_stats(src, norm)
+t_fs = timeit(lambda: layer.forward_stats(src, norm))
+t_np0 = timeit(lambda: norm.forward_pool(layer.y, pool, stats_ready=0))
+layer.forward_stats(src, norm)
+def chain1():
+    f = layer.forward_stats(src, norm)
+    norm.forward_pool(layer.y, pool, stats_ready=f)
+def chain0():
+    layer.forward(src)
+    norm.forward_pool(layer.y, pool, stats_ready=0)
+t_c1, t_c0 = timeit(chain1), timeit(chain0)
+print("first layer + group-norm(gs %d) + max-pool: forward %.1f us, forward with the sums %.1f us (fused=%d); norm+pool with its statistics pass %.1f us;"
+      " chain %.1f us -> %.1f us" % (gs, tf, t_fs, flag, t_np0, t_c0, t_c1))

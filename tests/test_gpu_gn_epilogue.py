@@ -103,6 +103,97 @@ def test_epilogue_statistics_equal_the_statistics_pass(cabi, shape, dtype_name):
         assert (outs[1][1] != outs[0][1]).mean() < 2e-3
 
 
+# first layer straight from the dataset batch (conv_first.cu): (batch, in_c, size, out_c, filter, pad, group size, length, flag)
+FIRST_SHAPES = [
+    (3, 3, 32, 32, 3, 1, 4, 3, 1),        # the Darknet19 first layer in small: 32 x 4 tiles of one sample, group size 4
+    (3, 3, 40, 32, 3, 1, 8, 2, 1),        # 16 x 8 tiles, partial in both directions (rows outside the map must not count), a dead sample
+    (3, 1, 32, 32, 3, 1, 16, 3, 1),       # grey input (KP = 16), groups of 16
+    (2, 3, 32, 32, 3, 1, 32, 2, 1),       # one group; tiles of 32 x 2 pixels of TWO samples (the headline's tile is 64 x 1 x 2)
+    (4, 3, 64, 32, 3, 1, 4, 3, 1),        # 64 x 1 x 2 tiles, a dead sample sharing tiles with a live one
+    (3, 1, 28, 32, 5, 2, 4, 3, 1),        # 5x5 on one channel, partial tiles
+    (3, 3, 32, 24, 3, 1, 8, 3, 0),        # 24 filters: rows narrower than the staging tile (plain stores), refused
+    (2, 2, 32, 64, 3, 1, 8, 2, 0),        # 64 filters (BN = 64): refused
+    (130, 3, 4, 32, 3, 1, 4, 130, 0),     # 16 pixels per sample: a warp's rows span two samples, refused
+    (3, 3, 32, 32, 3, 1, 2, 3, 0),        # group size 2 (the sums are kept per 4 columns): refused
+]
+
+
+@pytest.mark.parametrize("dtype_name", ["FP16", "BF16"])
+@pytest.mark.parametrize("shape", FIRST_SHAPES)
+def test_first_layer_epilogue_statistics(cabi, shape, dtype_name):
+    """conv_first_fwd_kernel<GN>: the sums of the first layer's output (the largest statistics pass of Darknet19) from
+    its epilogue.  They are taken from the activated FP32 values BEFORE the rounding to 16 bit, the statistics pass reads
+    the rounded tensor.  Two checks: (i) tight - inputs and filters are representable in the 16-bit type, so every product
+    is exact and the float64 oracle of the UNROUNDED layer output must give the same mean / variance to FP32 accumulation
+    order (1e-5); (ii) against the statistics pass they differ by the mean rounding error of a group (~ulp / sqrt(n): 2e-4
+    FP16, 2e-3 BF16 for the 4096 values of the smallest group here; 3e-7 for the headline's 800k), the normalised output
+    by one unit of the storage type; the convolution output itself is bit-identical."""
+    import ctypes
+    B, C, S, N, f, pad, gs, length, want_flag = shape
+    dtype = getattr(cabi, dtype_name)
+    L = cabi.lib()
+    rng = np.random.default_rng(abs(hash(shape)) % 2**31)
+    def q16(a):      # representable in the storage type: the casts on the way to the device are exact
+        a = np.ascontiguousarray(a, np.float32)
+        return a.astype(np.float16).astype(np.float32) if dtype_name == "FP16" else (a.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+    x = np.empty((B, C * S * S + 1), np.float32)
+    x[:, :-1] = q16(rng.standard_normal((B, C * S * S)) * 0.7)
+    x[:, -1] = 0.125
+    w = q16(rng.standard_normal((N, f * f * C + 1)) * (1.5 / np.sqrt(f * f * C)))
+    conv = cabi.ConvLayer(dtype, B, C, S, S, N, f, 1, pad, bias_value=0.125, act=cabi.activ(cabi.RELU), length=length)
+    conv.d.input_is_patches = 2
+    assert L.cb200_conv_first_direct(ctypes.byref(conv.d)) == 1
+    conv.set_weights(w)
+    xt = np.empty(x.size, np.uint16)
+    cabi.check(L.cb200_host_cast_from_f32(xt.ctypes.data, dtype, x.ctypes.data, x.size))
+    src = cabi.DevBuf.from_numpy(xt)
+    So = S + 2 * pad - f + 1
+    G = (N + gs - 1) // gs
+    gamma = (1 + 0.2 * rng.standard_normal(G)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(G)).astype(np.float32)
+
+    n1 = cabi.NormLayer(dtype, B, N, So, So, gs, 0, length)
+    n1.set_params(gamma, beta)
+    y_conv1 = cabi.download_act(conv.forward(src), dtype, B, N, So, So)
+    y1 = cabi.download_act(n1.forward(conv.y), dtype, B, N, So, So)
+    mean1, var1 = n1.stats()[:2]
+
+    n2 = cabi.NormLayer(dtype, B, N, So, So, gs, 0, length)
+    n2.set_params(gamma, beta)
+    done = conv.forward_stats(src, n2)
+    assert L.cb200_last_conv_impl() == b"tcgen05"
+    assert done == want_flag
+    y_conv2 = cabi.download_act(conv.y, dtype, B, N, So, So)
+    assert np.array_equal(y_conv2, y_conv1)
+    y2 = cabi.download_act(n2.forward(conv.y, stats_ready=done), dtype, B, N, So, So)
+    mean2, var2 = n2.stats()[:2]
+    tol = {"FP16": 2e-4, "BF16": 2e-3}[dtype_name] if done else 1e-6
+    assert rel_err(mean2, mean1) < tol and rel_err(var2, var1) < tol, (rel_err(mean2, mean1), rel_err(var2, var1))
+    if done:
+        pre, _ = co.conv_forward(x, w, True, B, C, S, S, f, 1, pad, 0.125)
+        _, mean_u, var_u = co.group_norm_forward(co.relu_forward(pre, length), gamma, beta, gs, 0, length)
+        e_m, e_v = rel_err(mean2[:length], mean_u[:length]), rel_err(var2[:length], var_u[:length])
+        assert e_m < 1e-5 and e_v < 1e-5, (e_m, e_v)
+    ulp = {"FP16": 2.0 ** -10, "BF16": 2.0 ** -7}[dtype_name]
+    assert rel_err(y2, y1) <= ulp
+    ref_y, ref_mean, ref_var = co.group_norm_forward(y_conv2, gamma, beta, gs, 0, length)
+    assert rel_err(mean2[:length], ref_mean[:length]) < max(tol, 1e-4) and rel_err(var2[:length], ref_var[:length]) < max(tol, 1e-4)
+    assert rel_err(y2, ref_y) < 2e-2
+    if length < B:
+        assert not y2[:, length:].any()
+
+    # fused with the max-pool, as the network runs it
+    outs = []
+    for use in (0, 1):
+        n3 = cabi.NormLayer(dtype, B, N, So, So, gs, 0, length)
+        n3.set_params(gamma, beta)
+        p3 = cabi.PoolLayer(dtype, B, N, So, So, 2, 2, 0, cabi.POOL_MAX, length=length)
+        flag = conv.forward_stats(src, n3) if use else (conv.forward(src), 0)[1]
+        outs.append((cabi.download_act(n3.forward_pool(conv.y, p3, stats_ready=flag), dtype, B, N, So // 2, So // 2), p3.map_ref_layout()))
+    assert rel_err(outs[1][0], outs[0][0]) <= ulp
+    assert (outs[1][1] != outs[0][1]).mean() < 2e-3
+
+
 def test_network_uses_the_epilogue_statistics(cabi):
     """host library: a conv -> group-norm (-> max-pool) chain takes its statistics from the epilogue (one statistics
     launch less per pair), results unchanged against the run with the switch off"""
