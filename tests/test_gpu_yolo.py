@@ -240,9 +240,15 @@ def test_yolo_network_training_matches_live_reference(cnn, mode):
     cnn.set_iter(1, train_size=spec["batch"], network=0)
     S = 32.0 if mode == "FP16C_FP32A" else 1.0
     cnn.set_TC_scale_factor(S, network=0)
+    # a SEEDED Xavier-normal draw written into the reference (it seeds rand() with the time): with its own draw every run
+    # is another network, and in 16 bit one box <-> target association that flips at step 1 (counted below, allowed) moves
+    # the step-2 output of this tiny detector by tens of percent - the test would pass or fail by the draw
+    rng = np.random.default_rng(2024)
     for i, k in enumerate(kinds):
         if k == "conv":
-            cnn.set_layer_weights(i, ref.weights_view(i))
+            w = ref.weights_view(i)
+            w[...] = (rng.standard_normal(w.shape) * np.sqrt(2.0 / (w.shape[0] + w.shape[1]))).astype(np.float32)
+            cnn.set_layer_weights(i, w)
     last = len(kinds) - 1
     tol = TOL[mode] * 3
     flips = 0
