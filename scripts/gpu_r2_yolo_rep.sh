@@ -1,5 +1,5 @@
 #!/bin/bash
-# the live-reference YOLO training test with its seeded draw, twice (must be the same case both times)
+# live-reference tests with seeded draws: must pass, twice the same
 for i in 1 2; do
-  timeout 100 python -m pytest tests/test_gpu_yolo.py -m gpu -q --tb=short -k "yolo_network_training_matches_live_reference" 2>&1 | tail -6 | cut -c1-300
+  timeout 150 python -m pytest tests/test_gpu_generic_geometry.py tests/test_gpu_network.py tests/test_gpu_yolo.py -m gpu -q --tb=short -k "live_reference or reference_train_api" 2>&1 | tail -8 | cut -c1-300
 done
